@@ -1,0 +1,201 @@
+/*
+ * matx_b200.h — C ABI of libmatx_b200.so, the B200 (sm_100a) engine behind the MatX operator API.
+ *
+ * This is the drop-in boundary.  Everything above it (the MatX expression templates,
+ * `(out = sum(a*b+c, {1})).run(exec)`) stays the reference's own code; the header shim
+ * `include/matx_b200/executor.h` lowers a statement to the plain-C descriptors declared here and
+ * calls one of the entry points below.  No C++ types, no torch types, no exceptions cross this line.
+ *
+ * Reference interfaces each entry point replaces (paths relative to the reference tree):
+ *   mxb_elementwise  <- cudaExecutor::Exec                    include/matx/executors/cuda.h:84-230
+ *                       + matxOpT{0..4,D}Kernel               include/matx/executors/kernel.h:41-223
+ *   mxb_reduce       <- sum_impl / mean_impl / var_impl / stdd_impl / max_impl / min_impl / argmax_impl /
+ *                       argmin_impl / any_impl / all_impl / prod_impl (cudaExecutor overloads)
+ *                                                             include/matx/transforms/reduce.h:266-290,646-655,
+ *                                                             712-722,786-795,856-869,934-943,1003-1017,
+ *                                                             1170-1178,1243-1251,1406-1444,1474-1479
+ *                       + matxCubPlan_t::Exec{Sum,Min,Max,Reduce,ArgReduce}
+ *                                                             include/matx/transforms/cub.h:647-894,1281-1328
+ *   mxb_create / mxb_destroy / mxb_set_stream
+ *                    <- cudaExecutor ctor / getStream         include/matx/executors/cuda.h:60-82
+ *   mxb_sync         <- CudaExecutorBase::sync                include/matx/executors/cuda_executor_common.h:137
+ *
+ * Conventions
+ *   - every call is asynchronous and ordered on the handle's stream (like the reference);
+ *   - every call returns an mxb_status_t; mxb_last_error() gives the text for the calling thread;
+ *   - sizes, strides and indices are int64 end to end (the reference's CUB path is limited to int);
+ *   - strides are in ELEMENTS, stride 0 = broadcast (MatX clone / scalar / lower-rank operand);
+ *   - there is no CPU fallback: without a CUDA device every compute entry point returns
+ *     MXB_ERR_NO_DEVICE.
+ */
+#ifndef MATX_B200_H
+#define MATX_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MXB_VERSION_MAJOR 0
+#define MXB_VERSION_MINOR 1
+
+#define MXB_MAX_RANK   8   /* rank of an expression's index space */
+#define MXB_MAX_LEAVES 12  /* distinct tensor views in one expression */
+#define MXB_MAX_NODES  96  /* SSA nodes in one expression */
+#define MXB_MAX_CONSTS 24  /* scalar constants in one expression */
+
+typedef enum {
+  MXB_OK = 0,
+  MXB_ERR_INVALID = 1,       /* bad argument / malformed program     -> matxInvalidParameter */
+  MXB_ERR_NOT_SUPPORTED = 2, /* legal MatX, not lowered by this path -> matxNotSupported (shim falls back) */
+  MXB_ERR_CUDA = 3,          /* CUDA runtime error                   -> matxCudaError */
+  MXB_ERR_NO_DEVICE = 4,     /* no CUDA device visible */
+  MXB_ERR_JIT = 5,           /* NVRTC missing or generated kernel failed to build */
+  MXB_ERR_SIZE = 6           /* output shape does not match          -> matxInvalidSize */
+} mxb_status_t;
+
+/* element types (reference: value_type of tensor_t; core/half.h for the 16-bit floats) */
+typedef enum {
+  MXB_F32 = 0,
+  MXB_F64 = 1,
+  MXB_BF16 = 2,
+  MXB_F16 = 3,
+  MXB_C64 = 4,  /* cuda::std::complex<float>, interleaved re,im */
+  MXB_I32 = 5,
+  MXB_I64 = 6,  /* matx::index_t */
+  MXB_U8 = 7,   /* bool / uint8 */
+  MXB_DTYPE_COUNT
+} mxb_dtype_t;
+
+/* reductions (reference: transforms/reduce.h) */
+typedef enum {
+  MXB_RED_SUM = 0,
+  MXB_RED_MEAN = 1,
+  MXB_RED_VAR = 2,   /* two-pass arithmetic, divisor N - ddof */
+  MXB_RED_STDD = 3,
+  MXB_RED_MAX = 4,
+  MXB_RED_MIN = 5,
+  MXB_RED_ARGMAX = 6, /* value + absolute flat index, lowest index wins ties */
+  MXB_RED_ARGMIN = 7,
+  MXB_RED_ANY = 8,
+  MXB_RED_ALL = 9,
+  MXB_RED_PROD = 10,
+  MXB_RED_COUNT
+} mxb_reduce_op_t;
+
+/* node opcodes of the expression program (reference functors: operators/scalar_ops.h:434-503) */
+typedef enum {
+  MXB_OP_LEAF = 0,  /* src[0] = leaf index */
+  MXB_OP_CONST = 1, /* src[0] = constant index */
+  /* binary */
+  MXB_OP_ADD = 10, MXB_OP_SUB, MXB_OP_MUL, MXB_OP_DIV, MXB_OP_MOD, MXB_OP_POW, MXB_OP_MAX, MXB_OP_MIN,
+  MXB_OP_LT, MXB_OP_GT, MXB_OP_LE, MXB_OP_GE, MXB_OP_EQ, MXB_OP_NE, MXB_OP_AND, MXB_OP_OR, MXB_OP_ATAN2,
+  /* unary */
+  MXB_OP_NEG = 40, MXB_OP_SQRT, MXB_OP_RSQRT, MXB_OP_EXP, MXB_OP_LOG, MXB_OP_LOG2, MXB_OP_LOG10, MXB_OP_ABS,
+  MXB_OP_ABS2, MXB_OP_CONJ, MXB_OP_REAL, MXB_OP_IMAG, MXB_OP_SIN, MXB_OP_COS, MXB_OP_TAN, MXB_OP_TANH,
+  MXB_OP_NORMCDF, MXB_OP_NOT, MXB_OP_ISNAN, MXB_OP_ISINF, MXB_OP_FLOOR, MXB_OP_CEIL, MXB_OP_ROUND,
+  MXB_OP_SINH, MXB_OP_COSH, MXB_OP_ASIN, MXB_OP_ACOS, MXB_OP_ATAN, MXB_OP_EXPJ, MXB_OP_CSQRT_UNUSED,
+  /* casts: src[0] = value, result dtype = aux */
+  MXB_OP_CAST = 80
+} mxb_opcode_t;
+
+/* one SSA node: value id == its position in nodes[] */
+typedef struct {
+  int32_t opcode;
+  int32_t src[2]; /* operand value ids (or leaf / constant index) */
+  int32_t aux;    /* MXB_OP_CAST: target mxb_dtype_t */
+} mxb_node_t;
+
+/* a tensor view inside an expression: pointer + strides over the EXPRESSION's dims
+ * (reference: tensor_impl_t = ldata_ + tensor_desc_t, core/tensor_impl.h, core/tensor_desc.h:221-233).
+ * Permute / clone / slice / lower-rank broadcast are all expressed by the strides. */
+typedef struct {
+  const void *data; /* device pointer to element (0,0,...,0) of the view */
+  int32_t dtype;    /* mxb_dtype_t */
+  int32_t _pad;
+  int64_t stride[MXB_MAX_RANK];
+} mxb_leaf_t;
+
+typedef struct {
+  double re, im;  /* im used only for MXB_C64 */
+  int32_t dtype;  /* mxb_dtype_t the literal has in the C++ expression (0.5f -> F32) */
+  int32_t _pad;
+} mxb_const_t;
+
+/* expression program: SSA nodes over an N-D index space */
+typedef struct {
+  int32_t rank; /* 0 = scalar */
+  int32_t n_nodes;
+  int32_t n_leaves;
+  int32_t n_consts;
+  int32_t root; /* value id the expression evaluates to */
+  int32_t _pad;
+  int64_t size[MXB_MAX_RANK];
+  mxb_node_t nodes[MXB_MAX_NODES];
+  mxb_leaf_t leaves[MXB_MAX_LEAVES];
+  mxb_const_t consts[MXB_MAX_CONSTS];
+} mxb_expr_t;
+
+/* destination view (reference: the LHS tensor of set<T,Op>, operators/set.h:121-553) */
+typedef struct {
+  void *data;
+  int32_t dtype;
+  int32_t rank;
+  int64_t size[MXB_MAX_RANK];
+  int64_t stride[MXB_MAX_RANK];
+} mxb_out_t;
+
+typedef struct mxb_context *mxb_handle_t;
+
+/* ---- lifetime ------------------------------------------------------------------------------- */
+/* Creates a handle bound to the calling thread's current device and to `stream` (a cudaStream_t,
+ * NULL = legacy default stream).  The handle owns the grid-combine scratch used by its launches,
+ * so one handle must not be used from two host threads at once (use one handle per executor). */
+int mxb_create(mxb_handle_t *out_handle, void *stream);
+int mxb_destroy(mxb_handle_t h);
+int mxb_set_stream(mxb_handle_t h, void *stream);
+int mxb_sync(mxb_handle_t h);
+
+/* ---- the hot path --------------------------------------------------------------------------- */
+/* out(idx...) = expr(idx...)   — one fused kernel, each distinct leaf read once. */
+int mxb_elementwise(mxb_handle_t h, const mxb_expr_t *expr, const mxb_out_t *out);
+
+/* Reduce the trailing `n_reduce_dims` dims of `expr` (the caller has already moved the reduced dims
+ * innermost, as the reference's sum(x, dims) does through permute: operators/sum.h:373-405).
+ * `out` has rank expr->rank - n_reduce_dims.  `idx_out` (MXB_I64) is required for ARGMAX/ARGMIN and
+ * receives b * R + r, the absolute flat offset in the collapsed input (cub.h:1289-1326 convention),
+ * R = product of the reduced sizes.  `ddof` is used by VAR/STDD only.
+ * One launch per call (VAR/STDD: one launch when a reduced row fits in shared memory). */
+int mxb_reduce(mxb_handle_t h, int reduce_op, const mxb_expr_t *expr, int n_reduce_dims,
+               const mxb_out_t *out, const mxb_out_t *idx_out, int ddof);
+
+/* ---- multi-GPU (no counterpart in the reference) -------------------------------- */
+/* Slab-sharded full-tensor reductions: each rank reduces its slab with mxb_reduce_partial into a
+ * 32-byte device record, the host exchanges the records with ONE collective (NCCL all-gather of
+ * world*32 bytes), and mxb_reduce_finalize folds them in rank order (deterministic; lowest global
+ * index wins ties).  `slab_offset` is the global flat index of the slab's first element and
+ * `global_count` the total element count (MEAN/VAR divisors). */
+#define MXB_PARTIAL_BYTES 32
+int mxb_reduce_partial(mxb_handle_t h, int reduce_op, const mxb_expr_t *expr, int64_t slab_offset,
+                       void *partial_record);
+int mxb_reduce_finalize(mxb_handle_t h, int reduce_op, int32_t value_dtype, const void *gathered_records,
+                        int world, int64_t global_count, int ddof, const mxb_out_t *out,
+                        const mxb_out_t *idx_out);
+
+/* ---- introspection ---------------------------------------------------------------------------- */
+int mxb_version(void);                /* major*1000 + minor */
+const char *mxb_last_error(void);     /* thread-local text of the last non-OK status */
+int mxb_device_count(void);           /* 0 when no CUDA device / driver */
+/* Name of the kernel family the last mxb_elementwise / mxb_reduce on this handle launched
+ * (e.g. "reduce_inner<f32,sum,aot:fma3>"), and how many kernels the handle has launched. */
+const char *mxb_last_kernel(mxb_handle_t h);
+int64_t mxb_launch_count(mxb_handle_t h);
+/* 1 if (expr, op) is served by an ahead-of-time kernel, 0 if it would be JIT-compiled. */
+int mxb_is_aot(const mxb_expr_t *expr, int reduce_op_or_minus1);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MATX_B200_H */

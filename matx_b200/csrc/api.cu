@@ -1,0 +1,827 @@
+// api.cu — the extern "C" boundary of libmatx_b200.so (declared in include/matx_b200.h): argument
+// checking, view collapsing, kernel-family selection, workspace ownership and the launches.
+//
+// Host-side counterpart of, in the reference:
+//   cudaExecutor::Exec + find_best_launch_params + get_grid_dims
+//       (executors/cuda.h:84-230, executors/cuda_executor_common.h:325-493, core/get_grid_dims.h:45-174)
+//   the *_impl(cudaExecutor) reductions and matxCubPlan_t
+//       (transforms/reduce.h, transforms/cub.h:119-298,647-894,1281-1328)
+//   ReduceInput / lcollapse / rcollapse (core/reduce_utils.h:45-102, operators/collapse.h)
+// Differences by design: one launch per statement (no size-query call, no cudaMallocAsync per call, no
+// second "single tile" launch, no separate scale kernel for mean), int64 sizes, deterministic results.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "mxb_device.cuh"
+#include "mxb_internal.h"
+
+using namespace mxbh;
+using mxb::EwParams;
+using mxb::KMAXD;
+using mxb::RedParams;
+
+// ---------------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------------
+struct mxb_context {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int sm_count = 148;
+  int max_smem_optin = 227 * 1024;
+  void *ws = nullptr;
+  size_t ws_bytes = 0;
+  unsigned *tickets = nullptr;
+  size_t n_tickets = 0;
+  void *tmp = nullptr;  // mean scratch of the two-launch variance
+  size_t tmp_bytes = 0;
+  std::string last_kernel;
+  int64_t launches = 0;
+};
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int st, const std::string &m) { g_err = m; return st; }
+int cuda_fail(cudaError_t e, const char *what) {
+  g_err = std::string(what) + ": " + cudaGetErrorString(e);
+  return MXB_ERR_CUDA;
+}
+#define MXB_CUDA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_fail(e_, #call); } while (0)
+
+int ensure_ws(mxb_context *h, size_t bytes, size_t tickets) {
+  if (bytes > h->ws_bytes) {
+    if (h->ws) MXB_CUDA(cudaFreeAsync(h->ws, h->stream));
+    const size_t nb = std::max<size_t>(bytes, 64 * 1024);
+    MXB_CUDA(cudaMallocAsync(&h->ws, nb, h->stream));
+    h->ws_bytes = nb;
+  }
+  if (tickets > h->n_tickets) {
+    if (h->tickets) MXB_CUDA(cudaFreeAsync(h->tickets, h->stream));
+    const size_t nt = std::max<size_t>(tickets, 1024);
+    MXB_CUDA(cudaMallocAsync((void **)&h->tickets, nt * sizeof(unsigned), h->stream));
+    // zeroed once: the grid stage leaves every ticket at zero again (atomicInc wrap-around)
+    MXB_CUDA(cudaMemsetAsync(h->tickets, 0, nt * sizeof(unsigned), h->stream));
+    h->n_tickets = nt;
+  }
+  return MXB_OK;
+}
+int ensure_tmp(mxb_context *h, size_t bytes) {
+  if (bytes > h->tmp_bytes) {
+    if (h->tmp) MXB_CUDA(cudaFreeAsync(h->tmp, h->stream));
+    const size_t nb = std::max<size_t>(bytes, 64 * 1024);
+    MXB_CUDA(cudaMallocAsync(&h->tmp, nb, h->stream));
+    h->tmp_bytes = nb;
+  }
+  return MXB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// view collapsing: drop size-1 dims, merge neighbours that every leaf (and the outputs) walk contiguously
+// ---------------------------------------------------------------------------------------------------
+struct Group {
+  int n = 0;
+  int64_t size[MXB_MAX_RANK];
+  int64_t ls[MXB_MAX_LEAVES][MXB_MAX_RANK];  // leaf strides
+  int64_t os[MXB_MAX_RANK];                  // out strides (0 when unused)
+  int64_t is[MXB_MAX_RANK];                  // index-out strides
+};
+
+void collapse(Group &g, int nleaf) {
+  // 1. drop size-1 dims
+  int m = 0;
+  for (int d = 0; d < g.n; ++d) {
+    if (g.size[d] == 1) continue;
+    g.size[m] = g.size[d];
+    for (int k = 0; k < nleaf; ++k) g.ls[k][m] = g.ls[k][d];
+    g.os[m] = g.os[d];
+    g.is[m] = g.is[d];
+    ++m;
+  }
+  g.n = m;
+  // 2. merge (d, d+1) when stride[d] == stride[d+1] * size[d+1] everywhere
+  int d = 0;
+  while (d + 1 < g.n) {
+    bool ok = (g.os[d] == g.os[d + 1] * g.size[d + 1]) && (g.is[d] == g.is[d + 1] * g.size[d + 1]);
+    for (int k = 0; ok && k < nleaf; ++k) ok = (g.ls[k][d] == g.ls[k][d + 1] * g.size[d + 1]);
+    if (!ok) { ++d; continue; }
+    g.size[d] *= g.size[d + 1];
+    for (int k = 0; k < nleaf; ++k) g.ls[k][d] = g.ls[k][d + 1];
+    g.os[d] = g.os[d + 1];
+    g.is[d] = g.is[d + 1];
+    for (int j = d + 1; j + 1 < g.n; ++j) {
+      g.size[j] = g.size[j + 1];
+      for (int k = 0; k < nleaf; ++k) g.ls[k][j] = g.ls[k][j + 1];
+      g.os[j] = g.os[j + 1];
+      g.is[j] = g.is[j + 1];
+    }
+    --g.n;
+  }
+  if (g.n == 0) {
+    g.n = 1;
+    g.size[0] = 1;
+    for (int k = 0; k < nleaf; ++k) g.ls[k][0] = 0;
+    g.os[0] = 0;
+    g.is[0] = 0;
+  }
+}
+
+void fill_consts(const mxb_expr_t &e, mxb::ConstDev &c) {
+  memset(&c, 0, sizeof c);
+  for (int k = 0; k < e.n_consts; ++k) {
+    c.dre[k] = e.consts[k].re;
+    c.dim[k] = e.consts[k].im;
+    c.fre[k] = (float)e.consts[k].re;
+    c.fim[k] = (float)e.consts[k].im;
+    c.ire[k] = (long long)e.consts[k].re;
+  }
+}
+
+bool aligned_to(const void *p, int64_t bytes) { return ((uintptr_t)p % (uintptr_t)bytes) == 0; }
+
+int acc_bytes(int op, int value_dtype) {
+  switch (op) {
+    case MXB_RED_ARGMAX: case MXB_RED_ARGMIN: return 16;
+    case MXB_RED_ANY: case MXB_RED_ALL: return 4;
+    default: return dtype_bytes(value_dtype);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// kernel lookup (AOT table, then NVRTC) and launch
+// ---------------------------------------------------------------------------------------------------
+struct Kernel { const void *fn = nullptr; bool jit = false; std::string key; };
+
+int get_kernel(const ExprInfo &info, const KernelSpec &spec, Kernel *k) {
+  k->key = kernel_key(info, spec);
+  k->fn = lookup_aot(k->key);
+  k->jit = false;
+  if (k->fn) return MXB_OK;
+  if (getenv("MXB_DISABLE_JIT")) return fail(MXB_ERR_JIT, "no ahead-of-time kernel for " + k->key + " and MXB_DISABLE_JIT is set");
+  const std::string sym = kernel_symbol(k->key);
+  std::string wrap, err;
+  int st = kernel_wrapper_src(info, spec, sym, &wrap, &err);
+  if (st != MXB_OK) return fail(st, err);
+  const std::string src = "#include \"mxb_device.cuh\"\n" + info.src + "\n" + wrap;
+  k->fn = jit_get_kernel(k->key, sym, src, &err);
+  if (!k->fn) return fail(MXB_ERR_JIT, "JIT of " + k->key + " failed: " + err);
+  k->jit = true;
+  return MXB_OK;
+}
+
+template <class P>
+int launch(mxb_context *h, const Kernel &k, unsigned grid, unsigned block, unsigned smem, P &params) {
+  if (grid == 0) return MXB_OK;
+  if (k.jit) {
+    std::string err;
+    int st = jit_launch(k.fn, grid, block, smem, (void *)h->stream, (void *)&params, &err);
+    if (st != MXB_OK) return fail(st, err);
+  } else {
+    if (smem > 48 * 1024) MXB_CUDA(cudaFuncSetAttribute(k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    void *args[] = {(void *)&params};
+    MXB_CUDA(cudaLaunchKernel(k.fn, dim3(grid), dim3(block), args, smem, h->stream));
+  }
+  h->launches++;
+  h->last_kernel = k.key + (k.jit ? "|jit" : "|aot");
+  return MXB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// reductions
+// ---------------------------------------------------------------------------------------------------
+struct RedOptions {
+  bool post_div = false;
+  double post_scale = 1.0;
+  bool post_sqrt = false;
+  bool raw_partial = false;
+  int64_t idx_base = 0;
+};
+
+int check_expr_shape(const mxb_expr_t *e) {
+  if (!e) return fail(MXB_ERR_INVALID, "null expression");
+  if (e->rank < 0 || e->rank > MXB_MAX_RANK) return fail(MXB_ERR_INVALID, "expression rank out of range");
+  for (int d = 0; d < e->rank; ++d)
+    if (e->size[d] < 0) return fail(MXB_ERR_INVALID, "negative size");
+  for (int k = 0; k < e->n_leaves && k < MXB_MAX_LEAVES; ++k)
+    if (!e->leaves[k].data) return fail(MXB_ERR_INVALID, "leaf " + std::to_string(k) + " has a null data pointer");
+  return MXB_OK;
+}
+
+// kernel op actually launched for a public op
+int kernel_op(int op) {
+  switch (op) {
+    case MXB_RED_MEAN: return MXB_RED_SUM;
+    case MXB_RED_STDD: return MXB_RED_VAR;
+    default: return op;
+  }
+}
+
+// One reduction launch (everything except the variance family).  `e` is canonical.
+int reduce_launch(mxb_context *h, int kop, const mxb_expr_t &e, const ExprInfo &info, int n_reduce, const mxb_out_t *out,
+                  const mxb_out_t *idx_out, const RedOptions &opt, bool var_smem = false) {
+  const int nbd = e.rank - n_reduce;
+  Group gb, gr;
+  gb.n = nbd;
+  gr.n = n_reduce;
+  for (int d = 0; d < nbd; ++d) {
+    gb.size[d] = e.size[d];
+    for (int k = 0; k < e.n_leaves; ++k) gb.ls[k][d] = e.leaves[k].stride[d];
+    gb.os[d] = (out && !opt.raw_partial) ? out->stride[d] : 0;
+    gb.is[d] = idx_out ? idx_out->stride[d] : 0;
+  }
+  for (int d = 0; d < n_reduce; ++d) {
+    gr.size[d] = e.size[nbd + d];
+    for (int k = 0; k < e.n_leaves; ++k) gr.ls[k][d] = e.leaves[k].stride[nbd + d];
+    gr.os[d] = 0;
+    gr.is[d] = 0;
+  }
+  // size-1 batch dims carry no information for the output either
+  collapse(gb, e.n_leaves);
+  collapse(gr, e.n_leaves);
+  if (gb.n > KMAXD || gr.n > KMAXD)
+    return fail(MXB_ERR_NOT_SUPPORTED, "view does not collapse to <= 4 batch and <= 4 reduce dims");
+
+  int64_t B = 1, R = 1;
+  for (int d = 0; d < gb.n; ++d) B *= gb.size[d];
+  for (int d = 0; d < gr.n; ++d) R *= gr.size[d];
+  if (B == 0) return MXB_OK;
+  if (R == 0) return fail(MXB_ERR_INVALID, "reduction over zero elements");
+
+  const int out_dtype = opt.raw_partial ? info.value_dtype : out->dtype;
+  const int vmax = policy_vmax(info);
+  const int nl = e.n_leaves;
+
+  // ---- can the innermost reduce dim be the vector dim? ----
+  auto inner_ok = [&](int V) {
+    bool any_unit = false;
+    for (int k = 0; k < nl; ++k) {
+      const int64_t in = gr.ls[k][gr.n - 1];
+      if (in != 0 && in != 1) return false;
+      if (in == 0) continue;
+      any_unit = true;
+      const int64_t bytes = (int64_t)V * dtype_bytes(e.leaves[k].dtype);
+      if (!aligned_to(e.leaves[k].data, bytes)) return false;
+      for (int d = 0; d < gb.n; ++d) if (gb.ls[k][d] % V) return false;
+      for (int d = 0; d + 1 < gr.n; ++d) if (gr.ls[k][d] % V) return false;
+    }
+    return any_unit;
+  };
+  // ---- or a batch dim (rotated last)? ----
+  auto outer_dim = [&](int V) {
+    for (int c = gb.n - 1; c >= 0; --c) {
+      if (gb.size[c] < 2) continue;
+      bool any_unit = false, ok = true;
+      for (int k = 0; ok && k < nl; ++k) {
+        const int64_t in = gb.ls[k][c];
+        if (in != 0 && in != 1) { ok = false; break; }
+        if (in == 0) continue;
+        any_unit = true;
+        const int64_t bytes = (int64_t)V * dtype_bytes(e.leaves[k].dtype);
+        if (!aligned_to(e.leaves[k].data, bytes)) ok = false;
+        for (int d = 0; ok && d < gb.n; ++d) if (d != c && gb.ls[k][d] % V) ok = false;
+        for (int d = 0; ok && d < gr.n; ++d) if (gr.ls[k][d] % V) ok = false;
+      }
+      if (ok && any_unit) return c;
+    }
+    return -1;
+  };
+
+  KernelSpec spec;
+  spec.op = kop;
+  spec.out_dtype = out_dtype;
+  int rot = -1;
+  if (var_smem) {
+    spec.family = FAM_VAR_SMEM;
+    spec.V = (vmax > 1 && inner_ok(vmax)) ? vmax : 1;
+  } else if (vmax > 1 && inner_ok(vmax)) {
+    spec.family = FAM_RED_INNER;
+    spec.V = vmax;
+  } else if (vmax > 1 && (rot = outer_dim(vmax)) >= 0) {
+    spec.family = FAM_RED_OUTER;
+    spec.V = vmax;
+  } else if (inner_ok(1)) {
+    spec.family = FAM_RED_INNER;
+    spec.V = 1;
+  } else if ((rot = outer_dim(1)) >= 0) {
+    spec.family = FAM_RED_OUTER;
+    spec.V = 1;
+  } else {
+    spec.family = FAM_RED_INNER;  // V == 1 walks any strides
+    spec.V = 1;
+  }
+  spec.U = policy_unroll(info, spec.V, spec.family);
+
+  RedParams p;
+  memset(&p, 0, sizeof p);
+  p.nb = gb.n;
+  p.nr = gr.n;
+  p.B = B;
+  p.R = R;
+  p.nleaf = nl;
+  p.splits = 1;
+  // original row-major weights of the batch dims
+  int64_t bflat[MXB_MAX_RANK];
+  {
+    int64_t w = 1;
+    for (int d = gb.n - 1; d >= 0; --d) { bflat[d] = w; w *= gb.size[d]; }
+  }
+  // batch dim order on the device (rot moved last for the outer family)
+  int order[MXB_MAX_RANK];
+  {
+    int m = 0;
+    for (int d = 0; d < gb.n; ++d) if (d != rot) order[m++] = d;
+    if (rot >= 0) order[m++] = rot;
+  }
+  for (int i = 0; i < gb.n; ++i) {
+    const int d = order[i];
+    p.bsz[i] = gb.size[d];
+    p.bflat[i] = bflat[d];
+    p.out.bs[i] = gb.os[d];
+    p.idx.bs[i] = gb.is[d];
+    for (int k = 0; k < nl; ++k) p.leaf[k].bs[i] = gb.ls[k][d];
+  }
+  for (int d = 0; d < gr.n; ++d) {
+    p.rsz[d] = gr.size[d];
+    for (int k = 0; k < nl; ++k) p.leaf[k].rs[d] = gr.ls[k][d];
+  }
+  for (int k = 0; k < nl; ++k) p.leaf[k].ptr = e.leaves[k].data;
+  p.out.ptr = out ? out->data : nullptr;
+  p.idx.ptr = idx_out ? idx_out->data : nullptr;
+  p.idx_base = opt.idx_base;
+  p.post_div = opt.post_div ? 1 : 0;
+  p.post_scale_f = (float)opt.post_scale;
+  p.post_scale_d = opt.post_scale;
+  p.post_sqrt = opt.post_sqrt ? 1 : 0;
+  p.raw_partial = opt.raw_partial ? 1 : 0;
+  fill_consts(e, p.c);
+
+  const int sm = h->sm_count;
+  unsigned grid = 1, block = 256, smem = 0;
+  if (spec.family == FAM_VAR_SMEM) {
+    block = R >= 4096 ? 512 : 256;
+    smem = (unsigned)(R * dtype_bytes(info.value_dtype));
+    grid = (unsigned)std::min<int64_t>(B, (int64_t)sm * 16);
+  } else if (spec.family == FAM_RED_INNER) {
+    const int64_t row_bytes = R * info.max_leaf_bytes;
+    spec.team = (row_bytes >= 8192) ? 0 : 1;
+    if (spec.team == 0) {
+      const int64_t L = gr.size[gr.n - 1];
+      const int64_t Q = (R / L) * (L / spec.V);  // vector steps per row
+      int64_t S = 1;
+      if (B < 2 * (int64_t)sm) {
+        S = ((int64_t)sm * 8 + B - 1) / B;
+        const int64_t maxS = std::max<int64_t>(1, Q / ((int64_t)block * spec.U * 2));
+        S = std::max<int64_t>(1, std::min(S, maxS));
+      }
+      p.splits = (int)S;
+      if (S > 1) {
+        int st = ensure_ws(h, (size_t)(B * S) * (size_t)acc_bytes(kop, info.value_dtype), (size_t)B);
+        if (st != MXB_OK) return st;
+        p.ws = h->ws;
+        p.tickets = h->tickets;
+      }
+      grid = (unsigned)std::min<int64_t>(B * S, (int64_t)sm * 8);
+    } else {
+      const int64_t wpb = block / 32;
+      grid = (unsigned)std::min<int64_t>((B + wpb - 1) / wpb, (int64_t)sm * 8);
+    }
+  } else {  // FAM_RED_OUTER
+    const int64_t C = p.bsz[p.nb - 1];
+    const int64_t cv = (C + spec.V - 1) / spec.V;
+    int tx = 1;
+    while (tx < 128 && tx < cv) tx <<= 1;
+    p.tx = tx;
+    const int ty = (int)block / tx;
+    smem = ty > 1 ? (unsigned)(ty * tx * spec.V * acc_bytes(kop, info.value_dtype)) : 0;
+    const int64_t tile = (int64_t)tx * spec.V;
+    const int64_t work = (B / C) * ((C + tile - 1) / tile);
+    grid = (unsigned)std::min<int64_t>(work, (int64_t)sm * 8);
+  }
+
+  Kernel k;
+  int st = get_kernel(info, spec, &k);
+  if (st != MXB_OK) return st;
+  return launch(h, k, grid, block, smem, p);
+}
+
+bool is_floating(int t) { return t == MXB_F32 || t == MXB_F64 || t == MXB_C64; }
+
+int reduce_impl(mxb_context *h, int op, const mxb_expr_t *expr_in, int n_reduce, const mxb_out_t *out, const mxb_out_t *idx_out,
+                int ddof, const RedOptions *partial_opt) {
+  if (!h) return fail(MXB_ERR_INVALID, "null handle");
+  if (op < 0 || op >= MXB_RED_COUNT) return fail(MXB_ERR_INVALID, "unknown reduce op");
+  int st = check_expr_shape(expr_in);
+  if (st != MXB_OK) return st;
+  if (n_reduce < 0 || n_reduce > expr_in->rank) return fail(MXB_ERR_INVALID, "n_reduce_dims out of range");
+  const int nbd = expr_in->rank - n_reduce;
+  const bool arg = (op == MXB_RED_ARGMAX || op == MXB_RED_ARGMIN);
+  if (!partial_opt) {
+    if (!out || !out->data) return fail(MXB_ERR_INVALID, "null output");
+    if (out->rank != nbd) return fail(MXB_ERR_SIZE, "output rank must be expr rank - n_reduce_dims");
+    for (int d = 0; d < nbd; ++d)
+      if (out->size[d] != expr_in->size[d]) return fail(MXB_ERR_SIZE, "output size mismatch in dim " + std::to_string(d));
+    if (out->dtype < 0 || out->dtype >= MXB_DTYPE_COUNT) return fail(MXB_ERR_INVALID, "output dtype out of range");
+    if (arg) {
+      if (!idx_out || !idx_out->data) return fail(MXB_ERR_INVALID, "argmax/argmin need an index output");
+      if (idx_out->dtype != MXB_I64) return fail(MXB_ERR_INVALID, "index output must be MXB_I64 (matx::index_t)");
+      if (idx_out->rank != nbd) return fail(MXB_ERR_SIZE, "index output rank mismatch");
+      for (int d = 0; d < nbd; ++d)
+        if (idx_out->size[d] != expr_in->size[d]) return fail(MXB_ERR_SIZE, "index output size mismatch");
+    }
+  }
+  if (!arg) idx_out = nullptr;
+  MXB_CUDA(cudaSetDevice(h->device));
+
+  mxb_expr_t e;
+  std::string err;
+  st = canonicalize(expr_in, &e, &err);
+  if (st != MXB_OK) return fail(st, err);
+  ExprInfo info;
+  st = analyze_expr(&e, &info, &err);
+  if (st != MXB_OK) return fail(st, err);
+  if (out && !partial_opt && info.value_dtype == MXB_C64 && out->dtype != MXB_C64 &&
+      (op == MXB_RED_SUM || op == MXB_RED_MEAN || op == MXB_RED_PROD))
+    return fail(MXB_ERR_INVALID, "complex reduction needs a complex output");
+
+  RedOptions opt;
+  if (partial_opt) opt = *partial_opt;
+  int64_t R = 1;
+  for (int d = nbd; d < e.rank; ++d) R *= e.size[d];
+
+  if (op == MXB_RED_VAR || op == MXB_RED_STDD) {
+    if (partial_opt) return fail(MXB_ERR_NOT_SUPPORTED, "slab-sharded variance is not implemented yet");
+    if (!is_floating(info.value_dtype)) return fail(MXB_ERR_NOT_SUPPORTED, "var/stdd of a non-floating expression");
+    if (out->dtype == MXB_C64) return fail(MXB_ERR_INVALID, "var/stdd output is real (the reference uses the inner type)");
+    opt.post_scale = (double)(R - ddof);
+    opt.post_sqrt = (op == MXB_RED_STDD);
+    const int64_t row_bytes = R * dtype_bytes(info.value_dtype);
+    if (row_bytes <= (int64_t)h->max_smem_optin - 4096 && !getenv("MXB_VAR_TWO_LAUNCH")) {
+      return reduce_launch(h, MXB_RED_VAR, e, info, n_reduce, out, nullptr, opt, /*var_smem=*/true);
+    }
+    // Row does not fit in shared memory: the reference's own scheme — mean, then the sum of
+    // |x - mean|^2 — as two launches over the same skeletons (two reads of the input, like the reference).
+    int64_t B = 1;
+    for (int d = 0; d < nbd; ++d) B *= e.size[d];
+    st = ensure_tmp(h, (size_t)std::max<int64_t>(B, 1) * (size_t)dtype_bytes(info.value_dtype));
+    if (st != MXB_OK) return st;
+    mxb_out_t mean_out;
+    memset(&mean_out, 0, sizeof mean_out);
+    mean_out.data = h->tmp;
+    mean_out.dtype = info.value_dtype;
+    mean_out.rank = nbd;
+    {
+      int64_t w = 1;
+      for (int d = nbd - 1; d >= 0; --d) { mean_out.size[d] = e.size[d]; mean_out.stride[d] = w; w *= e.size[d]; }
+    }
+    RedOptions mo;
+    mo.post_div = true;
+    mo.post_scale = (double)R;
+    st = reduce_launch(h, MXB_RED_SUM, e, info, n_reduce, &mean_out, nullptr, mo);
+    if (st != MXB_OK) return st;
+    if (e.n_leaves >= MXB_MAX_LEAVES || e.n_nodes + 3 > MXB_MAX_NODES) return fail(MXB_ERR_NOT_SUPPORTED, "expression too large for the two-launch variance");
+    mxb_expr_t e2 = e;
+    const int lk = e2.n_leaves++;
+    memset(&e2.leaves[lk], 0, sizeof e2.leaves[lk]);
+    e2.leaves[lk].data = h->tmp;
+    e2.leaves[lk].dtype = info.value_dtype;
+    for (int d = 0; d < nbd; ++d) e2.leaves[lk].stride[d] = mean_out.stride[d];
+    const int nleafnode = e2.n_nodes++;
+    e2.nodes[nleafnode] = mxb_node_t{MXB_OP_LEAF, {lk, -1}, 0};
+    const int nsub = e2.n_nodes++;
+    e2.nodes[nsub] = mxb_node_t{MXB_OP_SUB, {e.root, nleafnode}, 0};
+    const int nabs2 = e2.n_nodes++;
+    e2.nodes[nabs2] = mxb_node_t{MXB_OP_ABS2, {nsub, -1}, 0};
+    e2.root = nabs2;
+    mxb_expr_t e2c;
+    st = canonicalize(&e2, &e2c, &err);
+    if (st != MXB_OK) return fail(st, err);
+    ExprInfo info2;
+    st = analyze_expr(&e2c, &info2, &err);
+    if (st != MXB_OK) return fail(st, err);
+    opt.post_div = true;
+    return reduce_launch(h, MXB_RED_SUM, e2c, info2, n_reduce, out, nullptr, opt);
+  }
+
+  if (op == MXB_RED_MEAN && !partial_opt) {
+    if (!is_floating(info.value_dtype)) return fail(MXB_ERR_NOT_SUPPORTED, "mean of a non-floating expression");
+    opt.post_div = true;
+    opt.post_scale = (double)R;
+  }
+  return reduce_launch(h, kernel_op(op), e, info, n_reduce, out, idx_out, opt);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// multi-GPU finalize: fold `world` 32-byte records in rank order, one thread
+// ---------------------------------------------------------------------------------------------------
+template <class Op, class OutT>
+__global__ void finalize_kernel(const mxb::PartialRec *recs, int world, const __grid_constant__ RedParams p) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  typename Op::acc_t a = Op::init();
+  for (int r = 0; r < world; ++r) {
+    union { mxb::PartialRec rec; typename Op::acc_t acc; } u;
+    u.rec = recs[r];
+    Op::merge(a, u.acc);
+  }
+  mxb::store_result<Op, OutT>(p, 0, a);
+}
+
+template <class T, class OutT>
+int finalize_dispatch_op(mxb_context *h, int kop, const void *recs, int world, RedParams &p) {
+#define MXB_FIN(...) finalize_kernel<__VA_ARGS__, OutT><<<1, 32, 0, h->stream>>>((const mxb::PartialRec *)recs, world, p)
+  switch (kop) {
+    case MXB_RED_SUM: MXB_FIN(mxb::OpSum<T>); break;
+    case MXB_RED_PROD: MXB_FIN(mxb::OpProd<T>); break;
+    case MXB_RED_ANY: MXB_FIN(mxb::OpLogic<T, true>); break;
+    case MXB_RED_ALL: MXB_FIN(mxb::OpLogic<T, false>); break;
+    default:
+      if constexpr (!mxb::is_complex<T>::value) {
+        switch (kop) {
+          case MXB_RED_MAX: MXB_FIN(mxb::OpExt<T, true>); break;
+          case MXB_RED_MIN: MXB_FIN(mxb::OpExt<T, false>); break;
+          case MXB_RED_ARGMAX: MXB_FIN(mxb::OpArg<T, true>); break;
+          case MXB_RED_ARGMIN: MXB_FIN(mxb::OpArg<T, false>); break;
+          default: return fail(MXB_ERR_NOT_SUPPORTED, "finalize: op not supported");
+        }
+      } else {
+        return fail(MXB_ERR_NOT_SUPPORTED, "finalize: op not supported for complex");
+      }
+  }
+#undef MXB_FIN
+  MXB_CUDA(cudaGetLastError());
+  h->launches++;
+  h->last_kernel = "finalize";
+  return MXB_OK;
+}
+
+}  // namespace
+
+// ===================================================================================================
+// extern "C"
+// ===================================================================================================
+extern "C" {
+
+int mxb_version(void) { return MXB_VERSION_MAJOR * 1000 + MXB_VERSION_MINOR; }
+const char *mxb_last_error(void) { return g_err.c_str(); }
+
+int mxb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int mxb_create(mxb_handle_t *out_handle, void *stream) {
+  if (!out_handle) return fail(MXB_ERR_INVALID, "null handle pointer");
+  *out_handle = nullptr;
+  if (mxb_device_count() <= 0) return fail(MXB_ERR_NO_DEVICE, "no CUDA device visible: this library has no CPU fallback");
+  mxb_context *h = new mxb_context();
+  cudaError_t e = cudaGetDevice(&h->device);
+  if (e != cudaSuccess) { delete h; return cuda_fail(e, "cudaGetDevice"); }
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, h->device);
+  if (e != cudaSuccess) { delete h; return cuda_fail(e, "cudaGetDeviceProperties"); }
+  if (prop.major != 10) {
+    delete h;
+    return fail(MXB_ERR_NO_DEVICE, std::string("device is sm_") + std::to_string(prop.major) + std::to_string(prop.minor) +
+                                       ", this library is built for sm_100a (B200) only");
+  }
+  h->sm_count = prop.multiProcessorCount;
+  h->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+  h->stream = (cudaStream_t)stream;
+  *out_handle = h;
+  return MXB_OK;
+}
+
+int mxb_destroy(mxb_handle_t h) {
+  if (!h) return MXB_OK;
+  cudaSetDevice(h->device);
+  if (h->ws) cudaFreeAsync(h->ws, h->stream);
+  if (h->tickets) cudaFreeAsync(h->tickets, h->stream);
+  if (h->tmp) cudaFreeAsync(h->tmp, h->stream);
+  delete h;
+  return MXB_OK;
+}
+
+int mxb_set_stream(mxb_handle_t h, void *stream) {
+  if (!h) return fail(MXB_ERR_INVALID, "null handle");
+  if ((cudaStream_t)stream != h->stream) {
+    // scratch is stream-ordered: hand it over only once the old stream is done with it
+    MXB_CUDA(cudaStreamSynchronize(h->stream));
+    h->stream = (cudaStream_t)stream;
+  }
+  return MXB_OK;
+}
+
+int mxb_sync(mxb_handle_t h) {
+  if (!h) return fail(MXB_ERR_INVALID, "null handle");
+  MXB_CUDA(cudaStreamSynchronize(h->stream));
+  return MXB_OK;
+}
+
+const char *mxb_last_kernel(mxb_handle_t h) { return h ? h->last_kernel.c_str() : ""; }
+int64_t mxb_launch_count(mxb_handle_t h) { return h ? h->launches : 0; }
+
+int mxb_reduce(mxb_handle_t h, int reduce_op, const mxb_expr_t *expr, int n_reduce_dims, const mxb_out_t *out,
+               const mxb_out_t *idx_out, int ddof) {
+  return reduce_impl(h, reduce_op, expr, n_reduce_dims, out, idx_out, ddof, nullptr);
+}
+
+int mxb_reduce_partial(mxb_handle_t h, int reduce_op, const mxb_expr_t *expr, int64_t slab_offset, void *partial_record) {
+  if (!partial_record) return fail(MXB_ERR_INVALID, "null partial record");
+  if (!expr) return fail(MXB_ERR_INVALID, "null expression");
+  RedOptions opt;
+  opt.raw_partial = true;
+  opt.idx_base = slab_offset;
+  mxb_out_t o;
+  memset(&o, 0, sizeof o);
+  o.data = partial_record;
+  mxb_out_t io = o;
+  io.dtype = MXB_I64;
+  int op = reduce_op == MXB_RED_MEAN ? MXB_RED_SUM : reduce_op;
+  return reduce_impl(h, op, expr, expr->rank, &o, &io, 0, &opt);
+}
+
+int mxb_reduce_finalize(mxb_handle_t h, int reduce_op, int32_t value_dtype, const void *gathered_records, int world,
+                        int64_t global_count, int ddof, const mxb_out_t *out, const mxb_out_t *idx_out) {
+  (void)ddof;
+  if (!h) return fail(MXB_ERR_INVALID, "null handle");
+  if (!gathered_records || world <= 0) return fail(MXB_ERR_INVALID, "no records to fold");
+  if (!out || !out->data) return fail(MXB_ERR_INVALID, "null output");
+  const bool arg = reduce_op == MXB_RED_ARGMAX || reduce_op == MXB_RED_ARGMIN;
+  if (arg && (!idx_out || !idx_out->data || idx_out->dtype != MXB_I64)) return fail(MXB_ERR_INVALID, "argmax/argmin need an MXB_I64 index output");
+  if (out->dtype != value_dtype) return fail(MXB_ERR_NOT_SUPPORTED, "finalize writes the value dtype only");
+  MXB_CUDA(cudaSetDevice(h->device));
+  RedParams p;
+  memset(&p, 0, sizeof p);
+  p.nb = 1; p.nr = 1; p.bsz[0] = 1; p.rsz[0] = 1; p.B = 1; p.R = global_count; p.bflat[0] = 1;
+  p.out.ptr = out->data;
+  p.idx.ptr = arg ? idx_out->data : nullptr;
+  if (reduce_op == MXB_RED_MEAN) { p.post_div = 1; p.post_scale_f = (float)global_count; p.post_scale_d = (double)global_count; }
+  const int kop = kernel_op(reduce_op);
+  switch (value_dtype) {
+    case MXB_F32: return finalize_dispatch_op<float, float>(h, kop, gathered_records, world, p);
+    case MXB_F64: return finalize_dispatch_op<double, double>(h, kop, gathered_records, world, p);
+    case MXB_C64: return finalize_dispatch_op<mxb::cfloat, mxb::cfloat>(h, kop, gathered_records, world, p);
+    case MXB_I32: return finalize_dispatch_op<int, int>(h, kop, gathered_records, world, p);
+    case MXB_I64: return finalize_dispatch_op<mxb::i64, mxb::i64>(h, kop, gathered_records, world, p);
+  }
+  return fail(MXB_ERR_NOT_SUPPORTED, "finalize: value dtype not supported");
+}
+
+int mxb_elementwise(mxb_handle_t h, const mxb_expr_t *expr_in, const mxb_out_t *out) {
+  if (!h) return fail(MXB_ERR_INVALID, "null handle");
+  int st = check_expr_shape(expr_in);
+  if (st != MXB_OK) return st;
+  if (!out || !out->data) return fail(MXB_ERR_INVALID, "null output");
+  if (out->rank != expr_in->rank) return fail(MXB_ERR_SIZE, "output rank must equal the expression rank");
+  for (int d = 0; d < out->rank; ++d)
+    if (out->size[d] != expr_in->size[d]) return fail(MXB_ERR_SIZE, "output size mismatch in dim " + std::to_string(d));
+  if (out->dtype < 0 || out->dtype >= MXB_DTYPE_COUNT) return fail(MXB_ERR_INVALID, "output dtype out of range");
+  MXB_CUDA(cudaSetDevice(h->device));
+
+  mxb_expr_t e;
+  std::string err;
+  st = canonicalize(expr_in, &e, &err);
+  if (st != MXB_OK) return fail(st, err);
+  ExprInfo info;
+  st = analyze_expr(&e, &info, &err);
+  if (st != MXB_OK) return fail(st, err);
+  if (info.value_dtype == MXB_C64 && out->dtype != MXB_C64) return fail(MXB_ERR_INVALID, "complex expression needs a complex output");
+
+  Group g;
+  g.n = e.rank;
+  for (int d = 0; d < e.rank; ++d) {
+    g.size[d] = e.size[d];
+    for (int k = 0; k < e.n_leaves; ++k) g.ls[k][d] = e.leaves[k].stride[d];
+    g.os[d] = out->stride[d];
+    g.is[d] = 0;
+  }
+  collapse(g, e.n_leaves);
+  if (g.n > KMAXD) return fail(MXB_ERR_NOT_SUPPORTED, "view does not collapse to <= 4 dims");
+  int64_t N = 1;
+  for (int d = 0; d < g.n; ++d) N *= g.size[d];
+  if (N == 0) return MXB_OK;
+
+  const int nl = e.n_leaves;
+  const int obytes = dtype_bytes(out->dtype);
+  int vmax = policy_vmax(info);
+  // the store must fit one instruction too (STG.256 at most)
+  while (vmax > 1 && vmax * obytes > 32) vmax >>= 1;
+  auto vec_ok = [&](int V) {
+    if (g.os[g.n - 1] != 1) return false;
+    if (!aligned_to(out->data, (int64_t)V * obytes)) return false;
+    for (int d = 0; d + 1 < g.n; ++d) if (g.os[d] % V) return false;
+    for (int k = 0; k < nl; ++k) {
+      const int64_t in = g.ls[k][g.n - 1];
+      if (in != 0 && in != 1) return false;
+      if (in == 0) continue;
+      if (!aligned_to(e.leaves[k].data, (int64_t)V * dtype_bytes(e.leaves[k].dtype))) return false;
+      for (int d = 0; d + 1 < g.n; ++d) if (g.ls[k][d] % V) return false;
+    }
+    return true;
+  };
+  KernelSpec spec;
+  spec.family = FAM_EW;
+  spec.op = -1;
+  spec.out_dtype = out->dtype;
+  spec.V = (vmax > 1 && vec_ok(vmax)) ? vmax : 1;
+  spec.U = policy_unroll(info, spec.V, FAM_EW);
+
+  EwParams p;
+  memset(&p, 0, sizeof p);
+  p.nd = g.n;
+  p.N = N;
+  p.nleaf = nl;
+  for (int d = 0; d < g.n; ++d) {
+    p.sz[d] = g.size[d];
+    p.out.bs[d] = g.os[d];
+    for (int k = 0; k < nl; ++k) p.leaf[k].bs[d] = g.ls[k][d];
+  }
+  for (int k = 0; k < nl; ++k) p.leaf[k].ptr = e.leaves[k].data;
+  p.out.ptr = out->data;
+  fill_consts(e, p.c);
+
+  const unsigned block = 256;
+  const int64_t items = (N + spec.V - 1) / spec.V;
+  const int64_t want = (items + (int64_t)block * spec.U - 1) / ((int64_t)block * spec.U);
+  const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)h->sm_count * 8));
+  Kernel k;
+  st = get_kernel(info, spec, &k);
+  if (st != MXB_OK) return st;
+  return launch(h, k, grid, block, 0, p);
+}
+
+int mxb_is_aot(const mxb_expr_t *expr, int reduce_op_or_minus1) {
+  if (!expr) return 0;
+  mxb_expr_t e;
+  std::string err;
+  if (canonicalize(expr, &e, &err) != MXB_OK) return 0;
+  ExprInfo info;
+  if (analyze_expr(&e, &info, &err) != MXB_OK) return 0;
+  KernelSpec spec;
+  if (reduce_op_or_minus1 < 0) {
+    spec.family = FAM_EW;
+    spec.op = -1;
+    spec.out_dtype = info.value_dtype;
+  } else {
+    spec.family = (reduce_op_or_minus1 == MXB_RED_VAR || reduce_op_or_minus1 == MXB_RED_STDD) ? FAM_VAR_SMEM : FAM_RED_INNER;
+    spec.op = kernel_op(reduce_op_or_minus1);
+    spec.out_dtype = info.value_dtype;
+  }
+  spec.V = policy_vmax(info);
+  spec.U = policy_unroll(info, spec.V, spec.family);
+  spec.team = 0;
+  return lookup_aot(kernel_key(info, spec)) ? 1 : 0;
+}
+
+// ---- test hooks (not part of the reference-facing surface) -----------------------------------------
+// Canonical signature + generated functor of a program, for the CPU-side tests of the lowering.
+int mxb_debug_codegen(const mxb_expr_t *expr, char *buf, size_t buflen) {
+  if (!expr || !buf || buflen == 0) return fail(MXB_ERR_INVALID, "bad arguments");
+  mxb_expr_t e;
+  std::string err;
+  int st = canonicalize(expr, &e, &err);
+  if (st != MXB_OK) return fail(st, err);
+  ExprInfo info;
+  st = analyze_expr(&e, &info, &err);
+  if (st != MXB_OK) return fail(st, err);
+  const std::string s = std::string("value_dtype=") + dtype_name(info.value_dtype) + "\n" + info.src;
+  snprintf(buf, buflen, "%s", s.c_str());
+  return MXB_OK;
+}
+
+// Build (NVRTC only, no device needed) the kernel a call would use; proves on a CPU box that the
+// generated source compiles for sm_100a.  family: 0 red_inner, 1 red_outer, 2 var_smem, 3 elementwise.
+int mxb_debug_compile(const mxb_expr_t *expr, int family, int reduce_op, int out_dtype, int V, int team, char *log, size_t loglen) {
+  if (!expr) return fail(MXB_ERR_INVALID, "null expression");
+  mxb_expr_t e;
+  std::string err;
+  int st = canonicalize(expr, &e, &err);
+  if (st != MXB_OK) return fail(st, err);
+  ExprInfo info;
+  st = analyze_expr(&e, &info, &err);
+  if (st != MXB_OK) return fail(st, err);
+  KernelSpec spec;
+  spec.family = family;
+  spec.op = family == FAM_EW ? -1 : kernel_op(reduce_op);
+  spec.out_dtype = out_dtype;
+  spec.V = V > 0 ? V : policy_vmax(info);
+  spec.U = policy_unroll(info, spec.V, family);
+  spec.team = team;
+  const std::string key = kernel_key(info, spec);
+  std::string wrap;
+  st = kernel_wrapper_src(info, spec, kernel_symbol(key), &wrap, &err);
+  if (st != MXB_OK) return fail(st, err);
+  const std::string src = "#include \"mxb_device.cuh\"\n" + info.src + "\n" + wrap;
+  std::string lg;
+  st = jit_compile_only(src, &lg);
+  if (log && loglen) snprintf(log, loglen, "%s", lg.c_str());
+  if (st != MXB_OK) return fail(st, "NVRTC: " + lg);
+  return MXB_OK;
+}
+
+}  // extern "C"

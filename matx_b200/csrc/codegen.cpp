@@ -1,0 +1,406 @@
+// codegen.cpp — lowers an expression program (mxb_expr_t, SSA over leaves / constants) to the device
+// functor `struct E_<hash>` that the kernel skeletons in mxb_device.cuh are instantiated with.
+//
+// The same generator feeds both builds: the AOT tool (gen_main.cpp) prints the functors of the named
+// programs into .cu files that nvcc compiles into the library, and jit.cpp hands the text to NVRTC for
+// any other program.  The typing rules restate what the reference gets from C++ on its functors
+// (operators/scalar_ops.h:434-503, operators/binary_operators.h:91-381, unary_operators.h:58-):
+// usual arithmetic conversions between operand types, comparisons / logic yield bool, abs / abs2 /
+// real / imag of a complex yield its real type.  16-bit float leaves are widened to fp32 on load and
+// all arithmetic on them is fp32 (the north star's "fp32 accumulation for fp16/bf16 inputs").
+#include <cstdio>
+#include <cstring>
+#include <sstream>
+
+#include "mxb_internal.h"
+
+namespace mxbh {
+
+int dtype_bytes(int d) {
+  switch (d) {
+    case MXB_F32: return 4;
+    case MXB_F64: return 8;
+    case MXB_BF16: return 2;
+    case MXB_F16: return 2;
+    case MXB_C64: return 8;
+    case MXB_I32: return 4;
+    case MXB_I64: return 8;
+    case MXB_U8: return 1;
+  }
+  return 0;
+}
+const char *dtype_name(int d) {
+  static const char *n[] = {"f32", "f64", "bf16", "f16", "c64", "i32", "i64", "u8"};
+  return (d >= 0 && d < MXB_DTYPE_COUNT) ? n[d] : "?";
+}
+const char *dtype_ctype(int d) {
+  static const char *n[] = {"float", "double", "__nv_bfloat16", "__half", "mxb::cfloat", "int", "mxb::i64", "unsigned char"};
+  return (d >= 0 && d < MXB_DTYPE_COUNT) ? n[d] : "?";
+}
+const char *reduce_op_name(int op) {
+  static const char *n[] = {"sum", "mean", "var", "stdd", "max", "min", "argmax", "argmin", "any", "all", "prod"};
+  return (op >= 0 && op < MXB_RED_COUNT) ? n[op] : "?";
+}
+uint64_t fnv64(const std::string &s) {
+  uint64_t h = 1469598103934665603ULL;
+  for (unsigned char c : s) { h ^= c; h *= 1099511628211ULL; }
+  return h;
+}
+
+namespace {
+
+int compute_type(int storage) { return (storage == MXB_BF16 || storage == MXB_F16) ? MXB_F32 : storage; }
+bool is_int(int t) { return t == MXB_I32 || t == MXB_I64 || t == MXB_U8; }
+bool is_real_float(int t) { return t == MXB_F32 || t == MXB_F64; }
+int rank_of(int t) {
+  switch (t) {
+    case MXB_U8: return 0;
+    case MXB_I32: return 1;
+    case MXB_I64: return 2;
+    case MXB_F32: return 3;
+    case MXB_F64: return 4;
+  }
+  return -1;
+}
+// usual arithmetic conversions; -1 = unsupported combination
+int promote(int a, int b) {
+  if (a == MXB_C64 || b == MXB_C64) {
+    const int o = (a == MXB_C64) ? b : a;
+    if (o == MXB_F64) return -1;  // complex<double> is not lowered
+    return MXB_C64;
+  }
+  int r = rank_of(a) > rank_of(b) ? a : b;
+  if (r == MXB_U8) r = MXB_I32;  // integral promotion
+  return r;
+}
+// type a math function sees for an operand: integers go to double, as std:: overloads do
+int math_type(int t) { return is_int(t) ? MXB_F64 : t; }
+
+std::string val(int id) { return "t" + std::to_string(id); }
+std::string as(int want, int have, const std::string &x) {
+  if (want == have) return x;
+  return std::string("mxb::cvt<") + dtype_ctype(want) + ">(" + x + ")";
+}
+
+struct UnaryFn { int opcode; const char *name; const char *ffn; const char *dfn; };
+const UnaryFn kUnary[] = {
+    {MXB_OP_SQRT, "sqrt", "sqrtf", "sqrt"},     {MXB_OP_LOG, "log", "logf", "log"},       {MXB_OP_LOG2, "log2", "log2f", "log2"},
+    {MXB_OP_LOG10, "log10", "log10f", "log10"}, {MXB_OP_SIN, "sin", "sinf", "sin"},       {MXB_OP_COS, "cos", "cosf", "cos"},
+    {MXB_OP_TAN, "tan", "tanf", "tan"},         {MXB_OP_TANH, "tanh", "tanhf", "tanh"},   {MXB_OP_SINH, "sinh", "sinhf", "sinh"},
+    {MXB_OP_COSH, "cosh", "coshf", "cosh"},     {MXB_OP_ASIN, "asin", "asinf", "asin"},   {MXB_OP_ACOS, "acos", "acosf", "acos"},
+    {MXB_OP_ATAN, "atan", "atanf", "atan"},     {MXB_OP_FLOOR, "floor", "floorf", "floor"}, {MXB_OP_CEIL, "ceil", "ceilf", "ceil"},
+    {MXB_OP_ROUND, "round", "roundf", "round"}, {MXB_OP_RSQRT, "rsqrt", "rsqrtf", "rsqrt"}, {MXB_OP_NORMCDF, "normcdf", "normcdff", "normcdf"},
+};
+const char *opcode_tag(int op) {
+  switch (op) {
+    case MXB_OP_LEAF: return "L";
+    case MXB_OP_CONST: return "C";
+    case MXB_OP_ADD: return "add";
+    case MXB_OP_SUB: return "sub";
+    case MXB_OP_MUL: return "mul";
+    case MXB_OP_DIV: return "div";
+    case MXB_OP_MOD: return "mod";
+    case MXB_OP_POW: return "pow";
+    case MXB_OP_MAX: return "max";
+    case MXB_OP_MIN: return "min";
+    case MXB_OP_LT: return "lt";
+    case MXB_OP_GT: return "gt";
+    case MXB_OP_LE: return "le";
+    case MXB_OP_GE: return "ge";
+    case MXB_OP_EQ: return "eq";
+    case MXB_OP_NE: return "ne";
+    case MXB_OP_AND: return "and";
+    case MXB_OP_OR: return "or";
+    case MXB_OP_ATAN2: return "atan2";
+    case MXB_OP_NEG: return "neg";
+    case MXB_OP_EXP: return "exp";
+    case MXB_OP_ABS: return "abs";
+    case MXB_OP_ABS2: return "abs2";
+    case MXB_OP_CONJ: return "conj";
+    case MXB_OP_REAL: return "real";
+    case MXB_OP_IMAG: return "imag";
+    case MXB_OP_NOT: return "not";
+    case MXB_OP_ISNAN: return "isnan";
+    case MXB_OP_ISINF: return "isinf";
+    case MXB_OP_EXPJ: return "expj";
+    case MXB_OP_CAST: return "cast";
+  }
+  for (const UnaryFn &u : kUnary)
+    if (u.opcode == op) return u.name;
+  return nullptr;
+}
+bool is_binary(int op) { return op >= MXB_OP_ADD && op <= MXB_OP_ATAN2; }
+
+}  // namespace
+
+int analyze_expr(const mxb_expr_t *e, ExprInfo *info, std::string *err) {
+  auto fail = [&](int st, const std::string &m) { if (err) *err = m; return st; };
+  if (!e) return fail(MXB_ERR_INVALID, "null expression");
+  if (e->rank < 0 || e->rank > MXB_MAX_RANK) return fail(MXB_ERR_INVALID, "expression rank out of range");
+  if (e->n_nodes <= 0 || e->n_nodes > MXB_MAX_NODES) return fail(MXB_ERR_INVALID, "node count out of range");
+  if (e->n_leaves < 0 || e->n_leaves > MXB_MAX_LEAVES) return fail(MXB_ERR_INVALID, "leaf count out of range");
+  if (e->n_consts < 0 || e->n_consts > MXB_MAX_CONSTS) return fail(MXB_ERR_INVALID, "constant count out of range");
+  if (e->root < 0 || e->root >= e->n_nodes) return fail(MXB_ERR_INVALID, "root id out of range");
+
+  std::vector<int> type(e->n_nodes, -1);
+  std::ostringstream sig, body;
+  info->nleaf = e->n_leaves;
+  info->max_leaf_bytes = 1;
+  info->min_leaf_bytes = 16;
+  for (int k = 0; k < e->n_leaves; ++k) {
+    const int d = e->leaves[k].dtype;
+    if (d < 0 || d >= MXB_DTYPE_COUNT) return fail(MXB_ERR_INVALID, "leaf dtype out of range");
+    info->leaf_dtype[k] = d;
+    if (dtype_bytes(d) > info->max_leaf_bytes) info->max_leaf_bytes = dtype_bytes(d);
+    if (dtype_bytes(d) < info->min_leaf_bytes) info->min_leaf_bytes = dtype_bytes(d);
+    sig << "l" << k << ":" << dtype_name(d) << ";";
+  }
+  if (e->n_leaves == 0) info->min_leaf_bytes = info->max_leaf_bytes = 4;
+
+  for (int i = 0; i < e->n_nodes; ++i) {
+    const mxb_node_t &n = e->nodes[i];
+    const char *tag = opcode_tag(n.opcode);
+    if (!tag) return fail(MXB_ERR_NOT_SUPPORTED, "opcode " + std::to_string(n.opcode) + " is not lowered");
+    int t = -1;
+    std::string rhs;
+    if (n.opcode == MXB_OP_LEAF) {
+      const int k = n.src[0];
+      if (k < 0 || k >= e->n_leaves) return fail(MXB_ERR_INVALID, "leaf index out of range");
+      t = compute_type(e->leaves[k].dtype);
+      rhs = as(t, e->leaves[k].dtype, "r.x" + std::to_string(k) + ".v[v]");
+      sig << i << "=L" << k << ";";
+    } else if (n.opcode == MXB_OP_CONST) {
+      const int k = n.src[0];
+      if (k < 0 || k >= e->n_consts) return fail(MXB_ERR_INVALID, "constant index out of range");
+      const int d = e->consts[k].dtype;
+      if (d < 0 || d >= MXB_DTYPE_COUNT) return fail(MXB_ERR_INVALID, "constant dtype out of range");
+      t = compute_type(d);
+      const std::string ks = std::to_string(k);
+      switch (t) {
+        case MXB_F32: rhs = "c.fre[" + ks + "]"; break;
+        case MXB_F64: rhs = "c.dre[" + ks + "]"; break;
+        case MXB_C64: rhs = "mxb::cfloat(c.fre[" + ks + "], c.fim[" + ks + "])"; break;
+        case MXB_I32: rhs = "(int)c.ire[" + ks + "]"; break;
+        case MXB_I64: rhs = "c.ire[" + ks + "]"; break;
+        case MXB_U8: rhs = "(unsigned char)c.ire[" + ks + "]"; break;
+      }
+      sig << i << "=C" << k << ":" << dtype_name(t) << ";";
+    } else {
+      const int a = n.src[0];
+      if (a < 0 || a >= i) return fail(MXB_ERR_INVALID, "operand id must precede its use");
+      const int ta = type[a];
+      if (is_binary(n.opcode)) {
+        const int b = n.src[1];
+        if (b < 0 || b >= i) return fail(MXB_ERR_INVALID, "operand id must precede its use");
+        const int tb = type[b];
+        int pt = promote(ta, tb);
+        if (pt < 0) return fail(MXB_ERR_NOT_SUPPORTED, "complex<double> arithmetic is not lowered");
+        // complex (x) real keeps the real operand real (scalar multiply / divide, like cuda::std::complex)
+        auto opnd = [&](int id, int tid) {
+          if (pt == MXB_C64 && tid != MXB_C64) return as(MXB_F32, tid, val(id));
+          return as(pt, tid, val(id));
+        };
+        const std::string A = opnd(a, ta), B = opnd(b, tb);
+        switch (n.opcode) {
+          case MXB_OP_ADD: t = pt; rhs = A + " + " + B; break;
+          case MXB_OP_SUB: t = pt; rhs = A + " - " + B; break;
+          case MXB_OP_MUL: t = pt; rhs = A + " * " + B; break;
+          case MXB_OP_DIV: t = pt; rhs = A + " / " + B; break;
+          case MXB_OP_MOD:
+            if (pt == MXB_C64) return fail(MXB_ERR_NOT_SUPPORTED, "mod of complex");
+            t = pt; rhs = "mxb::f_mod(" + A + ", " + B + ")"; break;
+          case MXB_OP_POW: {
+            if (pt == MXB_C64) return fail(MXB_ERR_NOT_SUPPORTED, "pow of complex");
+            t = math_type(pt);
+            rhs = "mxb::f_pow(" + as(t, ta, val(a)) + ", " + as(t, tb, val(b)) + ")";
+            break;
+          }
+          case MXB_OP_ATAN2: {
+            if (pt == MXB_C64) return fail(MXB_ERR_NOT_SUPPORTED, "atan2 of complex");
+            t = math_type(pt);
+            rhs = std::string(t == MXB_F32 ? "atan2f(" : "atan2(") + as(t, ta, val(a)) + ", " + as(t, tb, val(b)) + ")";
+            break;
+          }
+          case MXB_OP_MAX: case MXB_OP_MIN:
+            if (pt == MXB_C64) return fail(MXB_ERR_NOT_SUPPORTED, "max/min of complex");
+            t = pt;
+            rhs = std::string(n.opcode == MXB_OP_MAX ? "mxb::f_max<" : "mxb::f_min<") + dtype_ctype(pt) + ">(" + A + ", " + B + ")";
+            break;
+          case MXB_OP_LT: case MXB_OP_GT: case MXB_OP_LE: case MXB_OP_GE: {
+            if (pt == MXB_C64) return fail(MXB_ERR_NOT_SUPPORTED, "ordering of complex");
+            const char *o = n.opcode == MXB_OP_LT ? " < " : n.opcode == MXB_OP_GT ? " > " : n.opcode == MXB_OP_LE ? " <= " : " >= ";
+            t = MXB_U8; rhs = "(unsigned char)(" + A + o + B + ")"; break;
+          }
+          case MXB_OP_EQ: case MXB_OP_NE: {
+            const std::string A2 = as(pt, ta, val(a)), B2 = as(pt, tb, val(b));
+            t = MXB_U8; rhs = "(unsigned char)(" + A2 + (n.opcode == MXB_OP_EQ ? " == " : " != ") + B2 + ")"; break;
+          }
+          case MXB_OP_AND: case MXB_OP_OR:
+            t = MXB_U8;
+            rhs = "(unsigned char)(mxb::nonzero(" + val(a) + (n.opcode == MXB_OP_AND ? ") && mxb::nonzero(" : ") || mxb::nonzero(") + val(b) + "))";
+            break;
+          default: return fail(MXB_ERR_NOT_SUPPORTED, "binary opcode not lowered");
+        }
+        sig << i << "=" << tag << "(" << a << "," << b << ");";
+      } else {
+        const std::string X = val(a);
+        bool done = false;
+        for (const UnaryFn &u : kUnary) {
+          if (u.opcode != n.opcode) continue;
+          if (ta == MXB_C64) return fail(MXB_ERR_NOT_SUPPORTED, std::string(u.name) + " of complex is not lowered");
+          t = math_type(ta);
+          rhs = std::string(t == MXB_F32 ? u.ffn : u.dfn) + "(" + as(t, ta, X) + ")";
+          done = true;
+        }
+        if (!done) {
+          switch (n.opcode) {
+            case MXB_OP_NEG: t = (ta == MXB_U8) ? MXB_I32 : ta; rhs = "-" + as(t, ta, X); break;
+            case MXB_OP_EXP:
+              t = math_type(ta); rhs = "mxb::f_exp(" + as(t, ta, X) + ")"; break;
+            case MXB_OP_ABS: t = (ta == MXB_C64) ? MXB_F32 : (ta == MXB_U8 ? MXB_I32 : ta); rhs = "mxb::f_abs(" + as(ta == MXB_U8 ? MXB_I32 : ta, ta, X) + ")"; break;
+            case MXB_OP_ABS2: t = (ta == MXB_C64) ? MXB_F32 : (ta == MXB_U8 ? MXB_I32 : ta); rhs = "mxb::f_abs2(" + as(ta == MXB_U8 ? MXB_I32 : ta, ta, X) + ")"; break;
+            case MXB_OP_CONJ: t = ta; rhs = "mxb::f_conj(" + X + ")"; break;
+            case MXB_OP_REAL: t = (ta == MXB_C64) ? MXB_F32 : ta; rhs = "mxb::f_real(" + X + ")"; break;
+            case MXB_OP_IMAG: t = (ta == MXB_C64) ? MXB_F32 : ta; rhs = "mxb::f_imag(" + X + ")"; break;
+            case MXB_OP_NOT: t = MXB_U8; rhs = "(unsigned char)(!mxb::nonzero(" + X + "))"; break;
+            case MXB_OP_ISNAN: t = MXB_U8; rhs = "(unsigned char)mxb::f_isnan(" + X + ")"; break;
+            case MXB_OP_ISINF: t = MXB_U8; rhs = "(unsigned char)mxb::f_isinf(" + X + ")"; break;
+            case MXB_OP_EXPJ:
+              if (ta == MXB_C64) return fail(MXB_ERR_NOT_SUPPORTED, "expj of complex");
+              t = MXB_C64; rhs = "mxb::f_expj(" + as(MXB_F32, ta, X) + ")"; break;
+            case MXB_OP_CAST: {
+              const int d = n.aux;
+              if (d < 0 || d >= MXB_DTYPE_COUNT) return fail(MXB_ERR_INVALID, "cast dtype out of range");
+              t = compute_type(d);
+              // a cast to a 16-bit float rounds through that format, then the value lives on as fp32
+              rhs = (d == t) ? as(t, ta, X) : as(t, d, as(d, ta, X));
+              break;
+            }
+            default: return fail(MXB_ERR_NOT_SUPPORTED, "unary opcode not lowered");
+          }
+        }
+        sig << i << "=" << tag << "(" << a;
+        if (n.opcode == MXB_OP_CAST) sig << ":" << dtype_name(n.aux);
+        sig << ");";
+      }
+    }
+    type[i] = t;
+    body << "    const " << dtype_ctype(t) << " " << val(i) << " = " << rhs << ";\n";
+  }
+  sig << "root=" << e->root;
+  info->value_dtype = type[e->root];
+  info->sig = sig.str();
+  char nm[32];
+  snprintf(nm, sizeof nm, "E_%016llx", (unsigned long long)fnv64(info->sig));
+  info->name = nm;
+
+  // ---- emit the functor ----
+  std::ostringstream s;
+  const int nl = e->n_leaves > 0 ? e->n_leaves : 1;
+  s << "// " << info->sig << "\n";
+  s << "struct " << info->name << " {\n";
+  s << "  typedef " << dtype_ctype(info->value_dtype) << " value_type;\n";
+  s << "  enum { NLEAF = " << e->n_leaves << ", NL = " << nl << " };\n";
+  s << "  static __device__ __forceinline__ constexpr int leaf_bytes(int k) { return ";
+  for (int k = 0; k < e->n_leaves; ++k) s << "k == " << k << " ? " << dtype_bytes(e->leaves[k].dtype) << " : ";
+  s << "1; }\n";
+  s << "  template <int V> struct Regs {";
+  for (int k = 0; k < e->n_leaves; ++k) s << " mxb::Vec<" << dtype_ctype(e->leaves[k].dtype) << ", V> x" << k << ";";
+  if (e->n_leaves == 0) s << " int unused_;";
+  s << " };\n";
+  s << "  template <int V> static __device__ __forceinline__ void loadv(Regs<V> &r, const char *const *base, const mxb::i64 *inner, mxb::i64 j) {\n";
+  for (int k = 0; k < e->n_leaves; ++k)
+    s << "    mxb::ldleaf<" << dtype_ctype(e->leaves[k].dtype) << ", V>(r.x" << k << ", base[" << k << "], j, inner[" << k << "]);\n";
+  if (e->n_leaves == 0) s << "    (void)r; (void)base; (void)inner; (void)j;\n";
+  s << "  }\n";
+  s << "  template <int V> static __device__ __forceinline__ value_type eval(const Regs<V> &r, int v, const mxb::ConstDev &c) {\n";
+  s << "    (void)r; (void)v; (void)c;\n";
+  s << body.str();
+  s << "    return " << val(e->root) << ";\n";
+  s << "  }\n";
+  s << "};\n";
+  info->src = s.str();
+  return MXB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// kernel instances
+// ---------------------------------------------------------------------------------------------------
+int policy_vmax(const ExprInfo &info) {
+  // widest leaf moves 16 bytes per load (LDG.128); narrower leaves ride along with fewer bytes
+  int v = 16 / info.max_leaf_bytes;
+  if (v < 1) v = 1;
+  if (v > 8) v = 8;
+  return v;
+}
+int policy_unroll(const ExprInfo &info, int V, int family) {
+  (void)V;
+  if (family == FAM_RED_OUTER) return 4;
+  if (family == FAM_EW) return info.nleaf <= 2 ? 4 : 2;
+  if (family == FAM_VAR_SMEM) return 4;
+  return info.nleaf <= 2 ? 4 : 2;
+}
+
+std::string kernel_key(const ExprInfo &info, const KernelSpec &s) {
+  std::ostringstream k;
+  static const char *fam[] = {"red_inner", "red_outer", "var_smem", "ew"};
+  k << fam[s.family] << "|" << info.name << "|" << (s.op >= 0 ? reduce_op_name(s.op) : "-") << "|" << dtype_name(s.out_dtype)
+    << "|V" << s.V << "|U" << s.U << "|T" << s.team;
+  return k.str();
+}
+std::string kernel_symbol(const std::string &key) {
+  char nm[40];
+  snprintf(nm, sizeof nm, "mxbk_%016llx", (unsigned long long)fnv64(key));
+  return nm;
+}
+
+int kernel_wrapper_src(const ExprInfo &info, const KernelSpec &s, const std::string &symbol, std::string *out, std::string *err) {
+  auto fail = [&](const std::string &m) { if (err) *err = m; return (int)MXB_ERR_NOT_SUPPORTED; };
+  const std::string T = dtype_ctype(info.value_dtype);
+  const std::string O = dtype_ctype(s.out_dtype);
+  const bool cplx = info.value_dtype == MXB_C64;
+  std::ostringstream k;
+  std::string op;
+  if (s.family == FAM_RED_INNER || s.family == FAM_RED_OUTER) {
+    switch (s.op) {
+      case MXB_RED_SUM: op = "mxb::OpSum<" + T + ">"; break;
+      case MXB_RED_PROD: op = "mxb::OpProd<" + T + ">"; break;
+      case MXB_RED_MAX: case MXB_RED_MIN:
+        if (cplx) return fail("max/min of a complex expression (the reference rejects it too)");
+        op = "mxb::OpExt<" + T + (s.op == MXB_RED_MAX ? ", true>" : ", false>"); break;
+      case MXB_RED_ARGMAX: case MXB_RED_ARGMIN:
+        if (cplx) return fail("argmax/argmin of a complex expression (the reference rejects it too)");
+        op = "mxb::OpArg<" + T + (s.op == MXB_RED_ARGMAX ? ", true>" : ", false>"); break;
+      case MXB_RED_ANY: op = "mxb::OpLogic<" + T + ", true>"; break;
+      case MXB_RED_ALL: op = "mxb::OpLogic<" + T + ", false>"; break;
+      default: return fail("reduce op has no kernel of its own");
+    }
+  }
+  const std::string E = info.name;
+  const std::string VU = std::to_string(s.V) + ", " + std::to_string(s.U);
+  switch (s.family) {
+    case FAM_RED_INNER:
+      k << "extern \"C\" __global__ void __launch_bounds__(" << (s.team == 0 ? 512 : 256) << ") " << symbol
+        << "(const __grid_constant__ mxb::RedParams p) { mxb::reduce_inner_body<" << E << ", " << op << ", " << O << ", " << VU
+        << ", " << s.team << ">(p); }\n";
+      break;
+    case FAM_RED_OUTER:
+      k << "extern \"C\" __global__ void __launch_bounds__(256) " << symbol
+        << "(const __grid_constant__ mxb::RedParams p) { mxb::reduce_outer_body<" << E << ", " << op << ", " << O << ", " << VU << ">(p); }\n";
+      break;
+    case FAM_VAR_SMEM:
+      if (!(info.value_dtype == MXB_F32 || info.value_dtype == MXB_F64 || cplx)) return fail("var of a non-floating expression");
+      k << "extern \"C\" __global__ void __launch_bounds__(512) " << symbol
+        << "(const __grid_constant__ mxb::RedParams p) { mxb::var_inner_smem_body<" << E << ", " << O << ", " << VU << ">(p); }\n";
+      break;
+    case FAM_EW:
+      k << "extern \"C\" __global__ void __launch_bounds__(256) " << symbol
+        << "(const __grid_constant__ mxb::EwParams p) { mxb::ew_body<" << E << ", " << O << ", " << VU << ">(p); }\n";
+      break;
+    default: return fail("unknown kernel family");
+  }
+  *out = k.str();
+  return MXB_OK;
+}
+
+}  // namespace mxbh

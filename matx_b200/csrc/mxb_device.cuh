@@ -1,0 +1,1118 @@
+// mxb_device.cuh — device-side skeletons of the B200 reduce / fused-elementwise engine.
+//
+// This header is compiled two ways from the same text:
+//   * ahead of time by nvcc (-gencode arch=compute_100a,code=sm_100a) for the named expressions, and
+//   * at run time by NVRTC for any other expression program (see jit.cpp),
+// so it must stay free of host headers.  A generated `struct Expr` (codegen.cpp) supplies the leaf
+// loads and the per-element arithmetic; the kernels below supply everything the reference gets from
+// the generic executor kernels (executors/kernel.h:41-223) and from CUB's device / segmented reduce
+// (transforms/cub.h:647-894,1281-1328): index decomposition, vectorised coalesced loads, the
+// per-thread / warp / CTA / grid reduction stages and the output conversion.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+namespace mxb {
+
+typedef long long i64;
+typedef unsigned long long u64;
+typedef unsigned int u32;
+
+constexpr int KMAXD = 4;      // collapsed dims per group handled on the device
+constexpr int KMAXLEAF = 12;  // == MXB_MAX_LEAVES
+constexpr int KMAXCONST = 24; // == MXB_MAX_CONSTS
+
+// ------------------------------------------------------------------------------------------------
+// value types
+// ------------------------------------------------------------------------------------------------
+struct __align__(8) cfloat {
+  float re, im;
+  cfloat() = default;
+  __device__ __forceinline__ cfloat(float r, float i = 0.f) : re(r), im(i) {}
+};
+__device__ __forceinline__ cfloat operator+(cfloat a, cfloat b) { return cfloat(a.re + b.re, a.im + b.im); }
+__device__ __forceinline__ cfloat operator-(cfloat a, cfloat b) { return cfloat(a.re - b.re, a.im - b.im); }
+__device__ __forceinline__ cfloat operator-(cfloat a) { return cfloat(-a.re, -a.im); }
+__device__ __forceinline__ cfloat operator*(cfloat a, cfloat b) {
+  return cfloat(a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re);
+}
+__device__ __forceinline__ cfloat operator*(cfloat a, float b) { return cfloat(a.re * b, a.im * b); }
+__device__ __forceinline__ cfloat operator*(float a, cfloat b) { return cfloat(a * b.re, a * b.im); }
+__device__ __forceinline__ cfloat operator/(cfloat a, float b) { return cfloat(a.re / b, a.im / b); }
+__device__ __forceinline__ cfloat operator+(cfloat a, float b) { return cfloat(a.re + b, a.im); }
+__device__ __forceinline__ cfloat operator+(float a, cfloat b) { return cfloat(a + b.re, b.im); }
+__device__ __forceinline__ cfloat operator-(cfloat a, float b) { return cfloat(a.re - b, a.im); }
+__device__ __forceinline__ cfloat operator-(float a, cfloat b) { return cfloat(a - b.re, -b.im); }
+__device__ __forceinline__ cfloat operator/(cfloat a, cfloat b) {
+  // Smith's algorithm, as libcu++'s complex division does for finite operands
+  if (fabsf(b.re) >= fabsf(b.im)) {
+    float r = b.im / b.re, d = b.re + b.im * r;
+    return cfloat((a.re + a.im * r) / d, (a.im - a.re * r) / d);
+  } else {
+    float r = b.re / b.im, d = b.re * r + b.im;
+    return cfloat((a.re * r + a.im) / d, (a.im * r - a.re) / d);
+  }
+}
+__device__ __forceinline__ cfloat operator/(float a, cfloat b) { return cfloat(a, 0.f) / b; }
+__device__ __forceinline__ bool operator==(cfloat a, cfloat b) { return a.re == b.re && a.im == b.im; }
+__device__ __forceinline__ bool operator!=(cfloat a, cfloat b) { return !(a == b); }
+
+template <class T> struct is_complex { enum { value = 0 }; };
+template <> struct is_complex<cfloat> { enum { value = 1 }; };
+template <class A, class B> struct same_t { enum { value = 0 }; };
+template <class A> struct same_t<A, A> { enum { value = 1 }; };
+
+// ------------------------------------------------------------------------------------------------
+// kernel parameter blocks (plain data, passed by value as __grid_constant__)
+// ------------------------------------------------------------------------------------------------
+struct LeafDev {
+  const void *ptr;
+  i64 bs[KMAXD];  // strides over the (collapsed) batch / outer dims, elements
+  i64 rs[KMAXD];  // strides over the (collapsed) reduce dims, elements
+};
+struct OutDev {
+  void *ptr;
+  i64 bs[KMAXD];
+};
+struct ConstDev {
+  double dre[KMAXCONST], dim[KMAXCONST];
+  float fre[KMAXCONST], fim[KMAXCONST];
+  i64 ire[KMAXCONST];
+};
+
+// reduction: batch dims (nb of them, row-major) x reduce dims (nr of them, row-major, innermost last)
+struct RedParams {
+  int nb, nr;
+  i64 bsz[KMAXD], rsz[KMAXD];
+  i64 B, R;        // products of bsz / rsz
+  i64 bflat[KMAXD]; // weight of each batch dim in the ORIGINAL row-major batch index (dims may be rotated)
+  int nleaf;
+  int splits;      // CTAs cooperating on one row (inner_cta) or on one output tile (outer)
+  LeafDev leaf[KMAXLEAF];
+  OutDev out, idx;
+  void *ws;        // splits > 1: B*splits partial records
+  u32 *tickets;    // splits > 1: one self-resetting counter per row / tile
+  i64 idx_base;    // added to every reported flat index (slab offset in multi-GPU partials)
+  float post_scale_f; double post_scale_d; // MEAN: divide by this; VAR: N - ddof
+  int post_div;    // 1 = divide the sum by post_scale
+  int post_sqrt;   // STDD
+  int raw_partial; // 1 = write the 32-byte partial record instead of the finalised value (multi-GPU)
+  int tx;          // outer family: threads along the vector (column) dim; blockDim.x / tx reduce lanes
+  ConstDev c;
+};
+
+// elementwise: up to KMAXD collapsed dims, innermost last
+struct EwParams {
+  int nd;
+  i64 sz[KMAXD];
+  i64 N;           // product
+  int nleaf;
+  LeafDev leaf[KMAXLEAF]; // bs[] used
+  OutDev out;
+  ConstDev c;
+};
+
+// ------------------------------------------------------------------------------------------------
+// vector register bundles and global loads
+// ------------------------------------------------------------------------------------------------
+template <class T, int V> struct Vec { T v[V]; };
+
+// streaming read-only loads: data is touched once, keep it out of L1
+
+template <int BYTES> struct LdBytes;
+template <> struct LdBytes<1> {
+  static __device__ __forceinline__ void ld(void *d, const void *s) { *(unsigned char *)d = __ldg((const unsigned char *)s); }
+};
+template <> struct LdBytes<2> {
+  static __device__ __forceinline__ void ld(void *d, const void *s) { *(unsigned short *)d = __ldg((const unsigned short *)s); }
+};
+template <> struct LdBytes<4> {
+  static __device__ __forceinline__ void ld(void *d, const void *s) {
+    u32 r;
+    asm volatile("ld.global.nc.L1::no_allocate.b32 %0, [%1];" : "=r"(r) : "l"(s));
+    *(u32 *)d = r;
+  }
+};
+template <> struct LdBytes<8> {
+  static __device__ __forceinline__ void ld(void *d, const void *s) {
+    u32 a, b;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.b32 {%0,%1}, [%2];" : "=r"(a), "=r"(b) : "l"(s));
+    ((u32 *)d)[0] = a; ((u32 *)d)[1] = b;
+  }
+};
+template <> struct LdBytes<16> {
+  static __device__ __forceinline__ void ld(void *d, const void *s) {
+    u32 a, b, c, e;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.b32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(a), "=r"(b), "=r"(c), "=r"(e) : "l"(s));
+    ((u32 *)d)[0] = a; ((u32 *)d)[1] = b; ((u32 *)d)[2] = c; ((u32 *)d)[3] = e;
+  }
+};
+template <> struct LdBytes<32> {  // LDG.E.256 on sm_100
+  static __device__ __forceinline__ void ld(void *d, const void *s) {
+    u32 r0, r1, r2, r3, r4, r5, r6, r7;
+    asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3), "=r"(r4), "=r"(r5), "=r"(r6), "=r"(r7) : "l"(s));
+    u32 *o = (u32 *)d;
+    o[0] = r0; o[1] = r1; o[2] = r2; o[3] = r3; o[4] = r4; o[5] = r5; o[6] = r6; o[7] = r7;
+  }
+};
+template <> struct LdBytes<64> {
+  static __device__ __forceinline__ void ld(void *d, const void *s) {
+    LdBytes<32>::ld(d, s);
+    LdBytes<32>::ld((char *)d + 32, (const char *)s + 32);
+  }
+};
+
+// load V consecutive elements (address must be aligned to V*sizeof(T), or V == 1)
+template <class T, int V> __device__ __forceinline__ void ldv(Vec<T, V> &r, const T *p) {
+  LdBytes<(int)sizeof(T) * V>::ld(&r, p);
+}
+// leaf whose innermost stride is 0: one scalar load, replicated
+template <class T, int V> __device__ __forceinline__ void ldsplat(Vec<T, V> &r, const T *p) {
+  Vec<T, 1> s;
+  LdBytes<(int)sizeof(T)>::ld(&s, p);
+#pragma unroll
+  for (int i = 0; i < V; ++i) r.v[i] = s.v[0];
+}
+template <class T, int V> __device__ __forceinline__ void ldleaf(Vec<T, V> &r, const void *base, i64 j, i64 inner) {
+  const T *p = (const T *)base;
+  if (V == 1) {
+    LdBytes<(int)sizeof(T)>::ld(&r, p + j * inner);
+  } else if (inner != 0) {
+    ldv<T, V>(r, p + j);
+  } else {
+    ldsplat<T, V>(r, p);
+  }
+}
+
+// streaming stores
+template <int BYTES> struct StBytes;
+template <> struct StBytes<1> { static __device__ __forceinline__ void st(void *d, const void *s) { *(unsigned char *)d = *(const unsigned char *)s; } };
+template <> struct StBytes<2> { static __device__ __forceinline__ void st(void *d, const void *s) { *(unsigned short *)d = *(const unsigned short *)s; } };
+template <> struct StBytes<4> {
+  static __device__ __forceinline__ void st(void *d, const void *s) {
+    asm volatile("st.global.L1::no_allocate.b32 [%0], %1;" ::"l"(d), "r"(*(const u32 *)s) : "memory");
+  }
+};
+template <> struct StBytes<8> {
+  static __device__ __forceinline__ void st(void *d, const void *s) {
+    const u32 *x = (const u32 *)s;
+    asm volatile("st.global.L1::no_allocate.v2.b32 [%0], {%1,%2};" ::"l"(d), "r"(x[0]), "r"(x[1]) : "memory");
+  }
+};
+template <> struct StBytes<16> {
+  static __device__ __forceinline__ void st(void *d, const void *s) {
+    const u32 *x = (const u32 *)s;
+    asm volatile("st.global.L1::no_allocate.v4.b32 [%0], {%1,%2,%3,%4};" ::"l"(d), "r"(x[0]), "r"(x[1]), "r"(x[2]), "r"(x[3]) : "memory");
+  }
+};
+template <> struct StBytes<32> {  // STG.E.256 on sm_100
+  static __device__ __forceinline__ void st(void *d, const void *s) {
+    const u32 *x = (const u32 *)s;
+    asm volatile("st.global.L1::no_allocate.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(d), "r"(x[0]), "r"(x[1]),
+                 "r"(x[2]), "r"(x[3]), "r"(x[4]), "r"(x[5]), "r"(x[6]), "r"(x[7]) : "memory");
+  }
+};
+template <> struct StBytes<64> {
+  static __device__ __forceinline__ void st(void *d, const void *s) {
+    StBytes<32>::st(d, s);
+    StBytes<32>::st((char *)d + 32, (const char *)s + 32);
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// conversions between the arithmetic type of an expression and a stored element type
+// ------------------------------------------------------------------------------------------------
+template <class To, class From> struct Cvt {
+  static __device__ __forceinline__ To go(From x) { return (To)x; }
+};
+template <class From> struct Cvt<__nv_bfloat16, From> {
+  static __device__ __forceinline__ __nv_bfloat16 go(From x) { return __float2bfloat16_rn((float)x); }
+};
+template <class From> struct Cvt<__half, From> {
+  static __device__ __forceinline__ __half go(From x) { return __float2half_rn((float)x); }
+};
+template <class To> struct Cvt<To, __nv_bfloat16> {
+  static __device__ __forceinline__ To go(__nv_bfloat16 x) { return (To)__bfloat162float(x); }
+};
+template <class To> struct Cvt<To, __half> {
+  static __device__ __forceinline__ To go(__half x) { return (To)__half2float(x); }
+};
+template <> struct Cvt<__nv_bfloat16, __nv_bfloat16> { static __device__ __forceinline__ __nv_bfloat16 go(__nv_bfloat16 x) { return x; } };
+template <> struct Cvt<__half, __half> { static __device__ __forceinline__ __half go(__half x) { return x; } };
+template <> struct Cvt<__half, __nv_bfloat16> { static __device__ __forceinline__ __half go(__nv_bfloat16 x) { return __float2half_rn(__bfloat162float(x)); } };
+template <> struct Cvt<__nv_bfloat16, __half> { static __device__ __forceinline__ __nv_bfloat16 go(__half x) { return __float2bfloat16_rn(__half2float(x)); } };
+template <> struct Cvt<cfloat, cfloat> { static __device__ __forceinline__ cfloat go(cfloat x) { return x; } };
+template <class From> struct Cvt<cfloat, From> {
+  static __device__ __forceinline__ cfloat go(From x) { return cfloat(Cvt<float, From>::go(x), 0.f); }
+};
+template <class To> struct Cvt<To, cfloat> {  // complex -> real keeps the real part (only reached for any/all style 0/1 outputs)
+  static __device__ __forceinline__ To go(cfloat x) { return Cvt<To, float>::go(x.re); }
+};
+template <class To, class From> __device__ __forceinline__ To cvt(From x) { return Cvt<To, From>::go(x); }
+
+template <class T> __device__ __forceinline__ bool nonzero(T x) { return x != (T)0; }
+template <> __device__ __forceinline__ bool nonzero<cfloat>(cfloat x) { return x.re != 0.f || x.im != 0.f; }
+
+// ------------------------------------------------------------------------------------------------
+// scalar math used by generated expressions (reference functors: operators/scalar_ops.h:434-503,
+// scalar_internal.h:44-297 which forward to cuda::std / CUDA math)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float f_normcdf(float x) { return normcdff(x); }
+__device__ __forceinline__ double f_normcdf(double x) { return normcdf(x); }
+__device__ __forceinline__ float f_abs(float x) { return fabsf(x); }
+__device__ __forceinline__ double f_abs(double x) { return fabs(x); }
+__device__ __forceinline__ int f_abs(int x) { return x < 0 ? -x : x; }
+__device__ __forceinline__ i64 f_abs(i64 x) { return x < 0 ? -x : x; }
+__device__ __forceinline__ float f_abs(cfloat x) { return hypotf(x.re, x.im); }
+__device__ __forceinline__ float f_abs2(float x) { return x * x; }
+__device__ __forceinline__ double f_abs2(double x) { return x * x; }
+__device__ __forceinline__ int f_abs2(int x) { return x * x; }
+__device__ __forceinline__ i64 f_abs2(i64 x) { return x * x; }
+__device__ __forceinline__ float f_abs2(cfloat x) { return x.re * x.re + x.im * x.im; }
+__device__ __forceinline__ cfloat f_conj(cfloat x) { return cfloat(x.re, -x.im); }
+template <class T> __device__ __forceinline__ T f_conj(T x) { return x; }
+__device__ __forceinline__ float f_real(cfloat x) { return x.re; }
+__device__ __forceinline__ float f_imag(cfloat x) { return x.im; }
+template <class T> __device__ __forceinline__ T f_real(T x) { return x; }
+template <class T> __device__ __forceinline__ T f_imag(T) { return (T)0; }
+__device__ __forceinline__ float f_pow(float a, float b) { return powf(a, b); }
+__device__ __forceinline__ double f_pow(double a, double b) { return pow(a, b); }
+__device__ __forceinline__ float f_mod(float a, float b) { return fmodf(a, b); }
+__device__ __forceinline__ double f_mod(double a, double b) { return fmod(a, b); }
+__device__ __forceinline__ int f_mod(int a, int b) { return a % b; }
+__device__ __forceinline__ i64 f_mod(i64 a, i64 b) { return a % b; }
+template <class T> __device__ __forceinline__ T f_max(T a, T b) { return a > b ? a : b; }  // scalar_internal.h: cuda::std::max
+template <class T> __device__ __forceinline__ T f_min(T a, T b) { return a < b ? a : b; }
+__device__ __forceinline__ float f_sqrt(float x) { return sqrtf(x); }
+__device__ __forceinline__ double f_sqrt(double x) { return sqrt(x); }
+__device__ __forceinline__ float f_rsqrt(float x) { return rsqrtf(x); }
+__device__ __forceinline__ double f_rsqrt(double x) { return rsqrt(x); }
+__device__ __forceinline__ cfloat f_expj(float x) { float s, c; sincosf(x, &s, &c); return cfloat(c, s); }
+__device__ __forceinline__ cfloat f_exp(cfloat x) { float e = expf(x.re), s, c; sincosf(x.im, &s, &c); return cfloat(e * c, e * s); }
+__device__ __forceinline__ float f_exp(float x) { return expf(x); }
+__device__ __forceinline__ double f_exp(double x) { return exp(x); }
+__device__ __forceinline__ float f_round(float x) { return roundf(x); }
+__device__ __forceinline__ double f_round(double x) { return round(x); }
+template <class T> __device__ __forceinline__ bool f_isnan(T) { return false; }
+__device__ __forceinline__ bool f_isnan(float x) { return x != x; }
+__device__ __forceinline__ bool f_isnan(double x) { return x != x; }
+__device__ __forceinline__ bool f_isnan(cfloat x) { return x.re != x.re || x.im != x.im; }
+template <class T> __device__ __forceinline__ bool f_isinf(T) { return false; }
+__device__ __forceinline__ bool f_isinf(float x) { return isinf(x); }
+__device__ __forceinline__ bool f_isinf(double x) { return isinf(x); }
+__device__ __forceinline__ bool f_isinf(cfloat x) { return isinf(x.re) || isinf(x.im); }
+
+// ------------------------------------------------------------------------------------------------
+// reduction operators: accumulate (per element), combine (associative, order-preserving), warp stage
+// ------------------------------------------------------------------------------------------------
+template <class T> __device__ __forceinline__ T shfl_xor_t(T x, int m) {
+  // bounce any trivially copyable record through 32-bit shuffles
+  enum { W = (sizeof(T) + 3) / 4 };
+  union { T t; u32 w[W]; } u;
+  u.t = x;
+#pragma unroll
+  for (int i = 0; i < W; ++i) u.w[i] = __shfl_xor_sync(0xffffffffu, u.w[i], m);
+  return u.t;
+}
+template <class T> __device__ __forceinline__ T shfl_down_t(T x, int d) {
+  enum { W = (sizeof(T) + 3) / 4 };
+  union { T t; u32 w[W]; } u;
+  u.t = x;
+#pragma unroll
+  for (int i = 0; i < W; ++i) u.w[i] = __shfl_down_sync(0xffffffffu, u.w[i], d);
+  return u.t;
+}
+
+template <class T> struct Limits;
+template <> struct Limits<float> {
+  static __device__ __forceinline__ float lowest() { return -__int_as_float(0x7f800000); }
+  static __device__ __forceinline__ float highest() { return __int_as_float(0x7f800000); }
+};
+template <> struct Limits<double> {
+  static __device__ __forceinline__ double lowest() { return -__longlong_as_double(0x7ff0000000000000LL); }
+  static __device__ __forceinline__ double highest() { return __longlong_as_double(0x7ff0000000000000LL); }
+};
+template <> struct Limits<int> {
+  static __device__ __forceinline__ int lowest() { return (int)0x80000000; }
+  static __device__ __forceinline__ int highest() { return 0x7fffffff; }
+};
+template <> struct Limits<i64> {
+  static __device__ __forceinline__ i64 lowest() { return (i64)0x8000000000000000ULL; }
+  static __device__ __forceinline__ i64 highest() { return 0x7fffffffffffffffLL; }
+};
+template <> struct Limits<unsigned char> {
+  static __device__ __forceinline__ unsigned char lowest() { return 0; }
+  static __device__ __forceinline__ unsigned char highest() { return 255; }
+};
+
+// Every op exposes:
+//   acc_t                       running state of one thread / partial record (<= 16 bytes)
+//   init()
+//   step(acc, x, flat_index)    fold one element; elements arrive in increasing flat_index per thread
+//   merge(a, b)                 a = a (+) b where every index in a precedes / is unrelated to b's (commutative here:
+//                               arg ops compare indices explicitly, so order does not matter)
+//   warp(acc)                   all-lanes result of the warp-wide merge
+//   result_t / finish(acc)      value written to `out`
+//   HAS_INDEX, index(acc)
+template <class T> struct OpSum {
+  typedef T acc_t; typedef T result_t; enum { HAS_INDEX = 0 };
+  static __device__ __forceinline__ acc_t init() { return (T)0; }
+  static __device__ __forceinline__ void step(acc_t &a, T x, i64) { a = a + x; }
+  static __device__ __forceinline__ void merge(acc_t &a, acc_t b) { a = a + b; }
+  static __device__ __forceinline__ acc_t warp(acc_t a) {
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) a = a + shfl_xor_t(a, m);
+    return a;
+  }
+  static __device__ __forceinline__ result_t finish(acc_t a) { return a; }
+  static __device__ __forceinline__ i64 index(acc_t) { return 0; }
+};
+template <> struct OpSum<cfloat> {
+  typedef cfloat acc_t; typedef cfloat result_t; enum { HAS_INDEX = 0 };
+  static __device__ __forceinline__ acc_t init() { return cfloat(0.f, 0.f); }
+  static __device__ __forceinline__ void step(acc_t &a, cfloat x, i64) { a = a + x; }
+  static __device__ __forceinline__ void merge(acc_t &a, acc_t b) { a = a + b; }
+  static __device__ __forceinline__ acc_t warp(acc_t a) {
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) a = a + shfl_xor_t(a, m);
+    return a;
+  }
+  static __device__ __forceinline__ result_t finish(acc_t a) { return a; }
+  static __device__ __forceinline__ i64 index(acc_t) { return 0; }
+};
+// integer sums ride redux.sync
+template <> __device__ __forceinline__ int OpSum<int>::warp(int a) { return __reduce_add_sync(0xffffffffu, a); }
+
+template <class T> struct OpProd {
+  typedef T acc_t; typedef T result_t; enum { HAS_INDEX = 0 };
+  static __device__ __forceinline__ acc_t init() { return (T)1; }
+  static __device__ __forceinline__ void step(acc_t &a, T x, i64) { a = a * x; }
+  static __device__ __forceinline__ void merge(acc_t &a, acc_t b) { a = a * b; }
+  static __device__ __forceinline__ acc_t warp(acc_t a) {
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) a = a * shfl_xor_t(a, m);
+    return a;
+  }
+  static __device__ __forceinline__ result_t finish(acc_t a) { return a; }
+  static __device__ __forceinline__ i64 index(acc_t) { return 0; }
+};
+template <> struct OpProd<cfloat> {
+  typedef cfloat acc_t; typedef cfloat result_t; enum { HAS_INDEX = 0 };
+  static __device__ __forceinline__ acc_t init() { return cfloat(1.f, 0.f); }
+  static __device__ __forceinline__ void step(acc_t &a, cfloat x, i64) { a = a * x; }
+  static __device__ __forceinline__ void merge(acc_t &a, acc_t b) { a = a * b; }
+  static __device__ __forceinline__ acc_t warp(acc_t a) {
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) a = a * shfl_xor_t(a, m);
+    return a;
+  }
+  static __device__ __forceinline__ result_t finish(acc_t a) { return a; }
+  static __device__ __forceinline__ i64 index(acc_t) { return 0; }
+};
+
+// max / min by value (reference: reduceOpMax / reduceOpMin, transforms/reduce.h:127-177)
+template <class T, bool IS_MAX> struct OpExt {
+  typedef T acc_t; typedef T result_t; enum { HAS_INDEX = 0 };
+  static __device__ __forceinline__ bool better(T a, T b) { return IS_MAX ? (a > b) : (a < b); }
+  static __device__ __forceinline__ acc_t init() { return IS_MAX ? Limits<T>::lowest() : Limits<T>::highest(); }
+  static __device__ __forceinline__ void step(acc_t &a, T x, i64) { a = better(x, a) ? x : a; }
+  static __device__ __forceinline__ void merge(acc_t &a, acc_t b) { a = better(b, a) ? b : a; }
+  static __device__ __forceinline__ acc_t warp(acc_t a) {
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) { T o = shfl_xor_t(a, m); a = better(o, a) ? o : a; }
+    return a;
+  }
+  static __device__ __forceinline__ result_t finish(acc_t a) { return a; }
+  static __device__ __forceinline__ i64 index(acc_t) { return 0; }
+};
+// fp32 max / min: one redux.sync.{max,min}.f32 (sm_100a) instead of five shuffle rounds.  NaN-free
+// inputs give the same value as the compare-select form; with a NaN the shuffle form is used.
+template <> __device__ __forceinline__ float OpExt<float, true>::warp(float a) {
+  float r;
+  asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(a));
+  return r;
+}
+template <> __device__ __forceinline__ float OpExt<float, false>::warp(float a) {
+  float r;
+  asm volatile("redux.sync.min.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(a));
+  return r;
+}
+template <> __device__ __forceinline__ int OpExt<int, true>::warp(int a) { return __reduce_max_sync(0xffffffffu, a); }
+template <> __device__ __forceinline__ int OpExt<int, false>::warp(int a) { return __reduce_min_sync(0xffffffffu, a); }
+
+// argmax / argmin: (value, absolute flat index), lowest index wins ties — the HostExecutor result
+// (std::max_element / std::min_element, transforms/host_algorithms.h:262-296).
+template <class T> struct __align__(16) ArgAcc { T val; i64 idx; };
+template <class T, bool IS_MAX> struct OpArg {
+  typedef ArgAcc<T> acc_t; typedef T result_t; enum { HAS_INDEX = 1 };
+  static __device__ __forceinline__ bool better(T a, T b) { return IS_MAX ? (a > b) : (a < b); }
+  static __device__ __forceinline__ acc_t init() {
+    acc_t a; a.val = IS_MAX ? Limits<T>::lowest() : Limits<T>::highest(); a.idx = 0x7fffffffffffffffLL; return a;
+  }
+  // per-thread elements arrive in increasing index order: strict compare keeps the first occurrence
+  static __device__ __forceinline__ void step(acc_t &a, T x, i64 i) {
+    if (better(x, a.val) || (a.idx == 0x7fffffffffffffffLL && x == a.val)) { a.val = x; a.idx = i; }
+  }
+  static __device__ __forceinline__ void merge(acc_t &a, acc_t b) {
+    if (better(b.val, a.val) || (b.val == a.val && b.idx < a.idx)) a = b;
+  }
+  static __device__ __forceinline__ acc_t warp(acc_t a) {
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) { acc_t o = shfl_xor_t(a, m); merge(a, o); }
+    return a;
+  }
+  static __device__ __forceinline__ result_t finish(acc_t a) { return a.val; }
+  static __device__ __forceinline__ i64 index(acc_t a) { return a.idx; }
+};
+// fp32 arg ops: the warp stage is two redux.sync — value first, then the lowest index among the
+// lanes that hold that value (u32 halves of the index, high word first).
+template <bool IS_MAX> __device__ __forceinline__ ArgAcc<float> warp_arg_f32(ArgAcc<float> a) {
+  float best;
+  if (IS_MAX) asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(best) : "f"(a.val));
+  else asm volatile("redux.sync.min.f32 %0, %1, 0xffffffff;" : "=f"(best) : "f"(a.val));
+  const bool mine = (a.val == best);
+  u32 hi = mine ? (u32)((u64)a.idx >> 32) : 0xffffffffu;
+  u32 hmin = __reduce_min_sync(0xffffffffu, hi);
+  u32 lo = (mine && hi == hmin) ? (u32)(u64)a.idx : 0xffffffffu;
+  u32 lmin = __reduce_min_sync(0xffffffffu, lo);
+  ArgAcc<float> r; r.val = best; r.idx = (i64)(((u64)hmin << 32) | (u64)lmin);
+  return r;
+}
+template <> __device__ __forceinline__ ArgAcc<float> OpArg<float, true>::warp(ArgAcc<float> a) { return warp_arg_f32<true>(a); }
+template <> __device__ __forceinline__ ArgAcc<float> OpArg<float, false>::warp(ArgAcc<float> a) { return warp_arg_f32<false>(a); }
+
+// any / all (reference: reduceOpAny / reduceOpAll, transforms/reduce.h:153-177; result is 0 / 1 in the
+// output tensor's type).  The warp stage is a vote.
+template <class T, bool IS_ANY> struct OpLogic {
+  typedef int acc_t; typedef int result_t; enum { HAS_INDEX = 0 };
+  static __device__ __forceinline__ acc_t init() { return IS_ANY ? 0 : 1; }
+  static __device__ __forceinline__ void step(acc_t &a, T x, i64) { a = IS_ANY ? (a | (int)nonzero(x)) : (a & (int)nonzero(x)); }
+  static __device__ __forceinline__ void merge(acc_t &a, acc_t b) { a = IS_ANY ? (a | b) : (a & b); }
+  static __device__ __forceinline__ acc_t warp(acc_t a) {
+    return IS_ANY ? (int)__any_sync(0xffffffffu, a) : (int)__all_sync(0xffffffffu, a);
+  }
+  static __device__ __forceinline__ result_t finish(acc_t a) { return a; }
+  static __device__ __forceinline__ i64 index(acc_t) { return 0; }
+};
+
+
+// ------------------------------------------------------------------------------------------------
+// post-processing of a finished sum (mean / var divisor, stdd sqrt) and the store
+// ------------------------------------------------------------------------------------------------
+template <class R> struct Post {
+  static __device__ __forceinline__ R go(R x, const RedParams &) { return x; }
+};
+template <> struct Post<float> {
+  static __device__ __forceinline__ float go(float x, const RedParams &p) {
+    if (p.post_div) x = x / p.post_scale_f;
+    if (p.post_sqrt) x = sqrtf(x);
+    return x;
+  }
+};
+template <> struct Post<double> {
+  static __device__ __forceinline__ double go(double x, const RedParams &p) {
+    if (p.post_div) x = x / p.post_scale_d;
+    if (p.post_sqrt) x = sqrt(x);
+    return x;
+  }
+};
+template <> struct Post<cfloat> {
+  static __device__ __forceinline__ cfloat go(cfloat x, const RedParams &p) {
+    if (p.post_div) x = x / p.post_scale_f;
+    return x;
+  }
+};
+
+// 32-byte partial record exchanged between GPUs (mxb_reduce_partial / mxb_reduce_finalize)
+struct __align__(16) PartialRec { u32 w[8]; };
+
+// flat index -> per-dim indices (row-major over n dims of sizes sz[])
+__device__ __forceinline__ void decomp(i64 flat, int n, const i64 *sz, i64 *idx) {
+#pragma unroll
+  for (int d = KMAXD - 1; d >= 0; --d) {
+    if (d < n) {
+      if (d == 0) { idx[0] = flat; }
+      else { const i64 q = flat / sz[d]; idx[d] = flat - q * sz[d]; flat = q; }
+    } else idx[d] = 0;
+  }
+}
+
+template <class Op, class OutT>
+__device__ __forceinline__ void store_result(const RedParams &p, i64 b, typename Op::acc_t acc) {
+  if (p.raw_partial) {
+    union { PartialRec rec; typename Op::acc_t a; } u;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) u.rec.w[i] = 0;
+    u.a = acc;
+    ((PartialRec *)p.out.ptr)[b] = u.rec;
+    return;
+  }
+  i64 bidx[KMAXD];
+  decomp(b, p.nb, p.bsz, bidx);
+  i64 oo = 0, io = 0;
+#pragma unroll
+  for (int d = 0; d < KMAXD; ++d) {
+    if (d < p.nb) { oo += bidx[d] * p.out.bs[d]; io += bidx[d] * p.idx.bs[d]; }
+  }
+  typename Op::result_t r = Post<typename Op::result_t>::go(Op::finish(acc), p);
+  ((OutT *)p.out.ptr)[oo] = cvt<OutT>(r);
+  if (Op::HAS_INDEX) {
+    i64 ix = Op::index(acc);
+    // nothing compared better than the identity (row of -inf / +inf): first element, as std::max_element
+    if (ix == 0x7fffffffffffffffLL) {
+      i64 fb = 0;
+#pragma unroll
+      for (int d = 0; d < KMAXD; ++d) if (d < p.nb) fb += bidx[d] * p.bflat[d];
+      ix = p.idx_base + fb * p.R;
+    }
+    ((i64 *)p.idx.ptr)[io] = ix;
+  }
+}
+
+// read a record another CTA wrote during this launch (L2, never a stale L1 line)
+template <class T> __device__ __forceinline__ T ld_cg_t(const T *p) {
+  enum { W = sizeof(T) / 4 };
+  union { T t; u32 w[W]; } u;
+#pragma unroll
+  for (int i = 0; i < W; ++i) u.w[i] = __ldcg((const u32 *)p + i);
+  return u.t;
+}
+template <class T> __device__ __forceinline__ void st_cg_t(T *p, T v) {
+  enum { W = sizeof(T) / 4 };
+  union { T t; u32 w[W]; } u;
+  u.t = v;
+#pragma unroll
+  for (int i = 0; i < W; ++i) __stcg((u32 *)p + i, u.w[i]);
+}
+
+// CTA-wide merge; result valid in thread 0.  `smem` holds one acc_t per warp (32 max).
+template <class Op> __device__ __forceinline__ typename Op::acc_t cta_merge(typename Op::acc_t a, typename Op::acc_t *smem) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+  a = Op::warp(a);
+  if (nwarp == 1) return a;
+  __syncthreads();  // previous use of smem is over
+  if (lane == 0) smem[warp] = a;
+  __syncthreads();
+  if (warp == 0) {
+    typename Op::acc_t v = (lane < nwarp) ? smem[lane] : Op::init();
+    a = Op::warp(v);
+  }
+  return a;
+}
+
+// per-leaf byte offset of an outer (non-innermost) reduce index
+template <class E>
+__device__ __forceinline__ void outer_bases(const RedParams &p, i64 o, const char *const *base, const char **rb) {
+  i64 oidx[KMAXD];
+  decomp(o, p.nr - 1, p.rsz, oidx);
+#pragma unroll
+  for (int k = 0; k < E::NL; ++k) {
+    i64 off = 0;
+#pragma unroll
+    for (int d = 0; d < KMAXD - 1; ++d) if (d < p.nr - 1) off += oidx[d] * p.leaf[k].rs[d];
+    rb[k] = base[k] + off * E::leaf_bytes(k);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1: reduce_inner — rows whose innermost reduce dim is the vector dim (unit stride or broadcast in
+// every leaf when V > 1; any stride when V == 1, which makes V == 1 the universal fallback).
+//
+// TEAM == 0: one CTA — or `splits` CTAs — per row.  Thread stage: V lane accumulators, U vector
+//   loads per leaf in flight.  Warp stage: shuffle / redux.sync / vote.  CTA stage: shared memory.
+//   Grid stage (splits > 1), same launch: each CTA drops its partial in the workspace and takes a
+//   ticket; the last to arrive folds the partials in a fixed order (deterministic) and stores.  The
+//   ticket is an atomicInc that wraps to zero, so no memset is needed between launches.
+// TEAM == 1: one warp per row, no shared memory, no barrier (short rows).
+// ------------------------------------------------------------------------------------------------
+template <class E, class Op, class OutT, int V, int U, int TEAM>
+__device__ __forceinline__ void reduce_inner_body(const RedParams &p) {
+  typedef typename Op::acc_t acc_t;
+  __shared__ acc_t s_acc[32];
+  __shared__ int s_last;
+
+  const int nthr = TEAM == 0 ? (int)blockDim.x : 32;
+  const int tid = TEAM == 0 ? (int)threadIdx.x : (int)(threadIdx.x & 31);
+  const i64 team0 = TEAM == 0 ? (i64)blockIdx.x : (i64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const i64 nteam = TEAM == 0 ? (i64)gridDim.x : (i64)gridDim.x * (blockDim.x >> 5);
+  const int nr = p.nr;
+  const i64 L = p.rsz[nr - 1];  // innermost run
+  const i64 Lv = L / V;         // full vectors per run
+  const i64 tail = L - Lv * V;  // leftover scalars per run
+  const i64 O = p.R / L;        // runs per row
+  const i64 S = TEAM == 0 ? (i64)p.splits : 1;
+  const i64 work = p.B * S;
+
+  for (i64 w = team0; w < work; w += nteam) {
+    const i64 b = w / S;
+    const i64 s = w - b * S;
+    const char *base[E::NL];
+    i64 inner[E::NL];
+    i64 row0 = p.idx_base;  // flat index of the row's first element
+    {
+      i64 bidx[KMAXD];
+      decomp(b, p.nb, p.bsz, bidx);
+#pragma unroll
+      for (int k = 0; k < E::NL; ++k) {
+        i64 off = 0;
+#pragma unroll
+        for (int d = 0; d < KMAXD; ++d) if (d < p.nb) off += bidx[d] * p.leaf[k].bs[d];
+        base[k] = (const char *)p.leaf[k].ptr + off * E::leaf_bytes(k);
+        inner[k] = p.leaf[k].rs[nr - 1];
+      }
+      if (Op::HAS_INDEX) {
+#pragma unroll
+        for (int d = 0; d < KMAXD; ++d) if (d < p.nb) row0 += bidx[d] * p.bflat[d] * p.R;
+      }
+    }
+    acc_t acc[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) acc[v] = Op::init();
+
+    // vector steps of the row: q = o * Lv + jv; this split owns [q0, q1)
+    const i64 Q = O * Lv;
+    const i64 per = (Q + S - 1) / S;
+    const i64 q0 = s * per;
+    const i64 q1 = (q0 + per < Q) ? (q0 + per) : Q;
+
+    if (nr == 1) {
+      i64 q = q0 + tid;
+      for (; q + (i64)(U - 1) * nthr < q1; q += (i64)U * nthr) {
+        typename E::template Regs<V> r[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) E::template loadv<V>(r[u], base, inner, (q + (i64)u * nthr) * V);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const i64 j0 = (q + (i64)u * nthr) * V;
+#pragma unroll
+          for (int v = 0; v < V; ++v) Op::step(acc[v], E::template eval<V>(r[u], v, p.c), row0 + j0 + v);
+        }
+      }
+      for (; q < q1; q += nthr) {
+        typename E::template Regs<V> r;
+        E::template loadv<V>(r, base, inner, q * V);
+#pragma unroll
+        for (int v = 0; v < V; ++v) Op::step(acc[v], E::template eval<V>(r, v, p.c), row0 + q * V + v);
+      }
+    } else {
+      for (i64 q = q0 + tid; q < q1; q += nthr) {
+        const i64 o = q / Lv, jv = q - o * Lv;
+        const char *rb[E::NL];
+        outer_bases<E>(p, o, base, rb);
+        typename E::template Regs<V> r;
+        E::template loadv<V>(r, rb, inner, jv * V);
+#pragma unroll
+        for (int v = 0; v < V; ++v) Op::step(acc[v], E::template eval<V>(r, v, p.c), row0 + o * L + jv * V + v);
+      }
+    }
+    // scalar tails of the runs (L % V elements each), taken by split 0
+    if (V > 1 && tail > 0 && s == 0) {
+      const i64 nt = O * tail;
+      for (i64 t = tid; t < nt; t += nthr) {
+        const i64 o = t / tail, j = Lv * V + (t - o * tail);
+        const char *rb[E::NL];
+        outer_bases<E>(p, o, base, rb);
+        typename E::template Regs<1> r;
+        E::template loadv<1>(r, rb, inner, j);
+        // this index may precede ones the thread already folded: merge, do not step
+        acc_t one = Op::init();
+        Op::step(one, E::template eval<1>(r, 0, p.c), row0 + o * L + j);
+        Op::merge(acc[0], one);
+      }
+    }
+#pragma unroll
+    for (int v = 1; v < V; ++v) Op::merge(acc[0], acc[v]);
+
+    if (TEAM == 1) {
+      acc_t tot = Op::warp(acc[0]);
+      if (tid == 0) store_result<Op, OutT>(p, b, tot);
+    } else {
+      acc_t tot = cta_merge<Op>(acc[0], s_acc);
+      if (S == 1) {
+        if (tid == 0) store_result<Op, OutT>(p, b, tot);
+      } else {
+        acc_t *ws = (acc_t *)p.ws;
+        if (tid == 0) {
+          st_cg_t(&ws[b * S + s], tot);
+          __threadfence();
+          const u32 t = atomicInc(&p.tickets[b], (u32)(S - 1));
+          s_last = (t == (u32)(S - 1));
+        }
+        __syncthreads();
+        if (s_last) {
+          __threadfence();
+          acc_t a = Op::init();
+          for (i64 i = tid; i < S; i += nthr) Op::merge(a, ld_cg_t(&ws[b * S + i]));
+          a = cta_merge<Op>(a, s_acc);
+          if (tid == 0) store_result<Op, OutT>(p, b, a);
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2: reduce_outer — the reduce dims are strided and a BATCH dim is the vector dim (unit stride in
+// every leaf): column sums, `sum(permute(t,{2,0,1}),{2})`.  The host rotates that batch dim to the
+// last batch position of the parameter block (strides travel with it, so nothing is copied) and the
+// output strides follow.  A CTA is blockDim.x/TY column groups x TY reduce lanes; each thread owns V
+// adjacent columns, walks the reduce index with stride TY (U loads in flight), keeps V accumulators
+// in registers, and the TY partials meet in shared memory.  Loads stay coalesced along the unit-stride
+// dim however the reduce dims are strided.
+// ------------------------------------------------------------------------------------------------
+template <class E, class Op, class OutT, int V, int U>
+__device__ __forceinline__ void reduce_outer_body(const RedParams &p) {
+  typedef typename Op::acc_t acc_t;
+  extern __shared__ __align__(16) unsigned char s_dyn[];
+  acc_t *s_part = (acc_t *)s_dyn;  // [TY][TX*V]
+
+  const int TX = p.tx, TY = (int)blockDim.x / TX;
+  const int tx = (int)threadIdx.x % TX, ty = (int)threadIdx.x / TX;
+  const int nb = p.nb, nr = p.nr;
+  const i64 C = p.bsz[nb - 1];                 // vector (column) dim extent
+  const i64 tile = (i64)TX * V;                // columns per CTA
+  const i64 ctiles = (C + tile - 1) / tile;
+  const i64 Bo = p.B / C;                      // product of the other batch dims
+  const i64 work = Bo * ctiles;
+
+  for (i64 w = blockIdx.x; w < work; w += gridDim.x) {
+    const i64 bo = w / ctiles, ct = w - bo * ctiles;
+    const i64 c0 = ct * tile + (i64)tx * V;    // first column of this thread
+    const bool active = c0 < C;
+    const bool fullvec = c0 + V <= C;
+    const char *base[E::NL];
+    i64 inner[E::NL];
+    i64 bidx[KMAXD];
+    decomp(bo, nb - 1, p.bsz, bidx);
+#pragma unroll
+    for (int k = 0; k < E::NL; ++k) {
+      i64 off = 0;
+#pragma unroll
+      for (int d = 0; d < KMAXD - 1; ++d) if (d < nb - 1) off += bidx[d] * p.leaf[k].bs[d];
+      base[k] = (const char *)p.leaf[k].ptr + off * E::leaf_bytes(k);
+      inner[k] = p.leaf[k].bs[nb - 1];
+    }
+    acc_t acc[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) acc[v] = Op::init();
+    // flat index of (batch row, reduce r) = (sum_d bidx[d]*bflat[d]) * R + r; column c adds c*bflat[nb-1]
+    i64 rowflat = p.idx_base + c0 * p.bflat[nb - 1] * p.R;
+    if (Op::HAS_INDEX) {
+#pragma unroll
+      for (int d = 0; d < KMAXD - 1; ++d) if (d < nb - 1) rowflat += bidx[d] * p.bflat[d] * p.R;
+    }
+    const i64 colflat = p.bflat[nb - 1] * p.R;  // flat-index step between adjacent columns
+
+    if (active) {
+      if (fullvec) {
+        i64 r = ty;
+        for (; r + (i64)(U - 1) * TY < p.R; r += (i64)U * TY) {
+          typename E::template Regs<V> reg[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const char *rb[E::NL];
+            if (nr == 1) {
+#pragma unroll
+              for (int k = 0; k < E::NL; ++k) rb[k] = base[k] + (r + (i64)u * TY) * p.leaf[k].rs[0] * E::leaf_bytes(k);
+            } else {
+              i64 ridx[KMAXD];
+              decomp(r + (i64)u * TY, nr, p.rsz, ridx);
+#pragma unroll
+              for (int k = 0; k < E::NL; ++k) {
+                i64 off = 0;
+#pragma unroll
+                for (int d = 0; d < KMAXD; ++d) if (d < nr) off += ridx[d] * p.leaf[k].rs[d];
+                rb[k] = base[k] + off * E::leaf_bytes(k);
+              }
+            }
+            E::template loadv<V>(reg[u], rb, inner, c0);
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+#pragma unroll
+            for (int v = 0; v < V; ++v)
+              Op::step(acc[v], E::template eval<V>(reg[u], v, p.c), rowflat + (i64)v * colflat + r + (i64)u * TY);
+          }
+        }
+        for (; r < p.R; r += TY) {
+          const char *rb[E::NL];
+          i64 ridx[KMAXD];
+          decomp(r, nr, p.rsz, ridx);
+#pragma unroll
+          for (int k = 0; k < E::NL; ++k) {
+            i64 off = 0;
+#pragma unroll
+            for (int d = 0; d < KMAXD; ++d) if (d < nr) off += ridx[d] * p.leaf[k].rs[d];
+            rb[k] = base[k] + off * E::leaf_bytes(k);
+          }
+          typename E::template Regs<V> reg;
+          E::template loadv<V>(reg, rb, inner, c0);
+#pragma unroll
+          for (int v = 0; v < V; ++v) Op::step(acc[v], E::template eval<V>(reg, v, p.c), rowflat + (i64)v * colflat + r);
+        }
+      } else {
+        // ragged last vector of the column dim: scalar lanes
+        for (i64 r = ty; r < p.R; r += TY) {
+          const char *rb[E::NL];
+          i64 ridx[KMAXD];
+          decomp(r, nr, p.rsz, ridx);
+#pragma unroll
+          for (int k = 0; k < E::NL; ++k) {
+            i64 off = 0;
+#pragma unroll
+            for (int d = 0; d < KMAXD; ++d) if (d < nr) off += ridx[d] * p.leaf[k].rs[d];
+            rb[k] = base[k] + off * E::leaf_bytes(k);
+          }
+#pragma unroll
+          for (int v = 0; v < V; ++v) {
+            if (c0 + v < C) {
+              typename E::template Regs<1> reg;
+              E::template loadv<1>(reg, rb, inner, c0 + v);
+              Op::step(acc[v], E::template eval<1>(reg, 0, p.c), rowflat + (i64)v * colflat + r);
+            }
+          }
+        }
+      }
+    }
+    // TY partials per column meet in shared memory (fixed order: ty = 0, 1, ...)
+    if (TY > 1) {
+      __syncthreads();
+#pragma unroll
+      for (int v = 0; v < V; ++v) s_part[(ty * TX + tx) * V + v] = acc[v];
+      __syncthreads();
+      if (ty == 0) {
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          acc_t a = acc[v];
+          for (int y = 1; y < TY; ++y) Op::merge(a, s_part[(y * TX + tx) * V + v]);
+          acc[v] = a;
+        }
+      }
+    }
+    if (ty == 0 && active) {
+#pragma unroll
+      for (int v = 0; v < V; ++v)
+        if (c0 + v < C) store_result<Op, OutT>(p, bo * C + c0 + v, acc[v]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3: var_inner_smem — variance / standard deviation of rows that fit in shared memory, with the
+// reference's exact two-pass arithmetic (transforms/reduce.h:1406-1444: mean, then the sum of
+// |x - mean|^2, then / (N - ddof)) but ONE read of the row from HBM: pass 1 evaluates the expression,
+// parks the values in shared memory and sums them; pass 2 re-reads shared memory only.
+// ------------------------------------------------------------------------------------------------
+template <class T> struct AbsDev2 {
+  typedef T real_t;
+  static __device__ __forceinline__ T go(T x, T m) { const T d = x - m; return d * d; }
+};
+template <> struct AbsDev2<cfloat> {
+  typedef float real_t;
+  static __device__ __forceinline__ float go(cfloat x, cfloat m) { const float a = x.re - m.re, b = x.im - m.im; return a * a + b * b; }
+};
+template <class T> struct MeanDiv {
+  static __device__ __forceinline__ T go(T s, i64 n) { return s / (T)n; }
+};
+template <> struct MeanDiv<cfloat> {
+  static __device__ __forceinline__ cfloat go(cfloat s, i64 n) { return s / (float)n; }
+};
+
+template <class E, class OutT, int V, int U>
+__device__ __forceinline__ void var_inner_smem_body(const RedParams &p) {
+  typedef typename E::value_type T;
+  typedef typename AbsDev2<T>::real_t RT;
+  extern __shared__ __align__(16) unsigned char s_dyn[];
+  T *s_row = (T *)s_dyn;  // [R]
+  __shared__ T s_sum[32];
+  __shared__ RT s_sq[32];
+  __shared__ T s_mean;
+
+  const int nthr = blockDim.x, tid = threadIdx.x;
+  const int nr = p.nr;
+  const i64 L = p.rsz[nr - 1], Lv = L / V, tail = L - Lv * V, O = p.R / L;
+
+  for (i64 b = blockIdx.x; b < p.B; b += gridDim.x) {
+    const char *base[E::NL];
+    i64 inner[E::NL];
+    {
+      i64 bidx[KMAXD];
+      decomp(b, p.nb, p.bsz, bidx);
+#pragma unroll
+      for (int k = 0; k < E::NL; ++k) {
+        i64 off = 0;
+#pragma unroll
+        for (int d = 0; d < KMAXD; ++d) if (d < p.nb) off += bidx[d] * p.leaf[k].bs[d];
+        base[k] = (const char *)p.leaf[k].ptr + off * E::leaf_bytes(k);
+        inner[k] = p.leaf[k].rs[nr - 1];
+      }
+    }
+    T acc[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) acc[v] = OpSum<T>::init();
+    const i64 Q = O * Lv;
+    if (nr == 1) {
+      i64 q = tid;
+      for (; q + (i64)(U - 1) * nthr < Q; q += (i64)U * nthr) {
+        typename E::template Regs<V> r[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) E::template loadv<V>(r[u], base, inner, (q + (i64)u * nthr) * V);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          Vec<T, V> x;
+#pragma unroll
+          for (int v = 0; v < V; ++v) { x.v[v] = E::template eval<V>(r[u], v, p.c); acc[v] = acc[v] + x.v[v]; }
+          *(Vec<T, V> *)(s_row + (q + (i64)u * nthr) * V) = x;
+        }
+      }
+      for (; q < Q; q += nthr) {
+        typename E::template Regs<V> r;
+        E::template loadv<V>(r, base, inner, q * V);
+        Vec<T, V> x;
+#pragma unroll
+        for (int v = 0; v < V; ++v) { x.v[v] = E::template eval<V>(r, v, p.c); acc[v] = acc[v] + x.v[v]; }
+        *(Vec<T, V> *)(s_row + q * V) = x;
+      }
+    } else {
+      for (i64 q = tid; q < Q; q += nthr) {
+        const i64 o = q / Lv, jv = q - o * Lv;
+        const char *rb[E::NL];
+        outer_bases<E>(p, o, base, rb);
+        typename E::template Regs<V> r;
+        E::template loadv<V>(r, rb, inner, jv * V);
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          const T x = E::template eval<V>(r, v, p.c);
+          acc[v] = acc[v] + x;
+          s_row[o * L + jv * V + v] = x;
+        }
+      }
+    }
+    if (V > 1 && tail > 0) {
+      const i64 nt = O * tail;
+      for (i64 t = tid; t < nt; t += nthr) {
+        const i64 o = t / tail, j = Lv * V + (t - o * tail);
+        const char *rb[E::NL];
+        outer_bases<E>(p, o, base, rb);
+        typename E::template Regs<1> r;
+        E::template loadv<1>(r, rb, inner, j);
+        const T x = E::template eval<1>(r, 0, p.c);
+        acc[0] = acc[0] + x;
+        s_row[o * L + j] = x;
+      }
+    }
+#pragma unroll
+    for (int v = 1; v < V; ++v) acc[0] = acc[0] + acc[v];
+    T tot = cta_merge<OpSum<T> >(acc[0], s_sum);
+    if (tid == 0) s_mean = MeanDiv<T>::go(tot, p.R);
+    __syncthreads();  // also orders the s_row writes before pass 2
+    const T mean = s_mean;
+    RT sq = (RT)0;
+    for (i64 i = tid; i < p.R; i += nthr) sq += AbsDev2<T>::go(s_row[i], mean);
+    sq = cta_merge<OpSum<RT> >(sq, s_sq);
+    if (tid == 0) {
+      RT r = sq / (RT)p.post_scale_d;
+      if (p.post_sqrt) r = f_sqrt(r);
+      i64 bidx[KMAXD];
+      decomp(b, p.nb, p.bsz, bidx);
+      i64 oo = 0;
+#pragma unroll
+      for (int d = 0; d < KMAXD; ++d) if (d < p.nb) oo += bidx[d] * p.out.bs[d];
+      ((OutT *)p.out.ptr)[oo] = cvt<OutT>(r);
+    }
+    __syncthreads();  // s_row / s_mean are reused by the next row
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// E1: elementwise — out(idx) = expr(idx).  Persistent grid-stride over V-wide vectors of the innermost
+// dim (LDG.128/256 per leaf, each distinct leaf loaded once, STG.128/256), U vectors per thread in
+// flight; V == 1 takes any strides.  Replaces the one-vector-per-thread generic kernels of
+// executors/kernel.h:41-223.
+// ------------------------------------------------------------------------------------------------
+template <class E, class OutT, int V>
+__device__ __forceinline__ void ew_store(const EwParams &p, char *obase, i64 oinner, i64 j, const typename E::template Regs<V> &r) {
+  Vec<OutT, V> o;
+#pragma unroll
+  for (int v = 0; v < V; ++v) o.v[v] = cvt<OutT>(E::template eval<V>(r, v, p.c));
+  if (V == 1) ((OutT *)obase)[j * oinner] = o.v[0];
+  else StBytes<(int)sizeof(OutT) * V>::st((OutT *)obase + j, &o);
+}
+
+template <class E, class OutT, int V, int U>
+__device__ __forceinline__ void ew_body(const EwParams &p) {
+  const int nd = p.nd;
+  const i64 L = p.sz[nd - 1], Lv = L / V, tail = L - Lv * V, O = p.N / L;
+  const i64 Q = O * Lv;
+  const i64 nthr = (i64)gridDim.x * blockDim.x;
+  const i64 t0 = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  i64 inner[E::NL];
+#pragma unroll
+  for (int k = 0; k < E::NL; ++k) inner[k] = p.leaf[k].bs[nd - 1];
+  const i64 oinner = p.out.bs[nd - 1];
+
+  if (nd == 1) {
+    const char *base[E::NL];
+#pragma unroll
+    for (int k = 0; k < E::NL; ++k) base[k] = (const char *)p.leaf[k].ptr;
+    i64 q = t0;
+    for (; q + (i64)(U - 1) * nthr < Q; q += (i64)U * nthr) {
+      typename E::template Regs<V> r[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) E::template loadv<V>(r[u], base, inner, (q + (i64)u * nthr) * V);
+#pragma unroll
+      for (int u = 0; u < U; ++u) ew_store<E, OutT, V>(p, (char *)p.out.ptr, oinner, (q + (i64)u * nthr) * V, r[u]);
+    }
+    for (; q < Q; q += nthr) {
+      typename E::template Regs<V> r;
+      E::template loadv<V>(r, base, inner, q * V);
+      ew_store<E, OutT, V>(p, (char *)p.out.ptr, oinner, q * V, r);
+    }
+  } else {
+    for (i64 q = t0; q < Q; q += nthr) {
+      const i64 o = q / Lv, jv = q - o * Lv;
+      i64 oidx[KMAXD];
+      decomp(o, nd - 1, p.sz, oidx);
+      const char *base[E::NL];
+#pragma unroll
+      for (int k = 0; k < E::NL; ++k) {
+        i64 off = 0;
+#pragma unroll
+        for (int d = 0; d < KMAXD - 1; ++d) if (d < nd - 1) off += oidx[d] * p.leaf[k].bs[d];
+        base[k] = (const char *)p.leaf[k].ptr + off * E::leaf_bytes(k);
+      }
+      i64 ooff = 0;
+#pragma unroll
+      for (int d = 0; d < KMAXD - 1; ++d) if (d < nd - 1) ooff += oidx[d] * p.out.bs[d];
+      typename E::template Regs<V> r;
+      E::template loadv<V>(r, base, inner, jv * V);
+      ew_store<E, OutT, V>(p, (char *)p.out.ptr + ooff * (i64)sizeof(OutT), oinner, jv * V, r);
+    }
+  }
+  if (V > 1 && tail > 0) {
+    const i64 nt = O * tail;
+    for (i64 t = t0; t < nt; t += nthr) {
+      const i64 o = t / tail, j = Lv * V + (t - o * tail);
+      i64 oidx[KMAXD];
+      decomp(o, nd - 1, p.sz, oidx);
+      const char *base[E::NL];
+#pragma unroll
+      for (int k = 0; k < E::NL; ++k) {
+        i64 off = 0;
+#pragma unroll
+        for (int d = 0; d < KMAXD - 1; ++d) if (d < nd - 1) off += oidx[d] * p.leaf[k].bs[d];
+        base[k] = (const char *)p.leaf[k].ptr + off * E::leaf_bytes(k);
+      }
+      i64 ooff = 0;
+#pragma unroll
+      for (int d = 0; d < KMAXD - 1; ++d) if (d < nd - 1) ooff += oidx[d] * p.out.bs[d];
+      typename E::template Regs<1> r;
+      E::template loadv<1>(r, base, inner, j);
+      ew_store<E, OutT, 1>(p, (char *)p.out.ptr + ooff * (i64)sizeof(OutT), oinner, j, r);
+    }
+  }
+}
+
+}  // namespace mxb
