@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""bench.py — the headline measurement (BASELINE.json: "reduce/fused-elementwise HBM GB/s (% of B200 peak) and
+elements/sec at 1/2/4/8 GPU").
+
+Workload (config 2 of BASELINE.json, the configuration the metric is quoted on): full-tensor `sum`, `max` and
+`argmax` of a 2^30-element fp32 tensor.  A step = those three MatX statements, each reading the whole tensor
+(4 GiB, far larger than the 126 MB L2, so no flush is needed between iterations).  With N > 1 ranks the tensor is
+slab-sharded (strong scaling, total work fixed): every rank reduces its slab into 32-byte partial records, ONE
+NCCL all-gather over NVLink exchanges them, and every rank folds them in rank order.
+
+    python bench.py --gpus N --steps K --warmup W          # this repo's CUDA path
+    python bench.py --impl reference ...                   # the reference's HostExecutor on the host cores
+
+`value` = algorithmic bytes of the whole job / device time (inputs resident in HBM); `e2e` = the same through the
+public API with HOST buffers (pinned host -> device copy of the input and device -> host read of the results inside
+the timed region).  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_ELEMS = 1 << 30
+OPS = ("sum", "max", "argmax")
+METRIC = "reduce/fused-elementwise HBM GB/s"
+UNIT = "GB/s"
+
+
+def algorithmic_bytes(n: int) -> int:
+    # per statement: every input element read once + the outputs written once
+    return 3 * n * 4 + (4 + 4 + 4 + 8)
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+    return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx_, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx_ = float(r[1])
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx_, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------------------
+# reference arm: matx::HostExecutor<ThreadsMode::ALL> compiled from /root/reference (oracle/_ref), host cores only
+# --------------------------------------------------------------------------------------------------------------
+def cpu_reference_pass(ref, x, n: int):
+    """One pass = the three statements on the first n elements; returns seconds."""
+    import numpy as np
+    from matx_b200 import _abi as A
+    out = np.zeros((), np.float32)
+    idx = np.zeros((), np.int64)
+    t0 = time.perf_counter()
+    for op in (A.RED_SUM, A.RED_MAX, A.RED_ARGMAX):
+        rc = ref.reduce(op, x.ctypes.data, A.F32, [n], [1], [0], out.ctypes.data, idx.ctypes.data, 1, mode=1)
+        if rc != 0:
+            raise RuntimeError("reference statement failed (%d)" % rc)
+    return time.perf_counter() - t0
+
+
+def load_reference():
+    from tests import oracle_harness as H
+    ref = H.load_ref_host()
+    if ref is None:
+        raise RuntimeError("oracle/_ref/libmatx_ref_host.so is missing (build it here with `python oracle/build_ref.py`)")
+    f = ref.fn("mref_threads")
+    return ref, int(f())
+
+
+def run_reference(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import numpy as np
+    ref, cores = load_reference()
+    n = 1 << 28  # bounded sample of the workload: 1 GiB of the 4 GiB tensor
+    rng = np.random.default_rng(4)
+    x = rng.random(n, dtype=np.float32)
+    for _ in range(max(1, args.warmup)):
+        cpu_reference_pass(ref, x, n)
+    ts = [cpu_reference_pass(ref, x, n) for _ in range(args.steps)]
+    t = sum(ts) / len(ts)
+    val = algorithmic_bytes(n) / t / 1e9
+    sample = "first 2^28 of the 2^30 fp32 elements, sum+max+argmax per step, HostExecutor<ThreadsMode::ALL>"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "elements_per_sec": 3 * n / t,
+        "config": {"workload": "C2: full-tensor sum/max/argmax, fp32 2^30 elements (reference arm runs a 2^28 sample per step)"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# this repo's arm
+# --------------------------------------------------------------------------------------------------------------
+def run_ours(args) -> None:
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from matx_b200 import _abi as A
+    from matx_b200 import ops as mx
+    from matx_b200 import dist as mxd
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    ex = mx.CudaExecutor()
+    start, count = mxd.slab(N_ELEMS, rank, world)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(4 + rank)
+    x = torch.rand(count, device=dev, dtype=torch.float32, generator=gen)
+    tx = mx.make_tensor(x)
+    o_sum = torch.zeros((), device=dev)
+    o_max = torch.zeros((), device=dev)
+    o_amax = torch.zeros((), device=dev)
+    o_idx = torch.zeros((), device=dev, dtype=torch.int64)
+    sharded = mxd.ShardedFullReduce(ex, world, rank) if world > 1 else None
+
+    def step():
+        if world == 1:
+            mx.make_tensor(o_sum).set(mx.sum(tx)).run(ex)
+            mx.make_tensor(o_max).set(mx.max(tx)).run(ex)
+            mx.mtie(mx.make_tensor(o_amax), mx.make_tensor(o_idx)).set(mx.argmax(tx)).run(ex)
+        else:
+            sharded.run([(A.RED_SUM, o_sum, None), (A.RED_MAX, o_max, None), (A.RED_ARGMAX, o_amax, o_idx)], tx, start, N_ELEMS)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    barrier()
+
+    # ---- correctness of what is being timed (full size, fp64 truth on the device) ----
+    tsum = x.double().sum()
+    tmax = x.max()
+    if world > 1:
+        dist.all_reduce(tsum)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    assert abs(o_sum.item() - tsum.item()) <= 1e-5 * tsum.item(), (o_sum.item(), tsum.item())
+    assert o_max.item() == tmax.item() and o_amax.item() == tmax.item()
+    gi = o_idx.item()
+    if start <= gi < start + count:
+        assert x[gi - start].item() == tmax.item()
+        assert not bool((x[:gi - start] == tmax).any().item()), "argmax is not the lowest index"
+
+    # ---- timed region: K steps, CUDA events on the launching stream, max over ranks ----
+    sampler = ClockSampler(local_rank)
+    l0 = ex.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    sampler.start()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    launches = ex.launch_count() - l0
+    tms = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms_step = tms.item() / args.steps
+    value = algorithmic_bytes(N_ELEMS) / (ms_step * 1e-3) / 1e9
+
+    # ---- roofline of the dominant kernel (per-launch CUDA-event duration inside this process) ----
+    peak, peak_src = measured_peak()
+    per_kernel = {}
+    for name in OPS:
+        evs = []
+        for _ in range(10):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            if name == "sum":
+                mx.make_tensor(o_sum).set(mx.sum(tx)).run(ex)
+            elif name == "max":
+                mx.make_tensor(o_max).set(mx.max(tx)).run(ex)
+            else:
+                mx.mtie(mx.make_tensor(o_amax), mx.make_tensor(o_idx)).set(mx.argmax(tx)).run(ex)
+            b.record()
+            evs.append((a, b))
+        torch.cuda.synchronize()
+        ts = [a.elapsed_time(b) for a, b in evs]
+        per_kernel[name] = {"ms_avg": sum(ts) / len(ts), "ms_best": min(ts), "kernel": ex.last_kernel(),
+                            "GBps": (count * 4 + 16) / (sum(ts) / len(ts) * 1e-3) / 1e9}
+    dom = per_kernel["sum"]
+    roofline = {"bound": "hbm", "achieved": dom["GBps"], "peak": peak, "unit": "GB/s", "frac": dom["GBps"] / peak,
+                "traffic": None, "kernel": dom["kernel"], "peak_source": peak_src, "frac_of_nominal_8000": dom["GBps"] / 8000.0,
+                "per_kernel": per_kernel}
+
+    # ---- e2e: host buffers through the public API, H2D of the input + D2H of the results inside the timed region ----
+    e2e = None
+    if not args.no_e2e:
+        hx = torch.empty(count, dtype=torch.float32, pin_memory=True)
+        hx.copy_(x)
+        hres = torch.empty(4, dtype=torch.float64, pin_memory=True)
+        xd = torch.empty_like(x)
+        txd = mx.make_tensor(xd)
+        pack = torch.zeros(4, device=dev, dtype=torch.float64)
+
+        def e2e_step():
+            xd.copy_(hx, non_blocking=True)
+            if world == 1:
+                mx.make_tensor(o_sum).set(mx.sum(txd)).run(ex)
+                mx.make_tensor(o_max).set(mx.max(txd)).run(ex)
+                mx.mtie(mx.make_tensor(o_amax), mx.make_tensor(o_idx)).set(mx.argmax(txd)).run(ex)
+            else:
+                sharded.run([(A.RED_SUM, o_sum, None), (A.RED_MAX, o_max, None), (A.RED_ARGMAX, o_amax, o_idx)], txd, start, N_ELEMS)
+            pack[0], pack[1], pack[2], pack[3] = o_sum, o_max, o_amax, o_idx
+            hres.copy_(pack, non_blocking=True)
+            torch.cuda.synchronize()
+            return hres
+
+        e2e_steps = max(2, min(args.steps, 5))
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        barrier()
+        dt = (time.perf_counter() - t0) / e2e_steps
+        tdt = torch.tensor([dt], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tdt, op=dist.ReduceOp.MAX)
+        e2e = {"value": algorithmic_bytes(N_ELEMS) / tdt.item() / 1e9, "unit": UNIT, "h2d_bytes_per_step": count * 4,
+               "d2h_bytes_per_step": 32, "ms_per_step": tdt.item() * 1e3, "steps": e2e_steps,
+               "note": "bound by the host->device copy of the 4 GiB input (PCIe), not by the kernels"}
+        del hx, xd
+
+    # ---- CPU baseline beside it: the reference's HostExecutor on this box's host cores (rank 0, N = 1 only) ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        try:
+            ref, cores = load_reference()
+            n = 1 << 28
+            hxs = np.random.default_rng(4).random(n, dtype=np.float32)
+            cpu_reference_pass(ref, hxs, n)
+            reps, t_acc = 0, 0.0
+            while t_acc < 10.0 and reps < 50:
+                t_acc += cpu_reference_pass(ref, hxs, n)
+                reps += 1
+            cpu = {"value": algorithmic_bytes(n) / (t_acc / reps) / 1e9, "unit": UNIT, "cores": cores, "kind": "reference",
+                   "sample": "first 2^28 of the 2^30 elements, %d passes of sum+max+argmax, matx::HostExecutor<ThreadsMode::ALL>" % reps}
+        except Exception as exc:  # the checker is optional for the GPU number; say why it is absent
+            cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference", "sample": "unavailable: %s" % exc}
+
+    others = None
+    if rank == 0 and world == 1 and args.all_configs:
+        del x, tx
+        torch.cuda.empty_cache()
+        from matx_b200 import bench_configs
+        others = bench_configs.run_all(ex, peak)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "elements_per_sec": 3 * N_ELEMS / (ms_step * 1e-3),
+            "config": {"workload": "C2: full-tensor sum + max + argmax, fp32 2^30 elements" +
+                       ("" if world == 1 else ", slab-sharded over %d GPUs, one NCCL all-gather of 96 B per rank per step" % world),
+                       "l2": "inputs (4 GiB per statement) are larger than L2; no flush between iterations",
+                       "parallelism": "slab%d" % world},
+            "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu,
+        }
+        if others is not None:
+            line["other_configs"] = others
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--all-configs", action="store_true", help="also time configs 1, 3, 4, 5 (reported under other_configs)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

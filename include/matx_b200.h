@@ -176,13 +176,15 @@ int mxb_reduce(mxb_handle_t h, int reduce_op, const mxb_expr_t *expr, int n_redu
  * 32-byte device record, the host exchanges the records with ONE collective (NCCL all-gather of
  * world*32 bytes), and mxb_reduce_finalize folds them in rank order (deterministic; lowest global
  * index wins ties).  `slab_offset` is the global flat index of the slab's first element and
- * `global_count` the total element count (MEAN/VAR divisors). */
+ * `global_count` the total element count (MEAN/VAR divisors).  Rank r's record is read at
+ * gathered_records + r * record_stride_bytes, so the records of several statements can share one
+ * exchange (record_stride_bytes = 32 * statements per step; 0 means 32). */
 #define MXB_PARTIAL_BYTES 32
 int mxb_reduce_partial(mxb_handle_t h, int reduce_op, const mxb_expr_t *expr, int64_t slab_offset,
                        void *partial_record);
 int mxb_reduce_finalize(mxb_handle_t h, int reduce_op, int32_t value_dtype, const void *gathered_records,
-                        int world, int64_t global_count, int ddof, const mxb_out_t *out,
-                        const mxb_out_t *idx_out);
+                        int world, int64_t record_stride_bytes, int64_t global_count, int ddof,
+                        const mxb_out_t *out, const mxb_out_t *idx_out);
 
 /* ---- introspection ---------------------------------------------------------------------------- */
 int mxb_version(void);                /* major*1000 + minor */

@@ -1,0 +1,125 @@
+"""Kernel-level timing of the other BASELINE.json configs (1, 3, 4, 5) at their full sizes; bench.py reports them
+under `other_configs`.  CUDA events on the launching stream, working sets far larger than L2 (no flush needed)."""
+from __future__ import annotations
+
+from . import ops as mx
+
+
+def _time(ex, fn, iters=8, warm=2):
+    import torch
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    evs = []
+    for _ in range(iters):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        evs.append((a, b))
+    torch.cuda.synchronize()
+    ts = [a.elapsed_time(b) for a, b in evs]
+    return sum(ts) / len(ts), min(ts)
+
+
+def _entry(ex, ms, best, nbytes, nelem, peak):
+    return {"ms_avg": ms, "ms_best": best, "GBps": nbytes / (ms * 1e-3) / 1e9, "frac_of_measured_peak": nbytes / (ms * 1e-3) / 1e9 / peak,
+            "Gelem_per_s": nelem / (ms * 1e-3) / 1e9, "algorithmic_bytes": nbytes, "kernel": ex.last_kernel()}
+
+
+def run_c1(ex, peak):
+    import torch
+    rows, cols = 16384, 4096
+    a, b = torch.rand(rows, cols, device="cuda"), torch.rand(rows, cols, device="cuda")
+    c = torch.rand(rows, cols, device="cuda") - 0.5
+    out = torch.empty(rows, device="cuda")
+    ta, tb, tc, to = (mx.make_tensor(t) for t in (a, b, c, out))
+    ms, best = _time(ex, lambda: to.set(mx.sum(ta * tb + tc, [1])).run(ex))
+    ref = (a.double() * b.double() + c.double()).sum(1)
+    err = ((out.double() - ref).abs() / ref.abs()).max().item()
+    r = _entry(ex, ms, best, 3 * rows * cols * 4 + rows * 4, rows * cols, peak)
+    r["max_rel_err_vs_fp64"] = err
+    return {"sum(a*b+c,{1}) fp32 16384x4096": r}
+
+
+def run_c3(ex, peak):
+    import torch
+    rows, cols = 65536, 8192
+    x = torch.view_as_complex(torch.randn(rows, cols, 2, device="cuda"))
+    tx = mx.make_tensor(x)
+    n = rows * cols
+    res = {}
+    om = torch.empty(rows, dtype=torch.complex64, device="cuda")
+    ms, best = _time(ex, lambda: mx.make_tensor(om).set(mx.mean(tx, [1])).run(ex), iters=5)
+    res["mean(x,{1}) c64 65536x8192"] = _entry(ex, ms, best, n * 8 + rows * 8, n, peak)
+    ov = torch.empty(rows, device="cuda")
+    ms, best = _time(ex, lambda: mx.make_tensor(ov).set(mx.var(tx, [1], 1)).run(ex), iters=5)
+    res["var(x,{1},ddof=1) c64 65536x8192"] = _entry(ex, ms, best, n * 8 + rows * 4, n, peak)
+    oa, oi = torch.empty(rows, device="cuda"), torch.empty(rows, dtype=torch.int64, device="cuda")
+    ms, best = _time(ex, lambda: mx.mtie(mx.make_tensor(oa), mx.make_tensor(oi)).set(mx.argmax(mx.abs2(tx), [1])).run(ex), iters=5)
+    res["argmax(abs2(x),{1}) c64 65536x8192"] = _entry(ex, ms, best, n * 8 + rows * 12, n, peak)
+    # spot checks on a few rows against torch (fp64)
+    xs = x[:64].to(torch.complex128)
+    res["mean(x,{1}) c64 65536x8192"]["max_abs_err_rows0_63"] = (om[:64].to(torch.complex128) - xs.mean(1)).abs().max().item()
+    v64 = ((xs - xs.mean(1, keepdim=True)).abs() ** 2).sum(1) / (cols - 1)
+    res["var(x,{1},ddof=1) c64 65536x8192"]["max_rel_err_rows0_63"] = ((ov[:64].double() - v64).abs() / v64).max().item()
+    a2 = (x[:64].real.double() ** 2 + x[:64].imag.double() ** 2)
+    res["argmax(abs2(x),{1}) c64 65536x8192"]["index_match_rows0_63"] = bool(
+        ((oi[:64] - torch.arange(64, device="cuda") * cols) == a2.argmax(1)).all().item())
+    return res
+
+
+def black_scholes_expr(K, S, V, r, T):
+    VsqrtT = V * mx.sqrt(T)
+    d1 = (mx.log(S / K) + (r + 0.5 * V * V) * T) / VsqrtT
+    d2 = d1 - VsqrtT
+    return S * mx.normcdf(d1) - K * mx.exp(-1.0 * r * T) * mx.normcdf(d2)
+
+
+def run_c4(ex, peak):
+    import torch
+    n = 1 << 28
+    S = torch.rand(n, device="cuda") * 90 + 10
+    K = torch.rand(n, device="cuda") * 90 + 10
+    V = torch.rand(n, device="cuda") * 0.45 + 0.05
+    r = torch.rand(n, device="cuda") * 0.09 + 0.01
+    T = torch.rand(n, device="cuda") * 1.9 + 0.1
+    out = torch.empty(n, device="cuda")
+    tK, tS, tV, tr, tT, to = (mx.make_tensor(t) for t in (K, S, V, r, T, out))
+    expr = black_scholes_expr(tK, tS, tV, tr, tT)
+    ms, best = _time(ex, lambda: to.set(expr).run(ex), iters=5)
+    res = _entry(ex, ms, best, 6 * n * 4, n, peak)
+    m = 1 << 20
+    s, k, v, rr, t = (z[:m].double() for z in (S, K, V, r, T))
+    vs = v * t.sqrt()
+    d1 = ((s / k).log() + (rr + 0.5 * v * v) * t) / vs
+    d2 = d1 - vs
+    N = lambda z: 0.5 * torch.erfc(-z / 2 ** 0.5)  # noqa: E731
+    want = s * N(d1) - k * (-rr * t).exp() * N(d2)
+    res["max_abs_err_first_2^20_vs_fp64"] = (out[:m].double() - want).abs().max().item()
+    return {"black_scholes fp32 2^28 (5 in + 1 out)": res}
+
+
+def run_c5(ex, peak):
+    import torch
+    d = 1024
+    t = (torch.rand(d, d, d, device="cuda") * 0.25).to(torch.bfloat16)
+    out = torch.empty(d, d, dtype=torch.bfloat16, device="cuda")
+    tt, to = mx.make_tensor(t), mx.make_tensor(out)
+    ms, best = _time(ex, lambda: to.set(mx.sum(mx.permute(tt, [2, 0, 1]), [2])).run(ex), iters=8)
+    res = _entry(ex, ms, best, d * d * d * 2 + d * d * 2, d * d * d, peak)
+    want = t[:8].float().sum(1).t()  # out[i][j] = sum_k t[j][k][i]
+    res["max_rel_err_j0_7_vs_fp32"] = ((out[:, :8].float() - want).abs() / want).max().item()
+    return {"sum(permute(t,{2,0,1}),{2}) bf16 1024^3": res}
+
+
+def run_all(ex, peak):
+    import torch
+    out = {}
+    for f in (run_c1, run_c3, run_c4, run_c5):
+        try:
+            out.update(f(ex, peak))
+        except Exception as exc:  # report, do not hide
+            out[f.__name__] = {"error": repr(exc)}
+        torch.cuda.empty_cache()
+    return out

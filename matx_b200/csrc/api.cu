@@ -519,20 +519,20 @@ int reduce_impl(mxb_context *h, int op, const mxb_expr_t *expr_in, int n_reduce,
 // multi-GPU finalize: fold `world` 32-byte records in rank order, one thread
 // ---------------------------------------------------------------------------------------------------
 template <class Op, class OutT>
-__global__ void finalize_kernel(const mxb::PartialRec *recs, int world, const __grid_constant__ RedParams p) {
+__global__ void finalize_kernel(const uint4 *recs, int world, int stride16, const __grid_constant__ RedParams p) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   typename Op::acc_t a = Op::init();
   for (int r = 0; r < world; ++r) {
-    union { mxb::PartialRec rec; typename Op::acc_t acc; } u;
-    u.rec = recs[r];
+    union { uint4 q; typename Op::acc_t acc; } u;  // every acc_t fits the first 16 bytes of the 32-byte record
+    u.q = recs[(size_t)r * stride16];
     Op::merge(a, u.acc);
   }
   mxb::store_result<Op, OutT>(p, 0, a);
 }
 
 template <class T, class OutT>
-int finalize_dispatch_op(mxb_context *h, int kop, const void *recs, int world, RedParams &p) {
-#define MXB_FIN(...) finalize_kernel<__VA_ARGS__, OutT><<<1, 32, 0, h->stream>>>((const mxb::PartialRec *)recs, world, p)
+int finalize_dispatch_op(mxb_context *h, int kop, const void *recs, int world, int stride16, RedParams &p) {
+#define MXB_FIN(...) finalize_kernel<__VA_ARGS__, OutT><<<1, 32, 0, h->stream>>>((const uint4 *)recs, world, stride16, p)
   switch (kop) {
     case MXB_RED_SUM: MXB_FIN(mxb::OpSum<T>); break;
     case MXB_RED_PROD: MXB_FIN(mxb::OpProd<T>); break;
@@ -646,10 +646,13 @@ int mxb_reduce_partial(mxb_handle_t h, int reduce_op, const mxb_expr_t *expr, in
 }
 
 int mxb_reduce_finalize(mxb_handle_t h, int reduce_op, int32_t value_dtype, const void *gathered_records, int world,
-                        int64_t global_count, int ddof, const mxb_out_t *out, const mxb_out_t *idx_out) {
+                        int64_t record_stride_bytes, int64_t global_count, int ddof, const mxb_out_t *out, const mxb_out_t *idx_out) {
   (void)ddof;
   if (!h) return fail(MXB_ERR_INVALID, "null handle");
   if (!gathered_records || world <= 0) return fail(MXB_ERR_INVALID, "no records to fold");
+  if (record_stride_bytes == 0) record_stride_bytes = MXB_PARTIAL_BYTES;
+  if (record_stride_bytes < MXB_PARTIAL_BYTES || record_stride_bytes % 16) return fail(MXB_ERR_INVALID, "record stride must be a multiple of 16 and >= 32");
+  const int rstride = (int)(record_stride_bytes / 16);
   if (!out || !out->data) return fail(MXB_ERR_INVALID, "null output");
   const bool arg = reduce_op == MXB_RED_ARGMAX || reduce_op == MXB_RED_ARGMIN;
   if (arg && (!idx_out || !idx_out->data || idx_out->dtype != MXB_I64)) return fail(MXB_ERR_INVALID, "argmax/argmin need an MXB_I64 index output");
@@ -663,11 +666,11 @@ int mxb_reduce_finalize(mxb_handle_t h, int reduce_op, int32_t value_dtype, cons
   if (reduce_op == MXB_RED_MEAN) { p.post_div = 1; p.post_scale_f = (float)global_count; p.post_scale_d = (double)global_count; }
   const int kop = kernel_op(reduce_op);
   switch (value_dtype) {
-    case MXB_F32: return finalize_dispatch_op<float, float>(h, kop, gathered_records, world, p);
-    case MXB_F64: return finalize_dispatch_op<double, double>(h, kop, gathered_records, world, p);
-    case MXB_C64: return finalize_dispatch_op<mxb::cfloat, mxb::cfloat>(h, kop, gathered_records, world, p);
-    case MXB_I32: return finalize_dispatch_op<int, int>(h, kop, gathered_records, world, p);
-    case MXB_I64: return finalize_dispatch_op<mxb::i64, mxb::i64>(h, kop, gathered_records, world, p);
+    case MXB_F32: return finalize_dispatch_op<float, float>(h, kop, gathered_records, world, rstride, p);
+    case MXB_F64: return finalize_dispatch_op<double, double>(h, kop, gathered_records, world, rstride, p);
+    case MXB_C64: return finalize_dispatch_op<mxb::cfloat, mxb::cfloat>(h, kop, gathered_records, world, rstride, p);
+    case MXB_I32: return finalize_dispatch_op<int, int>(h, kop, gathered_records, world, rstride, p);
+    case MXB_I64: return finalize_dispatch_op<mxb::i64, mxb::i64>(h, kop, gathered_records, world, rstride, p);
   }
   return fail(MXB_ERR_NOT_SUPPORTED, "finalize: value dtype not supported");
 }

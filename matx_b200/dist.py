@@ -1,0 +1,80 @@
+"""Multi-GPU layer (no counterpart in the reference, which is single-device: SURVEY.md section 2.3 / 8e).
+
+One process per GPU, `torch.distributed` for the plumbing.
+  * batched reductions / elementwise: shard the outer (batch) dim with `shard_rows` — no communication at all;
+  * full-tensor reductions: contiguous slab per rank (`slab`), each rank reduces its slab into 32-byte partial
+    records with mxb_reduce_partial, ONE all-gather exchanges the records of every statement of the step, and
+    every rank folds them in rank order with mxb_reduce_finalize (deterministic; the lowest GLOBAL index wins
+    argmax / argmin ties because slab offsets are folded into the indices before the exchange).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+from . import _abi as A
+from . import ops as mx
+
+ALIGN = 1024  # slab boundaries stay aligned for 128/256-bit loads
+
+
+def slab(n: int, rank: int, world: int, align: int = ALIGN) -> tuple[int, int]:
+    """(start, count) of rank's contiguous slab of an n-element tensor; counts differ by at most `align`."""
+    per = -(-n // world)
+    per = -(-per // align) * align
+    start = min(rank * per, n)
+    return start, max(0, min(n, start + per) - start)
+
+
+def shard_rows(n_rows: int, rank: int, world: int) -> tuple[int, int]:
+    """(start, count) of rank's block of the outermost batch dim (no communication needed afterwards)."""
+    base, rem = divmod(n_rows, world)
+    start = rank * base + min(rank, rem)
+    return start, base + (1 if rank < rem else 0)
+
+
+class ShardedFullReduce:
+    """Full-tensor reductions over slab-sharded data: partial -> one all-gather -> finalize."""
+
+    MAX_ITEMS = 8
+
+    def __init__(self, ex, world: int, rank: int, group=None):
+        import torch
+        self.ex, self.world, self.rank, self.group = ex, world, rank, group
+        self._torch = torch
+        self.records = self._alloc(self.MAX_ITEMS * A.MXB_PARTIAL_BYTES)
+        self.gathered = self._alloc(world * self.MAX_ITEMS * A.MXB_PARTIAL_BYTES)
+
+    # -- overridable pieces (the CPU / gloo tests substitute the oracle for the two device calls) --
+    def _alloc(self, nbytes: int):
+        return self._torch.zeros(nbytes, dtype=self._torch.uint8, device="cuda")
+
+    def _partial(self, op: int, operand, slab_offset: int, k: int) -> None:
+        e = mx.lower_reduce(mx.ReduceExpr(op, operand, None))
+        ptr = self.records.data_ptr() + k * A.MXB_PARTIAL_BYTES
+        A.check(A.lib.mxb_reduce_partial(self.ex.handle, op, C.byref(e), slab_offset, C.c_void_p(ptr)))
+
+    def _exchange(self, n_items: int) -> None:
+        import torch.distributed as dist
+        nb = n_items * A.MXB_PARTIAL_BYTES
+        dist.all_gather_into_tensor(self.gathered[: self.world * nb], self.records[:nb], group=self.group)
+
+    def _finalize(self, op: int, value_dtype: int, k: int, n_items: int, global_count: int, out, idx) -> None:
+        stride = n_items * A.MXB_PARTIAL_BYTES
+        ptr = self.gathered.data_ptr() + k * A.MXB_PARTIAL_BYTES
+        o = mx._out_desc(mx.make_tensor(out))
+        io = mx._out_desc(mx.make_tensor(idx)) if idx is not None else None
+        A.check(A.lib.mxb_reduce_finalize(self.ex.handle, op, value_dtype, C.c_void_p(ptr), self.world, stride, global_count, 1,
+                                          C.byref(o), C.byref(io) if io is not None else None))
+
+    def run(self, items: Sequence[tuple], operand, slab_offset: int, global_count: int, value_dtype: Optional[int] = None) -> None:
+        """items = [(reduce_op, out_tensor, idx_tensor_or_None), ...] all over the same sharded operand."""
+        if len(items) > self.MAX_ITEMS:
+            raise ValueError("at most %d statements per exchange" % self.MAX_ITEMS)
+        if value_dtype is None:
+            value_dtype = operand.dtype_hint if operand.dtype_hint not in (A.BF16, A.F16) else A.F32
+        for k, (op, _, _) in enumerate(items):
+            self._partial(op, operand, slab_offset, k)
+        self._exchange(len(items))
+        for k, (op, out, idx) in enumerate(items):
+            self._finalize(op, value_dtype, k, len(items), global_count, out, idx)

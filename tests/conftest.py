@@ -1,0 +1,25 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def built_lib():
+    """libmatx_b200.so, built on demand (nvcc cross-compiles without a GPU)."""
+    from matx_b200 import build
+    return build.build()
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    from tests import oracle_harness
+    return oracle_harness.load_oracle()

@@ -1,0 +1,285 @@
+"""-m gpu parity tests: the CUDA path, called through the C ABI, against the CPU oracle on the same seeded
+inputs, at sizes the oracle finishes in seconds.  Bars (north star): min / max / argmin / argmax / any / all
+bit-exact with lowest-index ties; sum / mean / var within 1e-5 relative for fp32 (fp64: 1e-12), 1e-2 for bf16.
+The test bodies mirror test/00_operators/ReductionTests.cu of the reference (cited per test)."""
+import zlib
+
+import numpy as np
+import pytest
+
+from matx_b200 import _abi as A
+from matx_b200 import ops as mx
+from tests import gpu_util as G
+from tests.oracle_harness import f32_to_bf16_bits, bf16_bits_to_f32
+
+pytestmark = pytest.mark.gpu
+
+TOL = {A.F32: 1e-5, A.F64: 1e-12, A.C64: 1e-5, A.BF16: 1e-2}
+NPDT = {A.F32: np.float32, A.F64: np.float64, A.C64: np.complex64, A.I32: np.int32, A.I64: np.int64}
+
+
+def data(rng, shape, dt, ties=False):
+    if dt == A.C64:
+        return (rng.standard_normal(shape) + 1j * rng.standard_normal(shape)).astype(np.complex64)
+    if dt in (A.I32, A.I64):
+        return rng.integers(-50, 50, shape).astype(NPDT[dt])
+    if ties:
+        return rng.integers(0, 7, shape).astype(NPDT[dt])  # few distinct values: ties everywhere
+    return rng.random(shape).astype(NPDT[dt])
+
+
+EXACT_OPS = ["max", "min", "argmax", "argmin", "any", "all"]
+SUM_OPS = ["sum", "mean", "prod", "var", "stdd"]
+
+
+def check(oracle, opname, build, arrays, out_dt, dtypes=None, tol=None, expect_kernel=None):
+    got, gi, want, wi, k = G.run_reduce(oracle, build, arrays, out_dt, dtypes)
+    if expect_kernel:
+        assert expect_kernel in k, k
+    if opname in EXACT_OPS:
+        assert np.array_equal(got, want), (opname, k)
+        if gi is not None:
+            assert np.array_equal(gi, wi), (opname, k, gi.ravel()[:8], wi.ravel()[:8])
+    else:
+        if out_dt == A.BF16:
+            got, want = bf16_bits_to_f32(got), bf16_bits_to_f32(want)
+        err = G.rel_err(got, want)
+        assert err <= (tol or TOL[out_dt]), (opname, k, err)
+    return k
+
+
+# ---- known-answer vectors of the reference tests, on the device ------------------------------------------
+def test_known_answers_device(oracle):
+    # ReductionTests.cu:948-954, 973-979, 1255-1261, 1272-1280, 1332-1351; CUBTests.cu:328-340
+    t = np.array([1, 3, 8, 2, 9, 10, 6, 7, 4, 5, 11], np.float32)
+    got, gi, _, _, _ = G.run_reduce(oracle, lambda x: mx.argmax(x), [t], A.F32)
+    assert (got, gi) == (11, 10)
+    got, gi, _, _, _ = G.run_reduce(oracle, lambda x: mx.argmin(x), [t], A.F32)
+    assert (got, gi) == (1, 0)
+    got, gi, _, _, _ = G.run_reduce(oracle, lambda x: mx.argmax(x + 0), [t], A.F32)
+    assert (got, gi) == (11, 10)
+    t2 = np.array([[2, 4, 1, 3, 5], [3, 1, 5, 2, 4]], np.float32)
+    got, gi, _, _, _ = G.run_reduce(oracle, lambda x: mx.argmax(x, [1]), [t2], A.F32)
+    assert got.tolist() == [5, 5] and gi.tolist() == [4, 7]
+    got, gi, _, _, _ = G.run_reduce(oracle, lambda x: mx.argmin(x, [1]), [t2], A.F32)
+    assert got.tolist() == [1, 1] and gi.tolist() == [2, 6]
+    t3 = np.array([[1, 5, 2], [4, 3, 6]], np.float32)
+    got, gi, _, _, _ = G.run_reduce(oracle, lambda x: mx.argmax(x, [1]), [t3], A.F32)
+    assert got.tolist() == [5, 6] and gi.tolist() == [1, 5]
+    t4 = np.array([-3, -1, -7], np.float32)
+    got, gi, _, _, _ = G.run_reduce(oracle, lambda x: mx.argmax(x), [t4], A.F32)
+    assert (got, gi) == (-1, 1)
+    tie = np.array([3, 7, 1, 7, 1, 3, 7, 1], np.float32)
+    assert G.run_reduce(oracle, lambda x: mx.argmax(x), [tie], A.F32)[1] == 1
+    assert G.run_reduce(oracle, lambda x: mx.argmin(x), [tie], A.F32)[1] == 2
+
+
+@pytest.mark.parametrize("sign,op", [(1, "argmax"), (-1, "argmin")])
+def test_planted_extrema_device(oracle, sign, op):
+    # ReductionTests.cu:1296-1311, 1367-1383
+    planted = [31 * 33 + 22, 32 * 33 + 24, 19 * 33 + 12, 21 * 33 + 17, 17 * 33 + 7, 1 * 33 + 24]
+    t = np.zeros((6, 33, 33), np.float32)
+    for n, p in enumerate(planted):
+        t[n, p // 33, p % 33] = sign
+    got, gi, _, _, _ = G.run_reduce(oracle, lambda x: getattr(mx, op)(x, [1, 2]), [t], A.F32)
+    assert gi.tolist() == [n * 1089 + p for n, p in enumerate(planted)]
+    assert got.tolist() == [sign] * 6
+
+
+def test_any_all_device(oracle):
+    # ReductionTests.cu:591-635, 688-732
+    for dt, a in [(np.float32, A.F32), (np.int32, A.I32)]:
+        t1, t3, t4 = np.zeros(30, dt), np.zeros((30, 40, 50), dt), np.zeros((3, 4, 5, 6), dt)
+        t1[5] = 5
+        t3[1, 1, 1] = 6
+        assert G.run_reduce(oracle, lambda x: mx.any(x), [t4], a)[0] == 0
+        assert G.run_reduce(oracle, lambda x: mx.any(x), [t3], a)[0] == 1
+        assert G.run_reduce(oracle, lambda x: mx.any(x), [t1], a)[0] == 1
+        got = G.run_reduce(oracle, lambda x: mx.any(x, [2]), [t3], a)[0]
+        want = np.zeros((30, 40), dt)
+        want[1, 1] = 1
+        assert np.array_equal(got, want)
+        o3 = np.ones((30, 40, 50), dt)
+        o3[1, 1, 1] = 0
+        assert G.run_reduce(oracle, lambda x: mx.all(x), [o3], a)[0] == 0
+        got = G.run_reduce(oracle, lambda x: mx.all(x, [2]), [o3], a)[0]
+        assert np.array_equal(got, 1 - want)
+
+
+# ---- op x dtype x layout matrix ----------------------------------------------------------------------------
+SHAPES = [
+    ((1,), None), ((33,), None), ((1000,), None), ((4099,), None), ((70001,), None),
+    ((37, 129), [1]), ((37, 129), [0]), ((5, 4096), [1]), ((3, 9000), [1]), ((300, 64), [1]), ((300, 64), [0]),
+    ((6, 33, 33), [1, 2]), ((6, 33, 33), [2]), ((6, 33, 33), [0]), ((6, 33, 33), [0, 2]),
+    ((5, 6, 7, 8), [2, 3]), ((5, 6, 7, 8), [0, 1]), ((5, 6, 7, 8), [1, 3]), ((5, 6, 7, 8), None),
+]
+
+
+@pytest.mark.parametrize("shape,dims", SHAPES)
+@pytest.mark.parametrize("dt", [A.F32, A.F64, A.I32])
+def test_exact_ops_matrix(oracle, dt, shape, dims):
+    rng = np.random.default_rng(zlib.crc32(repr((dt, shape, dims)).encode()))
+    x = data(rng, shape, dt, ties=True)
+    x.ravel()[rng.integers(0, x.size)] = 0  # make all() interesting
+    for op in EXACT_OPS:
+        check(oracle, op, lambda t, op=op: getattr(mx, op)(t, dims), [x], dt)
+
+
+@pytest.mark.parametrize("shape,dims", SHAPES)
+@pytest.mark.parametrize("dt", [A.F32, A.F64, A.C64])
+def test_sum_ops_matrix(oracle, dt, shape, dims):
+    rng = np.random.default_rng(zlib.crc32(repr((dt, shape, dims, 1)).encode()))
+    x = data(rng, shape, dt)
+    if dt != A.C64:
+        x = x + NPDT[dt](0.5)
+    n_red = int(np.prod([shape[d] for d in (dims if dims is not None else range(len(shape)))]))
+    for op in SUM_OPS:
+        if op == "prod":
+            y = (NPDT[dt](0.9) + x * NPDT[dt](0.2) - NPDT[dt](0.1)) if dt != A.C64 else x
+            if n_red > 300:
+                continue  # overflows / underflows in any order
+            check(oracle, op, lambda t: mx.prod(t, dims), [y], dt, tol=1e-4 if dt != A.F64 else 1e-10)
+            continue
+        if op in ("var", "stdd"):
+            if n_red < 2:
+                continue
+            out_dt = A.F32 if dt == A.C64 else dt
+            check(oracle, op, lambda t, op=op: getattr(mx, op)(t, dims, 1), [x], out_dt, tol=2e-5 if dt != A.F64 else 1e-10)
+            check(oracle, op, lambda t, op=op: getattr(mx, op)(t, dims, 0), [x], out_dt, tol=2e-5 if dt != A.F64 else 1e-10)
+            continue
+        check(oracle, op, lambda t, op=op: getattr(mx, op)(t, dims), [x], dt)
+
+
+def test_permuted_reduce(oracle):
+    # ReductionTests.cu:353-573: every reduction of permute(t4,{2,3,0,1}) over {2,3} equals the {0,1} form
+    rng = np.random.default_rng(7)
+    t = (rng.random((12, 10, 9, 16)) + 0.5).astype(np.float32)
+    for op in ["sum", "mean", "max", "min", "any", "all", "var", "stdd"]:
+        f = getattr(mx, op)
+        a = G.run_reduce(oracle, lambda x: f(mx.permute(x, [2, 3, 0, 1]), [2, 3]), [t], A.F32)
+        b = G.run_reduce(oracle, lambda x: f(x, [0, 1]), [t], A.F32)
+        assert np.array_equal(a[0], b[0]), op
+        assert G.rel_err(a[0], a[2]) <= 2e-5, op
+    for op in ["argmax", "argmin"]:
+        f = getattr(mx, op)
+        a = G.run_reduce(oracle, lambda x: f(mx.permute(x, [2, 3, 0, 1]), [2, 3]), [t], A.F32)
+        assert np.array_equal(a[0], a[2]) and np.array_equal(a[1], a[3]), op
+
+
+def test_kernel_families_are_selected(oracle):
+    rng = np.random.default_rng(8)
+    x = data(rng, (64, 4096), A.F32)
+    k = check(oracle, "sum", lambda t: mx.sum(t, [1]), [x], A.F32)
+    assert k.startswith("red_inner") and "|T0" in k and "|V4" in k and k.endswith("aot"), k
+    x = data(rng, (512, 256), A.F32)
+    k = check(oracle, "sum", lambda t: mx.sum(t, [1]), [x], A.F32)
+    assert k.startswith("red_inner") and "|T1" in k, k
+    k = check(oracle, "sum", lambda t: mx.sum(t, [0]), [x], A.F32)
+    assert k.startswith("red_outer") and "|V4" in k, k
+    x = data(rng, (3, 1 << 20), A.F32)  # few long rows: several CTAs per row + in-launch grid combine
+    k = check(oracle, "argmax", lambda t: mx.argmax(t, [1]), [x.round(2)], A.F32)
+    assert k.startswith("red_inner") and "|T0" in k, k
+    x = data(rng, (257, 129), A.F32)    # odd row pitch: scalar path
+    k = check(oracle, "sum", lambda t: mx.sum(t, [1]), [x], A.F32)
+    assert "|V1" in k, k
+
+
+def test_grid_combine_is_deterministic(oracle):
+    import torch
+    rng = np.random.default_rng(9)
+    x = G.to_dev(rng.random(1 << 22).astype(np.float32))
+    ex = G.executor()
+    outs = []
+    for _ in range(5):
+        o = torch.zeros((), dtype=torch.float32, device="cuda")
+        mx.make_tensor(o).set(mx.sum(mx.make_tensor(x))).run(ex)
+        ex.sync()
+        outs.append(o.item())
+    assert len(set(outs)) == 1
+    truth = float(x.double().sum().item())
+    assert abs(outs[0] - truth) <= 1e-5 * truth
+
+
+def test_sliced_unaligned_views(oracle):
+    rng = np.random.default_rng(10)
+    x = data(rng, (40, 1031), A.F32, ties=True)
+    for op in ["sum", "max", "argmax", "argmin", "all"]:
+        check(oracle, op, lambda t, op=op: getattr(mx, op)(t.Slice([3, 1], [37, 1030]), [1]), [x], A.F32)
+        check(oracle, op, lambda t, op=op: getattr(mx, op)(t.Slice([0, 5], [40, 900])), [x], A.F32)
+
+
+def test_fused_fma_sum_config1_shape(oracle):
+    # config 1 at reduced height: (out = sum(a*b+c, {1})).run(exec)
+    rng = np.random.default_rng(11)
+    a, b = (rng.random((96, 4096)).astype(np.float32) for _ in range(2))
+    c = (rng.random((96, 4096)) - 0.5).astype(np.float32)
+    k = check(oracle, "sum", lambda A_, B_, C_: mx.sum(A_ * B_ + C_, [1]), [a, b, c], A.F32)
+    assert k.endswith("aot"), k
+    for op in ["max", "argmax"]:
+        check(oracle, op, lambda A_, B_, C_, op=op: getattr(mx, op)(A_ * B_ + C_, [1]), [a, b, c], A.F32, tol=None)
+
+
+def test_complex_rows_config3_shape(oracle):
+    # config 3 at reduced height: mean / var(ddof=1) / argmax(abs2(x)) of complex<float> rows of 8192
+    rng = np.random.default_rng(12)
+    x = data(rng, (24, 8192), A.C64)
+    check(oracle, "mean", lambda t: mx.mean(t, [1]), [x], A.C64)
+    k = check(oracle, "var", lambda t: mx.var(t, [1], 1), [x], A.F32, tol=2e-5)
+    assert k.startswith("var_smem"), k
+    got, gi, want, wi, k = G.run_reduce(oracle, lambda t: mx.argmax(mx.abs2(t), [1]), [x], A.F32)
+    # abs2 contracts to an FMA on the device: values may differ in the last bit, the winner may not
+    assert np.array_equal(gi, wi) and G.rel_err(got, want) < 1e-6, k
+
+
+def test_var_two_launch_path(oracle, monkeypatch):
+    rng = np.random.default_rng(13)
+    x = (rng.random((3, 70000)) + 2).astype(np.float32)  # 280 KB rows: do not fit in shared memory
+    k = check(oracle, "var", lambda t: mx.var(t, [1], 1), [x], A.F32, tol=5e-5)
+    assert k.startswith("red_inner"), k
+    monkeypatch.setenv("MXB_VAR_TWO_LAUNCH", "1")
+    y = data(rng, (50, 300), A.C64)
+    check(oracle, "stdd", lambda t: mx.stdd(t, [1], 0), [y], A.F32, tol=2e-5)
+
+
+def test_bf16_permuted_config5_shape(oracle):
+    # config 5 at reduced size: sum(permute(t,{2,0,1}),{2}) on bf16 with fp32 accumulation, bf16 output
+    rng = np.random.default_rng(14)
+    f = (rng.random((16, 96, 256)) * 0.25).astype(np.float32)
+    bits = f32_to_bf16_bits(f).reshape(f.shape)
+    got, _, want, _, k = G.run_reduce(oracle, lambda t: mx.sum(mx.permute(t, [2, 0, 1]), [2]), [bits], A.BF16, dtypes=[A.BF16])
+    assert k.startswith("red_outer") and "|V8" in k, k
+    g, w = bf16_bits_to_f32(got), bf16_bits_to_f32(want)
+    assert g.shape == (256, 16)
+    assert np.array_equal(got, want), float(np.max(np.abs(g - w) / w))   # fp32 accumulate + one rounding on both sides
+    truth = bf16_bits_to_f32(bits).astype(np.float64).sum(axis=1).T
+    assert np.max(np.abs(g - truth) / truth) <= 2 ** -8
+    # secondary: {1,2}
+    got, _, want, _, k = G.run_reduce(oracle, lambda t: mx.sum(mx.permute(t, [2, 0, 1]), [1, 2]), [bits], A.BF16, dtypes=[A.BF16])
+    assert G.rel_err(bf16_bits_to_f32(got), bf16_bits_to_f32(want)) <= 1e-2
+
+
+def test_jit_arbitrary_expression_reduce(oracle):
+    rng = np.random.default_rng(15)
+    a = (rng.random((33, 500)) + 0.1).astype(np.float32)
+    b = (rng.random((500,)) + 0.1).astype(np.float32)  # lower-rank operand broadcasts over rows
+    k = check(oracle, "sum", lambda x, y: mx.sum(mx.sqrt(x) * y - mx.log(x + 1.0) / 3.0, [1]), [a, b], A.F32, tol=2e-5)
+    assert k.endswith("jit"), k
+    check(oracle, "argmax", lambda x, y: mx.argmax(mx.floor(x * 10.0) + mx.floor(y * 3.0), [1]), [a, b], A.F32)
+    check(oracle, "any", lambda x, y: mx.any((x > 1.05) & (y > 0.5), [1]), [a, b], A.U8)
+
+
+def test_error_convention():
+    import torch
+    ex = G.executor()
+    x = mx.make_tensor(torch.zeros((4, 8), device="cuda"))
+    bad = mx.make_tensor(torch.zeros((5,), device="cuda"))
+    with pytest.raises(A.MatxB200Error) as ei:
+        bad.set(mx.sum(x, [1]))          # matxInvalidSize at set construction (operators/set.h:196-198)
+    assert ei.value.status == A.ERR_SIZE
+    out = mx.make_tensor(torch.zeros((4,), device="cuda"))
+    with pytest.raises(TypeError):
+        out.set(mx.argmax(x, [1])).run(ex)
+    c = mx.make_tensor(torch.zeros((4, 8), dtype=torch.complex64, device="cuda"))
+    with pytest.raises(A.MatxB200Error) as ei:
+        out.set(mx.max(c, [1])).run(ex)   # the reference rejects ordering of complex too
+    assert ei.value.status == A.ERR_NOT_SUPPORTED
