@@ -197,6 +197,10 @@ void aot_manifest(std::vector<ManifestItem> *items) {
   }
   for (int d : {MXB_F32, MXB_C64}) add(prog_identity(d), FAM_VAR_SMEM, MXB_RED_VAR, MXB_F32, 0, false);
   add(prog_identity(MXB_F64), FAM_VAR_SMEM, MXB_RED_VAR, MXB_F64, 0, false);
+  for (int ipt : {1, 2, 4, 8}) {
+    for (int d : {MXB_F32, MXB_C64}) add(prog_identity(d), FAM_VAR_REG, MXB_RED_VAR, MXB_F32, ipt, false);
+    add(prog_identity(MXB_F64), FAM_VAR_REG, MXB_RED_VAR, MXB_F64, ipt, false);
+  }
   // config 1: sum(a*b+c, {1})
   for (int op : {MXB_RED_SUM, MXB_RED_MAX, MXB_RED_ARGMAX})
     for (int team : {0, 1}) add(prog_fma3(MXB_F32), FAM_RED_INNER, op, MXB_F32, team, false);

@@ -295,9 +295,21 @@ int reduce_launch(mxb_context *h, int kop, const mxb_expr_t &e, const ExprInfo &
   spec.op = kop;
   spec.out_dtype = out_dtype;
   int rot = -1;
+  int var_ipt = 0, var_threads = 0;
   if (var_smem) {
     spec.family = FAM_VAR_SMEM;
     spec.V = (vmax > 1 && inner_ok(vmax)) ? vmax : 1;
+    // rows that fit in the registers of one CTA: blockDim.x * IPT vectors, single contiguous run, no ragged tail
+    if (gr.n == 1 && inner_ok(spec.V) && gr.size[0] % spec.V == 0 && !getenv("MXB_VAR_SMEM_ONLY")) {
+      const int64_t Lv = gr.size[0] / spec.V;
+      for (int thr : {32, 64, 128, 256, 512}) {
+        for (int ipt : {1, 2, 4, 8}) {
+          if (Lv <= (int64_t)thr * ipt && (thr >= 256 || ipt == 1)) { var_threads = thr; var_ipt = ipt; break; }
+        }
+        if (var_ipt) break;
+      }
+      if (var_ipt) spec.family = FAM_VAR_REG;
+    }
   } else if (vmax > 1 && inner_ok(vmax)) {
     spec.family = FAM_RED_INNER;
     spec.V = vmax;
@@ -315,6 +327,7 @@ int reduce_launch(mxb_context *h, int kop, const mxb_expr_t &e, const ExprInfo &
     spec.V = 1;
   }
   spec.U = policy_unroll(info, spec.V, spec.family);
+  if (spec.family == FAM_VAR_REG) spec.team = var_ipt;
 
   RedParams p;
   memset(&p, 0, sizeof p);
@@ -359,10 +372,23 @@ int reduce_launch(mxb_context *h, int kop, const mxb_expr_t &e, const ExprInfo &
   p.post_sqrt = opt.post_sqrt ? 1 : 0;
   p.raw_partial = opt.raw_partial ? 1 : 0;
   fill_consts(e, p.c);
+  const int vec_is_batch_dim = (rot >= 0);
 
+  {
+    // every leaf unit-stride along the vector dim -> the hot loops drop the per-leaf stride test
+    bool unit = nl > 0;
+    for (int k = 0; k < nl; ++k) {
+      const int64_t in = vec_is_batch_dim ? p.leaf[k].bs[p.nb - 1] : p.leaf[k].rs[p.nr - 1];
+      unit = unit && (in == 1);
+    }
+    p.all_unit = unit ? 1 : 0;
+  }
   const int sm = h->sm_count;
   unsigned grid = 1, block = 256, smem = 0;
-  if (spec.family == FAM_VAR_SMEM) {
+  if (spec.family == FAM_VAR_REG) {
+    block = (unsigned)var_threads;
+    grid = (unsigned)std::min<int64_t>(B, (int64_t)sm * 32);
+  } else if (spec.family == FAM_VAR_SMEM) {
     block = R >= 4096 ? 512 : 256;
     smem = (unsigned)(R * dtype_bytes(info.value_dtype));
     grid = (unsigned)std::min<int64_t>(B, (int64_t)sm * 16);
@@ -746,6 +772,11 @@ int mxb_elementwise(mxb_handle_t h, const mxb_expr_t *expr_in, const mxb_out_t *
   }
   for (int k = 0; k < nl; ++k) p.leaf[k].ptr = e.leaves[k].data;
   p.out.ptr = out->data;
+  {
+    bool unit = nl > 0;
+    for (int k = 0; k < nl; ++k) unit = unit && (p.leaf[k].bs[g.n - 1] == 1);
+    p.all_unit = unit ? 1 : 0;
+  }
   fill_consts(e, p.c);
 
   const unsigned block = 256;

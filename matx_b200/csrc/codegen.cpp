@@ -308,9 +308,9 @@ int analyze_expr(const mxb_expr_t *e, ExprInfo *info, std::string *err) {
   for (int k = 0; k < e->n_leaves; ++k) s << " mxb::Vec<" << dtype_ctype(e->leaves[k].dtype) << ", V> x" << k << ";";
   if (e->n_leaves == 0) s << " int unused_;";
   s << " };\n";
-  s << "  template <int V> static __device__ __forceinline__ void loadv(Regs<V> &r, const char *const *base, const mxb::i64 *inner, mxb::i64 j) {\n";
+  s << "  template <int V, bool UNIT> static __device__ __forceinline__ void loadv(Regs<V> &r, const char *const *base, const mxb::i64 *inner, mxb::i64 j) {\n";
   for (int k = 0; k < e->n_leaves; ++k)
-    s << "    mxb::ldleaf<" << dtype_ctype(e->leaves[k].dtype) << ", V>(r.x" << k << ", base[" << k << "], j, inner[" << k << "]);\n";
+    s << "    mxb::ldleaf<" << dtype_ctype(e->leaves[k].dtype) << ", V, UNIT>(r.x" << k << ", base[" << k << "], j, inner[" << k << "]);\n";
   if (e->n_leaves == 0) s << "    (void)r; (void)base; (void)inner; (void)j;\n";
   s << "  }\n";
   s << "  template <int V> static __device__ __forceinline__ value_type eval(const Regs<V> &r, int v, const mxb::ConstDev &c) {\n";
@@ -338,12 +338,13 @@ int policy_unroll(const ExprInfo &info, int V, int family) {
   if (family == FAM_RED_OUTER) return 4;
   if (family == FAM_EW) return info.nleaf <= 2 ? 4 : 2;
   if (family == FAM_VAR_SMEM) return 4;
+  if (family == FAM_VAR_REG) return 1;
   return info.nleaf <= 2 ? 4 : 2;
 }
 
 std::string kernel_key(const ExprInfo &info, const KernelSpec &s) {
   std::ostringstream k;
-  static const char *fam[] = {"red_inner", "red_outer", "var_smem", "ew"};
+  static const char *fam[] = {"red_inner", "red_outer", "var_smem", "ew", "var_reg"};
   k << fam[s.family] << "|" << info.name << "|" << (s.op >= 0 ? reduce_op_name(s.op) : "-") << "|" << dtype_name(s.out_dtype)
     << "|V" << s.V << "|U" << s.U << "|T" << s.team;
   return k.str();
@@ -392,6 +393,11 @@ int kernel_wrapper_src(const ExprInfo &info, const KernelSpec &s, const std::str
       if (!(info.value_dtype == MXB_F32 || info.value_dtype == MXB_F64 || cplx)) return fail("var of a non-floating expression");
       k << "extern \"C\" __global__ void __launch_bounds__(512) " << symbol
         << "(const __grid_constant__ mxb::RedParams p) { mxb::var_inner_smem_body<" << E << ", " << O << ", " << VU << ">(p); }\n";
+      break;
+    case FAM_VAR_REG:
+      if (!(info.value_dtype == MXB_F32 || info.value_dtype == MXB_F64 || cplx)) return fail("var of a non-floating expression");
+      k << "extern \"C\" __global__ void __launch_bounds__(512) " << symbol
+        << "(const __grid_constant__ mxb::RedParams p) { mxb::var_inner_reg_body<" << E << ", " << O << ", " << s.V << ", " << s.team << ">(p); }\n";
       break;
     case FAM_EW:
       k << "extern \"C\" __global__ void __launch_bounds__(256) " << symbol

@@ -97,6 +97,7 @@ struct RedParams {
   int post_div;    // 1 = divide the sum by post_scale
   int post_sqrt;   // STDD
   int raw_partial; // 1 = write the 32-byte partial record instead of the finalised value (multi-GPU)
+  int all_unit;    // 1 = every leaf is unit-stride along the vector dim
   int tx;          // outer family: threads along the vector (column) dim; blockDim.x / tx reduce lanes
   ConstDev c;
 };
@@ -107,6 +108,7 @@ struct EwParams {
   i64 sz[KMAXD];
   i64 N;           // product
   int nleaf;
+  int all_unit;    // 1 = every leaf is unit-stride along the vector dim
   LeafDev leaf[KMAXLEAF]; // bs[] used
   OutDev out;
   ConstDev c;
@@ -129,21 +131,21 @@ template <> struct LdBytes<2> {
 template <> struct LdBytes<4> {
   static __device__ __forceinline__ void ld(void *d, const void *s) {
     u32 r;
-    asm volatile("ld.global.nc.L1::no_allocate.b32 %0, [%1];" : "=r"(r) : "l"(s));
+    asm("ld.global.nc.L1::no_allocate.b32 %0, [%1];" : "=r"(r) : "l"(s));
     *(u32 *)d = r;
   }
 };
 template <> struct LdBytes<8> {
   static __device__ __forceinline__ void ld(void *d, const void *s) {
     u32 a, b;
-    asm volatile("ld.global.nc.L1::no_allocate.v2.b32 {%0,%1}, [%2];" : "=r"(a), "=r"(b) : "l"(s));
+    asm("ld.global.nc.L1::no_allocate.v2.b32 {%0,%1}, [%2];" : "=r"(a), "=r"(b) : "l"(s));
     ((u32 *)d)[0] = a; ((u32 *)d)[1] = b;
   }
 };
 template <> struct LdBytes<16> {
   static __device__ __forceinline__ void ld(void *d, const void *s) {
     u32 a, b, c, e;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.b32 {%0,%1,%2,%3}, [%4];"
+    asm("ld.global.nc.L1::no_allocate.v4.b32 {%0,%1,%2,%3}, [%4];"
                  : "=r"(a), "=r"(b), "=r"(c), "=r"(e) : "l"(s));
     ((u32 *)d)[0] = a; ((u32 *)d)[1] = b; ((u32 *)d)[2] = c; ((u32 *)d)[3] = e;
   }
@@ -151,7 +153,7 @@ template <> struct LdBytes<16> {
 template <> struct LdBytes<32> {  // LDG.E.256 on sm_100
   static __device__ __forceinline__ void ld(void *d, const void *s) {
     u32 r0, r1, r2, r3, r4, r5, r6, r7;
-    asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+    asm("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3), "=r"(r4), "=r"(r5), "=r"(r6), "=r"(r7) : "l"(s));
     u32 *o = (u32 *)d;
     o[0] = r0; o[1] = r1; o[2] = r2; o[3] = r3; o[4] = r4; o[5] = r5; o[6] = r6; o[7] = r7;
@@ -175,9 +177,13 @@ template <class T, int V> __device__ __forceinline__ void ldsplat(Vec<T, V> &r, 
 #pragma unroll
   for (int i = 0; i < V; ++i) r.v[i] = s.v[0];
 }
-template <class T, int V> __device__ __forceinline__ void ldleaf(Vec<T, V> &r, const void *base, i64 j, i64 inner) {
+// UNIT: every leaf of the expression is unit-stride along the vector dim (decided once per launch on the
+// host), so the hot loops carry no per-leaf stride test and the loads of an unrolled batch can all be in flight.
+template <class T, int V, bool UNIT> __device__ __forceinline__ void ldleaf(Vec<T, V> &r, const void *base, i64 j, i64 inner) {
   const T *p = (const T *)base;
-  if (V == 1) {
+  if (UNIT) {
+    ldv<T, V>(r, p + j);
+  } else if (V == 1) {
     LdBytes<(int)sizeof(T)>::ld(&r, p + j * inner);
   } else if (inner != 0) {
     ldv<T, V>(r, p + j);
@@ -627,8 +633,8 @@ __device__ __forceinline__ void outer_bases(const RedParams &p, i64 o, const cha
 //   ticket is an atomicInc that wraps to zero, so no memset is needed between launches.
 // TEAM == 1: one warp per row, no shared memory, no barrier (short rows).
 // ------------------------------------------------------------------------------------------------
-template <class E, class Op, class OutT, int V, int U, int TEAM>
-__device__ __forceinline__ void reduce_inner_body(const RedParams &p) {
+template <class E, class Op, class OutT, int V, int U, int TEAM, bool UNIT>
+__device__ __forceinline__ void reduce_inner_body_impl(const RedParams &p) {
   typedef typename Op::acc_t acc_t;
   __shared__ acc_t s_acc[32];
   __shared__ int s_last;
@@ -682,7 +688,7 @@ __device__ __forceinline__ void reduce_inner_body(const RedParams &p) {
       for (; q + (i64)(U - 1) * nthr < q1; q += (i64)U * nthr) {
         typename E::template Regs<V> r[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) E::template loadv<V>(r[u], base, inner, (q + (i64)u * nthr) * V);
+        for (int u = 0; u < U; ++u) E::template loadv<V, UNIT>(r[u], base, inner, (q + (i64)u * nthr) * V);
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           const i64 j0 = (q + (i64)u * nthr) * V;
@@ -692,7 +698,7 @@ __device__ __forceinline__ void reduce_inner_body(const RedParams &p) {
       }
       for (; q < q1; q += nthr) {
         typename E::template Regs<V> r;
-        E::template loadv<V>(r, base, inner, q * V);
+        E::template loadv<V, UNIT>(r, base, inner, q * V);
 #pragma unroll
         for (int v = 0; v < V; ++v) Op::step(acc[v], E::template eval<V>(r, v, p.c), row0 + q * V + v);
       }
@@ -702,7 +708,7 @@ __device__ __forceinline__ void reduce_inner_body(const RedParams &p) {
         const char *rb[E::NL];
         outer_bases<E>(p, o, base, rb);
         typename E::template Regs<V> r;
-        E::template loadv<V>(r, rb, inner, jv * V);
+        E::template loadv<V, UNIT>(r, rb, inner, jv * V);
 #pragma unroll
         for (int v = 0; v < V; ++v) Op::step(acc[v], E::template eval<V>(r, v, p.c), row0 + o * L + jv * V + v);
       }
@@ -715,7 +721,7 @@ __device__ __forceinline__ void reduce_inner_body(const RedParams &p) {
         const char *rb[E::NL];
         outer_bases<E>(p, o, base, rb);
         typename E::template Regs<1> r;
-        E::template loadv<1>(r, rb, inner, j);
+        E::template loadv<1, UNIT>(r, rb, inner, j);
         // this index may precede ones the thread already folded: merge, do not step
         acc_t one = Op::init();
         Op::step(one, E::template eval<1>(r, 0, p.c), row0 + o * L + j);
@@ -762,8 +768,8 @@ __device__ __forceinline__ void reduce_inner_body(const RedParams &p) {
 // in registers, and the TY partials meet in shared memory.  Loads stay coalesced along the unit-stride
 // dim however the reduce dims are strided.
 // ------------------------------------------------------------------------------------------------
-template <class E, class Op, class OutT, int V, int U>
-__device__ __forceinline__ void reduce_outer_body(const RedParams &p) {
+template <class E, class Op, class OutT, int V, int U, bool UNIT>
+__device__ __forceinline__ void reduce_outer_body_impl(const RedParams &p) {
   typedef typename Op::acc_t acc_t;
   extern __shared__ __align__(16) unsigned char s_dyn[];
   acc_t *s_part = (acc_t *)s_dyn;  // [TY][TX*V]
@@ -827,7 +833,7 @@ __device__ __forceinline__ void reduce_outer_body(const RedParams &p) {
                 rb[k] = base[k] + off * E::leaf_bytes(k);
               }
             }
-            E::template loadv<V>(reg[u], rb, inner, c0);
+            E::template loadv<V, UNIT>(reg[u], rb, inner, c0);
           }
 #pragma unroll
           for (int u = 0; u < U; ++u) {
@@ -848,7 +854,7 @@ __device__ __forceinline__ void reduce_outer_body(const RedParams &p) {
             rb[k] = base[k] + off * E::leaf_bytes(k);
           }
           typename E::template Regs<V> reg;
-          E::template loadv<V>(reg, rb, inner, c0);
+          E::template loadv<V, UNIT>(reg, rb, inner, c0);
 #pragma unroll
           for (int v = 0; v < V; ++v) Op::step(acc[v], E::template eval<V>(reg, v, p.c), rowflat + (i64)v * colflat + r);
         }
@@ -869,7 +875,7 @@ __device__ __forceinline__ void reduce_outer_body(const RedParams &p) {
           for (int v = 0; v < V; ++v) {
             if (c0 + v < C) {
               typename E::template Regs<1> reg;
-              E::template loadv<1>(reg, rb, inner, c0 + v);
+              E::template loadv<1, UNIT>(reg, rb, inner, c0 + v);
               Op::step(acc[v], E::template eval<1>(reg, 0, p.c), rowflat + (i64)v * colflat + r);
             }
           }
@@ -920,8 +926,8 @@ template <> struct MeanDiv<cfloat> {
   static __device__ __forceinline__ cfloat go(cfloat s, i64 n) { return s / (float)n; }
 };
 
-template <class E, class OutT, int V, int U>
-__device__ __forceinline__ void var_inner_smem_body(const RedParams &p) {
+template <class E, class OutT, int V, int U, bool UNIT>
+__device__ __forceinline__ void var_inner_smem_body_impl(const RedParams &p) {
   typedef typename E::value_type T;
   typedef typename AbsDev2<T>::real_t RT;
   extern __shared__ __align__(16) unsigned char s_dyn[];
@@ -958,7 +964,7 @@ __device__ __forceinline__ void var_inner_smem_body(const RedParams &p) {
       for (; q + (i64)(U - 1) * nthr < Q; q += (i64)U * nthr) {
         typename E::template Regs<V> r[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) E::template loadv<V>(r[u], base, inner, (q + (i64)u * nthr) * V);
+        for (int u = 0; u < U; ++u) E::template loadv<V, UNIT>(r[u], base, inner, (q + (i64)u * nthr) * V);
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           Vec<T, V> x;
@@ -969,7 +975,7 @@ __device__ __forceinline__ void var_inner_smem_body(const RedParams &p) {
       }
       for (; q < Q; q += nthr) {
         typename E::template Regs<V> r;
-        E::template loadv<V>(r, base, inner, q * V);
+        E::template loadv<V, UNIT>(r, base, inner, q * V);
         Vec<T, V> x;
 #pragma unroll
         for (int v = 0; v < V; ++v) { x.v[v] = E::template eval<V>(r, v, p.c); acc[v] = acc[v] + x.v[v]; }
@@ -981,7 +987,7 @@ __device__ __forceinline__ void var_inner_smem_body(const RedParams &p) {
         const char *rb[E::NL];
         outer_bases<E>(p, o, base, rb);
         typename E::template Regs<V> r;
-        E::template loadv<V>(r, rb, inner, jv * V);
+        E::template loadv<V, UNIT>(r, rb, inner, jv * V);
 #pragma unroll
         for (int v = 0; v < V; ++v) {
           const T x = E::template eval<V>(r, v, p.c);
@@ -997,7 +1003,7 @@ __device__ __forceinline__ void var_inner_smem_body(const RedParams &p) {
         const char *rb[E::NL];
         outer_bases<E>(p, o, base, rb);
         typename E::template Regs<1> r;
-        E::template loadv<1>(r, rb, inner, j);
+        E::template loadv<1, UNIT>(r, rb, inner, j);
         const T x = E::template eval<1>(r, 0, p.c);
         acc[0] = acc[0] + x;
         s_row[o * L + j] = x;
@@ -1027,6 +1033,82 @@ __device__ __forceinline__ void var_inner_smem_body(const RedParams &p) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// K3r: var_inner_reg — the same exact two-pass variance for rows of up to blockDim.x * IPT vectors, with
+// the evaluated row parked in REGISTERS instead of shared memory: every thread issues its IPT vector loads
+// back to back (all in flight at once), keeps the values, and both passes run out of registers.  One read of
+// HBM, no shared-memory traffic beyond the two CTA reductions.  Needs a single contiguous reduce dim whose
+// length is a multiple of V (the host checks); everything else goes to var_inner_smem or the two-launch path.
+// ------------------------------------------------------------------------------------------------
+template <class E, class OutT, int V, int IPT, bool UNIT>
+__device__ __forceinline__ void var_inner_reg_body_impl(const RedParams &p) {
+  typedef typename E::value_type T;
+  typedef typename AbsDev2<T>::real_t RT;
+  __shared__ T s_sum[32];
+  __shared__ RT s_sq[32];
+  __shared__ T s_mean;
+  const int nthr = blockDim.x, tid = threadIdx.x;
+  const i64 Lv = p.rsz[0] / V;
+
+  for (i64 b = blockIdx.x; b < p.B; b += gridDim.x) {
+    const char *base[E::NL];
+    i64 inner[E::NL];
+    {
+      i64 bidx[KMAXD];
+      decomp(b, p.nb, p.bsz, bidx);
+#pragma unroll
+      for (int k = 0; k < E::NL; ++k) {
+        i64 off = 0;
+#pragma unroll
+        for (int d = 0; d < KMAXD; ++d) if (d < p.nb) off += bidx[d] * p.leaf[k].bs[d];
+        base[k] = (const char *)p.leaf[k].ptr + off * E::leaf_bytes(k);
+        inner[k] = p.leaf[k].rs[0];
+      }
+    }
+    typename E::template Regs<V> r[IPT];
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) {
+      const i64 q = tid + (i64)i * nthr;
+      if (q < Lv) E::template loadv<V, UNIT>(r[i], base, inner, q * V);
+    }
+    Vec<T, V> x[IPT];
+    T acc = OpSum<T>::init();
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) {
+      const i64 q = tid + (i64)i * nthr;
+      if (q < Lv) {
+#pragma unroll
+        for (int v = 0; v < V; ++v) { x[i].v[v] = E::template eval<V>(r[i], v, p.c); acc = acc + x[i].v[v]; }
+      }
+    }
+    const T tot = cta_merge<OpSum<T> >(acc, s_sum);
+    if (tid == 0) s_mean = MeanDiv<T>::go(tot, p.R);
+    __syncthreads();
+    const T mean = s_mean;
+    RT sq = (RT)0;
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) {
+      const i64 q = tid + (i64)i * nthr;
+      if (q < Lv) {
+#pragma unroll
+        for (int v = 0; v < V; ++v) sq += AbsDev2<T>::go(x[i].v[v], mean);
+      }
+    }
+    sq = cta_merge<OpSum<RT> >(sq, s_sq);
+    if (tid == 0) {
+      RT res = sq / (RT)p.post_scale_d;
+      if (p.post_sqrt) res = f_sqrt(res);
+      i64 bidx[KMAXD];
+      decomp(b, p.nb, p.bsz, bidx);
+      i64 oo = 0;
+#pragma unroll
+      for (int d = 0; d < KMAXD; ++d) if (d < p.nb) oo += bidx[d] * p.out.bs[d];
+      ((OutT *)p.out.ptr)[oo] = cvt<OutT>(res);
+    }
+    __syncthreads();  // s_mean is reused by the next row
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // E1: elementwise — out(idx) = expr(idx).  Persistent grid-stride over V-wide vectors of the innermost
 // dim (LDG.128/256 per leaf, each distinct leaf loaded once, STG.128/256), U vectors per thread in
 // flight; V == 1 takes any strides.  Replaces the one-vector-per-thread generic kernels of
@@ -1041,8 +1123,8 @@ __device__ __forceinline__ void ew_store(const EwParams &p, char *obase, i64 oin
   else StBytes<(int)sizeof(OutT) * V>::st((OutT *)obase + j, &o);
 }
 
-template <class E, class OutT, int V, int U>
-__device__ __forceinline__ void ew_body(const EwParams &p) {
+template <class E, class OutT, int V, int U, bool UNIT>
+__device__ __forceinline__ void ew_body_impl(const EwParams &p) {
   const int nd = p.nd;
   const i64 L = p.sz[nd - 1], Lv = L / V, tail = L - Lv * V, O = p.N / L;
   const i64 Q = O * Lv;
@@ -1061,13 +1143,13 @@ __device__ __forceinline__ void ew_body(const EwParams &p) {
     for (; q + (i64)(U - 1) * nthr < Q; q += (i64)U * nthr) {
       typename E::template Regs<V> r[U];
 #pragma unroll
-      for (int u = 0; u < U; ++u) E::template loadv<V>(r[u], base, inner, (q + (i64)u * nthr) * V);
+      for (int u = 0; u < U; ++u) E::template loadv<V, UNIT>(r[u], base, inner, (q + (i64)u * nthr) * V);
 #pragma unroll
       for (int u = 0; u < U; ++u) ew_store<E, OutT, V>(p, (char *)p.out.ptr, oinner, (q + (i64)u * nthr) * V, r[u]);
     }
     for (; q < Q; q += nthr) {
       typename E::template Regs<V> r;
-      E::template loadv<V>(r, base, inner, q * V);
+      E::template loadv<V, UNIT>(r, base, inner, q * V);
       ew_store<E, OutT, V>(p, (char *)p.out.ptr, oinner, q * V, r);
     }
   } else {
@@ -1087,7 +1169,7 @@ __device__ __forceinline__ void ew_body(const EwParams &p) {
 #pragma unroll
       for (int d = 0; d < KMAXD - 1; ++d) if (d < nd - 1) ooff += oidx[d] * p.out.bs[d];
       typename E::template Regs<V> r;
-      E::template loadv<V>(r, base, inner, jv * V);
+      E::template loadv<V, UNIT>(r, base, inner, jv * V);
       ew_store<E, OutT, V>(p, (char *)p.out.ptr + ooff * (i64)sizeof(OutT), oinner, jv * V, r);
     }
   }
@@ -1109,10 +1191,42 @@ __device__ __forceinline__ void ew_body(const EwParams &p) {
 #pragma unroll
       for (int d = 0; d < KMAXD - 1; ++d) if (d < nd - 1) ooff += oidx[d] * p.out.bs[d];
       typename E::template Regs<1> r;
-      E::template loadv<1>(r, base, inner, j);
+      E::template loadv<1, UNIT>(r, base, inner, j);
       ew_store<E, OutT, 1>(p, (char *)p.out.ptr + ooff * (i64)sizeof(OutT), oinner, j, r);
     }
   }
+}
+
+
+// launch-time dispatch on the unit-stride flag
+template <class E, class Op, class OutT, int V, int U, int TEAM>
+__device__ __forceinline__ void reduce_inner_body(const RedParams &p) {
+  if (p.all_unit) reduce_inner_body_impl<E, Op, OutT, V, U, TEAM, true>(p);
+  else reduce_inner_body_impl<E, Op, OutT, V, U, TEAM, false>(p);
+}
+
+template <class E, class Op, class OutT, int V, int U>
+__device__ __forceinline__ void reduce_outer_body(const RedParams &p) {
+  if (p.all_unit) reduce_outer_body_impl<E, Op, OutT, V, U, true>(p);
+  else reduce_outer_body_impl<E, Op, OutT, V, U, false>(p);
+}
+
+template <class E, class OutT, int V, int U>
+__device__ __forceinline__ void var_inner_smem_body(const RedParams &p) {
+  if (p.all_unit) var_inner_smem_body_impl<E, OutT, V, U, true>(p);
+  else var_inner_smem_body_impl<E, OutT, V, U, false>(p);
+}
+
+template <class E, class OutT, int V, int U>
+__device__ __forceinline__ void ew_body(const EwParams &p) {
+  if (p.all_unit) ew_body_impl<E, OutT, V, U, true>(p);
+  else ew_body_impl<E, OutT, V, U, false>(p);
+}
+
+template <class E, class OutT, int V, int IPT>
+__device__ __forceinline__ void var_inner_reg_body(const RedParams &p) {
+  if (p.all_unit) var_inner_reg_body_impl<E, OutT, V, IPT, true>(p);
+  else var_inner_reg_body_impl<E, OutT, V, IPT, false>(p);
 }
 
 }  // namespace mxb

@@ -31,14 +31,14 @@ uint64_t fnv64(const std::string &s);
 int analyze_expr(const mxb_expr_t *e, ExprInfo *info, std::string *err);
 
 // ---- kernel instances ----------------------------------------------------------------------------
-enum Family { FAM_RED_INNER = 0, FAM_RED_OUTER = 1, FAM_VAR_SMEM = 2, FAM_EW = 3 };
+enum Family { FAM_RED_INNER = 0, FAM_RED_OUTER = 1, FAM_VAR_SMEM = 2, FAM_EW = 3, FAM_VAR_REG = 4 };
 
 struct KernelSpec {
   int family = 0;
   int op = -1;        // mxb_reduce_op_t for reductions (SUM also serves MEAN; VAR serves STDD), -1 for elementwise
   int out_dtype = 0;
   int V = 1, U = 1;
-  int team = 0;       // FAM_RED_INNER: 0 = CTA per row, 1 = warp per row
+  int team = 0;       // FAM_RED_INNER: 0 = CTA per row, 1 = warp per row; FAM_VAR_REG: vectors per thread (IPT)
 };
 
 // unique key of (expression, spec); also yields the extern "C" symbol name

@@ -20,7 +20,8 @@ NPDT = {A.F32: np.float32, A.F64: np.float64, A.C64: np.complex64, A.I32: np.int
 
 def data(rng, shape, dt, ties=False):
     if dt == A.C64:
-        return (rng.standard_normal(shape) + 1j * rng.standard_normal(shape)).astype(np.complex64)
+        # non-zero mean: a relative bound on a sum is meaningless under cancellation
+        return (rng.standard_normal(shape) + 1j * rng.standard_normal(shape) + (4 + 3j)).astype(np.complex64)
     if dt in (A.I32, A.I64):
         return rng.integers(-50, 50, shape).astype(NPDT[dt])
     if ties:
@@ -215,17 +216,23 @@ def test_fused_fma_sum_config1_shape(oracle):
     c = (rng.random((96, 4096)) - 0.5).astype(np.float32)
     k = check(oracle, "sum", lambda A_, B_, C_: mx.sum(A_ * B_ + C_, [1]), [a, b, c], A.F32)
     assert k.endswith("aot"), k
-    for op in ["max", "argmax"]:
-        check(oracle, op, lambda A_, B_, C_, op=op: getattr(mx, op)(A_ * B_ + C_, [1]), [a, b, c], A.F32, tol=None)
+    # max / argmax of the fused expression: the device contracts a*b+c into one FMA (so does the reference's CUDA
+    # build), the host oracle rounds twice; compare with the FMA value computed exactly in fp64
+    fma = (a.astype(np.float64) * b.astype(np.float64) + c.astype(np.float64)).astype(np.float32)
+    got, gi, _, _, _ = G.run_reduce(oracle, lambda A_, B_, C_: mx.argmax(A_ * B_ + C_, [1]), [a, b, c], A.F32)
+    assert np.array_equal(got, fma.max(1)) and np.array_equal(gi, fma.argmax(1) + np.arange(96) * 4096)
+    got = G.run_reduce(oracle, lambda A_, B_, C_: mx.max(A_ * B_ + C_, [1]), [a, b, c], A.F32)[0]
+    assert np.array_equal(got, fma.max(1))
 
 
 def test_complex_rows_config3_shape(oracle):
     # config 3 at reduced height: mean / var(ddof=1) / argmax(abs2(x)) of complex<float> rows of 8192
     rng = np.random.default_rng(12)
-    x = data(rng, (24, 8192), A.C64)
-    check(oracle, "mean", lambda t: mx.mean(t, [1]), [x], A.C64)
+    x = (rng.standard_normal((24, 8192)) + 1j * rng.standard_normal((24, 8192))).astype(np.complex64)  # zero mean, as config 3
+    got, _, want, _, k = G.run_reduce(oracle, lambda t: mx.mean(t, [1]), [x], A.C64)
+    assert np.max(np.abs(got - want)) <= 1e-5 * np.mean(np.abs(x)), k   # norm-wise bound: the mean itself is ~0
     k = check(oracle, "var", lambda t: mx.var(t, [1], 1), [x], A.F32, tol=2e-5)
-    assert k.startswith("var_smem"), k
+    assert k.startswith("var_reg") and "|T8" in k, k
     got, gi, want, wi, k = G.run_reduce(oracle, lambda t: mx.argmax(mx.abs2(t), [1]), [x], A.F32)
     # abs2 contracts to an FMA on the device: values may differ in the last bit, the winner may not
     assert np.array_equal(gi, wi) and G.rel_err(got, want) < 1e-6, k
@@ -236,9 +243,13 @@ def test_var_two_launch_path(oracle, monkeypatch):
     x = (rng.random((3, 70000)) + 2).astype(np.float32)  # 280 KB rows: do not fit in shared memory
     k = check(oracle, "var", lambda t: mx.var(t, [1], 1), [x], A.F32, tol=5e-5)
     assert k.startswith("red_inner"), k
-    monkeypatch.setenv("MXB_VAR_TWO_LAUNCH", "1")
     y = data(rng, (50, 300), A.C64)
-    check(oracle, "stdd", lambda t: mx.stdd(t, [1], 0), [y], A.F32, tol=2e-5)
+    monkeypatch.setenv("MXB_VAR_SMEM_ONLY", "1")
+    k = check(oracle, "stdd", lambda t: mx.stdd(t, [1], 0), [y], A.F32, tol=2e-5)
+    assert k.startswith("var_smem"), k
+    monkeypatch.setenv("MXB_VAR_TWO_LAUNCH", "1")
+    k = check(oracle, "stdd", lambda t: mx.stdd(t, [1], 0), [y], A.F32, tol=2e-5)
+    assert k.startswith("red_inner"), k
 
 
 def test_bf16_permuted_config5_shape(oracle):
