@@ -1,0 +1,130 @@
+"""CPU-side tests of the boundary: the C-ABI library loads without a GPU, exports every symbol include/matx_b200.h
+declares, refuses to compute without a device (no CPU fallback), and the host-side lowering / code generator behave.
+NVRTC is used in compile-only mode to prove that generated kernels build for sm_100a on a box with no GPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from matx_b200 import _abi as A
+from matx_b200 import ops as mx
+from tests.oracle_harness import np_tensor
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    hdr = open(os.path.join(ROOT, "include", "matx_b200.h")).read()
+    declared = set(re.findall(r"\b(mxb_[a-z_]+)\s*\(", hdr))
+    declared -= {"mxb_context"}
+    assert declared == set(A.EXPORTED), declared ^ set(A.EXPORTED)
+    lib = C.CDLL(built_lib)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.mxb_version() == 1
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    assert A.lib.mxb_device_count() == 0
+    h = C.c_void_p()
+    st = A.lib.mxb_create(C.byref(h), None)
+    assert st == A.ERR_NO_DEVICE and not h.value
+    assert b"no CPU fallback" in A.lib.mxb_last_error()
+    with pytest.raises(A.MatxB200Error) as ei:
+        mx.CudaExecutor()
+    assert ei.value.status == A.ERR_NO_DEVICE
+    # compute entry points reject a null handle instead of computing anything
+    x = np_tensor(np.ones(8, np.float32))
+    e = mx.lower_reduce(mx.sum(x))
+    o = mx._out_desc(np_tensor(np.zeros((), np.float32)))
+    assert A.lib.mxb_reduce(None, A.RED_SUM, C.byref(e), 1, C.byref(o), None, 1) == A.ERR_INVALID
+    assert A.lib.mxb_elementwise(None, C.byref(mx.lower_elementwise(x + 1.0)), C.byref(mx._out_desc(x))) == A.ERR_INVALID
+
+
+def codegen(expr) -> str:
+    buf = C.create_string_buffer(1 << 16)
+    A.check(A.lib.mxb_debug_codegen(C.byref(expr), buf, len(buf)))
+    return buf.value.decode()
+
+
+def test_lowering_of_sum_dims_moves_reduced_dims_last():
+    # sum(x, {0}) on a contiguous 4x8x16 tensor == trailing-dim reduce of the view with strides (16, 1, 128)
+    # (getPermuteDims, core/utils.h:96-127; SURVEY.md section 8a row a6 states the reference's result on this shape)
+    t = np_tensor(np.zeros((4, 8, 16), np.float32))
+    r = mx.sum(mx.permute(t, [2, 0, 1]), [2])      # config 5 statement
+    e = mx.lower_reduce(r)
+    assert r.out_shape == (16, 4) and e.rank == 3
+    assert list(e.size[:3]) == [16, 4, 8] and list(e.leaves[0].stride[:3]) == [1, 128, 16]
+    r = mx.sum(t, [0])
+    e = mx.lower_reduce(r)
+    assert list(e.size[:3]) == [8, 16, 4] and list(e.leaves[0].stride[:3]) == [16, 1, 128]
+
+
+def test_broadcast_clone_and_cse():
+    a = np_tensor(np.zeros((5, 7), np.float32))
+    v = np_tensor(np.zeros(7, np.float32))
+    e = mx.lower_elementwise(a * v + mx.clone(v, [5, mx.matxKeepDim]) + a)
+    src = codegen(e)
+    assert src.count("mxb::ldleaf<") == 2            # a and v are each loaded once although they appear twice
+    assert list(e.leaves[1].stride[:2]) == [0, 1]    # lower-rank operand lines up with the trailing dim
+
+
+def test_types_follow_cpp_promotion():
+    f = np_tensor(np.zeros(4, np.float32))
+    d = np_tensor(np.zeros(4, np.float64))
+    i = np_tensor(np.zeros(4, np.int32))
+    c = np_tensor(np.zeros(4, np.complex64))
+    assert "value_dtype=f64" in codegen(mx.lower_elementwise(f + d))
+    assert "value_dtype=f32" in codegen(mx.lower_elementwise(f * i))
+    assert "value_dtype=i32" in codegen(mx.lower_elementwise(i / i))
+    assert "value_dtype=f64" in codegen(mx.lower_elementwise(mx.sqrt(i)))
+    assert "value_dtype=c64" in codegen(mx.lower_elementwise(c * f))
+    assert "value_dtype=f32" in codegen(mx.lower_elementwise(mx.abs2(c)))
+    assert "value_dtype=u8" in codegen(mx.lower_elementwise(f > 0.5))
+    with pytest.raises(A.MatxB200Error) as ei:
+        codegen(mx.lower_elementwise(c * d))           # complex<double> is not lowered
+    assert ei.value.status == A.ERR_NOT_SUPPORTED
+
+
+def test_named_programs_are_ahead_of_time():
+    f = lambda *s: np_tensor(np.zeros(s, np.float32))  # noqa: E731
+    a, b, c = f(4, 8), f(4, 8), f(4, 8)
+    assert A.lib.mxb_is_aot(C.byref(mx.lower_reduce(mx.sum(a * b + c, [1]))), A.RED_SUM) == 1
+    assert A.lib.mxb_is_aot(C.byref(mx.lower_reduce(mx.argmax(a))), A.RED_ARGMAX) == 1
+    x = np_tensor(np.zeros((4, 8), np.complex64))
+    assert A.lib.mxb_is_aot(C.byref(mx.lower_reduce(mx.argmax(mx.abs2(x), [1]))), A.RED_ARGMAX) == 1
+    K, S, V, r, T = (f(16) for _ in range(5))
+    VsqrtT = V * mx.sqrt(T)
+    d1 = (mx.log(S / K) + (r + 0.5 * V * V) * T) / VsqrtT
+    d2 = d1 - VsqrtT
+    bs = S * mx.normcdf(d1) - K * mx.exp(-1.0 * r * T) * mx.normcdf(d2)
+    assert A.lib.mxb_is_aot(C.byref(mx.lower_elementwise(bs)), -1) == 1
+    assert A.lib.mxb_is_aot(C.byref(mx.lower_elementwise(mx.tanh(a) * 3.0)), -1) == 0
+
+
+@pytest.mark.parametrize("family,op,team", [(0, A.RED_SUM, 0), (0, A.RED_ARGMIN, 1), (1, A.RED_MAX, 0), (2, A.RED_VAR, 0),
+                                            (4, A.RED_VAR, 4), (3, -1, 0)])
+def test_generated_kernels_compile_for_sm100a(family, op, team):
+    a = np_tensor(np.zeros((4, 8), np.float32))
+    h = np_tensor(np.zeros((4, 8), np.uint16), A.BF16)
+    expr = mx.sqrt(mx.abs(a)) * h - mx.tanh(a) / 3.0 + mx.as_type(mx.floor(a), A.I32)
+    e = mx.lower_reduce(mx.ReduceExpr(max(op, 0), expr, [1])) if family != 3 else mx.lower_elementwise(expr)
+    log = C.create_string_buffer(1 << 16)
+    st = A.lib.mxb_debug_compile(C.byref(e), family, op, A.F32, 0, team, log, len(log))
+    assert st == A.OK, (A.lib.mxb_last_error(), log.value.decode()[:2000])
+
+
+def test_set_checks_shapes_like_the_reference():
+    a = np_tensor(np.zeros((4, 8), np.float32))
+    with pytest.raises(A.MatxB200Error) as ei:
+        np_tensor(np.zeros(5, np.float32)).set(mx.sum(a, [1]))
+    assert ei.value.status == A.ERR_SIZE
+    with pytest.raises(ValueError):
+        a + np_tensor(np.zeros(7, np.float32))
+    with pytest.raises(TypeError):
+        mx.mtie(a, a).set(mx.sum(a))
