@@ -143,6 +143,10 @@ void fill_consts(const mxb_expr_t &e, mxb::ConstDev &c) {
 }
 
 bool aligned_to(const void *p, int64_t bytes) { return ((uintptr_t)p % (uintptr_t)bytes) == 0; }
+int env_int(const char *name, int dflt) {
+  const char *v = getenv(name);
+  return (v && *v) ? atoi(v) : dflt;
+}
 
 int acc_bytes(int op, int value_dtype) {
   switch (op) {
@@ -253,7 +257,7 @@ int reduce_launch(mxb_context *h, int kop, const mxb_expr_t &e, const ExprInfo &
   if (R == 0) return fail(MXB_ERR_INVALID, "reduction over zero elements");
 
   const int out_dtype = opt.raw_partial ? info.value_dtype : out->dtype;
-  const int vmax = policy_vmax(info);
+  const int vmax = env_int("MXB_TUNE_V", 0) > 0 ? env_int("MXB_TUNE_V", 0) : policy_vmax(info);
   const int nl = e.n_leaves;
 
   // ---- can the innermost reduce dim be the vector dim? ----
@@ -328,6 +332,10 @@ int reduce_launch(mxb_context *h, int kop, const mxb_expr_t &e, const ExprInfo &
   }
   spec.U = policy_unroll(info, spec.V, spec.family);
   if (spec.family == FAM_VAR_REG) spec.team = var_ipt;
+  // development knobs (tools/sweep.py): override the unroll / launch shape; any combination is JIT-compiled on demand
+  const int tune_u = env_int("MXB_TUNE_U", 0), tune_block = env_int("MXB_TUNE_BLOCK", 0), tune_cps = env_int("MXB_TUNE_CTAS_PER_SM", 0);
+  const int tune_tx = env_int("MXB_TUNE_TX", 0);
+  if (tune_u > 0 && spec.family != FAM_VAR_REG) spec.U = tune_u;
 
   RedParams p;
   memset(&p, 0, sizeof p);
@@ -384,23 +392,26 @@ int reduce_launch(mxb_context *h, int kop, const mxb_expr_t &e, const ExprInfo &
     p.all_unit = unit ? 1 : 0;
   }
   const int sm = h->sm_count;
-  unsigned grid = 1, block = 256, smem = 0;
+  unsigned grid = 1, block = tune_block > 0 ? (unsigned)tune_block : 256u, smem = 0;
+  // persistent grids: CTAs per SM x SM count (every CTA loops over its share of the rows / tiles)
   if (spec.family == FAM_VAR_REG) {
     block = (unsigned)var_threads;
-    grid = (unsigned)std::min<int64_t>(B, (int64_t)sm * 32);
+    grid = (unsigned)std::min<int64_t>(B, (int64_t)sm * (tune_cps > 0 ? tune_cps : 32));
   } else if (spec.family == FAM_VAR_SMEM) {
-    block = R >= 4096 ? 512 : 256;
+    if (tune_block <= 0) block = R >= 4096 ? 512 : 256;
     smem = (unsigned)(R * dtype_bytes(info.value_dtype));
-    grid = (unsigned)std::min<int64_t>(B, (int64_t)sm * 16);
+    grid = (unsigned)std::min<int64_t>(B, (int64_t)sm * (tune_cps > 0 ? tune_cps : 16));
   } else if (spec.family == FAM_RED_INNER) {
     const int64_t row_bytes = R * info.max_leaf_bytes;
     spec.team = (row_bytes >= 8192) ? 0 : 1;
+    if (env_int("MXB_TUNE_TEAM", -1) >= 0) spec.team = env_int("MXB_TUNE_TEAM", -1);
+    const int cps = tune_cps > 0 ? tune_cps : 8;
     if (spec.team == 0) {
       const int64_t L = gr.size[gr.n - 1];
       const int64_t Q = (R / L) * (L / spec.V);  // vector steps per row
       int64_t S = 1;
       if (B < 2 * (int64_t)sm) {
-        S = ((int64_t)sm * 8 + B - 1) / B;
+        S = ((int64_t)sm * cps + B - 1) / B;
         const int64_t maxS = std::max<int64_t>(1, Q / ((int64_t)block * spec.U * 2));
         S = std::max<int64_t>(1, std::min(S, maxS));
       }
@@ -411,22 +422,23 @@ int reduce_launch(mxb_context *h, int kop, const mxb_expr_t &e, const ExprInfo &
         p.ws = h->ws;
         p.tickets = h->tickets;
       }
-      grid = (unsigned)std::min<int64_t>(B * S, (int64_t)sm * 8);
+      grid = (unsigned)std::min<int64_t>(B * S, (int64_t)sm * cps);
     } else {
       const int64_t wpb = block / 32;
-      grid = (unsigned)std::min<int64_t>((B + wpb - 1) / wpb, (int64_t)sm * 8);
+      grid = (unsigned)std::min<int64_t>((B + wpb - 1) / wpb, (int64_t)sm * cps);
     }
   } else {  // FAM_RED_OUTER
     const int64_t C = p.bsz[p.nb - 1];
     const int64_t cv = (C + spec.V - 1) / spec.V;
     int tx = 1;
-    while (tx < 128 && tx < cv) tx <<= 1;
+    const int txmax = tune_tx > 0 ? tune_tx : 128;
+    while (tx < txmax && tx < cv && tx < (int)block) tx <<= 1;
     p.tx = tx;
     const int ty = (int)block / tx;
     smem = ty > 1 ? (unsigned)(ty * tx * spec.V * acc_bytes(kop, info.value_dtype)) : 0;
     const int64_t tile = (int64_t)tx * spec.V;
     const int64_t work = (B / C) * ((C + tile - 1) / tile);
-    grid = (unsigned)std::min<int64_t>(work, (int64_t)sm * 8);
+    grid = (unsigned)std::min<int64_t>(work, (int64_t)sm * (tune_cps > 0 ? tune_cps : 8));
   }
 
   Kernel k;
@@ -737,7 +749,7 @@ int mxb_elementwise(mxb_handle_t h, const mxb_expr_t *expr_in, const mxb_out_t *
 
   const int nl = e.n_leaves;
   const int obytes = dtype_bytes(out->dtype);
-  int vmax = policy_vmax(info);
+  int vmax = env_int("MXB_TUNE_V", 0) > 0 ? env_int("MXB_TUNE_V", 0) : policy_vmax(info);
   // the store must fit one instruction too (STG.256 at most)
   while (vmax > 1 && vmax * obytes > 32) vmax >>= 1;
   auto vec_ok = [&](int V) {
@@ -759,6 +771,7 @@ int mxb_elementwise(mxb_handle_t h, const mxb_expr_t *expr_in, const mxb_out_t *
   spec.out_dtype = out->dtype;
   spec.V = (vmax > 1 && vec_ok(vmax)) ? vmax : 1;
   spec.U = policy_unroll(info, spec.V, FAM_EW);
+  if (env_int("MXB_TUNE_U", 0) > 0) spec.U = env_int("MXB_TUNE_U", 0);
 
   EwParams p;
   memset(&p, 0, sizeof p);
@@ -779,10 +792,11 @@ int mxb_elementwise(mxb_handle_t h, const mxb_expr_t *expr_in, const mxb_out_t *
   }
   fill_consts(e, p.c);
 
-  const unsigned block = 256;
+  const unsigned block = env_int("MXB_TUNE_BLOCK", 0) > 0 ? (unsigned)env_int("MXB_TUNE_BLOCK", 0) : 256u;
   const int64_t items = (N + spec.V - 1) / spec.V;
   const int64_t want = (items + (int64_t)block * spec.U - 1) / ((int64_t)block * spec.U);
-  const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)h->sm_count * 8));
+  const int ew_cps = env_int("MXB_TUNE_CTAS_PER_SM", 0) > 0 ? env_int("MXB_TUNE_CTAS_PER_SM", 0) : 8;
+  const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)h->sm_count * ew_cps));
   Kernel k;
   st = get_kernel(info, spec, &k);
   if (st != MXB_OK) return st;

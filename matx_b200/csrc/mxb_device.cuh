@@ -153,7 +153,7 @@ template <> struct LdBytes<16> {
 template <> struct LdBytes<32> {  // LDG.E.256 on sm_100
   static __device__ __forceinline__ void ld(void *d, const void *s) {
     u32 r0, r1, r2, r3, r4, r5, r6, r7;
-    asm("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+    asm("ld.global.nc.L1::no_allocate.L2::256B.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3), "=r"(r4), "=r"(r5), "=r"(r6), "=r"(r7) : "l"(s));
     u32 *o = (u32 *)d;
     o[0] = r0; o[1] = r1; o[2] = r2; o[3] = r3; o[4] = r4; o[5] = r5; o[6] = r6; o[7] = r7;

@@ -95,9 +95,36 @@ def build_ref(cuda: bool = False, force: bool = False) -> str | None:
     return lib
 
 
+DROPIN_BIN = os.path.join(OUT_REF, "dropin_test")
+
+
+def build_dropin(force: bool = False) -> str | None:
+    """tests/cpp/dropin_test.cu: unmodified MatX statements on matx::cudaExecutor vs matx::b200Executor (the header
+    shim include/matx_b200/executor.h over libmatx_b200.so).  Needs /root/reference; the binary travels to the GPU box."""
+    root = os.path.dirname(HERE)
+    src = os.path.join(root, "tests", "cpp", "dropin_test.cu")
+    shim = os.path.join(root, "include", "matx_b200", "executor.h")
+    lib = os.path.join(root, "matx_b200", "libmatx_b200.so")
+    if not reference_available():
+        return DROPIN_BIN if os.path.exists(DROPIN_BIN) else None
+    if not os.path.exists(lib):
+        raise RuntimeError("build matx_b200/libmatx_b200.so first (python -m matx_b200.build)")
+    newest = max(os.path.getmtime(src), os.path.getmtime(shim), os.path.getmtime(os.path.join(root, "include", "matx_b200.h")))
+    if not force and os.path.exists(DROPIN_BIN) and os.path.getmtime(DROPIN_BIN) >= newest:
+        return DROPIN_BIN
+    os.makedirs(OUT_REF, exist_ok=True)
+    cmd = _nvcc_base(False) + ["-I" + os.path.join(root, "include"), src, "-o", DROPIN_BIN, "-L" + os.path.join(root, "matx_b200"),
+                               "-lmatx_b200", "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN/../../matx_b200",
+                               "-lcublas", "-lcublasLt", "-lcufft", "-lcurand", "-lcusolver", "-lcusparse", "-lcuda"]
+    _run(cmd)
+    return DROPIN_BIN
+
+
 if __name__ == "__main__":
     force = "--force" in sys.argv
     print(build_oracle(force))
     print(build_ref(False, force))
     if "--cuda" in sys.argv:
         print(build_ref(True, force))
+    if "--dropin" in sys.argv:
+        print(build_dropin(force))

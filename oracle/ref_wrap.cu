@@ -18,8 +18,10 @@ using namespace matx;
 
 #ifdef MREF_CUDA
 #define MREF_SUFFIX _cuda
+static constexpr bool kCuda = true;   // the reference's CUB path does not compile any()/all() of a complex tensor
 #else
 #define MREF_SUFFIX _host
+static constexpr bool kCuda = false;
 #endif
 
 #define MREF_CAT2(a, b) a##b
@@ -88,8 +90,8 @@ static void reduce_stmt(Exec &ex, int op, void *in, const int64_t *shape, const 
       case R_SUM: (o = sum(v)).run(ex); break;
       case R_MEAN: if constexpr (!half) { (o = mean(v)).run(ex); } break;
       case R_PROD: if constexpr (!half) { (o = prod(v)).run(ex); } break;
-      case R_ANY: (o = any(v)).run(ex); break;
-      case R_ALL: (o = all(v)).run(ex); break;
+      case R_ANY: if constexpr (!(cplx && kCuda)) { (o = any(v)).run(ex); } break;
+      case R_ALL: if constexpr (!(cplx && kCuda)) { (o = all(v)).run(ex); } break;
       case R_VAR: if constexpr (!std::is_integral_v<T> && !half) { (orl = var(v, ddof)).run(ex); } break;
       case R_STDD: if constexpr (!std::is_integral_v<T> && !half) { (orl = stdd(v, ddof)).run(ex); } break;
       default:
@@ -109,8 +111,8 @@ static void reduce_stmt(Exec &ex, int op, void *in, const int64_t *shape, const 
       case R_SUM: (o = sum(v, dims)).run(ex); break;
       case R_MEAN: if constexpr (!half) { (o = mean(v, dims)).run(ex); } break;
       case R_PROD: if constexpr (!half) { (o = prod(v, dims)).run(ex); } break;
-      case R_ANY: (o = any(v, dims)).run(ex); break;
-      case R_ALL: (o = all(v, dims)).run(ex); break;
+      case R_ANY: if constexpr (!(cplx && kCuda)) { (o = any(v, dims)).run(ex); } break;
+      case R_ALL: if constexpr (!(cplx && kCuda)) { (o = all(v, dims)).run(ex); } break;
       case R_VAR: if constexpr (!std::is_integral_v<T> && !half) { (orl = var(v, dims, ddof)).run(ex); } break;
       case R_STDD: if constexpr (!std::is_integral_v<T> && !half) { (orl = stdd(v, dims, ddof)).run(ex); } break;
       default:

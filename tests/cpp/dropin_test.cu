@@ -1,0 +1,258 @@
+// dropin_test.cu — the drop-in proof: UNMODIFIED MatX statements run twice, once with the reference's
+// matx::cudaExecutor (CUB path) and once with matx::b200Executor (libmatx_b200.so), on the same inputs, and the
+// results are compared.  Also prints which native kernel served each statement.  Built here against the reference
+// headers by oracle/build_ref.py --dropin (into oracle/_ref/dropin_test), executed on the GPU box by
+// tests/test_gpu_dropin.py.  With `--bench` it times both executors on the BASELINE.json configs (A/B on one box).
+#include <matx.h>
+#include <matx_b200/executor.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <random>
+#include <vector>
+
+using namespace matx;
+using cf = cuda::std::complex<float>;
+
+static int g_fail = 0, g_pass = 0;
+static void report(const char *name, bool ok, const char *kernel, double err = 0.0) {
+  printf("%s %-44s err=%.3g kernel=%s\n", ok ? "PASS" : "FAIL", name, err, kernel && *kernel ? kernel : "(reference fallback)");
+  (ok ? g_pass : g_fail)++;
+}
+template <class T> static double max_rel(const T &a, const T &b, index_t n) {
+  double m = 0;
+  for (index_t i = 0; i < n; ++i) {
+    const double x = static_cast<double>(a(i)), y = static_cast<double>(b(i));
+    m = std::max(m, std::fabs(x - y) / std::max(std::fabs(y), 1e-30));
+  }
+  return m;
+}
+
+static void fill_uniform(tensor_t<float, 2> &t, unsigned seed, float lo, float hi) {
+  std::mt19937 g(seed);
+  std::uniform_real_distribution<float> d(lo, hi);
+  for (index_t i = 0; i < t.Size(0); ++i) for (index_t j = 0; j < t.Size(1); ++j) t(i, j) = d(g);
+}
+
+static int run_checks() {
+  cudaStream_t stream;
+  cudaStreamCreate(&stream);
+  cudaExecutor ref{stream};
+  b200Executor b200{stream};
+
+  // ---- config 1: (out = sum(a*b+c, {1})).run(exec) ----
+  {
+    const index_t rows = 64, cols = 4096;
+    auto a = make_tensor<float>({rows, cols}), b = make_tensor<float>({rows, cols}), c = make_tensor<float>({rows, cols});
+    fill_uniform(a, 1, 0.f, 1.f); fill_uniform(b, 2, 0.f, 1.f); fill_uniform(c, 3, -0.5f, 0.5f);
+    auto o1 = make_tensor<float>({rows}), o2 = make_tensor<float>({rows});
+    (o1 = sum(a * b + c, {1})).run(ref);
+    (o2 = sum(a * b + c, {1})).run(b200);
+    ref.sync();
+    const double e = max_rel(o2, o1, rows);
+    report("sum(a*b+c,{1}) fp32 64x4096", e <= 1e-5 && *b200.last_kernel(), b200.last_kernel(), e);
+
+    // mean / var / stdd / max / min / any / all over the same rows
+    auto v1 = make_tensor<float>({rows}), v2 = make_tensor<float>({rows});
+    (v1 = mean(a, {1})).run(ref); (v2 = mean(a, {1})).run(b200); ref.sync();
+    report("mean(a,{1})", max_rel(v2, v1, rows) <= 1e-5 && *b200.last_kernel(), b200.last_kernel(), max_rel(v2, v1, rows));
+    (v1 = var(a, {1}, 1)).run(ref); (v2 = var(a, {1}, 1)).run(b200); ref.sync();
+    report("var(a,{1})", max_rel(v2, v1, rows) <= 2e-5 && *b200.last_kernel(), b200.last_kernel(), max_rel(v2, v1, rows));
+    (v1 = stdd(a, {1}, 1)).run(ref); (v2 = stdd(a, {1}, 1)).run(b200); ref.sync();
+    report("stdd(a,{1})", max_rel(v2, v1, rows) <= 2e-5 && *b200.last_kernel(), b200.last_kernel(), max_rel(v2, v1, rows));
+    (v1 = max(a, {1})).run(ref); (v2 = max(a, {1})).run(b200); ref.sync();
+    report("max(a,{1}) bit-exact", max_rel(v2, v1, rows) == 0 && *b200.last_kernel(), b200.last_kernel());
+    (v1 = min(a, {1})).run(ref); (v2 = min(a, {1})).run(b200); ref.sync();
+    report("min(a,{1}) bit-exact", max_rel(v2, v1, rows) == 0 && *b200.last_kernel(), b200.last_kernel());
+    // permuted view: reduce the OUTER dim (strided), PermutedReduce of ReductionTests.cu:353-573
+    auto w1 = make_tensor<float>({cols}), w2 = make_tensor<float>({cols});
+    (w1 = sum(a, {0})).run(ref); (w2 = sum(a, {0})).run(b200); ref.sync();
+    report("sum(a,{0}) strided reduce dim", max_rel(w2, w1, cols) <= 1e-5 && *b200.last_kernel(), b200.last_kernel(), max_rel(w2, w1, cols));
+    (w1 = sum(permute(a, {1, 0}), {1})).run(ref); (w2 = sum(permute(a, {1, 0}), {1})).run(b200); ref.sync();
+    report("sum(permute(a,{1,0}),{1})", max_rel(w2, w1, cols) <= 1e-5 && *b200.last_kernel(), b200.last_kernel(), max_rel(w2, w1, cols));
+    // full reductions to a rank-0 tensor
+    auto s1 = make_tensor<float>({}), s2 = make_tensor<float>({});
+    (s1 = sum(a)).run(ref); (s2 = sum(a)).run(b200); ref.sync();
+    report("sum(a) full", std::fabs(s2() - s1()) <= 1e-5 * std::fabs(s1()) && *b200.last_kernel(), b200.last_kernel(), std::fabs(s2() - s1()) / s1());
+    auto i1 = make_tensor<index_t>({}), i2 = make_tensor<index_t>({});
+    (mtie(s1, i1) = argmax(a)).run(ref); (mtie(s2, i2) = argmax(a)).run(b200); ref.sync();
+    report("mtie(v,i)=argmax(a) full", s1() == s2() && i1() == i2() && *b200.last_kernel(), b200.last_kernel());
+    auto ir1 = make_tensor<index_t>({rows}), ir2 = make_tensor<index_t>({rows});
+    (mtie(v1, ir1) = argmin(a, {1})).run(ref); (mtie(v2, ir2) = argmin(a, {1})).run(b200); ref.sync();
+    bool same = true;
+    for (index_t r = 0; r < rows; ++r) same = same && v1(r) == v2(r) && ir1(r) == ir2(r);
+    report("mtie(v,i)=argmin(a,{1}) absolute index", same && *b200.last_kernel(), b200.last_kernel());
+    (v1 = any(a > 0.9999f, {1})).run(ref); (v2 = any(a > 0.9999f, {1})).run(b200); ref.sync();
+    report("any(a>0.9999f,{1})", max_rel(v2, v1, rows) == 0 && *b200.last_kernel(), b200.last_kernel());
+    // elementwise with broadcast scalar, unary chain
+    auto e1 = make_tensor<float>({rows, cols}), e2 = make_tensor<float>({rows, cols});
+    (e1 = sqrt(a) * 2.f + exp(-b) / (c * c + 1.f)).run(ref);
+    (e2 = sqrt(a) * 2.f + exp(-b) / (c * c + 1.f)).run(b200);
+    ref.sync();
+    double em = 0;
+    for (index_t i = 0; i < rows; ++i) for (index_t j = 0; j < cols; j += 17) em = std::max(em, std::fabs((double)e1(i, j) - e2(i, j)) / std::fabs(e1(i, j)));
+    report("elementwise sqrt/exp/div chain", em <= 1e-6 && *b200.last_kernel(), b200.last_kernel(), em);
+  }
+  // ---- config 3: complex rows ----
+  {
+    const index_t rows = 32, cols = 8192;
+    auto x = make_tensor<cf>({rows, cols});
+    std::mt19937 g(5);
+    std::normal_distribution<float> d(0.f, 1.f);
+    for (index_t i = 0; i < rows; ++i) for (index_t j = 0; j < cols; ++j) x(i, j) = cf(d(g), d(g));
+    auto v1 = make_tensor<float>({rows}), v2 = make_tensor<float>({rows});
+    auto i1 = make_tensor<index_t>({rows}), i2 = make_tensor<index_t>({rows});
+    (mtie(v1, i1) = argmax(abs2(x), {1})).run(ref); (mtie(v2, i2) = argmax(abs2(x), {1})).run(b200); ref.sync();
+    bool same = true;
+    for (index_t r = 0; r < rows; ++r) same = same && i1(r) == i2(r);
+    report("argmax(abs2(x),{1}) complex<float>", same && max_rel(v2, v1, rows) <= 1e-6 && *b200.last_kernel(), b200.last_kernel(), max_rel(v2, v1, rows));
+    (v1 = var(x, {1}, 1)).run(ref); (v2 = var(x, {1}, 1)).run(b200); ref.sync();
+    report("var(x,{1}) complex<float> -> float", max_rel(v2, v1, rows) <= 2e-5 && *b200.last_kernel(), b200.last_kernel(), max_rel(v2, v1, rows));
+    auto m1 = make_tensor<cf>({rows}), m2 = make_tensor<cf>({rows});
+    (m1 = mean(x, {1})).run(ref); (m2 = mean(x, {1})).run(b200); ref.sync();
+    double em = 0;
+    for (index_t r = 0; r < rows; ++r) em = std::max(em, (double)cuda::std::abs(m1(r) - m2(r)));
+    report("mean(x,{1}) complex<float>", em <= 1e-5 && *b200.last_kernel(), b200.last_kernel(), em);
+  }
+  // ---- config 4: Black-Scholes expression of examples/black_scholes.cu:122-138 ----
+  {
+    const index_t n = 1 << 16;
+    auto K = make_tensor<float>({n}), S = make_tensor<float>({n}), V = make_tensor<float>({n}), r = make_tensor<float>({n}), T = make_tensor<float>({n});
+    std::mt19937 g(6);
+    std::uniform_real_distribution<float> u(0.f, 1.f);
+    for (index_t i = 0; i < n; ++i) { S(i) = 10 + 90 * u(g); K(i) = 10 + 90 * u(g); V(i) = 0.05f + 0.45f * u(g); r(i) = 0.01f + 0.09f * u(g); T(i) = 0.1f + 1.9f * u(g); }
+    auto o1 = make_tensor<float>({n}), o2 = make_tensor<float>({n});
+    auto bs = [&](auto &out, auto &exec) {
+      auto VsqrtT = V * sqrt(T);
+      auto d1 = (log(S / K) + (r + 0.5f * V * V) * T) / VsqrtT;
+      auto d2 = d1 - VsqrtT;
+      auto cdf_d1 = normcdf(d1);
+      auto cdf_d2 = normcdf(d2);
+      auto expRT = exp(-1.f * r * T);
+      (out = S * cdf_d1 - K * expRT * cdf_d2).run(exec);
+    };
+    bs(o1, ref); bs(o2, b200); ref.sync();
+    double em = 0;
+    for (index_t i = 0; i < n; ++i) em = std::max(em, std::fabs((double)o1(i) - o2(i)));
+    report("black_scholes expression (abs err)", em <= 1e-4 && *b200.last_kernel(), b200.last_kernel(), em);
+  }
+  // ---- config 5: bf16, reduce over a permuted non-contiguous dim ----
+  {
+    const index_t d0 = 16, d1 = 96, d2 = 256;
+    auto t = make_tensor<matxBf16>({d0, d1, d2});
+    std::mt19937 g(11);
+    std::uniform_real_distribution<float> u(0.f, 0.25f);
+    for (index_t i = 0; i < d0; ++i) for (index_t j = 0; j < d1; ++j) for (index_t k = 0; k < d2; ++k) t(i, j, k) = matxBf16(u(g));
+    auto o1 = make_tensor<matxBf16>({d2, d0}), o2 = make_tensor<matxBf16>({d2, d0});
+    (o1 = sum(permute(t, {2, 0, 1}), {2})).run(ref); (o2 = sum(permute(t, {2, 0, 1}), {2})).run(b200); ref.sync();
+    double em = 0, et = 0;
+    for (index_t i = 0; i < d2; ++i) for (index_t j = 0; j < d0; ++j) {
+      double truth = 0;
+      for (index_t k = 0; k < d1; ++k) truth += static_cast<float>(t(j, k, i));
+      em = std::max(em, std::fabs((double)static_cast<float>(o1(i, j)) - static_cast<float>(o2(i, j))) / truth);
+      et = std::max(et, std::fabs((double)static_cast<float>(o2(i, j)) - truth) / truth);
+    }
+    report("sum(permute(t,{2,0,1}),{2}) bf16 vs reference (1e-2)", em <= 1e-2 && *b200.last_kernel(), b200.last_kernel(), em);
+    report("sum(permute(t,{2,0,1}),{2}) bf16 vs fp64 truth (2^-8)", et <= 1.0 / 256, b200.last_kernel(), et);
+  }
+  // ---- a node the shim does not lower falls back to the reference, same answer ----
+  {
+    auto a = make_tensor<float>({1000});
+    for (index_t i = 0; i < 1000; ++i) a(i) = float(i % 37);
+    auto o1 = make_tensor<float>({1000}), o2 = make_tensor<float>({1000});
+    (o1 = shift<0>(a, 3) + 1.f).run(ref); (o2 = shift<0>(a, 3) + 1.f).run(b200); ref.sync();
+    report("unknown node (shift) falls back", max_rel(o2, o1, 1000) == 0, "");
+  }
+  printf("SUMMARY pass=%d fail=%d native_launches=%lld\n", g_pass, g_fail, b200.native_launches());
+  return g_fail;
+}
+
+template <class F> static float time_ms(cudaStream_t s, int iters, F &&f) {
+  cudaEvent_t a, b;
+  cudaEventCreate(&a); cudaEventCreate(&b);
+  f(); f();
+  cudaStreamSynchronize(s);
+  cudaEventRecord(a, s);
+  for (int i = 0; i < iters; ++i) f();
+  cudaEventRecord(b, s);
+  cudaEventSynchronize(b);
+  float ms;
+  cudaEventElapsedTime(&ms, a, b);
+  return ms / iters;
+}
+
+static void run_bench() {
+  cudaStream_t stream;
+  cudaStreamCreate(&stream);
+  cudaExecutor ref{stream};
+  b200Executor b200{stream};
+  auto line = [](const char *cfg, const char *op, double bytes, float ms_ref, float ms_new) {
+    printf("BENCH {\"config\": \"%s\", \"op\": \"%s\", \"algorithmic_bytes\": %.0f, \"reference_cudaExecutor_ms\": %.4f, \"b200Executor_ms\": %.4f, "
+           "\"reference_GBps\": %.1f, \"b200_GBps\": %.1f, \"speedup\": %.2f}\n",
+           cfg, op, bytes, ms_ref, ms_new, bytes / ms_ref / 1e6, bytes / ms_new / 1e6, ms_ref / ms_new);
+    fflush(stdout);
+  };
+  {  // C2
+    const index_t n = index_t(1) << 30;
+    auto x = make_tensor<float>({n}, MATX_DEVICE_MEMORY);
+    (x = random<float>({n}, UNIFORM)).run(ref);
+    auto s = make_tensor<float>({}, MATX_DEVICE_MEMORY);
+    auto i = make_tensor<index_t>({}, MATX_DEVICE_MEMORY);
+    line("C2 fp32 2^30", "sum", n * 4.0, time_ms(stream, 10, [&] { (s = sum(x)).run(ref); }), time_ms(stream, 10, [&] { (s = sum(x)).run(b200); }));
+    line("C2 fp32 2^30", "max", n * 4.0, time_ms(stream, 10, [&] { (s = max(x)).run(ref); }), time_ms(stream, 10, [&] { (s = max(x)).run(b200); }));
+    line("C2 fp32 2^30", "argmax", n * 4.0, time_ms(stream, 10, [&] { (mtie(s, i) = argmax(x)).run(ref); }), time_ms(stream, 10, [&] { (mtie(s, i) = argmax(x)).run(b200); }));
+  }
+  {  // C1
+    const index_t rows = 16384, cols = 4096;
+    auto a = make_tensor<float>({rows, cols}, MATX_DEVICE_MEMORY), b = make_tensor<float>({rows, cols}, MATX_DEVICE_MEMORY), c = make_tensor<float>({rows, cols}, MATX_DEVICE_MEMORY);
+    (a = random<float>({rows, cols}, UNIFORM)).run(ref); (b = random<float>({rows, cols}, UNIFORM)).run(ref); (c = random<float>({rows, cols}, UNIFORM)).run(ref);
+    auto o = make_tensor<float>({rows}, MATX_DEVICE_MEMORY);
+    line("C1 fp32 16384x4096", "sum(a*b+c,{1})", 3.0 * rows * cols * 4 + rows * 4, time_ms(stream, 10, [&] { (o = sum(a * b + c, {1})).run(ref); }),
+         time_ms(stream, 10, [&] { (o = sum(a * b + c, {1})).run(b200); }));
+  }
+  {  // C3
+    const index_t rows = 65536, cols = 8192;
+    auto x = make_tensor<cf>({rows, cols}, MATX_DEVICE_MEMORY);
+    (x = random<cf>({rows, cols}, NORMAL)).run(ref);
+    auto m = make_tensor<cf>({rows}, MATX_DEVICE_MEMORY);
+    auto v = make_tensor<float>({rows}, MATX_DEVICE_MEMORY);
+    auto i = make_tensor<index_t>({rows}, MATX_DEVICE_MEMORY);
+    const double bytes = 8.0 * rows * cols;
+    line("C3 c64 65536x8192", "mean(x,{1})", bytes, time_ms(stream, 5, [&] { (m = mean(x, {1})).run(ref); }), time_ms(stream, 5, [&] { (m = mean(x, {1})).run(b200); }));
+    line("C3 c64 65536x8192", "var(x,{1})", bytes, time_ms(stream, 5, [&] { (v = var(x, {1}, 1)).run(ref); }), time_ms(stream, 5, [&] { (v = var(x, {1}, 1)).run(b200); }));
+    line("C3 c64 65536x8192", "argmax(abs2(x),{1})", bytes, time_ms(stream, 5, [&] { (mtie(v, i) = argmax(abs2(x), {1})).run(ref); }),
+         time_ms(stream, 5, [&] { (mtie(v, i) = argmax(abs2(x), {1})).run(b200); }));
+  }
+  {  // C4
+    const index_t n = index_t(1) << 28;
+    auto K = make_tensor<float>({n}, MATX_DEVICE_MEMORY), S = make_tensor<float>({n}, MATX_DEVICE_MEMORY), V = make_tensor<float>({n}, MATX_DEVICE_MEMORY),
+         r = make_tensor<float>({n}, MATX_DEVICE_MEMORY), T = make_tensor<float>({n}, MATX_DEVICE_MEMORY), out = make_tensor<float>({n}, MATX_DEVICE_MEMORY);
+    (S = random<float>({n}, UNIFORM) * 90.f + 10.f).run(ref); (K = random<float>({n}, UNIFORM) * 90.f + 10.f).run(ref);
+    (V = random<float>({n}, UNIFORM) * 0.45f + 0.05f).run(ref); (r = random<float>({n}, UNIFORM) * 0.09f + 0.01f).run(ref);
+    (T = random<float>({n}, UNIFORM) * 1.9f + 0.1f).run(ref);
+    auto bs = [&](auto &exec) {
+      auto VsqrtT = V * sqrt(T);
+      auto d1 = (log(S / K) + (r + 0.5f * V * V) * T) / VsqrtT;
+      auto d2 = d1 - VsqrtT;
+      (out = S * normcdf(d1) - K * exp(-1.f * r * T) * normcdf(d2)).run(exec);
+    };
+    line("C4 fp32 2^28", "black_scholes", 6.0 * n * 4, time_ms(stream, 5, [&] { bs(ref); }), time_ms(stream, 5, [&] { bs(b200); }));
+    line("vector_add fp32 2^28", "out = S + K", 3.0 * n * 4, time_ms(stream, 5, [&] { (out = S + K).run(ref); }), time_ms(stream, 5, [&] { (out = S + K).run(b200); }));
+  }
+  {  // C5
+    const index_t d = 1024;
+    auto t = make_tensor<matxBf16>({d, d, d}, MATX_DEVICE_MEMORY);
+    (t = as_type<matxBf16>(random<float>({d, d, d}, UNIFORM) * 0.25f)).run(ref);
+    auto o = make_tensor<matxBf16>({d, d}, MATX_DEVICE_MEMORY);
+    line("C5 bf16 1024^3", "sum(permute(t,{2,0,1}),{2})", 2.0 * d * d * d + 2.0 * d * d, time_ms(stream, 3, [&] { (o = sum(permute(t, {2, 0, 1}), {2})).run(ref); }),
+         time_ms(stream, 5, [&] { (o = sum(permute(t, {2, 0, 1}), {2})).run(b200); }));
+  }
+}
+
+int main(int argc, char **argv) {
+  MATX_ENTER_HANDLER();
+  if (argc > 1 && !strcmp(argv[1], "--bench")) { run_bench(); return 0; }
+  return run_checks() ? 1 : 0;
+  MATX_EXIT_HANDLER();
+}
