@@ -124,11 +124,38 @@ struct Builder {
   mxb_expr_t e;
   bool ok = true;
   Builder() { std::memset(&e, 0, sizeof e); }
+  // Expression templates hold their operands by value, so `auto d1 = ...;` used twice arrives as two identical
+  // sub-trees: nodes, leaves and constants are hash-consed here and the program becomes a DAG again (every distinct
+  // tensor view is one leaf, i.e. one load per element — the reference re-loads it per occurrence,
+  // examples/black_scholes.cu:42-49).
   int node(int opcode, int s0, int s1 = -1, int aux = 0) {
+    for (int i = 0; i < e.n_nodes; ++i) {
+      const mxb_node_t &n = e.nodes[i];
+      if (n.opcode == opcode && n.src[0] == s0 && n.src[1] == s1 && n.aux == aux) return i;
+    }
     if (e.n_nodes >= MXB_MAX_NODES) { ok = false; return 0; }
     mxb_node_t &n = e.nodes[e.n_nodes];
     n.opcode = opcode; n.src[0] = s0; n.src[1] = s1; n.aux = aux;
     return e.n_nodes++;
+  }
+  int leaf(const mxb_leaf_t &lf) {
+    for (int k = 0; k < e.n_leaves; ++k) {
+      if (e.leaves[k].data == lf.data && e.leaves[k].dtype == lf.dtype &&
+          std::memcmp(e.leaves[k].stride, lf.stride, sizeof lf.stride) == 0) return node(MXB_OP_LEAF, k);
+    }
+    if (e.n_leaves >= MXB_MAX_LEAVES) { ok = false; return 0; }
+    e.leaves[e.n_leaves] = lf;
+    return node(MXB_OP_LEAF, e.n_leaves++);
+  }
+  int constant(double re, double im, int dtype) {
+    for (int k = 0; k < e.n_consts; ++k) {
+      if (e.consts[k].dtype == dtype && std::memcmp(&e.consts[k].re, &re, sizeof re) == 0 && std::memcmp(&e.consts[k].im, &im, sizeof im) == 0)
+        return node(MXB_OP_CONST, k);
+    }
+    if (e.n_consts >= MXB_MAX_CONSTS) { ok = false; return 0; }
+    mxb_const_t &c = e.consts[e.n_consts];
+    c.re = re; c.im = im; c.dtype = dtype;
+    return node(MXB_OP_CONST, e.n_consts++);
   }
 };
 
@@ -136,19 +163,15 @@ struct Builder {
 template <class Op0> int lower(Builder &b, const Op0 &op, const int *axes) {
   using Op = remove_cvref_t<Op0>;
   if constexpr (std::is_arithmetic_v<Op> || std::is_same_v<Op, cuda::std::complex<float>>) {
-    if (b.e.n_consts >= MXB_MAX_CONSTS) { b.ok = false; return 0; }
-    mxb_const_t &c = b.e.consts[b.e.n_consts];
-    if constexpr (std::is_arithmetic_v<Op>) { c.re = static_cast<double>(op); c.im = 0; }
-    else { c.re = op.real(); c.im = op.imag(); }
-    c.dtype = dtype_of<Op>::value;
-    return b.node(MXB_OP_CONST, b.e.n_consts++);
+    if constexpr (std::is_arithmetic_v<Op>) return b.constant(static_cast<double>(op), 0.0, dtype_of<Op>::value);
+    else return b.constant(op.real(), op.imag(), dtype_of<Op>::value);
   } else if constexpr (is_tensor_view_v<Op> || matx::is_tensor_impl_v<Op>) {
-    if (b.e.n_leaves >= MXB_MAX_LEAVES) { b.ok = false; return 0; }
-    mxb_leaf_t &lf = b.e.leaves[b.e.n_leaves];
+    mxb_leaf_t lf;
+    std::memset(&lf, 0, sizeof lf);
     lf.data = op.Data();
     lf.dtype = dtype_of<typename Op::value_type>::value;
     for (int d = 0; d < Op::Rank(); ++d) lf.stride[axes[d]] += op.Stride(d);
-    return b.node(MXB_OP_LEAF, b.e.n_leaves++);
+    return b.leaf(lf);
   } else if constexpr (node_kind<Op>::value == 1) {
     using K = node_kind<Op>;
     static_assert(sizeof(typename K::Mirror) == sizeof(Op), "matxBinaryOp layout changed: update the mirror");

@@ -135,7 +135,7 @@ static int run_checks() {
     bs(o1, ref); bs(o2, b200); ref.sync();
     double em = 0;
     for (index_t i = 0; i < n; ++i) em = std::max(em, std::fabs((double)o1(i) - o2(i)));
-    report("black_scholes expression (abs err)", em <= 1e-4 && *b200.last_kernel(), b200.last_kernel(), em);
+    report("black_scholes expression (abs err)", em <= 1e-4 && !strncmp(b200.last_kernel(), "ew|", 3), b200.last_kernel(), em);
   }
   // ---- config 5: bf16, reduce over a permuted non-contiguous dim ----
   {
@@ -146,14 +146,18 @@ static int run_checks() {
     for (index_t i = 0; i < d0; ++i) for (index_t j = 0; j < d1; ++j) for (index_t k = 0; k < d2; ++k) t(i, j, k) = matxBf16(u(g));
     auto o1 = make_tensor<matxBf16>({d2, d0}), o2 = make_tensor<matxBf16>({d2, d0});
     (o1 = sum(permute(t, {2, 0, 1}), {2})).run(ref); (o2 = sum(permute(t, {2, 0, 1}), {2})).run(b200); ref.sync();
-    double em = 0, et = 0;
+    // The reference accumulates in bf16 (core/type_utils_both.h:738-746), so ITS distance to the fp64 truth of the
+    // same bf16 inputs is ~1e-2; this path accumulates in fp32 and rounds once.  Report all three distances.
+    double em = 0, et = 0, er = 0;
     for (index_t i = 0; i < d2; ++i) for (index_t j = 0; j < d0; ++j) {
       double truth = 0;
       for (index_t k = 0; k < d1; ++k) truth += static_cast<float>(t(j, k, i));
       em = std::max(em, std::fabs((double)static_cast<float>(o1(i, j)) - static_cast<float>(o2(i, j))) / truth);
       et = std::max(et, std::fabs((double)static_cast<float>(o2(i, j)) - truth) / truth);
+      er = std::max(er, std::fabs((double)static_cast<float>(o1(i, j)) - truth) / truth);
     }
-    report("sum(permute(t,{2,0,1}),{2}) bf16 vs reference (1e-2)", em <= 1e-2 && *b200.last_kernel(), b200.last_kernel(), em);
+    printf("     bf16 distances: |b200-ref|=%.3g  |b200-fp64|=%.3g  |ref-fp64|=%.3g\n", em, et, er);
+    report("sum(permute(t,{2,0,1}),{2}) bf16 vs reference", em <= er + 1.0 / 256 && *b200.last_kernel(), b200.last_kernel(), em);
     report("sum(permute(t,{2,0,1}),{2}) bf16 vs fp64 truth (2^-8)", et <= 1.0 / 256, b200.last_kernel(), et);
   }
   // ---- a node the shim does not lower falls back to the reference, same answer ----
