@@ -314,6 +314,23 @@ int reduce_launch(mxb_context *h, int kop, const mxb_expr_t &e, const ExprInfo &
       }
       if (var_ipt) spec.family = FAM_VAR_REG;
     }
+    // plain tensor, long contiguous rows: TMA-staged ring of rows in shared memory (one HBM read, copy engine keeps
+    // rows in flight while the SM runs the two passes)
+    if (e.n_nodes == 1 && nl == 1 && gr.n == 1 && gr.ls[0][0] == 1 && !getenv("MXB_VAR_SMEM_ONLY") && !getenv("MXB_VAR_NO_TMA")) {
+      const int64_t esz = dtype_bytes(e.leaves[0].dtype);
+      const int64_t rowbytes = gr.size[0] * esz;
+      const int64_t rowstride = (rowbytes + 127) & ~int64_t(127);
+      bool ok = rowbytes % 16 == 0 && rowbytes >= env_int("MXB_VAR_TMA_MIN_ROW", 16 * 1024) && aligned_to(e.leaves[0].data, 16) && rowbytes < (1 << 20);
+      for (int d = 0; ok && d < gb.n; ++d) ok = (gb.ls[0][d] * esz) % 16 == 0;
+      int64_t stages = (((int64_t)h->max_smem_optin - 128 - 2048) / rowstride);
+      if (stages > 8) stages = 8;
+      if (env_int("MXB_TUNE_STAGES", 0) > 0 && env_int("MXB_TUNE_STAGES", 0) < stages) stages = env_int("MXB_TUNE_STAGES", 0);
+      if (ok && stages >= 2) {
+        spec.family = FAM_VAR_TMA;
+        spec.V = policy_vmax(info);
+        var_ipt = (int)stages;
+      }
+    }
   } else if (vmax > 1 && inner_ok(vmax)) {
     spec.family = FAM_RED_INNER;
     spec.V = vmax;
@@ -332,6 +349,7 @@ int reduce_launch(mxb_context *h, int kop, const mxb_expr_t &e, const ExprInfo &
   }
   spec.U = policy_unroll(info, spec.V, spec.family);
   if (spec.family == FAM_VAR_REG) spec.team = var_ipt;
+  if (spec.family == FAM_VAR_TMA) spec.team = 0;
   // development knobs (tools/sweep.py): override the unroll / launch shape; any combination is JIT-compiled on demand
   const int tune_u = env_int("MXB_TUNE_U", 0), tune_block = env_int("MXB_TUNE_BLOCK", 0), tune_cps = env_int("MXB_TUNE_CTAS_PER_SM", 0);
   const int tune_tx = env_int("MXB_TUNE_TX", 0);
@@ -394,7 +412,13 @@ int reduce_launch(mxb_context *h, int kop, const mxb_expr_t &e, const ExprInfo &
   const int sm = h->sm_count;
   unsigned grid = 1, block = tune_block > 0 ? (unsigned)tune_block : 256u, smem = 0;
   // persistent grids: CTAs per SM x SM count (every CTA loops over its share of the rows / tiles)
-  if (spec.family == FAM_VAR_REG) {
+  if (spec.family == FAM_VAR_TMA) {
+    const int64_t rowstride = (R * dtype_bytes(e.leaves[0].dtype) + 127) & ~int64_t(127);
+    p.splits = var_ipt;  // ring depth
+    if (tune_block <= 0) block = 512;
+    smem = (unsigned)(128 + (int64_t)var_ipt * rowstride);
+    grid = (unsigned)std::min<int64_t>(B, (int64_t)sm);
+  } else if (spec.family == FAM_VAR_REG) {
     block = (unsigned)var_threads;
     grid = (unsigned)std::min<int64_t>(B, (int64_t)sm * (tune_cps > 0 ? tune_cps : 32));
   } else if (spec.family == FAM_VAR_SMEM) {
@@ -431,7 +455,7 @@ int reduce_launch(mxb_context *h, int kop, const mxb_expr_t &e, const ExprInfo &
     const int64_t C = p.bsz[p.nb - 1];
     const int64_t cv = (C + spec.V - 1) / spec.V;
     int tx = 1;
-    const int txmax = tune_tx > 0 ? tune_tx : 128;
+    const int txmax = tune_tx > 0 ? tune_tx : 64;   // 64 x V columns per CTA, 4 reduce lanes (sweep: profiles/r1_sweeps.md)
     while (tx < txmax && tx < cv && tx < (int)block) tx <<= 1;
     p.tx = tx;
     const int ty = (int)block / tx;
@@ -795,8 +819,10 @@ int mxb_elementwise(mxb_handle_t h, const mxb_expr_t *expr_in, const mxb_out_t *
   const unsigned block = env_int("MXB_TUNE_BLOCK", 0) > 0 ? (unsigned)env_int("MXB_TUNE_BLOCK", 0) : 256u;
   const int64_t items = (N + spec.V - 1) / spec.V;
   const int64_t want = (items + (int64_t)block * spec.U - 1) / ((int64_t)block * spec.U);
-  const int ew_cps = env_int("MXB_TUNE_CTAS_PER_SM", 0) > 0 ? env_int("MXB_TUNE_CTAS_PER_SM", 0) : 8;
-  const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)h->sm_count * ew_cps));
+  // one U-batch per thread (no grid-stride wrap) unless told otherwise: the hardware block scheduler balances the
+  // SMs better than a static persistent loop for pure streaming (sweep: profiles/r1_sweeps.md)
+  const int ew_cps = env_int("MXB_TUNE_CTAS_PER_SM", 0) > 0 ? env_int("MXB_TUNE_CTAS_PER_SM", 0) : 1000000;
+  const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(want, (int64_t)h->sm_count * ew_cps), 0x7fffffff));
   Kernel k;
   st = get_kernel(info, spec, &k);
   if (st != MXB_OK) return st;

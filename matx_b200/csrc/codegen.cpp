@@ -327,24 +327,26 @@ int analyze_expr(const mxb_expr_t *e, ExprInfo *info, std::string *err) {
 // kernel instances
 // ---------------------------------------------------------------------------------------------------
 int policy_vmax(const ExprInfo &info) {
-  // widest leaf moves 16 bytes per load (LDG.128); narrower leaves ride along with fewer bytes
-  int v = 16 / info.max_leaf_bytes;
+  // Measured on B200 (profiles/r1_sweeps.md): for 2- and 4-byte elements LDG.128 per leaf is already at the HBM
+  // ceiling and LDG.256 changes nothing; for 8-byte elements (complex<float>, double) 32-byte loads cut the index /
+  // loop overhead per element and win 1-15 %.
+  int v = (info.max_leaf_bytes >= 8 ? 32 : 16) / info.max_leaf_bytes;
   if (v < 1) v = 1;
   if (v > 8) v = 8;
   return v;
 }
 int policy_unroll(const ExprInfo &info, int V, int family) {
-  (void)V;
+  const int bytes = V * info.max_leaf_bytes;  // widest load of one step
   if (family == FAM_RED_OUTER) return 4;
-  if (family == FAM_EW) return info.nleaf <= 2 ? 4 : 2;
-  if (family == FAM_VAR_SMEM) return 4;
-  if (family == FAM_VAR_REG) return 1;
-  return info.nleaf <= 2 ? 4 : 2;
+  if (family == FAM_VAR_REG || family == FAM_VAR_TMA) return 1;
+  if (family == FAM_VAR_SMEM) return bytes >= 32 ? 4 : 8;
+  if (family == FAM_EW) return bytes >= 32 ? (info.nleaf <= 2 ? 2 : 1) : (info.nleaf <= 2 ? 4 : 2);
+  return bytes >= 32 ? 2 : (info.nleaf <= 2 ? 4 : 2);
 }
 
 std::string kernel_key(const ExprInfo &info, const KernelSpec &s) {
   std::ostringstream k;
-  static const char *fam[] = {"red_inner", "red_outer", "var_smem", "ew", "var_reg"};
+  static const char *fam[] = {"red_inner", "red_outer", "var_smem", "ew", "var_reg", "var_tma"};
   k << fam[s.family] << "|" << info.name << "|" << (s.op >= 0 ? reduce_op_name(s.op) : "-") << "|" << dtype_name(s.out_dtype)
     << "|V" << s.V << "|U" << s.U << "|T" << s.team;
   return k.str();
@@ -398,6 +400,12 @@ int kernel_wrapper_src(const ExprInfo &info, const KernelSpec &s, const std::str
       if (!(info.value_dtype == MXB_F32 || info.value_dtype == MXB_F64 || cplx)) return fail("var of a non-floating expression");
       k << "extern \"C\" __global__ void __launch_bounds__(512) " << symbol
         << "(const __grid_constant__ mxb::RedParams p) { mxb::var_inner_reg_body<" << E << ", " << O << ", " << s.V << ", " << s.team << ">(p); }\n";
+      break;
+    case FAM_VAR_TMA:
+      if (info.nleaf != 1) return fail("var_tma serves plain tensors only");
+      if (!(info.value_dtype == MXB_F32 || info.value_dtype == MXB_F64 || cplx)) return fail("var of a non-floating expression");
+      k << "extern \"C\" __global__ void __launch_bounds__(1024) " << symbol
+        << "(const __grid_constant__ mxb::RedParams p) { mxb::var_inner_tma_body<" << dtype_ctype(info.leaf_dtype[0]) << ", " << O << ">(p); }\n";
       break;
     case FAM_EW:
       k << "extern \"C\" __global__ void __launch_bounds__(256) " << symbol

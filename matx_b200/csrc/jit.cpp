@@ -68,7 +68,7 @@ Dyn g_dyn;
 
 void *open_first(const std::vector<std::string> &names) {
   for (const std::string &n : names) {
-    void *h = dlopen(n.c_str(), RTLD_NOW | RTLD_GLOBAL);
+    void *h = dlopen(n.c_str(), RTLD_NOW | RTLD_LOCAL);
     if (h) return h;
   }
   return nullptr;
@@ -82,8 +82,12 @@ bool dyn_init(std::string *err) {
   std::vector<std::string> roots;
   for (const char *ev : {"MXB_CUDA_HOME", "CUDA_HOME", "CUDA_PATH"}) if (const char *v = getenv(ev)) roots.push_back(v);
   roots.push_back("/usr/local/cuda");
-  std::vector<std::string> nv = {"libnvrtc.so.12", "libnvrtc.so"};
+  // The toolkit's own NVRTC first, by absolute path: a bare "libnvrtc.so.12" resolves to whatever copy the process
+  // already holds (PyTorch bundles NVRTC 12.8, whose ptxas rejects the 256-bit loads of PTX ISA 8.8).
+  std::vector<std::string> nv;
   for (const std::string &r : roots) { nv.push_back(r + "/lib64/libnvrtc.so.12"); nv.push_back(r + "/lib64/libnvrtc.so"); }
+  nv.push_back("libnvrtc.so.12");
+  nv.push_back("libnvrtc.so");
   void *hn = open_first(nv);
   if (!hn) { g_dyn.why = "libnvrtc.so.12 not found (set MXB_CUDA_HOME)"; if (err) *err = g_dyn.why; return false; }
   void *hc = open_first({"libcuda.so.1", "libcuda.so"});
@@ -226,8 +230,10 @@ int jit_compile_only(const std::string &source, std::string *log) {
   std::vector<std::string> roots;
   for (const char *ev : {"MXB_CUDA_HOME", "CUDA_HOME", "CUDA_PATH"}) if (const char *v = getenv(ev)) roots.push_back(v);
   roots.push_back("/usr/local/cuda");
-  std::vector<std::string> nv = {"libnvrtc.so.12", "libnvrtc.so"};
+  std::vector<std::string> nv;
   for (const std::string &r : roots) { nv.push_back(r + "/lib64/libnvrtc.so.12"); nv.push_back(r + "/lib64/libnvrtc.so"); }
+  nv.push_back("libnvrtc.so.12");
+  nv.push_back("libnvrtc.so");
   void *hn = open_first(nv);
   if (!hn) { if (log) *log = "libnvrtc not found"; return MXB_ERR_JIT; }
   Dyn d;

@@ -150,13 +150,23 @@ template <> struct LdBytes<16> {
     ((u32 *)d)[0] = a; ((u32 *)d)[1] = b; ((u32 *)d)[2] = c; ((u32 *)d)[3] = e;
   }
 };
+#if defined(__CUDACC_VER_MAJOR__) && (__CUDACC_VER_MAJOR__ * 100 + __CUDACC_VER_MINOR__ < 1209)
+// 256-bit global accesses need PTX ISA 8.8 (CUDA 12.9); an older NVRTC gets two 128-bit accesses instead
+#define MXB_NO_256BIT 1
+#endif
 template <> struct LdBytes<32> {  // LDG.E.256 on sm_100
   static __device__ __forceinline__ void ld(void *d, const void *s) {
+#ifdef MXB_NO_256BIT
+    LdBytes<16>::ld(d, s);
+    LdBytes<16>::ld((char *)d + 16, (const char *)s + 16);
+    return;
+#else
     u32 r0, r1, r2, r3, r4, r5, r6, r7;
     asm("ld.global.nc.L1::no_allocate.L2::256B.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3), "=r"(r4), "=r"(r5), "=r"(r6), "=r"(r7) : "l"(s));
     u32 *o = (u32 *)d;
     o[0] = r0; o[1] = r1; o[2] = r2; o[3] = r3; o[4] = r4; o[5] = r5; o[6] = r6; o[7] = r7;
+#endif
   }
 };
 template <> struct LdBytes<64> {
@@ -215,6 +225,11 @@ template <> struct StBytes<16> {
 };
 template <> struct StBytes<32> {  // STG.E.256 on sm_100
   static __device__ __forceinline__ void st(void *d, const void *s) {
+#ifdef MXB_NO_256BIT
+    StBytes<16>::st(d, s);
+    StBytes<16>::st((char *)d + 16, (const char *)s + 16);
+    return;
+#endif
     const u32 *x = (const u32 *)s;
     asm volatile("st.global.L1::no_allocate.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(d), "r"(x[0]), "r"(x[1]),
                  "r"(x[2]), "r"(x[3]), "r"(x[4]), "r"(x[5]), "r"(x[6]), "r"(x[7]) : "memory");
@@ -677,15 +692,16 @@ __device__ __forceinline__ void reduce_inner_body_impl(const RedParams &p) {
 #pragma unroll
     for (int v = 0; v < V; ++v) acc[v] = Op::init();
 
-    // vector steps of the row: q = o * Lv + jv; this split owns [q0, q1)
+    // vector steps of the row are numbered q = o * Lv + jv, Q of them
     const i64 Q = O * Lv;
-    const i64 per = (Q + S - 1) / S;
-    const i64 q0 = s * per;
-    const i64 q1 = (q0 + per < Q) ? (q0 + per) : Q;
 
     if (nr == 1) {
-      i64 q = q0 + tid;
-      for (; q + (i64)(U - 1) * nthr < q1; q += (i64)U * nthr) {
+      // Tiles of nthr * U vectors are dealt round-robin to the row's splits (neighbouring CTAs stream neighbouring
+      // tiles, which keeps the DRAM pages they open shared); inside a tile every thread has U loads in flight.
+      const i64 tile = (i64)nthr * U;
+      const i64 nfull = Q / tile;
+      for (i64 t = s; t < nfull; t += S) {
+        const i64 q = t * tile + tid;
         typename E::template Regs<V> r[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) E::template loadv<V, UNIT>(r[u], base, inner, (q + (i64)u * nthr) * V);
@@ -696,13 +712,19 @@ __device__ __forceinline__ void reduce_inner_body_impl(const RedParams &p) {
           for (int v = 0; v < V; ++v) Op::step(acc[v], E::template eval<V>(r[u], v, p.c), row0 + j0 + v);
         }
       }
-      for (; q < q1; q += nthr) {
-        typename E::template Regs<V> r;
-        E::template loadv<V, UNIT>(r, base, inner, q * V);
+      if (s == nfull % S) {  // the ragged last tile goes to the next split in turn
+        for (i64 q = nfull * tile + tid; q < Q; q += nthr) {
+          typename E::template Regs<V> r;
+          E::template loadv<V, UNIT>(r, base, inner, q * V);
 #pragma unroll
-        for (int v = 0; v < V; ++v) Op::step(acc[v], E::template eval<V>(r, v, p.c), row0 + q * V + v);
+          for (int v = 0; v < V; ++v) Op::step(acc[v], E::template eval<V>(r, v, p.c), row0 + q * V + v);
+        }
       }
     } else {
+      // several runs per row: this split owns the contiguous range [q0, q1) of vector steps
+      const i64 per = (Q + S - 1) / S;
+      const i64 q0 = s * per;
+      const i64 q1 = (q0 + per < Q) ? (q0 + per) : Q;
       for (i64 q = q0 + tid; q < q1; q += nthr) {
         const i64 o = q / Lv, jv = q - o * Lv;
         const char *rb[E::NL];
@@ -1105,6 +1127,137 @@ __device__ __forceinline__ void var_inner_reg_body_impl(const RedParams &p) {
       ((OutT *)p.out.ptr)[oo] = cvt<OutT>(res);
     }
     __syncthreads();  // s_mean is reused by the next row
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3t: var_inner_tma — variance / stdd of contiguous rows of a plain tensor, rows staged ONCE in shared memory by
+// the TMA engine.  Persistent grid, one CTA per SM, a ring of `stages` row buffers: thread 0 arms an mbarrier with
+// the row's byte count and issues one `cp.async.bulk.shared::cluster.global` (SASS UBLKCP) per row; the whole CTA
+// waits on the barrier's phase, runs the reference's exact two passes (mean, then sum |x - mean|^2) out of shared
+// memory, and the freed buffer is immediately re-armed with the row `stages` ahead.  The copy engine keeps
+// (stages - 1) rows in flight per SM while the SM computes, so HBM never idles between a row's two passes —
+// which is what limits var_inner_smem / var_inner_reg (load phase and compute phase alternate there).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ u32 smem_u32(const void *p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(u64 *bar, u32 count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(u64 *bar, u32 bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u32 bytes, u64 *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template <class Tin> struct Widen { typedef Tin type; };
+template <> struct Widen<__nv_bfloat16> { typedef float type; };
+template <> struct Widen<__half> { typedef float type; };
+
+template <class Tin, class OutT>
+__device__ __forceinline__ void var_inner_tma_body(const RedParams &p) {
+  typedef typename Widen<Tin>::type T;
+  typedef typename AbsDev2<T>::real_t RT;
+  enum { V = 16 / (int)sizeof(Tin) };
+  extern __shared__ __align__(128) unsigned char s_dyn[];
+  __shared__ T s_sum[32];
+  __shared__ RT s_sq[32];
+  __shared__ T s_mean;
+  u64 *full = (u64 *)s_dyn;           // one mbarrier per stage (first 128 bytes)
+  unsigned char *buf = s_dyn + 128;
+  const int nthr = blockDim.x, tid = threadIdx.x;
+  const int stages = p.splits;        // ring depth chosen by the host from the row size
+  const i64 R = p.R;
+  const u32 rowbytes = (u32)(R * (i64)sizeof(Tin));
+  const u32 rowstride = (rowbytes + 127u) & ~127u;
+  const i64 Rv = R / V;
+
+  auto row_src = [&](i64 b) -> const char * {
+    i64 bidx[KMAXD];
+    decomp(b, p.nb, p.bsz, bidx);
+    i64 off = 0;
+#pragma unroll
+    for (int d = 0; d < KMAXD; ++d) if (d < p.nb) off += bidx[d] * p.leaf[0].bs[d];
+    return (const char *)p.leaf[0].ptr + off * (i64)sizeof(Tin);
+  };
+
+  if (tid == 0) {
+    for (int s = 0; s < stages; ++s) mbar_init(&full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0) {
+    for (int k = 0; k < stages; ++k) {
+      const i64 b = (i64)blockIdx.x + (i64)k * gridDim.x;
+      if (b < p.B) {
+        mbar_expect_tx(&full[k], rowbytes);
+        bulk_g2s(buf + (size_t)k * rowstride, row_src(b), rowbytes, &full[k]);
+      }
+    }
+  }
+  i64 k = 0;
+  for (i64 b = blockIdx.x; b < p.B; b += gridDim.x, ++k) {
+    const int s = (int)(k % stages);
+    const u32 parity = (u32)((k / stages) & 1);
+    mbar_wait(&full[s], parity);
+    const Vec<Tin, V> *x = (const Vec<Tin, V> *)(buf + (size_t)s * rowstride);
+    // pass 1: mean
+    T acc[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) acc[v] = OpSum<T>::init();
+    for (i64 i = tid; i < Rv; i += nthr) {
+      const Vec<Tin, V> q = x[i];
+#pragma unroll
+      for (int v = 0; v < V; ++v) acc[v] = acc[v] + cvt<T>(q.v[v]);
+    }
+#pragma unroll
+    for (int v = 1; v < V; ++v) acc[0] = acc[0] + acc[v];
+    const T tot = cta_merge<OpSum<T> >(acc[0], s_sum);
+    if (tid == 0) s_mean = MeanDiv<T>::go(tot, R);
+    __syncthreads();
+    const T mean = s_mean;
+    // pass 2: sum of |x - mean|^2, from shared memory
+    RT sq[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) sq[v] = (RT)0;
+    for (i64 i = tid; i < Rv; i += nthr) {
+      const Vec<Tin, V> q = x[i];
+#pragma unroll
+      for (int v = 0; v < V; ++v) sq[v] += AbsDev2<T>::go(cvt<T>(q.v[v]), mean);
+    }
+#pragma unroll
+    for (int v = 1; v < V; ++v) sq[0] += sq[v];
+    const RT tsq = cta_merge<OpSum<RT> >(sq[0], s_sq);
+    if (tid == 0) {
+      RT res = tsq / (RT)p.post_scale_d;
+      if (p.post_sqrt) res = f_sqrt(res);
+      i64 bidx[KMAXD];
+      decomp(b, p.nb, p.bsz, bidx);
+      i64 oo = 0;
+#pragma unroll
+      for (int d = 0; d < KMAXD; ++d) if (d < p.nb) oo += bidx[d] * p.out.bs[d];
+      ((OutT *)p.out.ptr)[oo] = cvt<OutT>(res);
+    }
+    __syncthreads();  // every thread is done with buffer s (and with s_mean)
+    if (tid == 0) {
+      const i64 nb2 = b + (i64)stages * gridDim.x;
+      if (nb2 < p.B) {
+        mbar_expect_tx(&full[s], rowbytes);
+        bulk_g2s(buf + (size_t)s * rowstride, row_src(nb2), rowbytes, &full[s]);
+      }
+    }
   }
 }
 

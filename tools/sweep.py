@@ -52,7 +52,7 @@ if "c2" in which:
     x = torch.rand(n, device="cuda")
     tx = mx.make_tensor(x)
     o, oi = torch.zeros((), device="cuda"), torch.zeros((), dtype=torch.int64, device="cuda")
-    g = {"MXB_TUNE_V": [4, 8], "MXB_TUNE_U": [2, 4], "MXB_TUNE_BLOCK": [256, 512], "MXB_TUNE_CTAS_PER_SM": [8, 16, 32, 64]}
+    g = {"MXB_TUNE_V": [8], "MXB_TUNE_U": [1, 2, 4], "MXB_TUNE_BLOCK": [256, 512], "MXB_TUNE_CTAS_PER_SM": [4, 8, 16]}
     sweep("c2.sum", n * 4, lambda: mx.make_tensor(o).set(mx.sum(tx)).run(ex), g)
     sweep("c2.argmax", n * 4, lambda: mx.mtie(mx.make_tensor(o), mx.make_tensor(oi)).set(mx.argmax(tx)).run(ex), g)
     del x, tx
@@ -62,7 +62,7 @@ if "c1" in which:
     a, b, c = (torch.rand(rows, cols, device="cuda") for _ in range(3))
     out = torch.empty(rows, device="cuda")
     ta, tb, tc, to = (mx.make_tensor(t) for t in (a, b, c, out))
-    g = {"MXB_TUNE_V": [4, 8], "MXB_TUNE_U": [1, 2], "MXB_TUNE_BLOCK": [128, 256], "MXB_TUNE_CTAS_PER_SM": [8, 16, 32], "MXB_TUNE_TEAM": [0]}
+    g = {"MXB_TUNE_V": [8], "MXB_TUNE_U": [1, 2], "MXB_TUNE_BLOCK": [128, 256], "MXB_TUNE_CTAS_PER_SM": [8, 16], "MXB_TUNE_TEAM": [0]}
     sweep("c1.fma_sum", 3 * rows * cols * 4, lambda: to.set(mx.sum(ta * tb + tc, [1])).run(ex), g)
     del a, b, c
     torch.cuda.empty_cache()
@@ -73,11 +73,11 @@ if "c3" in which:
     n = rows * cols
     oa, oi = torch.empty(rows, device="cuda"), torch.empty(rows, dtype=torch.int64, device="cuda")
     ov = torch.empty(rows, device="cuda")
-    g = {"MXB_TUNE_V": [2, 4], "MXB_TUNE_U": [2, 4], "MXB_TUNE_BLOCK": [256], "MXB_TUNE_CTAS_PER_SM": [8, 16, 32]}
+    g = {"MXB_TUNE_V": [4], "MXB_TUNE_U": [1, 2, 4], "MXB_TUNE_BLOCK": [256], "MXB_TUNE_CTAS_PER_SM": [8, 16]}
     om = torch.empty(rows, dtype=torch.complex64, device="cuda")
     sweep("c3.mean", n * 8, lambda: mx.make_tensor(om).set(mx.mean(tx, [1])).run(ex), g)
     sweep("c3.argmax_abs2", n * 8, lambda: mx.mtie(mx.make_tensor(oa), mx.make_tensor(oi)).set(mx.argmax(mx.abs2(tx), [1])).run(ex), g)
-    g = {"MXB_VAR_SMEM_ONLY": [1], "MXB_TUNE_V": [2, 4], "MXB_TUNE_U": [4, 8, 16], "MXB_TUNE_BLOCK": [512], "MXB_TUNE_CTAS_PER_SM": [3, 16]}
+    g = {"MXB_VAR_SMEM_ONLY": [1], "MXB_TUNE_V": [4], "MXB_TUNE_U": [2, 4, 8], "MXB_TUNE_BLOCK": [512, 1024], "MXB_TUNE_CTAS_PER_SM": [16]}
     sweep("c3.var", n * 8, lambda: mx.make_tensor(ov).set(mx.var(tx, [1], 1)).run(ex), g)
     del x, tx
     torch.cuda.empty_cache()
@@ -91,9 +91,9 @@ if "c4" in which:
     out = torch.empty(n, device="cuda")
     tK, tS, tV, tr, tT, to = (mx.make_tensor(t) for t in (K, S, V, r, T, out))
     expr = bc.black_scholes_expr(tK, tS, tV, tr, tT)
-    g = {"MXB_TUNE_V": [4, 8], "MXB_TUNE_U": [1, 2], "MXB_TUNE_BLOCK": [128, 256], "MXB_TUNE_CTAS_PER_SM": [16, 32, 100000]}
+    g = {"MXB_TUNE_V": [8], "MXB_TUNE_U": [1], "MXB_TUNE_BLOCK": [128, 256], "MXB_TUNE_CTAS_PER_SM": [16, 32]}
     sweep("c4.black_scholes", 6 * n * 4, lambda: to.set(expr).run(ex), g)
-    g = {"MXB_TUNE_V": [4, 8], "MXB_TUNE_U": [1, 2, 4], "MXB_TUNE_BLOCK": [128, 256], "MXB_TUNE_CTAS_PER_SM": [8, 32, 128, 100000]}
+    g = {"MXB_TUNE_V": [8], "MXB_TUNE_U": [1, 2, 4], "MXB_TUNE_BLOCK": [128, 256], "MXB_TUNE_CTAS_PER_SM": [32, 100000]}
     sweep("vector_add", 3 * n * 4, lambda: to.set(tS + tK).run(ex), g)
     del S, K, V, r, T, out
     torch.cuda.empty_cache()
@@ -102,5 +102,5 @@ if "c5" in which:
     t = (torch.rand(d, d, d, device="cuda") * 0.25).to(torch.bfloat16)
     out = torch.empty(d, d, dtype=torch.bfloat16, device="cuda")
     tt, to = mx.make_tensor(t), mx.make_tensor(out)
-    g = {"MXB_TUNE_V": [8, 16], "MXB_TUNE_U": [4, 8], "MXB_TUNE_BLOCK": [256], "MXB_TUNE_TX": [16, 32, 64], "MXB_TUNE_CTAS_PER_SM": [8, 32]}
+    g = {"MXB_TUNE_V": [16], "MXB_TUNE_U": [2, 4], "MXB_TUNE_BLOCK": [256], "MXB_TUNE_TX": [16, 32, 64], "MXB_TUNE_CTAS_PER_SM": [8]}
     sweep("c5.bf16_permuted_sum", d * d * d * 2, lambda: to.set(mx.sum(mx.permute(tt, [2, 0, 1]), [2])).run(ex), g)
