@@ -299,7 +299,7 @@ int reduce_launch(mxb_context *h, int kop, const mxb_expr_t &e, const ExprInfo &
   spec.op = kop;
   spec.out_dtype = out_dtype;
   int rot = -1;
-  int var_ipt = 0, var_threads = 0;
+  int var_ipt = 0, var_threads = 0, tma_ctas = 1;
   if (var_smem) {
     spec.family = FAM_VAR_SMEM;
     spec.V = (vmax > 1 && inner_ok(vmax)) ? vmax : 1;
@@ -320,15 +320,25 @@ int reduce_launch(mxb_context *h, int kop, const mxb_expr_t &e, const ExprInfo &
       const int64_t esz = dtype_bytes(e.leaves[0].dtype);
       const int64_t rowbytes = gr.size[0] * esz;
       const int64_t rowstride = (rowbytes + 127) & ~int64_t(127);
-      bool ok = rowbytes % 16 == 0 && rowbytes >= env_int("MXB_VAR_TMA_MIN_ROW", 16 * 1024) && aligned_to(e.leaves[0].data, 16) && rowbytes < (1 << 20);
+      bool ok = rowbytes % 16 == 0 && rowbytes >= env_int("MXB_VAR_TMA_MIN_ROW", 16 * 1024) && aligned_to(e.leaves[0].data, 16) && rowbytes <= 128 * 1024;
       for (int d = 0; ok && d < gb.n; ++d) ok = (gb.ls[0][d] * esz) % 16 == 0;
-      int64_t stages = (((int64_t)h->max_smem_optin - 128 - 2048) / rowstride);
-      if (stages > 8) stages = 8;
+      // Rows resident per SM = CTAs per SM x ring depth.  One CTA works on one row at a time, and a row costs a
+      // fixed latency chain (barrier wait, two CTA reductions), so short rows want several CTAs per SM; long rows
+      // only fit one CTA with a 2-3 deep ring (profiles/r1_sweeps.md).
+      const int64_t per_sm = (int64_t)228 * 1024;
+      int64_t ctas = 1, stages = 0;
+      for (int64_t c = 4; c >= 1; --c) {
+        const int64_t budget = std::min<int64_t>(per_sm / c - 1024 - 2048, (int64_t)h->max_smem_optin - 2048) - 128;
+        int64_t st = budget / rowstride;
+        if (st > 4) st = 4;
+        if (st >= 2) { ctas = c; stages = st; break; }
+      }
       if (env_int("MXB_TUNE_STAGES", 0) > 0 && env_int("MXB_TUNE_STAGES", 0) < stages) stages = env_int("MXB_TUNE_STAGES", 0);
       if (ok && stages >= 2) {
         spec.family = FAM_VAR_TMA;
         spec.V = policy_vmax(info);
         var_ipt = (int)stages;
+        tma_ctas = (int)ctas;
       }
     }
   } else if (vmax > 1 && inner_ok(vmax)) {
@@ -349,10 +359,21 @@ int reduce_launch(mxb_context *h, int kop, const mxb_expr_t &e, const ExprInfo &
   }
   spec.U = policy_unroll(info, spec.V, spec.family);
   if (spec.family == FAM_VAR_REG) spec.team = var_ipt;
-  if (spec.family == FAM_VAR_TMA) spec.team = 0;
   // development knobs (tools/sweep.py): override the unroll / launch shape; any combination is JIT-compiled on demand
   const int tune_u = env_int("MXB_TUNE_U", 0), tune_block = env_int("MXB_TUNE_BLOCK", 0), tune_cps = env_int("MXB_TUNE_CTAS_PER_SM", 0);
   const int tune_tx = env_int("MXB_TUNE_TX", 0);
+  int tma_block = 0;
+  if (spec.family == FAM_VAR_TMA) {
+    // 16-byte vectors of the row per thread, held in registers: IPT in {1,2,4,8} x up to 1024 threads
+    const int64_t Rv16 = gr.size[0] * dtype_bytes(e.leaves[0].dtype) / 16;
+    tma_block = 128;
+    while (tma_block < 1024 && (int64_t)tma_block * 8 < Rv16) tma_block <<= 1;   // 8 vectors per thread when the row allows
+    if (tune_block > 0) tma_block = tune_block;
+    int ipt = 1;
+    while ((int64_t)ipt * tma_block < Rv16) ipt <<= 1;
+    if (ipt > 8) { tma_block = 1024; ipt = 8; }
+    spec.team = ipt;
+  }
   if (tune_u > 0 && spec.family != FAM_VAR_REG) spec.U = tune_u;
 
   RedParams p;
@@ -415,9 +436,9 @@ int reduce_launch(mxb_context *h, int kop, const mxb_expr_t &e, const ExprInfo &
   if (spec.family == FAM_VAR_TMA) {
     const int64_t rowstride = (R * dtype_bytes(e.leaves[0].dtype) + 127) & ~int64_t(127);
     p.splits = var_ipt;  // ring depth
-    if (tune_block <= 0) block = 512;
+    block = (unsigned)tma_block;
     smem = (unsigned)(128 + (int64_t)var_ipt * rowstride);
-    grid = (unsigned)std::min<int64_t>(B, (int64_t)sm);
+    grid = (unsigned)std::min<int64_t>(B, (int64_t)sm * (tune_cps > 0 ? tune_cps : tma_ctas));
   } else if (spec.family == FAM_VAR_REG) {
     block = (unsigned)var_threads;
     grid = (unsigned)std::min<int64_t>(B, (int64_t)sm * (tune_cps > 0 ? tune_cps : 32));

@@ -405,7 +405,7 @@ int kernel_wrapper_src(const ExprInfo &info, const KernelSpec &s, const std::str
       if (info.nleaf != 1) return fail("var_tma serves plain tensors only");
       if (!(info.value_dtype == MXB_F32 || info.value_dtype == MXB_F64 || cplx)) return fail("var of a non-floating expression");
       k << "extern \"C\" __global__ void __launch_bounds__(1024) " << symbol
-        << "(const __grid_constant__ mxb::RedParams p) { mxb::var_inner_tma_body<" << dtype_ctype(info.leaf_dtype[0]) << ", " << O << ">(p); }\n";
+        << "(const __grid_constant__ mxb::RedParams p) { mxb::var_inner_tma_body<" << dtype_ctype(info.leaf_dtype[0]) << ", " << O << ", " << s.team << ">(p); }\n";
       break;
     case FAM_EW:
       k << "extern \"C\" __global__ void __launch_bounds__(256) " << symbol

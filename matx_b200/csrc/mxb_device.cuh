@@ -1135,7 +1135,8 @@ __device__ __forceinline__ void var_inner_reg_body_impl(const RedParams &p) {
 // the TMA engine.  Persistent grid, one CTA per SM, a ring of `stages` row buffers: thread 0 arms an mbarrier with
 // the row's byte count and issues one `cp.async.bulk.shared::cluster.global` (SASS UBLKCP) per row; the whole CTA
 // waits on the barrier's phase, runs the reference's exact two passes (mean, then sum |x - mean|^2) out of shared
-// memory, and the freed buffer is immediately re-armed with the row `stages` ahead.  The copy engine keeps
+// registers (one pass over shared memory), and the buffer is re-armed with the row `stages` ahead as soon as
+// every thread holds its share (after the first of the two barriers per row).  The copy engine keeps
 // (stages - 1) rows in flight per SM while the SM computes, so HBM never idles between a row's two passes —
 // which is what limits var_inner_smem / var_inner_reg (load phase and compute phase alternate there).
 // ------------------------------------------------------------------------------------------------
@@ -1166,19 +1167,18 @@ template <class Tin> struct Widen { typedef Tin type; };
 template <> struct Widen<__nv_bfloat16> { typedef float type; };
 template <> struct Widen<__half> { typedef float type; };
 
-template <class Tin, class OutT>
+template <class Tin, class OutT, int IPT>
 __device__ __forceinline__ void var_inner_tma_body(const RedParams &p) {
   typedef typename Widen<Tin>::type T;
   typedef typename AbsDev2<T>::real_t RT;
   enum { V = 16 / (int)sizeof(Tin) };
   extern __shared__ __align__(128) unsigned char s_dyn[];
-  __shared__ T s_sum[32];
-  __shared__ RT s_sq[32];
-  __shared__ T s_mean;
-  u64 *full = (u64 *)s_dyn;           // one mbarrier per stage (first 128 bytes)
+  __shared__ T s_sum[2][32];    // per-warp partials, double-buffered by row parity: two barriers per row suffice
+  __shared__ RT s_sq[2][32];
+  u64 *full = (u64 *)s_dyn;     // one mbarrier per stage (first 128 bytes)
   unsigned char *buf = s_dyn + 128;
-  const int nthr = blockDim.x, tid = threadIdx.x;
-  const int stages = p.splits;        // ring depth chosen by the host from the row size
+  const int nthr = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
+  const int stages = p.splits;  // ring depth chosen by the host from the row size
   const i64 R = p.R;
   const u32 rowbytes = (u32)(R * (i64)sizeof(Tin));
   const u32 rowstride = (rowbytes + 127u) & ~127u;
@@ -1210,37 +1210,53 @@ __device__ __forceinline__ void var_inner_tma_body(const RedParams &p) {
   i64 k = 0;
   for (i64 b = blockIdx.x; b < p.B; b += gridDim.x, ++k) {
     const int s = (int)(k % stages);
-    const u32 parity = (u32)((k / stages) & 1);
-    mbar_wait(&full[s], parity);
+    const int par = (int)(k & 1);
+    mbar_wait(&full[s], (u32)((k / stages) & 1));
+    // the thread's share of the row: shared memory -> registers, once
     const Vec<Tin, V> *x = (const Vec<Tin, V> *)(buf + (size_t)s * rowstride);
+    Vec<Tin, V> q[IPT];
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) {
+      const i64 j = tid + (i64)i * nthr;
+      if (j < Rv) q[i] = x[j];
+    }
     // pass 1: mean
-    T acc[V];
+    T acc = OpSum<T>::init();
 #pragma unroll
-    for (int v = 0; v < V; ++v) acc[v] = OpSum<T>::init();
-    for (i64 i = tid; i < Rv; i += nthr) {
-      const Vec<Tin, V> q = x[i];
+    for (int i = 0; i < IPT; ++i) {
+      if (tid + (i64)i * nthr < Rv) {
 #pragma unroll
-      for (int v = 0; v < V; ++v) acc[v] = acc[v] + cvt<T>(q.v[v]);
+        for (int v = 0; v < V; ++v) acc = acc + cvt<T>(q[i].v[v]);
+      }
     }
-#pragma unroll
-    for (int v = 1; v < V; ++v) acc[0] = acc[0] + acc[v];
-    const T tot = cta_merge<OpSum<T> >(acc[0], s_sum);
-    if (tid == 0) s_mean = MeanDiv<T>::go(tot, R);
-    __syncthreads();
-    const T mean = s_mean;
-    // pass 2: sum of |x - mean|^2, from shared memory
-    RT sq[V];
-#pragma unroll
-    for (int v = 0; v < V; ++v) sq[v] = (RT)0;
-    for (i64 i = tid; i < Rv; i += nthr) {
-      const Vec<Tin, V> q = x[i];
-#pragma unroll
-      for (int v = 0; v < V; ++v) sq[v] += AbsDev2<T>::go(cvt<T>(q.v[v]), mean);
-    }
-#pragma unroll
-    for (int v = 1; v < V; ++v) sq[0] += sq[v];
-    const RT tsq = cta_merge<OpSum<RT> >(sq[0], s_sq);
+    acc = OpSum<T>::warp(acc);
+    if (lane == 0) s_sum[par][warp] = acc;
+    __syncthreads();  // (A) partials visible; every thread holds its share in registers, so buffer s is free
     if (tid == 0) {
+      const i64 nb2 = b + (i64)stages * gridDim.x;
+      if (nb2 < p.B) {
+        mbar_expect_tx(&full[s], rowbytes);
+        bulk_g2s(buf + (size_t)s * rowstride, row_src(nb2), rowbytes, &full[s]);
+      }
+    }
+    T tot = OpSum<T>::init();
+    for (int w = 0; w < nwarp; ++w) tot = tot + s_sum[par][w];  // same order in every thread
+    const T mean = MeanDiv<T>::go(tot, R);
+    // pass 2: sum of |x - mean|^2 out of registers
+    RT sq = (RT)0;
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) {
+      if (tid + (i64)i * nthr < Rv) {
+#pragma unroll
+        for (int v = 0; v < V; ++v) sq += AbsDev2<T>::go(cvt<T>(q[i].v[v]), mean);
+      }
+    }
+    sq = OpSum<RT>::warp(sq);
+    if (lane == 0) s_sq[par][warp] = sq;
+    __syncthreads();  // (B)
+    if (tid == 0) {
+      RT tsq = (RT)0;
+      for (int w = 0; w < nwarp; ++w) tsq += s_sq[par][w];
       RT res = tsq / (RT)p.post_scale_d;
       if (p.post_sqrt) res = f_sqrt(res);
       i64 bidx[KMAXD];
@@ -1249,14 +1265,6 @@ __device__ __forceinline__ void var_inner_tma_body(const RedParams &p) {
 #pragma unroll
       for (int d = 0; d < KMAXD; ++d) if (d < p.nb) oo += bidx[d] * p.out.bs[d];
       ((OutT *)p.out.ptr)[oo] = cvt<OutT>(res);
-    }
-    __syncthreads();  // every thread is done with buffer s (and with s_mean)
-    if (tid == 0) {
-      const i64 nb2 = b + (i64)stages * gridDim.x;
-      if (nb2 < p.B) {
-        mbar_expect_tx(&full[s], rowbytes);
-        bulk_g2s(buf + (size_t)s * rowstride, row_src(nb2), rowbytes, &full[s]);
-      }
     }
   }
 }
