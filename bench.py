@@ -158,6 +158,9 @@ def run_ours(args) -> None:
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # keep stdout to the ONE JSON line: NCCL's version banner goes to stderr
+        os.environ["NCCL_DEBUG"] = os.environ.get("MXB_NCCL_DEBUG", "WARN")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     ex = mx.CudaExecutor()

@@ -163,7 +163,9 @@ struct Kernel { const void *fn = nullptr; bool jit = false; std::string key; };
 
 int get_kernel(const ExprInfo &info, const KernelSpec &spec, Kernel *k) {
   k->key = kernel_key(info, spec);
-  k->fn = lookup_aot(k->key);
+  const char *flavor = getenv("MXB_LD_FLAVOR");  // development knob: forces a JIT build with another load cache policy
+  if (flavor && *flavor) k->key += std::string("|F") + flavor;
+  k->fn = (flavor && *flavor) ? nullptr : lookup_aot(k->key);
   k->jit = false;
   if (k->fn) return MXB_OK;
   if (getenv("MXB_DISABLE_JIT")) return fail(MXB_ERR_JIT, "no ahead-of-time kernel for " + k->key + " and MXB_DISABLE_JIT is set");
@@ -186,7 +188,8 @@ int launch(mxb_context *h, const Kernel &k, unsigned grid, unsigned block, unsig
     int st = jit_launch(k.fn, grid, block, smem, (void *)h->stream, (void *)&params, &err);
     if (st != MXB_OK) return fail(st, err);
   } else {
-    if (smem > 48 * 1024) MXB_CUDA(cudaFuncSetAttribute(k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // static + dynamic shared memory above 48 KB needs the opt-in; the kernels carry up to ~3 KB of static smem
+    if (smem > 40 * 1024) MXB_CUDA(cudaFuncSetAttribute(k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     void *args[] = {(void *)&params};
     MXB_CUDA(cudaLaunchKernel(k.fn, dim3(grid), dim3(block), args, smem, h->stream));
   }

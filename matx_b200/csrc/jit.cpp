@@ -149,7 +149,7 @@ const void *jit_get_kernel(const std::string &key, const std::string &symbol, co
 
   // disk cache keyed by the full source text (skeleton + functor + wrapper)
   char hname[64];
-  snprintf(hname, sizeof hname, "%016llx_%016llx.cubin", (unsigned long long)fnv64(source),
+  snprintf(hname, sizeof hname, "%016llx_%016llx.cubin", (unsigned long long)fnv64(source + (getenv("MXB_LD_FLAVOR") ? getenv("MXB_LD_FLAVOR") : "")),
            (unsigned long long)fnv64(std::string(kDeviceHeaderText)));
   const std::string cpath = cache_dir() + "/" + hname;
   std::string cubin;
@@ -164,8 +164,10 @@ const void *jit_get_kernel(const std::string &key, const std::string &symbol, co
     nvrtcResult r = g_dyn.CreateProgram(&prog, source.c_str(), "mxb_jit.cu", 1, hdr_src, hdr_name);
     if (r != 0) { if (err) *err = std::string("nvrtcCreateProgram: ") + g_dyn.GetErrorString(r); return nullptr; }
     const std::string inc = "--include-path=" + g_dyn.include_dir;
-    const char *opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", inc.c_str(), "-lineinfo"};
-    r = g_dyn.CompileProgram(prog, 4, opts);
+    std::string flavor = "-DMXB_LD_FLAVOR=0";
+    if (const char *fv = getenv("MXB_LD_FLAVOR")) flavor = std::string("-DMXB_LD_FLAVOR=") + fv;
+    const char *opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", inc.c_str(), "-lineinfo", flavor.c_str()};
+    r = g_dyn.CompileProgram(prog, 5, opts);
     if (r != 0) {
       size_t n = 0;
       g_dyn.GetProgramLogSize(prog, &n);
@@ -207,7 +209,7 @@ const void *jit_get_kernel(const std::string &key, const std::string &symbol, co
 int jit_launch(const void *fn, unsigned grid, unsigned block, unsigned smem, void *stream, void *params, std::string *err) {
   if (!g_dyn.ok) { if (err) *err = "JIT runtime not initialised"; return MXB_ERR_JIT; }
   CUfunction f = (CUfunction)fn;
-  if (smem > 48 * 1024) {
+  if (smem > 40 * 1024) {
     const CUresult a = g_dyn.FuncSetAttribute(f, 8 /* CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES */, (int)smem);
     if (a != 0) { if (err) *err = "cuFuncSetAttribute(max dynamic smem) failed"; return MXB_ERR_CUDA; }
   }

@@ -142,10 +142,27 @@ template <> struct LdBytes<8> {
     ((u32 *)d)[0] = a; ((u32 *)d)[1] = b;
   }
 };
+// MXB_LD_FLAVOR (development knob, JIT only): cache policy of the 128-bit streaming load
+#ifndef MXB_LD_FLAVOR
+#define MXB_LD_FLAVOR 0
+#endif
+#if MXB_LD_FLAVOR == 1
+#define MXB_LD16 "ld.global.nc.v4.b32"
+#elif MXB_LD_FLAVOR == 2
+#define MXB_LD16 "ld.global.L1::no_allocate.v4.b32"
+#elif MXB_LD_FLAVOR == 3
+#define MXB_LD16 "ld.global.nc.L1::no_allocate.L2::256B.v4.b32"
+#elif MXB_LD_FLAVOR == 4
+#define MXB_LD16 "ld.global.nc.L1::evict_first.v4.b32"
+#elif MXB_LD_FLAVOR == 5
+#define MXB_LD16 "ld.global.nc.L1::no_allocate.L2::128B.v4.b32"
+#else
+#define MXB_LD16 "ld.global.nc.L1::no_allocate.v4.b32"
+#endif
 template <> struct LdBytes<16> {
   static __device__ __forceinline__ void ld(void *d, const void *s) {
     u32 a, b, c, e;
-    asm("ld.global.nc.L1::no_allocate.v4.b32 {%0,%1,%2,%3}, [%4];"
+    asm(MXB_LD16 " {%0,%1,%2,%3}, [%4];"
                  : "=r"(a), "=r"(b), "=r"(c), "=r"(e) : "l"(s));
     ((u32 *)d)[0] = a; ((u32 *)d)[1] = b; ((u32 *)d)[2] = c; ((u32 *)d)[3] = e;
   }
