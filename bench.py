@@ -152,6 +152,11 @@ def run_ours(args) -> None:
     from matx_b200 import ops as mx
     from matx_b200 import dist as mxd
 
+    # stdout carries exactly ONE JSON line: everything else written to fd 1 by libraries (NCCL's version banner,
+    # torchrun notices) is sent to stderr, and the line is written to the saved descriptor at the end
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -163,7 +168,12 @@ def run_ours(args) -> None:
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
-    ex = mx.CudaExecutor()
+    # N > 1: the step (3 partial kernels, one all-gather, 3 folds) is launch-latency sensitive (~75 us kernels at N = 8),
+    # so it runs on a side stream and is replayed as ONE CUDA graph; N = 1 uses the default stream like a MatX program.
+    side = torch.cuda.Stream() if world > 1 else None
+    if side is not None:
+        torch.cuda.set_stream(side)
+    ex = mx.CudaExecutor(side)
     start, count = mxd.slab(N_ELEMS, rank, world)
     gen = torch.Generator(device=dev)
     gen.manual_seed(4 + rank)
@@ -174,14 +184,26 @@ def run_ours(args) -> None:
     o_amax = torch.zeros((), device=dev)
     o_idx = torch.zeros((), device=dev, dtype=torch.int64)
     sharded = mxd.ShardedFullReduce(ex, world, rank) if world > 1 else None
+    graph = None
+    if world > 1:
+        plan = sharded.prepare([(A.RED_SUM, o_sum, None), (A.RED_MAX, o_max, None), (A.RED_ARGMAX, o_amax, o_idx)], tx, start, N_ELEMS)
+        for _ in range(3):   # warm-up outside capture: kernels loaded, scratch allocated, NCCL connected
+            sharded.run_prepared(plan)
+        torch.cuda.synchronize()
+        if not args.no_graph:
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=side):
+                sharded.run_prepared(plan)
 
     def step():
         if world == 1:
             mx.make_tensor(o_sum).set(mx.sum(tx)).run(ex)
             mx.make_tensor(o_max).set(mx.max(tx)).run(ex)
             mx.mtie(mx.make_tensor(o_amax), mx.make_tensor(o_idx)).set(mx.argmax(tx)).run(ex)
+        elif graph is not None:
+            graph.replay()
         else:
-            sharded.run([(A.RED_SUM, o_sum, None), (A.RED_MAX, o_max, None), (A.RED_ARGMAX, o_amax, o_idx)], tx, start, N_ELEMS)
+            sharded.run_prepared(plan)
 
     def barrier():
         if world > 1:
@@ -219,6 +241,8 @@ def run_ours(args) -> None:
     clocks = sampler.stop()
     ms = e0.elapsed_time(e1)
     launches = ex.launch_count() - l0
+    if graph is not None:
+        launches = 6 * args.steps   # per replayed step: 3 slab-reduce kernels + 3 fold kernels of this library (+ 1 NCCL all-gather)
     tms = torch.tensor([ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
@@ -326,7 +350,7 @@ def run_ours(args) -> None:
         }
         if others is not None:
             line["other_configs"] = others
-        print(json.dumps(line), flush=True)
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
@@ -339,6 +363,7 @@ def main() -> None:
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="N > 1: launch the step kernel by kernel instead of replaying a CUDA graph")
     ap.add_argument("--all-configs", action="store_true", help="also time configs 1, 3, 4, 5 (reported under other_configs)")
     args = ap.parse_args()
     if args.impl == "reference":

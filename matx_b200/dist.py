@@ -78,3 +78,31 @@ class ShardedFullReduce:
         self._exchange(len(items))
         for k, (op, out, idx) in enumerate(items):
             self._finalize(op, value_dtype, k, len(items), global_count, out, idx)
+
+    # -- prepared form: the statements are lowered once, a step is then 2 x len(items) C calls + one all-gather --
+    def prepare(self, items: Sequence[tuple], operand, slab_offset: int, global_count: int, value_dtype: Optional[int] = None):
+        if len(items) > self.MAX_ITEMS:
+            raise ValueError("at most %d statements per exchange" % self.MAX_ITEMS)
+        if value_dtype is None:
+            value_dtype = operand.dtype_hint if operand.dtype_hint not in (A.BF16, A.F16) else A.F32
+        n = len(items)
+        stride = n * A.MXB_PARTIAL_BYTES
+        plan = {"n": n, "partial": [], "final": [], "keep": []}
+        for k, (op, out, idx) in enumerate(items):
+            e = mx.lower_reduce(mx.ReduceExpr(op, operand, None))
+            rec = C.c_void_p(self.records.data_ptr() + k * A.MXB_PARTIAL_BYTES)
+            plan["partial"].append((op, e, C.c_int64(slab_offset), rec))
+            o = mx._out_desc(mx.make_tensor(out))
+            io = mx._out_desc(mx.make_tensor(idx)) if idx is not None else None
+            g = C.c_void_p(self.gathered.data_ptr() + k * A.MXB_PARTIAL_BYTES)
+            plan["final"].append((op, value_dtype, g, stride, C.c_int64(global_count), o, io))
+            plan["keep"].append((out, idx, operand))
+        return plan
+
+    def run_prepared(self, plan) -> None:
+        lib, h = A.lib, self.ex.handle
+        for op, e, off, rec in plan["partial"]:
+            A.check(lib.mxb_reduce_partial(h, op, C.byref(e), off, rec))
+        self._exchange(plan["n"])
+        for op, vdt, g, stride, gcount, o, io in plan["final"]:
+            A.check(lib.mxb_reduce_finalize(h, op, vdt, g, self.world, stride, gcount, 1, C.byref(o), C.byref(io) if io is not None else None))

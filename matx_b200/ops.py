@@ -469,6 +469,12 @@ class CudaExecutor:
     def getStream(self) -> int:
         return self._stream_ptr
 
+    def set_stream(self, stream) -> None:
+        """Rebind the executor (and its library handle) to another stream (torch.cuda.Stream, raw pointer or None)."""
+        ptr = 0 if stream is None else (stream if isinstance(stream, int) else int(stream.cuda_stream))
+        A.check(A.lib.mxb_set_stream(self.handle, C.c_void_p(ptr)))
+        self._stream_ptr = ptr
+
     def sync(self) -> None:
         A.check(A.lib.mxb_sync(self.handle))
 
