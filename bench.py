@@ -352,7 +352,19 @@ def run_ours(args) -> None:
             line["other_configs"] = others
         os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
-        dist.destroy_process_group()
+        # a captured graph holds NCCL work: drop it before tearing the communicator down, and never let teardown hang the job
+        graph = None
+        sharded = None
+        torch.cuda.synchronize()
+        sys.stderr.flush()
+        watchdog = threading.Timer(20.0, lambda: os._exit(0))
+        watchdog.daemon = True
+        watchdog.start()
+        try:
+            dist.barrier()
+            dist.destroy_process_group()
+        finally:
+            watchdog.cancel()
 
 
 def main() -> None:
