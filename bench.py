@@ -86,7 +86,11 @@ class ClockSampler:
             for n, v in zip(names, r[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx_, "reasons": sorted(reasons), "samples": len(sm)}
+        # the first sample or two can predate the load: the median is taken over the upper half of the readings
+        sm_sorted = sorted(sm)
+        loaded = sm_sorted[len(sm_sorted) // 2:] if sm_sorted else []
+        return {"sm_mhz": statistics.median(loaded) if loaded else None, "sm_max_mhz": mx_, "reasons": sorted(reasons), "samples": len(sm),
+                "window": "100 ms samples from the start of the warm-up (same load, >= 0.6 s) to the end of the timed region"}
 
 
 # --------------------------------------------------------------------------------------------------------------
@@ -210,8 +214,17 @@ def run_ours(args) -> None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(3, args.warmup)):
+    # nvidia-smi needs ~100 ms per sample: the sampler starts before the warm-up and the warm-up keeps the same load
+    # running for at least 0.6 s, so the clock record covers the run-up to and the whole of the timed region
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    t_w = time.perf_counter()
+    n_w = 0
+    while n_w < max(3, args.warmup) or time.perf_counter() - t_w < 0.6:
         step()
+        n_w += 1
+        if n_w % 8 == 0:
+            torch.cuda.synchronize()
     barrier()
 
     # ---- correctness of what is being timed (full size, fp64 truth on the device) ----
@@ -228,11 +241,9 @@ def run_ours(args) -> None:
         assert not bool((x[:gi - start] == tmax).any().item()), "argmax is not the lowest index"
 
     # ---- timed region: K steps, CUDA events on the launching stream, max over ranks ----
-    sampler = ClockSampler(local_rank)
     l0 = ex.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
-    sampler.start()
     e0.record()
     for _ in range(args.steps):
         step()
