@@ -281,8 +281,18 @@ def run_ours(args) -> None:
         per_kernel[name] = {"ms_avg": sum(ts) / len(ts), "ms_best": min(ts), "kernel": ex.last_kernel(),
                             "GBps": (count * 4 + 16) / (sum(ts) / len(ts) * 1e-3) / 1e9}
     dom = per_kernel["sum"]
+    # DRAM traffic of the dominant kernel per launch, from the committed `ncu --set full` capture of the same kernel
+    # on the full 2^30-element input (only meaningful at N = 1, where the launch processes the same bytes)
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            tr = json.load(f).get(dom["kernel"].rsplit("|", 1)[0])
+        if tr and world == 1:
+            traffic = tr["dram_bytes_per_launch"]
+    except (OSError, ValueError):
+        pass
     roofline = {"bound": "hbm", "achieved": dom["GBps"], "peak": peak, "unit": "GB/s", "frac": dom["GBps"] / peak,
-                "traffic": None, "kernel": dom["kernel"], "peak_source": peak_src, "frac_of_nominal_8000": dom["GBps"] / 8000.0,
+                "traffic": traffic, "algorithmic_bytes_per_launch": count * 4 + 16, "kernel": dom["kernel"], "peak_source": peak_src, "frac_of_nominal_8000": dom["GBps"] / 8000.0,
                 "per_kernel": per_kernel}
 
     # ---- e2e: host buffers through the public API, H2D of the input + D2H of the results inside the timed region ----
