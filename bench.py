@@ -189,8 +189,28 @@ def run_ours(args) -> None:
     o_idx = torch.zeros((), device=dev, dtype=torch.int64)
     sharded = mxd.ShardedFullReduce(ex, world, rank) if world > 1 else None
     graph = None
+    exchange = "none"
     if world > 1:
-        plan = sharded.prepare([(A.RED_SUM, o_sum, None), (A.RED_MAX, o_max, None), (A.RED_ARGMAX, o_amax, o_idx)], tx, start, N_ELEMS)
+        items = [(A.RED_SUM, o_sum, None), (A.RED_MAX, o_max, None), (A.RED_ARGMAX, o_amax, o_idx)]
+        plan = None
+        if args.exchange == "p2p":
+            # fused exchange: records are stored straight into every rank's buffer over NVLink peer mappings by the
+            # reduction kernels themselves; falls back to the NCCL all-gather if the IPC mapping is not possible
+            ok = torch.ones((), device=dev)
+            try:
+                runner = mxd.PeerExchange(ex, world, rank)
+                plan = runner.prepare(items, tx, start, N_ELEMS)
+            except Exception as exc:  # noqa: BLE001 - any failure means "use NCCL", decided collectively below
+                print("rank %d: peer exchange unavailable (%s), using NCCL" % (rank, exc), file=sys.stderr)
+                ok.zero_()
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if ok.item() == 1:
+                sharded, exchange = runner, "p2p"
+            else:
+                plan = None
+        if plan is None:
+            plan = sharded.prepare(items, tx, start, N_ELEMS)
+            exchange = "nccl"
         for _ in range(3):   # warm-up outside capture: kernels loaded, scratch allocated, NCCL connected
             sharded.run_prepared(plan)
         torch.cuda.synchronize()
@@ -253,7 +273,8 @@ def run_ours(args) -> None:
     ms = e0.elapsed_time(e1)
     launches = ex.launch_count() - l0
     if graph is not None:
-        launches = 6 * args.steps   # per replayed step: 3 slab-reduce kernels + 3 fold kernels of this library (+ 1 NCCL all-gather)
+        # per replayed step: 3 slab-reduce kernels + 1 fold kernel (p2p) or 3 fold kernels + 1 NCCL all-gather (nccl)
+        launches = (4 if exchange == "p2p" else 6) * args.steps
     tms = torch.tensor([ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
@@ -305,6 +326,8 @@ def run_ours(args) -> None:
         txd = mx.make_tensor(xd)
         pack = torch.zeros(4, device=dev, dtype=torch.float64)
 
+        e2e_plan = sharded.prepare(items, txd, start, N_ELEMS) if world > 1 else None
+
         def e2e_step():
             xd.copy_(hx, non_blocking=True)
             if world == 1:
@@ -312,7 +335,7 @@ def run_ours(args) -> None:
                 mx.make_tensor(o_max).set(mx.max(txd)).run(ex)
                 mx.mtie(mx.make_tensor(o_amax), mx.make_tensor(o_idx)).set(mx.argmax(txd)).run(ex)
             else:
-                sharded.run([(A.RED_SUM, o_sum, None), (A.RED_MAX, o_max, None), (A.RED_ARGMAX, o_amax, o_idx)], txd, start, N_ELEMS)
+                sharded.run_prepared(e2e_plan)
             pack[0], pack[1], pack[2], pack[3] = o_sum, o_max, o_amax, o_idx
             hres.copy_(pack, non_blocking=True)
             torch.cuda.synchronize()
@@ -364,7 +387,10 @@ def run_ours(args) -> None:
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "elements_per_sec": 3 * N_ELEMS / (ms_step * 1e-3),
             "config": {"workload": "C2: full-tensor sum + max + argmax, fp32 2^30 elements" +
-                       ("" if world == 1 else ", slab-sharded over %d GPUs, one NCCL all-gather of 96 B per rank per step" % world),
+                       ("" if world == 1 else ", slab-sharded over %d GPUs, " % world +
+                        ("records pushed to every rank over NVLink peer memory by the reduction kernels (no collective call), one fold kernel per step"
+                         if exchange == "p2p" else "one NCCL all-gather of 96 B per rank per step")),
+                       "exchange": exchange, "cuda_graph": graph is not None,
                        "l2": "inputs (4 GiB per statement) are larger than L2; no flush between iterations",
                        "parallelism": "slab%d" % world},
             "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu,
@@ -396,6 +422,7 @@ def main() -> None:
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="N > 1: how the 32-byte partial records travel")
     ap.add_argument("--no-graph", action="store_true", help="N > 1: launch the step kernel by kernel instead of replaying a CUDA graph")
     ap.add_argument("--all-configs", action="store_true", help="also time configs 1, 3, 4, 5 (reported under other_configs)")
     args = ap.parse_args()

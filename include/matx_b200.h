@@ -186,6 +186,36 @@ int mxb_reduce_finalize(mxb_handle_t h, int reduce_op, int32_t value_dtype, cons
                         int world, int64_t record_stride_bytes, int64_t global_count, int ddof,
                         const mxb_out_t *out, const mxb_out_t *idx_out);
 
+/* Fused exchange over NVLink peer memory (one box, <= 8 ranks): instead of handing the records to a collective,
+ * the reduction kernel's last block stores its record directly into EVERY rank's exchange buffer through peer
+ * mappings and bumps an arrival counter there; mxb_exchange_finalize is one small kernel per step that waits for the
+ * counters of all ranks and folds all statements' records in rank order.  No NCCL call, no host round trip, graph
+ * capturable.  The host maps the buffers once (CUDA IPC): rec[r] / flag[r] point at rank r's buffers as seen from
+ * THIS device; buffers are zero-initialised and sized MXB_EXCHANGE_REC_BYTES(world) / MXB_EXCHANGE_FLAG_BYTES(world);
+ * epoch is a zeroed local u32.  Records are double-buffered by step parity, so a fast rank can run one step ahead. */
+#define MXB_MAX_PEERS 8
+#define MXB_MAX_ITEMS 8
+#define MXB_EXCHANGE_REC_BYTES(world) (2 * (world) * MXB_MAX_ITEMS * MXB_PARTIAL_BYTES)
+#define MXB_EXCHANGE_FLAG_BYTES(world) ((world) * 4)
+typedef struct {
+  void *rec[MXB_MAX_PEERS];
+  void *flag[MXB_MAX_PEERS];
+  void *epoch;
+  int32_t world, rank;
+} mxb_peers_t;
+typedef struct {
+  int32_t reduce_op;   /* SUM, MEAN, PROD, MAX, MIN, ARGMAX, ARGMIN, ANY, ALL */
+  int32_t value_dtype; /* arithmetic type of the reduced expression (F32, F64, C64, I32, I64) */
+  void *out;           /* one element of value_dtype */
+  void *idx_out;       /* one int64 (ARGMAX / ARGMIN), else NULL */
+} mxb_fold_item_t;
+int mxb_reduce_partial_push(mxb_handle_t h, int reduce_op, const mxb_expr_t *expr, int64_t slab_offset,
+                            const mxb_peers_t *peers, int item, int n_items);
+int mxb_exchange_finalize(mxb_handle_t h, const mxb_peers_t *peers, const mxb_fold_item_t *items, int n_items,
+                          int64_t global_count);
+/* cudaDeviceEnablePeerAccess(peer_device) from the handle's device (already-enabled is not an error). */
+int mxb_enable_peer_access(mxb_handle_t h, int peer_device);
+
 /* ---- introspection ---------------------------------------------------------------------------- */
 int mxb_version(void);                /* major*1000 + minor */
 const char *mxb_last_error(void);     /* thread-local text of the last non-OK status */

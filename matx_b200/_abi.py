@@ -67,8 +67,25 @@ class Out(C.Structure):
 EXPORTED = [
     "mxb_create", "mxb_destroy", "mxb_set_stream", "mxb_sync", "mxb_elementwise", "mxb_reduce", "mxb_reduce_partial",
     "mxb_reduce_finalize", "mxb_version", "mxb_last_error", "mxb_device_count", "mxb_last_kernel", "mxb_launch_count",
-    "mxb_is_aot",
+    "mxb_is_aot", "mxb_reduce_partial_push", "mxb_exchange_finalize", "mxb_enable_peer_access",
 ]
+
+
+MXB_MAX_PEERS = 8
+MXB_MAX_ITEMS = 8
+
+
+class Peers(C.Structure):
+    _fields_ = [("rec", C.c_void_p * MXB_MAX_PEERS), ("flag", C.c_void_p * MXB_MAX_PEERS), ("epoch", C.c_void_p),
+                ("world", C.c_int32), ("rank", C.c_int32)]
+
+
+class FoldItem(C.Structure):
+    _fields_ = [("reduce_op", C.c_int32), ("value_dtype", C.c_int32), ("out", C.c_void_p), ("idx_out", C.c_void_p)]
+
+
+def exchange_rec_bytes(world: int) -> int:
+    return 2 * world * MXB_MAX_ITEMS * MXB_PARTIAL_BYTES
 
 
 class MatxB200Error(RuntimeError):
@@ -92,6 +109,9 @@ def _load() -> C.CDLL:
     lib.mxb_reduce.argtypes = [vp, i32, C.POINTER(Expr), i32, C.POINTER(Out), C.POINTER(Out), i32]
     lib.mxb_reduce_partial.argtypes = [vp, i32, C.POINTER(Expr), i64, vp]
     lib.mxb_reduce_finalize.argtypes = [vp, i32, i32, vp, i32, i64, i64, i32, C.POINTER(Out), C.POINTER(Out)]
+    lib.mxb_reduce_partial_push.argtypes = [vp, i32, C.POINTER(Expr), i64, C.POINTER(Peers), i32, i32]
+    lib.mxb_exchange_finalize.argtypes = [vp, C.POINTER(Peers), C.POINTER(FoldItem), i32, i64]
+    lib.mxb_enable_peer_access.argtypes = [vp, i32]
     lib.mxb_last_error.restype = C.c_char_p
     lib.mxb_last_kernel.argtypes = [vp]
     lib.mxb_last_kernel.restype = C.c_char_p

@@ -207,6 +207,8 @@ struct RedOptions {
   bool post_sqrt = false;
   bool raw_partial = false;
   int64_t idx_base = 0;
+  const mxb_peers_t *peers = nullptr;  // raw_partial + peers: push the record into every rank's exchange buffer
+  int peer_item = 0;
 };
 
 int check_expr_shape(const mxb_expr_t *e) {
@@ -421,6 +423,17 @@ int reduce_launch(mxb_context *h, int kop, const mxb_expr_t &e, const ExprInfo &
   p.post_scale_d = opt.post_scale;
   p.post_sqrt = opt.post_sqrt ? 1 : 0;
   p.raw_partial = opt.raw_partial ? 1 : 0;
+  if (opt.raw_partial && opt.peers) {
+    p.raw_partial = 2;
+    for (int r = 0; r < opt.peers->world; ++r) {
+      p.peer_rec[r] = opt.peers->rec[r];
+      p.peer_flag[r] = (unsigned *)opt.peers->flag[r];
+    }
+    p.peer_epoch = (const unsigned *)opt.peers->epoch;
+    p.peer_world = opt.peers->world;
+    p.peer_rank = opt.peers->rank;
+    p.peer_item = opt.peer_item;
+  }
   fill_consts(e, p.c);
   const int vec_is_batch_dim = (rot >= 0);
 
@@ -644,6 +657,109 @@ int finalize_dispatch_op(mxb_context *h, int kop, const void *recs, int world, i
   return MXB_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// fused exchange: wait for every rank's arrival counter, then fold all statements (one warp, one launch per step)
+// ---------------------------------------------------------------------------------------------------
+struct FoldItemDev { int op, dtype; void *out; long long *idx; };
+struct ExchangeParams {
+  const uint4 *rec;        // this rank's buffer: PartialRec[2][world][KMAXITEMS]
+  const unsigned *flag;    // this rank's arrival counters [world]
+  unsigned *epoch;
+  int world, n_items;
+  double scale;            // MEAN divisor (global element count)
+  FoldItemDev item[mxb::KMAXITEMS];
+};
+
+template <class Op> __device__ void fold_one(const uint4 *recs, int world, int stride16, void *out, long long *idx, bool div, double scale) {
+  typename Op::acc_t a = Op::init();
+  for (int r = 0; r < world; ++r) {
+    union { uint4 q; typename Op::acc_t acc; } u;
+    const volatile uint4 *src = recs + (size_t)r * stride16;   // written by peers during this launch: never from L1
+    u.q.x = src->x; u.q.y = src->y; u.q.z = src->z; u.q.w = src->w;
+    Op::merge(a, u.acc);
+  }
+  typename Op::result_t v = Op::finish(a);
+  if (div) {
+    RedParams fake;
+    fake.post_div = 1; fake.post_sqrt = 0; fake.post_scale_d = scale; fake.post_scale_f = (float)scale;
+    v = mxb::Post<typename Op::result_t>::go(v, fake);
+  }
+  *(typename Op::result_t *)out = v;
+  if (Op::HAS_INDEX) *idx = Op::index(a);
+}
+template <class T> __device__ void fold_dtype(int op, const uint4 *recs, int world, int stride16, void *out, long long *idx, double scale) {
+  switch (op) {
+    case MXB_RED_SUM: fold_one<mxb::OpSum<T> >(recs, world, stride16, out, idx, false, scale); break;
+    case MXB_RED_MEAN: fold_one<mxb::OpSum<T> >(recs, world, stride16, out, idx, true, scale); break;
+    case MXB_RED_PROD: fold_one<mxb::OpProd<T> >(recs, world, stride16, out, idx, false, scale); break;
+    default:
+      if constexpr (!mxb::is_complex<T>::value) {
+        switch (op) {
+          case MXB_RED_MAX: fold_one<mxb::OpExt<T, true> >(recs, world, stride16, out, idx, false, scale); break;
+          case MXB_RED_MIN: fold_one<mxb::OpExt<T, false> >(recs, world, stride16, out, idx, false, scale); break;
+          case MXB_RED_ARGMAX: fold_one<mxb::OpArg<T, true> >(recs, world, stride16, out, idx, false, scale); break;
+          case MXB_RED_ARGMIN: fold_one<mxb::OpArg<T, false> >(recs, world, stride16, out, idx, false, scale); break;
+          default: break;
+        }
+      }
+  }
+}
+// any / all records hold an int whatever the value type; the result is written in the value type
+template <class T> __device__ void fold_logic(int op, const uint4 *recs, int world, int stride16, void *out) {
+  int a = op == MXB_RED_ANY ? 0 : 1;
+  for (int r = 0; r < world; ++r) {
+    const int v = (int)((const volatile uint4 *)(recs + (size_t)r * stride16))->x;
+    a = op == MXB_RED_ANY ? (a | v) : (a & v);
+  }
+  *(T *)out = mxb::cvt<T>(a);
+}
+
+__global__ void exchange_finalize_kernel(const __grid_constant__ ExchangeParams p) {
+  const int lane = threadIdx.x;
+  const unsigned e = *p.epoch + 1u;
+  const unsigned target = e * (unsigned)p.n_items;
+  // lanes 0..world-1 each wait for one source rank (bounded: a dead peer must not hang this GPU)
+  if (lane < p.world) {
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+    while (true) {
+      unsigned v;
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p.flag + lane) : "memory");
+      if ((int)(v - target) >= 0) break;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+      if (t1 - t0 > 5000000000ull) break;  // 5 s
+      __nanosleep(100);
+    }
+  }
+  __syncwarp();
+  const int slot = (int)(e & 1u);
+  if (lane < p.n_items) {
+    const FoldItemDev it = p.item[lane];
+    const uint4 *recs = p.rec + ((size_t)slot * p.world * mxb::KMAXITEMS + lane) * 2;  // 2 x uint4 per 32-byte record
+    const int stride16 = mxb::KMAXITEMS * 2;
+    if (it.op == MXB_RED_ANY || it.op == MXB_RED_ALL) {
+      switch (it.dtype) {
+        case MXB_F32: fold_logic<float>(it.op, recs, p.world, stride16, it.out); break;
+        case MXB_F64: fold_logic<double>(it.op, recs, p.world, stride16, it.out); break;
+        case MXB_I32: fold_logic<int>(it.op, recs, p.world, stride16, it.out); break;
+        case MXB_I64: fold_logic<long long>(it.op, recs, p.world, stride16, it.out); break;
+        default: break;
+      }
+    } else {
+      switch (it.dtype) {
+        case MXB_F32: fold_dtype<float>(it.op, recs, p.world, stride16, it.out, it.idx, p.scale); break;
+        case MXB_F64: fold_dtype<double>(it.op, recs, p.world, stride16, it.out, it.idx, p.scale); break;
+        case MXB_C64: fold_dtype<mxb::cfloat>(it.op, recs, p.world, stride16, it.out, it.idx, p.scale); break;
+        case MXB_I32: fold_dtype<int>(it.op, recs, p.world, stride16, it.out, it.idx, p.scale); break;
+        case MXB_I64: fold_dtype<long long>(it.op, recs, p.world, stride16, it.out, it.idx, p.scale); break;
+        default: break;
+      }
+    }
+  }
+  __syncwarp();
+  if (lane == 0) *p.epoch = e;
+}
+
 }  // namespace
 
 // ===================================================================================================
@@ -759,6 +875,80 @@ int mxb_reduce_finalize(mxb_handle_t h, int reduce_op, int32_t value_dtype, cons
     case MXB_I64: return finalize_dispatch_op<mxb::i64, mxb::i64>(h, kop, gathered_records, world, rstride, p);
   }
   return fail(MXB_ERR_NOT_SUPPORTED, "finalize: value dtype not supported");
+}
+
+int mxb_reduce_partial_push(mxb_handle_t h, int reduce_op, const mxb_expr_t *expr, int64_t slab_offset, const mxb_peers_t *peers,
+                            int item, int n_items) {
+  if (!expr) return fail(MXB_ERR_INVALID, "null expression");
+  if (!peers || peers->world < 1 || peers->world > MXB_MAX_PEERS || peers->rank < 0 || peers->rank >= peers->world || !peers->epoch)
+    return fail(MXB_ERR_INVALID, "bad peer table");
+  if (item < 0 || item >= n_items || n_items > MXB_MAX_ITEMS) return fail(MXB_ERR_INVALID, "item index out of range");
+  for (int r = 0; r < peers->world; ++r)
+    if (!peers->rec[r] || !peers->flag[r]) return fail(MXB_ERR_INVALID, "peer buffer missing");
+  if (reduce_op == MXB_RED_VAR || reduce_op == MXB_RED_STDD) return fail(MXB_ERR_NOT_SUPPORTED, "slab-sharded variance is not implemented yet");
+  RedOptions opt;
+  opt.raw_partial = true;
+  opt.idx_base = slab_offset;
+  opt.peers = peers;
+  opt.peer_item = item;
+  mxb_out_t o;
+  memset(&o, 0, sizeof o);
+  o.data = peers->rec[peers->rank];
+  mxb_out_t io = o;
+  io.dtype = MXB_I64;
+  const int op = reduce_op == MXB_RED_MEAN ? MXB_RED_SUM : reduce_op;
+  return reduce_impl(h, op, expr, expr->rank, &o, &io, 0, &opt);
+}
+
+int mxb_enable_peer_access(mxb_handle_t h, int peer_device) {
+  if (!h) return fail(MXB_ERR_INVALID, "null handle");
+  MXB_CUDA(cudaSetDevice(h->device));
+  if (peer_device == h->device) return MXB_OK;
+  int can = 0;
+  MXB_CUDA(cudaDeviceCanAccessPeer(&can, h->device, peer_device));
+  if (!can) return fail(MXB_ERR_NOT_SUPPORTED, "no peer access between device " + std::to_string(h->device) + " and " + std::to_string(peer_device));
+  const cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+  if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return MXB_OK; }
+  if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceEnablePeerAccess");
+  return MXB_OK;
+}
+
+int mxb_exchange_finalize(mxb_handle_t h, const mxb_peers_t *peers, const mxb_fold_item_t *items, int n_items, int64_t global_count) {
+  if (!h) return fail(MXB_ERR_INVALID, "null handle");
+  if (!peers || !items || n_items < 1 || n_items > MXB_MAX_ITEMS) return fail(MXB_ERR_INVALID, "bad exchange arguments");
+  if (peers->world < 1 || peers->world > MXB_MAX_PEERS) return fail(MXB_ERR_INVALID, "bad peer table");
+  MXB_CUDA(cudaSetDevice(h->device));
+  ExchangeParams p;
+  memset(&p, 0, sizeof p);
+  p.rec = (const uint4 *)peers->rec[peers->rank];
+  p.flag = (const unsigned *)peers->flag[peers->rank];
+  p.epoch = (unsigned *)peers->epoch;
+  p.world = peers->world;
+  p.n_items = n_items;
+  p.scale = (double)global_count;
+  for (int k = 0; k < n_items; ++k) {
+    const mxb_fold_item_t &it = items[k];
+    const bool arg = it.reduce_op == MXB_RED_ARGMAX || it.reduce_op == MXB_RED_ARGMIN;
+    if (!it.out || (arg && !it.idx_out)) return fail(MXB_ERR_INVALID, "null output in fold item");
+    switch (it.reduce_op) {
+      case MXB_RED_SUM: case MXB_RED_MEAN: case MXB_RED_PROD: case MXB_RED_MAX: case MXB_RED_MIN: case MXB_RED_ARGMAX:
+      case MXB_RED_ARGMIN: case MXB_RED_ANY: case MXB_RED_ALL: break;
+      default: return fail(MXB_ERR_NOT_SUPPORTED, "fold: reduce op not supported");
+    }
+    if (it.value_dtype != MXB_F32 && it.value_dtype != MXB_F64 && it.value_dtype != MXB_C64 && it.value_dtype != MXB_I32 && it.value_dtype != MXB_I64)
+      return fail(MXB_ERR_NOT_SUPPORTED, "fold: value dtype not supported");
+    if (it.value_dtype == MXB_C64 && it.reduce_op != MXB_RED_SUM && it.reduce_op != MXB_RED_MEAN && it.reduce_op != MXB_RED_PROD)
+      return fail(MXB_ERR_NOT_SUPPORTED, "fold: op not defined for complex");
+    p.item[k].op = it.reduce_op;
+    p.item[k].dtype = it.value_dtype;
+    p.item[k].out = it.out;
+    p.item[k].idx = (long long *)it.idx_out;
+  }
+  exchange_finalize_kernel<<<1, 32, 0, h->stream>>>(p);
+  MXB_CUDA(cudaGetLastError());
+  h->launches++;
+  h->last_kernel = "exchange_finalize";
+  return MXB_OK;
 }
 
 int mxb_elementwise(mxb_handle_t h, const mxb_expr_t *expr_in, const mxb_out_t *out) {

@@ -100,7 +100,15 @@ struct RedParams {
   int all_unit;    // 1 = every leaf is unit-stride along the vector dim
   int tx;          // outer family: threads along the vector (column) dim; blockDim.x / tx reduce lanes
   ConstDev c;
+  // raw_partial == 2: the finished 32-byte record is pushed straight into every rank's exchange buffer over
+  // NVLink peer mappings (no collective call): rec[r] = rank r's PartialRec[2 slots][world][KMAXITEMS],
+  // flag[r] = rank r's arrival counters u32[world], epoch = this rank's count of completed exchanges
+  void *peer_rec[8];
+  u32 *peer_flag[8];
+  const u32 *peer_epoch;
+  int peer_world, peer_rank, peer_item;
 };
+constexpr int KMAXITEMS = 8;  // statements per exchange
 
 // elementwise: up to KMAXD collapsed dims, innermost last
 struct EwParams {
@@ -584,6 +592,17 @@ __device__ __forceinline__ void store_result(const RedParams &p, i64 b, typename
 #pragma unroll
     for (int i = 0; i < 8; ++i) u.rec.w[i] = 0;
     u.a = acc;
+    if (p.raw_partial == 2) {
+      // fused exchange: one writer thread stores the record into every rank's buffer (its own included), fences at
+      // system scope, then bumps that rank's arrival counter for this source — a release over NVLink P2P
+      const u32 e = *(volatile const u32 *)p.peer_epoch + 1u;
+      const int slot = (int)(e & 1u);
+      for (int r = 0; r < p.peer_world; ++r)
+        ((PartialRec *)p.peer_rec[r])[((size_t)slot * p.peer_world + p.peer_rank) * KMAXITEMS + p.peer_item] = u.rec;
+      __threadfence_system();
+      for (int r = 0; r < p.peer_world; ++r) atomicAdd_system(p.peer_flag[r] + p.peer_rank, 1u);
+      return;
+    }
     ((PartialRec *)p.out.ptr)[b] = u.rec;
     return;
   }

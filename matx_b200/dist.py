@@ -106,3 +106,72 @@ class ShardedFullReduce:
         self._exchange(plan["n"])
         for op, vdt, g, stride, gcount, o, io in plan["final"]:
             A.check(lib.mxb_reduce_finalize(h, op, vdt, g, self.world, stride, gcount, 1, C.byref(o), C.byref(io) if io is not None else None))
+
+
+class PeerExchange:
+    """Exchange buffers of every rank, mapped into this process through CUDA IPC, for the fused (NCCL-free) exchange:
+    mxb_reduce_partial_push stores records into all ranks' buffers over NVLink, mxb_exchange_finalize waits and folds.
+    `torch.distributed` is used once, to pass the IPC handles around."""
+
+    FLAG_OFF_PAD = 256
+
+    def __init__(self, ex, world: int, rank: int, group=None, _sim_buffers=None):
+        import torch
+        self.ex, self.world, self.rank = ex, world, rank
+        rec_bytes = A.exchange_rec_bytes(world)
+        self.rec_bytes = rec_bytes
+        total = rec_bytes + 2 * self.FLAG_OFF_PAD
+        self._keep = []
+        if _sim_buffers is not None:              # single-process simulation of `world` ranks on one device (tests)
+            bufs = _sim_buffers
+            self.buf = bufs[rank]
+            bases = [b.data_ptr() for b in bufs]
+        else:
+            import torch.distributed as dist
+            self.buf = torch.zeros(total, dtype=torch.uint8, device="cuda")
+            torch.cuda.synchronize()
+            handle = self.buf.untyped_storage()._share_cuda_()
+            handles = [None] * world
+            dist.all_gather_object(handles, (torch.cuda.current_device(), handle), group=group)
+            bases = []
+            for r, (dev, hd) in enumerate(handles):
+                if r == rank:
+                    bases.append(self.buf.data_ptr())
+                    continue
+                A.check(A.lib.mxb_enable_peer_access(ex.handle, int(dev)))
+                st = torch.UntypedStorage._new_shared_cuda(*hd)
+                self._keep.append(st)
+                bases.append(st.data_ptr())
+            dist.barrier(group=group)
+        self.peers = A.Peers()
+        for r in range(world):
+            self.peers.rec[r] = bases[r]
+            self.peers.flag[r] = bases[r] + rec_bytes
+        self.peers.epoch = self.buf.data_ptr() + rec_bytes + self.FLAG_OFF_PAD
+        self.peers.world, self.peers.rank = world, rank
+
+    @staticmethod
+    def buffer_bytes(world: int) -> int:
+        return A.exchange_rec_bytes(world) + 2 * PeerExchange.FLAG_OFF_PAD
+
+    def prepare(self, items: Sequence[tuple], operand, slab_offset: int, global_count: int, value_dtype: Optional[int] = None):
+        if len(items) > A.MXB_MAX_ITEMS:
+            raise ValueError("at most %d statements per exchange" % A.MXB_MAX_ITEMS)
+        if value_dtype is None:
+            value_dtype = operand.dtype_hint if operand.dtype_hint not in (A.BF16, A.F16) else A.F32
+        n = len(items)
+        fold = (A.FoldItem * n)()
+        pushes = []
+        for k, (op, out, idx) in enumerate(items):
+            e = mx.lower_reduce(mx.ReduceExpr(op, operand, None))
+            pushes.append((op, e, C.c_int64(slab_offset), k))
+            fold[k].reduce_op, fold[k].value_dtype = op, value_dtype
+            fold[k].out = out.data_ptr()
+            fold[k].idx_out = idx.data_ptr() if idx is not None else None
+        return {"n": n, "push": pushes, "fold": fold, "count": C.c_int64(global_count), "keep": (items, operand)}
+
+    def run_prepared(self, plan) -> None:
+        lib, h, peers = A.lib, self.ex.handle, C.byref(self.peers)
+        for op, e, off, k in plan["push"]:
+            A.check(lib.mxb_reduce_partial_push(h, op, C.byref(e), off, peers, k, plan["n"]))
+        A.check(lib.mxb_exchange_finalize(h, peers, plan["fold"], plan["n"], plan["count"]))
