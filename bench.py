@@ -401,6 +401,10 @@ def run_ours(args) -> None:
     if world > 1:
         # a captured graph holds NCCL work: drop it before tearing the communicator down, and never let teardown hang the job
         graph = None
+        torch.cuda.synchronize()
+        dist.barrier()
+        if hasattr(sharded, "close"):
+            sharded.close()
         sharded = None
         torch.cuda.synchronize()
         sys.stderr.flush()

@@ -213,8 +213,15 @@ int mxb_reduce_partial_push(mxb_handle_t h, int reduce_op, const mxb_expr_t *exp
                             const mxb_peers_t *peers, int item, int n_items);
 int mxb_exchange_finalize(mxb_handle_t h, const mxb_peers_t *peers, const mxb_fold_item_t *items, int n_items,
                           int64_t global_count);
-/* cudaDeviceEnablePeerAccess(peer_device) from the handle's device (already-enabled is not an error). */
-int mxb_enable_peer_access(mxb_handle_t h, int peer_device);
+/* Exchange-buffer plumbing (CUDA IPC, one box).  mxb_exchange_alloc: cudaMalloc + zero `bytes` on the handle's
+ * device and export a 64-byte IPC handle; the host passes the handles around (any transport) and every other rank
+ * maps them with mxb_exchange_open from ITS device (peer access is enabled as part of the mapping).  The owner
+ * releases with mxb_exchange_free, importers with mxb_exchange_close. */
+#define MXB_IPC_HANDLE_BYTES 64
+int mxb_exchange_alloc(mxb_handle_t h, size_t bytes, void **out_ptr, unsigned char ipc_handle_out[MXB_IPC_HANDLE_BYTES]);
+int mxb_exchange_open(mxb_handle_t h, const unsigned char ipc_handle[MXB_IPC_HANDLE_BYTES], void **out_peer_ptr);
+int mxb_exchange_close(mxb_handle_t h, void *peer_ptr);
+int mxb_exchange_free(mxb_handle_t h, void *ptr);
 
 /* ---- introspection ---------------------------------------------------------------------------- */
 int mxb_version(void);                /* major*1000 + minor */

@@ -900,16 +900,46 @@ int mxb_reduce_partial_push(mxb_handle_t h, int reduce_op, const mxb_expr_t *exp
   return reduce_impl(h, op, expr, expr->rank, &o, &io, 0, &opt);
 }
 
-int mxb_enable_peer_access(mxb_handle_t h, int peer_device) {
-  if (!h) return fail(MXB_ERR_INVALID, "null handle");
+int mxb_exchange_alloc(mxb_handle_t h, size_t bytes, void **out_ptr, unsigned char ipc_handle_out[MXB_IPC_HANDLE_BYTES]) {
+  if (!h || !out_ptr || !ipc_handle_out || bytes == 0) return fail(MXB_ERR_INVALID, "bad arguments");
+  static_assert(sizeof(cudaIpcMemHandle_t) == MXB_IPC_HANDLE_BYTES, "IPC handle size");
   MXB_CUDA(cudaSetDevice(h->device));
-  if (peer_device == h->device) return MXB_OK;
-  int can = 0;
-  MXB_CUDA(cudaDeviceCanAccessPeer(&can, h->device, peer_device));
-  if (!can) return fail(MXB_ERR_NOT_SUPPORTED, "no peer access between device " + std::to_string(h->device) + " and " + std::to_string(peer_device));
-  const cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
-  if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return MXB_OK; }
-  if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceEnablePeerAccess");
+  void *p = nullptr;
+  MXB_CUDA(cudaMalloc(&p, bytes));
+  MXB_CUDA(cudaMemset(p, 0, bytes));
+  MXB_CUDA(cudaDeviceSynchronize());
+  cudaIpcMemHandle_t hd;
+  cudaError_t e = cudaIpcGetMemHandle(&hd, p);
+  if (e != cudaSuccess) { cudaFree(p); return cuda_fail(e, "cudaIpcGetMemHandle"); }
+  memcpy(ipc_handle_out, &hd, sizeof hd);
+  *out_ptr = p;
+  return MXB_OK;
+}
+
+int mxb_exchange_open(mxb_handle_t h, const unsigned char ipc_handle[MXB_IPC_HANDLE_BYTES], void **out_peer_ptr) {
+  if (!h || !ipc_handle || !out_peer_ptr) return fail(MXB_ERR_INVALID, "bad arguments");
+  MXB_CUDA(cudaSetDevice(h->device));
+  cudaIpcMemHandle_t hd;
+  memcpy(&hd, ipc_handle, sizeof hd);
+  void *p = nullptr;
+  MXB_CUDA(cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess));
+  *out_peer_ptr = p;
+  return MXB_OK;
+}
+
+int mxb_exchange_close(mxb_handle_t h, void *peer_ptr) {
+  if (!h) return fail(MXB_ERR_INVALID, "null handle");
+  if (!peer_ptr) return MXB_OK;
+  MXB_CUDA(cudaSetDevice(h->device));
+  MXB_CUDA(cudaIpcCloseMemHandle(peer_ptr));
+  return MXB_OK;
+}
+
+int mxb_exchange_free(mxb_handle_t h, void *ptr) {
+  if (!h) return fail(MXB_ERR_INVALID, "null handle");
+  if (!ptr) return MXB_OK;
+  MXB_CUDA(cudaSetDevice(h->device));
+  MXB_CUDA(cudaFree(ptr));
   return MXB_OK;
 }
 

@@ -128,27 +128,40 @@ class PeerExchange:
             bases = [b.data_ptr() for b in bufs]
         else:
             import torch.distributed as dist
-            self.buf = torch.zeros(total, dtype=torch.uint8, device="cuda")
-            torch.cuda.synchronize()
-            handle = self.buf.untyped_storage()._share_cuda_()
+            own = C.c_void_p()
+            hbuf = C.create_string_buffer(64)
+            A.check(A.lib.mxb_exchange_alloc(ex.handle, total, C.byref(own), hbuf))
+            self._own, self._opened = own, []
             handles = [None] * world
-            dist.all_gather_object(handles, (torch.cuda.current_device(), handle), group=group)
+            dist.all_gather_object(handles, bytes(hbuf.raw), group=group)
             bases = []
-            for r, (dev, hd) in enumerate(handles):
+            for r, hd in enumerate(handles):
                 if r == rank:
-                    bases.append(self.buf.data_ptr())
+                    bases.append(own.value)
                     continue
-                A.check(A.lib.mxb_enable_peer_access(ex.handle, int(dev)))
-                st = torch.UntypedStorage._new_shared_cuda(*hd)
-                self._keep.append(st)
-                bases.append(st.data_ptr())
+                pp = C.c_void_p()
+                A.check(A.lib.mxb_exchange_open(ex.handle, hd, C.byref(pp)))
+                self._opened.append(pp)
+                bases.append(pp.value)
             dist.barrier(group=group)
+            self.buf = None
+            self._base = own.value
         self.peers = A.Peers()
         for r in range(world):
             self.peers.rec[r] = bases[r]
             self.peers.flag[r] = bases[r] + rec_bytes
-        self.peers.epoch = self.buf.data_ptr() + rec_bytes + self.FLAG_OFF_PAD
+        own_base = bases[rank]
+        self.peers.epoch = own_base + rec_bytes + self.FLAG_OFF_PAD
         self.peers.world, self.peers.rank = world, rank
+
+    def close(self) -> None:
+        """Unmap the peers' buffers and free this rank's (call after a barrier: peers may still be reading)."""
+        for pp in getattr(self, "_opened", []):
+            A.lib.mxb_exchange_close(self.ex.handle, pp)
+        self._opened = []
+        if getattr(self, "_own", None) is not None:
+            A.lib.mxb_exchange_free(self.ex.handle, self._own)
+            self._own = None
 
     @staticmethod
     def buffer_bytes(world: int) -> int:
