@@ -191,7 +191,24 @@ int launch(mxb_context *h, const Kernel &k, unsigned grid, unsigned block, unsig
     // static + dynamic shared memory above 48 KB needs the opt-in; the kernels carry up to ~3 KB of static smem
     if (smem > 40 * 1024) MXB_CUDA(cudaFuncSetAttribute(k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     void *args[] = {(void *)&params};
-    MXB_CUDA(cudaLaunchKernel(k.fn, dim3(grid), dim3(block), args, smem, h->stream));
+    if (env_int("MXB_PDL", 1)) {
+      // programmatic dependent launch: the kernel may be scheduled while its predecessor on the stream drains; every
+      // kernel body starts with griddepcontrol.wait, so nothing is read or written before the predecessor has completed
+      cudaLaunchConfig_t cfg;
+      memset(&cfg, 0, sizeof cfg);
+      cfg.gridDim = dim3(grid);
+      cfg.blockDim = dim3(block);
+      cfg.dynamicSmemBytes = smem;
+      cfg.stream = h->stream;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      MXB_CUDA(cudaLaunchKernelExC(&cfg, k.fn, args));
+    } else {
+      MXB_CUDA(cudaLaunchKernel(k.fn, dim3(grid), dim3(block), args, smem, h->stream));
+    }
   }
   h->launches++;
   h->last_kernel = k.key + (k.jit ? "|jit" : "|aot");
@@ -466,7 +483,10 @@ int reduce_launch(mxb_context *h, int kop, const mxb_expr_t &e, const ExprInfo &
     const int64_t row_bytes = R * info.max_leaf_bytes;
     spec.team = (row_bytes >= 8192) ? 0 : 1;
     if (env_int("MXB_TUNE_TEAM", -1) >= 0) spec.team = env_int("MXB_TUNE_TEAM", -1);
-    const int cps = tune_cps > 0 ? tune_cps : 8;
+    // 8 CTAs of 256 threads per SM = two waves (the block scheduler evens out the tail) for big inputs; below ~8 MiB
+    // per SM one resident wave (4 CTAs/SM at 64 registers) has the smaller fixed cost (tools/small_sweep.py)
+    const int64_t bytes_per_sm = B * R * info.max_leaf_bytes * std::max(1, nl) / sm;
+    const int cps = tune_cps > 0 ? tune_cps : (bytes_per_sm < (8ll << 20) ? 4 : 8);
     if (spec.team == 0) {
       const int64_t L = gr.size[gr.n - 1];
       const int64_t Q = (R / L) * (L / spec.V);  // vector steps per row

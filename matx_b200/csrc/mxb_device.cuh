@@ -788,6 +788,9 @@ __device__ __forceinline__ void reduce_inner_body_impl(const RedParams &p) {
     }
 #pragma unroll
     for (int v = 1; v < V; ++v) Op::merge(acc[0], acc[v]);
+    // streaming part of this CTA's last work item is over: let the next kernel on the stream start launching while
+    // the warp / CTA / grid stages finish (it still waits for this grid to complete before touching memory)
+    if (w + nteam >= work) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     if (TEAM == 1) {
       acc_t tot = Op::warp(acc[0]);
@@ -1205,6 +1208,7 @@ template <> struct Widen<__half> { typedef float type; };
 
 template <class Tin, class OutT, int IPT>
 __device__ __forceinline__ void var_inner_tma_body(const RedParams &p) {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   typedef typename Widen<Tin>::type T;
   typedef typename AbsDev2<T>::real_t RT;
   enum { V = 16 / (int)sizeof(Tin) };
@@ -1395,33 +1399,44 @@ __device__ __forceinline__ void ew_body_impl(const EwParams &p) {
 }
 
 
+// Programmatic dependent launch: let the next kernel on the stream start its launch while this one runs, and do not
+// touch memory before the previous kernel has completed and flushed (no-ops without the launch attribute).
+__device__ __forceinline__ void pdl_prologue() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 // launch-time dispatch on the unit-stride flag
 template <class E, class Op, class OutT, int V, int U, int TEAM>
 __device__ __forceinline__ void reduce_inner_body(const RedParams &p) {
+  pdl_prologue();
   if (p.all_unit) reduce_inner_body_impl<E, Op, OutT, V, U, TEAM, true>(p);
   else reduce_inner_body_impl<E, Op, OutT, V, U, TEAM, false>(p);
 }
 
 template <class E, class Op, class OutT, int V, int U>
 __device__ __forceinline__ void reduce_outer_body(const RedParams &p) {
+  pdl_prologue();
   if (p.all_unit) reduce_outer_body_impl<E, Op, OutT, V, U, true>(p);
   else reduce_outer_body_impl<E, Op, OutT, V, U, false>(p);
 }
 
 template <class E, class OutT, int V, int U>
 __device__ __forceinline__ void var_inner_smem_body(const RedParams &p) {
+  pdl_prologue();
   if (p.all_unit) var_inner_smem_body_impl<E, OutT, V, U, true>(p);
   else var_inner_smem_body_impl<E, OutT, V, U, false>(p);
 }
 
 template <class E, class OutT, int V, int U>
 __device__ __forceinline__ void ew_body(const EwParams &p) {
+  pdl_prologue();
   if (p.all_unit) ew_body_impl<E, OutT, V, U, true>(p);
   else ew_body_impl<E, OutT, V, U, false>(p);
 }
 
 template <class E, class OutT, int V, int IPT>
 __device__ __forceinline__ void var_inner_reg_body(const RedParams &p) {
+  pdl_prologue();
   if (p.all_unit) var_inner_reg_body_impl<E, OutT, V, IPT, true>(p);
   else var_inner_reg_body_impl<E, OutT, V, IPT, false>(p);
 }
