@@ -349,6 +349,21 @@ MXB_SHIM_ARGREDUCE(argmax, MXB_RED_ARGMAX)
 MXB_SHIM_ARGREDUCE(argmin, MXB_RED_ARGMIN)
 #undef MXB_SHIM_ARGREDUCE
 
+// argminmax (transforms/reduce.h:1090-1109): min and max with their indices.  Served as argmin + argmax — two
+// single-pass launches at the HBM roofline each (the reference's dual-arg CUB path first materialises operator inputs
+// and carries 32-byte tuples); a fused dual-arg operator is listed under "next" in DESIGN.md.
+template <typename OutType, typename TensorIndexType, typename InType>
+void argminmax_impl(OutType destmin, TensorIndexType &idestmin, OutType destmax, TensorIndexType &idestmax, const InType &in,
+                    const b200Executor &exec) {
+  if (exec.reduce_idx(MXB_RED_ARGMIN, destmin, &idestmin, in, 1) && exec.reduce_idx(MXB_RED_ARGMAX, destmax, &idestmax, in, 1)) return;
+  argminmax_impl(destmin, idestmin, destmax, idestmax, in, static_cast<const cudaExecutor &>(exec));
+}
+template <typename OutType, typename TensorIndexType, typename InType>
+void argminmax_impl(OutType destmin, TensorIndexType &idestmin, OutType destmax, TensorIndexType &idestmax, const InType &in,
+                    b200Executor &exec) {
+  argminmax_impl(destmin, idestmin, destmax, idestmax, in, static_cast<const b200Executor &>(exec));
+}
+
 // var / stdd are generic over the executor in the reference (transforms/reduce.h:1406-1479); these are more specialised
 #define MXB_SHIM_VAR(NAME, CODE)                                                                              \
   template <typename OutType, typename InType>                                                                \

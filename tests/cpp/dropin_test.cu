@@ -83,6 +83,16 @@ static int run_checks() {
     bool same = true;
     for (index_t r = 0; r < rows; ++r) same = same && v1(r) == v2(r) && ir1(r) == ir2(r);
     report("mtie(v,i)=argmin(a,{1}) absolute index", same && *b200.last_kernel(), b200.last_kernel());
+    {
+      auto mn1 = make_tensor<float>({rows}), mn2 = make_tensor<float>({rows}), mx1 = make_tensor<float>({rows}), mx2 = make_tensor<float>({rows});
+      auto in1 = make_tensor<index_t>({rows}), in2 = make_tensor<index_t>({rows}), ix1 = make_tensor<index_t>({rows}), ix2 = make_tensor<index_t>({rows});
+      (mtie(mn1, in1, mx1, ix1) = argminmax(a, {1})).run(ref);
+      (mtie(mn2, in2, mx2, ix2) = argminmax(a, {1})).run(b200);
+      ref.sync();
+      bool ok = true;
+      for (index_t r = 0; r < rows; ++r) ok = ok && mn1(r) == mn2(r) && mx1(r) == mx2(r) && in1(r) == in2(r) && ix1(r) == ix2(r);
+      report("mtie(mn,imn,mx,imx)=argminmax(a,{1})", ok && *b200.last_kernel(), b200.last_kernel());
+    }
     (v1 = any(a > 0.9999f, {1})).run(ref); (v2 = any(a > 0.9999f, {1})).run(b200); ref.sync();
     report("any(a>0.9999f,{1})", max_rel(v2, v1, rows) == 0 && *b200.last_kernel(), b200.last_kernel());
     // elementwise with broadcast scalar, unary chain
