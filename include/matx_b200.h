@@ -176,7 +176,8 @@ int mxb_reduce(mxb_handle_t h, int reduce_op, const mxb_expr_t *expr, int n_redu
  * 32-byte device record, the host exchanges the records with ONE collective (NCCL all-gather of
  * world*32 bytes), and mxb_reduce_finalize folds them in rank order (deterministic; lowest global
  * index wins ties).  `slab_offset` is the global flat index of the slab's first element and
- * `global_count` the total element count (MEAN/VAR divisors).  Rank r's record is read at
+ * `global_count` the total element count (MEAN divisor).  VAR / STDD records hold the slab's (mean, sum |x-mean|^2, n)
+ * in fp64 and are combined with Chan's formula in rank order, divisor N - ddof.  Rank r's record is read at
  * gathered_records + r * record_stride_bytes, so the records of several statements can share one
  * exchange (record_stride_bytes = 32 * statements per step; 0 means 32). */
 #define MXB_PARTIAL_BYTES 32
@@ -204,10 +205,12 @@ typedef struct {
   int32_t world, rank;
 } mxb_peers_t;
 typedef struct {
-  int32_t reduce_op;   /* SUM, MEAN, PROD, MAX, MIN, ARGMAX, ARGMIN, ANY, ALL */
+  int32_t reduce_op;   /* SUM, MEAN, PROD, MAX, MIN, ARGMAX, ARGMIN, ANY, ALL, VAR, STDD */
   int32_t value_dtype; /* arithmetic type of the reduced expression (F32, F64, C64, I32, I64) */
-  void *out;           /* one element of value_dtype */
+  void *out;           /* one element of value_dtype (VAR / STDD: the real type, fp32 for F32 / C64, fp64 for F64) */
   void *idx_out;       /* one int64 (ARGMAX / ARGMIN), else NULL */
+  int32_t ddof;        /* VAR / STDD divisor N - ddof */
+  int32_t _pad;
 } mxb_fold_item_t;
 int mxb_reduce_partial_push(mxb_handle_t h, int reduce_op, const mxb_expr_t *expr, int64_t slab_offset,
                             const mxb_peers_t *peers, int item, int n_items);

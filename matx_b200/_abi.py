@@ -82,7 +82,8 @@ class Peers(C.Structure):
 
 
 class FoldItem(C.Structure):
-    _fields_ = [("reduce_op", C.c_int32), ("value_dtype", C.c_int32), ("out", C.c_void_p), ("idx_out", C.c_void_p)]
+    _fields_ = [("reduce_op", C.c_int32), ("value_dtype", C.c_int32), ("out", C.c_void_p), ("idx_out", C.c_void_p),
+                ("ddof", C.c_int32), ("_pad", C.c_int32)]
 
 
 def exchange_rec_bytes(world: int) -> int:

@@ -142,6 +142,18 @@ void fill_consts(const mxb_expr_t &e, mxb::ConstDev &c) {
   }
 }
 
+void fill_peer_push(mxb::PeerPush &pp, const mxb_peers_t &peers, int item) {
+  memset(&pp, 0, sizeof pp);
+  for (int r = 0; r < peers.world; ++r) {
+    pp.rec[r] = peers.rec[r];
+    pp.flag[r] = (unsigned *)peers.flag[r];
+  }
+  pp.epoch = (const unsigned *)peers.epoch;
+  pp.world = peers.world;
+  pp.rank = peers.rank;
+  pp.item = item;
+}
+
 bool aligned_to(const void *p, int64_t bytes) { return ((uintptr_t)p % (uintptr_t)bytes) == 0; }
 int env_int(const char *name, int dflt) {
   const char *v = getenv(name);
@@ -442,14 +454,7 @@ int reduce_launch(mxb_context *h, int kop, const mxb_expr_t &e, const ExprInfo &
   p.raw_partial = opt.raw_partial ? 1 : 0;
   if (opt.raw_partial && opt.peers) {
     p.raw_partial = 2;
-    for (int r = 0; r < opt.peers->world; ++r) {
-      p.peer_rec[r] = opt.peers->rec[r];
-      p.peer_flag[r] = (unsigned *)opt.peers->flag[r];
-    }
-    p.peer_epoch = (const unsigned *)opt.peers->epoch;
-    p.peer_world = opt.peers->world;
-    p.peer_rank = opt.peers->rank;
-    p.peer_item = opt.peer_item;
+    fill_peer_push(p.peer, *opt.peers, opt.peer_item);
   }
   fill_consts(e, p.c);
   const int vec_is_batch_dim = (rot >= 0);
@@ -530,6 +535,85 @@ int reduce_launch(mxb_context *h, int kop, const mxb_expr_t &e, const ExprInfo &
 
 bool is_floating(int t) { return t == MXB_F32 || t == MXB_F64 || t == MXB_C64; }
 
+// ---- slab-sharded variance: the slab's (mean, M2 = sum |x - mean|^2, n) as one 32-byte record of doubles ----
+struct VarRec { double mre, mim, m2, n; };
+static_assert(sizeof(VarRec) == MXB_PARTIAL_BYTES, "variance record is one partial record");
+
+template <class T, class RT>
+__global__ void pack_var_kernel(const T *mean, const RT *m2, double n, VarRec *dst, int push, const __grid_constant__ mxb::PeerPush pp) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  VarRec r;
+  if constexpr (mxb::is_complex<T>::value) { r.mre = mean->re; r.mim = mean->im; }
+  else { r.mre = (double)*mean; r.mim = 0.0; }
+  r.m2 = (double)*m2;
+  r.n = n;
+  if (push) {
+    union { VarRec v; mxb::PartialRec p; } u;
+    u.v = r;
+    mxb::push_record(pp, u.p);
+  } else {
+    *dst = r;
+  }
+}
+
+// the slab's record: mean (one launch), sum |x - mean|^2 with the mean as a broadcast leaf (one launch), pack / push
+int var_partial(mxb_context *h, const mxb_expr_t &e, const ExprInfo &info, const RedOptions &popt, void *record) {
+  int64_t n = 1;
+  for (int d = 0; d < e.rank; ++d) n *= e.size[d];
+  if (n <= 0) return fail(MXB_ERR_INVALID, "variance of an empty slab");
+  int st = ensure_tmp(h, 64);
+  if (st != MXB_OK) return st;
+  const int rdt = info.value_dtype == MXB_F64 ? MXB_F64 : MXB_F32;
+  mxb_out_t mean_out;
+  memset(&mean_out, 0, sizeof mean_out);
+  mean_out.data = h->tmp;
+  mean_out.dtype = info.value_dtype;
+  RedOptions mo;
+  mo.post_div = true;
+  mo.post_scale = (double)n;
+  st = reduce_launch(h, MXB_RED_SUM, e, info, e.rank, &mean_out, nullptr, mo, false);
+  if (st != MXB_OK) return st;
+  if (e.n_leaves >= MXB_MAX_LEAVES || e.n_nodes + 3 > MXB_MAX_NODES) return fail(MXB_ERR_NOT_SUPPORTED, "expression too large for the sharded variance");
+  mxb_expr_t e2 = e;
+  const int lk = e2.n_leaves++;
+  memset(&e2.leaves[lk], 0, sizeof e2.leaves[lk]);
+  e2.leaves[lk].data = h->tmp;
+  e2.leaves[lk].dtype = info.value_dtype;
+  const int nleafnode = e2.n_nodes++;
+  e2.nodes[nleafnode] = mxb_node_t{MXB_OP_LEAF, {lk, -1}, 0};
+  const int nsub = e2.n_nodes++;
+  e2.nodes[nsub] = mxb_node_t{MXB_OP_SUB, {e.root, nleafnode}, 0};
+  const int nabs2 = e2.n_nodes++;
+  e2.nodes[nabs2] = mxb_node_t{MXB_OP_ABS2, {nsub, -1}, 0};
+  e2.root = nabs2;
+  mxb_expr_t e2c;
+  std::string err;
+  st = canonicalize(&e2, &e2c, &err);
+  if (st != MXB_OK) return fail(st, err);
+  ExprInfo info2;
+  st = analyze_expr(&e2c, &info2, &err);
+  if (st != MXB_OK) return fail(st, err);
+  mxb_out_t m2_out;
+  memset(&m2_out, 0, sizeof m2_out);
+  m2_out.data = (char *)h->tmp + 16;
+  m2_out.dtype = rdt;
+  st = reduce_launch(h, MXB_RED_SUM, e2c, info2, e.rank, &m2_out, nullptr, RedOptions(), false);
+  if (st != MXB_OK) return st;
+  mxb::PeerPush pp;
+  memset(&pp, 0, sizeof pp);
+  const int push = popt.peers ? 1 : 0;
+  if (push) fill_peer_push(pp, *popt.peers, popt.peer_item);
+  VarRec *dst = (VarRec *)record;
+  switch (info.value_dtype) {
+    case MXB_F32: pack_var_kernel<float, float><<<1, 32, 0, h->stream>>>((const float *)h->tmp, (const float *)((char *)h->tmp + 16), (double)n, dst, push, pp); break;
+    case MXB_F64: pack_var_kernel<double, double><<<1, 32, 0, h->stream>>>((const double *)h->tmp, (const double *)((char *)h->tmp + 16), (double)n, dst, push, pp); break;
+    default: pack_var_kernel<mxb::cfloat, float><<<1, 32, 0, h->stream>>>((const mxb::cfloat *)h->tmp, (const float *)((char *)h->tmp + 16), (double)n, dst, push, pp); break;
+  }
+  MXB_CUDA(cudaGetLastError());
+  h->launches++;
+  return MXB_OK;
+}
+
 int reduce_impl(mxb_context *h, int op, const mxb_expr_t *expr_in, int n_reduce, const mxb_out_t *out, const mxb_out_t *idx_out,
                 int ddof, const RedOptions *partial_opt) {
   if (!h) return fail(MXB_ERR_INVALID, "null handle");
@@ -573,8 +657,8 @@ int reduce_impl(mxb_context *h, int op, const mxb_expr_t *expr_in, int n_reduce,
   for (int d = nbd; d < e.rank; ++d) R *= e.size[d];
 
   if (op == MXB_RED_VAR || op == MXB_RED_STDD) {
-    if (partial_opt) return fail(MXB_ERR_NOT_SUPPORTED, "slab-sharded variance is not implemented yet");
     if (!is_floating(info.value_dtype)) return fail(MXB_ERR_NOT_SUPPORTED, "var/stdd of a non-floating expression");
+    if (partial_opt) return var_partial(h, e, info, *partial_opt, out->data);
     if (out->dtype == MXB_C64) return fail(MXB_ERR_INVALID, "var/stdd output is real (the reference uses the inner type)");
     opt.post_scale = (double)(R - ddof);
     opt.post_sqrt = (op == MXB_RED_STDD);
@@ -649,6 +733,33 @@ __global__ void finalize_kernel(const uint4 *recs, int world, int stride16, cons
   mxb::store_result<Op, OutT>(p, 0, a);
 }
 
+// Chan's parallel combination of (n, mean, M2) triples, in fp64, rank order
+__device__ inline double combine_var(const uint4 *recs, int world, int stride16, int ddof) {
+  double n_tot = 0, mre = 0, mim = 0;
+  for (int r = 0; r < world; ++r) {
+    const volatile double *v = (const volatile double *)(recs + (size_t)r * stride16);
+    n_tot += v[3];
+    mre += v[3] * v[0];
+    mim += v[3] * v[1];
+  }
+  mre /= n_tot;
+  mim /= n_tot;
+  double m2 = 0;
+  for (int r = 0; r < world; ++r) {
+    const volatile double *v = (const volatile double *)(recs + (size_t)r * stride16);
+    const double dr = v[0] - mre, di = v[1] - mim;
+    m2 += v[2] + v[3] * (dr * dr + di * di);
+  }
+  return m2 / (n_tot - (double)ddof);
+}
+template <class OutT>
+__global__ void finalize_var_kernel(const uint4 *recs, int world, int stride16, int ddof, int take_sqrt, OutT *out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double v = combine_var(recs, world, stride16, ddof);
+  if (take_sqrt) v = sqrt(v);
+  *out = (OutT)v;
+}
+
 template <class T, class OutT>
 int finalize_dispatch_op(mxb_context *h, int kop, const void *recs, int world, int stride16, RedParams &p) {
 #define MXB_FIN(...) finalize_kernel<__VA_ARGS__, OutT><<<1, 32, 0, h->stream>>>((const uint4 *)recs, world, stride16, p)
@@ -680,7 +791,7 @@ int finalize_dispatch_op(mxb_context *h, int kop, const void *recs, int world, i
 // ---------------------------------------------------------------------------------------------------
 // fused exchange: wait for every rank's arrival counter, then fold all statements (one warp, one launch per step)
 // ---------------------------------------------------------------------------------------------------
-struct FoldItemDev { int op, dtype; void *out; long long *idx; };
+struct FoldItemDev { int op, dtype; void *out; long long *idx; int ddof, pad_; };
 struct ExchangeParams {
   const uint4 *rec;        // this rank's buffer: PartialRec[2][world][KMAXITEMS]
   const unsigned *flag;    // this rank's arrival counters [world]
@@ -757,7 +868,12 @@ __global__ void exchange_finalize_kernel(const __grid_constant__ ExchangeParams 
     const FoldItemDev it = p.item[lane];
     const uint4 *recs = p.rec + ((size_t)slot * p.world * mxb::KMAXITEMS + lane) * 2;  // 2 x uint4 per 32-byte record
     const int stride16 = mxb::KMAXITEMS * 2;
-    if (it.op == MXB_RED_ANY || it.op == MXB_RED_ALL) {
+    if (it.op == MXB_RED_VAR || it.op == MXB_RED_STDD) {
+      double v = combine_var(recs, p.world, stride16, it.ddof);
+      if (it.op == MXB_RED_STDD) v = sqrt(v);
+      if (it.dtype == MXB_F64) *(double *)it.out = v;
+      else *(float *)it.out = (float)v;   // fp32 and complex<float> inputs: fp32 result (the reference's inner type)
+    } else if (it.op == MXB_RED_ANY || it.op == MXB_RED_ALL) {
       switch (it.dtype) {
         case MXB_F32: fold_logic<float>(it.op, recs, p.world, stride16, it.out); break;
         case MXB_F64: fold_logic<double>(it.op, recs, p.world, stride16, it.out); break;
@@ -869,7 +985,6 @@ int mxb_reduce_partial(mxb_handle_t h, int reduce_op, const mxb_expr_t *expr, in
 
 int mxb_reduce_finalize(mxb_handle_t h, int reduce_op, int32_t value_dtype, const void *gathered_records, int world,
                         int64_t record_stride_bytes, int64_t global_count, int ddof, const mxb_out_t *out, const mxb_out_t *idx_out) {
-  (void)ddof;
   if (!h) return fail(MXB_ERR_INVALID, "null handle");
   if (!gathered_records || world <= 0) return fail(MXB_ERR_INVALID, "no records to fold");
   if (record_stride_bytes == 0) record_stride_bytes = MXB_PARTIAL_BYTES;
@@ -878,6 +993,17 @@ int mxb_reduce_finalize(mxb_handle_t h, int reduce_op, int32_t value_dtype, cons
   if (!out || !out->data) return fail(MXB_ERR_INVALID, "null output");
   const bool arg = reduce_op == MXB_RED_ARGMAX || reduce_op == MXB_RED_ARGMIN;
   if (arg && (!idx_out || !idx_out->data || idx_out->dtype != MXB_I64)) return fail(MXB_ERR_INVALID, "argmax/argmin need an MXB_I64 index output");
+  if (reduce_op == MXB_RED_VAR || reduce_op == MXB_RED_STDD) {
+    MXB_CUDA(cudaSetDevice(h->device));
+    const int sq = reduce_op == MXB_RED_STDD;
+    if (out->dtype == MXB_F32) finalize_var_kernel<float><<<1, 32, 0, h->stream>>>((const uint4 *)gathered_records, world, rstride, ddof, sq, (float *)out->data);
+    else if (out->dtype == MXB_F64) finalize_var_kernel<double><<<1, 32, 0, h->stream>>>((const uint4 *)gathered_records, world, rstride, ddof, sq, (double *)out->data);
+    else return fail(MXB_ERR_INVALID, "var/stdd output is real (fp32 or fp64)");
+    MXB_CUDA(cudaGetLastError());
+    h->launches++;
+    h->last_kernel = "finalize_var";
+    return MXB_OK;
+  }
   if (out->dtype != value_dtype) return fail(MXB_ERR_NOT_SUPPORTED, "finalize writes the value dtype only");
   MXB_CUDA(cudaSetDevice(h->device));
   RedParams p;
@@ -905,7 +1031,6 @@ int mxb_reduce_partial_push(mxb_handle_t h, int reduce_op, const mxb_expr_t *exp
   if (item < 0 || item >= n_items || n_items > MXB_MAX_ITEMS) return fail(MXB_ERR_INVALID, "item index out of range");
   for (int r = 0; r < peers->world; ++r)
     if (!peers->rec[r] || !peers->flag[r]) return fail(MXB_ERR_INVALID, "peer buffer missing");
-  if (reduce_op == MXB_RED_VAR || reduce_op == MXB_RED_STDD) return fail(MXB_ERR_NOT_SUPPORTED, "slab-sharded variance is not implemented yet");
   RedOptions opt;
   opt.raw_partial = true;
   opt.idx_base = slab_offset;
@@ -982,17 +1107,19 @@ int mxb_exchange_finalize(mxb_handle_t h, const mxb_peers_t *peers, const mxb_fo
     if (!it.out || (arg && !it.idx_out)) return fail(MXB_ERR_INVALID, "null output in fold item");
     switch (it.reduce_op) {
       case MXB_RED_SUM: case MXB_RED_MEAN: case MXB_RED_PROD: case MXB_RED_MAX: case MXB_RED_MIN: case MXB_RED_ARGMAX:
-      case MXB_RED_ARGMIN: case MXB_RED_ANY: case MXB_RED_ALL: break;
+      case MXB_RED_ARGMIN: case MXB_RED_ANY: case MXB_RED_ALL: case MXB_RED_VAR: case MXB_RED_STDD: break;
       default: return fail(MXB_ERR_NOT_SUPPORTED, "fold: reduce op not supported");
     }
     if (it.value_dtype != MXB_F32 && it.value_dtype != MXB_F64 && it.value_dtype != MXB_C64 && it.value_dtype != MXB_I32 && it.value_dtype != MXB_I64)
       return fail(MXB_ERR_NOT_SUPPORTED, "fold: value dtype not supported");
-    if (it.value_dtype == MXB_C64 && it.reduce_op != MXB_RED_SUM && it.reduce_op != MXB_RED_MEAN && it.reduce_op != MXB_RED_PROD)
+    if (it.value_dtype == MXB_C64 && it.reduce_op != MXB_RED_SUM && it.reduce_op != MXB_RED_MEAN && it.reduce_op != MXB_RED_PROD &&
+        it.reduce_op != MXB_RED_VAR && it.reduce_op != MXB_RED_STDD)
       return fail(MXB_ERR_NOT_SUPPORTED, "fold: op not defined for complex");
     p.item[k].op = it.reduce_op;
     p.item[k].dtype = it.value_dtype;
     p.item[k].out = it.out;
     p.item[k].idx = (long long *)it.idx_out;
+    p.item[k].ddof = it.ddof;
   }
   exchange_finalize_kernel<<<1, 32, 0, h->stream>>>(p);
   MXB_CUDA(cudaGetLastError());

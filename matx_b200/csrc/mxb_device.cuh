@@ -80,6 +80,15 @@ struct ConstDev {
   i64 ire[KMAXCONST];
 };
 
+constexpr int KMAXITEMS = 8;  // statements per exchange
+// where a finished 32-byte record is pushed in the fused multi-GPU exchange
+struct PeerPush {
+  void *rec[8];        // rank r's PartialRec[2 slots][world][KMAXITEMS], as mapped into this device
+  u32 *flag[8];        // rank r's arrival counters u32[world]
+  const u32 *epoch;    // this rank's count of completed exchanges
+  int world, rank, item, pad_;
+};
+
 // reduction: batch dims (nb of them, row-major) x reduce dims (nr of them, row-major, innermost last)
 struct RedParams {
   int nb, nr;
@@ -103,12 +112,8 @@ struct RedParams {
   // raw_partial == 2: the finished 32-byte record is pushed straight into every rank's exchange buffer over
   // NVLink peer mappings (no collective call): rec[r] = rank r's PartialRec[2 slots][world][KMAXITEMS],
   // flag[r] = rank r's arrival counters u32[world], epoch = this rank's count of completed exchanges
-  void *peer_rec[8];
-  u32 *peer_flag[8];
-  const u32 *peer_epoch;
-  int peer_world, peer_rank, peer_item;
+  PeerPush peer;
 };
-constexpr int KMAXITEMS = 8;  // statements per exchange
 
 // elementwise: up to KMAXD collapsed dims, innermost last
 struct EwParams {
@@ -574,6 +579,17 @@ template <> struct Post<cfloat> {
 // 32-byte partial record exchanged between GPUs (mxb_reduce_partial / mxb_reduce_finalize)
 struct __align__(16) PartialRec { u32 w[8]; };
 
+// fused exchange: one writer thread stores the record into every rank's buffer (its own included), fences at system
+// scope, then bumps that rank's arrival counter for this source — a release over NVLink peer mappings
+__device__ __forceinline__ void push_record(const PeerPush &pp, const PartialRec &rec) {
+  const u32 e = *(volatile const u32 *)pp.epoch + 1u;
+  const int slot = (int)(e & 1u);
+  for (int r = 0; r < pp.world; ++r)
+    ((PartialRec *)pp.rec[r])[((size_t)slot * pp.world + pp.rank) * KMAXITEMS + pp.item] = rec;
+  __threadfence_system();
+  for (int r = 0; r < pp.world; ++r) atomicAdd_system(pp.flag[r] + pp.rank, 1u);
+}
+
 // flat index -> per-dim indices (row-major over n dims of sizes sz[])
 __device__ __forceinline__ void decomp(i64 flat, int n, const i64 *sz, i64 *idx) {
 #pragma unroll
@@ -593,14 +609,7 @@ __device__ __forceinline__ void store_result(const RedParams &p, i64 b, typename
     for (int i = 0; i < 8; ++i) u.rec.w[i] = 0;
     u.a = acc;
     if (p.raw_partial == 2) {
-      // fused exchange: one writer thread stores the record into every rank's buffer (its own included), fences at
-      // system scope, then bumps that rank's arrival counter for this source — a release over NVLink P2P
-      const u32 e = *(volatile const u32 *)p.peer_epoch + 1u;
-      const int slot = (int)(e & 1u);
-      for (int r = 0; r < p.peer_world; ++r)
-        ((PartialRec *)p.peer_rec[r])[((size_t)slot * p.peer_world + p.peer_rank) * KMAXITEMS + p.peer_item] = u.rec;
-      __threadfence_system();
-      for (int r = 0; r < p.peer_world; ++r) atomicAdd_system(p.peer_flag[r] + p.peer_rank, 1u);
+      push_record(p.peer, u.rec);
       return;
     }
     ((PartialRec *)p.out.ptr)[b] = u.rec;

@@ -167,7 +167,7 @@ class PeerExchange:
     def buffer_bytes(world: int) -> int:
         return A.exchange_rec_bytes(world) + 2 * PeerExchange.FLAG_OFF_PAD
 
-    def prepare(self, items: Sequence[tuple], operand, slab_offset: int, global_count: int, value_dtype: Optional[int] = None):
+    def prepare(self, items: Sequence[tuple], operand, slab_offset: int, global_count: int, value_dtype: Optional[int] = None, ddof: int = 1):
         if len(items) > A.MXB_MAX_ITEMS:
             raise ValueError("at most %d statements per exchange" % A.MXB_MAX_ITEMS)
         if value_dtype is None:
@@ -181,6 +181,7 @@ class PeerExchange:
             fold[k].reduce_op, fold[k].value_dtype = op, value_dtype
             fold[k].out = out.data_ptr()
             fold[k].idx_out = idx.data_ptr() if idx is not None else None
+            fold[k].ddof = ddof
         return {"n": n, "push": pushes, "fold": fold, "count": C.c_int64(global_count), "keep": (items, operand)}
 
     def run_prepared(self, plan) -> None:

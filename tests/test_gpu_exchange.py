@@ -28,7 +28,9 @@ def test_fused_exchange_simulated_ranks(world):
             start, count = mxd.slab(n, r, world, align=64)
             t = mx.make_tensor(dx[start:start + count])
             o = [torch.zeros((), device="cuda") for _ in range(4)] + [torch.zeros((), dtype=torch.int64, device="cuda")]
-            items = [(A.RED_SUM, o[0], None), (A.RED_MAX, o[1], None), (A.RED_ARGMAX, o[2], o[4]), (A.RED_MEAN, o[3], None)]
+            o += [torch.zeros((), device="cuda") for _ in range(2)]
+            items = [(A.RED_SUM, o[0], None), (A.RED_MAX, o[1], None), (A.RED_ARGMAX, o[2], o[4]), (A.RED_MEAN, o[3], None),
+                     (A.RED_VAR, o[5], None), (A.RED_STDD, o[6], None)]
             outs.append(o)
             plans.append((pes[r], pes[r].prepare(items, t, start, n)))
         # all ranks push, then all ranks fold (a real run interleaves freely; the counters make any order safe)
@@ -45,4 +47,42 @@ def test_fused_exchange_simulated_ranks(world):
             assert o[1].item() == x.max() and o[2].item() == x.max()
             assert o[4].item() == int(np.argmax(x))             # lowest GLOBAL index among ties
             assert abs(o[3].item() - truth / n) <= 1e-5 * truth / n
+            v = x.astype(np.float64).var(ddof=1)
+            assert abs(o[5].item() - v) <= 1e-5 * v and abs(o[6].item() - np.sqrt(v)) <= 1e-5 * np.sqrt(v)
         assert len({tuple(v.item() for v in o) for o in outs}) == 1   # every rank folded the same records in the same order
+
+
+@pytest.mark.parametrize("world", [1, 4])
+def test_partial_records_and_rank_order_fold(world):
+    """The collective-based form: mxb_reduce_partial per slab -> (here: one buffer instead of an all-gather) -> mxb_reduce_finalize."""
+    import ctypes as C
+    import torch
+    n = 200_000
+    rng = np.random.default_rng(10 + world)
+    ex = mx.CudaExecutor()
+    xr = (rng.standard_normal(n) * 3 + 7).astype(np.float32)
+    xc = (rng.standard_normal(n) + 1j * rng.standard_normal(n) + (2 - 1j)).astype(np.complex64)
+    for x, vdt, ops in ((xr, A.F32, [A.RED_SUM, A.RED_MEAN, A.RED_MIN, A.RED_ARGMIN, A.RED_ANY, A.RED_VAR, A.RED_STDD]),
+                        (xc, A.C64, [A.RED_SUM, A.RED_MEAN, A.RED_VAR])):
+        dx = torch.from_numpy(x).cuda()
+        for op in ops:
+            gathered = torch.zeros(world * 32, dtype=torch.uint8, device="cuda")
+            for r in range(world):
+                start, count = mxd.slab(n, r, world, align=64)
+                e = mx.lower_reduce(mx.ReduceExpr(op, mx.make_tensor(dx[start:start + count]), None))
+                A.check(A.lib.mxb_reduce_partial(ex.handle, op, C.byref(e), start, C.c_void_p(gathered.data_ptr() + 32 * r)))
+            real_out = op in (A.RED_VAR, A.RED_STDD, A.RED_ANY) or vdt == A.F32
+            out = torch.zeros((), dtype=torch.float32 if real_out and not (vdt == A.C64 and op in (A.RED_SUM, A.RED_MEAN)) else torch.complex64, device="cuda")
+            idx = torch.zeros((), dtype=torch.int64, device="cuda")
+            o = mx._out_desc(mx.make_tensor(out))
+            io = mx._out_desc(mx.make_tensor(idx))
+            A.check(A.lib.mxb_reduce_finalize(ex.handle, op, vdt, C.c_void_p(gathered.data_ptr()), world, 32, n, 1, C.byref(o),
+                                              C.byref(io) if op == A.RED_ARGMIN else None))
+            ex.sync()
+            x64 = x.astype(np.complex128 if vdt == A.C64 else np.float64)
+            want = {A.RED_SUM: x64.sum(), A.RED_MEAN: x64.mean(), A.RED_MIN: x.min() if vdt == A.F32 else 0, A.RED_ARGMIN: x.min() if vdt == A.F32 else 0,
+                    A.RED_ANY: 1.0, A.RED_VAR: x64.var(ddof=1), A.RED_STDD: x64.std(ddof=1)}[op]
+            got = out.item()
+            assert abs(got - want) <= 2e-5 * abs(want), (op, vdt, got, want)
+            if op == A.RED_ARGMIN:
+                assert idx.item() == int(np.argmin(x))
