@@ -300,3 +300,39 @@ def test_error_convention():
     with pytest.raises(A.MatxB200Error) as ei:
         out.set(mx.max(c, [1])).run(ex)   # the reference rejects ordering of complex too
     assert ei.value.status == A.ERR_NOT_SUPPORTED
+
+
+def test_broadcast_leaf_along_the_vector_dim(oracle):
+    """A leaf whose stride along the vector dim is 0 (clone / per-row scalar) takes the splat path of the loads."""
+    rng = np.random.default_rng(21)
+    a = (rng.random((64, 1024)) + 0.5).astype(np.float32)
+    rowv = (rng.random(64) + 0.5).astype(np.float32)       # one value per row, broadcast along the reduced dim
+    colv = (rng.random(1024) + 0.5).astype(np.float32)     # one value per column, broadcast along the batch dim
+    for op in ["sum", "max", "argmax", "var"]:
+        f = getattr(mx, op)
+        k = check(oracle, op, lambda x, r, c, f=f: f(x * mx.clone(r, [mx.matxKeepDim, 1024]) + c, [1]), [a, rowv, colv], A.F32, tol=2e-5)
+        assert "|V4" in k, k                               # still the vector kernel; only the row scalar is splat
+        k = check(oracle, op, lambda x, r, c, f=f: f(x * mx.clone(r, [mx.matxKeepDim, 1024]) + c, [0]), [a, rowv, colv], A.F32, tol=2e-5)
+        assert k.startswith("red_outer") or op == "var", k
+    got, want, k = G.run_elementwise(oracle, lambda x, r, c: x / mx.clone(r, [mx.matxKeepDim, 1024]) - c, [a, rowv, colv], a.shape, A.F32)
+    assert np.allclose(got, want, rtol=1e-6, atol=1e-6) and "|V4" in k, k
+
+
+def test_handles_are_independent_and_streams_respected(oracle):
+    import torch
+    rng = np.random.default_rng(22)
+    x = G.to_dev(rng.random((3, 1 << 20)).astype(np.float32))
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    e1, e2 = mx.CudaExecutor(s1), mx.CudaExecutor(s2)
+    outs = []
+    for ex_, st in ((e1, s1), (e2, s2)):
+        with torch.cuda.stream(st):
+            o = torch.zeros(3, device="cuda")
+            for _ in range(20):                              # grid-combine scratch of the two handles must not interfere
+                mx.make_tensor(o).set(mx.sum(mx.make_tensor(x), [1])).run(ex_)
+            outs.append(o)
+    e1.sync(); e2.sync()
+    truth = x.double().sum(1)
+    for o in outs:
+        assert ((o.double() - truth).abs() / truth).max().item() <= 1e-5
+    assert torch.equal(outs[0], outs[1])
