@@ -32,6 +32,7 @@
 
 #include <matx.h>
 
+#include <cstdio>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -243,6 +244,16 @@ template <class T> bool out_desc(const T &t, mxb_out_t &o) {
 inline bool check_or_fallback(int st) {
   if (st == MXB_OK) return false;
   if (st == MXB_ERR_NOT_SUPPORTED) return true;
+  if (st == MXB_ERR_JIT) {
+    // no ahead-of-time kernel for this expression and NVRTC is unavailable / failed: the statement is still valid
+    // MatX, so it runs on the reference path; say so once, the fallback is a performance cliff
+    static bool warned = false;
+    if (!warned) {
+      warned = true;
+      fprintf(stderr, "matx_b200: falling back to the reference kernels for expressions without an ahead-of-time kernel (%s)\n", mxb_last_error());
+    }
+    return true;
+  }
   const std::string msg = std::string("libmatx_b200: ") + mxb_last_error();
   if (st == MXB_ERR_SIZE) { MATX_THROW(matxInvalidSize, msg); }
   if (st == MXB_ERR_INVALID) { MATX_THROW(matxInvalidParameter, msg); }
