@@ -202,6 +202,7 @@ void aot_manifest(std::vector<ManifestItem> *items) {
     add(prog_identity(MXB_F64), FAM_VAR_TMA, MXB_RED_VAR, MXB_F64, ipt, false);
   }
   for (int ipt : {1, 2, 4, 8}) {
+    for (int d : {MXB_F32, MXB_C64}) add(prog_identity(d), FAM_VAR_GROUP, MXB_RED_VAR, MXB_F32, ipt, false);
     for (int d : {MXB_F32, MXB_C64}) add(prog_identity(d), FAM_VAR_REG, MXB_RED_VAR, MXB_F32, ipt, false);
     add(prog_identity(MXB_F64), FAM_VAR_REG, MXB_RED_VAR, MXB_F64, ipt, false);
   }

@@ -333,20 +333,29 @@ int reduce_launch(mxb_context *h, int kop, const mxb_expr_t &e, const ExprInfo &
   spec.op = kop;
   spec.out_dtype = out_dtype;
   int rot = -1;
-  int var_ipt = 0, var_threads = 0, tma_ctas = 1;
+  int var_ipt = 0, var_threads = 0, tma_ctas = 1, var_group_g = 0;
   if (var_smem) {
     spec.family = FAM_VAR_SMEM;
     spec.V = (vmax > 1 && inner_ok(vmax)) ? vmax : 1;
     // rows that fit in the registers of one CTA: blockDim.x * IPT vectors, single contiguous run, no ragged tail
     if (gr.n == 1 && inner_ok(spec.V) && gr.size[0] % spec.V == 0 && !getenv("MXB_VAR_SMEM_ONLY")) {
       const int64_t Lv = gr.size[0] / spec.V;
-      for (int thr : {32, 64, 128, 256, 512}) {
-        for (int ipt : {1, 2, 4, 8}) {
-          if (Lv <= (int64_t)thr * ipt && (thr >= 256 || ipt == 1)) { var_threads = thr; var_ipt = ipt; break; }
-        }
-        if (var_ipt) break;
+      if (Lv <= 256 && !getenv("MXB_VAR_NO_GROUP")) {
+        // short rows: G lanes of a warp per row, the row in registers, shuffles only
+        int G = 1;
+        while (G < 32 && G < Lv) G <<= 1;
+        int ipt = 1;
+        while ((int64_t)G * ipt < Lv) ipt <<= 1;
+        var_group_g = G;
+        var_ipt = ipt;
+      } else {
+        int thr = 64;
+        while (thr < 512 && (int64_t)thr * 8 < Lv) thr <<= 1;
+        int ipt = 1;
+        while ((int64_t)thr * ipt < Lv && ipt < 8) ipt <<= 1;
+        if ((int64_t)thr * ipt >= Lv) { var_threads = thr; var_ipt = ipt; }
       }
-      if (var_ipt) spec.family = FAM_VAR_REG;
+      if (var_ipt) spec.family = var_group_g ? FAM_VAR_GROUP : FAM_VAR_REG;
     }
     // plain tensor, long contiguous rows: TMA-staged ring of rows in shared memory (one HBM read, copy engine keeps
     // rows in flight while the SM runs the two passes)
@@ -370,6 +379,7 @@ int reduce_launch(mxb_context *h, int kop, const mxb_expr_t &e, const ExprInfo &
       if (env_int("MXB_TUNE_STAGES", 0) > 0 && env_int("MXB_TUNE_STAGES", 0) < stages) stages = env_int("MXB_TUNE_STAGES", 0);
       if (ok && stages >= 2) {
         spec.family = FAM_VAR_TMA;
+        var_group_g = 0;
         spec.V = policy_vmax(info);
         var_ipt = (int)stages;
         tma_ctas = (int)ctas;
@@ -392,7 +402,7 @@ int reduce_launch(mxb_context *h, int kop, const mxb_expr_t &e, const ExprInfo &
     spec.V = 1;
   }
   spec.U = policy_unroll(info, spec.V, spec.family);
-  if (spec.family == FAM_VAR_REG) spec.team = var_ipt;
+  if (spec.family == FAM_VAR_REG || spec.family == FAM_VAR_GROUP) spec.team = var_ipt;
   // development knobs (tools/sweep.py): override the unroll / launch shape; any combination is JIT-compiled on demand
   const int tune_u = env_int("MXB_TUNE_U", 0), tune_block = env_int("MXB_TUNE_BLOCK", 0), tune_cps = env_int("MXB_TUNE_CTAS_PER_SM", 0);
   const int tune_tx = env_int("MXB_TUNE_TX", 0);
@@ -477,6 +487,11 @@ int reduce_launch(mxb_context *h, int kop, const mxb_expr_t &e, const ExprInfo &
     block = (unsigned)tma_block;
     smem = (unsigned)(128 + (int64_t)var_ipt * rowstride);
     grid = (unsigned)std::min<int64_t>(B, (int64_t)sm * (tune_cps > 0 ? tune_cps : tma_ctas));
+  } else if (spec.family == FAM_VAR_GROUP) {
+    p.tx = var_group_g;
+    block = 256;
+    const int64_t rows_per_cta = (int64_t)(block / 32) * (32 / var_group_g);
+    grid = (unsigned)std::min<int64_t>((B + rows_per_cta - 1) / rows_per_cta, (int64_t)sm * (tune_cps > 0 ? tune_cps : 8));
   } else if (spec.family == FAM_VAR_REG) {
     block = (unsigned)var_threads;
     grid = (unsigned)std::min<int64_t>(B, (int64_t)sm * (tune_cps > 0 ? tune_cps : 32));
@@ -486,17 +501,19 @@ int reduce_launch(mxb_context *h, int kop, const mxb_expr_t &e, const ExprInfo &
     grid = (unsigned)std::min<int64_t>(B, (int64_t)sm * (tune_cps > 0 ? tune_cps : 16));
   } else if (spec.family == FAM_RED_INNER) {
     const int64_t row_bytes = R * info.max_leaf_bytes;
-    spec.team = (row_bytes >= 8192) ? 0 : 1;
+    spec.team = (row_bytes >= 16384) ? 0 : 1;   // rows under 16 KB: a warp (or a slice of one) per row, no barrier
     if (env_int("MXB_TUNE_TEAM", -1) >= 0) spec.team = env_int("MXB_TUNE_TEAM", -1);
-    // 8 CTAs of 256 threads per SM = two waves (the block scheduler evens out the tail) for big inputs; below ~8 MiB
-    // per SM one resident wave (4 CTAs/SM at 64 registers) has the smaller fixed cost (tools/small_sweep.py)
-    const int64_t bytes_per_sm = B * R * info.max_leaf_bytes * std::max(1, nl) / sm;
-    const int cps = tune_cps > 0 ? tune_cps : (bytes_per_sm < (8ll << 20) ? 4 : 8);
     if (spec.team == 0) {
       const int64_t L = gr.size[gr.n - 1];
       const int64_t Q = (R / L) * (L / spec.V);  // vector steps per row
       int64_t S = 1;
+      int cps = tune_cps > 0 ? tune_cps : 8;
       if (B < 2 * (int64_t)sm) {
+        // few long rows: `S` CTAs per row.  8 CTAs of 256 threads per SM = two waves (the block scheduler evens out the
+        // tail) for big inputs; below ~8 MiB per SM one resident wave (4 CTAs/SM at 64 registers) has the smaller fixed
+        // cost (tools/small_sweep.py)
+        const int64_t bytes_per_sm = B * R * info.max_leaf_bytes * std::max(1, nl) / sm;
+        if (tune_cps <= 0 && bytes_per_sm < (8ll << 20)) cps = 4;
         S = ((int64_t)sm * cps + B - 1) / B;
         const int64_t maxS = std::max<int64_t>(1, Q / ((int64_t)block * spec.U * 2));
         S = std::max<int64_t>(1, std::min(S, maxS));
@@ -510,8 +527,15 @@ int reduce_launch(mxb_context *h, int kop, const mxb_expr_t &e, const ExprInfo &
       }
       grid = (unsigned)std::min<int64_t>(B * S, (int64_t)sm * cps);
     } else {
-      const int64_t wpb = block / 32;
-      grid = (unsigned)std::min<int64_t>((B + wpb - 1) / wpb, (int64_t)sm * cps);
+      // G lanes per row: enough lanes for one vector step each, at most a warp; 32 / G rows share a warp
+      const int64_t L = gr.size[gr.n - 1];
+      const int64_t steps = (R / L) * std::max<int64_t>(1, (L + spec.V - 1) / spec.V);
+      int G = 1;
+      while (G < 32 && G < steps) G <<= 1;
+      if (env_int("MXB_TUNE_G", 0) > 0) G = env_int("MXB_TUNE_G", 0);
+      p.tx = G;
+      const int64_t rows_per_cta = (int64_t)(block / 32) * (32 / G);
+      grid = (unsigned)std::min<int64_t>((B + rows_per_cta - 1) / rows_per_cta, (int64_t)sm * (tune_cps > 0 ? tune_cps : 8));
     }
   } else {  // FAM_RED_OUTER
     const int64_t C = p.bsz[p.nb - 1];
@@ -523,8 +547,24 @@ int reduce_launch(mxb_context *h, int kop, const mxb_expr_t &e, const ExprInfo &
     const int ty = (int)block / tx;
     smem = ty > 1 ? (unsigned)(ty * tx * spec.V * acc_bytes(kop, info.value_dtype)) : 0;
     const int64_t tile = (int64_t)tx * spec.V;
-    const int64_t work = (B / C) * ((C + tile - 1) / tile);
-    grid = (unsigned)std::min<int64_t>(work, (int64_t)sm * (tune_cps > 0 ? tune_cps : 8));
+    const int64_t tiles = (B / C) * ((C + tile - 1) / tile);
+    // few output tiles, long reduce dim (column sums of a tall matrix): several CTAs per tile + in-launch combine
+    int64_t S = 1;
+    const int cps = tune_cps > 0 ? tune_cps : 8;
+    if (tiles < 2 * (int64_t)sm) {
+      S = ((int64_t)sm * cps + tiles - 1) / tiles;
+      const int64_t maxS = std::max<int64_t>(1, R / ((int64_t)ty * spec.U * 4));
+      S = std::max<int64_t>(1, std::min(S, maxS));
+      if (env_int("MXB_TUNE_SPLITS", 0) > 0) S = env_int("MXB_TUNE_SPLITS", 0);
+    }
+    p.splits = (int)S;
+    if (S > 1) {
+      int st = ensure_ws(h, (size_t)(tiles * S * tile) * (size_t)acc_bytes(kop, info.value_dtype), (size_t)tiles);
+      if (st != MXB_OK) return st;
+      p.ws = h->ws;
+      p.tickets = h->tickets;
+    }
+    grid = (unsigned)std::min<int64_t>(tiles * S, (int64_t)sm * cps);
   }
 
   Kernel k;

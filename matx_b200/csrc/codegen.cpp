@@ -338,7 +338,7 @@ int policy_vmax(const ExprInfo &info) {
 int policy_unroll(const ExprInfo &info, int V, int family) {
   const int bytes = V * info.max_leaf_bytes;  // widest load of one step
   if (family == FAM_RED_OUTER) return 4;
-  if (family == FAM_VAR_REG || family == FAM_VAR_TMA) return 1;
+  if (family == FAM_VAR_REG || family == FAM_VAR_TMA || family == FAM_VAR_GROUP) return 1;
   if (family == FAM_VAR_SMEM) return bytes >= 32 ? 4 : 8;
   if (family == FAM_EW) return bytes >= 32 ? (info.nleaf <= 2 ? 2 : 1) : (info.nleaf <= 2 ? 4 : 2);
   return bytes >= 32 ? 2 : (info.nleaf <= 2 ? 4 : 2);
@@ -346,7 +346,7 @@ int policy_unroll(const ExprInfo &info, int V, int family) {
 
 std::string kernel_key(const ExprInfo &info, const KernelSpec &s) {
   std::ostringstream k;
-  static const char *fam[] = {"red_inner", "red_outer", "var_smem", "ew", "var_reg", "var_tma"};
+  static const char *fam[] = {"red_inner", "red_outer", "var_smem", "ew", "var_reg", "var_tma", "var_group"};
   k << fam[s.family] << "|" << info.name << "|" << (s.op >= 0 ? reduce_op_name(s.op) : "-") << "|" << dtype_name(s.out_dtype)
     << "|V" << s.V << "|U" << s.U << "|T" << s.team;
   return k.str();
@@ -400,6 +400,11 @@ int kernel_wrapper_src(const ExprInfo &info, const KernelSpec &s, const std::str
       if (!(info.value_dtype == MXB_F32 || info.value_dtype == MXB_F64 || cplx)) return fail("var of a non-floating expression");
       k << "extern \"C\" __global__ void __launch_bounds__(512) " << symbol
         << "(const __grid_constant__ mxb::RedParams p) { mxb::var_inner_reg_body<" << E << ", " << O << ", " << s.V << ", " << s.team << ">(p); }\n";
+      break;
+    case FAM_VAR_GROUP:
+      if (!(info.value_dtype == MXB_F32 || info.value_dtype == MXB_F64 || cplx)) return fail("var of a non-floating expression");
+      k << "extern \"C\" __global__ void __launch_bounds__(256) " << symbol
+        << "(const __grid_constant__ mxb::RedParams p) { mxb::var_group_body<" << E << ", " << O << ", " << s.V << ", " << s.team << ">(p); }\n";
       break;
     case FAM_VAR_TMA:
       if (info.nleaf != 1) return fail("var_tma serves plain tensors only");

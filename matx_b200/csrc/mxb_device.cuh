@@ -668,6 +668,16 @@ template <class Op> __device__ __forceinline__ typename Op::acc_t cta_merge(type
   return a;
 }
 
+// merge across the G lanes (power of two) that share a row; G == 32 takes the op's redux / vote path
+template <class Op> __device__ __forceinline__ typename Op::acc_t group_merge(typename Op::acc_t a, int G) {
+  if (G == 32) return Op::warp(a);
+  for (int m = G >> 1; m > 0; m >>= 1) {
+    typename Op::acc_t o = shfl_xor_t(a, m);
+    Op::merge(a, o);
+  }
+  return a;
+}
+
 // per-leaf byte offset of an outer (non-innermost) reduce index
 template <class E>
 __device__ __forceinline__ void outer_bases(const RedParams &p, i64 o, const char *const *base, const char **rb) {
@@ -699,10 +709,15 @@ __device__ __forceinline__ void reduce_inner_body_impl(const RedParams &p) {
   __shared__ acc_t s_acc[32];
   __shared__ int s_last;
 
-  const int nthr = TEAM == 0 ? (int)blockDim.x : 32;
-  const int tid = TEAM == 0 ? (int)threadIdx.x : (int)(threadIdx.x & 31);
-  const i64 team0 = TEAM == 0 ? (i64)blockIdx.x : (i64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const i64 nteam = TEAM == 0 ? (i64)gridDim.x : (i64)gridDim.x * (blockDim.x >> 5);
+  // TEAM == 1: G lanes per row (G = p.tx, a power of two <= 32), 32 / G rows per warp; the row loop is warp-uniform
+  // (groups past the last row redo the last row and skip the store) so the full-mask shuffles stay legal
+  const int G = TEAM == 0 ? (int)blockDim.x : p.tx;
+  const int nthr = G;
+  const int tid = TEAM == 0 ? (int)threadIdx.x : (int)(threadIdx.x & (G - 1));
+  const int gid = TEAM == 0 ? 0 : (int)((threadIdx.x & 31) / G);
+  const int gpw = TEAM == 0 ? 1 : 32 / G;
+  const i64 wb0 = TEAM == 0 ? (i64)blockIdx.x : ((i64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * gpw;
+  const i64 wstep = TEAM == 0 ? (i64)gridDim.x : (i64)gridDim.x * (blockDim.x >> 5) * gpw;
   const int nr = p.nr;
   const i64 L = p.rsz[nr - 1];  // innermost run
   const i64 Lv = L / V;         // full vectors per run
@@ -711,7 +726,10 @@ __device__ __forceinline__ void reduce_inner_body_impl(const RedParams &p) {
   const i64 S = TEAM == 0 ? (i64)p.splits : 1;
   const i64 work = p.B * S;
 
-  for (i64 w = team0; w < work; w += nteam) {
+  for (i64 wb = wb0; wb < work; wb += wstep) {
+    i64 w = wb + gid;
+    const bool valid = w < work;
+    if (!valid) w = work - 1;
     const i64 b = w / S;
     const i64 s = w - b * S;
     const char *base[E::NL];
@@ -799,11 +817,11 @@ __device__ __forceinline__ void reduce_inner_body_impl(const RedParams &p) {
     for (int v = 1; v < V; ++v) Op::merge(acc[0], acc[v]);
     // streaming part of this CTA's last work item is over: let the next kernel on the stream start launching while
     // the warp / CTA / grid stages finish (it still waits for this grid to complete before touching memory)
-    if (w + nteam >= work) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (wb + wstep >= work) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     if (TEAM == 1) {
-      acc_t tot = Op::warp(acc[0]);
-      if (tid == 0) store_result<Op, OutT>(p, b, tot);
+      acc_t tot = group_merge<Op>(acc[0], G);
+      if (tid == 0 && valid) store_result<Op, OutT>(p, b, tot);
     } else {
       acc_t tot = cta_merge<Op>(acc[0], s_acc);
       if (S == 1) {
@@ -843,6 +861,7 @@ __device__ __forceinline__ void reduce_outer_body_impl(const RedParams &p) {
   typedef typename Op::acc_t acc_t;
   extern __shared__ __align__(16) unsigned char s_dyn[];
   acc_t *s_part = (acc_t *)s_dyn;  // [TY][TX*V]
+  __shared__ int s_last;
 
   const int TX = p.tx, TY = (int)blockDim.x / TX;
   const int tx = (int)threadIdx.x % TX, ty = (int)threadIdx.x / TX;
@@ -851,10 +870,15 @@ __device__ __forceinline__ void reduce_outer_body_impl(const RedParams &p) {
   const i64 tile = (i64)TX * V;                // columns per CTA
   const i64 ctiles = (C + tile - 1) / tile;
   const i64 Bo = p.B / C;                      // product of the other batch dims
-  const i64 work = Bo * ctiles;
+  // few output tiles and a long reduce dim (column sums of a tall matrix): `splits` CTAs share a tile, each walks the
+  // reduce index with stride splits * TY, and the last CTA to finish folds the partial vectors in split order
+  const i64 S = p.splits;
+  const i64 RS = S * TY;                       // stride of one lane through the reduce index
+  const i64 work = Bo * ctiles * S;
 
   for (i64 w = blockIdx.x; w < work; w += gridDim.x) {
-    const i64 bo = w / ctiles, ct = w - bo * ctiles;
+    const i64 tile_id = w / S, s = w - tile_id * S;
+    const i64 bo = tile_id / ctiles, ct = tile_id - bo * ctiles;
     const i64 c0 = ct * tile + (i64)tx * V;    // first column of this thread
     const bool active = c0 < C;
     const bool fullvec = c0 + V <= C;
@@ -883,18 +907,18 @@ __device__ __forceinline__ void reduce_outer_body_impl(const RedParams &p) {
 
     if (active) {
       if (fullvec) {
-        i64 r = ty;
-        for (; r + (i64)(U - 1) * TY < p.R; r += (i64)U * TY) {
+        i64 r = s * TY + ty;
+        for (; r + (i64)(U - 1) * RS < p.R; r += (i64)U * RS) {
           typename E::template Regs<V> reg[U];
 #pragma unroll
           for (int u = 0; u < U; ++u) {
             const char *rb[E::NL];
             if (nr == 1) {
 #pragma unroll
-              for (int k = 0; k < E::NL; ++k) rb[k] = base[k] + (r + (i64)u * TY) * p.leaf[k].rs[0] * E::leaf_bytes(k);
+              for (int k = 0; k < E::NL; ++k) rb[k] = base[k] + (r + (i64)u * RS) * p.leaf[k].rs[0] * E::leaf_bytes(k);
             } else {
               i64 ridx[KMAXD];
-              decomp(r + (i64)u * TY, nr, p.rsz, ridx);
+              decomp(r + (i64)u * RS, nr, p.rsz, ridx);
 #pragma unroll
               for (int k = 0; k < E::NL; ++k) {
                 i64 off = 0;
@@ -909,10 +933,10 @@ __device__ __forceinline__ void reduce_outer_body_impl(const RedParams &p) {
           for (int u = 0; u < U; ++u) {
 #pragma unroll
             for (int v = 0; v < V; ++v)
-              Op::step(acc[v], E::template eval<V>(reg[u], v, p.c), rowflat + (i64)v * colflat + r + (i64)u * TY);
+              Op::step(acc[v], E::template eval<V>(reg[u], v, p.c), rowflat + (i64)v * colflat + r + (i64)u * RS);
           }
         }
-        for (; r < p.R; r += TY) {
+        for (; r < p.R; r += RS) {
           const char *rb[E::NL];
           i64 ridx[KMAXD];
           decomp(r, nr, p.rsz, ridx);
@@ -930,7 +954,7 @@ __device__ __forceinline__ void reduce_outer_body_impl(const RedParams &p) {
         }
       } else {
         // ragged last vector of the column dim: scalar lanes
-        for (i64 r = ty; r < p.R; r += TY) {
+        for (i64 r = s * TY + ty; r < p.R; r += RS) {
           const char *rb[E::NL];
           i64 ridx[KMAXD];
           decomp(r, nr, p.rsz, ridx);
@@ -967,10 +991,39 @@ __device__ __forceinline__ void reduce_outer_body_impl(const RedParams &p) {
         }
       }
     }
-    if (ty == 0 && active) {
+    if (S == 1) {
+      if (ty == 0 && active) {
 #pragma unroll
-      for (int v = 0; v < V; ++v)
-        if (c0 + v < C) store_result<Op, OutT>(p, bo * C + c0 + v, acc[v]);
+        for (int v = 0; v < V; ++v)
+          if (c0 + v < C) store_result<Op, OutT>(p, bo * C + c0 + v, acc[v]);
+      }
+    } else {
+      acc_t *ws = (acc_t *)p.ws + (size_t)tile_id * S * tile;
+      if (ty == 0) {
+#pragma unroll
+        for (int v = 0; v < V; ++v) st_cg_t(&ws[(size_t)s * tile + (size_t)tx * V + v], acc[v]);
+      }
+      __threadfence();
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        const u32 t = atomicInc(&p.tickets[tile_id], (u32)(S - 1));
+        s_last = (t == (u32)(S - 1));
+      }
+      __syncthreads();
+      if (s_last) {
+        __threadfence();
+        if (ty == 0 && active) {
+#pragma unroll
+          for (int v = 0; v < V; ++v) {
+            if (c0 + v < C) {
+              acc_t a = Op::init();
+              for (i64 s2 = 0; s2 < S; ++s2) Op::merge(a, ld_cg_t(&ws[(size_t)s2 * tile + (size_t)tx * V + v]));
+              store_result<Op, OutT>(p, bo * C + c0 + v, a);
+            }
+          }
+        }
+      }
+      __syncthreads();  // s_last is reused by the next work item
     }
   }
 }
@@ -1175,6 +1228,73 @@ __device__ __forceinline__ void var_inner_reg_body_impl(const RedParams &p) {
       ((OutT *)p.out.ptr)[oo] = cvt<OutT>(res);
     }
     __syncthreads();  // s_mean is reused by the next row
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3g: var_group — the exact two-pass variance for SHORT rows (<= 32 * IPT vectors): G lanes of a warp share a row
+// (G = p.tx), 32 / G rows per warp, the row lives in registers, both reductions are shuffles inside the group; no
+// shared memory, no barrier.  One HBM read.
+// ------------------------------------------------------------------------------------------------
+template <class E, class OutT, int V, int IPT, bool UNIT>
+__device__ __forceinline__ void var_group_body_impl(const RedParams &p) {
+  typedef typename E::value_type T;
+  typedef typename AbsDev2<T>::real_t RT;
+  const int G = p.tx, gpw = 32 / G;
+  const int tid = (int)(threadIdx.x & (G - 1)), gid = (int)((threadIdx.x & 31) / G);
+  const i64 wb0 = ((i64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * gpw;
+  const i64 wstep = (i64)gridDim.x * (blockDim.x >> 5) * gpw;
+  const i64 Lv = p.rsz[0] / V;
+  for (i64 wb = wb0; wb < p.B; wb += wstep) {
+    i64 b = wb + gid;
+    const bool valid = b < p.B;
+    if (!valid) b = p.B - 1;
+    const char *base[E::NL];
+    i64 inner[E::NL];
+    i64 bidx[KMAXD];
+    decomp(b, p.nb, p.bsz, bidx);
+#pragma unroll
+    for (int k = 0; k < E::NL; ++k) {
+      i64 off = 0;
+#pragma unroll
+      for (int d = 0; d < KMAXD; ++d) if (d < p.nb) off += bidx[d] * p.leaf[k].bs[d];
+      base[k] = (const char *)p.leaf[k].ptr + off * E::leaf_bytes(k);
+      inner[k] = p.leaf[k].rs[0];
+    }
+    typename E::template Regs<V> r[IPT];
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) {
+      const i64 q = tid + (i64)i * G;
+      if (q < Lv) E::template loadv<V, UNIT>(r[i], base, inner, q * V);
+    }
+    Vec<T, V> x[IPT];
+    T acc = OpSum<T>::init();
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) {
+      if (tid + (i64)i * G < Lv) {
+#pragma unroll
+        for (int v = 0; v < V; ++v) { x[i].v[v] = E::template eval<V>(r[i], v, p.c); acc = acc + x[i].v[v]; }
+      }
+    }
+    for (int m = G >> 1; m > 0; m >>= 1) acc = acc + shfl_xor_t(acc, m);
+    const T mean = MeanDiv<T>::go(acc, p.R);
+    RT sq = (RT)0;
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) {
+      if (tid + (i64)i * G < Lv) {
+#pragma unroll
+        for (int v = 0; v < V; ++v) sq += AbsDev2<T>::go(x[i].v[v], mean);
+      }
+    }
+    for (int m = G >> 1; m > 0; m >>= 1) sq += shfl_xor_t(sq, m);
+    if (tid == 0 && valid) {
+      RT res = sq / (RT)p.post_scale_d;
+      if (p.post_sqrt) res = f_sqrt(res);
+      i64 oo = 0;
+#pragma unroll
+      for (int d = 0; d < KMAXD; ++d) if (d < p.nb) oo += bidx[d] * p.out.bs[d];
+      ((OutT *)p.out.ptr)[oo] = cvt<OutT>(res);
+    }
   }
 }
 
@@ -1448,6 +1568,13 @@ __device__ __forceinline__ void var_inner_reg_body(const RedParams &p) {
   pdl_prologue();
   if (p.all_unit) var_inner_reg_body_impl<E, OutT, V, IPT, true>(p);
   else var_inner_reg_body_impl<E, OutT, V, IPT, false>(p);
+}
+
+template <class E, class OutT, int V, int IPT>
+__device__ __forceinline__ void var_group_body(const RedParams &p) {
+  pdl_prologue();
+  if (p.all_unit) var_group_body_impl<E, OutT, V, IPT, true>(p);
+  else var_group_body_impl<E, OutT, V, IPT, false>(p);
 }
 
 }  // namespace mxb

@@ -236,9 +236,14 @@ def test_complex_rows_config3_shape(oracle):
     assert np.max(np.abs(got - want)) <= 1e-5 * np.mean(np.abs(x)), k   # norm-wise bound: the mean itself is ~0
     k = check(oracle, "var", lambda t: mx.var(t, [1], 1), [x], A.F32, tol=2e-5)
     assert k.startswith("var_tma"), k   # rows of 64 KB: TMA-staged ring in shared memory
-    x2 = x[:, :1024].copy()             # rows of 8 KB: register-resident kernel
+    x2 = x[:, :1024].copy()             # rows of 8 KB: a warp per row, row in registers
     k = check(oracle, "var", lambda t: mx.var(t, [1], 1), [x2], A.F32, tol=2e-5)
+    assert k.startswith("var_group"), k
+    k = check(oracle, "var", lambda t: mx.var(t * 2.0, [1], 1), [x], A.F32, tol=2e-5)   # fused expression, 64 KB rows: CTA per row, registers
     assert k.startswith("var_reg"), k
+    x3 = x[:, :48].copy()               # 48 complex per row: 12 vectors -> 16 lanes per row, 2 rows per warp
+    k = check(oracle, "stdd", lambda t: mx.stdd(t, [1], 0), [x3], A.F32, tol=2e-5)
+    assert k.startswith("var_group"), k
     got, gi, want, wi, k = G.run_reduce(oracle, lambda t: mx.argmax(mx.abs2(t), [1]), [x], A.F32)
     # abs2 contracts to an FMA on the device: values may differ in the last bit, the winner may not
     assert np.array_equal(gi, wi) and G.rel_err(got, want) < 1e-6, k
@@ -336,3 +341,32 @@ def test_handles_are_independent_and_streams_respected(oracle):
     for o in outs:
         assert ((o.double() - truth).abs() / truth).max().item() <= 1e-5
     assert torch.equal(outs[0], outs[1])
+
+
+@pytest.mark.parametrize("cols", [1, 2, 3, 4, 7, 8, 20, 64, 100, 1000])
+def test_short_rows_share_a_warp(oracle, cols):
+    """Rows shorter than a warp's worth of vectors: G lanes per row, 32/G rows per warp (ragged last warp included)."""
+    rng = np.random.default_rng(30 + cols)
+    rows = 1237                                            # not a multiple of any rows-per-warp
+    x = data(rng, (rows, cols), A.F32, ties=True)
+    for op in ["sum", "max", "argmax", "argmin", "any", "all"]:
+        check(oracle, op, lambda t, op=op: getattr(mx, op)(t, [1]), [x], A.F32)
+    y = data(rng, (rows, cols), A.F32) + np.float32(0.5)
+    check(oracle, "mean", lambda t: mx.mean(t, [1]), [y], A.F32)
+    if cols >= 2:
+        check(oracle, "var", lambda t: mx.var(t, [1], 1), [y], A.F32, tol=2e-5)
+
+
+@pytest.mark.parametrize("shape", [(200_000, 8), (50_000, 33), (30_000, 128), (3_000, 1000)])
+def test_column_reductions_of_tall_matrices(oracle, shape):
+    """Few output tiles, long strided reduce dim: several CTAs per tile with the in-launch combine (reduce_outer splits)."""
+    rng = np.random.default_rng(40 + shape[1])
+    x = data(rng, shape, A.F32, ties=True)
+    for op in ["max", "argmax", "argmin", "all"]:
+        k = check(oracle, op, lambda t, op=op: getattr(mx, op)(t, [0]), [x], A.F32)
+    assert k.startswith("red_outer"), k
+    y = (data(rng, shape, A.F32) + np.float32(0.5))
+    got, _, want, _, k = G.run_reduce(oracle, lambda t: mx.sum(t, [0]), [y], A.F32)
+    truth = y.astype(np.float64).sum(0)
+    assert np.max(np.abs(got - truth) / truth) <= 1e-5, k   # the sequential fp32 oracle is the less accurate side here
+    assert np.max(np.abs(want - truth) / truth) <= 5e-3

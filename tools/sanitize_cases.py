@@ -38,7 +38,11 @@ seen = set()
 for f in (mx.sum, mx.max, mx.argmax, mx.argmin, mx.any, mx.all, mx.prod):
     for src, dims in ((x, [1]), (x, [0]), (y, [1]), (y, [0]), (big, None), (t3, [0, 2]), (t3, [1])):
         seen.add(red(f(src, dims), idx=f in (mx.argmax, mx.argmin)).split("|")[0])
-seen.add(red(mx.var(y, [1])).split("|")[0])                                 # var_reg (short rows)
+seen.add(red(mx.var(y, [1])).split("|")[0])                                 # var_group (short rows)
+seen.add(red(mx.var(x * 2.0, [1])).split("|")[0])                           # var_reg (fused expression)
+tall = mx.make_tensor(dev(rng.random((100_000, 24), dtype=np.float32)))   # reduce_outer with splits
+for f in (mx.sum, mx.argmax):
+    seen.add(red(f(tall, [0]), idx=f is mx.argmax).split("|")[0])
 seen.add(red(mx.var(x, [1])).split("|")[0])                                 # var_tma (16 KB rows)
 seen.add(red(mx.var(c, [1])).split("|")[0])                                 # var_tma
 os.environ["MXB_VAR_SMEM_ONLY"] = "1"
