@@ -349,8 +349,9 @@ int reduce_launch(mxb_context *h, int kop, const mxb_expr_t &e, const ExprInfo &
         var_group_g = G;
         var_ipt = ipt;
       } else {
+        const int vpt = env_int("MXB_TUNE_VAR_VPT", 4);   // vectors per thread the CTA size is chosen for
         int thr = 64;
-        while (thr < 512 && (int64_t)thr * 8 < Lv) thr <<= 1;
+        while (thr < 512 && (int64_t)thr * vpt < Lv) thr <<= 1;
         int ipt = 1;
         while ((int64_t)thr * ipt < Lv && ipt < 8) ipt <<= 1;
         if ((int64_t)thr * ipt >= Lv) { var_threads = thr; var_ipt = ipt; }
@@ -501,7 +502,8 @@ int reduce_launch(mxb_context *h, int kop, const mxb_expr_t &e, const ExprInfo &
     grid = (unsigned)std::min<int64_t>(B, (int64_t)sm * (tune_cps > 0 ? tune_cps : 16));
   } else if (spec.family == FAM_RED_INNER) {
     const int64_t row_bytes = R * info.max_leaf_bytes;
-    spec.team = (row_bytes >= 16384) ? 0 : 1;   // rows under 16 KB: a warp (or a slice of one) per row, no barrier
+    // rows under 32 KB: a warp (or a slice of one) per row, no barrier (tools/shape_sweep.py)
+    spec.team = (row_bytes >= env_int("MXB_TUNE_T1_BYTES", 32768)) ? 0 : 1;
     if (env_int("MXB_TUNE_TEAM", -1) >= 0) spec.team = env_int("MXB_TUNE_TEAM", -1);
     if (spec.team == 0) {
       const int64_t L = gr.size[gr.n - 1];
@@ -530,8 +532,11 @@ int reduce_launch(mxb_context *h, int kop, const mxb_expr_t &e, const ExprInfo &
       // G lanes per row: enough lanes for one vector step each, at most a warp; 32 / G rows share a warp
       const int64_t L = gr.size[gr.n - 1];
       const int64_t steps = (R / L) * std::max<int64_t>(1, (L + spec.V - 1) / spec.V);
+      // up to `spl` vector steps per lane: adjacent lanes still read adjacent rows' bytes, and fewer lanes per row
+      // means fewer shuffle rounds and more rows per warp
+      const int spl = env_int("MXB_TUNE_STEPS_PER_LANE", 4);
       int G = 1;
-      while (G < 32 && G < steps) G <<= 1;
+      while (G < 32 && (int64_t)G * spl < steps) G <<= 1;
       if (env_int("MXB_TUNE_G", 0) > 0) G = env_int("MXB_TUNE_G", 0);
       p.tx = G;
       const int64_t rows_per_cta = (int64_t)(block / 32) * (32 / G);

@@ -592,6 +592,12 @@ __device__ __forceinline__ void push_record(const PeerPush &pp, const PartialRec
 
 // flat index -> per-dim indices (row-major over n dims of sizes sz[])
 __device__ __forceinline__ void decomp(i64 flat, int n, const i64 *sz, i64 *idx) {
+  if (n <= 1) {  // the common case (one collapsed dim): no division at all
+    idx[0] = flat;
+#pragma unroll
+    for (int d = 1; d < KMAXD; ++d) idx[d] = 0;
+    return;
+  }
 #pragma unroll
   for (int d = KMAXD - 1; d >= 0; --d) {
     if (d < n) {
@@ -616,11 +622,18 @@ __device__ __forceinline__ void store_result(const RedParams &p, i64 b, typename
     return;
   }
   i64 bidx[KMAXD];
-  decomp(b, p.nb, p.bsz, bidx);
   i64 oo = 0, io = 0;
+  if (p.nb == 1) {
+    bidx[0] = b;
+    bidx[1] = bidx[2] = bidx[3] = 0;
+    oo = b * p.out.bs[0];
+    io = b * p.idx.bs[0];
+  } else {
+    decomp(b, p.nb, p.bsz, bidx);
 #pragma unroll
-  for (int d = 0; d < KMAXD; ++d) {
-    if (d < p.nb) { oo += bidx[d] * p.out.bs[d]; io += bidx[d] * p.idx.bs[d]; }
+    for (int d = 0; d < KMAXD; ++d) {
+      if (d < p.nb) { oo += bidx[d] * p.out.bs[d]; io += bidx[d] * p.idx.bs[d]; }
+    }
   }
   typename Op::result_t r = Post<typename Op::result_t>::go(Op::finish(acc), p);
   ((OutT *)p.out.ptr)[oo] = cvt<OutT>(r);
@@ -735,7 +748,14 @@ __device__ __forceinline__ void reduce_inner_body_impl(const RedParams &p) {
     const char *base[E::NL];
     i64 inner[E::NL];
     i64 row0 = p.idx_base;  // flat index of the row's first element
-    {
+    if (p.nb == 1) {
+#pragma unroll
+      for (int k = 0; k < E::NL; ++k) {
+        base[k] = (const char *)p.leaf[k].ptr + b * p.leaf[k].bs[0] * E::leaf_bytes(k);
+        inner[k] = p.leaf[k].rs[nr - 1];
+      }
+      if (Op::HAS_INDEX) row0 += b * p.bflat[0] * p.R;
+    } else {
       i64 bidx[KMAXD];
       decomp(b, p.nb, p.bsz, bidx);
 #pragma unroll

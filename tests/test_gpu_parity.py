@@ -174,7 +174,10 @@ def test_kernel_families_are_selected(oracle):
     rng = np.random.default_rng(8)
     x = data(rng, (64, 4096), A.F32)
     k = check(oracle, "sum", lambda t: mx.sum(t, [1]), [x], A.F32)
-    assert k.startswith("red_inner") and "|T0" in k and "|V4" in k and k.endswith("aot"), k
+    assert k.startswith("red_inner") and "|T1" in k and "|V4" in k and k.endswith("aot"), k   # 16 KB rows: a warp per row
+    x = data(rng, (16, 16384), A.F32)
+    k = check(oracle, "sum", lambda t: mx.sum(t, [1]), [x], A.F32)
+    assert k.startswith("red_inner") and "|T0" in k, k                                          # 64 KB rows: a CTA per row
     x = data(rng, (512, 256), A.F32)
     k = check(oracle, "sum", lambda t: mx.sum(t, [1]), [x], A.F32)
     assert k.startswith("red_inner") and "|T1" in k, k
@@ -315,9 +318,9 @@ def test_broadcast_leaf_along_the_vector_dim(oracle):
     colv = (rng.random(1024) + 0.5).astype(np.float32)     # one value per column, broadcast along the batch dim
     for op in ["sum", "max", "argmax", "var"]:
         f = getattr(mx, op)
-        k = check(oracle, op, lambda x, r, c, f=f: f(x * mx.clone(r, [mx.matxKeepDim, 1024]) + c, [1]), [a, rowv, colv], A.F32, tol=2e-5)
+        k = check(oracle, op, lambda x, r, c, f=f: f((x + c) * mx.clone(r, [mx.matxKeepDim, 1024]), [1]), [a, rowv, colv], A.F32, tol=2e-5)
         assert "|V4" in k, k                               # still the vector kernel; only the row scalar is splat
-        k = check(oracle, op, lambda x, r, c, f=f: f(x * mx.clone(r, [mx.matxKeepDim, 1024]) + c, [0]), [a, rowv, colv], A.F32, tol=2e-5)
+        k = check(oracle, op, lambda x, r, c, f=f: f((x + c) * mx.clone(r, [mx.matxKeepDim, 1024]), [0]), [a, rowv, colv], A.F32, tol=2e-5)
         assert k.startswith("red_outer") or op == "var", k
     got, want, k = G.run_elementwise(oracle, lambda x, r, c: x / mx.clone(r, [mx.matxKeepDim, 1024]) - c, [a, rowv, colv], a.shape, A.F32)
     assert np.allclose(got, want, rtol=1e-6, atol=1e-6) and "|V4" in k, k
