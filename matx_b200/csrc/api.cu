@@ -502,8 +502,12 @@ int reduce_launch(mxb_context *h, int kop, const mxb_expr_t &e, const ExprInfo &
     grid = (unsigned)std::min<int64_t>(B, (int64_t)sm * (tune_cps > 0 ? tune_cps : 16));
   } else if (spec.family == FAM_RED_INNER) {
     const int64_t row_bytes = R * info.max_leaf_bytes;
-    // rows under 32 KB: a warp (or a slice of one) per row, no barrier (tools/shape_sweep.py)
-    spec.team = (row_bytes >= env_int("MXB_TUNE_T1_BYTES", 32768)) ? 0 : 1;
+    // rows under 32 KB (arg ops, whose CTA stage is the expensive one: under 128 KB): a warp — or a slice of one —
+    // per row, no shared memory, no barrier; longer rows: a CTA, or several, per row (tools/shape_sweep*.py)
+    const bool arg_op = (kop == MXB_RED_ARGMAX || kop == MXB_RED_ARGMIN);
+    const int64_t t1_limit = env_int("MXB_TUNE_T1_BYTES", arg_op ? 131072 : 32768);
+    spec.team = (row_bytes >= t1_limit || B < 8 * (int64_t)sm) ? 0 : 1;
+    if (row_bytes < 4096) spec.team = 1;   // short rows never want a whole CTA
     if (env_int("MXB_TUNE_TEAM", -1) >= 0) spec.team = env_int("MXB_TUNE_TEAM", -1);
     if (spec.team == 0) {
       const int64_t L = gr.size[gr.n - 1];
