@@ -16,6 +16,7 @@
  *                                                             1170-1178,1243-1251,1406-1444,1474-1479
  *                       + matxCubPlan_t::Exec{Sum,Min,Max,Reduce,ArgReduce}
  *                                                             include/matx/transforms/cub.h:647-894,1281-1328
+ *   mxb_softmax      <- softmax_impl (both overloads)         include/matx/transforms/reduce.h:362-445
  *   mxb_create / mxb_destroy / mxb_set_stream
  *                    <- cudaExecutor ctor / getStream         include/matx/executors/cuda.h:60-82
  *   mxb_sync         <- CudaExecutorBase::sync                include/matx/executors/cuda_executor_common.h:137
@@ -170,6 +171,14 @@ int mxb_elementwise(mxb_handle_t h, const mxb_expr_t *expr, const mxb_out_t *out
  * One launch per call (VAR/STDD: one launch when a reduced row fits in shared memory). */
 int mxb_reduce(mxb_handle_t h, int reduce_op, const mxb_expr_t *expr, int n_reduce_dims,
                const mxb_out_t *out, const mxb_out_t *idx_out, int ddof);
+
+/* out(b..., r...) = exp(x(b..., r...) - max_r x(b..., :)) / sum_r exp(x(b..., :) - max_r x(b..., :)) over the trailing
+ * `n_reduce_dims` dims of `expr` (1 <= n_reduce_dims <= rank; the caller permutes the softmax axes innermost in BOTH
+ * `expr` and `out`, which have the same rank and sizes) — the arithmetic of the reference's softmax_impl
+ * (transforms/reduce.h:362-445: max_impl, sum_impl(exp(in - max)), then the divide; three passes, two temporaries and
+ * five launches there).  Real floating expressions only.  One launch with one read and one write when a row fits in
+ * the registers of a CTA (<= 64 KB of fp32), otherwise a one-pass statistics launch + one elementwise launch. */
+int mxb_softmax(mxb_handle_t h, const mxb_expr_t *expr, int n_reduce_dims, const mxb_out_t *out);
 
 /* ---- multi-GPU (no counterpart in the reference) -------------------------------- */
 /* Slab-sharded full-tensor reductions: each rank reduces its slab with mxb_reduce_partial into a

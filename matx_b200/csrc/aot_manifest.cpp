@@ -206,6 +206,21 @@ void aot_manifest(std::vector<ManifestItem> *items) {
     for (int d : {MXB_F32, MXB_C64}) add(prog_identity(d), FAM_VAR_REG, MXB_RED_VAR, MXB_F32, ipt, false);
     add(prog_identity(MXB_F64), FAM_VAR_REG, MXB_RED_VAR, MXB_F64, ipt, false);
   }
+  // softmax: rows in registers, plus the statistics + apply pair for everything else
+  for (int ipt : {1, 2, 4, 8}) {
+    for (int fam : {FAM_SM_GROUP, FAM_SM_REG}) {
+      add(prog_identity(MXB_F32), fam, -1, MXB_F32, ipt, true);
+      add(prog_identity(MXB_BF16), fam, -1, MXB_BF16, ipt, false);
+      add(prog_identity(MXB_F64), fam, -1, MXB_F64, ipt, false);
+    }
+  }
+  for (int team : {0, 1}) add(prog_identity(MXB_F32), FAM_RED_INNER, KOP_LSE, MXB_F32, team, true);
+  add(prog_identity(MXB_F32), FAM_RED_OUTER, KOP_LSE, MXB_F32, 0, false);
+  {
+    ExprBuilder b;
+    const int x = b.leaf(MXB_F32), m = b.leaf(MXB_F32), sm = b.leaf(MXB_F32);
+    add(b.finish(b.bin(MXB_OP_MUL, b.un(MXB_OP_EXP, b.bin(MXB_OP_SUB, x, m)), sm)), FAM_EW, -1, MXB_F32, 0, false);
+  }
   // config 1: sum(a*b+c, {1})
   for (int op : {MXB_RED_SUM, MXB_RED_MAX, MXB_RED_ARGMAX})
     for (int team : {0, 1}) add(prog_fma3(MXB_F32), FAM_RED_INNER, op, MXB_F32, team, false);

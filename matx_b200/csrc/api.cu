@@ -164,6 +164,7 @@ int acc_bytes(int op, int value_dtype) {
   switch (op) {
     case MXB_RED_ARGMAX: case MXB_RED_ARGMIN: return 16;
     case MXB_RED_ANY: case MXB_RED_ALL: return 4;
+    case KOP_LSE: return 2 * dtype_bytes(value_dtype);
     default: return dtype_bytes(value_dtype);
   }
 }
@@ -1269,6 +1270,186 @@ int mxb_elementwise(mxb_handle_t h, const mxb_expr_t *expr_in, const mxb_out_t *
   return launch(h, k, grid, block, 0, p);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// softmax over the trailing n_reduce dims (reference: softmax_impl, transforms/reduce.h:362-445)
+// ---------------------------------------------------------------------------------------------------
+int mxb_softmax(mxb_handle_t h, const mxb_expr_t *expr_in, int n_reduce, const mxb_out_t *out) {
+  if (!h) return fail(MXB_ERR_INVALID, "null handle");
+  int st = check_expr_shape(expr_in);
+  if (st != MXB_OK) return st;
+  if (n_reduce < 1 || n_reduce > expr_in->rank) return fail(MXB_ERR_INVALID, "softmax needs 1 <= n_reduce_dims <= rank");
+  if (!out || !out->data) return fail(MXB_ERR_INVALID, "null output");
+  if (out->rank != expr_in->rank) return fail(MXB_ERR_SIZE, "softmax output rank must equal the input rank");
+  for (int d = 0; d < out->rank; ++d)
+    if (out->size[d] != expr_in->size[d]) return fail(MXB_ERR_SIZE, "output size mismatch in dim " + std::to_string(d));
+  if (out->dtype != MXB_F32 && out->dtype != MXB_F64 && out->dtype != MXB_BF16 && out->dtype != MXB_F16)
+    return fail(MXB_ERR_NOT_SUPPORTED, "softmax output must be a real floating type");
+  MXB_CUDA(cudaSetDevice(h->device));
+
+  mxb_expr_t e;
+  std::string err;
+  st = canonicalize(expr_in, &e, &err);
+  if (st != MXB_OK) return fail(st, err);
+  ExprInfo info;
+  st = analyze_expr(&e, &info, &err);
+  if (st != MXB_OK) return fail(st, err);
+  if (info.value_dtype != MXB_F32 && info.value_dtype != MXB_F64)
+    return fail(MXB_ERR_NOT_SUPPORTED, "softmax of a non-real-floating expression (the reference's max_impl rejects complex too)");
+
+  const int nbd = e.rank - n_reduce, nl = e.n_leaves;
+  Group gb, gr;
+  gb.n = nbd;
+  gr.n = n_reduce;
+  for (int d = 0; d < nbd; ++d) {
+    gb.size[d] = e.size[d];
+    for (int k = 0; k < nl; ++k) gb.ls[k][d] = e.leaves[k].stride[d];
+    gb.os[d] = out->stride[d];
+    gb.is[d] = 0;
+  }
+  for (int d = 0; d < n_reduce; ++d) {
+    gr.size[d] = e.size[nbd + d];
+    for (int k = 0; k < nl; ++k) gr.ls[k][d] = e.leaves[k].stride[nbd + d];
+    gr.os[d] = out->stride[nbd + d];
+    gr.is[d] = 0;
+  }
+  collapse(gb, nl);
+  collapse(gr, nl);
+  int64_t B = 1, R = 1;
+  for (int d = 0; d < gb.n; ++d) B *= gb.size[d];
+  for (int d = 0; d < gr.n; ++d) R *= gr.size[d];
+  if (B == 0 || R == 0) return MXB_OK;
+
+  // ---- one launch, row in registers: a single reduce run that every leaf and the output walk with stride 0 / 1 ----
+  const int obytes = dtype_bytes(out->dtype);
+  bool rows_ok = gr.n == 1 && gb.n <= KMAXD && gr.os[0] == 1 && !getenv("MXB_SOFTMAX_TWO_LAUNCH");
+  for (int k = 0; rows_ok && k < nl; ++k) rows_ok = (gr.ls[k][0] == 0 || gr.ls[k][0] == 1);
+  if (rows_ok) {
+    int vmax = env_int("MXB_TUNE_V", 0) > 0 ? env_int("MXB_TUNE_V", 0) : policy_vmax(info);
+    while (vmax > 1 && vmax * obytes > 32) vmax >>= 1;
+    auto vec_ok = [&](int V) {
+      if (R % V) return false;
+      if (!aligned_to(out->data, (int64_t)V * obytes)) return false;
+      for (int d = 0; d < gb.n; ++d) if (gb.os[d] % V) return false;
+      for (int k = 0; k < nl; ++k) {
+        if (gr.ls[k][0] == 0) continue;
+        if (!aligned_to(e.leaves[k].data, (int64_t)V * dtype_bytes(e.leaves[k].dtype))) return false;
+        for (int d = 0; d < gb.n; ++d) if (gb.ls[k][d] % V) return false;
+      }
+      return true;
+    };
+    int V = vmax;
+    while (V > 1 && !vec_ok(V)) V >>= 1;
+    const int64_t Lv = R / V;
+    KernelSpec spec;
+    spec.op = -1;
+    spec.out_dtype = out->dtype;
+    spec.V = V;
+    spec.U = 1;
+    int G = 0, thr = 0, ipt = 0;
+    const int max_ipt = env_int("MXB_SOFTMAX_MAX_IPT", 4);   // vectors per lane held in registers (8 spills under the budgets)
+    if (Lv <= 32 * max_ipt) {
+      G = 1;
+      while (G < 32 && G < Lv) G <<= 1;
+      ipt = 1;
+      while ((int64_t)G * ipt < Lv) ipt <<= 1;
+      spec.family = FAM_SM_GROUP;
+    } else {
+      const int vpt = env_int("MXB_TUNE_VAR_VPT", 4);
+      thr = 64;
+      while (thr < 1024 && (int64_t)thr * vpt < Lv) thr <<= 1;
+      ipt = 1;
+      while ((int64_t)thr * ipt < Lv && ipt < max_ipt) ipt <<= 1;
+      if ((int64_t)thr * ipt >= Lv) spec.family = FAM_SM_REG;
+      else ipt = 0;
+    }
+    if (ipt) {
+      spec.team = ipt;
+      RedParams p;
+      memset(&p, 0, sizeof p);
+      p.nb = gb.n;
+      p.nr = 1;
+      p.B = B;
+      p.R = R;
+      p.nleaf = nl;
+      p.splits = 1;
+      for (int d = 0; d < gb.n; ++d) {
+        p.bsz[d] = gb.size[d];
+        p.out.bs[d] = gb.os[d];
+        for (int k = 0; k < nl; ++k) p.leaf[k].bs[d] = gb.ls[k][d];
+      }
+      p.rsz[0] = R;
+      p.out_rs[0] = gr.os[0];
+      bool unit = nl > 0;
+      for (int k = 0; k < nl; ++k) {
+        p.leaf[k].rs[0] = gr.ls[k][0];
+        p.leaf[k].ptr = e.leaves[k].data;
+        unit = unit && gr.ls[k][0] == 1;
+      }
+      p.all_unit = unit ? 1 : 0;
+      p.out.ptr = out->data;
+      fill_consts(e, p.c);
+      const int sm = h->sm_count;
+      const int tune_cps = env_int("MXB_TUNE_CTAS_PER_SM", 0);
+      unsigned grid, block;
+      if (spec.family == FAM_SM_GROUP) {
+        p.tx = G;
+        block = 256;
+        const int64_t rows_per_cta = (int64_t)(block / 32) * (32 / G);
+        grid = (unsigned)std::min<int64_t>((B + rows_per_cta - 1) / rows_per_cta, (int64_t)sm * (tune_cps > 0 ? tune_cps : 8));
+      } else {
+        block = (unsigned)thr;
+        grid = (unsigned)std::min<int64_t>(B, (int64_t)sm * (tune_cps > 0 ? tune_cps : 32));
+      }
+      Kernel k;
+      st = get_kernel(info, spec, &k);
+      if (st != MXB_OK) return st;
+      return launch(h, k, grid, block, 0, p);
+    }
+  }
+
+  // ---- any other shape: statistics launch (running max / sum of exp through the ordinary reduction families, so long
+  // rows split over CTAs and strided reduce dims ride reduce_outer), then out = exp(x - max) * (1 / sum) as an elementwise
+  // statement with the two statistics as broadcast leaves.  Two reads (the second mostly from L2), one write; the
+  // reference does three reads, two temporaries and five launches.
+  const int64_t esz = dtype_bytes(info.value_dtype);
+  const size_t s_off = ((size_t)(B * esz) + 255) & ~(size_t)255;
+  st = ensure_tmp(h, 2 * s_off);
+  if (st != MXB_OK) return st;
+  mxb_out_t m_out;
+  memset(&m_out, 0, sizeof m_out);
+  m_out.data = h->tmp;
+  m_out.dtype = info.value_dtype;
+  m_out.rank = nbd;
+  {
+    int64_t w = 1;
+    for (int d = nbd - 1; d >= 0; --d) { m_out.size[d] = e.size[d]; m_out.stride[d] = w; w *= e.size[d]; }
+  }
+  mxb_out_t s_out = m_out;
+  s_out.data = (char *)h->tmp + s_off;
+  st = reduce_launch(h, KOP_LSE, e, info, n_reduce, &m_out, &s_out, RedOptions());
+  if (st != MXB_OK) return st;
+  if (e.n_leaves + 2 > MXB_MAX_LEAVES || e.n_nodes + 5 > MXB_MAX_NODES) return fail(MXB_ERR_NOT_SUPPORTED, "expression too large for the two-launch softmax");
+  mxb_expr_t e2 = e;
+  int stat_node[2];
+  for (int j = 0; j < 2; ++j) {
+    const int lk = e2.n_leaves++;
+    memset(&e2.leaves[lk], 0, sizeof e2.leaves[lk]);
+    e2.leaves[lk].data = j == 0 ? m_out.data : s_out.data;
+    e2.leaves[lk].dtype = info.value_dtype;
+    for (int d = 0; d < nbd; ++d) e2.leaves[lk].stride[d] = m_out.stride[d];
+    stat_node[j] = e2.n_nodes++;
+    e2.nodes[stat_node[j]] = mxb_node_t{MXB_OP_LEAF, {lk, -1}, 0};
+  }
+  const int nsub = e2.n_nodes++;
+  e2.nodes[nsub] = mxb_node_t{MXB_OP_SUB, {e.root, stat_node[0]}, 0};
+  const int nexp = e2.n_nodes++;
+  e2.nodes[nexp] = mxb_node_t{MXB_OP_EXP, {nsub, -1}, 0};
+  const int ndiv = e2.n_nodes++;
+  e2.nodes[ndiv] = mxb_node_t{MXB_OP_MUL, {nexp, stat_node[1]}, 0};   // stat 1 holds 1 / sum
+  e2.root = ndiv;
+  return mxb_elementwise(h, &e2, out);
+}
+
 int mxb_is_aot(const mxb_expr_t *expr, int reduce_op_or_minus1) {
   if (!expr) return 0;
   mxb_expr_t e;
@@ -1321,7 +1502,7 @@ int mxb_debug_compile(const mxb_expr_t *expr, int family, int reduce_op, int out
   if (st != MXB_OK) return fail(st, err);
   KernelSpec spec;
   spec.family = family;
-  spec.op = family == FAM_EW ? -1 : kernel_op(reduce_op);
+  spec.op = (family == FAM_EW || family == FAM_SM_GROUP || family == FAM_SM_REG) ? -1 : kernel_op(reduce_op);
   spec.out_dtype = out_dtype;
   spec.V = V > 0 ? V : policy_vmax(info);
   spec.U = policy_unroll(info, spec.V, family);

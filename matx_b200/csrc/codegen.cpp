@@ -39,6 +39,7 @@ const char *dtype_ctype(int d) {
 }
 const char *reduce_op_name(int op) {
   static const char *n[] = {"sum", "mean", "var", "stdd", "max", "min", "argmax", "argmin", "any", "all", "prod"};
+  if (op == KOP_LSE) return "lse";
   return (op >= 0 && op < MXB_RED_COUNT) ? n[op] : "?";
 }
 uint64_t fnv64(const std::string &s) {
@@ -338,7 +339,7 @@ int policy_vmax(const ExprInfo &info) {
 int policy_unroll(const ExprInfo &info, int V, int family) {
   const int bytes = V * info.max_leaf_bytes;  // widest load of one step
   if (family == FAM_RED_OUTER) return 4;
-  if (family == FAM_VAR_REG || family == FAM_VAR_TMA || family == FAM_VAR_GROUP) return 1;
+  if (family == FAM_VAR_REG || family == FAM_VAR_TMA || family == FAM_VAR_GROUP || family == FAM_SM_GROUP || family == FAM_SM_REG) return 1;
   if (family == FAM_VAR_SMEM) return bytes >= 32 ? 4 : 8;
   if (family == FAM_EW) return bytes >= 32 ? (info.nleaf <= 2 ? 2 : 1) : (info.nleaf <= 2 ? 4 : 2);
   return bytes >= 32 ? 2 : (info.nleaf <= 2 ? 4 : 2);
@@ -346,7 +347,7 @@ int policy_unroll(const ExprInfo &info, int V, int family) {
 
 std::string kernel_key(const ExprInfo &info, const KernelSpec &s) {
   std::ostringstream k;
-  static const char *fam[] = {"red_inner", "red_outer", "var_smem", "ew", "var_reg", "var_tma", "var_group"};
+  static const char *fam[] = {"red_inner", "red_outer", "var_smem", "ew", "var_reg", "var_tma", "var_group", "softmax_group", "softmax_reg"};
   k << fam[s.family] << "|" << info.name << "|" << (s.op >= 0 ? reduce_op_name(s.op) : "-") << "|" << dtype_name(s.out_dtype)
     << "|V" << s.V << "|U" << s.U << "|T" << s.team;
   return k.str();
@@ -376,6 +377,9 @@ int kernel_wrapper_src(const ExprInfo &info, const KernelSpec &s, const std::str
         op = "mxb::OpArg<" + T + (s.op == MXB_RED_ARGMAX ? ", true>" : ", false>"); break;
       case MXB_RED_ANY: op = "mxb::OpLogic<" + T + ", true>"; break;
       case MXB_RED_ALL: op = "mxb::OpLogic<" + T + ", false>"; break;
+      case KOP_LSE:
+        if (!(info.value_dtype == MXB_F32 || info.value_dtype == MXB_F64)) return fail("softmax of a non-real-floating expression");
+        op = "mxb::OpLse<" + T + ">"; break;
       default: return fail("reduce op has no kernel of its own");
     }
   }
@@ -405,6 +409,13 @@ int kernel_wrapper_src(const ExprInfo &info, const KernelSpec &s, const std::str
       if (!(info.value_dtype == MXB_F32 || info.value_dtype == MXB_F64 || cplx)) return fail("var of a non-floating expression");
       k << "extern \"C\" __global__ void __launch_bounds__(256) " << symbol
         << "(const __grid_constant__ mxb::RedParams p) { mxb::var_group_body<" << E << ", " << O << ", " << s.V << ", " << s.team << ">(p); }\n";
+      break;
+    case FAM_SM_GROUP: case FAM_SM_REG:
+      if (!(info.value_dtype == MXB_F32 || info.value_dtype == MXB_F64)) return fail("softmax of a non-real-floating expression");
+      // register budgets from ptxas (no spills): group 78 regs at 4 vectors per lane, CTA family <= 64 regs up to 1024 threads
+      k << "extern \"C\" __global__ void __launch_bounds__(" << (s.family == FAM_SM_GROUP ? (s.team >= 4 ? "256, 3" : "256, 4") : "1024") << ") " << symbol
+        << "(const __grid_constant__ mxb::RedParams p) { mxb::" << (s.family == FAM_SM_GROUP ? "softmax_group_body<" : "softmax_reg_body<") << E << ", " << O
+        << ", " << s.V << ", " << s.team << ">(p); }\n";
       break;
     case FAM_VAR_TMA:
       if (info.nleaf != 1) return fail("var_tma serves plain tensors only");

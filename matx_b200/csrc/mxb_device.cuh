@@ -113,6 +113,7 @@ struct RedParams {
   // NVLink peer mappings (no collective call): rec[r] = rank r's PartialRec[2 slots][world][KMAXITEMS],
   // flag[r] = rank r's arrival counters u32[world], epoch = this rank's count of completed exchanges
   PeerPush peer;
+  i64 out_rs[KMAXD];  // softmax: strides of the output over the reduce dims
 };
 
 // elementwise: up to KMAXD collapsed dims, innermost last
@@ -548,6 +549,45 @@ template <class T, bool IS_ANY> struct OpLogic {
   static __device__ __forceinline__ i64 index(acc_t) { return 0; }
 };
 
+// running (max, sum of exp(x - max)) of a row: the one-pass form of the reference's softmax statistics
+// (max_impl, then sum_impl(exp(in - max)), transforms/reduce.h:371-373,440-441).  `out` receives the max, the
+// auxiliary output (the index slot of the parameter block, here in the value type) the reciprocal of the sum.
+template <class T> struct __align__(2 * sizeof(T)) LseAcc { T m, s; };
+template <class T> struct OpLse {
+  typedef LseAcc<T> acc_t; typedef T result_t; enum { HAS_INDEX = 0 };
+  static __device__ __forceinline__ acc_t init() { acc_t a; a.m = Limits<T>::lowest(); a.s = (T)0; return a; }
+  // exp(-|hi - lo|), with equal operands (two -inf included) giving exactly 1
+  static __device__ __forceinline__ T decay(T d, bool same) { return same ? (T)1 : f_exp(d > (T)0 ? -d : d); }
+  static __device__ __forceinline__ void step(acc_t &a, T x, i64) {
+    const T d = x - a.m;
+    const T e = decay(d, x == a.m);
+    if (d > (T)0) { a.s = a.s * e + (T)1; a.m = x; }
+    else a.s = a.s + e;
+  }
+  static __device__ __forceinline__ void merge(acc_t &a, acc_t b) {
+    if (b.s == (T)0) return;             // identity
+    if (a.s == (T)0) { a = b; return; }
+    const T d = b.m - a.m;
+    const T e = decay(d, b.m == a.m);
+    if (d > (T)0) { a.s = a.s * e + b.s; a.m = b.m; }
+    else a.s = a.s + b.s * e;
+  }
+  static __device__ __forceinline__ acc_t warp(acc_t a) {
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) { acc_t o = shfl_xor_t(a, m); merge(a, o); }
+    return a;
+  }
+  static __device__ __forceinline__ result_t finish(acc_t a) { return a.m; }
+  static __device__ __forceinline__ i64 index(acc_t) { return 0; }
+};
+// second output of an op (none by default)
+template <class Op> struct AuxStore {
+  static __device__ __forceinline__ void go(void *, i64, typename Op::acc_t) {}
+};
+template <class T> struct AuxStore<OpLse<T> > {
+  static __device__ __forceinline__ void go(void *ptr, i64 off, LseAcc<T> a) { ((T *)ptr)[off] = (T)1 / a.s; }  // the apply pass multiplies
+};
+
 
 // ------------------------------------------------------------------------------------------------
 // post-processing of a finished sum (mean / var divisor, stdd sqrt) and the store
@@ -648,6 +688,7 @@ __device__ __forceinline__ void store_result(const RedParams &p, i64 b, typename
     }
     ((i64 *)p.idx.ptr)[io] = ix;
   }
+  AuxStore<Op>::go(p.idx.ptr, io, acc);
 }
 
 // read a record another CTA wrote during this launch (L2, never a stale L1 line)
@@ -1319,6 +1360,163 @@ __device__ __forceinline__ void var_group_body_impl(const RedParams &p) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// S1: softmax_group / softmax_reg — out(b, :) = exp(x(b, :) - max_b) / sum(exp(x(b, :) - max_b)), the arithmetic of
+// the reference's softmax_impl (transforms/reduce.h:362-445: max_impl, sum_impl(exp(in - max)), then the divide) in
+// ONE launch with one HBM read and one write: the evaluated row is parked in registers (IPT vectors per lane),
+// max -> exp -> sum -> divide run out of them.  softmax_group: G = p.tx lanes of a warp own a row (32 / G rows per
+// warp, shuffles only); softmax_reg: a CTA owns a row (two barriers per row, per-warp partials double-buffered by
+// row parity and folded by every thread in the same order).  Needs a single contiguous reduce dim; anything else
+// takes the two-launch path (OpLse statistics + the elementwise kernel).
+// ------------------------------------------------------------------------------------------------
+template <class OutT, int V>
+__device__ __forceinline__ void softmax_store(OutT *orow, i64 q, i64 ostride, const Vec<OutT, V> &o) {
+  if (V == 1) orow[q * ostride] = o.v[0];
+  else StBytes<(int)sizeof(OutT) * V>::st(orow + q * V, &o);
+}
+
+template <class E, class OutT, int V, int IPT, bool UNIT>
+__device__ __forceinline__ void softmax_group_body_impl(const RedParams &p) {
+  typedef typename E::value_type T;
+  const int G = p.tx, gpw = 32 / G;
+  const int tid = (int)(threadIdx.x & (G - 1)), gid = (int)((threadIdx.x & 31) / G);
+  const i64 wb0 = ((i64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * gpw;
+  const i64 wstep = (i64)gridDim.x * (blockDim.x >> 5) * gpw;
+  const i64 Lv = p.rsz[0] / V;
+  const i64 ostride = p.out_rs[0];
+  for (i64 wb = wb0; wb < p.B; wb += wstep) {
+    i64 b = wb + gid;
+    const bool valid = b < p.B;
+    if (!valid) b = p.B - 1;
+    const char *base[E::NL];
+    i64 inner[E::NL];
+    i64 bidx[KMAXD];
+    decomp(b, p.nb, p.bsz, bidx);
+#pragma unroll
+    for (int k = 0; k < E::NL; ++k) {
+      i64 off = 0;
+#pragma unroll
+      for (int d = 0; d < KMAXD; ++d) if (d < p.nb) off += bidx[d] * p.leaf[k].bs[d];
+      base[k] = (const char *)p.leaf[k].ptr + off * E::leaf_bytes(k);
+      inner[k] = p.leaf[k].rs[0];
+    }
+    i64 oo = 0;
+#pragma unroll
+    for (int d = 0; d < KMAXD; ++d) if (d < p.nb) oo += bidx[d] * p.out.bs[d];
+    OutT *orow = (OutT *)p.out.ptr + oo;
+    typename E::template Regs<V> r[IPT];
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) {
+      const i64 q = tid + (i64)i * G;
+      if (q < Lv) E::template loadv<V, UNIT>(r[i], base, inner, q * V);
+    }
+    Vec<T, V> x[IPT];
+    T mx = Limits<T>::lowest();
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) {
+      if (tid + (i64)i * G < Lv) {
+#pragma unroll
+        for (int v = 0; v < V; ++v) { x[i].v[v] = E::template eval<V>(r[i], v, p.c); mx = x[i].v[v] > mx ? x[i].v[v] : mx; }
+      }
+    }
+    for (int m = G >> 1; m > 0; m >>= 1) { const T o = shfl_xor_t(mx, m); mx = o > mx ? o : mx; }
+    T sum = (T)0;
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) {
+      if (tid + (i64)i * G < Lv) {
+#pragma unroll
+        for (int v = 0; v < V; ++v) { x[i].v[v] = f_exp(x[i].v[v] - mx); sum = sum + x[i].v[v]; }
+      }
+    }
+    for (int m = G >> 1; m > 0; m >>= 1) sum = sum + shfl_xor_t(sum, m);
+    const T inv = (T)1 / sum;   // one IEEE reciprocal per row; exp * inv is within 1 ulp of the reference's exp / sum
+    if (valid) {
+#pragma unroll
+      for (int i = 0; i < IPT; ++i) {
+        const i64 q = tid + (i64)i * G;
+        if (q < Lv) {
+          Vec<OutT, V> o;
+#pragma unroll
+          for (int v = 0; v < V; ++v) o.v[v] = cvt<OutT>(x[i].v[v] * inv);
+          softmax_store<OutT, V>(orow, q, ostride, o);
+        }
+      }
+    }
+  }
+}
+
+template <class E, class OutT, int V, int IPT, bool UNIT>
+__device__ __forceinline__ void softmax_reg_body_impl(const RedParams &p) {
+  typedef typename E::value_type T;
+  __shared__ T s_max[2][32];
+  __shared__ T s_sum[2][32];
+  const int nthr = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
+  const i64 Lv = p.rsz[0] / V;
+  const i64 ostride = p.out_rs[0];
+  int par = 0;
+  for (i64 b = blockIdx.x; b < p.B; b += gridDim.x, par ^= 1) {
+    const char *base[E::NL];
+    i64 inner[E::NL];
+    i64 bidx[KMAXD];
+    decomp(b, p.nb, p.bsz, bidx);
+#pragma unroll
+    for (int k = 0; k < E::NL; ++k) {
+      i64 off = 0;
+#pragma unroll
+      for (int d = 0; d < KMAXD; ++d) if (d < p.nb) off += bidx[d] * p.leaf[k].bs[d];
+      base[k] = (const char *)p.leaf[k].ptr + off * E::leaf_bytes(k);
+      inner[k] = p.leaf[k].rs[0];
+    }
+    i64 oo = 0;
+#pragma unroll
+    for (int d = 0; d < KMAXD; ++d) if (d < p.nb) oo += bidx[d] * p.out.bs[d];
+    OutT *orow = (OutT *)p.out.ptr + oo;
+    typename E::template Regs<V> r[IPT];
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) {
+      const i64 q = tid + (i64)i * nthr;
+      if (q < Lv) E::template loadv<V, UNIT>(r[i], base, inner, q * V);
+    }
+    Vec<T, V> x[IPT];
+    T mx = Limits<T>::lowest();
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) {
+      if (tid + (i64)i * nthr < Lv) {
+#pragma unroll
+        for (int v = 0; v < V; ++v) { x[i].v[v] = E::template eval<V>(r[i], v, p.c); mx = x[i].v[v] > mx ? x[i].v[v] : mx; }
+      }
+    }
+    mx = OpExt<T, true>::warp(mx);
+    if (lane == 0) s_max[par][warp] = mx;
+    __syncthreads();  // (A)
+    for (int w = 0; w < nwarp; ++w) { const T o = s_max[par][w]; mx = o > mx ? o : mx; }
+    T sum = (T)0;
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) {
+      if (tid + (i64)i * nthr < Lv) {
+#pragma unroll
+        for (int v = 0; v < V; ++v) { x[i].v[v] = f_exp(x[i].v[v] - mx); sum = sum + x[i].v[v]; }
+      }
+    }
+    sum = OpSum<T>::warp(sum);
+    if (lane == 0) s_sum[par][warp] = sum;
+    __syncthreads();  // (B)
+    T tot = (T)0;
+    for (int w = 0; w < nwarp; ++w) tot = tot + s_sum[par][w];  // same order in every thread
+    const T inv = (T)1 / tot;
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) {
+      const i64 q = tid + (i64)i * nthr;
+      if (q < Lv) {
+        Vec<OutT, V> o;
+#pragma unroll
+        for (int v = 0; v < V; ++v) o.v[v] = cvt<OutT>(x[i].v[v] * inv);
+        softmax_store<OutT, V>(orow, q, ostride, o);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // K3t: var_inner_tma — variance / stdd of contiguous rows of a plain tensor, rows staged ONCE in shared memory by
 // the TMA engine.  Persistent grid, one CTA per SM, a ring of `stages` row buffers: thread 0 arms an mbarrier with
 // the row's byte count and issues one `cp.async.bulk.shared::cluster.global` (SASS UBLKCP) per row; the whole CTA
@@ -1595,6 +1793,20 @@ __device__ __forceinline__ void var_group_body(const RedParams &p) {
   pdl_prologue();
   if (p.all_unit) var_group_body_impl<E, OutT, V, IPT, true>(p);
   else var_group_body_impl<E, OutT, V, IPT, false>(p);
+}
+
+template <class E, class OutT, int V, int IPT>
+__device__ __forceinline__ void softmax_group_body(const RedParams &p) {
+  pdl_prologue();
+  if (p.all_unit) softmax_group_body_impl<E, OutT, V, IPT, true>(p);
+  else softmax_group_body_impl<E, OutT, V, IPT, false>(p);
+}
+
+template <class E, class OutT, int V, int IPT>
+__device__ __forceinline__ void softmax_reg_body(const RedParams &p) {
+  pdl_prologue();
+  if (p.all_unit) softmax_reg_body_impl<E, OutT, V, IPT, true>(p);
+  else softmax_reg_body_impl<E, OutT, V, IPT, false>(p);
 }
 
 }  // namespace mxb

@@ -297,6 +297,17 @@ def all(a, dims=None): return ReduceExpr(A.RED_ALL, a, dims)        # noqa: A001
 def prod(a, dims=None): return ReduceExpr(A.RED_PROD, a, dims)
 
 
+class SoftmaxExpr(ReduceExpr):
+    """softmax(a, dims) (operators/softmax.h:40-140 -> softmax_impl, transforms/reduce.h:362-445): same rank as the operand."""
+
+    def __init__(self, a, dims):
+        super().__init__(-1, a, dims)
+        self.out_shape = tuple(self.a.shape)
+
+
+def softmax(a, dims=None): return SoftmaxExpr(a, dims)
+
+
 class mtie:
     """mtie(values, indices) — multi-output LHS (core/tie.h:44-117)."""
 
@@ -425,7 +436,16 @@ class Set:
                 raise A.MatxB200Error(A.ERR_SIZE, "lhs shape %s does not match rhs shape %s" % (o.shape, shape))  # matxInvalidSize
 
     def run(self, ex: "CudaExecutor") -> None:
-        if isinstance(self.rhs, ReduceExpr):
+        if isinstance(self.rhs, SoftmaxExpr):
+            r = self.rhs
+            e = lower_reduce(r)
+            o = _out_desc(self.lhs)
+            out = A.Out()
+            out.data, out.dtype, out.rank = o.data, o.dtype, o.rank
+            for i, d in enumerate(r.perm):   # the output is walked in the same permuted order as the operand
+                out.size[i], out.stride[i] = o.size[d], o.stride[d]
+            A.check(A.lib.mxb_softmax(ex.handle, C.byref(e), len(r.dims), C.byref(out)))
+        elif isinstance(self.rhs, ReduceExpr):
             r = self.rhs
             e = lower_reduce(r)
             if isinstance(self.lhs, mtie):

@@ -460,3 +460,40 @@ int orc_reduce(int op, const mxb_expr_t *e, int n_reduce, const mxb_out_t *out, 
   }
   return 0;
 }
+
+/* softmax over the trailing n_reduce dims — softmax_impl, transforms/reduce.h:362-445: tmp_max = max(in);
+ * tmp_sum = sum(exp(in - tmp_max)); dest = exp(in - tmp_max) / tmp_sum, all in the value type (the reference has a
+ * CUDA implementation only; the reductions are restated sequentially here, so sums agree with it to rounding).
+ * `out` has the rank and sizes of `e`. */
+int orc_softmax(const mxb_expr_t *e, int n_reduce, const mxb_out_t *out) {
+  const int nb = e->rank - n_reduce;
+  int64_t B = 1, R = 1;
+  for (int d = 0; d < nb; ++d) B *= e->size[d];
+  for (int d = nb; d < e->rank; ++d) R *= e->size[d];
+  if (n_reduce < 1) return 1;
+  int64_t idx[MXB_MAX_RANK] = {0};
+  for (int64_t b = 0; b < B; ++b) {
+    unflatten(b, nb, e->size, idx);
+    val_t mx; memset(&mx, 0, sizeof mx);
+    for (int64_t r = 0; r < R; ++r) {
+      unflatten(r, n_reduce, e->size + nb, idx + nb);
+      val_t x = eval_expr(e, idx);
+      if (x.t != MXB_F32 && x.t != MXB_F64) return 2;
+      if (r == 0 || val_less(mx, x)) mx = x;
+    }
+    val_t sum; memset(&sum, 0, sizeof sum); sum.t = mx.t;
+    for (int64_t r = 0; r < R; ++r) {
+      unflatten(r, n_reduce, e->size + nb, idx + nb);
+      val_t ex = unary_math(MXB_OP_EXP, arith(MXB_OP_SUB, eval_expr(e, idx), mx));
+      sum = arith(MXB_OP_ADD, sum, ex);
+    }
+    for (int64_t r = 0; r < R; ++r) {
+      unflatten(r, n_reduce, e->size + nb, idx + nb);
+      val_t ex = unary_math(MXB_OP_EXP, arith(MXB_OP_SUB, eval_expr(e, idx), mx));
+      int64_t off = 0;
+      for (int d = 0; d < e->rank; ++d) off += idx[d] * out->stride[d];
+      store_val(out->data, out->dtype, off, arith(MXB_OP_DIV, ex, sum));
+    }
+  }
+  return 0;
+}

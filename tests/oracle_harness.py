@@ -46,6 +46,7 @@ class Oracle:
         self.lib = lib
         lib.orc_elementwise.argtypes = [C.POINTER(A.Expr), C.POINTER(A.Out)]
         lib.orc_reduce.argtypes = [C.c_int, C.POINTER(A.Expr), C.c_int, C.POINTER(A.Out), C.POINTER(A.Out), C.c_int, C.c_int]
+        lib.orc_softmax.argtypes = [C.POINTER(A.Expr), C.c_int, C.POINTER(A.Out)]
 
     def elementwise(self, rhs, out: np.ndarray, out_dtype: int | None = None) -> np.ndarray:
         rhs = mx._wrap(rhs, None)
@@ -55,6 +56,16 @@ class Oracle:
         e = mx.lower_elementwise(rhs)
         o = mx._out_desc(lhs)
         assert self.lib.orc_elementwise(C.byref(e), C.byref(o)) == 0
+        return out
+
+    def softmax(self, r: "mx.SoftmaxExpr", out: np.ndarray, out_dtype: int | None = None) -> np.ndarray:
+        e = mx.lower_reduce(r)
+        o = mx._out_desc(np_tensor(out, out_dtype))
+        po = A.Out()
+        po.data, po.dtype, po.rank = o.data, o.dtype, o.rank
+        for i, d in enumerate(r.perm):
+            po.size[i], po.stride[i] = o.size[d], o.stride[d]
+        assert self.lib.orc_softmax(C.byref(e), len(r.dims), C.byref(po)) == 0
         return out
 
     def reduce(self, r: mx.ReduceExpr, out: np.ndarray, idx: np.ndarray | None = None, out_dtype: int | None = None,

@@ -108,7 +108,8 @@ def test_named_programs_are_ahead_of_time():
 
 
 @pytest.mark.parametrize("family,op,team", [(0, A.RED_SUM, 0), (0, A.RED_ARGMIN, 1), (1, A.RED_MAX, 0), (2, A.RED_VAR, 0),
-                                            (4, A.RED_VAR, 4), (3, -1, 0)])
+                                            (4, A.RED_VAR, 4), (3, -1, 0), (6, A.RED_VAR, 2), (7, -1, 2), (8, -1, 4),
+                                            (0, 11, 0), (1, 11, 0)])   # 7 / 8: softmax in registers; op 11: its statistics pass
 def test_generated_kernels_compile_for_sm100a(family, op, team):
     a = np_tensor(np.zeros((4, 8), np.float32))
     h = np_tensor(np.zeros((4, 8), np.uint16), A.BF16)

@@ -211,3 +211,26 @@ def test_bf16_host_accumulation_stagnates(oracle):
     out = np.zeros((), np.uint16)
     oracle.reduce(mx.sum(np_tensor(bits, A.BF16)), out, None, out_dtype=A.BF16)  # fp32 accumulation (the B200 path)
     assert bf16_bits_to_f32(out.reshape(1))[0] == 128.0
+
+
+# ---- softmax: the reference's golden generator is scipy.special.softmax (generators/00_reductions.py:10-26) -----
+@pytest.mark.parametrize("npdt,tol", [(np.float32, 2e-6), (np.float64, 1e-14)])
+def test_softmax_matches_the_reference_generator(oracle, npdt, tol):
+    from scipy import special
+    np.random.seed(1234)                      # the generator's seed
+    t1 = np.random.randn(300).astype(npdt)    # ReductionTests.cu:327-339 (size 300)
+    t3 = np.random.randn(8, 30, 300).astype(npdt)
+    out = np.zeros_like(t1)
+    oracle.softmax(mx.softmax(np_tensor(t1)), out)
+    assert np.allclose(out, special.softmax(t1.astype(np.float64)), rtol=tol, atol=0)
+    out3 = np.zeros_like(t3)
+    oracle.softmax(mx.softmax(np_tensor(t3), [2]), out3)
+    assert np.allclose(out3, special.softmax(t3.astype(np.float64), axis=2), rtol=tol, atol=0)
+    assert np.allclose(out3.sum(axis=2), 1.0, rtol=1e-5)
+    # a middle axis walks both the operand and the output through the same permutation (reduce.h:404-445)
+    oracle.softmax(mx.softmax(np_tensor(t3), [1]), out3)
+    assert np.allclose(out3, special.softmax(t3.astype(np.float64), axis=1), rtol=tol, atol=0)
+    # strided output view
+    wide = np.full((8, 30, 600), -5, npdt)
+    oracle.softmax(mx.softmax(np_tensor(t3), [2]), wide[:, :, ::2])
+    assert np.allclose(wide[:, :, ::2], special.softmax(t3.astype(np.float64), axis=2), rtol=tol, atol=0) and (wide[:, :, 1::2] == -5).all()
