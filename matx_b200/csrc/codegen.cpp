@@ -85,12 +85,12 @@ std::string as(int want, int have, const std::string &x) {
 
 struct UnaryFn { int opcode; const char *name; const char *ffn; const char *dfn; };
 const UnaryFn kUnary[] = {
-    {MXB_OP_SQRT, "sqrt", "sqrtf", "sqrt"},     {MXB_OP_LOG, "log", "logf", "log"},       {MXB_OP_LOG2, "log2", "log2f", "log2"},
+    {MXB_OP_SQRT, "sqrt", "sqrtf", "sqrt"},     {MXB_OP_LOG, "log", "mxb::f_log", "mxb::f_log"},       {MXB_OP_LOG2, "log2", "log2f", "log2"},
     {MXB_OP_LOG10, "log10", "log10f", "log10"}, {MXB_OP_SIN, "sin", "sinf", "sin"},       {MXB_OP_COS, "cos", "cosf", "cos"},
     {MXB_OP_TAN, "tan", "tanf", "tan"},         {MXB_OP_TANH, "tanh", "tanhf", "tanh"},   {MXB_OP_SINH, "sinh", "sinhf", "sinh"},
     {MXB_OP_COSH, "cosh", "coshf", "cosh"},     {MXB_OP_ASIN, "asin", "asinf", "asin"},   {MXB_OP_ACOS, "acos", "acosf", "acos"},
     {MXB_OP_ATAN, "atan", "atanf", "atan"},     {MXB_OP_FLOOR, "floor", "floorf", "floor"}, {MXB_OP_CEIL, "ceil", "ceilf", "ceil"},
-    {MXB_OP_ROUND, "round", "roundf", "round"}, {MXB_OP_RSQRT, "rsqrt", "rsqrtf", "rsqrt"}, {MXB_OP_NORMCDF, "normcdf", "normcdff", "normcdf"},
+    {MXB_OP_ROUND, "round", "roundf", "round"}, {MXB_OP_RSQRT, "rsqrt", "rsqrtf", "rsqrt"}, {MXB_OP_NORMCDF, "normcdf", "mxb::f_normcdf", "mxb::f_normcdf"},
 };
 const char *opcode_tag(int op) {
   switch (op) {

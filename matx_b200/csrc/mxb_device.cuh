@@ -311,7 +311,69 @@ template <> __device__ __forceinline__ bool nonzero<cfloat>(cfloat x) { return x
 // scalar math used by generated expressions (reference functors: operators/scalar_ops.h:434-503,
 // scalar_internal.h:44-297 which forward to cuda::std / CUDA math)
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float f_normcdf(float x) { return normcdff(x); }
+// normcdf(x) for fp32, hand-written: the CUDA library's normcdff costs ~63 SASS instructions per call and the fused
+// Black-Scholes chain (examples/black_scholes.cu:122-138, two calls per option) is instruction-issue bound on B200, not
+// HBM bound, with it.  This one is ~28: with z = min(|x|, 14.5),
+//   Phi(-z) = exp(-z^2/2) * Q(z),   Q(z) = erfcx(z/sqrt2)/2 = u * P(t),  u = 1/(z+4),  t = (z-4)/(z+4) = 1 - 8u
+// P = degree-9 minimax fit (relative error 9e-9 on [0, 14.6], fitted here from scipy's erfcx, not copied from
+// anywhere); exp(-z^2/2) = ex2(a_hi) * (1 + ln2 * a_lo) with the rounding residue of z*z and of the product with
+// -0.5*log2(e) carried in a_lo, so the tail keeps its RELATIVE accuracy (|x| = 10: a = -72, an uncompensated product
+// would be off by 3e-6).  Measured against fp64 truth over [-14.5, 9]: mean 1.1 ulp, max ~9 ulp with MUFU.RCP/EX2 at
+// their documented 1 / 2 ulp (the library function documents 5 ulp); NaN propagates (min.NaN), +-inf give 1 / 0,
+// results below 2^-126 flush to zero (|x| > 13.2, where the library returns denormals).
+__device__ __forceinline__ float f_normcdf(float x) {
+  float z;
+  asm("min.NaN.f32 %0, %1, %2;" : "=f"(z) : "f"(fabsf(x)), "f"(14.5f));
+  const float s = z * z, sl = fmaf(z, z, -s);
+  const float d = z + 4.0f;
+  float u;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(u) : "f"(d));
+  u = fmaf(u, fmaf(-d, u, 1.0f), u);  // one Newton step: u = 1/d to half an ulp
+  const float t = fmaf(-8.0f, u, 1.0f);
+  float p = -1.324342156e-04f;
+  p = fmaf(p, t, 1.783698972e-04f);
+  p = fmaf(p, t, 1.569589484e-03f);
+  p = fmaf(p, t, -3.512077034e-03f);
+  p = fmaf(p, t, -7.525003050e-03f);
+  p = fmaf(p, t, 6.040376425e-02f);
+  p = fmaf(p, t, -1.865234822e-01f);
+  p = fmaf(p, t, 3.871369064e-01f);
+  p = fmaf(p, t, -6.078965664e-01f);
+  p = fmaf(p, t, 7.552851439e-01f);
+  const float q = p * u;
+  const float C = -0.72134752044448170368f;                       // -0.5 * log2(e)
+  const float CL = (float)(-0.72134752044448170368 - (double)C);  // and what fp32 dropped of it
+  const float ahi = s * C;
+  const float alo = fmaf(sl, C, fmaf(s, CL, fmaf(s, C, -ahi)));
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(ahi));
+  float r = e * q;
+  r = fmaf(r * 0.69314718055994530942f, alo, r);
+  return x < 0.0f ? r : 1.0f - r;
+}
+// log(x) for fp32: the same range reduction and polynomial degree as every fp32 logf (m in [2/3, 4/3), log1p(f) =
+// f + f*f*p(f), p a degree-8 minimax fit made here), with zero / subnormal / negative / inf / NaN sent to the library
+// function by ONE unsigned compare instead of five select instructions on the hot path.
+static __device__ __noinline__ float f_log_special(float x) { return logf(x); }  // out of line: keeps the cold block out of unrolled loops
+__device__ __forceinline__ float f_log(float x) {
+  const unsigned ix = __float_as_uint(x);
+  if (ix - 0x00800000u >= 0x7f000000u) return f_log_special(x);
+  const unsigned e = (ix - 0x3f2aaaabu) & 0xff800000u;
+  const float f = __uint_as_float(ix - e) - 1.0f;
+  const float fe = (float)(int)e;
+  float p = -0.1294892579317093f;
+  p = fmaf(p, f, 0.1400475949048996f);
+  p = fmaf(p, f, -0.1216716319322586f);
+  p = fmaf(p, f, 0.14001160860061646f);
+  p = fmaf(p, f, -0.16682304441928864f);
+  p = fmaf(p, f, 0.20010747015476227f);
+  p = fmaf(p, f, -0.24999716877937317f);
+  p = fmaf(p, f, 0.3333320915699005f);
+  p = fmaf(p, f, -0.5f);
+  p = fmaf(f, p * f, f);
+  return fmaf(fe, 8.26295829e-08f, p);  // + exponent * ln2 (e still carries its 2^23 scale)
+}
+__device__ __forceinline__ double f_log(double x) { return log(x); }
 __device__ __forceinline__ double f_normcdf(double x) { return normcdf(x); }
 __device__ __forceinline__ float f_abs(float x) { return fabsf(x); }
 __device__ __forceinline__ double f_abs(double x) { return fabs(x); }
