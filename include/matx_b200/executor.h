@@ -25,7 +25,8 @@
 //     MXB_ERR_SIZE -> matxInvalidSize.
 //
 // Lowered node types: tensor views (any strides: permuted / sliced / cloned views are just strides), arithmetic
-// scalars, matxBinaryOp, matxUnaryOp with the functors of operators/scalar_ops.h:434-503, PermuteOp, CloneOp.
+// scalars, matxBinaryOp, matxUnaryOp with the functors of operators/scalar_ops.h:434-503, PermuteOp, CloneOp, DiagOp
+// (so trace(x) = sum(diag(x)) is one strided reduction) and IsCloseOp (so allclose is one fused all-reduction).
 // The expression-template nodes keep their operands private, so the walker reads them through layout mirrors
 // (same member types in the same order; sizes are checked with static_assert).
 #pragma once
@@ -103,6 +104,18 @@ template <int CRank, class T> struct node_kind<matx::detail::CloneOp<CRank, T>> 
   struct Mirror { matx::detail::base_type_t<T> op_; cuda::std::array<index_t, CRank> sizes_; cuda::std::array<index_t, T::Rank()> dims_; };
 };
 
+template <class T, int RANK> struct node_kind<matx::detail::DiagOp<T, RANK>> {   // operators/diag.h:52-56
+  static constexpr int value = (RANK >= 2) ? 5 : 0;   // diag(vector) builds a matrix: not on this path
+  using A = T;
+  struct Mirror { matx::detail::base_type_t<T> op_; index_t k_; };
+};
+template <class O1, class O2> struct node_kind<matx::detail::IsCloseOp<O1, O2>> {   // operators/isclose.h:234-238
+  static constexpr int value = 6;
+  using A = O1; using B = O2;
+  using inner = typename matx::detail::IsCloseOp<O1, O2>::inner_type;
+  struct Mirror { matx::detail::base_type_t<O1> op1_; matx::detail::base_type_t<O2> op2_; inner rtol_; inner atol_; };
+};
+
 template <class T> constexpr int rank_of_operand() {
   if constexpr (std::is_arithmetic_v<T> || is_complex_v<T>) return 0;
   else return T::Rank();
@@ -117,7 +130,10 @@ template <class T0> constexpr bool lowerable() {
   else if constexpr (node_kind<T>::value == 1)
     return fn_code<typename node_kind<T>::Fn>::value >= 0 && lowerable<typename node_kind<T>::A>() && lowerable<typename node_kind<T>::B>();
   else if constexpr (node_kind<T>::value == 2) return fn_code<typename node_kind<T>::Fn>::value >= 0 && lowerable<typename node_kind<T>::A>();
-  else if constexpr (node_kind<T>::value == 3 || node_kind<T>::value == 4) return lowerable<typename node_kind<T>::A>();
+  else if constexpr (node_kind<T>::value == 3 || node_kind<T>::value == 4 || node_kind<T>::value == 5) return lowerable<typename node_kind<T>::A>();
+  else if constexpr (node_kind<T>::value == 6)
+    return (std::is_same_v<typename node_kind<T>::inner, float> || std::is_same_v<typename node_kind<T>::inner, double>) &&
+           lowerable<typename node_kind<T>::A>() && lowerable<typename node_kind<T>::B>();
   else return false;
 }
 
@@ -211,6 +227,49 @@ template <class Op0> int lower(Builder &b, const Op0 &op, const int *axes) {
       child[d] = axes[od];
     }
     return lower(b, m.op_, child);
+  } else if constexpr (node_kind<Op>::value == 5) {
+    // diag(op, k): the result's last dim walks rows AND columns of the operand (operators/diag.h:145-190), i.e. both
+    // of the operand's last two dims map to the same root dim and their strides add up.  k != 0 offsets the data
+    // pointer, which only a tensor operand has.
+    using K = node_kind<Op>;
+    static_assert(sizeof(typename K::Mirror) == sizeof(Op), "DiagOp layout changed: update the mirror");
+    const auto &m = reinterpret_cast<const typename K::Mirror &>(op);
+    using Child = remove_cvref_t<decltype(m.op_)>;
+    constexpr int RA = Child::Rank();
+    int child[MXB_MAX_RANK];
+    for (int d = 0; d < RA - 2; ++d) child[d] = axes[d];
+    child[RA - 2] = child[RA - 1] = axes[RA - 2];
+    if (m.k_ == 0) return lower(b, m.op_, child);
+    {  // the reference's size rule for k != 0 (diag.h:262-267) runs off a non-square matrix: leave that to the reference
+      const index_t rows = m.op_.Size(RA - 2), cols = m.op_.Size(RA - 1);
+      const index_t valid = m.k_ > 0 ? cuda::std::min(rows, cols - m.k_) : cuda::std::min(rows + m.k_, cols);
+      if (op.Size(RA - 2) > valid) { b.ok = false; return 0; }
+    }
+    if constexpr (is_tensor_view_v<Child> || matx::is_tensor_impl_v<Child>) {
+      mxb_leaf_t lf;
+      std::memset(&lf, 0, sizeof lf);
+      const index_t off = m.k_ > 0 ? m.k_ * m.op_.Stride(RA - 1) : -m.k_ * m.op_.Stride(RA - 2);
+      lf.data = m.op_.Data() + off;
+      lf.dtype = dtype_of<typename Child::value_type>::value;
+      for (int d = 0; d < RA; ++d) lf.stride[child[d]] += m.op_.Stride(d);
+      return b.leaf(lf);
+    } else {
+      b.ok = false;
+      return 0;
+    }
+  } else if constexpr (node_kind<Op>::value == 6) {
+    // isclose: int(|a - b| <= atol + rtol * |b|), tolerances in the operands' inner type (operators/isclose.h)
+    using K = node_kind<Op>;
+    static_assert(sizeof(typename K::Mirror) == sizeof(Op), "IsCloseOp layout changed: update the mirror");
+    const auto &m = reinterpret_cast<const typename K::Mirror &>(op);
+    constexpr int R = Op::Rank(), RA = rank_of_operand<remove_cvref_t<decltype(m.op1_)>>(), RB = rank_of_operand<remove_cvref_t<decltype(m.op2_)>>();
+    const int a = lower(b, m.op1_, axes + (R - RA));
+    const int c = lower(b, m.op2_, axes + (R - RB));
+    constexpr int tol_dt = dtype_of<typename K::inner>::value;
+    const int diff = b.node(MXB_OP_ABS, b.node(MXB_OP_SUB, a, c));
+    const int bound = b.node(MXB_OP_ADD, b.constant(static_cast<double>(m.atol_), 0.0, tol_dt),
+                             b.node(MXB_OP_MUL, b.constant(static_cast<double>(m.rtol_), 0.0, tol_dt), b.node(MXB_OP_ABS, c)));
+    return b.node(MXB_OP_CAST, b.node(MXB_OP_LE, diff, bound), -1, MXB_I32);
   } else {
     b.ok = false;
     return 0;
@@ -235,7 +294,9 @@ template <class T> bool out_desc(const T &t, mxb_out_t &o) {
     o.data = const_cast<void *>(static_cast<const void *>(t.Data()));
     o.dtype = dtype_of<typename T::value_type>::value;
     o.rank = T::Rank();
-    for (int d = 0; d < T::Rank(); ++d) { o.size[d] = t.Size(d); o.stride[d] = t.Stride(d); }
+    if constexpr (T::Rank() > 0) {   // tensor_t<T, 0>::Stride is a static_assert (core/tensor.h:1026)
+      for (int d = 0; d < T::Rank(); ++d) { o.size[d] = t.Size(d); o.stride[d] = t.Stride(d); }
+    }
     return true;
   }
 }
@@ -293,6 +354,18 @@ class b200Executor : public cudaExecutor {
   // one reduction statement; returns false when the reference path has to take it
   template <class Out, class In> bool reduce(int op, Out &dest, const In &in, int ddof = 1) const {
     return reduce_idx<Out, Out, In>(op, dest, nullptr, in, ddof);
+  }
+  // softmax over the trailing n_axes dims of `in` (already permuted so that the softmax axes are innermost); `dest` is
+  // walked in the same permuted order
+  template <class Out, class In> bool softmax_trailing(Out &dest, const In &in, int n_axes) const {
+    if constexpr (!b200_detail::lowerable<In>()) return false;
+    else {
+      b200_detail::Builder b;
+      mxb_out_t out;
+      if (!b200_detail::out_desc(dest, out)) return false;
+      if (!b200_detail::lower_root(b, in)) return false;
+      return !b200_detail::check_or_fallback(mxb_softmax(h_.get(), &b.e, n_axes, &out));
+    }
   }
   template <class Out, class Idx, class In> bool reduce_idx(int op, Out &dest, Idx *idest, const In &in, int ddof) const {
     if constexpr (!b200_detail::lowerable<In>()) return false;
@@ -391,5 +464,36 @@ void argminmax_impl(OutType destmin, TensorIndexType &idestmin, OutType destmax,
 MXB_SHIM_VAR(var, MXB_RED_VAR)
 MXB_SHIM_VAR(stdd, MXB_RED_STDD)
 #undef MXB_SHIM_VAR
+
+// softmax (transforms/reduce.h:362-445).  NOTE the reference's SoftmaxOp::Exec hands softmax_impl the bare STREAM
+// (operators/softmax.h:105-108), so `(out = softmax(x)).run(exec)` cannot be told apart by executor type and keeps
+// running the reference's three passes; these overloads are for callers of softmax_impl and for an overlay of
+// operators/softmax.h that passes `ex` instead of `ex.getStream()`.
+template <typename OutType, typename InType>
+void softmax_impl(OutType dest, const InType &in, const b200Executor &exec) {
+  if (!exec.softmax_trailing(dest, in, InType::Rank())) softmax_impl(dest, in, exec.getStream());
+}
+template <typename OutType, typename InType, typename PermDims>
+void softmax_impl(OutType dest, const InType &in, PermDims dims, const b200Executor &exec) {
+  static_assert(OutType::Rank() == InType::Rank(), "softmax output rank must equal input rank");
+  if constexpr (is_tensor_view_v<OutType>) {
+    const auto perm = detail::getPermuteDims<InType::Rank()>(dims);   // batch dims first, softmax axes last (core/utils.h:96-127)
+    auto pdest = dest.Permute(perm);
+    if (exec.softmax_trailing(pdest, permute(in, perm), static_cast<int>(dims.size()))) return;
+  }
+  softmax_impl(dest, in, dims, exec.getStream());
+}
+
+// allclose (transforms/reduce.h:1321-1331): all(isclose(in1, in2, rtol, atol)) into a rank-0 int tensor, one launch
+template <typename OutType, typename InType1, typename InType2>
+void allclose(OutType dest, const InType1 &in1, const InType2 &in2, double rtol, double atol, const b200Executor &exec) {
+  static_assert(OutType::Rank() == 0, "allclose output must be rank 0");
+  if (!exec.reduce(MXB_RED_ALL, dest, isclose(in1, in2, rtol, atol)))
+    allclose(dest, in1, in2, rtol, atol, static_cast<const cudaExecutor &>(exec));
+}
+template <typename OutType, typename InType1, typename InType2>
+void allclose(OutType dest, const InType1 &in1, const InType2 &in2, double rtol, double atol, b200Executor &exec) {
+  allclose(dest, in1, in2, rtol, atol, static_cast<const b200Executor &>(exec));
+}
 
 }  // namespace matx

@@ -179,6 +179,7 @@ void aot_manifest(std::vector<ManifestItem> *items) {
       it.spec.op = op;
       it.spec.out_dtype = out_dtype;
       it.spec.V = pass == 0 ? policy_vmax(info) : 1;
+      if (family == FAM_EW_TR) it.spec.V = 16 / info.max_leaf_bytes;  // one 16-byte chunk
       it.spec.U = policy_unroll(info, it.spec.V, family);
       it.spec.team = team;
       items->push_back(it);
@@ -232,6 +233,9 @@ void aot_manifest(std::vector<ManifestItem> *items) {
   add(prog_fma3(MXB_F32), FAM_EW, -1, MXB_F32, 0, false);
   for (int d : {MXB_F32, MXB_F64, MXB_C64}) add(prog_vector_add(d), FAM_EW, -1, d, 0, false);
   for (int d : {MXB_F32, MXB_BF16}) add(prog_identity(d), FAM_EW, -1, d, 0, d == MXB_F32);
+  // permuted copies (bench/00_operators/operators.cu:40-59) and the row + column mix
+  for (int d : {MXB_F32, MXB_F64, MXB_C64, MXB_BF16, MXB_I32}) add(prog_identity(d), FAM_EW_TR, -1, d, 0, false);
+  add(prog_vector_add(MXB_F32), FAM_EW_TR, -1, MXB_F32, 0, false);
 }
 
 }  // namespace mxbh

@@ -1206,6 +1206,25 @@ int mxb_elementwise(mxb_handle_t h, const mxb_expr_t *expr_in, const mxb_out_t *
     g.os[d] = out->stride[d];
     g.is[d] = 0;
   }
+  // An elementwise statement may walk its index space in any order: put the dims in the order the OUTPUT is laid out
+  // (largest stride first), so that a permuted left-hand side `(y.Permute(...) = x)` is written along its own
+  // contiguous dim like any other and the transposing family below sees the read side as the permuted one.
+  {
+    bool sorted = true;
+    for (int d = 0; d + 1 < g.n; ++d) if (g.size[d] > 1 && g.size[d + 1] > 1 && g.os[d] < g.os[d + 1]) sorted = false;
+    if (!sorted) {
+      int order[MXB_MAX_RANK];
+      for (int d = 0; d < g.n; ++d) order[d] = d;
+      std::stable_sort(order, order + g.n, [&](int a, int b) { return g.os[a] > g.os[b]; });
+      Group s2 = g;
+      for (int d = 0; d < g.n; ++d) {
+        g.size[d] = s2.size[order[d]];
+        g.os[d] = s2.os[order[d]];
+        g.is[d] = s2.is[order[d]];
+        for (int k = 0; k < e.n_leaves; ++k) g.ls[k][d] = s2.ls[k][order[d]];
+      }
+    }
+  }
   collapse(g, e.n_leaves);
   if (g.n > KMAXD) return fail(MXB_ERR_NOT_SUPPORTED, "view does not collapse to <= 4 dims");
   int64_t N = 1;
@@ -1214,6 +1233,86 @@ int mxb_elementwise(mxb_handle_t h, const mxb_expr_t *expr_in, const mxb_out_t *
 
   const int nl = e.n_leaves;
   const int obytes = dtype_bytes(out->dtype);
+
+  // ---- transposing family: some leaf is unit-stride along a dim that is not the output's -------------------
+  if (g.n >= 2 && g.os[g.n - 1] == 1 && nl > 0 && env_int("MXB_NO_TRANSPOSE", 0) == 0) {
+    const int X = g.n - 1;
+    unsigned nonx = 0;
+    for (int k = 0; k < nl; ++k)
+      if (g.ls[k][X] != 0 && g.ls[k][X] != 1) nonx |= 1u << k;
+    int Y = -1;
+    int64_t best = 0;
+    for (int d = 0; d < X; ++d) {
+      int64_t score = 0;
+      for (int k = 0; k < nl; ++k)
+        if (((nonx >> k) & 1u) && g.ls[k][d] == 1) score += dtype_bytes(e.leaves[k].dtype);
+      if (score > best) { best = score; Y = d; }
+    }
+    bool ok = nonx != 0 && Y >= 0;
+    int eb = 0, staged = 0;
+    for (int k = 0; ok && k < nl; ++k) {
+      if (!((nonx >> k) & 1u)) continue;
+      const int b = dtype_bytes(e.leaves[k].dtype);
+      if (g.ls[k][Y] != 1 || (b != 2 && b != 4 && b != 8) || (eb != 0 && b != eb)) ok = false;
+      eb = b;
+      ++staged;
+    }
+    if (ok && staged > 3) ok = false;                       // shared-memory budget: <= 3 tiles
+    if (ok) {
+      const int V = 16 / eb, T = 16 * V;
+      const int64_t SX = g.size[X], SY = g.size[Y];
+      if (SX * 4 < T || SY * 4 < T) ok = false;             // tiles would be mostly empty: the row walker is as good
+      if (ok && V * obytes > 64) ok = false;
+      int64_t ntx = (SX + T - 1) / T, nty = (SY + T - 1) / T, outer = 1;
+      for (int d = 0; d < X; ++d) if (d != Y) outer *= g.size[d];
+      const int64_t ctas = ntx * nty * outer;
+      if (ok && ctas > 0x7fffffff) ok = false;
+      if (ok) {
+        EwParams p;
+        memset(&p, 0, sizeof p);
+        p.nd = g.n;
+        p.N = N;
+        p.nleaf = nl;
+        for (int d = 0; d < g.n; ++d) {
+          p.sz[d] = g.size[d];
+          p.out.bs[d] = g.os[d];
+          for (int k = 0; k < nl; ++k) p.leaf[k].bs[d] = g.ls[k][d];
+        }
+        for (int k = 0; k < nl; ++k) p.leaf[k].ptr = e.leaves[k].data;
+        p.out.ptr = out->data;
+        p.tr_ydim = Y;
+        p.tr_ymask = nonx;
+        // alignment of the three kinds of vector access (chunk starts are multiples of V along X and Y by construction)
+        bool yvec = true, xvec = true, ovec = aligned_to(out->data, (int64_t)V * obytes) && V * obytes <= 32;
+        for (int d = 0; d < g.n; ++d) if (d != X && g.os[d] % V) ovec = false;
+        for (int k = 0; k < nl; ++k) {
+          const int b = dtype_bytes(e.leaves[k].dtype);
+          if ((nonx >> k) & 1u) {
+            if (!aligned_to(e.leaves[k].data, 16)) yvec = false;
+            for (int d = 0; d < g.n; ++d) if (d != Y && g.ls[k][d] % V) yvec = false;
+          } else if (g.ls[k][X] == 1) {
+            if (!aligned_to(e.leaves[k].data, (int64_t)V * b)) xvec = false;
+            for (int d = 0; d < g.n; ++d) if (d != X && g.ls[k][d] % V) xvec = false;
+          }
+        }
+        p.tr_yvec = yvec ? 1 : 0;
+        p.tr_xvec = xvec ? 1 : 0;
+        p.tr_ovec = ovec ? 1 : 0;
+        fill_consts(e, p.c);
+        KernelSpec spec;
+        spec.family = FAM_EW_TR;
+        spec.op = -1;
+        spec.out_dtype = out->dtype;
+        spec.V = V;
+        spec.U = 1;
+        Kernel k;
+        st = get_kernel(info, spec, &k);
+        if (st != MXB_OK) return st;
+        return launch(h, k, (unsigned)ctas, 256u, (unsigned)(staged * T * 256), p);
+      }
+    }
+  }
+
   int vmax = env_int("MXB_TUNE_V", 0) > 0 ? env_int("MXB_TUNE_V", 0) : policy_vmax(info);
   // the store must fit one instruction too (STG.256 at most)
   while (vmax > 1 && vmax * obytes > 32) vmax >>= 1;
@@ -1490,7 +1589,7 @@ int mxb_debug_codegen(const mxb_expr_t *expr, char *buf, size_t buflen) {
 }
 
 // Build (NVRTC only, no device needed) the kernel a call would use; proves on a CPU box that the
-// generated source compiles for sm_100a.  family: 0 red_inner, 1 red_outer, 2 var_smem, 3 elementwise.
+// generated source compiles for sm_100a.  family: 0 red_inner, 1 red_outer, 2 var_smem, 3 elementwise, 9 transposing elementwise.
 int mxb_debug_compile(const mxb_expr_t *expr, int family, int reduce_op, int out_dtype, int V, int team, char *log, size_t loglen) {
   if (!expr) return fail(MXB_ERR_INVALID, "null expression");
   mxb_expr_t e;
@@ -1502,7 +1601,7 @@ int mxb_debug_compile(const mxb_expr_t *expr, int family, int reduce_op, int out
   if (st != MXB_OK) return fail(st, err);
   KernelSpec spec;
   spec.family = family;
-  spec.op = (family == FAM_EW || family == FAM_SM_GROUP || family == FAM_SM_REG) ? -1 : kernel_op(reduce_op);
+  spec.op = (family == FAM_EW || family == FAM_EW_TR || family == FAM_SM_GROUP || family == FAM_SM_REG) ? -1 : kernel_op(reduce_op);
   spec.out_dtype = out_dtype;
   spec.V = V > 0 ? V : policy_vmax(info);
   spec.U = policy_unroll(info, spec.V, family);

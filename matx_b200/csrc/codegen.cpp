@@ -314,6 +314,13 @@ int analyze_expr(const mxb_expr_t *e, ExprInfo *info, std::string *err) {
     s << "    mxb::ldleaf<" << dtype_ctype(e->leaves[k].dtype) << ", V, UNIT>(r.x" << k << ", base[" << k << "], j, inner[" << k << "]);\n";
   if (e->n_leaves == 0) s << "    (void)r; (void)base; (void)inner; (void)j;\n";
   s << "  }\n";
+  // transposing family: leaf k comes from a shared-memory tile (bit k of ymask) or straight from global memory
+  s << "  template <int V> static __device__ __forceinline__ void loadmix(Regs<V> &r, const char *const *gp, const mxb::i64 *ginner, const char *const *sp, unsigned ymask, bool vec, int n) {\n";
+  for (int k = 0; k < e->n_leaves; ++k)
+    s << "    if ((ymask >> " << k << ") & 1u) mxb::ldtile<" << dtype_ctype(e->leaves[k].dtype) << ", V>(r.x" << k << ", sp[" << k << "]); else mxb::ldrow<"
+      << dtype_ctype(e->leaves[k].dtype) << ", V>(r.x" << k << ", gp[" << k << "], ginner[" << k << "], vec, n);\n";
+  s << "    (void)r; (void)gp; (void)ginner; (void)sp; (void)ymask; (void)vec; (void)n;\n";
+  s << "  }\n";
   s << "  template <int V> static __device__ __forceinline__ value_type eval(const Regs<V> &r, int v, const mxb::ConstDev &c) {\n";
   s << "    (void)r; (void)v; (void)c;\n";
   s << body.str();
@@ -340,6 +347,7 @@ int policy_unroll(const ExprInfo &info, int V, int family) {
   const int bytes = V * info.max_leaf_bytes;  // widest load of one step
   if (family == FAM_RED_OUTER) return 4;
   if (family == FAM_VAR_REG || family == FAM_VAR_TMA || family == FAM_VAR_GROUP || family == FAM_SM_GROUP || family == FAM_SM_REG) return 1;
+  if (family == FAM_EW_TR) return 1;
   if (family == FAM_VAR_SMEM) return bytes >= 32 ? 4 : 8;
   if (family == FAM_EW) return bytes >= 32 ? (info.nleaf <= 2 ? 2 : 1) : (info.nleaf <= 2 ? 4 : 2);
   return bytes >= 32 ? 2 : (info.nleaf <= 2 ? 4 : 2);
@@ -347,7 +355,7 @@ int policy_unroll(const ExprInfo &info, int V, int family) {
 
 std::string kernel_key(const ExprInfo &info, const KernelSpec &s) {
   std::ostringstream k;
-  static const char *fam[] = {"red_inner", "red_outer", "var_smem", "ew", "var_reg", "var_tma", "var_group", "softmax_group", "softmax_reg"};
+  static const char *fam[] = {"red_inner", "red_outer", "var_smem", "ew", "var_reg", "var_tma", "var_group", "softmax_group", "softmax_reg", "ew_tr"};
   k << fam[s.family] << "|" << info.name << "|" << (s.op >= 0 ? reduce_op_name(s.op) : "-") << "|" << dtype_name(s.out_dtype)
     << "|V" << s.V << "|U" << s.U << "|T" << s.team;
   return k.str();
@@ -426,6 +434,11 @@ int kernel_wrapper_src(const ExprInfo &info, const KernelSpec &s, const std::str
     case FAM_EW:
       k << "extern \"C\" __global__ void __launch_bounds__(256) " << symbol
         << "(const __grid_constant__ mxb::EwParams p) { mxb::ew_body<" << E << ", " << O << ", " << VU << ">(p); }\n";
+      break;
+    case FAM_EW_TR:
+      if (s.V != 2 && s.V != 4 && s.V != 8) return fail("ew_tr moves 16-byte chunks of 2-, 4- or 8-byte elements");
+      k << "extern \"C\" __global__ void __launch_bounds__(256) " << symbol
+        << "(const __grid_constant__ mxb::EwParams p) { mxb::ew_tr_body<" << E << ", " << O << ", " << (16 / s.V) << ">(p); }\n";
       break;
     default: return fail("unknown kernel family");
   }

@@ -126,6 +126,12 @@ struct EwParams {
   LeafDev leaf[KMAXLEAF]; // bs[] used
   OutDev out;
   ConstDev c;
+  // transposing family (ew_tr) only
+  int tr_ydim;        // the dim the staged leaves are unit-stride along
+  unsigned tr_ymask;  // bit k: leaf k is staged through shared memory
+  int tr_yvec;        // staged leaves may be read in aligned 16-byte chunks
+  int tr_xvec;        // X-walking leaves may be read in aligned V-element vectors
+  int tr_ovec;        // the output may be written in aligned V-element vectors
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -313,33 +319,36 @@ template <> __device__ __forceinline__ bool nonzero<cfloat>(cfloat x) { return x
 // ------------------------------------------------------------------------------------------------
 // normcdf(x) for fp32, hand-written: the CUDA library's normcdff costs ~63 SASS instructions per call and the fused
 // Black-Scholes chain (examples/black_scholes.cu:122-138, two calls per option) is instruction-issue bound on B200, not
-// HBM bound, with it.  This one is ~28: with z = min(|x|, 14.5),
-//   Phi(-z) = exp(-z^2/2) * Q(z),   Q(z) = erfcx(z/sqrt2)/2 = u * P(t),  u = 1/(z+4),  t = (z-4)/(z+4) = 1 - 8u
-// P = degree-9 minimax fit (relative error 9e-9 on [0, 14.6], fitted here from scipy's erfcx, not copied from
-// anywhere); exp(-z^2/2) = ex2(a_hi) * (1 + ln2 * a_lo) with the rounding residue of z*z and of the product with
-// -0.5*log2(e) carried in a_lo, so the tail keeps its RELATIVE accuracy (|x| = 10: a = -72, an uncompensated product
-// would be off by 3e-6).  Measured against fp64 truth over [-14.5, 9]: mean 1.1 ulp, max ~9 ulp with MUFU.RCP/EX2 at
-// their documented 1 / 2 ulp (the library function documents 5 ulp); NaN propagates (min.NaN), +-inf give 1 / 0,
-// results below 2^-126 flush to zero (|x| > 13.2, where the library returns denormals).
+// HBM bound, with it.  This one is ~29: with z = min(|x|, 14.5),
+//   Phi(-z) = exp(-z^2/2) * Q(z),   Q(z) = erfcx(z/sqrt2)/2 = u * P(t),  u = 1/(z+2),  t = (z-2)/(z+2) = 1 - 4u
+// P = degree-10 minimax fit (relative error 2.4e-8 on [0, 14.6], fitted here from scipy's erfcx, not copied from
+// anywhere).  The pole offset 2 (not a larger one that would need fewer terms) keeps the map z -> u well conditioned
+// near z = 0, where half an ulp of u is worth (z+2) * 2^-25 in z.  exp(-z^2/2) = ex2(a_hi) * (1 + ln2 * a_lo) with
+// the rounding residue of z*z and of the product with -0.5*log2(e) carried in a_lo, so the tail keeps its RELATIVE
+// accuracy (|x| = 10: a = -72, an uncompensated product would be off by 3e-6).  Measured on B200 against fp64 truth
+// (tools/math_accuracy.py, profiles/): see DESIGN.md section 4; the library function documents 5 ulp.  NaN
+// propagates (min.NaN), +-inf give 1 / 0, results below 2^-126 flush to zero (|x| > 13.2, where the library returns
+// denormals).
 __device__ __forceinline__ float f_normcdf(float x) {
   float z;
   asm("min.NaN.f32 %0, %1, %2;" : "=f"(z) : "f"(fabsf(x)), "f"(14.5f));
   const float s = z * z, sl = fmaf(z, z, -s);
-  const float d = z + 4.0f;
+  const float d = z + 2.0f;
   float u;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(u) : "f"(d));
   u = fmaf(u, fmaf(-d, u, 1.0f), u);  // one Newton step: u = 1/d to half an ulp
-  const float t = fmaf(-8.0f, u, 1.0f);
-  float p = -1.324342156e-04f;
-  p = fmaf(p, t, 1.783698972e-04f);
-  p = fmaf(p, t, 1.569589484e-03f);
-  p = fmaf(p, t, -3.512077034e-03f);
-  p = fmaf(p, t, -7.525003050e-03f);
-  p = fmaf(p, t, 6.040376425e-02f);
-  p = fmaf(p, t, -1.865234822e-01f);
-  p = fmaf(p, t, 3.871369064e-01f);
-  p = fmaf(p, t, -6.078965664e-01f);
-  p = fmaf(p, t, 7.552851439e-01f);
+  const float t = fmaf(-4.0f, u, 1.0f);
+  float p = -7.689554332e-05f;
+  p = fmaf(p, t, 2.991535075e-05f);
+  p = fmaf(p, t, 7.246770547e-04f);
+  p = fmaf(p, t, 8.852431783e-04f);
+  p = fmaf(p, t, -1.890715910e-03f);
+  p = fmaf(p, t, -6.751993671e-03f);
+  p = fmaf(p, t, -4.832238483e-04f);
+  p = fmaf(p, t, 3.672166169e-02f);
+  p = fmaf(p, t, 2.879839949e-02f);
+  p = fmaf(p, t, -3.314045668e-01f);
+  p = fmaf(p, t, 6.724079847e-01f);
   const float q = p * u;
   const float C = -0.72134752044448170368f;                       // -0.5 * log2(e)
   const float CL = (float)(-0.72134752044448170368 - (double)C);  // and what fp32 dropped of it
@@ -1869,6 +1878,168 @@ __device__ __forceinline__ void softmax_reg_body(const RedParams &p) {
   pdl_prologue();
   if (p.all_unit) softmax_reg_body_impl<E, OutT, V, IPT, true>(p);
   else softmax_reg_body_impl<E, OutT, V, IPT, false>(p);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Transposing elementwise kernel: out(idx) = expr(idx) when some leaves are unit-stride along a dim Y that is NOT
+// the output's unit-stride dim X — permuted copies `(y = x.Permute(...)).run()` and expressions that mix row- and
+// column-walking operands (`a + permute(b)`).  The reference's generic kernel (executors/kernel.h:41-223) walks the
+// output index and reads such a leaf one element per 32-byte sector; its own answer is a separate tiled transpose
+// for the 2-D case only (kernels/transpose.cuh:28).  Here every CTA owns a TX x TY tile of the (X, Y) plane of one
+// outer index:
+//   phase 1  the Y-walking leaves are read along Y (16-byte chunks, a warp covers 4 rows x 128 B) and written
+//            element-wise into shared memory in [y][x] order;
+//   phase 2  threads walk X: a 16-byte chunk of every staged leaf comes back with one LDS.128, the X-walking leaves
+//            are loaded straight from global memory, the expression is evaluated and V results leave in one store
+//            (a warp covers 2 rows x 256 B).
+// Shared-memory layout per staged leaf: TY rows of 256 bytes (TX = 16 chunks of V = 16/EB elements), chunk index
+// XOR-swizzled with the row's own chunk number (y / V) & 15, which makes the phase-1 element stores and the phase-2
+// 16-byte loads bank-conflict free for EB = 2, 4, 8.  HBM traffic = algorithmic bytes (every sector fully used).
+// ------------------------------------------------------------------------------------------------
+template <int EB> struct TrTile {
+  enum { V = 16 / EB, TX = 16 * V, TY = 16 * V, BYTES = TY * 256 };
+};
+
+__device__ __forceinline__ void lds16(void *d, const void *smem_generic) {
+  const u32 a = (u32)__cvta_generic_to_shared(smem_generic);
+  u32 *o = (u32 *)d;
+  asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(o[0]), "=r"(o[1]), "=r"(o[2]), "=r"(o[3]) : "r"(a));
+}
+// leaf read from shared memory (one 16-byte chunk = V elements)
+template <class T, int V, bool CHUNK = (sizeof(T) * V == 16)> struct LdTile {
+  static __device__ __forceinline__ void go(Vec<T, V> &r, const char *s) { lds16(&r, s); }
+};
+template <class T, int V> struct LdTile<T, V, false> {  // a leaf of another element size is never staged (host rule)
+  static __device__ __forceinline__ void go(Vec<T, V> &, const char *) {}
+};
+template <class T, int V> __device__ __forceinline__ void ldtile(Vec<T, V> &r, const char *s) { LdTile<T, V>::go(r, s); }
+// leaf that walks X itself: V elements at p, p+inner, ... (inner is 0 or 1 in practice); `vec` = one aligned vector
+// load is legal, `n` = how many of the V elements exist
+template <class T, int V> __device__ __forceinline__ void ldrow(Vec<T, V> &r, const void *base, i64 inner, bool vec, int n) {
+  const T *p = (const T *)base;
+  if (inner == 0) {
+    ldsplat<T, V>(r, p);
+  } else if (vec && n == V && inner == 1) {
+    ldv<T, V>(r, p);
+  } else {
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      if (v < n) { Vec<T, 1> s; LdBytes<(int)sizeof(T)>::ld(&s, p + (i64)v * inner); r.v[v] = s.v[0]; }
+      else r.v[v] = r.v[0];
+    }
+  }
+}
+
+template <class E, class OutT, int EB>
+__device__ __forceinline__ void ew_tr_body(const EwParams &p) {
+  typedef TrTile<EB> TT;
+  constexpr int V = TT::V, TX = TT::TX, TY = TT::TY;
+  extern __shared__ __align__(16) unsigned char tr_smem[];
+  pdl_prologue();
+  const int nd = p.nd, ydim = p.tr_ydim, xdim = nd - 1;
+  const i64 SX = p.sz[xdim], SY = p.sz[ydim];
+  const i64 ntx = (SX + TX - 1) / TX, nty = (SY + TY - 1) / TY;
+  // CTA -> (outer index, x tile, y tile), y tiles fastest: neighbouring CTAs read neighbouring 256-byte runs
+  i64 b = blockIdx.x;
+  const i64 ty = b % nty; b /= nty;
+  const i64 tx = b % ntx; b /= ntx;
+  i64 lofs[E::NL], oofs = 0;
+#pragma unroll
+  for (int k = 0; k < E::NL; ++k) lofs[k] = 0;
+#pragma unroll
+  for (int d = KMAXD - 1; d >= 0; --d) {
+    if (d < nd - 1 && d != ydim) {
+      const i64 q = b / p.sz[d], i = b - q * p.sz[d];
+      b = q;
+#pragma unroll
+      for (int k = 0; k < E::NL; ++k) lofs[k] += i * p.leaf[k].bs[d];
+      oofs += i * p.out.bs[d];
+    }
+  }
+  const i64 x0 = tx * TX, y0 = ty * TY;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const unsigned ymask = p.tr_ymask;
+
+  // ---- phase 1: stage the Y-walking leaves ----
+  {
+    int slot = 0;
+#pragma unroll
+    for (int k = 0; k < E::NL; ++k) {
+      if (!((ymask >> k) & 1u)) continue;
+      unsigned char *tile = tr_smem + (size_t)slot * TT::BYTES;
+      ++slot;
+      const char *g = (const char *)p.leaf[k].ptr + (lofs[k] + y0) * EB;   // stride along Y is 1
+      const i64 sx = p.leaf[k].bs[xdim];
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const int unit = warp + 8 * i;
+        const int x = (unit >> 1) * 4 + (lane >> 3);
+        const int cy = (unit & 1) * 8 + (lane & 7);
+        const i64 gx = x0 + x, gy = y0 + (i64)cy * V;
+        if (gx >= SX || gy >= SY) continue;
+        const char *src = g + (gx * sx + (i64)cy * V) * EB;
+        unsigned char e[16];
+        const int n = (int)((SY - gy) < (i64)V ? (SY - gy) : (i64)V);
+        if (p.tr_yvec && n == V) {
+          LdBytes<16>::ld(e, src);
+        } else {
+#pragma unroll
+          for (int j = 0; j < V; ++j) if (j < n) LdBytes<EB>::ld(e + j * EB, src + j * EB);
+        }
+        // element (x, cy*V + j) -> row cy*V + j, chunk (x / V) ^ cy, slot x % V
+        const int col = (((x / V) ^ cy) * 16) + (x % V) * EB;
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+          unsigned char *dst = tile + (size_t)(cy * V + j) * 256 + col;
+          if (EB == 2) *(unsigned short *)dst = *(const unsigned short *)(e + j * EB);
+          else if (EB == 4) *(u32 *)dst = *(const u32 *)(e + j * EB);
+          else *(unsigned long long *)dst = *(const unsigned long long *)(e + j * EB);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+  // ---- phase 2: walk X, evaluate, store ----
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const int unit = warp + 8 * i;
+    const int yy = unit * 2 + (lane >> 4);
+    const int cx = lane & 15;
+    const i64 gy = y0 + yy, gx = x0 + (i64)cx * V;
+    if (gy >= SY || gx >= SX) continue;
+    const int n = (int)((SX - gx) < (i64)V ? (SX - gx) : (i64)V);
+    const char *sp[E::NL];
+    const char *gp[E::NL];
+    i64 ginner[E::NL];
+    int slot = 0;
+#pragma unroll
+    for (int k = 0; k < E::NL; ++k) {
+      if ((ymask >> k) & 1u) {
+        sp[k] = (const char *)tr_smem + (size_t)slot * TT::BYTES + (size_t)yy * 256 + ((cx ^ ((yy / V) & 15)) * 16);
+        gp[k] = nullptr;
+        ginner[k] = 0;
+        ++slot;
+      } else {
+        sp[k] = nullptr;
+        ginner[k] = p.leaf[k].bs[xdim];
+        gp[k] = (const char *)p.leaf[k].ptr + (lofs[k] + gy * p.leaf[k].bs[ydim] + gx * ginner[k]) * E::leaf_bytes(k);
+      }
+    }
+    typename E::template Regs<V> r;
+    E::template loadmix<V>(r, gp, ginner, sp, ymask, p.tr_xvec != 0, n);
+    Vec<OutT, V> o;
+#pragma unroll
+    for (int v = 0; v < V; ++v) o.v[v] = cvt<OutT>(E::template eval<V>(r, v, p.c));
+    OutT *op = (OutT *)p.out.ptr + oofs + gy * p.out.bs[ydim] + gx;
+    if (p.tr_ovec && n == V) {
+      StBytes<(int)sizeof(OutT) * V>::st(op, &o);
+    } else {
+#pragma unroll
+      for (int v = 0; v < V; ++v) if (v < n) op[v] = o.v[v];
+    }
+  }
 }
 
 }  // namespace mxb

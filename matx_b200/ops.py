@@ -23,7 +23,10 @@ from typing import Optional, Sequence
 
 from . import _abi as A
 
+import builtins
+
 matxKeepDim = -1  # clone(): keep this input dim
+builtins_min = builtins.min  # this module defines its own min / max / abs / sum / any / all (the MatX names)
 
 _TORCH_DTYPES = None
 
@@ -257,6 +260,45 @@ normcdf, isnan, isinf, floor, ceil, expj = (_un(o) for o in (A.OP_NORMCDF, A.OP_
 round_ = _un(A.OP_ROUND)
 
 
+class DiagOp(Op):
+    """diag(op, k) of a rank >= 2 operand (operators/diag.h:145-190): the k-th diagonal of the last two dims; the result
+    has one dim fewer, its last dim walks rows and columns together (one stride = s_row + s_col)."""
+
+    def __init__(self, a: Op, k: int = 0):
+        if len(a.shape) < 2:
+            raise ValueError("diag: operand rank must be >= 2 (building a matrix from a vector is not on this path)")
+        rows, cols = a.shape[-2], a.shape[-1]
+        # the reference sizes the result as min(cols, rows - k) / min(cols + k, rows) (operators/diag.h:253-268) while it
+        # INDEXES (i, i + k) / (i - k, i); the two agree for square matrices.  Where its size would run off the matrix
+        # (non-square, k != 0) this mirror refuses instead of reading out of bounds.
+        valid = builtins_min(rows, cols - k) if k >= 0 else builtins_min(rows + k, cols)
+        n = builtins_min(cols, rows - k) if k > 0 else (builtins_min(cols + k, rows) if k < 0 else valid)
+        if n <= 0 or n > valid:
+            raise ValueError("diag: diagonal %d of a %dx%d matrix is outside it (or the reference's size rule is)" % (k, rows, cols))
+        if k != 0 and not isinstance(a, Tensor):
+            raise A.MatxB200Error(A.ERR_NOT_SUPPORTED, "diag(expression, k != 0): take the diagonal of the tensors instead")
+        self.a, self.k = a, int(k)
+        self.shape = tuple(a.shape[:-2]) + (n,)
+        self.dtype_hint = a.dtype_hint
+
+
+def diag(a, k: int = 0):
+    if isinstance(a, Tensor):   # a strided view, like every other view on this path
+        d = DiagOp(a, k)
+        off = k * a.strides[-1] if k >= 0 else -k * a.strides[-2]
+        return Tensor(a.data_ptr + off * A.DTYPE_BYTES[a.dtype], a.dtype, d.shape, tuple(a.strides[:-2]) + (a.strides[-2] + a.strides[-1],), a._keep)
+    return DiagOp(a, k)
+
+
+def isclose(a, b, rtol: float = 1e-5, atol: float = 1e-8):
+    """isclose(a, b, rtol, atol) (operators/isclose.h:40-130): int(|a - b| <= atol + rtol * |b|), tolerances in the
+    operands' inner type."""
+    a = _wrap(a, b if isinstance(b, Op) else None)
+    b = _wrap(b, a)
+    inner = A.F64 if b.dtype_hint == A.F64 else A.F32
+    return as_type(abs(a - b) <= Const(float(atol), inner) + Const(float(rtol), inner) * abs(b), A.I32)
+
+
 def pow(a, b): return BinOp(A.OP_POW, a, b)  # noqa: A001
 def fmod(a, b): return BinOp(A.OP_MOD, a, b)
 def atan2(a, b): return BinOp(A.OP_ATAN2, a, b)
@@ -295,6 +337,16 @@ def argmin(a, dims=None): return ReduceExpr(A.RED_ARGMIN, a, dims)
 def any(a, dims=None): return ReduceExpr(A.RED_ANY, a, dims)        # noqa: A001
 def all(a, dims=None): return ReduceExpr(A.RED_ALL, a, dims)        # noqa: A001
 def prod(a, dims=None): return ReduceExpr(A.RED_PROD, a, dims)
+
+
+def trace(a): return ReduceExpr(A.RED_SUM, diag(a), None)          # trace_impl, transforms/reduce.h:1505-1511
+
+
+def allclose(dest: "Tensor", a, b, rtol: float, atol: float, ex: "CudaExecutor") -> None:
+    """allclose(dest, in1, in2, rtol, atol, exec) (transforms/reduce.h:1321-1331): runs immediately, rank-0 int output."""
+    if len(dest.shape) != 0:
+        raise TypeError("allclose output must be rank 0")
+    dest.set(all(isclose(a, b, rtol, atol))).run(ex)
 
 
 class SoftmaxExpr(ReduceExpr):
@@ -379,6 +431,8 @@ class _Lowering:
             for i, d in enumerate(node.dims):
                 child_axes[d] = axes[i]
             r = self.lower(node.a, child_axes)
+        elif isinstance(node, DiagOp):
+            r = self.lower(node.a, list(axes[:-1]) + [axes[-1], axes[-1]])   # rows and columns walk the same root dim
         elif isinstance(node, CloneOp):
             child_axes = [axes[i] for i, c in enumerate(node.cdims) if c == matxKeepDim]
             r = self.lower(node.a, child_axes)

@@ -170,6 +170,55 @@ static int run_checks() {
     report("sum(permute(t,{2,0,1}),{2}) bf16 vs reference", em <= er + 1.0 / 256 && *b200.last_kernel(), b200.last_kernel(), em);
     report("sum(permute(t,{2,0,1}),{2}) bf16 vs fp64 truth (2^-8)", et <= 1.0 / 256, b200.last_kernel(), et);
   }
+  // ---- trace, allclose, softmax_impl, permuted copy ----
+  {
+    const index_t n = 512;
+    auto m = make_tensor<float>({n, n});
+    fill_uniform(m, 21, -1.f, 1.f);
+    auto s1 = make_tensor<float>({}), s2 = make_tensor<float>({});
+    (s1 = trace(m)).run(ref); (s2 = trace(m)).run(b200); ref.sync();
+    report("trace(m) = sum(diag(m))", std::fabs(s2() - s1()) <= 1e-5 * std::max(1.f, std::fabs(s1())) && *b200.last_kernel(), b200.last_kernel(), std::fabs(s2() - s1()));
+    (s1 = sum(diag(m * m))).run(ref); (s2 = sum(diag(m * m))).run(b200); ref.sync();
+    report("sum(diag(m*m)) fused", std::fabs(s2() - s1()) <= 1e-5 * std::fabs(s1()) && *b200.last_kernel(), b200.last_kernel(), std::fabs(s2() - s1()));
+    auto d1 = make_tensor<float>({n - 3}), d2 = make_tensor<float>({n - 3});
+    (d1 = diag(m, 3) * 2.f).run(ref); (d2 = diag(m, 3) * 2.f).run(b200); ref.sync();
+    report("diag(m,3)*2 (off-diagonal view)", max_rel(d2, d1, n - 3) == 0 && *b200.last_kernel(), b200.last_kernel());
+
+    auto m2 = make_tensor<float>({n, n});
+    (m2 = m).run(ref); ref.sync();
+    m2(100, 7) += 1e-3f;
+    auto f1 = make_tensor<int>({}), f2 = make_tensor<int>({});
+    allclose(f1, m, m2, 1e-5, 1e-8, ref); allclose(f2, m, m2, 1e-5, 1e-8, b200); ref.sync();
+    report("allclose(m, m2) = 0", f1() == 0 && f2() == 0 && *b200.last_kernel(), b200.last_kernel());
+    allclose(f1, m, m2, 1e-1, 1e-2, ref); allclose(f2, m, m2, 1e-1, 1e-2, b200); ref.sync();
+    report("allclose(m, m2, loose) = 1", f1() == 1 && f2() == 1 && *b200.last_kernel(), b200.last_kernel());
+
+    auto p1 = make_tensor<float>({n, n}), p2 = make_tensor<float>({n, n});
+    softmax_impl(p1, m, cuda::std::array<int, 1>{1}, stream);
+    softmax_impl(p2, m, cuda::std::array<int, 1>{1}, b200);
+    ref.sync();
+    double em = 0;
+    for (index_t i = 0; i < n; ++i) for (index_t j = 0; j < n; ++j) em = std::max(em, std::fabs((double)p1(i, j) - p2(i, j)) / p1(i, j));
+    report("softmax_impl(p, m, {1}, exec) one launch", em <= 1e-5 && !strncmp(b200.last_kernel(), "softmax", 7), b200.last_kernel(), em);
+    softmax_impl(p1, m, cuda::std::array<int, 1>{0}, stream);
+    softmax_impl(p2, m, cuda::std::array<int, 1>{0}, b200);
+    ref.sync();
+    em = 0;
+    for (index_t i = 0; i < n; ++i) for (index_t j = 0; j < n; ++j) em = std::max(em, std::fabs((double)p1(i, j) - p2(i, j)) / p1(i, j));
+    report("softmax_impl(p, m, {0}, exec) column softmax", em <= 1e-5 && *b200.last_kernel(), b200.last_kernel(), em);
+
+    // permuted copy: bench/00_operators/operators.cu:40-59, scaled down
+    auto x = make_tensor<float>({50, 40, 6, 30});
+    std::mt19937 g(23);
+    std::uniform_real_distribution<float> u(-1.f, 1.f);
+    for (index_t a = 0; a < 50; ++a) for (index_t b = 0; b < 40; ++b) for (index_t c = 0; c < 6; ++c) for (index_t d = 0; d < 30; ++d) x(a, b, c, d) = u(g);
+    auto y1 = make_tensor<float>({30, 50, 6, 40}), y2 = make_tensor<float>({30, 50, 6, 40});
+    (y1 = x.Permute({3, 0, 2, 1})).run(ref); (y2 = x.Permute({3, 0, 2, 1})).run(b200); ref.sync();
+    bool same = true;
+    for (index_t a = 0; a < 30; ++a) for (index_t b = 0; b < 50; ++b) for (index_t c = 0; c < 6; ++c) for (index_t d = 0; d < 40; ++d)
+      same = same && y1(a, b, c, d) == y2(a, b, c, d) && y2(a, b, c, d) == x(b, d, c, a);
+    report("(y = x.Permute({3,0,2,1})) tiled transpose", same && !strncmp(b200.last_kernel(), "ew_tr|", 6), b200.last_kernel());
+  }
   // ---- a node the shim does not lower falls back to the reference, same answer ----
   {
     auto a = make_tensor<float>({1000});
@@ -253,6 +302,19 @@ static void run_bench() {
     };
     line("C4 fp32 2^28", "black_scholes", 6.0 * n * 4, time_ms(stream, 5, [&] { bs(ref); }), time_ms(stream, 5, [&] { bs(b200); }));
     line("vector_add fp32 2^28", "out = S + K", 3.0 * n * 4, time_ms(stream, 5, [&] { (out = S + K).run(ref); }), time_ms(stream, 5, [&] { (out = S + K).run(b200); }));
+  }
+  {  // permuted copy, the reference's own benchmark (bench/00_operators/operators.cu:40-59)
+    auto x = make_tensor<float>({1000, 200, 6, 300}, MATX_DEVICE_MEMORY);
+    auto y = make_tensor<float>({300, 1000, 6, 200}, MATX_DEVICE_MEMORY);
+    (x = random<float>({1000, 200, 6, 300}, UNIFORM)).run(ref);
+    line("permute fp32 {1000,200,6,300}", "y = x.Permute({3,0,2,1})", 2.0 * 4 * 1000 * 200 * 6 * 300, time_ms(stream, 3, [&] { (y = x.Permute({3, 0, 2, 1})).run(ref); }),
+         time_ms(stream, 5, [&] { (y = x.Permute({3, 0, 2, 1})).run(b200); }));
+    auto a = make_tensor<float>({8192, 8192}, MATX_DEVICE_MEMORY), t = make_tensor<float>({8192, 8192}, MATX_DEVICE_MEMORY);
+    (a = random<float>({8192, 8192}, UNIFORM)).run(ref);
+    line("transpose fp32 8192x8192", "t = a.Permute({1,0})", 2.0 * 4 * 8192 * 8192, time_ms(stream, 5, [&] { (t = a.Permute({1, 0})).run(ref); }),
+         time_ms(stream, 5, [&] { (t = a.Permute({1, 0})).run(b200); }));
+    line("transpose fp32 8192x8192", "t = transpose_matrix(a) (reference's tiled kernel)", 2.0 * 4 * 8192 * 8192, time_ms(stream, 5, [&] { (t = transpose_matrix(a)).run(ref); }),
+         time_ms(stream, 5, [&] { (t = a.Permute({1, 0})).run(b200); }));
   }
   {  // C5
     const index_t d = 1024;

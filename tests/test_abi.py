@@ -109,12 +109,12 @@ def test_named_programs_are_ahead_of_time():
 
 @pytest.mark.parametrize("family,op,team", [(0, A.RED_SUM, 0), (0, A.RED_ARGMIN, 1), (1, A.RED_MAX, 0), (2, A.RED_VAR, 0),
                                             (4, A.RED_VAR, 4), (3, -1, 0), (6, A.RED_VAR, 2), (7, -1, 2), (8, -1, 4),
-                                            (0, 11, 0), (1, 11, 0)])   # 7 / 8: softmax in registers; op 11: its statistics pass
+                                            (0, 11, 0), (1, 11, 0), (9, -1, 0)])   # 7 / 8: softmax in registers; op 11: its statistics pass; 9: transposing elementwise
 def test_generated_kernels_compile_for_sm100a(family, op, team):
     a = np_tensor(np.zeros((4, 8), np.float32))
     h = np_tensor(np.zeros((4, 8), np.uint16), A.BF16)
     expr = mx.sqrt(mx.abs(a)) * h - mx.tanh(a) / 3.0 + mx.as_type(mx.floor(a), A.I32)
-    e = mx.lower_reduce(mx.ReduceExpr(max(op, 0), expr, [1])) if family != 3 else mx.lower_elementwise(expr)
+    e = mx.lower_reduce(mx.ReduceExpr(max(op, 0), expr, [1])) if family not in (3, 9) else mx.lower_elementwise(expr)
     log = C.create_string_buffer(1 << 16)
     st = A.lib.mxb_debug_compile(C.byref(e), family, op, A.F32, 0, team, log, len(log))
     assert st == A.OK, (A.lib.mxb_last_error(), log.value.decode()[:2000])

@@ -137,8 +137,11 @@ def test_black_scholes_config4_shape(oracle):
     T = rng.uniform(0.1, 2, n).astype(np.float32)
     got, want, k = G.run_elementwise(oracle, lambda k_, s_, v_, r_, t_: black_scholes(s_, k_, v_, r_, t_), [K, S, V, r, T], (n,), A.F32)
     assert k.startswith("ew|") and k.endswith("aot") and "|V4" in k, k
-    # prices span 1e-20 .. 90; normcdf tails and the S*N(d1) - K*e^{-rT}*N(d2) cancellation amplify ulp-level
-    # differences between libdevice and glibc, so the bar is absolute on the price scale
-    assert np.max(np.abs(got - want)) <= 2e-4
-    big = want > 1.0
+    # prices span 1e-20 .. 90.  The price is a DIFFERENCE of two terms of size ~S, so an ulp-level difference in normcdf /
+    # log / exp (the engine's fp32 functions vs glibc here, vs libdevice in the reference) is worth ~1e-7 * S in the
+    # price whatever the price is: the bar is 1e-6 relative to the minuend's scale S, and the north star's 1e-5
+    # relative on the price itself where the subtraction does not cancel (price >= S/4).
+    assert np.max(np.abs(got - want) / S) <= 1e-6
+    big = want >= 0.25 * S
+    assert big.sum() > 1000
     assert np.max(np.abs(got[big] - want[big]) / want[big]) <= 1e-5

@@ -376,3 +376,50 @@ def test_column_reductions_of_tall_matrices(oracle, shape):
     truth = y.astype(np.float64).sum(0)
     assert np.max(np.abs(got - truth) / truth) <= 1e-5, k   # the sequential fp32 oracle is the less accurate side here
     assert np.max(np.abs(want - truth) / truth) <= 5e-3
+
+
+# ---- trace / diag / isclose / allclose (transforms/reduce.h:1321-1331,1505-1511; operators/diag.h, isclose.h) ----
+def test_trace_and_diag(oracle):
+    rng = np.random.default_rng(41)
+    for n in (1, 7, 256, 1000):
+        m = rng.standard_normal((n, n)).astype(np.float32)
+        got, _, want, _, k = G.run_reduce(oracle, lambda t: mx.trace(t), [m], A.F32)
+        assert abs(float(got) - float(want)) <= 1e-5 * max(1.0, float(np.sum(np.abs(np.diag(m)))))
+        assert abs(float(got) - float(np.trace(m.astype(np.float64)))) <= 1e-5 * max(1.0, float(np.sum(np.abs(np.diag(m)))))
+    # batched: trace of every matrix of a stack, and of a fused expression
+    s = rng.standard_normal((9, 33, 33)).astype(np.float32)
+    got, _, want, _, _ = G.run_reduce(oracle, lambda t: mx.sum(mx.diag(t * t), [1]), [s], A.F32)
+    ref = np.einsum("bii->b", s.astype(np.float64) ** 2)
+    assert np.allclose(got, want, rtol=1e-5) and np.allclose(got, ref, rtol=1e-5)
+    # off-diagonals of a square matrix as views
+    m = rng.standard_normal((64, 64)).astype(np.float32)
+    for kk in (1, -3):
+        got, want, _ = G.run_elementwise(oracle, lambda t: mx.diag(t, kk) * 1.0, [m], (64 - abs(kk),), A.F32)
+        assert np.array_equal(got, np.diag(m, kk)) and np.array_equal(got, want)
+    with pytest.raises(ValueError):
+        mx.diag(mx.make_tensor(__import__("torch").zeros(7, 5, device="cuda")), 1)
+
+
+def test_isclose_allclose(oracle):
+    import torch
+    rng = np.random.default_rng(42)
+    a = rng.standard_normal((300, 70)).astype(np.float32)
+    b = a.copy()
+    b[17, 3] += 1e-3
+    got, want, _ = G.run_elementwise(oracle, lambda x, y: mx.isclose(x, y, 1e-5, 1e-8), [a, b], a.shape, A.I32)
+    assert np.array_equal(got, want)
+    assert np.array_equal(got.astype(bool), np.abs(a - b) <= np.float32(1e-8) + np.float32(1e-5) * np.abs(b))
+    ex = G.executor()
+    da, db = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    flag = torch.full((), -1, dtype=torch.int32, device="cuda")
+    mx.allclose(mx.make_tensor(flag), mx.make_tensor(da), mx.make_tensor(db), 1e-5, 1e-8, ex)
+    ex.sync()
+    assert int(flag) == 0
+    mx.allclose(mx.make_tensor(flag), mx.make_tensor(da), mx.make_tensor(db), 1e-2, 1e-8, ex)
+    ex.sync()
+    assert int(flag) == 1
+    mx.allclose(mx.make_tensor(flag), mx.make_tensor(da), mx.make_tensor(da), 0.0, 0.0, ex)
+    ex.sync()
+    assert int(flag) == 1
+    with pytest.raises(TypeError):
+        mx.allclose(mx.make_tensor(torch.zeros(3, dtype=torch.int32, device="cuda")), mx.make_tensor(da), mx.make_tensor(db), 1e-5, 1e-8, ex)

@@ -234,3 +234,37 @@ def test_softmax_matches_the_reference_generator(oracle, npdt, tol):
     wide = np.full((8, 30, 600), -5, npdt)
     oracle.softmax(mx.softmax(np_tensor(t3), [2]), wide[:, :, ::2])
     assert np.allclose(wide[:, :, ::2], special.softmax(t3.astype(np.float64), axis=2), rtol=tol, atol=0) and (wide[:, :, 1::2] == -5).all()
+
+
+def test_trace_diag_isclose_lowering(oracle):
+    """trace_impl = sum(diag(in)) (transforms/reduce.h:1505-1511), diag sizes (operators/diag.h:253-268), isclose
+    (operators/isclose.h: |a - b| <= atol + rtol * |b| as int) — the host-side lowering, evaluated by the oracle."""
+    rng = np.random.default_rng(5)
+    m = rng.standard_normal((12, 12)).astype(np.float32)
+    w = np.zeros((), np.float32)
+    oracle.reduce(mx.trace(np_tensor(m)), w)
+    assert abs(float(w) - float(np.trace(m.astype(np.float64)))) < 1e-5
+    for k in (0, 1, 5, -2):
+        d = mx.diag(np_tensor(m), k)
+        assert d.shape == (12 - abs(k),)
+        w = np.zeros(d.shape, np.float32)
+        oracle.elementwise(d * 1.0, w, A.F32)
+        assert np.array_equal(w, np.diag(m, k))
+    # an expression operand takes the DiagOp route: both matrix dims walk the same root dim
+    w = np.zeros((), np.float32)
+    oracle.reduce(mx.sum(mx.diag(np_tensor(m) * np_tensor(m))), w)
+    assert abs(float(w) - float(np.sum(np.diag(m).astype(np.float64) ** 2))) < 1e-4
+    stack = rng.standard_normal((3, 5, 5)).astype(np.float32)
+    w = np.zeros(3, np.float32)
+    oracle.reduce(mx.sum(mx.diag(np_tensor(stack)), [1]), w)
+    assert np.allclose(w, np.einsum("bii->b", stack), rtol=1e-5, atol=1e-6)
+    with pytest.raises(ValueError):
+        mx.diag(np_tensor(np.zeros((7, 5), np.float32)), 1)   # the reference's size rule would run off the matrix
+    a = rng.standard_normal((8, 9)).astype(np.float32)
+    b = a + np.float32(1e-4) * (rng.random((8, 9)) > 0.5).astype(np.float32)
+    w = np.zeros(a.shape, np.int32)
+    oracle.elementwise(mx.isclose(np_tensor(a), np_tensor(b), 1e-5, 1e-8), w, A.I32)
+    assert np.array_equal(w.astype(bool), np.abs(a - b) <= np.float32(1e-8) + np.float32(1e-5) * np.abs(b))
+    flag = np.zeros((), np.int32)
+    oracle.reduce(mx.all(mx.isclose(np_tensor(a), np_tensor(b), 1e-5, 1e-8)), flag, out_dtype=A.I32)
+    assert int(flag) == int(np.all(w))

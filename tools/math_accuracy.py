@@ -99,7 +99,9 @@ def main():
                       "ours_max_abs": float(np.max(np.abs(got - truth))), "lib_max_abs": float(np.max(np.abs(lib - truth))),
                       "ours_max_rel_price>1": float(np.max(np.abs(got - truth)[big] / truth[big])),
                       "lib_max_rel_price>1": float(np.max(np.abs(lib - truth)[big] / truth[big])),
-                      "ours_vs_lib_max_abs": float(np.max(np.abs(got - lib)))}), flush=True)
+                      "ours_vs_lib_max_abs": float(np.max(np.abs(got - lib))),
+                      "ours_max_abs_over_S": float(np.max(np.abs(got - truth) / S6)), "lib_max_abs_over_S": float(np.max(np.abs(lib - truth) / S6)),
+                      "ours_vs_lib_max_abs_over_S": float(np.max(np.abs(got - lib) / S6))}), flush=True)
 
 
 if __name__ == "__main__":

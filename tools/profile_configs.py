@@ -26,4 +26,12 @@ for name, f in (("c1", bc.run_c1), ("c3", bc.run_c3), ("c4", bc.run_c4), ("c5", 
     if name in which:
         f(ex, 6456.8)
         torch.cuda.empty_cache()
+if "perm" in which:   # the reference's permute benchmark shape + a plain transpose, through the transposing family
+    x = torch.randn(1000, 200, 6, 300, device="cuda")
+    y = torch.empty(300, 1000, 6, 200, device="cuda")
+    mx.make_tensor(y).set(mx.make_tensor(x).Permute([3, 0, 2, 1])).run(ex)
+    a = torch.randn(8192, 8192, device="cuda")
+    t = torch.empty(8192, 8192, device="cuda")
+    mx.make_tensor(t).set(mx.make_tensor(a).Permute([1, 0])).run(ex)
+    ex.sync()
 print("profiled", which)
