@@ -17,6 +17,7 @@
  *                       + matxCubPlan_t::Exec{Sum,Min,Max,Reduce,ArgReduce}
  *                                                             include/matx/transforms/cub.h:647-894,1281-1328
  *   mxb_softmax      <- softmax_impl (both overloads)         include/matx/transforms/reduce.h:362-445
+ *   mxb_cumsum       <- cumsum_impl + ExecPrefixScanEx        include/matx/transforms/cub.h:2367-2395,375-408
  *   mxb_create / mxb_destroy / mxb_set_stream
  *                    <- cudaExecutor ctor / getStream         include/matx/executors/cuda.h:60-82
  *   mxb_sync         <- CudaExecutorBase::sync                include/matx/executors/cuda_executor_common.h:137
@@ -179,6 +180,14 @@ int mxb_reduce(mxb_handle_t h, int reduce_op, const mxb_expr_t *expr, int n_redu
  * five launches there).  Real floating expressions only.  One launch with one read and one write when a row fits in
  * the registers of a CTA (<= 64 KB of fp32), otherwise a one-pass statistics launch + one elementwise launch. */
 int mxb_softmax(mxb_handle_t h, const mxb_expr_t *expr, int n_reduce_dims, const mxb_out_t *out);
+
+/* out(b..., j) = sum_{i <= j} expr(b..., i): inclusive prefix sum along the LAST dim of `expr` (reference: cumsum_impl,
+ * transforms/cub.h:2367-2395 -> matxCubPlan_t::ExecPrefixScanEx :375-408, cub::DeviceScan::InclusiveSum launched once
+ * per row).  `out` has the rank and sizes of `expr`; accumulation in the expression's arithmetic type (fp32 for 16-bit
+ * floats).  One launch, one read and one write of every element, fixed summation order (run-to-run deterministic):
+ * many rows -> a CTA per row with a running carry; few long rows -> a CTA per tile, tile and group totals exchanged
+ * through L2 inside the launch. */
+int mxb_cumsum(mxb_handle_t h, const mxb_expr_t *expr, const mxb_out_t *out);
 
 /* ---- multi-GPU (no counterpart in the reference) -------------------------------- */
 /* Slab-sharded full-tensor reductions: each rank reduces its slab with mxb_reduce_partial into a

@@ -367,6 +367,16 @@ class b200Executor : public cudaExecutor {
       return !b200_detail::check_or_fallback(mxb_softmax(h_.get(), &b.e, n_axes, &out));
     }
   }
+  template <class Out, class In> bool cumsum(Out &dest, const In &in) const {
+    if constexpr (!b200_detail::lowerable<In>()) return false;
+    else {
+      b200_detail::Builder b;
+      mxb_out_t out;
+      if (!b200_detail::out_desc(dest, out)) return false;
+      if (!b200_detail::lower_root(b, in)) return false;
+      return !b200_detail::check_or_fallback(mxb_cumsum(h_.get(), &b.e, &out));
+    }
+  }
   template <class Out, class Idx, class In> bool reduce_idx(int op, Out &dest, Idx *idest, const In &in, int ddof) const {
     if constexpr (!b200_detail::lowerable<In>()) return false;
     else {
@@ -482,6 +492,17 @@ void softmax_impl(OutType dest, const InType &in, PermDims dims, const b200Execu
     if (exec.softmax_trailing(pdest, permute(in, perm), static_cast<int>(dims.size()))) return;
   }
   softmax_impl(dest, in, dims, exec.getStream());
+}
+
+// cumsum (transforms/cub.h:2367-2395): CumsumOp::Exec calls `cumsum_impl(out, a_, ex)` (operators/cumsum.h:293-296), so
+// `(out = cumsum(x)).run(exec)` lands here.  One launch for all rows (the reference launches CUB once per row).
+template <typename OutputTensor, typename InputOperator>
+void cumsum_impl(OutputTensor &a_out, const InputOperator &a, const b200Executor &exec) {
+  if (!exec.cumsum(a_out, a)) cumsum_impl(a_out, a, static_cast<const cudaExecutor &>(exec));
+}
+template <typename OutputTensor, typename InputOperator>
+void cumsum_impl(OutputTensor &a_out, const InputOperator &a, b200Executor &exec) {
+  cumsum_impl(a_out, a, static_cast<const b200Executor &>(exec));
 }
 
 // allclose (transforms/reduce.h:1321-1331): all(isclose(in1, in2, rtol, atol)) into a rank-0 int tensor, one launch

@@ -233,6 +233,23 @@ void aot_manifest(std::vector<ManifestItem> *items) {
   add(prog_fma3(MXB_F32), FAM_EW, -1, MXB_F32, 0, false);
   for (int d : {MXB_F32, MXB_F64, MXB_C64}) add(prog_vector_add(d), FAM_EW, -1, d, 0, false);
   for (int d : {MXB_F32, MXB_BF16}) add(prog_identity(d), FAM_EW, -1, d, 0, d == MXB_F32);
+  // cumsum of plain tensors: long-row (U = 4) and short-row (U = 1) tiles
+  for (int d : {MXB_F32, MXB_F64, MXB_C64, MXB_I32, MXB_BF16})
+    for (int u : {(d == MXB_F64 || d == MXB_C64) ? 2 : 4, 1}) {
+      const mxb_expr_t e = prog_identity(d);
+      ExprInfo info;
+      std::string err;
+      if (analyze_expr(&e, &info, &err) != MXB_OK) continue;
+      ManifestItem it;
+      it.expr = e;
+      it.spec.family = FAM_SCAN;
+      it.spec.op = -1;
+      it.spec.out_dtype = d;
+      it.spec.V = policy_vmax(info);
+      it.spec.U = u;
+      it.spec.team = 0;
+      items->push_back(it);
+    }
   // permuted copies (bench/00_operators/operators.cu:40-59) and the row + column mix
   for (int d : {MXB_F32, MXB_F64, MXB_C64, MXB_BF16, MXB_I32}) add(prog_identity(d), FAM_EW_TR, -1, d, 0, false);
   add(prog_vector_add(MXB_F32), FAM_EW_TR, -1, MXB_F32, 0, false);

@@ -41,6 +41,9 @@ struct mxb_context {
   size_t tmp_bytes = 0;
   std::string last_kernel;
   int64_t launches = 0;
+  void *scan_ws = nullptr;  // tile / group totals, epoch-coded flags, self-resetting counters of the scan family
+  size_t scan_ws_bytes = 0, scan_cap_tiles = 0, scan_cap_groups = 0;
+  unsigned scan_epoch = 0;
 };
 
 namespace {
@@ -990,6 +993,7 @@ int mxb_destroy(mxb_handle_t h) {
   if (h->ws) cudaFreeAsync(h->ws, h->stream);
   if (h->tickets) cudaFreeAsync(h->tickets, h->stream);
   if (h->tmp) cudaFreeAsync(h->tmp, h->stream);
+  if (h->scan_ws) cudaFreeAsync(h->scan_ws, h->stream);
   delete h;
   return MXB_OK;
 }
@@ -1549,6 +1553,155 @@ int mxb_softmax(mxb_handle_t h, const mxb_expr_t *expr_in, int n_reduce, const m
   return mxb_elementwise(h, &e2, out);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// cumsum: inclusive prefix sum along the innermost dim (reference: cumsum_impl, transforms/cub.h:2367-2395 ->
+// ExecPrefixScanEx :375-408: cub::DeviceScan::InclusiveSum, one launch per row for rank > 1)
+// ---------------------------------------------------------------------------------------------------
+int mxb_cumsum(mxb_handle_t h, const mxb_expr_t *expr_in, const mxb_out_t *out) {
+  if (!h) return fail(MXB_ERR_INVALID, "null handle");
+  int st = check_expr_shape(expr_in);
+  if (st != MXB_OK) return st;
+  if (expr_in->rank < 1) return fail(MXB_ERR_INVALID, "cumsum needs rank >= 1");
+  if (!out || !out->data) return fail(MXB_ERR_INVALID, "null output");
+  if (out->rank != expr_in->rank) return fail(MXB_ERR_SIZE, "cumsum output rank must equal the input rank");
+  for (int d = 0; d < out->rank; ++d)
+    if (out->size[d] != expr_in->size[d]) return fail(MXB_ERR_SIZE, "output size mismatch in dim " + std::to_string(d));
+  if (out->dtype < 0 || out->dtype >= MXB_DTYPE_COUNT) return fail(MXB_ERR_INVALID, "output dtype out of range");
+  MXB_CUDA(cudaSetDevice(h->device));
+
+  mxb_expr_t e;
+  std::string err;
+  st = canonicalize(expr_in, &e, &err);
+  if (st != MXB_OK) return fail(st, err);
+  ExprInfo info;
+  st = analyze_expr(&e, &info, &err);
+  if (st != MXB_OK) return fail(st, err);
+  const int vt = info.value_dtype;
+  if (!(vt == MXB_F32 || vt == MXB_F64 || vt == MXB_C64 || vt == MXB_I32 || vt == MXB_I64))
+    return fail(MXB_ERR_NOT_SUPPORTED, "cumsum of this value type is not lowered");
+  if (vt == MXB_C64 && out->dtype != MXB_C64) return fail(MXB_ERR_INVALID, "complex expression needs a complex output");
+
+  const int nbd = e.rank - 1, nl = e.n_leaves;
+  Group gb;
+  gb.n = nbd;
+  for (int d = 0; d < nbd; ++d) {
+    gb.size[d] = e.size[d];
+    for (int k = 0; k < nl; ++k) gb.ls[k][d] = e.leaves[k].stride[d];
+    gb.os[d] = out->stride[d];
+    gb.is[d] = 0;
+  }
+  collapse(gb, nl);
+  if (gb.n > KMAXD) return fail(MXB_ERR_NOT_SUPPORTED, "batch dims do not collapse to <= 4");
+  const int64_t L = e.size[e.rank - 1];
+  int64_t B = 1;
+  for (int d = 0; d < gb.n; ++d) B *= gb.size[d];
+  if (B == 0 || L == 0) return MXB_OK;
+  const int64_t ostride = out->stride[e.rank - 1];
+  const int obytes = dtype_bytes(out->dtype);
+
+  // vector width: every leaf unit-stride (or broadcast) along the scan dim, rows 16-byte aligned
+  int V = policy_vmax(info);
+  while (V > 1 && V * obytes > 32) V >>= 1;
+  auto in_ok = [&](int v) {
+    for (int k = 0; k < nl; ++k) {
+      const int64_t in = e.leaves[k].stride[e.rank - 1];
+      if (in != 0 && in != 1) return false;
+      if (in == 0) continue;
+      if (!aligned_to(e.leaves[k].data, (int64_t)v * dtype_bytes(e.leaves[k].dtype))) return false;
+      for (int d = 0; d < gb.n; ++d) if (gb.ls[k][d] % v) return false;
+    }
+    return true;
+  };
+  while (V > 1 && !in_ok(V)) V = 1;
+  bool ovec = V > 1 && ostride == 1 && aligned_to(out->data, (int64_t)V * obytes);
+  for (int d = 0; ovec && d < gb.n; ++d) if (gb.os[d] % V) ovec = false;
+
+  KernelSpec spec;
+  spec.family = FAM_SCAN;
+  spec.op = -1;
+  spec.out_dtype = out->dtype;
+  spec.V = V;
+  // tile = 256 threads x U chunks x V elements; short rows take the one-chunk instance
+  // (8-byte values: two chunks, or the 16 running values per thread spill)
+  spec.U = (L > (int64_t)256 * V) ? (dtype_bytes(vt) >= 8 ? 2 : 4) : 1;
+  if (env_int("MXB_TUNE_U", 0) > 0) spec.U = env_int("MXB_TUNE_U", 0);
+  const int64_t tile = (int64_t)256 * V * spec.U;
+  const int64_t tpr = (L + tile - 1) / tile;
+  const int sm = h->sm_count;
+  // few long rows: one CTA per tile with the in-launch carry exchange; otherwise a CTA walks whole rows
+  bool tiles_mode = tpr > 1 && B < 2 * (int64_t)sm;
+  if (env_int("MXB_SCAN_MODE", 0) == 1) tiles_mode = false;
+  if (env_int("MXB_SCAN_MODE", 0) == 2) tiles_mode = tpr > 1;
+  if (tiles_mode && B * tpr > 0x7fffffff) tiles_mode = false;
+
+  RedParams p;
+  memset(&p, 0, sizeof p);
+  p.nb = gb.n;
+  p.nr = 1;
+  p.B = B;
+  p.R = L;
+  p.nleaf = nl;
+  p.splits = tiles_mode ? 2 : 1;
+  for (int d = 0; d < gb.n; ++d) {
+    p.bsz[d] = gb.size[d];
+    p.out.bs[d] = gb.os[d];
+    for (int k = 0; k < nl; ++k) p.leaf[k].bs[d] = gb.ls[k][d];
+  }
+  p.rsz[0] = L;
+  p.out_rs[0] = ostride;
+  bool unit = nl > 0;
+  for (int k = 0; k < nl; ++k) {
+    p.leaf[k].rs[0] = e.leaves[k].stride[e.rank - 1];
+    p.leaf[k].ptr = e.leaves[k].data;
+    unit = unit && p.leaf[k].rs[0] == 1;
+  }
+  p.all_unit = unit ? 1 : 0;
+  p.tx = ovec ? 1 : 0;
+  p.out.ptr = out->data;
+  fill_consts(e, p.c);
+
+  unsigned grid;
+  if (tiles_mode) {
+    const int64_t gpr = (tpr + 127) / 128;   // SCAN_GROUP
+    // Regions are laid out from CAPACITIES that only grow (values are 8 bytes at most), so a word that is a flag in
+    // one launch is a flag in every launch: a stale tile total can never be mistaken for the current epoch.
+    const size_t need_t = (size_t)(B * tpr), need_g = (size_t)(B * gpr);
+    if (need_t > h->scan_cap_tiles || need_g > h->scan_cap_groups || !h->scan_ws) {
+      if (h->scan_ws) MXB_CUDA(cudaFreeAsync(h->scan_ws, h->stream));
+      h->scan_cap_tiles = std::max<size_t>(std::max(need_t, h->scan_cap_tiles), 4096);
+      h->scan_cap_groups = std::max<size_t>(std::max(need_g, h->scan_cap_groups), 1024);
+      const size_t nb = h->scan_cap_tiles * 12 + h->scan_cap_groups * 16 + 1024;
+      MXB_CUDA(cudaMallocAsync(&h->scan_ws, nb, h->stream));
+      MXB_CUDA(cudaMemsetAsync(h->scan_ws, 0, nb, h->stream));   // flags 0 = no epoch, counters at rest
+      h->scan_ws_bytes = nb;
+      h->scan_epoch = 0;
+    }
+    const size_t o_agg = 0, o_gagg = o_agg + h->scan_cap_tiles * 8, o_af = o_gagg + h->scan_cap_groups * 8,
+                 o_gf = o_af + h->scan_cap_tiles * 4, o_gt = o_gf + h->scan_cap_groups * 4, o_tc = o_gt + h->scan_cap_groups * 4;
+    // counters are at rest (zero) between launches, flags are epoch-coded: nothing to clear
+    if (++h->scan_epoch == 0) {   // 2^32 launches later: start over
+      MXB_CUDA(cudaMemsetAsync(h->scan_ws, 0, h->scan_ws_bytes, h->stream));
+      h->scan_epoch = 1;
+    }
+    char *w = (char *)h->scan_ws;
+    p.scan_agg = w + o_agg;
+    p.scan_gagg = w + o_gagg;
+    p.scan_agg_flag = (unsigned *)(w + o_af);
+    p.scan_gagg_flag = (unsigned *)(w + o_gf);
+    p.scan_group_ticket = (unsigned *)(w + o_gt);
+    p.scan_tile_counter = (unsigned *)(w + o_tc);
+    p.scan_epoch = h->scan_epoch;
+    grid = (unsigned)(B * tpr);
+  } else {
+    const int tune_cps = env_int("MXB_TUNE_CTAS_PER_SM", 0);
+    grid = (unsigned)std::min<int64_t>(B, (int64_t)sm * (tune_cps > 0 ? tune_cps : 8));
+  }
+  Kernel k;
+  st = get_kernel(info, spec, &k);
+  if (st != MXB_OK) return st;
+  return launch(h, k, grid, 256u, 0, p);
+}
+
 int mxb_is_aot(const mxb_expr_t *expr, int reduce_op_or_minus1) {
   if (!expr) return 0;
   mxb_expr_t e;
@@ -1601,7 +1754,7 @@ int mxb_debug_compile(const mxb_expr_t *expr, int family, int reduce_op, int out
   if (st != MXB_OK) return fail(st, err);
   KernelSpec spec;
   spec.family = family;
-  spec.op = (family == FAM_EW || family == FAM_EW_TR || family == FAM_SM_GROUP || family == FAM_SM_REG) ? -1 : kernel_op(reduce_op);
+  spec.op = (family == FAM_EW || family == FAM_EW_TR || family == FAM_SCAN || family == FAM_SM_GROUP || family == FAM_SM_REG) ? -1 : kernel_op(reduce_op);
   spec.out_dtype = out_dtype;
   spec.V = V > 0 ? V : policy_vmax(info);
   spec.U = policy_unroll(info, spec.V, family);

@@ -326,6 +326,87 @@ int analyze_expr(const mxb_expr_t *e, ExprInfo *info, std::string *err) {
   s << body.str();
   s << "    return " << val(e->root) << ";\n";
   s << "  }\n";
+  // ---- paired evaluation (elements v and v+1 in one pass) on Blackwell's packed fp32 instructions ----
+  // Pure-fp32 programs made of + - * / neg sqrt exp log normcdf abs get a second body over mxb::f2 (FFMA2 / FMUL2 /
+  // FADD2 carry two lanes per issue slot; the hand-written log / normcdf are packed too).  a*b+c is contracted
+  // explicitly (left product first, single-use products only), the way the scalar body is contracted by the compiler.
+  {
+    bool pair_ok = type[e->root] == MXB_F32 && e->n_leaves > 0;
+    std::vector<int> uses(e->n_nodes, 0);
+    for (int i = 0; i < e->n_nodes && pair_ok; ++i) {
+      const mxb_node_t &n = e->nodes[i];
+      if (type[i] != MXB_F32) { pair_ok = false; break; }
+      switch (n.opcode) {
+        case MXB_OP_LEAF: {
+          const int d = e->leaves[n.src[0]].dtype;
+          if (d != MXB_F32 && d != MXB_BF16 && d != MXB_F16) pair_ok = false;
+          break;
+        }
+        case MXB_OP_CONST: break;
+        case MXB_OP_ADD: case MXB_OP_SUB: case MXB_OP_MUL: case MXB_OP_DIV:
+          if (type[n.src[0]] != MXB_F32 || type[n.src[1]] != MXB_F32) pair_ok = false;
+          uses[n.src[0]]++; uses[n.src[1]]++;
+          break;
+        case MXB_OP_NEG: case MXB_OP_SQRT: case MXB_OP_EXP: case MXB_OP_LOG: case MXB_OP_NORMCDF: case MXB_OP_ABS:
+          if (type[n.src[0]] != MXB_F32) pair_ok = false;
+          uses[n.src[0]]++;
+          break;
+        default: pair_ok = false;
+      }
+    }
+    s << "  enum { PAIR = " << (pair_ok ? 1 : 0) << " };\n";
+    if (pair_ok) {
+      std::vector<char> fused(e->n_nodes, 0);  // product folded into the add / sub that consumes it
+      auto is_mul1 = [&](int id) { return e->nodes[id].opcode == MXB_OP_MUL && uses[id] == 1; };
+      for (int i = 0; i < e->n_nodes; ++i) {
+        const mxb_node_t &n = e->nodes[i];
+        if (n.opcode != MXB_OP_ADD && n.opcode != MXB_OP_SUB) continue;
+        if (is_mul1(n.src[0])) fused[n.src[0]] = 1;
+        else if (is_mul1(n.src[1])) fused[n.src[1]] = 1;
+      }
+      s << "  template <int V> static __device__ __forceinline__ mxb::f2 eval2(const Regs<V> &r, int v, const mxb::ConstDev &c) {\n";
+      s << "    (void)r; (void)v; (void)c;\n";
+      for (int i = 0; i < e->n_nodes; ++i) {
+        const mxb_node_t &n = e->nodes[i];
+        if (fused[i]) continue;
+        std::string rhs;
+        const std::string A = val(n.src[0]), B = val(n.src[1]);
+        switch (n.opcode) {
+          case MXB_OP_LEAF: {
+            const std::string x = "r.x" + std::to_string(n.src[0]);
+            const int d = e->leaves[n.src[0]].dtype;
+            rhs = "mxb::f2(" + as(MXB_F32, d, x + ".v[v]") + ", " + as(MXB_F32, d, x + ".v[v + 1]") + ")";
+            break;
+          }
+          case MXB_OP_CONST: rhs = "mxb::f2(c.fre[" + std::to_string(n.src[0]) + "])"; break;
+          case MXB_OP_ADD: case MXB_OP_SUB: {
+            const bool sub = n.opcode == MXB_OP_SUB;
+            if (fused[n.src[0]] && is_mul1(n.src[0])) {
+              const mxb_node_t &m = e->nodes[n.src[0]];
+              rhs = "mxb::fma2(" + val(m.src[0]) + ", " + val(m.src[1]) + ", " + (sub ? "mxb::neg2(" + B + ")" : B) + ")";
+            } else if (fused[n.src[1]] && is_mul1(n.src[1])) {
+              const mxb_node_t &m = e->nodes[n.src[1]];
+              rhs = "mxb::fma2(" + (sub ? "mxb::neg2(" + val(m.src[0]) + ")" : val(m.src[0])) + ", " + val(m.src[1]) + ", " + A + ")";
+            } else {
+              rhs = A + (sub ? " - " : " + ") + B;
+            }
+            break;
+          }
+          case MXB_OP_MUL: rhs = A + " * " + B; break;
+          case MXB_OP_DIV: rhs = A + " / " + B; break;
+          case MXB_OP_NEG: rhs = "mxb::neg2(" + A + ")"; break;
+          case MXB_OP_SQRT: rhs = "mxb::f_sqrt(" + A + ")"; break;
+          case MXB_OP_EXP: rhs = "mxb::f_exp(" + A + ")"; break;
+          case MXB_OP_LOG: rhs = "mxb::f_log(" + A + ")"; break;
+          case MXB_OP_NORMCDF: rhs = "mxb::f_normcdf(" + A + ")"; break;
+          case MXB_OP_ABS: rhs = "mxb::f_abs(" + A + ")"; break;
+        }
+        s << "    const mxb::f2 " << val(i) << " = " << rhs << ";\n";
+      }
+      s << "    return " << val(e->root) << ";\n";
+      s << "  }\n";
+    }
+  }
   s << "};\n";
   info->src = s.str();
   return MXB_OK;
@@ -355,7 +436,7 @@ int policy_unroll(const ExprInfo &info, int V, int family) {
 
 std::string kernel_key(const ExprInfo &info, const KernelSpec &s) {
   std::ostringstream k;
-  static const char *fam[] = {"red_inner", "red_outer", "var_smem", "ew", "var_reg", "var_tma", "var_group", "softmax_group", "softmax_reg", "ew_tr"};
+  static const char *fam[] = {"red_inner", "red_outer", "var_smem", "ew", "var_reg", "var_tma", "var_group", "softmax_group", "softmax_reg", "ew_tr", "scan"};
   k << fam[s.family] << "|" << info.name << "|" << (s.op >= 0 ? reduce_op_name(s.op) : "-") << "|" << dtype_name(s.out_dtype)
     << "|V" << s.V << "|U" << s.U << "|T" << s.team;
   return k.str();
@@ -400,7 +481,9 @@ int kernel_wrapper_src(const ExprInfo &info, const KernelSpec &s, const std::str
         << ", " << s.team << ">(p); }\n";
       break;
     case FAM_RED_OUTER:
-      k << "extern \"C\" __global__ void __launch_bounds__(256) " << symbol
+      // 3 CTAs per SM (<= 85 registers): at 2 the column walker has too few loads in flight (ncu: 112 registers,
+      // 24 % warps active, 0.435 ms on config 5; 76 registers, 34 %, 0.350 ms before the split-R code joined this body)
+      k << "extern \"C\" __global__ void __launch_bounds__(256, 3) " << symbol
         << "(const __grid_constant__ mxb::RedParams p) { mxb::reduce_outer_body<" << E << ", " << op << ", " << O << ", " << VU << ">(p); }\n";
       break;
     case FAM_VAR_SMEM:
@@ -434,6 +517,12 @@ int kernel_wrapper_src(const ExprInfo &info, const KernelSpec &s, const std::str
     case FAM_EW:
       k << "extern \"C\" __global__ void __launch_bounds__(256) " << symbol
         << "(const __grid_constant__ mxb::EwParams p) { mxb::ew_body<" << E << ", " << O << ", " << VU << ">(p); }\n";
+      break;
+    case FAM_SCAN:
+      if (!(info.value_dtype == MXB_F32 || info.value_dtype == MXB_F64 || cplx || info.value_dtype == MXB_I32 || info.value_dtype == MXB_I64))
+        return fail("cumsum of this value type is not lowered");
+      k << "extern \"C\" __global__ void __launch_bounds__(256, 3) " << symbol
+        << "(const __grid_constant__ mxb::RedParams p) { mxb::scan_inner_body<" << E << ", " << O << ", " << VU << ">(p); }\n";
       break;
     case FAM_EW_TR:
       if (s.V != 2 && s.V != 4 && s.V != 8) return fail("ew_tr moves 16-byte chunks of 2-, 4- or 8-byte elements");

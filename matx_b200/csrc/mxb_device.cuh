@@ -113,7 +113,11 @@ struct RedParams {
   // NVLink peer mappings (no collective call): rec[r] = rank r's PartialRec[2 slots][world][KMAXITEMS],
   // flag[r] = rank r's arrival counters u32[world], epoch = this rank's count of completed exchanges
   PeerPush peer;
-  i64 out_rs[KMAXD];  // softmax: strides of the output over the reduce dims
+  i64 out_rs[KMAXD];  // softmax / scan: strides of the output over the reduce dims
+  // scan family only: the handle's scan workspace (tile / group totals, epoch-coded flags, self-resetting counters)
+  void *scan_agg, *scan_gagg;
+  u32 *scan_agg_flag, *scan_gagg_flag, *scan_group_ticket, *scan_tile_counter;
+  u32 scan_epoch;
 };
 
 // elementwise: up to KMAXD collapsed dims, innermost last
@@ -383,6 +387,84 @@ __device__ __forceinline__ float f_log(float x) {
   return fmaf(fe, 8.26295829e-08f, p);  // + exponent * ln2 (e still carries its 2^23 scale)
 }
 __device__ __forceinline__ double f_log(double x) { return log(x); }
+
+// ------------------------------------------------------------------------------------------------
+// Two fp32 lanes per register pair: Blackwell's packed fp32 arithmetic (PTX fma / mul / add .f32x2 -> SASS FFMA2 /
+// FMUL2 / FADD2) carries two elements per issue slot.  The fused elementwise kernels are instruction-issue bound for
+// transcendental chains (Black-Scholes: 152 instructions per option at 89 % issue utilisation, HBM at 62 %), so the
+// generated `eval2` bodies evaluate elements v and v+1 together; division, sqrt and exp stay the scalar IEEE /
+// library code per half, log and normcdf are the packed twins of the functions above (same constants, same order
+// of operations, so a lane gives the same bits whichever body evaluates it).
+// ------------------------------------------------------------------------------------------------
+struct f2 {
+  float2 v;
+  __device__ __forceinline__ f2() {}
+  __device__ __forceinline__ f2(float a, float b) { v.x = a; v.y = b; }
+  __device__ __forceinline__ explicit f2(float a) { v.x = a; v.y = a; }
+  __device__ __forceinline__ explicit f2(float2 a) : v(a) {}
+};
+__device__ __forceinline__ f2 operator+(f2 a, f2 b) { return f2(__fadd2_rn(a.v, b.v)); }
+__device__ __forceinline__ f2 operator*(f2 a, f2 b) { return f2(__fmul2_rn(a.v, b.v)); }
+__device__ __forceinline__ f2 neg2(f2 a) { return f2(-a.v.x, -a.v.y); }
+__device__ __forceinline__ f2 operator-(f2 a, f2 b) { return f2(__fadd2_rn(a.v, neg2(b).v)); }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { return f2(__ffma2_rn(a.v, b.v, c.v)); }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, float c) { return f2(__ffma2_rn(a.v, b.v, make_float2(c, c))); }
+__device__ __forceinline__ f2 fma2(f2 a, float b, float c) { return f2(__ffma2_rn(a.v, make_float2(b, b), make_float2(c, c))); }
+__device__ __forceinline__ f2 operator/(f2 a, f2 b) { return f2(a.v.x / b.v.x, a.v.y / b.v.y); }
+__device__ __forceinline__ f2 f_sqrt(f2 a) { return f2(sqrtf(a.v.x), sqrtf(a.v.y)); }
+__device__ __forceinline__ f2 f_exp(f2 a) { return f2(expf(a.v.x), expf(a.v.y)); }
+__device__ __forceinline__ f2 f_abs(f2 a) { return f2(fabsf(a.v.x), fabsf(a.v.y)); }
+__device__ __forceinline__ f2 f_normcdf(f2 x) {   // f_normcdf(float) above, two lanes at a time
+  f2 z;
+  asm("min.NaN.f32 %0, %1, %2;" : "=f"(z.v.x) : "f"(fabsf(x.v.x)), "f"(14.5f));
+  asm("min.NaN.f32 %0, %1, %2;" : "=f"(z.v.y) : "f"(fabsf(x.v.y)), "f"(14.5f));
+  const f2 s = z * z, sl = fma2(z, z, neg2(s));
+  const f2 d = z + f2(2.0f);
+  f2 u;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(u.v.x) : "f"(d.v.x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(u.v.y) : "f"(d.v.y));
+  u = fma2(u, fma2(neg2(d), u, 1.0f), u);
+  const f2 t = fma2(u, -4.0f, 1.0f);
+  f2 p = fma2(t, -7.689554332e-05f, 2.991535075e-05f);
+  p = fma2(p, t, 7.246770547e-04f);
+  p = fma2(p, t, 8.852431783e-04f);
+  p = fma2(p, t, -1.890715910e-03f);
+  p = fma2(p, t, -6.751993671e-03f);
+  p = fma2(p, t, -4.832238483e-04f);
+  p = fma2(p, t, 3.672166169e-02f);
+  p = fma2(p, t, 2.879839949e-02f);
+  p = fma2(p, t, -3.314045668e-01f);
+  p = fma2(p, t, 6.724079847e-01f);
+  const f2 q = p * u;
+  const float C = -0.72134752044448170368f;
+  const float CL = (float)(-0.72134752044448170368 - (double)C);
+  const f2 ahi = s * f2(C);
+  const f2 alo = fma2(sl, f2(C), fma2(s, f2(CL), fma2(s, f2(C), neg2(ahi))));
+  f2 e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.v.x) : "f"(ahi.v.x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.v.y) : "f"(ahi.v.y));
+  f2 r = e * q;
+  r = fma2(r * f2(0.69314718055994530942f), alo, r);
+  const f2 om = f2(1.0f) - r;
+  return f2(x.v.x < 0.0f ? r.v.x : om.v.x, x.v.y < 0.0f ? r.v.y : om.v.y);
+}
+__device__ __forceinline__ f2 f_log(f2 x) {       // f_log(float) above, two lanes at a time
+  const unsigned ix = __float_as_uint(x.v.x), iy = __float_as_uint(x.v.y);
+  if ((ix - 0x00800000u >= 0x7f000000u) | (iy - 0x00800000u >= 0x7f000000u)) return f2(f_log(x.v.x), f_log(x.v.y));
+  const unsigned ex = (ix - 0x3f2aaaabu) & 0xff800000u, ey = (iy - 0x3f2aaaabu) & 0xff800000u;
+  const f2 f = f2(__uint_as_float(ix - ex), __uint_as_float(iy - ey)) + f2(-1.0f);
+  const f2 fe((float)(int)ex, (float)(int)ey);
+  f2 p = fma2(f, -0.1294892579317093f, 0.1400475949048996f);
+  p = fma2(p, f, -0.1216716319322586f);
+  p = fma2(p, f, 0.14001160860061646f);
+  p = fma2(p, f, -0.16682304441928864f);
+  p = fma2(p, f, 0.20010747015476227f);
+  p = fma2(p, f, -0.24999716877937317f);
+  p = fma2(p, f, 0.3333320915699005f);
+  p = fma2(p, f, -0.5f);
+  p = fma2(f, p * f, f);
+  return fma2(fe, f2(8.26295829e-08f), p);
+}
 __device__ __forceinline__ double f_normcdf(double x) { return normcdf(x); }
 __device__ __forceinline__ float f_abs(float x) { return fabsf(x); }
 __device__ __forceinline__ double f_abs(double x) { return fabs(x); }
@@ -1736,8 +1818,17 @@ __device__ __forceinline__ void var_inner_tma_body(const RedParams &p) {
 template <class E, class OutT, int V>
 __device__ __forceinline__ void ew_store(const EwParams &p, char *obase, i64 oinner, i64 j, const typename E::template Regs<V> &r) {
   Vec<OutT, V> o;
+  if constexpr (E::PAIR && V % 2 == 0) {
 #pragma unroll
-  for (int v = 0; v < V; ++v) o.v[v] = cvt<OutT>(E::template eval<V>(r, v, p.c));
+    for (int v = 0; v < V; v += 2) {
+      const f2 t = E::template eval2<V>(r, v, p.c);
+      o.v[v] = cvt<OutT>(t.v.x);
+      o.v[v + 1] = cvt<OutT>(t.v.y);
+    }
+  } else {
+#pragma unroll
+    for (int v = 0; v < V; ++v) o.v[v] = cvt<OutT>(E::template eval<V>(r, v, p.c));
+  }
   if (V == 1) ((OutT *)obase)[j * oinner] = o.v[0];
   else StBytes<(int)sizeof(OutT) * V>::st((OutT *)obase + j, &o);
 }
@@ -2040,6 +2131,225 @@ __device__ __forceinline__ void ew_tr_body(const EwParams &p) {
       for (int v = 0; v < V; ++v) if (v < n) op[v] = o.v[v];
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K9: scan_inner — inclusive prefix sum along the innermost dim (reference: cumsum_impl -> cub::DeviceScan::InclusiveSum,
+// transforms/cub.h:375-408,2367-2395; one CUB launch PER ROW there, plus a second pass inside CUB's own decoupled
+// look-back).  One launch here, every element read once and written once.
+//
+// A tile is NT threads x U chunks x V elements; thread t owns V adjacent elements of every chunk (vector loads stay
+// coalesced), scans them in registers, the warp scans the thread totals with shuffles, the eight warp totals of the U
+// chunks meet in shared memory.  All additions happen in a FIXED order, so results are run-to-run deterministic.
+//   mode ROWS  (p.splits == 1): a CTA owns whole rows and walks their tiles with a carry in a register.
+//   mode TILES (p.splits  > 1): few long rows -> every tile is its own CTA (tile ids handed out in order by an
+//     atomic counter, so a tile only ever waits for tiles that are already running).  A tile publishes its total,
+//     the LAST tile of each group of SCAN_GROUP tiles to do so publishes the group's total, and a tile's carry is
+//     (totals of the groups before its own) + (totals of the tiles before it in its group): two flat, fixed-order
+//     sums of at most a few hundred L2-resident values — no serial chain between tiles, and no dependence on which
+//     neighbour happened to finish first (CUB's look-back adds whatever it finds, so its float sums vary from run to
+//     run).  Flags carry the launch epoch, counters wrap to zero: nothing is cleared between launches.
+// ------------------------------------------------------------------------------------------------
+constexpr int SCAN_NT = 256;
+constexpr int SCAN_GROUP = 128;
+
+// workspace (RedParams::scan_*): agg = T[B * tiles_per_row] tile totals, gagg = T[B * groups_per_row] group totals,
+// *_flag == launch epoch once the value is valid, group_ticket = arrivals per group and tile_counter = next tile id
+// (both atomicInc with wrap-around, so they are zero again when the launch ends)
+
+__device__ __forceinline__ u32 ld_acquire_u32(const u32 *p) {
+  u32 v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_u32(u32 *p, u32 v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+template <class T> __device__ __forceinline__ T shfl_up_t(T v, int d) {
+  enum { W = sizeof(T) / 4 };
+  union { T t; u32 w[W]; } a, b;
+  a.t = v;
+#pragma unroll
+  for (int i = 0; i < W; ++i) b.w[i] = __shfl_up_sync(0xffffffffu, a.w[i], d);
+  return b.t;
+}
+template <class T> __device__ __forceinline__ T scan_zero() { return cvt<T>(0.0f); }
+
+// fixed-order sum of n published values by one warp: lane-strided partial sums, then a shuffle tree
+template <class T>
+__device__ __forceinline__ T warp_sum_published(const T *val, const u32 *flag, i64 n, u32 epoch, int lane) {
+  T acc = scan_zero<T>();
+  for (i64 i = lane; i < n; i += 32) {
+    while (ld_acquire_u32(flag + i) != epoch) __nanosleep(20);
+    acc = acc + ld_cg_t(val + i);
+  }
+#pragma unroll
+  for (int m = 16; m > 0; m >>= 1) acc = acc + shfl_xor_t(acc, m);
+  return acc;
+}
+
+template <class E, class OutT, int V, int U, bool UNIT>
+__device__ __forceinline__ void scan_inner_body_impl(const RedParams &p) {
+  typedef typename E::value_type T;
+  constexpr int NT = SCAN_NT, NW = NT / 32;
+  __shared__ T s_warp[U][NW];   // warp totals of every chunk, then their exclusive prefixes
+  __shared__ T s_chunk[U + 1];  // chunk totals; [U] = carry into this tile (mode TILES)
+  __shared__ i64 s_tile;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const u32 epoch = p.scan_epoch;
+  const i64 L = p.rsz[0];
+  const i64 TILE = (i64)NT * V * U;
+  const i64 tpr = (L + TILE - 1) / TILE;          // tiles per row
+  const bool tiles_mode = p.splits > 1;
+  const i64 gpr = (tpr + SCAN_GROUP - 1) / SCAN_GROUP;
+  const i64 total_tiles = p.B * tpr;
+
+  i64 b = blockIdx.x, t = 0;       // ROWS: row b, tile t loops; TILES: one (b, t) per CTA
+  if (tiles_mode) {
+    if (tid == 0) s_tile = (i64)atomicInc(p.scan_tile_counter, (u32)(total_tiles - 1));
+    __syncthreads();
+    b = s_tile / tpr;
+    t = s_tile - b * tpr;
+  }
+  for (; b < p.B; b += gridDim.x) {
+    const char *base[E::NL];
+    i64 inner[E::NL];
+    i64 oo = 0;
+    {
+      i64 bidx[KMAXD];
+      decomp(b, p.nb, p.bsz, bidx);
+#pragma unroll
+      for (int k = 0; k < E::NL; ++k) {
+        i64 off = 0;
+#pragma unroll
+        for (int d = 0; d < KMAXD; ++d) if (d < p.nb) off += bidx[d] * p.leaf[k].bs[d];
+        base[k] = (const char *)p.leaf[k].ptr + off * E::leaf_bytes(k);
+        inner[k] = p.leaf[k].rs[0];
+      }
+#pragma unroll
+      for (int d = 0; d < KMAXD; ++d) if (d < p.nb) oo += bidx[d] * p.out.bs[d];
+    }
+    OutT *orow = (OutT *)p.out.ptr + oo;
+    const i64 oinner = p.out_rs[0];
+    T carry = scan_zero<T>();
+    for (i64 tt = tiles_mode ? t : 0; tt < (tiles_mode ? t + 1 : tpr); ++tt) {
+      const i64 j0 = tt * TILE;
+      // ---- load + evaluate + thread-local scan ----
+      T x[U][V];
+      {
+        typename E::template Regs<V> r[U];
+        bool full[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const i64 j = j0 + ((i64)u * NT + tid) * V;
+          full[u] = V == 1 ? (j < L) : (j + V <= L);
+          if (full[u]) E::template loadv<V, UNIT>(r[u], base, inner, j);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const i64 j = j0 + ((i64)u * NT + tid) * V;
+          if (full[u]) {
+#pragma unroll
+            for (int v = 0; v < V; ++v) x[u][v] = E::template eval<V>(r[u], v, p.c);
+          } else {
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+              x[u][v] = scan_zero<T>();
+              if (V > 1 && j + v < L) {
+                typename E::template Regs<1> r1;
+                E::template loadv<1, false>(r1, base, inner, j + v);
+                x[u][v] = E::template eval<1>(r1, 0, p.c);
+              }
+            }
+          }
+#pragma unroll
+          for (int v = 1; v < V; ++v) x[u][v] = x[u][v - 1] + x[u][v];
+        }
+      }
+      // ---- warp stage: inclusive scan of the thread totals, U chunks at once ----
+      T wexcl[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        T incl = x[u][V - 1];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const T o = shfl_up_t(incl, d);
+          if (lane >= d) incl = o + incl;
+        }
+        const T ex = shfl_up_t(incl, 1);
+        wexcl[u] = lane == 0 ? scan_zero<T>() : ex;
+        if (lane == 31) s_warp[u][warp] = incl;
+      }
+      __syncthreads();
+      // ---- CTA stage: thread u turns chunk u's warp totals into exclusive prefixes and the chunk total ----
+      if (tid < U) {
+        T run = scan_zero<T>();
+#pragma unroll
+        for (int w = 0; w < NW; ++w) { const T v = s_warp[tid][w]; s_warp[tid][w] = run; run = run + v; }
+        s_chunk[tid] = run;
+      }
+      __syncthreads();
+      T ctot[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) ctot[u] = s_chunk[u];
+      if (tiles_mode) {
+        // ---- grid stage: publish, close the group if last, gather the carry ----
+        if (warp == 0) {
+          T total = ctot[0];
+#pragma unroll
+          for (int u = 1; u < U; ++u) total = total + ctot[u];
+          const i64 g = t / SCAN_GROUP, first = g * SCAN_GROUP;
+          const i64 gcount = (tpr - first) < SCAN_GROUP ? (tpr - first) : SCAN_GROUP;
+          T *agg = (T *)p.scan_agg + b * tpr;
+          T *gagg = (T *)p.scan_gagg + b * gpr;
+          u32 *aflag = p.scan_agg_flag + b * tpr, *gflag = p.scan_gagg_flag + b * gpr;
+          u32 last = 0;
+          if (lane == 0) {
+            st_cg_t(agg + t, total);
+            st_release_u32(aflag + t, epoch);
+            __threadfence();
+            last = atomicInc(p.scan_group_ticket + b * gpr + g, (u32)(gcount - 1)) == (u32)(gcount - 1);
+          }
+          last = __shfl_sync(0xffffffffu, last, 0);
+          if (last) {  // every tile of the group has published: its total, in tile order
+            const T gt = warp_sum_published(agg + first, aflag + first, gcount, epoch, lane);
+            if (lane == 0) { st_cg_t(gagg + g, gt); st_release_u32(gflag + g, epoch); }
+          }
+          const T cg = warp_sum_published(gagg, gflag, g, epoch, lane);
+          const T ct = warp_sum_published(agg + first, aflag + first, t - first, epoch, lane);
+          if (lane == 0) s_chunk[U] = cg + ct;
+        }
+        __syncthreads();
+        carry = s_chunk[U];
+      }
+      // ---- finish: carry + chunk prefix + warp prefix + lane prefix + local scan, one vector store ----
+      T cpre = carry;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const i64 j = j0 + ((i64)u * NT + tid) * V;
+        const T pre = (cpre + s_warp[u][warp]) + wexcl[u];
+        Vec<OutT, V> o;
+#pragma unroll
+        for (int v = 0; v < V; ++v) o.v[v] = cvt<OutT>(pre + x[u][v]);
+        if (V > 1 && j + V <= L && oinner == 1 && p.tx) StBytes<(int)sizeof(OutT) * V>::st(orow + j, &o);
+        else {
+#pragma unroll
+          for (int v = 0; v < V; ++v) if (j + v < L) orow[(j + v) * oinner] = o.v[v];
+        }
+        cpre = cpre + ctot[u];
+      }
+      carry = cpre;
+      __syncthreads();   // s_warp / s_chunk are reused by the next tile
+    }
+    if (tiles_mode) break;
+  }
+}
+
+template <class E, class OutT, int V, int U>
+__device__ __forceinline__ void scan_inner_body(const RedParams &p) {
+  pdl_prologue();
+  if (p.all_unit) scan_inner_body_impl<E, OutT, V, U, true>(p);
+  else scan_inner_body_impl<E, OutT, V, U, false>(p);
 }
 
 }  // namespace mxb

@@ -360,6 +360,20 @@ class SoftmaxExpr(ReduceExpr):
 def softmax(a, dims=None): return SoftmaxExpr(a, dims)
 
 
+class CumsumExpr:
+    """cumsum(a) (operators/cumsum.h -> cumsum_impl, transforms/cub.h:2367-2395): inclusive prefix sum along the LAST
+    dim, same rank and sizes as the operand."""
+
+    def __init__(self, a):
+        self.a = _wrap(a, None)
+        if len(self.a.shape) < 1:
+            raise ValueError("cumsum needs an operand of rank >= 1")
+        self.out_shape = tuple(self.a.shape)
+
+
+def cumsum(a): return CumsumExpr(a)
+
+
 class mtie:
     """mtie(values, indices) — multi-output LHS (core/tie.h:44-117)."""
 
@@ -475,22 +489,26 @@ class Set:
 
     def __init__(self, lhs, rhs):
         self.lhs = lhs
-        self.rhs = rhs if isinstance(rhs, ReduceExpr) else _wrap(rhs, lhs if isinstance(lhs, Op) else None)
+        self.rhs = rhs if isinstance(rhs, (ReduceExpr, CumsumExpr)) else _wrap(rhs, lhs if isinstance(lhs, Op) else None)
         if isinstance(lhs, mtie):
             if not isinstance(self.rhs, ReduceExpr) or self.rhs.op not in (A.RED_ARGMAX, A.RED_ARGMIN):
                 raise TypeError("mtie(...) takes argmax / argmin on the right-hand side")
             if len(lhs.outs) != 2:
                 raise TypeError("mtie(values, indices) needs two outputs")
-        shape = self.rhs.out_shape if isinstance(self.rhs, ReduceExpr) else self.rhs.shape
+        shape = self.rhs.out_shape if isinstance(self.rhs, (ReduceExpr, CumsumExpr)) else self.rhs.shape
         outs = lhs.outs if isinstance(lhs, mtie) else (lhs,)
         for o in outs:
             if tuple(o.shape) != tuple(shape) and not (len(shape) == 0 and len(o.shape) == 0):
-                if not isinstance(self.rhs, ReduceExpr) and len(shape) <= len(o.shape) and tuple(o.shape[len(o.shape) - len(shape):]) == tuple(shape):
+                if not isinstance(self.rhs, (ReduceExpr, CumsumExpr)) and len(shape) <= len(o.shape) and tuple(o.shape[len(o.shape) - len(shape):]) == tuple(shape):
                     continue  # lower-rank rhs broadcasts into the lhs
                 raise A.MatxB200Error(A.ERR_SIZE, "lhs shape %s does not match rhs shape %s" % (o.shape, shape))  # matxInvalidSize
 
     def run(self, ex: "CudaExecutor") -> None:
-        if isinstance(self.rhs, SoftmaxExpr):
+        if isinstance(self.rhs, CumsumExpr):
+            e = lower_elementwise(self.rhs.a)
+            out = _out_desc(self.lhs)
+            A.check(A.lib.mxb_cumsum(ex.handle, C.byref(e), C.byref(out)))
+        elif isinstance(self.rhs, SoftmaxExpr):
             r = self.rhs
             e = lower_reduce(r)
             o = _out_desc(self.lhs)

@@ -497,3 +497,29 @@ int orc_softmax(const mxb_expr_t *e, int n_reduce, const mxb_out_t *out) {
   }
   return 0;
 }
+
+/* cumsum along the last dim — cumsum_impl(HostExecutor), transforms/cub.h:2397-2440 -> host_inclusive_scan,
+ * transforms/host_algorithms.h:231-249: std::partial_sum per row, i.e. a sequential running sum in the value type
+ * (16-bit float leaves arrive widened to fp32 here, like everywhere on this path).  Pinned by the reference's own
+ * known answers: CUBTests.cu:203-226 (permuted int matrix), :536-575 (running float sums), stack_test.cu:72-80. */
+int orc_cumsum(const mxb_expr_t *e, const mxb_out_t *out) {
+  if (e->rank < 1) return 1;
+  const int nb = e->rank - 1;
+  int64_t B = 1;
+  for (int d = 0; d < nb; ++d) B *= e->size[d];
+  const int64_t L = e->size[nb];
+  int64_t idx[MXB_MAX_RANK] = {0};
+  for (int64_t b = 0; b < B; ++b) {
+    unflatten(b, nb, e->size, idx);
+    val_t run; memset(&run, 0, sizeof run);
+    for (int64_t j = 0; j < L; ++j) {
+      idx[nb] = j;
+      val_t x = eval_expr(e, idx);
+      run = j == 0 ? x : arith(MXB_OP_ADD, run, x);
+      int64_t off = 0;
+      for (int d = 0; d < e->rank; ++d) off += idx[d] * out->stride[d];
+      store_val(out->data, out->dtype, off, run);
+    }
+  }
+  return 0;
+}

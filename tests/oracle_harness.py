@@ -47,6 +47,7 @@ class Oracle:
         lib.orc_elementwise.argtypes = [C.POINTER(A.Expr), C.POINTER(A.Out)]
         lib.orc_reduce.argtypes = [C.c_int, C.POINTER(A.Expr), C.c_int, C.POINTER(A.Out), C.POINTER(A.Out), C.c_int, C.c_int]
         lib.orc_softmax.argtypes = [C.POINTER(A.Expr), C.c_int, C.POINTER(A.Out)]
+        lib.orc_cumsum.argtypes = [C.POINTER(A.Expr), C.POINTER(A.Out)]
 
     def elementwise(self, rhs, out: np.ndarray, out_dtype: int | None = None) -> np.ndarray:
         rhs = mx._wrap(rhs, None)
@@ -56,6 +57,12 @@ class Oracle:
         e = mx.lower_elementwise(rhs)
         o = mx._out_desc(lhs)
         assert self.lib.orc_elementwise(C.byref(e), C.byref(o)) == 0
+        return out
+
+    def cumsum(self, r: "mx.CumsumExpr", out: np.ndarray, out_dtype: int | None = None) -> np.ndarray:
+        e = mx.lower_elementwise(r.a)
+        o = mx._out_desc(np_tensor(out, out_dtype))
+        assert self.lib.orc_cumsum(C.byref(e), C.byref(o)) == 0
         return out
 
     def softmax(self, r: "mx.SoftmaxExpr", out: np.ndarray, out_dtype: int | None = None) -> np.ndarray:

@@ -109,15 +109,34 @@ def test_named_programs_are_ahead_of_time():
 
 @pytest.mark.parametrize("family,op,team", [(0, A.RED_SUM, 0), (0, A.RED_ARGMIN, 1), (1, A.RED_MAX, 0), (2, A.RED_VAR, 0),
                                             (4, A.RED_VAR, 4), (3, -1, 0), (6, A.RED_VAR, 2), (7, -1, 2), (8, -1, 4),
-                                            (0, 11, 0), (1, 11, 0), (9, -1, 0)])   # 7 / 8: softmax in registers; op 11: its statistics pass; 9: transposing elementwise
+                                            (0, 11, 0), (1, 11, 0), (9, -1, 0), (10, -1, 0)])   # 7 / 8: softmax in registers; op 11: its statistics pass; 9: transposing elementwise; 10: scan
 def test_generated_kernels_compile_for_sm100a(family, op, team):
     a = np_tensor(np.zeros((4, 8), np.float32))
     h = np_tensor(np.zeros((4, 8), np.uint16), A.BF16)
     expr = mx.sqrt(mx.abs(a)) * h - mx.tanh(a) / 3.0 + mx.as_type(mx.floor(a), A.I32)
-    e = mx.lower_reduce(mx.ReduceExpr(max(op, 0), expr, [1])) if family not in (3, 9) else mx.lower_elementwise(expr)
+    e = mx.lower_reduce(mx.ReduceExpr(max(op, 0), expr, [1])) if family not in (3, 9, 10) else mx.lower_elementwise(expr)
     log = C.create_string_buffer(1 << 16)
     st = A.lib.mxb_debug_compile(C.byref(e), family, op, A.F32, 0, team, log, len(log))
     assert st == A.OK, (A.lib.mxb_last_error(), log.value.decode()[:2000])
+
+
+def test_paired_fp32_body_compiles_for_sm100a():
+    """Pure-fp32 programs get a second body on the packed fp32 instructions (FFMA2 / FMUL2 / FADD2): NVRTC must know
+    the sm_100 intrinsics and the packed log / normcdf."""
+    a, b = (np_tensor(np.zeros((4, 8), np.float32)) for _ in range(2))
+    expr = mx.normcdf(mx.log(a / b) * 2.0 - mx.sqrt(b)) * a - mx.exp(-a) + mx.abs(b)
+    e = mx.lower_elementwise(expr)
+    buf = C.create_string_buffer(1 << 16)
+    assert A.lib.mxb_debug_codegen(C.byref(e), buf, len(buf)) == A.OK
+    src = buf.value.decode()
+    assert "PAIR = 1" in src and "eval2" in src and "mxb::fma2(" in src, src
+    log = C.create_string_buffer(1 << 16)
+    st = A.lib.mxb_debug_compile(C.byref(e), 3, -1, A.F32, 0, 0, log, len(log))
+    assert st == A.OK, (A.lib.mxb_last_error(), log.value.decode()[:2000])
+    # anything outside the packed subset keeps the scalar body only
+    e2 = mx.lower_elementwise(mx.tanh(a) + b)
+    assert A.lib.mxb_debug_codegen(C.byref(e2), buf, len(buf)) == A.OK
+    assert "PAIR = 0" in buf.value.decode()
 
 
 def test_set_checks_shapes_like_the_reference():

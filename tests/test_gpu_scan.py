@@ -1,0 +1,133 @@
+"""-m gpu parity tests of cumsum (mxb_cumsum, the `scan` kernel family) against the CPU oracle's sequential running sum
+(std::partial_sum, what the reference's HostExecutor does) and numpy.  Reference tests mirrored: test/00_tensor/
+CUBTests.cu:203-226 (permuted integer input), :536-575 (batched float rows), :640-670 (complex rows)."""
+import numpy as np
+import pytest
+
+from matx_b200 import _abi as A
+from matx_b200 import ops as mx
+from tests import gpu_util as G
+from tests.oracle_harness import np_tensor, f32_to_bf16_bits, bf16_bits_to_f32
+
+pytestmark = pytest.mark.gpu
+
+
+def run_cumsum(oracle, build, arrays, out_shape, out_dtype, dtypes=None, env=None):
+    import os
+    import torch
+    dtypes = dtypes or [None] * len(arrays)
+    dev = [G.to_dev(a, d) for a, d in zip(arrays, dtypes)]
+    npdt = G._NP_OF[out_dtype]
+    tdt = {A.BF16: torch.bfloat16, A.F16: torch.float16}.get(out_dtype)
+    out_d = torch.zeros(out_shape, dtype=tdt, device="cuda") if tdt else torch.from_numpy(np.zeros(out_shape, npdt)).cuda()
+    ex = G.executor()
+    old = {k: os.environ.get(k) for k in (env or {})}
+    os.environ.update({k: str(v) for k, v in (env or {}).items()})
+    try:
+        mx.make_tensor(out_d).set(mx.cumsum(build(*[mx.make_tensor(t) for t in dev]))).run(ex)
+        ex.sync()
+    finally:
+        for k, v in old.items():
+            os.environ.pop(k, None) if v is None else os.environ.__setitem__(k, v)
+    k = ex.last_kernel()
+    got = G.from_dev(out_d, out_dtype)
+    want = np.zeros(out_shape, npdt)
+    oracle.cumsum(mx.cumsum(build(*[np_tensor(np.ascontiguousarray(a), d) for a, d in zip(arrays, dtypes)])), want, out_dtype)
+    return got, want, k
+
+
+def test_reference_known_answers(oracle):
+    inv = np.array([[1, 2, 3, 4], [10, 20, 30, 40], [100, 200, 300, 400]], np.int32)
+    got, want, k = run_cumsum(oracle, lambda t: t.Permute([1, 0]), [inv], (4, 3), A.I32)
+    assert k.startswith("scan|"), k
+    assert np.array_equal(got, np.cumsum(inv.T, axis=1)) and np.array_equal(got, want)
+    a = np.array([1, 2, 3, 4, 5], np.float32)
+    got, want, _ = run_cumsum(oracle, lambda t: t, [a], (5,), A.F32)
+    assert got.tolist() == [1, 3, 6, 10, 15]
+    x = np.zeros((2, 3, 40), np.float32)
+    for i in range(2):
+        for j in range(3):
+            x[i, j] = 1000 * i + 100 * j + (40 - np.arange(40))
+    got, want, _ = run_cumsum(oracle, lambda t: t, [x], x.shape, A.F32)
+    assert np.max(np.abs(got - np.cumsum(x.astype(np.float64), axis=2))) <= 0.001   # the reference's own bar
+
+
+@pytest.mark.parametrize("shape", [(1,), (7,), (1023,), (1024,), (1025,), (4096,), (4097,), (20000,), (3, 5000), (300, 257), (2000, 64),
+                                   (5, 3, 1000), (1, 1 << 20), (2, 300001)])
+def test_int32_exact_all_shapes(oracle, shape):
+    """Integer sums do not care about the order of additions: every tiling / carry path must be bit-exact."""
+    rng = np.random.default_rng(sum(shape))
+    x = rng.integers(-1000, 1000, shape).astype(np.int32)
+    got, want, k = run_cumsum(oracle, lambda t: t, [x], shape, A.I32)
+    assert k.startswith("scan|"), k
+    assert np.array_equal(got, want)
+    assert np.array_equal(got, np.cumsum(x.astype(np.int64), axis=-1).astype(np.int32))
+
+
+@pytest.mark.parametrize("mode", [1, 2])     # 1 = a CTA walks whole rows with a register carry, 2 = one CTA per tile + exchange
+def test_both_grid_modes_exact(oracle, mode):
+    rng = np.random.default_rng(50 + mode)
+    for shape in [(4, 70000), (1, 1 << 21), (40, 9000)]:
+        x = rng.integers(-50, 50, shape).astype(np.int32)
+        got, want, k = run_cumsum(oracle, lambda t: t, [x], shape, A.I32, env={"MXB_SCAN_MODE": mode})
+        assert np.array_equal(got, want), (mode, shape)
+
+
+@pytest.mark.parametrize("dt,tol", [(A.F32, 1e-5), (A.F64, 1e-12), (A.C64, 1e-5)])
+def test_floating_within_tolerance(oracle, dt, tol):
+    rng = np.random.default_rng(60)
+    for shape in [(33,), (10000,), (64, 3000), (2, 1 << 19)]:
+        if dt == A.C64:
+            x = (rng.random(shape) + 1j * rng.random(shape)).astype(np.complex64)
+        else:
+            x = rng.random(shape).astype(np.float32 if dt == A.F32 else np.float64)   # positive: no cancellation
+        got, want, _ = run_cumsum(oracle, lambda t: t, [x], shape, dt)
+        truth = np.cumsum(x.astype(np.complex128 if dt == A.C64 else np.float64), axis=-1)
+        # tolerance stated on each prefix: |got - truth| <= tol * |truth| (north star: 1e-5 relative for fp32)
+        assert np.max(np.abs(got - truth) / np.abs(truth)) <= tol
+        # the sequential fp32 running sum of the reference's host path is itself ~sqrt(n) ulp off; both agree with truth
+        assert np.max(np.abs(want - truth) / np.abs(truth)) <= max(tol, 2e-4)
+
+
+def test_run_to_run_deterministic():
+    import torch
+    ex = G.executor()
+    x = torch.randn(3, 1 << 20, device="cuda")
+    a, b = torch.empty_like(x), torch.empty_like(x)
+    mx.make_tensor(a).set(mx.cumsum(mx.make_tensor(x))).run(ex)
+    for _ in range(5):
+        mx.make_tensor(b).set(mx.cumsum(mx.make_tensor(x))).run(ex)
+        ex.sync()
+        assert torch.equal(a, b)
+
+
+def test_fused_strided_and_bf16(oracle):
+    rng = np.random.default_rng(61)
+    a = rng.random((50, 700)).astype(np.float32)
+    b = rng.random((50, 700)).astype(np.float32)
+    got, want, k = run_cumsum(oracle, lambda x, y: x * y + 1.0, [a, b], a.shape, A.F32)
+    assert np.max(np.abs(got - np.cumsum(a.astype(np.float64) * b + 1, axis=1)) / np.cumsum(a.astype(np.float64) * b + 1, axis=1)) <= 1e-5
+    # scan along a strided dim (permuted view): the scalar instance
+    t = rng.integers(-9, 9, (300, 40)).astype(np.int32)
+    got, want, k = run_cumsum(oracle, lambda x: x.Permute([1, 0]), [t], (40, 300), A.I32)
+    assert "|V1|" in k, k
+    assert np.array_equal(got, np.cumsum(t.T, axis=1))
+    # bf16 in, fp32 accumulation, one rounding at the store
+    h = f32_to_bf16_bits(rng.random((8, 3000)).astype(np.float32))
+    got, want, k = run_cumsum(oracle, lambda x: x, [h], h.shape, A.BF16, dtypes=[A.BF16])
+    truth = np.cumsum(bf16_bits_to_f32(h).astype(np.float64), axis=1)
+    assert np.max(np.abs(bf16_bits_to_f32(got) - truth) / truth) <= 2 ** -8
+
+
+def test_full_size_properties():
+    """2^28 fp32 elements in one row (the tile-exchange mode at scale): last element = the sum; differences give the input back."""
+    import torch
+    ex = G.executor()
+    n = 1 << 28
+    x = (torch.rand(n, device="cuda") * 2 - 1).round() * 3      # integers in {-3, 0, 3}: every prefix is exact in fp32
+    y = torch.empty_like(x)
+    mx.make_tensor(y).set(mx.cumsum(mx.make_tensor(x))).run(ex)
+    ex.sync()
+    assert ex.last_kernel().startswith("scan|")
+    assert float(y[-1]) == float(x.double().sum())
+    assert torch.equal(y[1:] - y[:-1], x[1:]) and float(y[0]) == float(x[0])

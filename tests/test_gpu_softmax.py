@@ -30,9 +30,10 @@ def run_softmax(oracle, build, arrays, out_dtype=A.F32, dtypes=None, out_view=No
     k, nl = ex.last_kernel(), ex.launch_count() - n0
     got = G.from_dev(out_d, out_dtype)
     r2 = build(*[np_tensor(np.ascontiguousarray(a), d) for a, d in zip(arrays, dtypes)])
-    want = np.full(r2.out_shape, -77, G._NP_OF[out_dtype])
     if out_dtype in (A.BF16, A.F16):
-        want = f32_to_bf16_bits(want.astype(np.float32))
+        want = f32_to_bf16_bits(np.full(r2.out_shape, -77, np.float32))
+    else:
+        want = np.full(r2.out_shape, -77, G._NP_OF[out_dtype])
     oracle.softmax(r2, out_view(want) if out_view else want, out_dtype=out_dtype)
     return got, want, k, nl
 

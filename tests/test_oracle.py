@@ -268,3 +268,38 @@ def test_trace_diag_isclose_lowering(oracle):
     flag = np.zeros((), np.int32)
     oracle.reduce(mx.all(mx.isclose(np_tensor(a), np_tensor(b), 1e-5, 1e-8)), flag, out_dtype=A.I32)
     assert int(flag) == int(np.all(w))
+
+
+def test_cumsum_reference_known_answers(oracle):
+    """cumsum: the reference's own known answers (test/00_tensor/CUBTests.cu:203-226 permuted int matrix, :536-575 running
+    float sums per row, test/00_operators/stack_test.cu:72-80) and numpy on strided / fused inputs."""
+    inv = np.array([[1, 2, 3, 4], [10, 20, 30, 40], [100, 200, 300, 400]], np.int32)
+    out = np.zeros((4, 3), np.int32)
+    oracle.cumsum(mx.cumsum(np_tensor(inv).Permute([1, 0])), out)
+    assert np.array_equal(out, np.cumsum(inv.T, axis=1))
+    a = np.array([1, 2, 3, 4, 5], np.float32)
+    out = np.zeros(5, np.float32)
+    oracle.cumsum(mx.cumsum(np_tensor(a)), out)
+    assert out.tolist() == [1, 3, 6, 10, 15]
+    outer, batches, cols = 2, 3, 40                      # CUBTests.cu:536-575: in(i,j,k) = base + (cols - k)
+    x = np.zeros((outer, batches, cols), np.float32)
+    for i in range(outer):
+        for j in range(batches):
+            x[i, j] = 1000 * i + 100 * j + (cols - np.arange(cols))
+    out = np.zeros_like(x)
+    oracle.cumsum(mx.cumsum(np_tensor(x)), out)
+    assert np.max(np.abs(out - np.cumsum(x.astype(np.float64), axis=2))) <= 0.001
+    # sequential fp32 running sum, bit for bit (std::partial_sum)
+    rng = np.random.default_rng(3)
+    r = rng.standard_normal((3, 257)).astype(np.float32)
+    out = np.zeros_like(r)
+    oracle.cumsum(mx.cumsum(np_tensor(r)), out)
+    run = np.zeros(3, np.float32)
+    for j in range(257):
+        run = (run + r[:, j]).astype(np.float32) if j else r[:, 0].copy()
+        assert np.array_equal(out[:, j], run)
+    # fused operand, complex
+    c = (rng.standard_normal((2, 33)) + 1j * rng.standard_normal((2, 33))).astype(np.complex64)
+    out = np.zeros_like(c)
+    oracle.cumsum(mx.cumsum(np_tensor(c) * 2.0), out)
+    assert np.allclose(out, np.cumsum(c * 2, axis=1), rtol=1e-5, atol=1e-5)
