@@ -207,6 +207,25 @@ static int run_checks() {
     for (index_t i = 0; i < n; ++i) for (index_t j = 0; j < n; ++j) em = std::max(em, std::fabs((double)p1(i, j) - p2(i, j)) / p1(i, j));
     report("softmax_impl(p, m, {0}, exec) column softmax", em <= 1e-5 && *b200.last_kernel(), b200.last_kernel(), em);
 
+    // cumsum: CUBTests.cu:203-226 (permuted int input) and batched float rows
+    {
+      auto inv = make_tensor<int>({3, 4});
+      inv.SetVals({{1, 2, 3, 4}, {10, 20, 30, 40}, {100, 200, 300, 400}});
+      auto c1 = make_tensor<int>({4, 3}), c2 = make_tensor<int>({4, 3});
+      (c1 = cumsum(inv.Permute({1, 0}))).run(ref); (c2 = cumsum(inv.Permute({1, 0}))).run(b200); ref.sync();
+      bool ok = true;
+      for (index_t i = 0; i < 4; ++i) { int run = 0; for (index_t j = 0; j < 3; ++j) { run += inv(j, i); ok = ok && c1(i, j) == run && c2(i, j) == run; } }
+      report("cumsum(inv.Permute({1,0})) int", ok && !strncmp(b200.last_kernel(), "scan|", 5), b200.last_kernel());
+      auto r1 = make_tensor<float>({n, n}), r2 = make_tensor<float>({n, n});
+      (r1 = cumsum(m)).run(ref); (r2 = cumsum(m)).run(b200); ref.sync();
+      double ec = 0;
+      for (index_t i = 0; i < n; ++i) for (index_t j = 0; j < n; ++j) ec = std::max(ec, std::fabs((double)r1(i, j) - r2(i, j)));
+      report("cumsum(m) 512 rows, one launch", ec <= 1e-4 && !strncmp(b200.last_kernel(), "scan|", 5), b200.last_kernel(), ec);
+      auto lx = make_tensor<float>({1 << 20}), l1 = make_tensor<float>({1 << 20}), l2 = make_tensor<float>({1 << 20});
+      for (index_t i = 0; i < (1 << 20); ++i) lx(i) = float((i * 7) % 5) - 2.f;
+      (l1 = cumsum(lx)).run(ref); (l2 = cumsum(lx)).run(b200); ref.sync();
+      report("cumsum(x) 2^20 in one row (tile exchange)", max_rel(l2, l1, 1 << 20) == 0 && !strncmp(b200.last_kernel(), "scan|", 5), b200.last_kernel());
+    }
     // permuted copy: bench/00_operators/operators.cu:40-59, scaled down
     auto x = make_tensor<float>({50, 40, 6, 30});
     std::mt19937 g(23);
@@ -315,6 +334,18 @@ static void run_bench() {
          time_ms(stream, 5, [&] { (t = a.Permute({1, 0})).run(b200); }));
     line("transpose fp32 8192x8192", "t = transpose_matrix(a) (reference's tiled kernel)", 2.0 * 4 * 8192 * 8192, time_ms(stream, 5, [&] { (t = transpose_matrix(a)).run(ref); }),
          time_ms(stream, 5, [&] { (t = a.Permute({1, 0})).run(b200); }));
+  }
+  {  // cumsum: many rows (the reference launches CUB once per row) and one long row
+    const index_t rows = 4096, cols = 8192;
+    auto x = make_tensor<float>({rows, cols}, MATX_DEVICE_MEMORY), y = make_tensor<float>({rows, cols}, MATX_DEVICE_MEMORY);
+    (x = random<float>({rows, cols}, UNIFORM)).run(ref);
+    line("cumsum fp32 4096x8192", "y = cumsum(x)", 2.0 * 4 * rows * cols, time_ms(stream, 2, [&] { (y = cumsum(x)).run(ref); }),
+         time_ms(stream, 5, [&] { (y = cumsum(x)).run(b200); }));
+    const index_t n = index_t(1) << 28;
+    auto lx = make_tensor<float>({n}, MATX_DEVICE_MEMORY), ly = make_tensor<float>({n}, MATX_DEVICE_MEMORY);
+    (lx = random<float>({n}, UNIFORM)).run(ref);
+    line("cumsum fp32 2^28", "y = cumsum(x)", 2.0 * 4 * n, time_ms(stream, 5, [&] { (ly = cumsum(lx)).run(ref); }),
+         time_ms(stream, 5, [&] { (ly = cumsum(lx)).run(b200); }));
   }
   {  // C5
     const index_t d = 1024;
