@@ -249,6 +249,11 @@ void aot_manifest(std::vector<ManifestItem> *items) {
       it.spec.U = u;
       it.spec.team = 0;
       items->push_back(it);
+      // warp-per-row twins for short rows: U = 1, and U = 2 for the 2- and 4-byte types
+      it.spec.team = 1;
+      const bool one_only = d == MXB_F64 || d == MXB_C64 || d == MXB_BF16;
+      it.spec.U = (u == 1 || one_only) ? 1 : 2;
+      if (!(u != 1 && one_only)) items->push_back(it);
     }
   // permuted copies (bench/00_operators/operators.cu:40-59) and the row + column mix
   for (int d : {MXB_F32, MXB_F64, MXB_C64, MXB_BF16, MXB_I32}) add(prog_identity(d), FAM_EW_TR, -1, d, 0, false);

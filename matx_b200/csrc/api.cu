@@ -1625,11 +1625,19 @@ int mxb_cumsum(mxb_handle_t h, const mxb_expr_t *expr_in, const mxb_out_t *out) 
   // (8-byte values: two chunks, or the 16 running values per thread spill)
   spec.U = (L > (int64_t)256 * V) ? (dtype_bytes(vt) >= 8 ? 2 : 4) : 1;
   if (env_int("MXB_TUNE_U", 0) > 0) spec.U = env_int("MXB_TUNE_U", 0);
+  // short rows, many of them: a warp per row (no shared memory, no barrier)
+  const bool warp_team = env_int("MXB_TUNE_TEAM", -1) >= 0 ? env_int("MXB_TUNE_TEAM", -1) == 1
+                                                          : (L <= (int64_t)2048 && B >= 4 * (int64_t)h->sm_count);
+  if (warp_team) {
+    spec.team = 1;
+    // two vector steps per lane and pass (one for 8-byte values): four spill at the 3-CTAs-per-SM register budget
+    spec.U = (dtype_bytes(vt) >= 8 || V > 4 || L <= (int64_t)32 * V) ? 1 : 2;
+  }
   const int64_t tile = (int64_t)256 * V * spec.U;
   const int64_t tpr = (L + tile - 1) / tile;
   const int sm = h->sm_count;
   // few long rows: one CTA per tile with the in-launch carry exchange; otherwise a CTA walks whole rows
-  bool tiles_mode = tpr > 1 && B < 2 * (int64_t)sm;
+  bool tiles_mode = !warp_team && tpr > 1 && B < 2 * (int64_t)sm;
   if (env_int("MXB_SCAN_MODE", 0) == 1) tiles_mode = false;
   if (env_int("MXB_SCAN_MODE", 0) == 2) tiles_mode = tpr > 1;
   if (tiles_mode && B * tpr > 0x7fffffff) tiles_mode = false;
@@ -1694,7 +1702,8 @@ int mxb_cumsum(mxb_handle_t h, const mxb_expr_t *expr_in, const mxb_out_t *out) 
     grid = (unsigned)(B * tpr);
   } else {
     const int tune_cps = env_int("MXB_TUNE_CTAS_PER_SM", 0);
-    grid = (unsigned)std::min<int64_t>(B, (int64_t)sm * (tune_cps > 0 ? tune_cps : 8));
+    const int64_t rows_per_cta = warp_team ? 8 : 1;
+    grid = (unsigned)std::min<int64_t>((B + rows_per_cta - 1) / rows_per_cta, (int64_t)sm * (tune_cps > 0 ? tune_cps : 8));
   }
   Kernel k;
   st = get_kernel(info, spec, &k);

@@ -2029,25 +2029,30 @@ __device__ __forceinline__ void ew_tr_body(const EwParams &p) {
   pdl_prologue();
   const int nd = p.nd, ydim = p.tr_ydim, xdim = nd - 1;
   const i64 SX = p.sz[xdim], SY = p.sz[ydim];
-  const i64 ntx = (SX + TX - 1) / TX, nty = (SY + TY - 1) / TY;
-  // CTA -> (outer index, x tile, y tile), y tiles fastest: neighbouring CTAs read neighbouring 256-byte runs
-  i64 b = blockIdx.x;
-  const i64 ty = b % nty; b /= nty;
-  const i64 tx = b % ntx; b /= ntx;
+  // CTA -> (outer index, x tile, y tile), y tiles fastest: neighbouring CTAs read neighbouring 256-byte runs.  The grid
+  // fits 31 bits (host rule), so every quotient here is a 32-bit division — the 64-bit ones cost more instructions
+  // than moving the tile does.
+  unsigned b = blockIdx.x;
+  const unsigned nty = (unsigned)((SY + TY - 1) / TY), ntx = (unsigned)((SX + TX - 1) / TX);
+  const unsigned ty = b % nty; b /= nty;
+  const unsigned tx = b % ntx; b /= ntx;
   i64 lofs[E::NL], oofs = 0;
 #pragma unroll
   for (int k = 0; k < E::NL; ++k) lofs[k] = 0;
 #pragma unroll
   for (int d = KMAXD - 1; d >= 0; --d) {
     if (d < nd - 1 && d != ydim) {
-      const i64 q = b / p.sz[d], i = b - q * p.sz[d];
+      const unsigned szd = (unsigned)p.sz[d];
+      const unsigned q = b / szd, i = b - q * szd;
       b = q;
 #pragma unroll
-      for (int k = 0; k < E::NL; ++k) lofs[k] += i * p.leaf[k].bs[d];
-      oofs += i * p.out.bs[d];
+      for (int k = 0; k < E::NL; ++k) lofs[k] += (i64)i * p.leaf[k].bs[d];
+      oofs += (i64)i * p.out.bs[d];
     }
   }
-  const i64 x0 = tx * TX, y0 = ty * TY;
+  const i64 x0 = (i64)tx * TX, y0 = (i64)ty * TY;
+  const int remx = (int)((SX - x0) < (i64)TX ? (SX - x0) : (i64)TX);   // valid extent of this tile
+  const int remy = (int)((SY - y0) < (i64)TY ? (SY - y0) : (i64)TY);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const unsigned ymask = p.tr_ymask;
 
@@ -2059,18 +2064,17 @@ __device__ __forceinline__ void ew_tr_body(const EwParams &p) {
       if (!((ymask >> k) & 1u)) continue;
       unsigned char *tile = tr_smem + (size_t)slot * TT::BYTES;
       ++slot;
-      const char *g = (const char *)p.leaf[k].ptr + (lofs[k] + y0) * EB;   // stride along Y is 1
       const i64 sx = p.leaf[k].bs[xdim];
+      const char *g = (const char *)p.leaf[k].ptr + (lofs[k] + y0 + x0 * sx) * EB;   // stride along Y is 1
 #pragma unroll
       for (int i = 0; i < V; ++i) {
         const int unit = warp + 8 * i;
         const int x = (unit >> 1) * 4 + (lane >> 3);
         const int cy = (unit & 1) * 8 + (lane & 7);
-        const i64 gx = x0 + x, gy = y0 + (i64)cy * V;
-        if (gx >= SX || gy >= SY) continue;
-        const char *src = g + (gx * sx + (i64)cy * V) * EB;
+        if (x >= remx || cy * V >= remy) continue;
+        const char *src = g + ((i64)x * sx + cy * V) * EB;
         unsigned char e[16];
-        const int n = (int)((SY - gy) < (i64)V ? (SY - gy) : (i64)V);
+        const int n = (remy - cy * V) < V ? (remy - cy * V) : V;
         if (p.tr_yvec && n == V) {
           LdBytes<16>::ld(e, src);
         } else {
@@ -2098,9 +2102,9 @@ __device__ __forceinline__ void ew_tr_body(const EwParams &p) {
     const int unit = warp + 8 * i;
     const int yy = unit * 2 + (lane >> 4);
     const int cx = lane & 15;
+    if (yy >= remy || cx * V >= remx) continue;
     const i64 gy = y0 + yy, gx = x0 + (i64)cx * V;
-    if (gy >= SY || gx >= SX) continue;
-    const int n = (int)((SX - gx) < (i64)V ? (SX - gx) : (i64)V);
+    const int n = (remx - cx * V) < V ? (remx - cx * V) : V;
     const char *sp[E::NL];
     const char *gp[E::NL];
     i64 ginner[E::NL];
@@ -2188,13 +2192,120 @@ __device__ __forceinline__ T warp_sum_published(const T *val, const u32 *flag, i
   return acc;
 }
 
+// fixed-order sum over the CTA (shuffle tree per warp, warp totals added in warp order); result in every thread
+template <class T, int NW> __device__ __forceinline__ T scan_block_sum(T v, T *s_red) {
+#pragma unroll
+  for (int m = 16; m > 0; m >>= 1) v = v + shfl_xor_t(v, m);
+  __syncthreads();                       // previous use of s_red is over
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  T tot = s_red[0];
+#pragma unroll
+  for (int w = 1; w < NW; ++w) tot = tot + s_red[w];
+  return tot;
+}
+
+// warp-per-row flavour for short rows: no shared memory, no barrier; a warp walks its rows in steps of 32 x U x V
+template <class E, class OutT, int V, int U, bool UNIT>
+__device__ __forceinline__ void scan_warp_body_impl(const RedParams &p) {
+  typedef typename E::value_type T;
+  const int lane = threadIdx.x & 31;
+  const i64 L = p.rsz[0];
+  const i64 STEP = (i64)32 * V * U;
+  const i64 w0 = (i64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), wstep = (i64)gridDim.x * (blockDim.x >> 5);
+  const i64 oinner = p.out_rs[0];
+  for (i64 b = w0; b < p.B; b += wstep) {
+    const char *base[E::NL];
+    i64 inner[E::NL];
+    i64 oo = 0;
+    {
+      i64 bidx[KMAXD];
+      decomp(b, p.nb, p.bsz, bidx);
+#pragma unroll
+      for (int k = 0; k < E::NL; ++k) {
+        i64 off = 0;
+#pragma unroll
+        for (int d = 0; d < KMAXD; ++d) if (d < p.nb) off += bidx[d] * p.leaf[k].bs[d];
+        base[k] = (const char *)p.leaf[k].ptr + off * E::leaf_bytes(k);
+        inner[k] = p.leaf[k].rs[0];
+      }
+#pragma unroll
+      for (int d = 0; d < KMAXD; ++d) if (d < p.nb) oo += bidx[d] * p.out.bs[d];
+    }
+    OutT *orow = (OutT *)p.out.ptr + oo;
+    T carry = scan_zero<T>();
+    for (i64 j0 = 0; j0 < L; j0 += STEP) {
+      T x[U][V];
+      {
+        typename E::template Regs<V> r[U];
+        bool full[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const i64 j = j0 + ((i64)u * 32 + lane) * V;
+          full[u] = V == 1 ? (j < L) : (j + V <= L);
+          if (full[u]) E::template loadv<V, UNIT>(r[u], base, inner, j);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const i64 j = j0 + ((i64)u * 32 + lane) * V;
+          if (full[u]) {
+#pragma unroll
+            for (int v = 0; v < V; ++v) x[u][v] = E::template eval<V>(r[u], v, p.c);
+          } else {
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+              x[u][v] = scan_zero<T>();
+              if (V > 1 && j + v < L) {
+                typename E::template Regs<1> r1;
+                E::template loadv<1, false>(r1, base, inner, j + v);
+                x[u][v] = E::template eval<1>(r1, 0, p.c);
+              }
+            }
+          }
+#pragma unroll
+          for (int v = 1; v < V; ++v) x[u][v] = x[u][v - 1] + x[u][v];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        T incl = x[u][V - 1];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const T o = shfl_up_t(incl, d);
+          if (lane >= d) incl = o + incl;
+        }
+        const T ex = shfl_up_t(incl, 1);
+        const T pre = lane == 0 ? carry : carry + ex;
+        const i64 j = j0 + ((i64)u * 32 + lane) * V;
+        Vec<OutT, V> o;
+#pragma unroll
+        for (int v = 0; v < V; ++v) o.v[v] = cvt<OutT>(pre + x[u][v]);
+        if (V > 1 && j + V <= L && oinner == 1 && p.tx) StBytes<(int)sizeof(OutT) * V>::st(orow + j, &o);
+        else {
+#pragma unroll
+          for (int v = 0; v < V; ++v) if (j + v < L) orow[(j + v) * oinner] = o.v[v];
+        }
+        // chunk total = the last lane's inclusive value, broadcast
+        enum { W = sizeof(T) / 4 };
+        union { T t; u32 w[W]; } a, c;
+        a.t = incl;
+#pragma unroll
+        for (int i = 0; i < W; ++i) c.w[i] = __shfl_sync(0xffffffffu, a.w[i], 31);
+        carry = carry + c.t;
+      }
+    }
+  }
+}
+
 template <class E, class OutT, int V, int U, bool UNIT>
 __device__ __forceinline__ void scan_inner_body_impl(const RedParams &p) {
   typedef typename E::value_type T;
   constexpr int NT = SCAN_NT, NW = NT / 32;
   __shared__ T s_warp[U][NW];   // warp totals of every chunk, then their exclusive prefixes
-  __shared__ T s_chunk[U + 1];  // chunk totals; [U] = carry into this tile (mode TILES)
+  __shared__ T s_chunk[U];      // chunk totals
+  __shared__ T s_red[NW + 1];   // mode TILES: scratch of the fixed-order block sums
   __shared__ i64 s_tile;
+  __shared__ int s_last;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const u32 epoch = p.scan_epoch;
   const i64 L = p.rsz[0];
@@ -2293,34 +2404,43 @@ __device__ __forceinline__ void scan_inner_body_impl(const RedParams &p) {
 #pragma unroll
       for (int u = 0; u < U; ++u) ctot[u] = s_chunk[u];
       if (tiles_mode) {
-        // ---- grid stage: publish, close the group if last, gather the carry ----
-        if (warp == 0) {
-          T total = ctot[0];
+        // ---- grid stage: publish, close the group if last, gather the carry (all 256 threads fetch in parallel:
+        // a lane-by-lane walk costs one L2 round trip per value and was 4x slower than the copy itself) ----
+        T total = ctot[0];
 #pragma unroll
-          for (int u = 1; u < U; ++u) total = total + ctot[u];
-          const i64 g = t / SCAN_GROUP, first = g * SCAN_GROUP;
-          const i64 gcount = (tpr - first) < SCAN_GROUP ? (tpr - first) : SCAN_GROUP;
-          T *agg = (T *)p.scan_agg + b * tpr;
-          T *gagg = (T *)p.scan_gagg + b * gpr;
-          u32 *aflag = p.scan_agg_flag + b * tpr, *gflag = p.scan_gagg_flag + b * gpr;
-          u32 last = 0;
-          if (lane == 0) {
-            st_cg_t(agg + t, total);
-            st_release_u32(aflag + t, epoch);
-            __threadfence();
-            last = atomicInc(p.scan_group_ticket + b * gpr + g, (u32)(gcount - 1)) == (u32)(gcount - 1);
-          }
-          last = __shfl_sync(0xffffffffu, last, 0);
-          if (last) {  // every tile of the group has published: its total, in tile order
-            const T gt = warp_sum_published(agg + first, aflag + first, gcount, epoch, lane);
-            if (lane == 0) { st_cg_t(gagg + g, gt); st_release_u32(gflag + g, epoch); }
-          }
-          const T cg = warp_sum_published(gagg, gflag, g, epoch, lane);
-          const T ct = warp_sum_published(agg + first, aflag + first, t - first, epoch, lane);
-          if (lane == 0) s_chunk[U] = cg + ct;
+        for (int u = 1; u < U; ++u) total = total + ctot[u];
+        const i64 g = t / SCAN_GROUP, first = g * SCAN_GROUP;
+        const i64 gcount = (tpr - first) < SCAN_GROUP ? (tpr - first) : SCAN_GROUP;
+        T *agg = (T *)p.scan_agg + b * tpr;
+        T *gagg = (T *)p.scan_gagg + b * gpr;
+        u32 *aflag = p.scan_agg_flag + b * tpr, *gflag = p.scan_gagg_flag + b * gpr;
+        if (tid == 0) {
+          st_cg_t(agg + t, total);
+          st_release_u32(aflag + t, epoch);
+          __threadfence();
+          s_last = atomicInc(p.scan_group_ticket + b * gpr + g, (u32)(gcount - 1)) == (u32)(gcount - 1);
         }
         __syncthreads();
-        carry = s_chunk[U];
+        if (s_last) {  // every tile of the group has published: the group's total, summed in a fixed order
+          T v = scan_zero<T>();
+          if (tid < gcount) {
+            while (ld_acquire_u32(aflag + first + tid) != epoch) __nanosleep(20);
+            v = ld_cg_t(agg + first + tid);
+          }
+          const T gt = scan_block_sum<T, NW>(v, s_red);
+          if (tid == 0) { st_cg_t(gagg + g, gt); st_release_u32(gflag + g, epoch); }
+        }
+        // carry = (totals of the groups before this one) + (totals of the tiles before this one in its group)
+        T acc = scan_zero<T>();
+        const i64 n1 = g, n2 = t - first;
+        for (i64 i = tid; i < n1 + n2; i += NT) {
+          const bool grp = i < n1;
+          const u32 *f = grp ? gflag + i : aflag + first + (i - n1);
+          const T *vp = grp ? gagg + i : agg + first + (i - n1);
+          while (ld_acquire_u32(f) != epoch) __nanosleep(20);
+          acc = acc + ld_cg_t(vp);
+        }
+        carry = scan_block_sum<T, NW>(acc, s_red);
       }
       // ---- finish: carry + chunk prefix + warp prefix + lane prefix + local scan, one vector store ----
       T cpre = carry;
@@ -2345,11 +2465,16 @@ __device__ __forceinline__ void scan_inner_body_impl(const RedParams &p) {
   }
 }
 
-template <class E, class OutT, int V, int U>
+template <class E, class OutT, int V, int U, int TEAM>
 __device__ __forceinline__ void scan_inner_body(const RedParams &p) {
   pdl_prologue();
-  if (p.all_unit) scan_inner_body_impl<E, OutT, V, U, true>(p);
-  else scan_inner_body_impl<E, OutT, V, U, false>(p);
+  if (TEAM == 1) {
+    if (p.all_unit) scan_warp_body_impl<E, OutT, V, U, true>(p);
+    else scan_warp_body_impl<E, OutT, V, U, false>(p);
+  } else {
+    if (p.all_unit) scan_inner_body_impl<E, OutT, V, U, true>(p);
+    else scan_inner_body_impl<E, OutT, V, U, false>(p);
+  }
 }
 
 }  // namespace mxb

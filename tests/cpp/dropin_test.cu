@@ -200,12 +200,20 @@ static int run_checks() {
     double em = 0;
     for (index_t i = 0; i < n; ++i) for (index_t j = 0; j < n; ++j) em = std::max(em, std::fabs((double)p1(i, j) - p2(i, j)) / p1(i, j));
     report("softmax_impl(p, m, {1}, exec) one launch", em <= 1e-5 && !strncmp(b200.last_kernel(), "softmax", 7), b200.last_kernel(), em);
-    softmax_impl(p1, m, cuda::std::array<int, 1>{0}, stream);
+    // Column softmax.  The reference's own dims overload is not usable as the yardstick here: its statistics line
+    // subtracts clone(tmp_max, clone_dims) — laid out for the UNPERMUTED input — from permute(in, perm)
+    // (transforms/reduce.h:438-440), so for a square matrix every element meets another column's max (2 % off; a
+    // non-square one throws on the size check).  Yardstick: the softmax of each column in fp64 on the host.
     softmax_impl(p2, m, cuda::std::array<int, 1>{0}, b200);
     ref.sync();
     em = 0;
-    for (index_t i = 0; i < n; ++i) for (index_t j = 0; j < n; ++j) em = std::max(em, std::fabs((double)p1(i, j) - p2(i, j)) / p1(i, j));
-    report("softmax_impl(p, m, {0}, exec) column softmax", em <= 1e-5 && *b200.last_kernel(), b200.last_kernel(), em);
+    for (index_t j = 0; j < n; ++j) {
+      double mxv = -1e300, sum = 0;
+      for (index_t i = 0; i < n; ++i) mxv = std::max(mxv, (double)m(i, j));
+      for (index_t i = 0; i < n; ++i) sum += std::exp((double)m(i, j) - mxv);
+      for (index_t i = 0; i < n; ++i) { const double t = std::exp((double)m(i, j) - mxv) / sum; em = std::max(em, std::fabs(t - p2(i, j)) / t); }
+    }
+    report("softmax_impl(p, m, {0}, exec) column softmax vs fp64", em <= 1e-5 && *b200.last_kernel(), b200.last_kernel(), em);
 
     // cumsum: CUBTests.cu:203-226 (permuted int input) and batched float rows
     {

@@ -53,7 +53,7 @@ def test_reference_known_answers(oracle):
 
 
 @pytest.mark.parametrize("shape", [(1,), (7,), (1023,), (1024,), (1025,), (4096,), (4097,), (20000,), (3, 5000), (300, 257), (2000, 64),
-                                   (5, 3, 1000), (1, 1 << 20), (2, 300001)])
+                                   (5, 3, 1000), (1, 1 << 20), (2, 300001), (5000, 100), (1000, 2048), (70000, 7), (600, 513)])
 def test_int32_exact_all_shapes(oracle, shape):
     """Integer sums do not care about the order of additions: every tiling / carry path must be bit-exact."""
     rng = np.random.default_rng(sum(shape))
@@ -71,6 +71,21 @@ def test_both_grid_modes_exact(oracle, mode):
         x = rng.integers(-50, 50, shape).astype(np.int32)
         got, want, k = run_cumsum(oracle, lambda t: t, [x], shape, A.I32, env={"MXB_SCAN_MODE": mode})
         assert np.array_equal(got, want), (mode, shape)
+
+
+def test_warp_and_cta_teams_agree_exactly(oracle):
+    rng = np.random.default_rng(55)
+    for shape in [(700, 64), (900, 1000), (3, 129)]:
+        x = rng.integers(-50, 50, shape).astype(np.int32)
+        for team in (0, 1):
+            got, want, k = run_cumsum(oracle, lambda t: t, [x], shape, A.I32, env={"MXB_TUNE_TEAM": team})
+            assert ("|T%d|" % team) in k + "|", k
+            assert np.array_equal(got, want), (team, shape)
+    xf = rng.random((800, 300)).astype(np.float32)
+    for team in (0, 1):
+        got, want, k = run_cumsum(oracle, lambda t: t, [xf], xf.shape, A.F32, env={"MXB_TUNE_TEAM": team})
+        truth = np.cumsum(xf.astype(np.float64), axis=1)
+        assert np.max(np.abs(got - truth) / truth) <= 1e-5
 
 
 @pytest.mark.parametrize("dt,tol", [(A.F32, 1e-5), (A.F64, 1e-12), (A.C64, 1e-5)])

@@ -62,11 +62,13 @@ def test_softmax_shapes(oracle, shape, dims, family, launches):
     x = (rng.standard_normal(shape) * 3).astype(np.float32)
     got, want, k, nl = run_softmax(oracle, lambda t: mx.softmax(t, dims), [x])
     assert family in k and nl == launches, (k, nl)
-    # the oracle's sequential fp32 sum is itself off by ~R * 2^-25 on long rows; fp64 truth is the tighter check there
-    R = int(np.prod([shape[d] for d in (dims if dims is not None else range(len(shape)))]))
-    assert close(got, want, 1e-5 if R <= 4096 else 1e-4), (k, np.abs(got - want).max())
+    # the bar: 1e-5 relative against fp64 truth (scipy is the reference's own golden generator)
     axis = None if dims is None else tuple(dims)
     assert np.allclose(got, special.softmax(x.astype(np.float64), axis=axis), rtol=1e-5, atol=1e-9)
+    # the oracle restates the reference's SEQUENTIAL fp32 sum, which is itself off by up to ~R * 2^-25 (measured 1.8e-4
+    # at R = 138880): agreement with it is checked to that bound, not tighter
+    R = int(np.prod([shape[d] for d in (dims if dims is not None else range(len(shape)))]))
+    assert close(got, want, max(1e-5, R * 2.0 ** -25)), (k, np.abs(got - want).max())
 
 
 def test_softmax_f64_and_bf16(oracle):

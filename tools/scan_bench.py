@@ -26,7 +26,7 @@ def timed(f, iters=10):
 def main():
     ex = mx.CudaExecutor()
     cases = [("f32 1 x 2^28", torch.float32, (1 << 28,)), ("f32 8 x 2^25", torch.float32, (8, 1 << 25)), ("f32 16384 x 4096", torch.float32, (16384, 4096)),
-             ("f32 65536 x 1024", torch.float32, (65536, 1024)), ("f32 1M x 64", torch.float32, (1 << 20, 64)), ("f32 300 x 100000", torch.float32, (300, 100000)),
+             ("f32 65536 x 1024", torch.float32, (65536, 1024)), ("f32 262144 x 256", torch.float32, (1 << 18, 256)), ("f32 1M x 64", torch.float32, (1 << 20, 64)), ("f32 300 x 100000", torch.float32, (300, 100000)),
              ("c64 65536 x 2048", torch.complex64, (65536, 2048)), ("f64 4096 x 16384", torch.float64, (4096, 16384)), ("bf16 16384 x 8192", torch.bfloat16, (16384, 8192)),
              ("i32 1 x 2^28", torch.int32, (1 << 28,))]
     for name, dt, shape in cases:
@@ -38,7 +38,7 @@ def main():
             x = torch.rand(*shape, device="cuda").to(dt)
         y = torch.empty_like(x)
         tx, ty = mx.make_tensor(x), mx.make_tensor(y)
-        for mode in ([0] if len(shape) == 1 or shape[0] >= 296 else [0, 1, 2]):
+        for mode in [0]:
             if mode:
                 os.environ["MXB_SCAN_MODE"] = str(mode)
             ms = timed(lambda: ty.set(mx.cumsum(tx)).run(ex))
