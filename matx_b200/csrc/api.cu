@@ -1365,7 +1365,11 @@ int mxb_elementwise(mxb_handle_t h, const mxb_expr_t *expr_in, const mxb_out_t *
   const int64_t want = (items + (int64_t)block * spec.U - 1) / ((int64_t)block * spec.U);
   // one U-batch per thread (no grid-stride wrap) unless told otherwise: the hardware block scheduler balances the
   // SMs better than a static persistent loop for pure streaming (sweep: profiles/r1_sweeps.md)
-  const int ew_cps = env_int("MXB_TUNE_CTAS_PER_SM", 0) > 0 ? env_int("MXB_TUNE_CTAS_PER_SM", 0) : 1000000;
+  // ... except for arithmetic-heavy programs (Black-Scholes: 27 nodes), which are bound by instruction issue, not by
+  // HBM: there a persistent grid of 32 CTAs per SM amortises the per-thread prologue (parameter loads, 64-bit index
+  // setup, ~100 instructions) over many batches — measured 1.196 -> 1.138 ms on config 4 (profiles/r1_sweeps.md)
+  const int ew_default_cps = e.n_nodes >= 16 ? 32 : 1000000;
+  const int ew_cps = env_int("MXB_TUNE_CTAS_PER_SM", 0) > 0 ? env_int("MXB_TUNE_CTAS_PER_SM", 0) : ew_default_cps;
   const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(want, (int64_t)h->sm_count * ew_cps), 0x7fffffff));
   Kernel k;
   st = get_kernel(info, spec, &k);

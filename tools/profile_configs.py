@@ -34,4 +34,12 @@ if "perm" in which:   # the reference's permute benchmark shape + a plain transp
     t = torch.empty(8192, 8192, device="cuda")
     mx.make_tensor(t).set(mx.make_tensor(a).Permute([1, 0])).run(ex)
     ex.sync()
+if "scan" in which:   # cumsum: many rows (row walker), one long row (tile exchange), short rows (warp per row)
+    for shape in ((16384, 4096), (1 << 28,), (1 << 18, 256)):
+        x = torch.rand(*shape, device="cuda")
+        y = torch.empty_like(x)
+        mx.make_tensor(y).set(mx.cumsum(mx.make_tensor(x))).run(ex)
+        ex.sync()
+        del x, y
+        torch.cuda.empty_cache()
 print("profiled", which)
