@@ -113,10 +113,49 @@ def run_c5(ex, peak):
     return {"sum(permute(t,{2,0,1}),{2}) bf16 1024^3": res}
 
 
+def run_next(ex, peak):
+    """SURVEY.md section 8f rows built after the five configs: the reference's own permute benchmark
+    (bench/00_operators/operators.cu:40-59), a plain transpose, and cumsum (transforms/cub.h:2367-2395)."""
+    import torch
+    res = {}
+    x = torch.randn(1000, 200, 6, 300, device="cuda")
+    y = torch.empty(300, 1000, 6, 200, device="cuda")
+    tx, ty = mx.make_tensor(x), mx.make_tensor(y)
+    ms, best = _time(ex, lambda: ty.set(tx.Permute([3, 0, 2, 1])).run(ex))
+    r = _entry(ex, ms, best, 2 * x.numel() * 4, x.numel(), peak)
+    r["bit_exact"] = bool(torch.equal(y, x.permute(3, 0, 2, 1)))
+    res["y = x.Permute({3,0,2,1}) fp32 {1000,200,6,300} (reference bench shape)"] = r
+    del x, y
+    a = torch.randn(8192, 8192, device="cuda")
+    t = torch.empty(8192, 8192, device="cuda")
+    ta, tt = mx.make_tensor(a), mx.make_tensor(t)
+    ms, best = _time(ex, lambda: tt.set(ta.Permute([1, 0])).run(ex))
+    r = _entry(ex, ms, best, 2 * a.numel() * 4, a.numel(), peak)
+    r["bit_exact"] = bool(torch.equal(t, a.t()))
+    res["t = a.Permute({1,0}) fp32 8192x8192"] = r
+    del a, t
+    torch.cuda.empty_cache()
+    for name, shape in (("cumsum(x) fp32 16384x4096", (16384, 4096)), ("cumsum(x) fp32 2^28 (one row)", (1 << 28,))):
+        x = torch.rand(*shape, device="cuda")
+        y = torch.empty_like(x)
+        tx, ty = mx.make_tensor(x), mx.make_tensor(y)
+        ms, best = _time(ex, lambda: ty.set(mx.cumsum(tx)).run(ex))
+        r = _entry(ex, ms, best, 2 * x.numel() * 4, x.numel(), peak)
+        m = 1 << 16
+        head = x.reshape(-1)[:m] if len(shape) == 1 else x[0, :m]
+        got = y.reshape(-1)[:m] if len(shape) == 1 else y[0, :m]
+        ref = head.double().cumsum(0)
+        r["max_rel_err_first_row_head_vs_fp64"] = ((got.double() - ref).abs() / ref).max().item()
+        res[name] = r
+        del x, y
+        torch.cuda.empty_cache()
+    return res
+
+
 def run_all(ex, peak):
     import torch
     out = {}
-    for f in (run_c1, run_c3, run_c4, run_c5):
+    for f in (run_c1, run_c3, run_c4, run_c5, run_next):
         try:
             out.update(f(ex, peak))
         except Exception as exc:  # report, do not hide

@@ -230,6 +230,7 @@ void aot_manifest(std::vector<ManifestItem> *items) {
     for (int team : {0, 1}) add(prog_abs2(MXB_C64), FAM_RED_INNER, op, MXB_F32, team, false);
   // config 4 and the reference's own elementwise benches
   add(prog_black_scholes(), FAM_EW, -1, MXB_F32, 0, false);
+  add(prog_black_scholes(), FAM_EW, -1, MXB_F32, 4, false);   // 4 CTAs per SM (64 registers): the dispatcher's choice for heavy programs
   add(prog_fma3(MXB_F32), FAM_EW, -1, MXB_F32, 0, false);
   for (int d : {MXB_F32, MXB_F64, MXB_C64}) add(prog_vector_add(d), FAM_EW, -1, d, 0, false);
   for (int d : {MXB_F32, MXB_BF16}) add(prog_identity(d), FAM_EW, -1, d, 0, d == MXB_F32);

@@ -1340,6 +1340,7 @@ int mxb_elementwise(mxb_handle_t h, const mxb_expr_t *expr_in, const mxb_out_t *
   spec.V = (vmax > 1 && vec_ok(vmax)) ? vmax : 1;
   spec.U = policy_unroll(info, spec.V, FAM_EW);
   if (env_int("MXB_TUNE_U", 0) > 0) spec.U = env_int("MXB_TUNE_U", 0);
+  spec.team = env_int("MXB_TUNE_MINBLOCKS", -1) >= 0 ? env_int("MXB_TUNE_MINBLOCKS", -1) : (e.n_nodes >= 16 ? 4 : 0);
 
   EwParams p;
   memset(&p, 0, sizeof p);
@@ -1703,7 +1704,8 @@ int mxb_cumsum(mxb_handle_t h, const mxb_expr_t *expr_in, const mxb_out_t *out) 
     p.scan_group_ticket = (unsigned *)(w + o_gt);
     p.scan_tile_counter = (unsigned *)(w + o_tc);
     p.scan_epoch = h->scan_epoch;
-    grid = (unsigned)(B * tpr);
+    // tile ids are fetched in order from the counter, so any grid works; 4 CTAs per SM covers what can be resident
+    grid = (unsigned)std::min<int64_t>(B * tpr, (int64_t)sm * 4);
   } else {
     const int tune_cps = env_int("MXB_TUNE_CTAS_PER_SM", 0);
     const int64_t rows_per_cta = warp_team ? 8 : 1;
@@ -1734,7 +1736,7 @@ int mxb_is_aot(const mxb_expr_t *expr, int reduce_op_or_minus1) {
   }
   spec.V = policy_vmax(info);
   spec.U = policy_unroll(info, spec.V, spec.family);
-  spec.team = 0;
+  spec.team = (reduce_op_or_minus1 < 0 && e.n_nodes >= 16) ? 4 : 0;   // the dispatcher's occupancy hint for heavy elementwise programs
   return lookup_aot(kernel_key(info, spec)) ? 1 : 0;
 }
 

@@ -515,7 +515,9 @@ int kernel_wrapper_src(const ExprInfo &info, const KernelSpec &s, const std::str
         << "(const __grid_constant__ mxb::RedParams p) { mxb::var_inner_tma_body<" << dtype_ctype(info.leaf_dtype[0]) << ", " << O << ", " << s.team << ">(p); }\n";
       break;
     case FAM_EW:
-      k << "extern \"C\" __global__ void __launch_bounds__(256) " << symbol
+      // team = minimum resident CTAs per SM asked of the compiler (0 = no cap): arithmetic-heavy programs trade a few
+      // registers for occupancy once the packed-fp32 body has taken them off the issue limit
+      k << "extern \"C\" __global__ void __launch_bounds__(256" << (s.team > 0 ? ", " + std::to_string(s.team) : std::string()) << ") " << symbol
         << "(const __grid_constant__ mxb::EwParams p) { mxb::ew_body<" << E << ", " << O << ", " << VU << ">(p); }\n";
       break;
     case FAM_SCAN:

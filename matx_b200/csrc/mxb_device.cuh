@@ -2304,7 +2304,7 @@ __device__ __forceinline__ void scan_inner_body_impl(const RedParams &p) {
   __shared__ T s_warp[U][NW];   // warp totals of every chunk, then their exclusive prefixes
   __shared__ T s_chunk[U];      // chunk totals
   __shared__ T s_red[NW + 1];   // mode TILES: scratch of the fixed-order block sums
-  __shared__ i64 s_tile;
+  __shared__ u32 s_next;        // mode TILES: id of the tile this CTA takes next
   __shared__ int s_last;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const u32 epoch = p.scan_epoch;
@@ -2314,154 +2314,193 @@ __device__ __forceinline__ void scan_inner_body_impl(const RedParams &p) {
   const bool tiles_mode = p.splits > 1;
   const i64 gpr = (tpr + SCAN_GROUP - 1) / SCAN_GROUP;
   const i64 total_tiles = p.B * tpr;
+  // TILES: tile ids come from an atomic counter, in order, one fetch per loop trip; every CTA's last fetch fails,
+  // so the counter wraps to zero after total_tiles + gridDim.x increments
+  const u32 fetch_wrap = (u32)(total_tiles + gridDim.x - 1);
+  const i64 oinner = p.out_rs[0];
 
-  i64 b = blockIdx.x, t = 0;       // ROWS: row b, tile t loops; TILES: one (b, t) per CTA
-  if (tiles_mode) {
-    if (tid == 0) s_tile = (i64)atomicInc(p.scan_tile_counter, (u32)(total_tiles - 1));
-    __syncthreads();
-    b = s_tile / tpr;
-    t = s_tile - b * tpr;
-  }
-  for (; b < p.B; b += gridDim.x) {
-    const char *base[E::NL];
-    i64 inner[E::NL];
+  const char *base[E::NL];
+  i64 inner[E::NL];
+#pragma unroll
+  for (int k = 0; k < E::NL; ++k) inner[k] = p.leaf[k].rs[0];
+  // row b: leaf row bases (for the loads) and the output row
+  auto setup_row = [&](i64 b) -> OutT * {
+    i64 bidx[KMAXD];
+    decomp(b, p.nb, p.bsz, bidx);
     i64 oo = 0;
-    {
-      i64 bidx[KMAXD];
-      decomp(b, p.nb, p.bsz, bidx);
 #pragma unroll
-      for (int k = 0; k < E::NL; ++k) {
-        i64 off = 0;
+    for (int k = 0; k < E::NL; ++k) {
+      i64 off = 0;
 #pragma unroll
-        for (int d = 0; d < KMAXD; ++d) if (d < p.nb) off += bidx[d] * p.leaf[k].bs[d];
-        base[k] = (const char *)p.leaf[k].ptr + off * E::leaf_bytes(k);
-        inner[k] = p.leaf[k].rs[0];
-      }
-#pragma unroll
-      for (int d = 0; d < KMAXD; ++d) if (d < p.nb) oo += bidx[d] * p.out.bs[d];
+      for (int d = 0; d < KMAXD; ++d) if (d < p.nb) off += bidx[d] * p.leaf[k].bs[d];
+      base[k] = (const char *)p.leaf[k].ptr + off * E::leaf_bytes(k);
     }
-    OutT *orow = (OutT *)p.out.ptr + oo;
-    const i64 oinner = p.out_rs[0];
-    T carry = scan_zero<T>();
-    for (i64 tt = tiles_mode ? t : 0; tt < (tiles_mode ? t + 1 : tpr); ++tt) {
-      const i64 j0 = tt * TILE;
-      // ---- load + evaluate + thread-local scan ----
-      T x[U][V];
-      {
-        typename E::template Regs<V> r[U];
-        bool full[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const i64 j = j0 + ((i64)u * NT + tid) * V;
-          full[u] = V == 1 ? (j < L) : (j + V <= L);
-          if (full[u]) E::template loadv<V, UNIT>(r[u], base, inner, j);
-        }
+    for (int d = 0; d < KMAXD; ++d) if (d < p.nb) oo += bidx[d] * p.out.bs[d];
+    return (OutT *)p.out.ptr + oo;
+  };
+
+  // ---- first work item ----
+  i64 cb, ct;   // current row, current tile of it
+  if (tiles_mode) {
+    if (tid == 0) s_next = atomicInc(p.scan_tile_counter, fetch_wrap);
+    __syncthreads();
+    const i64 g = (i64)s_next;
+    __syncthreads();   // s_next is rewritten at the top of the loop
+    if (g >= total_tiles) return;
+    cb = g / tpr;
+    ct = g - cb * tpr;
+  } else {
+    cb = blockIdx.x;
+    ct = 0;
+    if (cb >= p.B) return;
+  }
+  OutT *orow = setup_row(cb);
+  typename E::template Regs<V> r[U];
+  bool full[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const i64 j = j0 + ((i64)u * NT + tid) * V;
-          if (full[u]) {
+  for (int u = 0; u < U; ++u) {
+    const i64 j = ct * TILE + ((i64)u * NT + tid) * V;
+    full[u] = V == 1 ? (j < L) : (j + V <= L);
+    if (full[u]) E::template loadv<V, UNIT>(r[u], base, inner, j);
+  }
+  T carry = scan_zero<T>();
+
+  while (true) {
+    if (tiles_mode && tid == 0) s_next = atomicInc(p.scan_tile_counter, fetch_wrap);   // lands before barrier (A)
+    const i64 j0 = ct * TILE;
+    // ---- evaluate + thread-local scan of the tile whose loads were issued one trip ago ----
+    T x[U][V];
 #pragma unroll
-            for (int v = 0; v < V; ++v) x[u][v] = E::template eval<V>(r[u], v, p.c);
-          } else {
+    for (int u = 0; u < U; ++u) {
+      const i64 j = j0 + ((i64)u * NT + tid) * V;
+      if (full[u]) {
 #pragma unroll
-            for (int v = 0; v < V; ++v) {
-              x[u][v] = scan_zero<T>();
-              if (V > 1 && j + v < L) {
-                typename E::template Regs<1> r1;
-                E::template loadv<1, false>(r1, base, inner, j + v);
-                x[u][v] = E::template eval<1>(r1, 0, p.c);
-              }
-            }
+        for (int v = 0; v < V; ++v) x[u][v] = E::template eval<V>(r[u], v, p.c);
+      } else {
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          x[u][v] = scan_zero<T>();
+          if (V > 1 && j + v < L) {
+            typename E::template Regs<1> r1;
+            E::template loadv<1, false>(r1, base, inner, j + v);
+            x[u][v] = E::template eval<1>(r1, 0, p.c);
           }
-#pragma unroll
-          for (int v = 1; v < V; ++v) x[u][v] = x[u][v - 1] + x[u][v];
         }
       }
-      // ---- warp stage: inclusive scan of the thread totals, U chunks at once ----
-      T wexcl[U];
+#pragma unroll
+      for (int v = 1; v < V; ++v) x[u][v] = x[u][v - 1] + x[u][v];
+    }
+    // ---- warp stage: inclusive scan of the thread totals, U chunks at once ----
+    T wexcl[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      T incl = x[u][V - 1];
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const T o = shfl_up_t(incl, d);
+        if (lane >= d) incl = o + incl;
+      }
+      const T ex = shfl_up_t(incl, 1);
+      wexcl[u] = lane == 0 ? scan_zero<T>() : ex;
+      if (lane == 31) s_warp[u][warp] = incl;
+    }
+    __syncthreads();   // (A)
+    // ---- the NEXT tile's loads go out now: they fly while this tile goes through the CTA / grid stages ----
+    i64 nb, nt;
+    if (tiles_mode) {
+      const i64 g = (i64)s_next;
+      nb = g < total_tiles ? g / tpr : p.B;
+      nt = g - nb * tpr;
+    } else {
+      nb = ct + 1 < tpr ? cb : cb + gridDim.x;
+      nt = ct + 1 < tpr ? ct + 1 : 0;
+    }
+    const bool more = nb < p.B;
+    OutT *orow_next = orow;
+    bool full_next[U];
+    if (more) {
+      if (nb != cb) orow_next = setup_row(nb);
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        T incl = x[u][V - 1];
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-          const T o = shfl_up_t(incl, d);
-          if (lane >= d) incl = o + incl;
-        }
-        const T ex = shfl_up_t(incl, 1);
-        wexcl[u] = lane == 0 ? scan_zero<T>() : ex;
-        if (lane == 31) s_warp[u][warp] = incl;
+        const i64 j = nt * TILE + ((i64)u * NT + tid) * V;
+        full_next[u] = V == 1 ? (j < L) : (j + V <= L);
+        if (full_next[u]) E::template loadv<V, UNIT>(r[u], base, inner, j);
       }
-      __syncthreads();
-      // ---- CTA stage: thread u turns chunk u's warp totals into exclusive prefixes and the chunk total ----
-      if (tid < U) {
-        T run = scan_zero<T>();
-#pragma unroll
-        for (int w = 0; w < NW; ++w) { const T v = s_warp[tid][w]; s_warp[tid][w] = run; run = run + v; }
-        s_chunk[tid] = run;
-      }
-      __syncthreads();
-      T ctot[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) ctot[u] = s_chunk[u];
-      if (tiles_mode) {
-        // ---- grid stage: publish, close the group if last, gather the carry (all 256 threads fetch in parallel:
-        // a lane-by-lane walk costs one L2 round trip per value and was 4x slower than the copy itself) ----
-        T total = ctot[0];
-#pragma unroll
-        for (int u = 1; u < U; ++u) total = total + ctot[u];
-        const i64 g = t / SCAN_GROUP, first = g * SCAN_GROUP;
-        const i64 gcount = (tpr - first) < SCAN_GROUP ? (tpr - first) : SCAN_GROUP;
-        T *agg = (T *)p.scan_agg + b * tpr;
-        T *gagg = (T *)p.scan_gagg + b * gpr;
-        u32 *aflag = p.scan_agg_flag + b * tpr, *gflag = p.scan_gagg_flag + b * gpr;
-        if (tid == 0) {
-          st_cg_t(agg + t, total);
-          st_release_u32(aflag + t, epoch);
-          __threadfence();
-          s_last = atomicInc(p.scan_group_ticket + b * gpr + g, (u32)(gcount - 1)) == (u32)(gcount - 1);
-        }
-        __syncthreads();
-        if (s_last) {  // every tile of the group has published: the group's total, summed in a fixed order
-          T v = scan_zero<T>();
-          if (tid < gcount) {
-            while (ld_acquire_u32(aflag + first + tid) != epoch) __nanosleep(20);
-            v = ld_cg_t(agg + first + tid);
-          }
-          const T gt = scan_block_sum<T, NW>(v, s_red);
-          if (tid == 0) { st_cg_t(gagg + g, gt); st_release_u32(gflag + g, epoch); }
-        }
-        // carry = (totals of the groups before this one) + (totals of the tiles before this one in its group)
-        T acc = scan_zero<T>();
-        const i64 n1 = g, n2 = t - first;
-        for (i64 i = tid; i < n1 + n2; i += NT) {
-          const bool grp = i < n1;
-          const u32 *f = grp ? gflag + i : aflag + first + (i - n1);
-          const T *vp = grp ? gagg + i : agg + first + (i - n1);
-          while (ld_acquire_u32(f) != epoch) __nanosleep(20);
-          acc = acc + ld_cg_t(vp);
-        }
-        carry = scan_block_sum<T, NW>(acc, s_red);
-      }
-      // ---- finish: carry + chunk prefix + warp prefix + lane prefix + local scan, one vector store ----
-      T cpre = carry;
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const i64 j = j0 + ((i64)u * NT + tid) * V;
-        const T pre = (cpre + s_warp[u][warp]) + wexcl[u];
-        Vec<OutT, V> o;
-#pragma unroll
-        for (int v = 0; v < V; ++v) o.v[v] = cvt<OutT>(pre + x[u][v]);
-        if (V > 1 && j + V <= L && oinner == 1 && p.tx) StBytes<(int)sizeof(OutT) * V>::st(orow + j, &o);
-        else {
-#pragma unroll
-          for (int v = 0; v < V; ++v) if (j + v < L) orow[(j + v) * oinner] = o.v[v];
-        }
-        cpre = cpre + ctot[u];
-      }
-      carry = cpre;
-      __syncthreads();   // s_warp / s_chunk are reused by the next tile
     }
-    if (tiles_mode) break;
+    // ---- CTA stage: thread u turns chunk u's warp totals into exclusive prefixes and the chunk total ----
+    if (tid < U) {
+      T run = scan_zero<T>();
+#pragma unroll
+      for (int w = 0; w < NW; ++w) { const T v = s_warp[tid][w]; s_warp[tid][w] = run; run = run + v; }
+      s_chunk[tid] = run;
+    }
+    __syncthreads();   // (B)
+    T ctot[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) ctot[u] = s_chunk[u];
+    if (tiles_mode) {
+      // ---- grid stage: publish, close the group if last, gather the carry (all threads fetch in parallel) ----
+      T total = ctot[0];
+#pragma unroll
+      for (int u = 1; u < U; ++u) total = total + ctot[u];
+      const i64 g = ct / SCAN_GROUP, first = g * SCAN_GROUP;
+      const i64 gcount = (tpr - first) < SCAN_GROUP ? (tpr - first) : SCAN_GROUP;
+      T *agg = (T *)p.scan_agg + cb * tpr;
+      T *gagg = (T *)p.scan_gagg + cb * gpr;
+      u32 *aflag = p.scan_agg_flag + cb * tpr, *gflag = p.scan_gagg_flag + cb * gpr;
+      if (tid == 0) {
+        st_cg_t(agg + ct, total);
+        st_release_u32(aflag + ct, epoch);
+        __threadfence();
+        s_last = atomicInc(p.scan_group_ticket + cb * gpr + g, (u32)(gcount - 1)) == (u32)(gcount - 1);
+      }
+      __syncthreads();
+      if (s_last) {  // every tile of the group has published: the group's total, summed in a fixed order
+        T v = scan_zero<T>();
+        if (tid < gcount) {
+          while (ld_acquire_u32(aflag + first + tid) != epoch) __nanosleep(20);
+          v = ld_cg_t(agg + first + tid);
+        }
+        const T gt = scan_block_sum<T, NW>(v, s_red);
+        if (tid == 0) { st_cg_t(gagg + g, gt); st_release_u32(gflag + g, epoch); }
+      }
+      // carry = (totals of the groups before this one) + (totals of the tiles before this one in its group)
+      T acc = scan_zero<T>();
+      const i64 n1 = g, n2 = ct - first;
+      for (i64 i = tid; i < n1 + n2; i += NT) {
+        const bool grp = i < n1;
+        const u32 *f = grp ? gflag + i : aflag + first + (i - n1);
+        const T *vp = grp ? gagg + i : agg + first + (i - n1);
+        while (ld_acquire_u32(f) != epoch) __nanosleep(20);
+        acc = acc + ld_cg_t(vp);
+      }
+      carry = scan_block_sum<T, NW>(acc, s_red);
+    }
+    // ---- finish: carry + chunk prefix + warp prefix + lane prefix + local scan, one vector store ----
+    T cpre = carry;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const i64 j = j0 + ((i64)u * NT + tid) * V;
+      const T pre = (cpre + s_warp[u][warp]) + wexcl[u];
+      Vec<OutT, V> o;
+#pragma unroll
+      for (int v = 0; v < V; ++v) o.v[v] = cvt<OutT>(pre + x[u][v]);
+      if (V > 1 && j + V <= L && oinner == 1 && p.tx) StBytes<(int)sizeof(OutT) * V>::st(orow + j, &o);
+      else {
+#pragma unroll
+        for (int v = 0; v < V; ++v) if (j + v < L) orow[(j + v) * oinner] = o.v[v];
+      }
+      cpre = cpre + ctot[u];
+    }
+    if (!more) break;
+    carry = (!tiles_mode && nb == cb) ? cpre : scan_zero<T>();
+    cb = nb;
+    ct = nt;
+    orow = orow_next;
+#pragma unroll
+    for (int u = 0; u < U; ++u) full[u] = full_next[u];
+    __syncthreads();   // (C) s_warp / s_chunk / s_next are reused by the next trip
   }
 }
 
