@@ -1705,7 +1705,9 @@ int mxb_cumsum(mxb_handle_t h, const mxb_expr_t *expr_in, const mxb_out_t *out) 
     p.scan_tile_counter = (unsigned *)(w + o_tc);
     p.scan_epoch = h->scan_epoch;
     // tile ids are fetched in order from the counter, so any grid works; 4 CTAs per SM covers what can be resident
-    grid = (unsigned)std::min<int64_t>(B * tpr, (int64_t)sm * 4);
+    const int per_sm = env_int("MXB_SCAN_GRID_PER_SM", 0) > 0 ? env_int("MXB_SCAN_GRID_PER_SM", 0) : 4;
+    grid = (unsigned)std::min<int64_t>(B * tpr, (int64_t)sm * per_sm);
+    p.scan_flags = (unsigned)env_int("MXB_SCAN_FLAGS", 0);
   } else {
     const int tune_cps = env_int("MXB_TUNE_CTAS_PER_SM", 0);
     const int64_t rows_per_cta = warp_team ? 8 : 1;

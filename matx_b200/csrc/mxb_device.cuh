@@ -118,6 +118,7 @@ struct RedParams {
   void *scan_agg, *scan_gagg;
   u32 *scan_agg_flag, *scan_gagg_flag, *scan_group_ticket, *scan_tile_counter;
   u32 scan_epoch;
+  u32 scan_flags;   // bit 0: TILES mode issues the next tile's loads before publishing (experiment knob)
 };
 
 // elementwise: up to KMAXD collapsed dims, innermost last
@@ -2419,15 +2420,21 @@ __device__ __forceinline__ void scan_inner_body_impl(const RedParams &p) {
     const bool more = nb < p.B;
     OutT *orow_next = orow;
     bool full_next[U];
-    if (more) {
-      if (nb != cb) orow_next = setup_row(nb);
+    auto prefetch = [&]() {
+      if (more) {
+        if (nb != cb) orow_next = setup_row(nb);
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const i64 j = nt * TILE + ((i64)u * NT + tid) * V;
-        full_next[u] = V == 1 ? (j < L) : (j + V <= L);
-        if (full_next[u]) E::template loadv<V, UNIT>(r[u], base, inner, j);
+        for (int u = 0; u < U; ++u) {
+          const i64 j = nt * TILE + ((i64)u * NT + tid) * V;
+          full_next[u] = V == 1 ? (j < L) : (j + V <= L);
+          if (full_next[u]) E::template loadv<V, UNIT>(r[u], base, inner, j);
+        }
       }
-    }
+    };
+    // ROWS: right away.  TILES: only after this tile's total is published — a release store waits for the thread's
+    // earlier loads, and every other tile's carry waits for that store
+    const bool early = !tiles_mode || (p.scan_flags & 1);
+    if (early) prefetch();
     // ---- CTA stage: thread u turns chunk u's warp totals into exclusive prefixes and the chunk total ----
     if (tid < U) {
       T run = scan_zero<T>();
@@ -2465,6 +2472,7 @@ __device__ __forceinline__ void scan_inner_body_impl(const RedParams &p) {
         const T gt = scan_block_sum<T, NW>(v, s_red);
         if (tid == 0) { st_cg_t(gagg + g, gt); st_release_u32(gflag + g, epoch); }
       }
+      if (!early) prefetch();
       // carry = (totals of the groups before this one) + (totals of the tiles before this one in its group)
       T acc = scan_zero<T>();
       const i64 n1 = g, n2 = ct - first;
