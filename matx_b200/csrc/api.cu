@@ -1685,13 +1685,13 @@ int mxb_cumsum(mxb_handle_t h, const mxb_expr_t *expr_in, const mxb_out_t *out) 
       h->scan_cap_groups = std::max<size_t>(std::max(need_g, h->scan_cap_groups), 1024);
       const size_t nb = h->scan_cap_tiles * 12 + h->scan_cap_groups * 16 + 1024;
       MXB_CUDA(cudaMallocAsync(&h->scan_ws, nb, h->stream));
-      MXB_CUDA(cudaMemsetAsync(h->scan_ws, 0, nb, h->stream));   // flags 0 = no epoch, counters at rest
+      MXB_CUDA(cudaMemsetAsync(h->scan_ws, 0, nb, h->stream));   // flags 0 = no epoch
       h->scan_ws_bytes = nb;
       h->scan_epoch = 0;
     }
     const size_t o_agg = 0, o_gagg = o_agg + h->scan_cap_tiles * 8, o_af = o_gagg + h->scan_cap_groups * 8,
-                 o_gf = o_af + h->scan_cap_tiles * 4, o_gt = o_gf + h->scan_cap_groups * 4, o_tc = o_gt + h->scan_cap_groups * 4;
-    // counters are at rest (zero) between launches, flags are epoch-coded: nothing to clear
+                 o_gf = o_af + h->scan_cap_tiles * 4;
+    // flags are epoch-coded: nothing to clear between launches
     if (++h->scan_epoch == 0) {   // 2^32 launches later: start over
       MXB_CUDA(cudaMemsetAsync(h->scan_ws, 0, h->scan_ws_bytes, h->stream));
       h->scan_epoch = 1;
@@ -1701,11 +1701,10 @@ int mxb_cumsum(mxb_handle_t h, const mxb_expr_t *expr_in, const mxb_out_t *out) 
     p.scan_gagg = w + o_gagg;
     p.scan_agg_flag = (unsigned *)(w + o_af);
     p.scan_gagg_flag = (unsigned *)(w + o_gf);
-    p.scan_group_ticket = (unsigned *)(w + o_gt);
-    p.scan_tile_counter = (unsigned *)(w + o_tc);
     p.scan_epoch = h->scan_epoch;
-    // tile ids are fetched in order from the counter, so any grid works; 4 CTAs per SM covers what can be resident
-    const int per_sm = env_int("MXB_SCAN_GRID_PER_SM", 0) > 0 ? env_int("MXB_SCAN_GRID_PER_SM", 0) : 4;
+    // tiles are dealt round-robin to the grid and a tile waits for its predecessors, so every CTA must be resident:
+    // the kernels are built with __launch_bounds__(256, 3), which guarantees 3 CTAs per SM
+    const int per_sm = env_int("MXB_SCAN_GRID_PER_SM", 0) > 0 ? std::min(env_int("MXB_SCAN_GRID_PER_SM", 0), 3) : 3;
     grid = (unsigned)std::min<int64_t>(B * tpr, (int64_t)sm * per_sm);
     p.scan_flags = (unsigned)env_int("MXB_SCAN_FLAGS", 0);
   } else {

@@ -114,9 +114,9 @@ struct RedParams {
   // flag[r] = rank r's arrival counters u32[world], epoch = this rank's count of completed exchanges
   PeerPush peer;
   i64 out_rs[KMAXD];  // softmax / scan: strides of the output over the reduce dims
-  // scan family only: the handle's scan workspace (tile / group totals, epoch-coded flags, self-resetting counters)
+  // scan family only: the handle's scan workspace (tile / group totals, epoch-coded flags)
   void *scan_agg, *scan_gagg;
-  u32 *scan_agg_flag, *scan_gagg_flag, *scan_group_ticket, *scan_tile_counter;
+  u32 *scan_agg_flag, *scan_gagg_flag;
   u32 scan_epoch;
   u32 scan_flags;   // bit 0: TILES mode issues the next tile's loads before publishing (experiment knob)
 };
@@ -2147,20 +2147,23 @@ __device__ __forceinline__ void ew_tr_body(const EwParams &p) {
 // coalesced), scans them in registers, the warp scans the thread totals with shuffles, the eight warp totals of the U
 // chunks meet in shared memory.  All additions happen in a FIXED order, so results are run-to-run deterministic.
 //   mode ROWS  (p.splits == 1): a CTA owns whole rows and walks their tiles with a carry in a register.
-//   mode TILES (p.splits  > 1): few long rows -> every tile is its own CTA (tile ids handed out in order by an
-//     atomic counter, so a tile only ever waits for tiles that are already running).  A tile publishes its total,
-//     the LAST tile of each group of SCAN_GROUP tiles to do so publishes the group's total, and a tile's carry is
-//     (totals of the groups before its own) + (totals of the tiles before it in its group): two flat, fixed-order
-//     sums of at most a few hundred L2-resident values — no serial chain between tiles, and no dependence on which
-//     neighbour happened to finish first (CUB's look-back adds whatever it finds, so its float sums vary from run to
-//     run).  Flags carry the launch epoch, counters wrap to zero: nothing is cleared between launches.
+//   mode TILES (p.splits  > 1): few long rows -> the tiles of all rows are dealt round-robin to a grid of co-resident
+//     CTAs (3 per SM, which the launch bounds guarantee), so a tile only ever waits for tiles that are running or
+//     done.  A tile publishes its total; the LAST tile of each group of SCAN_GROUP tiles also publishes the group's
+//     total; a tile's carry is (totals of the groups before its own) + (totals of the tiles before it in its group):
+//     two flat, fixed-order sums of at most a few hundred L2-resident values gathered by all 256 threads at once — no
+//     serial chain between tiles, no atomics (a tile counter on one address serialises at ~13 ns per tile, which was
+//     the whole run time of the first version), and no dependence on which neighbour happened to finish first (CUB's
+//     look-back adds whatever it finds, so its float sums vary from run to run).  Flags carry the launch epoch:
+//     nothing is cleared between launches.
+//   Both modes keep the NEXT tile's loads in flight while the current tile goes through its barriers and its carry
+//   exchange (the loads are issued into the registers the evaluation has just freed).
 // ------------------------------------------------------------------------------------------------
 constexpr int SCAN_NT = 256;
 constexpr int SCAN_GROUP = 128;
 
 // workspace (RedParams::scan_*): agg = T[B * tiles_per_row] tile totals, gagg = T[B * groups_per_row] group totals,
-// *_flag == launch epoch once the value is valid, group_ticket = arrivals per group and tile_counter = next tile id
-// (both atomicInc with wrap-around, so they are zero again when the launch ends)
+// *_flag == launch epoch once the value is valid
 
 __device__ __forceinline__ u32 ld_acquire_u32(const u32 *p) {
   u32 v;
@@ -2305,8 +2308,6 @@ __device__ __forceinline__ void scan_inner_body_impl(const RedParams &p) {
   __shared__ T s_warp[U][NW];   // warp totals of every chunk, then their exclusive prefixes
   __shared__ T s_chunk[U];      // chunk totals
   __shared__ T s_red[NW + 1];   // mode TILES: scratch of the fixed-order block sums
-  __shared__ u32 s_next;        // mode TILES: id of the tile this CTA takes next
-  __shared__ int s_last;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const u32 epoch = p.scan_epoch;
   const i64 L = p.rsz[0];
@@ -2315,9 +2316,6 @@ __device__ __forceinline__ void scan_inner_body_impl(const RedParams &p) {
   const bool tiles_mode = p.splits > 1;
   const i64 gpr = (tpr + SCAN_GROUP - 1) / SCAN_GROUP;
   const i64 total_tiles = p.B * tpr;
-  // TILES: tile ids come from an atomic counter, in order, one fetch per loop trip; every CTA's last fetch fails,
-  // so the counter wraps to zero after total_tiles + gridDim.x increments
-  const u32 fetch_wrap = (u32)(total_tiles + gridDim.x - 1);
   const i64 oinner = p.out_rs[0];
 
   const char *base[E::NL];
@@ -2343,14 +2341,11 @@ __device__ __forceinline__ void scan_inner_body_impl(const RedParams &p) {
 
   // ---- first work item ----
   i64 cb, ct;   // current row, current tile of it
+  i64 gid = blockIdx.x;   // TILES: global tile id, advanced by gridDim.x per trip
   if (tiles_mode) {
-    if (tid == 0) s_next = atomicInc(p.scan_tile_counter, fetch_wrap);
-    __syncthreads();
-    const i64 g = (i64)s_next;
-    __syncthreads();   // s_next is rewritten at the top of the loop
-    if (g >= total_tiles) return;
-    cb = g / tpr;
-    ct = g - cb * tpr;
+    if (gid >= total_tiles) return;
+    cb = gid / tpr;
+    ct = gid - cb * tpr;
   } else {
     cb = blockIdx.x;
     ct = 0;
@@ -2368,7 +2363,6 @@ __device__ __forceinline__ void scan_inner_body_impl(const RedParams &p) {
   T carry = scan_zero<T>();
 
   while (true) {
-    if (tiles_mode && tid == 0) s_next = atomicInc(p.scan_tile_counter, fetch_wrap);   // lands before barrier (A)
     const i64 j0 = ct * TILE;
     // ---- evaluate + thread-local scan of the tile whose loads were issued one trip ago ----
     T x[U][V];
@@ -2410,7 +2404,7 @@ __device__ __forceinline__ void scan_inner_body_impl(const RedParams &p) {
     // ---- the NEXT tile's loads go out now: they fly while this tile goes through the CTA / grid stages ----
     i64 nb, nt;
     if (tiles_mode) {
-      const i64 g = (i64)s_next;
+      const i64 g = gid + gridDim.x;
       nb = g < total_tiles ? g / tpr : p.B;
       nt = g - nb * tpr;
     } else {
@@ -2459,31 +2453,37 @@ __device__ __forceinline__ void scan_inner_body_impl(const RedParams &p) {
       if (tid == 0) {
         st_cg_t(agg + ct, total);
         st_release_u32(aflag + ct, epoch);
-        __threadfence();
-        s_last = atomicInc(p.scan_group_ticket + cb * gpr + g, (u32)(gcount - 1)) == (u32)(gcount - 1);
-      }
-      __syncthreads();
-      if (s_last) {  // every tile of the group has published: the group's total, summed in a fixed order
-        T v = scan_zero<T>();
-        if (tid < gcount) {
-          while (ld_acquire_u32(aflag + first + tid) != epoch) __nanosleep(20);
-          v = ld_cg_t(agg + first + tid);
-        }
-        const T gt = scan_block_sum<T, NW>(v, s_red);
-        if (tid == 0) { st_cg_t(gagg + g, gt); st_release_u32(gflag + g, epoch); }
       }
       if (!early) prefetch();
-      // carry = (totals of the groups before this one) + (totals of the tiles before this one in its group)
-      T acc = scan_zero<T>();
       const i64 n1 = g, n2 = ct - first;
-      for (i64 i = tid; i < n1 + n2; i += NT) {
-        const bool grp = i < n1;
-        const u32 *f = grp ? gflag + i : aflag + first + (i - n1);
-        const T *vp = grp ? gagg + i : agg + first + (i - n1);
-        while (ld_acquire_u32(f) != epoch) __nanosleep(20);
-        acc = acc + ld_cg_t(vp);
+      if (ct == first + gcount - 1) {
+        // last tile of its group: the group's total goes out first (it needs the group's own tiles only), then the
+        // totals of the earlier groups are gathered for this tile's carry
+        T a = scan_zero<T>();
+        for (i64 i = tid; i < n2; i += NT) {
+          while (ld_acquire_u32(aflag + first + i) != epoch) __nanosleep(20);
+          a = a + ld_cg_t(agg + first + i);
+        }
+        const T stiles = scan_block_sum<T, NW>(a, s_red);
+        if (tid == 0) { st_cg_t(gagg + g, stiles + total); st_release_u32(gflag + g, epoch); }
+        a = scan_zero<T>();
+        for (i64 i = tid; i < n1; i += NT) {
+          while (ld_acquire_u32(gflag + i) != epoch) __nanosleep(20);
+          a = a + ld_cg_t(gagg + i);
+        }
+        carry = scan_block_sum<T, NW>(a, s_red) + stiles;
+      } else {
+        // carry = (totals of the groups before this one) + (totals of the tiles before this one in its group)
+        T acc = scan_zero<T>();
+        for (i64 i = tid; i < n1 + n2; i += NT) {
+          const bool grp = i < n1;
+          const u32 *f = grp ? gflag + i : aflag + first + (i - n1);
+          const T *vp = grp ? gagg + i : agg + first + (i - n1);
+          while (ld_acquire_u32(f) != epoch) __nanosleep(20);
+          acc = acc + ld_cg_t(vp);
+        }
+        carry = scan_block_sum<T, NW>(acc, s_red);
       }
-      carry = scan_block_sum<T, NW>(acc, s_red);
     }
     // ---- finish: carry + chunk prefix + warp prefix + lane prefix + local scan, one vector store ----
     T cpre = carry;
@@ -2505,10 +2505,11 @@ __device__ __forceinline__ void scan_inner_body_impl(const RedParams &p) {
     carry = (!tiles_mode && nb == cb) ? cpre : scan_zero<T>();
     cb = nb;
     ct = nt;
+    gid += gridDim.x;
     orow = orow_next;
 #pragma unroll
     for (int u = 0; u < U; ++u) full[u] = full_next[u];
-    __syncthreads();   // (C) s_warp / s_chunk / s_next are reused by the next trip
+    __syncthreads();   // (C) s_warp / s_chunk are reused by the next trip
   }
 }
 
