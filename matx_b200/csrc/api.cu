@@ -1683,14 +1683,18 @@ int mxb_cumsum(mxb_handle_t h, const mxb_expr_t *expr_in, const mxb_out_t *out) 
       if (h->scan_ws) MXB_CUDA(cudaFreeAsync(h->scan_ws, h->stream));
       h->scan_cap_tiles = std::max<size_t>(std::max(need_t, h->scan_cap_tiles), 4096);
       h->scan_cap_groups = std::max<size_t>(std::max(need_g, h->scan_cap_groups), 1024);
-      const size_t nb = h->scan_cap_tiles * 12 + h->scan_cap_groups * 16 + 1024;
+      const size_t nb = h->scan_cap_tiles * 20 + h->scan_cap_groups * 20 + 1024;
       MXB_CUDA(cudaMallocAsync(&h->scan_ws, nb, h->stream));
       MXB_CUDA(cudaMemsetAsync(h->scan_ws, 0, nb, h->stream));   // flags 0 = no epoch
       h->scan_ws_bytes = nb;
       h->scan_epoch = 0;
     }
-    const size_t o_agg = 0, o_gagg = o_agg + h->scan_cap_tiles * 8, o_af = o_gagg + h->scan_cap_groups * 8,
-                 o_gf = o_af + h->scan_cap_tiles * 4;
+    // 4-byte totals travel packed with their epoch in 8-byte slots; 8-byte totals have their own slots plus flag words.
+    // The two never share memory, so a stale 8-byte total cannot pose as a packed {epoch, value} word.
+    const bool wide = dtype_bytes(vt) >= 8;
+    const size_t o_agg4 = 0, o_gagg4 = o_agg4 + h->scan_cap_tiles * 8, o_agg8 = o_gagg4 + h->scan_cap_groups * 8,
+                 o_gagg8 = o_agg8 + h->scan_cap_tiles * 8, o_af = o_gagg8 + h->scan_cap_groups * 8, o_gf = o_af + h->scan_cap_tiles * 4;
+    const size_t o_agg = wide ? o_agg8 : o_agg4, o_gagg = wide ? o_gagg8 : o_gagg4;
     // flags are epoch-coded: nothing to clear between launches
     if (++h->scan_epoch == 0) {   // 2^32 launches later: start over
       MXB_CUDA(cudaMemsetAsync(h->scan_ws, 0, h->scan_ws_bytes, h->stream));
@@ -1706,6 +1710,8 @@ int mxb_cumsum(mxb_handle_t h, const mxb_expr_t *expr_in, const mxb_out_t *out) 
     // the kernels are built with __launch_bounds__(256, 3), which guarantees 3 CTAs per SM
     const int per_sm = env_int("MXB_SCAN_GRID_PER_SM", 0) > 0 ? std::min(env_int("MXB_SCAN_GRID_PER_SM", 0), 3) : 3;
     grid = (unsigned)std::min<int64_t>(B * tpr, (int64_t)sm * per_sm);
+    // MXB_SCAN_ONE_TILE_PER_CTA=1: a CTA per tile, relying on CTAs being dispatched in blockIdx order (CUB's assumption)
+    if (env_int("MXB_SCAN_ONE_TILE_PER_CTA", 0)) grid = (unsigned)(B * tpr);
     p.scan_flags = (unsigned)env_int("MXB_SCAN_FLAGS", 0);
   } else {
     const int tune_cps = env_int("MXB_TUNE_CTAS_PER_SM", 0);

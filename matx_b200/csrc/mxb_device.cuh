@@ -2173,6 +2173,39 @@ __device__ __forceinline__ u32 ld_acquire_u32(const u32 *p) {
 __device__ __forceinline__ void st_release_u32(u32 *p, u32 v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+// A published total.  4-byte values travel WITH their flag in one 8-byte word (epoch in the high half): one relaxed
+// load both tests and fetches, no acquire / release and no second round trip (what CUB's tile status words do).
+// 8-byte values use the separate epoch flag with release / acquire.
+template <class T> struct ScanSlot {
+  static __device__ __forceinline__ void publish(T *val, u32 *flag, i64 i, T v, u32 epoch) {
+    if (sizeof(T) == 4) {
+      union { T t; u32 w; } u;
+      u.t = v;
+      const unsigned long long word = ((unsigned long long)epoch << 32) | u.w;
+      asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"((unsigned long long *)val + i), "l"(word) : "memory");
+    } else {
+      st_cg_t(val + i, v);
+      st_release_u32(flag + i, epoch);
+    }
+  }
+  static __device__ __forceinline__ T wait(const T *val, const u32 *flag, i64 i, u32 epoch) {
+    if (sizeof(T) == 4) {
+      unsigned long long word;
+      while (true) {
+        asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(word) : "l"((const unsigned long long *)val + i) : "memory");
+        if ((u32)(word >> 32) == epoch) break;
+        __nanosleep(20);
+      }
+      union { T t; u32 w; } u;
+      u.w = (u32)word;
+      return u.t;
+    } else {
+      while (ld_acquire_u32(flag + i) != epoch) __nanosleep(20);
+      return ld_cg_t(val + i);
+    }
+  }
+};
+
 template <class T> __device__ __forceinline__ T shfl_up_t(T v, int d) {
   enum { W = sizeof(T) / 4 };
   union { T t; u32 w[W]; } a, b;
@@ -2447,41 +2480,28 @@ __device__ __forceinline__ void scan_inner_body_impl(const RedParams &p) {
       for (int u = 1; u < U; ++u) total = total + ctot[u];
       const i64 g = ct / SCAN_GROUP, first = g * SCAN_GROUP;
       const i64 gcount = (tpr - first) < SCAN_GROUP ? (tpr - first) : SCAN_GROUP;
-      T *agg = (T *)p.scan_agg + cb * tpr;
-      T *gagg = (T *)p.scan_gagg + cb * gpr;
+      // (4-byte values live in 8-byte slots, see ScanSlot)
+      T *agg = (T *)((char *)p.scan_agg + (size_t)(cb * tpr) * 8);
+      T *gagg = (T *)((char *)p.scan_gagg + (size_t)(cb * gpr) * 8);
       u32 *aflag = p.scan_agg_flag + cb * tpr, *gflag = p.scan_gagg_flag + cb * gpr;
-      if (tid == 0) {
-        st_cg_t(agg + ct, total);
-        st_release_u32(aflag + ct, epoch);
-      }
+      if (tid == 0) ScanSlot<T>::publish(agg, aflag, ct, total, epoch);
       if (!early) prefetch();
       const i64 n1 = g, n2 = ct - first;
       if (ct == first + gcount - 1) {
         // last tile of its group: the group's total goes out first (it needs the group's own tiles only), then the
         // totals of the earlier groups are gathered for this tile's carry
         T a = scan_zero<T>();
-        for (i64 i = tid; i < n2; i += NT) {
-          while (ld_acquire_u32(aflag + first + i) != epoch) __nanosleep(20);
-          a = a + ld_cg_t(agg + first + i);
-        }
+        for (i64 i = tid; i < n2; i += NT) a = a + ScanSlot<T>::wait(agg, aflag, first + i, epoch);
         const T stiles = scan_block_sum<T, NW>(a, s_red);
-        if (tid == 0) { st_cg_t(gagg + g, stiles + total); st_release_u32(gflag + g, epoch); }
+        if (tid == 0) ScanSlot<T>::publish(gagg, gflag, g, stiles + total, epoch);
         a = scan_zero<T>();
-        for (i64 i = tid; i < n1; i += NT) {
-          while (ld_acquire_u32(gflag + i) != epoch) __nanosleep(20);
-          a = a + ld_cg_t(gagg + i);
-        }
+        for (i64 i = tid; i < n1; i += NT) a = a + ScanSlot<T>::wait(gagg, gflag, i, epoch);
         carry = scan_block_sum<T, NW>(a, s_red) + stiles;
       } else {
         // carry = (totals of the groups before this one) + (totals of the tiles before this one in its group)
         T acc = scan_zero<T>();
-        for (i64 i = tid; i < n1 + n2; i += NT) {
-          const bool grp = i < n1;
-          const u32 *f = grp ? gflag + i : aflag + first + (i - n1);
-          const T *vp = grp ? gagg + i : agg + first + (i - n1);
-          while (ld_acquire_u32(f) != epoch) __nanosleep(20);
-          acc = acc + ld_cg_t(vp);
-        }
+        for (i64 i = tid; i < n1 + n2; i += NT)
+          acc = acc + (i < n1 ? ScanSlot<T>::wait(gagg, gflag, i, epoch) : ScanSlot<T>::wait(agg, aflag, first + (i - n1), epoch));
         carry = scan_block_sum<T, NW>(acc, s_red);
       }
     }
