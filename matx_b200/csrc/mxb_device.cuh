@@ -118,7 +118,7 @@ struct RedParams {
   void *scan_agg, *scan_gagg;
   u32 *scan_agg_flag, *scan_gagg_flag;
   u32 scan_epoch;
-  u32 scan_flags;   // bit 0: TILES mode issues the next tile's loads before publishing (experiment knob)
+  u32 scan_flags;   // TILES mode: bit 0 / bit 1 force the next tile's loads before / after the publish (sweep knob)
 };
 
 // elementwise: up to KMAXD collapsed dims, innermost last
@@ -2458,9 +2458,10 @@ __device__ __forceinline__ void scan_inner_body_impl(const RedParams &p) {
         }
       }
     };
-    // ROWS: right away.  TILES: only after this tile's total is published — a release store waits for the thread's
-    // earlier loads, and every other tile's carry waits for that store
-    const bool early = !tiles_mode || (p.scan_flags & 1);
+    // ROWS, and TILES with packed 4-byte totals (published by a relaxed store): right away.  TILES with 8-byte totals:
+    // only after this tile's total is published — a release store waits for the thread's earlier loads, and every
+    // other tile's carry waits for that store.  (scan_flags bit 0 / bit 1 force early / late: sweep knob)
+    const bool early = (p.scan_flags & 2) ? false : (!tiles_mode || sizeof(T) == 4 || (p.scan_flags & 1));
     if (early) prefetch();
     // ---- CTA stage: thread u turns chunk u's warp totals into exclusive prefixes and the chunk total ----
     if (tid < U) {

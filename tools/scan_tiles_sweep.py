@@ -15,7 +15,7 @@ x = (torch.rand(n, device="cuda") * 2 - 1).round() * 3
 y = torch.empty_like(x)
 tx, ty = mx.make_tensor(x), mx.make_tensor(y)
 want_last = float(x.double().sum())
-for env in [{}, {"MXB_SCAN_ONE_TILE_PER_CTA": 1}, {"MXB_SCAN_ONE_TILE_PER_CTA": 1, "MXB_TUNE_U": 8}, {"MXB_SCAN_ONE_TILE_PER_CTA": 1, "MXB_TUNE_U": 2}, {"MXB_TUNE_U": 8}]:
+for env in [{}, {"MXB_SCAN_FLAGS": 2}, {"MXB_SCAN_GRID_PER_SM": 2}, {"MXB_SCAN_ONE_TILE_PER_CTA": 1}, {"MXB_TUNE_U": 8}, {"MXB_TUNE_U": 2}]:
     for k, v in env.items():
         os.environ[k] = str(v)
     try:
