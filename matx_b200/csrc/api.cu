@@ -1673,6 +1673,17 @@ int mxb_cumsum(mxb_handle_t h, const mxb_expr_t *expr_in, const mxb_out_t *out) 
   p.out.ptr = out->data;
   fill_consts(e, p.c);
 
+  int64_t rows_per_warp = 1;
+  if (warp_team && spec.U == 1) {
+    // short rows share a warp: G lanes per row, G = smallest power of two that covers the row's vectors
+    const int64_t nv = (L + V - 1) / V;
+    if (nv <= 32 && env_int("MXB_SCAN_NO_GROUP", 0) == 0) {
+      int G = 1;
+      while (G < nv) G <<= 1;
+      p.scan_group = G;
+      rows_per_warp = 32 / G;
+    }
+  }
   unsigned grid;
   if (tiles_mode) {
     const int64_t gpr = (tpr + 127) / 128;   // SCAN_GROUP
@@ -1715,7 +1726,7 @@ int mxb_cumsum(mxb_handle_t h, const mxb_expr_t *expr_in, const mxb_out_t *out) 
     p.scan_flags = (unsigned)env_int("MXB_SCAN_FLAGS", 0);
   } else {
     const int tune_cps = env_int("MXB_TUNE_CTAS_PER_SM", 0);
-    const int64_t rows_per_cta = warp_team ? 8 : 1;
+    const int64_t rows_per_cta = warp_team ? 8 * rows_per_warp : 1;
     grid = (unsigned)std::min<int64_t>((B + rows_per_cta - 1) / rows_per_cta, (int64_t)sm * (tune_cps > 0 ? tune_cps : 8));
   }
   Kernel k;

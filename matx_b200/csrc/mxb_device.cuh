@@ -118,7 +118,8 @@ struct RedParams {
   void *scan_agg, *scan_gagg;
   u32 *scan_agg_flag, *scan_gagg_flag;
   u32 scan_epoch;
-  u32 scan_flags;   // TILES mode: bit 0 / bit 1 force the next tile's loads before / after the publish (sweep knob)
+  int scan_group;   // warp team, rows of <= 32 vectors: lanes per row (power of two), 0 = a whole warp per row
+  u32 scan_flags;   // TILES mode: bit 0 issues the next tile's loads before the publish instead of after (sweep knob)
 };
 
 // elementwise: up to KMAXD collapsed dims, innermost last
@@ -2251,6 +2252,73 @@ __device__ __forceinline__ void scan_warp_body_impl(const RedParams &p) {
   const i64 STEP = (i64)32 * V * U;
   const i64 w0 = (i64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), wstep = (i64)gridDim.x * (blockDim.x >> 5);
   const i64 oinner = p.out_rs[0];
+  if (U == 1 && p.scan_group > 0) {
+    // rows of at most G vectors (G = p.scan_group, a power of two <= 32): G lanes per row, 32 / G rows per warp, one
+    // segmented shuffle scan, no loop — a 64-element fp32 row would otherwise leave half of a warp idle and an
+    // 8-element one 30 lanes of 32
+    const int G = p.scan_group, lr = lane & (G - 1);
+    const i64 rpw = 32 / G;
+    for (i64 b0 = w0 * rpw; b0 < p.B; b0 += wstep * rpw) {   // warp-uniform trip count: the shuffles stay full-mask
+      const i64 b = b0 + lane / G;
+      const bool live = b < p.B;
+      const char *base[E::NL];
+      i64 inner[E::NL];
+      i64 oo = 0;
+      {
+        i64 bidx[KMAXD];
+        decomp(live ? b : 0, p.nb, p.bsz, bidx);
+#pragma unroll
+        for (int k = 0; k < E::NL; ++k) {
+          i64 off = 0;
+#pragma unroll
+          for (int d = 0; d < KMAXD; ++d) if (d < p.nb) off += bidx[d] * p.leaf[k].bs[d];
+          base[k] = (const char *)p.leaf[k].ptr + off * E::leaf_bytes(k);
+          inner[k] = p.leaf[k].rs[0];
+        }
+#pragma unroll
+        for (int d = 0; d < KMAXD; ++d) if (d < p.nb) oo += bidx[d] * p.out.bs[d];
+      }
+      OutT *orow = (OutT *)p.out.ptr + oo;
+      const i64 j = (i64)lr * V;
+      T x[V];
+      const bool full = V == 1 ? (j < L) : (j + V <= L);
+      if (live && full) {
+        typename E::template Regs<V> r;
+        E::template loadv<V, UNIT>(r, base, inner, j);
+#pragma unroll
+        for (int v = 0; v < V; ++v) x[v] = E::template eval<V>(r, v, p.c);
+      } else {
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          x[v] = scan_zero<T>();
+          if (live && V > 1 && j + v < L) {
+            typename E::template Regs<1> r1;
+            E::template loadv<1, false>(r1, base, inner, j + v);
+            x[v] = E::template eval<1>(r1, 0, p.c);
+          }
+        }
+      }
+#pragma unroll
+      for (int v = 1; v < V; ++v) x[v] = x[v - 1] + x[v];
+      T incl = x[V - 1];
+      for (int d = 1; d < G; d <<= 1) {
+        const T o = shfl_up_t(incl, d);
+        if (lr >= d) incl = o + incl;
+      }
+      const T ex = shfl_up_t(incl, 1);
+      if (live) {
+        Vec<OutT, V> o;
+#pragma unroll
+        for (int v = 0; v < V; ++v) o.v[v] = cvt<OutT>(lr == 0 ? x[v] : ex + x[v]);
+        if (V > 1 && j + V <= L && oinner == 1 && p.tx) StBytes<(int)sizeof(OutT) * V>::st(orow + j, &o);
+        else {
+#pragma unroll
+          for (int v = 0; v < V; ++v) if (j + v < L) orow[(j + v) * oinner] = o.v[v];
+        }
+      }
+    }
+    return;
+  }
   for (i64 b = w0; b < p.B; b += wstep) {
     const char *base[E::NL];
     i64 inner[E::NL];
@@ -2458,10 +2526,10 @@ __device__ __forceinline__ void scan_inner_body_impl(const RedParams &p) {
         }
       }
     };
-    // ROWS, and TILES with packed 4-byte totals (published by a relaxed store): right away.  TILES with 8-byte totals:
-    // only after this tile's total is published — a release store waits for the thread's earlier loads, and every
-    // other tile's carry waits for that store.  (scan_flags bit 0 / bit 1 force early / late: sweep knob)
-    const bool early = (p.scan_flags & 2) ? false : (!tiles_mode || sizeof(T) == 4 || (p.scan_flags & 1));
+    // ROWS: right away.  TILES: only after this tile's total is published — every other tile's carry waits for that
+    // store, and anything queued in front of it delays them all (measured on 2^28 fp32: 0.62 ms late, 0.69 ms early;
+    // with release stores, which also wait for the thread's earlier loads, 1.28 vs 1.53).  scan_flags bit 0 forces early.
+    const bool early = !tiles_mode || (p.scan_flags & 1);
     if (early) prefetch();
     // ---- CTA stage: thread u turns chunk u's warp totals into exclusive prefixes and the chunk total ----
     if (tid < U) {

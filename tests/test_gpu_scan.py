@@ -53,7 +53,8 @@ def test_reference_known_answers(oracle):
 
 
 @pytest.mark.parametrize("shape", [(1,), (7,), (1023,), (1024,), (1025,), (4096,), (4097,), (20000,), (3, 5000), (300, 257), (2000, 64),
-                                   (5, 3, 1000), (1, 1 << 20), (2, 300001), (5000, 100), (1000, 2048), (70000, 7), (600, 513)])
+                                   (5, 3, 1000), (1, 1 << 20), (2, 300001), (5000, 100), (1000, 2048), (70000, 7), (600, 513),
+                                   (100000, 8), (50000, 16), (3000, 33), (40000, 4), (9999, 1), (7777, 128), (1201, 124)])
 def test_int32_exact_all_shapes(oracle, shape):
     """Integer sums do not care about the order of additions: every tiling / carry path must be bit-exact."""
     rng = np.random.default_rng(sum(shape))
