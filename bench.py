@@ -374,13 +374,7 @@ def run_ours(args) -> None:
         except Exception as exc:  # the checker is optional for the GPU number; say why it is absent
             cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference", "sample": "unavailable: %s" % exc}
 
-    others = None
-    if rank == 0 and world == 1 and args.all_configs:
-        del x, tx
-        torch.cuda.empty_cache()
-        from matx_b200 import bench_configs
-        others = bench_configs.run_all(ex, peak)
-
+    line = None
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
@@ -395,9 +389,66 @@ def run_ours(args) -> None:
                        "parallelism": "slab%d" % world},
             "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu,
         }
-        if others is not None:
-            line["other_configs"] = others
-        os.write(json_fd, (json.dumps(line) + "\n").encode())
+
+    def emit():
+        if rank == 0:
+            os.write(json_fd, (json.dumps(line) + "\n").encode())
+
+    # ---- batched reductions / elementwise, sharded by the outermost batch dim with NO communication (configs 1, 3, 4, 5):
+    # every rank times its own block on the device, the job's time is the max over ranks (north star:
+    # ">= 7x at 8 GPUs for batched reductions").  Total work is fixed as N grows (strong scaling), like the headline.
+    # The headline line is complete at this point: if this extra section wedges (a rank lost, a refused capture), a
+    # watchdog prints the line as it stands and ends the process instead of losing the run.
+    if not args.no_batched:
+        from matx_b200 import bench_configs
+
+        def bail():
+            if rank == 0:
+                line["batched_sharded"] = {"error": "timed out after 240 s"}
+            emit()
+            os._exit(0)
+
+        guard = threading.Timer(240.0, bail)
+        guard.daemon = True
+        guard.start()
+        batched = None
+        try:
+            torch.cuda.empty_cache()
+            local, berr = None, None
+            try:
+                local = bench_configs.run_batched_shard(ex, rank, world, use_graph=world > 1)
+            except Exception as exc:  # noqa: BLE001 - reported in the line; the collective below still runs on every rank
+                berr = repr(exc)
+            names = bench_configs.BATCHED
+            tms_b = torch.tensor([local[n]["ms"] if local else 0.0 for n in names] + [1.0 if local else 0.0], device=dev, dtype=torch.float64)
+            ok_b = tms_b[-1:].clone()
+            if world > 1:
+                dist.all_reduce(tms_b, op=dist.ReduceOp.MAX)
+                dist.all_reduce(ok_b, op=dist.ReduceOp.MIN)
+            if ok_b.item() == 1.0:
+                batched = {"scaling": "strong", "sharding": "outermost batch dim in %d contiguous blocks, no collective" % world,
+                           "timing": "device time per launch, max over ranks" + (", 10 launches per CUDA-graph replay" if world > 1 else "")}
+                for i, n in enumerate(names):
+                    ms_b = tms_b[i].item()
+                    gbps = local[n]["bytes_total"] / (ms_b * 1e-3) / 1e9
+                    batched[n] = {"ms": ms_b, "GBps": gbps, "frac_of_measured_peak_per_gpu": gbps / world / peak,
+                                  "Gelem_per_s": local[n]["elems_total"] / (ms_b * 1e-3) / 1e9, "kernel": local[n]["kernel"],
+                                  "cuda_graph": local[n]["graph"]}
+            else:
+                batched = {"error": berr or "failed on another rank"}
+        except Exception as exc:  # noqa: BLE001
+            batched = {"error": repr(exc)}
+        guard.cancel()
+        if rank == 0:
+            line["batched_sharded"] = batched
+
+    if rank == 0 and world == 1 and args.all_configs:
+        del x, tx
+        torch.cuda.empty_cache()
+        from matx_b200 import bench_configs
+        line["other_configs"] = bench_configs.run_all(ex, peak)
+
+    emit()
     if world > 1:
         # a captured graph holds NCCL work: drop it before tearing the communicator down, and never let teardown hang the job
         graph = None
@@ -428,6 +479,7 @@ def main() -> None:
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="N > 1: how the 32-byte partial records travel")
     ap.add_argument("--no-graph", action="store_true", help="N > 1: launch the step kernel by kernel instead of replaying a CUDA graph")
+    ap.add_argument("--no-batched", action="store_true", help="skip the batch-sharded timing of configs 1, 3, 4, 5 (batched_sharded)")
     ap.add_argument("--all-configs", action="store_true", help="also time configs 1, 3, 4, 5 (reported under other_configs)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -152,6 +152,105 @@ def run_next(ex, peak):
     return res
 
 
+BATCHED = ("C1 sum(a*b+c,{1}) fp32 16384x4096", "C3 mean(x,{1}) c64 65536x8192", "C3 var(x,{1},1) c64 65536x8192",
+           "C3 argmax(abs2(x),{1}) c64 65536x8192", "C4 black_scholes fp32 2^28", "C5 sum(permute(t,{2,0,1}),{2}) bf16 1024^3")
+
+
+def _time_burst(fn, use_graph, launches=10, reps=3):
+    """Average device time of one launch: `launches` back-to-back calls captured into ONE CUDA graph (so the host-side
+    lowering cannot starve an ~80 us kernel at 8 GPUs) and replayed `reps` times between two events on the current
+    stream; falls back to plain back-to-back launches if the capture is refused."""
+    import torch
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    graph = None
+    try:
+        if not use_graph:   # the legacy default stream cannot be captured (N = 1: kernels of 0.1-1 ms need no graph)
+            raise RuntimeError("no capture")
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=torch.cuda.current_stream()):
+            for _ in range(launches):
+                fn()
+        graph = g
+        graph.replay()
+    except Exception:  # noqa: BLE001 - measured either way
+        graph = None
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        if graph is not None:
+            graph.replay()
+        else:
+            for _ in range(launches):
+                fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / (reps * launches), graph is not None
+
+
+def run_batched_shard(ex, rank, world, use_graph=False):
+    """Configs 1, 3, 4, 5 sharded by their outermost batch dim over `world` ranks with NO communication:
+    this rank times its own block.  Returns {name: {"ms", "bytes_total", "elems_total", "kernel", "graph"}} where the
+    totals are those of the WHOLE job (all ranks), so total / max-over-ranks(ms) is the job's throughput."""
+    import torch
+    from .dist import shard_rows
+    res = {}
+
+    def _tb(fn):
+        return _time_burst(fn, use_graph)
+
+    def put(name, ms_graph, nbytes, nelem):
+        res[name] = {"ms": ms_graph[0], "graph": ms_graph[1], "bytes_total": nbytes, "elems_total": nelem, "kernel": ex.last_kernel()}
+
+    # C1
+    rows, cols = 16384, 4096
+    _, r = shard_rows(rows, rank, world)
+    a, b = torch.rand(r, cols, device="cuda"), torch.rand(r, cols, device="cuda")
+    c = torch.rand(r, cols, device="cuda") - 0.5
+    out = torch.empty(r, device="cuda")
+    ta, tb, tc, to = (mx.make_tensor(t) for t in (a, b, c, out))
+    put(BATCHED[0], _tb(lambda: to.set(mx.sum(ta * tb + tc, [1])).run(ex)), 3 * rows * cols * 4 + rows * 4, rows * cols)
+    del a, b, c, out
+    # C3
+    rows, cols = 65536, 8192
+    _, r = shard_rows(rows, rank, world)
+    x = torch.view_as_complex(torch.randn(r, cols, 2, device="cuda"))
+    tx = mx.make_tensor(x)
+    n = rows * cols
+    om = torch.empty(r, dtype=torch.complex64, device="cuda")
+    put(BATCHED[1], _tb(lambda: mx.make_tensor(om).set(mx.mean(tx, [1])).run(ex)), n * 8 + rows * 8, n)
+    ov = torch.empty(r, device="cuda")
+    put(BATCHED[2], _tb(lambda: mx.make_tensor(ov).set(mx.var(tx, [1], 1)).run(ex)), n * 8 + rows * 4, n)
+    oa, oi = torch.empty(r, device="cuda"), torch.empty(r, dtype=torch.int64, device="cuda")
+    put(BATCHED[3], _tb(lambda: mx.mtie(mx.make_tensor(oa), mx.make_tensor(oi)).set(mx.argmax(mx.abs2(tx), [1])).run(ex)),
+        n * 8 + rows * 12, n)
+    del x, tx, om, ov, oa, oi
+    torch.cuda.empty_cache()
+    # C4
+    n = 1 << 28
+    _, m = shard_rows(n, rank, world)
+    S, K = torch.rand(m, device="cuda") * 90 + 10, torch.rand(m, device="cuda") * 90 + 10
+    V, rr, T = torch.rand(m, device="cuda") * 0.45 + 0.05, torch.rand(m, device="cuda") * 0.09 + 0.01, torch.rand(m, device="cuda") * 1.9 + 0.1
+    o4 = torch.empty(m, device="cuda")
+    tK, tS, tV, tr, tT, to4 = (mx.make_tensor(t) for t in (K, S, V, rr, T, o4))
+    expr = black_scholes_expr(tK, tS, tV, tr, tT)
+    put(BATCHED[4], _tb(lambda: to4.set(expr).run(ex)), 6 * n * 4, n)
+    del S, K, V, rr, T, o4
+    torch.cuda.empty_cache()
+    # C5: this rank owns whole 2 MiB slabs t[j] of the outermost dim and its columns out[:, j]
+    d = 1024
+    _, dj = shard_rows(d, rank, world)
+    t = (torch.rand(dj, d, d, device="cuda") * 0.25).to(torch.bfloat16)
+    o5 = torch.empty(d, dj, dtype=torch.bfloat16, device="cuda")
+    tt, to5 = mx.make_tensor(t), mx.make_tensor(o5)
+    put(BATCHED[5], _tb(lambda: to5.set(mx.sum(mx.permute(tt, [2, 0, 1]), [2])).run(ex)), d * d * d * 2 + d * d * 2, d * d * d)
+    del t, o5
+    torch.cuda.empty_cache()
+    return res
+
+
 def run_all(ex, peak):
     import torch
     out = {}

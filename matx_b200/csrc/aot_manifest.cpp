@@ -179,7 +179,7 @@ void aot_manifest(std::vector<ManifestItem> *items) {
       it.spec.op = op;
       it.spec.out_dtype = out_dtype;
       it.spec.V = pass == 0 ? policy_vmax(info) : 1;
-      if (family == FAM_EW_TR) it.spec.V = 16 / info.max_leaf_bytes;  // one 16-byte chunk
+      if (family == FAM_EW_TR || family == FAM_RED_OUTER_TMA) it.spec.V = 16 / info.max_leaf_bytes;  // one 16-byte chunk
       it.spec.U = policy_unroll(info, it.spec.V, family);
       it.spec.team = team;
       items->push_back(it);
@@ -194,6 +194,8 @@ void aot_manifest(std::vector<ManifestItem> *items) {
       if (d != MXB_F32 && op == MXB_RED_PROD) continue;
       for (int team : {0, 1}) add(e, FAM_RED_INNER, op, d, team, d == MXB_F32);
       if (d == MXB_F32 || d == MXB_BF16) add(e, FAM_RED_OUTER, op, d, 0, d == MXB_F32);
+      // TMA-staged tiles for a strided / permuted reduce dim (config 5 and column reductions of plain tensors)
+      if ((d == MXB_F32 || d == MXB_BF16) && op != MXB_RED_PROD) add(e, FAM_RED_OUTER_TMA, op, d, 0, false);
     }
   }
   for (int d : {MXB_F32, MXB_C64}) add(prog_identity(d), FAM_VAR_SMEM, MXB_RED_VAR, MXB_F32, 0, false);

@@ -406,6 +406,57 @@ int reduce_launch(mxb_context *h, int kop, const mxb_expr_t &e, const ExprInfo &
     spec.family = FAM_RED_INNER;  // V == 1 walks any strides
     spec.V = 1;
   }
+  // ---- strided / permuted reduce dim of a plain tensor: TMA-staged tiles instead of the LDG column walker ----
+  // (one collapsed reduce dim, 16-byte granularity everywhere, enough strips to fill the machine without splitting R)
+  int ot_tx = 0, ot_rt = 0, ot_stages = 0, ot_block = 256, ot_ctas = 2;
+  if (spec.family == FAM_RED_OUTER && spec.V > 1 && e.n_nodes == 1 && nl == 1 && gr.n == 1 && kop != KOP_LSE && env_int("MXB_OUTER_TMA", 1)) {
+    const int64_t esz = dtype_bytes(e.leaves[0].dtype);
+    const int64_t C = gb.size[rot];
+    const int64_t cv = C * esz / 16;                      // 16-byte chunks per row of the vector dim
+    bool ok = gb.ls[0][rot] == 1 && (C * esz) % 16 == 0 && aligned_to(e.leaves[0].data, 16) && gr.ls[0][0] > 0 &&
+              (gr.ls[0][0] * esz) % 16 == 0 && R >= env_int("MXB_OUTER_TMA_MIN_R", 64) && esz <= 16;
+    for (int d = 0; ok && d < gb.n; ++d) if (d != rot) ok = (gb.ls[0][d] * esz) % 16 == 0;
+    if (ok) {
+      ot_block = env_int("MXB_TUNE_BLOCK", 0) > 0 ? env_int("MXB_TUNE_BLOCK", 0) : 256;
+      ot_ctas = env_int("MXB_TUNE_OT_CTAS", 2);
+      const int64_t grid_max = (int64_t)h->sm_count * ot_ctas;
+      // strip width: the widest of 128 / 64 / 32 chunks whose item count spreads evenly over the persistent grid
+      // (the ring makes every item cost the same, so the last wave's fill is the whole imbalance)
+      double best = -1.0;
+      for (int tx = 128; tx >= 32; tx >>= 1) {
+        if (tx > ot_block) continue;
+        int t = tx;
+        while (t > 1 && t / 2 >= cv) t >>= 1;             // never wider than the row itself
+        if (t < 32) break;
+        const int64_t items = (B / C) * ((cv + t - 1) / t);
+        if (items < (int64_t)h->sm_count) continue;
+        const int64_t waves = (items + grid_max - 1) / grid_max;
+        // ragged last strip of a row (cv % t) wastes its threads, not bandwidth: only the wave fill is scored
+        const double fill = (double)items / (double)(waves * std::min<int64_t>(items, grid_max));
+        if (fill > best + 0.04) { best = fill; ot_tx = t; }
+        if (t != tx) break;
+      }
+      if (env_int("MXB_TUNE_TX", 0) >= 32 && env_int("MXB_TUNE_TX", 0) <= 128) ot_tx = env_int("MXB_TUNE_TX", 0);
+    }
+    if (ot_tx > 0) {
+      const int ty = ot_block / ot_tx;
+      const int64_t strip = (int64_t)ot_tx * 16;
+      const int64_t spart = (int64_t)(ty - 1) * ot_tx * spec.V * acc_bytes(kop, info.value_dtype);
+      const int64_t budget = std::min<int64_t>((int64_t)228 * 1024 / ot_ctas - 1024, (int64_t)h->max_smem_optin) - 1024 - 128 - spart;
+      int64_t stage = (int64_t)env_int("MXB_TUNE_OT_STAGE_KB", 32) * 1024;
+      int64_t want = env_int("MXB_TUNE_STAGES", 0) > 0 ? env_int("MXB_TUNE_STAGES", 0) : 3;
+      while (stage > strip * ty && stage * want > budget) stage >>= 1;
+      int64_t rt = std::max<int64_t>(ty, stage / strip / ty * ty);
+      if (rt > ((R + ty - 1) / ty) * ty) rt = ((R + ty - 1) / ty) * ty;
+      int64_t st = std::min<int64_t>(budget / (rt * strip), env_int("MXB_TUNE_STAGES", 0) > 0 ? env_int("MXB_TUNE_STAGES", 0) : 4);
+      if (st >= 2) {
+        spec.family = FAM_RED_OUTER_TMA;
+        spec.V = (int)(16 / esz);
+        ot_rt = (int)rt;
+        ot_stages = (int)st;
+      }
+    }
+  }
   spec.U = policy_unroll(info, spec.V, spec.family);
   if (spec.family == FAM_VAR_REG || spec.family == FAM_VAR_GROUP) spec.team = var_ipt;
   // development knobs (tools/sweep.py): override the unroll / launch shape; any combination is JIT-compiled on demand
@@ -550,6 +601,17 @@ int reduce_launch(mxb_context *h, int kop, const mxb_expr_t &e, const ExprInfo &
       const int64_t rows_per_cta = (int64_t)(block / 32) * (32 / G);
       grid = (unsigned)std::min<int64_t>((B + rows_per_cta - 1) / rows_per_cta, (int64_t)sm * (tune_cps > 0 ? tune_cps : 8));
     }
+  } else if (spec.family == FAM_RED_OUTER_TMA) {
+    const int64_t C = p.bsz[p.nb - 1];
+    const int64_t tile = (int64_t)ot_tx * spec.V;
+    const int64_t items = (B / C) * ((C + tile - 1) / tile);
+    const int ty = ot_block / ot_tx;
+    p.tx = ot_tx;
+    p.tma_rt = ot_rt;
+    p.splits = ot_stages;
+    block = (unsigned)ot_block;
+    smem = (unsigned)(128 + (int64_t)ot_stages * ot_rt * ot_tx * 16 + (int64_t)(ty - 1) * ot_tx * spec.V * acc_bytes(kop, info.value_dtype));
+    grid = (unsigned)std::min<int64_t>(items, (int64_t)sm * (tune_cps > 0 ? tune_cps : ot_ctas));
   } else {  // FAM_RED_OUTER
     const int64_t C = p.bsz[p.nb - 1];
     const int64_t cv = (C + spec.V - 1) / spec.V;

@@ -427,6 +427,7 @@ int policy_vmax(const ExprInfo &info) {
 int policy_unroll(const ExprInfo &info, int V, int family) {
   const int bytes = V * info.max_leaf_bytes;  // widest load of one step
   if (family == FAM_RED_OUTER) return 4;
+  if (family == FAM_RED_OUTER_TMA) return 1;
   if (family == FAM_VAR_REG || family == FAM_VAR_TMA || family == FAM_VAR_GROUP || family == FAM_SM_GROUP || family == FAM_SM_REG) return 1;
   if (family == FAM_EW_TR) return 1;
   if (family == FAM_VAR_SMEM) return bytes >= 32 ? 4 : 8;
@@ -436,7 +437,7 @@ int policy_unroll(const ExprInfo &info, int V, int family) {
 
 std::string kernel_key(const ExprInfo &info, const KernelSpec &s) {
   std::ostringstream k;
-  static const char *fam[] = {"red_inner", "red_outer", "var_smem", "ew", "var_reg", "var_tma", "var_group", "softmax_group", "softmax_reg", "ew_tr", "scan"};
+  static const char *fam[] = {"red_inner", "red_outer", "var_smem", "ew", "var_reg", "var_tma", "var_group", "softmax_group", "softmax_reg", "ew_tr", "scan", "red_outer_tma"};
   k << fam[s.family] << "|" << info.name << "|" << (s.op >= 0 ? reduce_op_name(s.op) : "-") << "|" << dtype_name(s.out_dtype)
     << "|V" << s.V << "|U" << s.U << "|T" << s.team;
   return k.str();
@@ -454,7 +455,7 @@ int kernel_wrapper_src(const ExprInfo &info, const KernelSpec &s, const std::str
   const bool cplx = info.value_dtype == MXB_C64;
   std::ostringstream k;
   std::string op;
-  if (s.family == FAM_RED_INNER || s.family == FAM_RED_OUTER) {
+  if (s.family == FAM_RED_INNER || s.family == FAM_RED_OUTER || s.family == FAM_RED_OUTER_TMA) {
     switch (s.op) {
       case MXB_RED_SUM: op = "mxb::OpSum<" + T + ">"; break;
       case MXB_RED_PROD: op = "mxb::OpProd<" + T + ">"; break;
@@ -485,6 +486,12 @@ int kernel_wrapper_src(const ExprInfo &info, const KernelSpec &s, const std::str
       // 24 % warps active, 0.435 ms on config 5; 76 registers, 34 %, 0.350 ms before the split-R code joined this body)
       k << "extern \"C\" __global__ void __launch_bounds__(256, 3) " << symbol
         << "(const __grid_constant__ mxb::RedParams p) { mxb::reduce_outer_body<" << E << ", " << op << ", " << O << ", " << VU << ">(p); }\n";
+      break;
+    case FAM_RED_OUTER_TMA:
+      if (info.nleaf != 1) return fail("red_outer_tma serves plain tensors only");
+      // 2 CTAs of up to 512 threads per SM (<= 64 registers): the ring, not the register file, holds the bytes in flight
+      k << "extern \"C\" __global__ void __launch_bounds__(512, 2) " << symbol
+        << "(const __grid_constant__ mxb::RedParams p) { mxb::reduce_outer_tma_body<" << dtype_ctype(info.leaf_dtype[0]) << ", " << op << ", " << O << ">(p); }\n";
       break;
     case FAM_VAR_SMEM:
       if (!(info.value_dtype == MXB_F32 || info.value_dtype == MXB_F64 || cplx)) return fail("var of a non-floating expression");

@@ -120,6 +120,7 @@ struct RedParams {
   u32 scan_epoch;
   int scan_group;   // warp team, rows of <= 32 vectors: lanes per row (power of two), 0 = a whole warp per row
   u32 scan_flags;   // TILES mode: bit 0 issues the next tile's loads before the publish instead of after (sweep knob)
+  int tma_rt;       // reduce_outer_tma: reduce rows per ring stage (splits = ring depth, tx = 16-byte chunks per strip)
 };
 
 // elementwise: up to KMAXD collapsed dims, innermost last
@@ -1807,6 +1808,154 @@ __device__ __forceinline__ void var_inner_tma_body(const RedParams &p) {
 #pragma unroll
       for (int d = 0; d < KMAXD; ++d) if (d < p.nb) oo += bidx[d] * p.out.bs[d];
       ((OutT *)p.out.ptr)[oo] = cvt<OutT>(res);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2t: reduce_outer_tma — reduce_outer (strided / permuted reduce dim, a batch dim is the unit-stride vector dim) for
+// a plain tensor with ONE collapsed reduce dim, tiles staged in shared memory by the TMA engine.  A CTA owns a strip
+// of TX 16-byte chunks of the vector dim (an "item" = one strip of one outer batch index) and walks the reduce index
+// in chunks of RT rows: one stage of the ring = RT rows x strip bytes, filled by `cp.async.bulk` (one copy when the
+// strip covers whole contiguous rows, else one copy per row issued by the lanes of warp 0) on an mbarrier; all
+// threads wait for the stage, fold their rows out of shared memory (one LDS.128 per row: a warp reads consecutive
+// chunks, conflict free), one barrier, and warp 0 re-arms the stage with the chunk `stages` ahead.  The ring runs
+// ACROSS the items of a CTA, so the copy engine keeps (stages - 1) x RT rows in flight per CTA through the item
+// epilogues — 3-4x the bytes the LDG walker can hold in registers, which is what bounds that one (48 KB per SM).
+// ------------------------------------------------------------------------------------------------
+template <class Tin, class Op, class OutT>
+__device__ __forceinline__ void reduce_outer_tma_body(const RedParams &p) {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  typedef typename Widen<Tin>::type T;
+  typedef typename Op::acc_t acc_t;
+  enum { V = 16 / (int)sizeof(Tin) };
+  extern __shared__ __align__(128) unsigned char s_dyn[];
+  u64 *full = (u64 *)s_dyn;                  // one mbarrier per stage (first 128 bytes)
+  const int stages = p.splits;               // ring depth
+  const int RT = p.tma_rt;                   // rows per stage
+  const int TX = p.tx, TY = (int)blockDim.x / TX;
+  const u32 stage_bytes = (u32)RT * (u32)TX * 16u;
+  unsigned char *ring = s_dyn + 128;
+  acc_t *s_part = (acc_t *)(ring + (size_t)stages * stage_bytes);   // [TY - 1][TX * V]
+  const int tid = threadIdx.x, tx = tid % TX, ty = tid / TX;
+  const int nb = p.nb;
+  const i64 C = p.bsz[nb - 1];
+  const i64 tile = (i64)TX * V;
+  const i64 ctiles = (C + tile - 1) / tile;
+  const i64 items = (p.B / C) * ctiles;
+  const i64 R = p.R;
+  const i64 nch = (R + RT - 1) / RT;
+  const i64 pitch = p.leaf[0].rs[0] * (i64)sizeof(Tin);   // bytes between consecutive reduce rows
+  const i64 n_items = items > (i64)blockIdx.x ? (items - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const i64 total = n_items * nch;           // chunks this CTA consumes
+
+  // warp 0: arm stage (q % stages) with chunk q of this CTA's chunk sequence
+  auto issue = [&](i64 q, int s) {
+    const int lane = tid & 31;
+    const i64 n = q / nch, ch = q - n * nch;
+    const i64 w = (i64)blockIdx.x + n * gridDim.x;
+    const i64 bo = w / ctiles, ct = w - bo * ctiles;
+    i64 bidx[KMAXD];
+    decomp(bo, nb - 1, p.bsz, bidx);
+    i64 off = ct * tile;
+#pragma unroll
+    for (int d = 0; d < KMAXD - 1; ++d) if (d < nb - 1) off += bidx[d] * p.leaf[0].bs[d];
+    const i64 cols = (C - ct * tile) < tile ? (C - ct * tile) : tile;
+    const u32 wb = (u32)(cols * (i64)sizeof(Tin));
+    const i64 r0 = ch * RT;
+    const int rows = (int)((R - r0) < RT ? (R - r0) : RT);
+    const char *src = (const char *)p.leaf[0].ptr + off * (i64)sizeof(Tin) + r0 * pitch;
+    unsigned char *dst = ring + (size_t)s * stage_bytes;
+    if (lane == 0) mbar_expect_tx(&full[s], (u32)rows * wb);
+    __syncwarp();
+    if (pitch == (i64)wb) {
+      if (lane == 0) bulk_g2s(dst, src, (u32)rows * wb, &full[s]);
+    } else {
+      for (int r = lane; r < rows; r += 32) bulk_g2s(dst + (size_t)r * wb, src + (i64)r * pitch, wb, &full[s]);
+    }
+  };
+
+  if (tid == 0) {
+    for (int s = 0; s < stages; ++s) mbar_init(&full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid < 32) {
+    for (int s = 0; s < stages; ++s) if ((i64)s < total) issue(s, s);
+  }
+
+  i64 q = 0;
+  int s = 0;
+  u32 phase = 0;
+  for (i64 n = 0; n < n_items; ++n) {
+    const i64 w = (i64)blockIdx.x + n * gridDim.x;
+    const i64 bo = w / ctiles, ct = w - bo * ctiles;
+    const i64 c0 = ct * tile + (i64)tx * V;      // first column of this thread (C is a multiple of V: host rule)
+    const bool active = c0 < C && ty < TY;
+    const i64 cols = (C - ct * tile) < tile ? (C - ct * tile) : tile;
+    const u32 wb = (u32)(cols * (i64)sizeof(Tin));
+    acc_t acc[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) acc[v] = Op::init();
+    // flat index of (batch row, reduce r) = (sum_d bidx[d]*bflat[d]) * R + r; column c adds c*bflat[nb-1]*R
+    i64 rowflat = p.idx_base + c0 * p.bflat[nb - 1] * R;
+    if (Op::HAS_INDEX) {
+      i64 bidx[KMAXD];
+      decomp(bo, nb - 1, p.bsz, bidx);
+#pragma unroll
+      for (int d = 0; d < KMAXD - 1; ++d) if (d < nb - 1) rowflat += bidx[d] * p.bflat[d] * R;
+    }
+    const i64 colflat = p.bflat[nb - 1] * R;
+    for (i64 ch = 0; ch < nch; ++ch, ++q) {
+      mbar_wait(&full[s], phase);
+      const i64 r0 = ch * RT;
+      const int rows = (int)((R - r0) < RT ? (R - r0) : RT);
+      if (active) {
+        const unsigned char *sbase = ring + (size_t)s * stage_bytes + (size_t)tx * 16;
+        int r = ty;
+        // four rows per trip: the LDS.128s go out together (a warp reads consecutive chunks of one row)
+        for (; r + 3 * TY < rows; r += 4 * TY) {
+          union { uint4 q; Vec<Tin, V> x; } u[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) u[i].q = *(const uint4 *)(sbase + (size_t)(r + i * TY) * wb);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+#pragma unroll
+            for (int v = 0; v < V; ++v) Op::step(acc[v], cvt<T>(u[i].x.v[v]), rowflat + (i64)v * colflat + r0 + r + i * TY);
+          }
+        }
+        for (; r < rows; r += TY) {
+          union { uint4 q; Vec<Tin, V> x; } u;
+          u.q = *(const uint4 *)(sbase + (size_t)r * wb);
+#pragma unroll
+          for (int v = 0; v < V; ++v) Op::step(acc[v], cvt<T>(u.x.v[v]), rowflat + (i64)v * colflat + r0 + r);
+        }
+      }
+      __syncthreads();   // every thread is done with stage s
+      if (tid < 32 && q + stages < total) issue(q + stages, s);
+      if (++s == stages) { s = 0; phase ^= 1u; }
+    }
+    if (n + 1 == n_items) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    // TY partials per column meet in shared memory (fixed order: ty = 0, 1, ...)
+    if (TY > 1) {
+      if (active && ty > 0) {
+#pragma unroll
+        for (int v = 0; v < V; ++v) s_part[((size_t)(ty - 1) * TX + tx) * V + v] = acc[v];
+      }
+      __syncthreads();
+      if (active && ty == 0) {
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          acc_t a = acc[v];
+          for (int y = 1; y < TY; ++y) Op::merge(a, s_part[((size_t)(y - 1) * TX + tx) * V + v]);
+          acc[v] = a;
+        }
+      }
+      // the next write to s_part comes after the next item's chunk barriers (nch >= 1), so no barrier is needed here
+    }
+    if (active && ty == 0) {
+#pragma unroll
+      for (int v = 0; v < V; ++v) store_result<Op, OutT>(p, bo * C + c0 + v, acc[v]);
     }
   }
 }

@@ -120,6 +120,18 @@ def test_generated_kernels_compile_for_sm100a(family, op, team):
     assert st == A.OK, (A.lib.mxb_last_error(), log.value.decode()[:2000])
 
 
+@pytest.mark.parametrize("npdt,dt,op", [(np.int32, A.I32, A.RED_SUM), (np.int32, A.I32, A.RED_ARGMIN), (np.float64, A.F64, A.RED_MAX),
+                                        (np.complex64, A.C64, A.RED_SUM), (np.float32, A.F32, A.RED_ALL)])
+def test_outer_tma_kernel_compiles_for_sm100a(npdt, dt, op):
+    """Family 11 (red_outer_tma: TMA-staged tiles for a strided reduce dim) serves plain tensors; the dtypes without an
+    ahead-of-time instance are built by NVRTC on first use — prove here that they compile (V = one 16-byte chunk)."""
+    x = np_tensor(np.zeros((8, 16), npdt))
+    e = mx.lower_reduce(mx.ReduceExpr(op, x, [0]))
+    log = C.create_string_buffer(1 << 16)
+    st = A.lib.mxb_debug_compile(C.byref(e), 11, op, dt, 16 // np.dtype(npdt).itemsize, 0, log, len(log))
+    assert st == A.OK, (A.lib.mxb_last_error(), log.value.decode()[:2000])
+
+
 def test_paired_fp32_body_compiles_for_sm100a():
     """Pure-fp32 programs get a second body on the packed fp32 instructions (FFMA2 / FMUL2 / FADD2): NVRTC must know
     the sm_100 intrinsics and the packed log / normcdf."""
