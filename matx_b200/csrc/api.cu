@@ -10,6 +10,7 @@
 // Differences by design: one launch per statement (no size-query call, no cudaMallocAsync per call, no
 // second "single tile" launch, no separate scale kernel for mean), int64 sizes, deterministic results.
 #include <cuda_runtime.h>
+#include <cuda.h>  // CUtensorMap types only; the encoder's entry point is queried at run time
 
 #include <algorithm>
 #include <cstdio>
@@ -155,6 +156,24 @@ void fill_peer_push(mxb::PeerPush &pp, const mxb_peers_t &peers, int item) {
   pp.world = peers.world;
   pp.rank = peers.rank;
   pp.item = item;
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver-entry-point query (no link against libcuda; the library still
+// loads on a CPU-only box).  nullptr when the driver does not have it.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn tensor_map_encoder() {
+  static EncodeTiledFn fn = [] {
+    void *f = nullptr;
+    cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+      cudaGetLastError();
+      return (EncodeTiledFn) nullptr;
+    }
+    return (EncodeTiledFn)f;
+  }();
+  return fn;
 }
 
 bool aligned_to(const void *p, int64_t bytes) { return ((uintptr_t)p % (uintptr_t)bytes) == 0; }
@@ -407,15 +426,23 @@ int reduce_launch(mxb_context *h, int kop, const mxb_expr_t &e, const ExprInfo &
     spec.V = 1;
   }
   // ---- strided / permuted reduce dim of a plain tensor: TMA-staged tiles instead of the LDG column walker ----
-  // (one collapsed reduce dim, 16-byte granularity everywhere, enough strips to fill the machine without splitting R)
-  int ot_tx = 0, ot_rt = 0, ot_stages = 0, ot_block = 256, ot_ctas = 2;
-  if (spec.family == FAM_RED_OUTER && spec.V > 1 && e.n_nodes == 1 && nl == 1 && gr.n == 1 && kop != KOP_LSE && env_int("MXB_OUTER_TMA", 1)) {
+  // (one collapsed reduce dim, at most one other batch dim, 16-byte granularity everywhere, enough strips to fill
+  // the machine without splitting R).  Tile copies go through a tensor map (any pitch); without one, plain bulk
+  // copies serve the case where a strip is whole contiguous rows (per-row bulk copies of 0.5-1 KB measured slower
+  // than the LDG walker: profiles/r1_outer_tma_sweep.jsonl).
+  int ot_tx = 0, ot_rt = 0, ot_stages = 0, ot_block = 256, ot_ctas = 2, ot_mode = 0;
+  CUtensorMap ot_map;
+  if (spec.family == FAM_RED_OUTER && spec.V > 1 && e.n_nodes == 1 && nl == 1 && gr.n == 1 && gb.n <= 2 && kop != KOP_LSE &&
+      env_int("MXB_OUTER_TMA", 1)) {
     const int64_t esz = dtype_bytes(e.leaves[0].dtype);
     const int64_t C = gb.size[rot];
     const int64_t cv = C * esz / 16;                      // 16-byte chunks per row of the vector dim
+    const int other = gb.n == 2 ? 1 - rot : -1;           // the other batch dim, if any
+    const int64_t pitch = gr.ls[0][0] * esz;
     bool ok = gb.ls[0][rot] == 1 && (C * esz) % 16 == 0 && aligned_to(e.leaves[0].data, 16) && gr.ls[0][0] > 0 &&
-              (gr.ls[0][0] * esz) % 16 == 0 && R >= env_int("MXB_OUTER_TMA_MIN_R", 64) && esz <= 16;
-    for (int d = 0; ok && d < gb.n; ++d) if (d != rot) ok = (gb.ls[0][d] * esz) % 16 == 0;
+              pitch % 16 == 0 && R >= env_int("MXB_OUTER_TMA_MIN_R", 64) && esz <= 16;
+    if (ok && other >= 0) ok = gb.ls[0][other] > 0 && (gb.ls[0][other] * esz) % 16 == 0;
+    const int want_mode = env_int("MXB_OUTER_TMA_MODE", -1);   // -1 auto, 0 bulk copies, 1 tensor map
     if (ok) {
       ot_block = env_int("MXB_TUNE_BLOCK", 0) > 0 ? env_int("MXB_TUNE_BLOCK", 0) : 256;
       ot_ctas = env_int("MXB_TUNE_OT_CTAS", 2);
@@ -433,7 +460,7 @@ int reduce_launch(mxb_context *h, int kop, const mxb_expr_t &e, const ExprInfo &
         const int64_t waves = (items + grid_max - 1) / grid_max;
         // ragged last strip of a row (cv % t) wastes its threads, not bandwidth: only the wave fill is scored
         const double fill = (double)items / (double)(waves * std::min<int64_t>(items, grid_max));
-        if (fill > best + 0.04) { best = fill; ot_tx = t; }
+        if (fill > best + env_int("MXB_TUNE_OT_FILL_PCT", 4) * 0.01) { best = fill; ot_tx = t; }
         if (t != tx) break;
       }
       if (env_int("MXB_TUNE_TX", 0) >= 32 && env_int("MXB_TUNE_TX", 0) <= 128) ot_tx = env_int("MXB_TUNE_TX", 0);
@@ -448,12 +475,32 @@ int reduce_launch(mxb_context *h, int kop, const mxb_expr_t &e, const ExprInfo &
       while (stage > strip * ty && stage * want > budget) stage >>= 1;
       int64_t rt = std::max<int64_t>(ty, stage / strip / ty * ty);
       if (rt > ((R + ty - 1) / ty) * ty) rt = ((R + ty - 1) / ty) * ty;
+      if (rt > 256) rt = 256 / ty * ty;                   // box dims of a tensor map are at most 256
       int64_t st = std::min<int64_t>(budget / (rt * strip), env_int("MXB_TUNE_STAGES", 0) > 0 ? env_int("MXB_TUNE_STAGES", 0) : 4);
-      if (st >= 2) {
+      if (st > 8) st = 8;
+      // tile copies: tensor map over {vector dim in 8-byte elements, reduce rows, other batch dim}
+      bool have_map = false;
+      EncodeTiledFn enc = want_mode == 0 ? nullptr : tensor_map_encoder();
+      if (enc && st >= 2) {
+        const int64_t Bo = other >= 0 ? gb.size[other] : 1;
+        const cuuint64_t gdim[3] = {(cuuint64_t)(C * esz / 8), (cuuint64_t)R, (cuuint64_t)Bo};
+        const cuuint64_t gstr[2] = {(cuuint64_t)pitch, (cuuint64_t)(other >= 0 ? gb.ls[0][other] * esz : pitch * R)};
+        const cuuint32_t box[3] = {(cuuint32_t)(ot_tx * 2), (cuuint32_t)rt, 1u};
+        const cuuint32_t estr[3] = {1u, 1u, 1u};
+        const int l2p = env_int("MXB_TUNE_OT_L2PROMO", 2);
+        const bool fits = gdim[0] < (1ull << 31) && gdim[1] < (1ull << 31) && gdim[2] < (1ull << 31) && gstr[0] < (1ull << 40) && gstr[1] < (1ull << 40);
+        if (fits && enc(&ot_map, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, const_cast<void *>(e.leaves[0].data), gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, (CUtensorMapL2promotion)l2p,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
+          have_map = true;
+      }
+      const bool contiguous_strips = pitch == C * esz && cv <= ot_tx;   // one bulk copy per stage
+      if (st >= 2 && (have_map ? want_mode != 0 : (contiguous_strips || want_mode == 0))) {
         spec.family = FAM_RED_OUTER_TMA;
         spec.V = (int)(16 / esz);
         ot_rt = (int)rt;
         ot_stages = (int)st;
+        ot_mode = have_map ? 1 : 0;
       }
     }
   }
@@ -609,7 +656,9 @@ int reduce_launch(mxb_context *h, int kop, const mxb_expr_t &e, const ExprInfo &
     p.tx = ot_tx;
     p.tma_rt = ot_rt;
     p.splits = ot_stages;
-    block = (unsigned)ot_block;
+    p.tma_mode = ot_mode;
+    if (ot_mode == 1) memcpy(p.tmap, &ot_map, sizeof ot_map);
+    block = (unsigned)ot_block + 32u;   // consumers + the producer warp
     smem = (unsigned)(128 + (int64_t)ot_stages * ot_rt * ot_tx * 16 + (int64_t)(ty - 1) * ot_tx * spec.V * acc_bytes(kop, info.value_dtype));
     grid = (unsigned)std::min<int64_t>(items, (int64_t)sm * (tune_cps > 0 ? tune_cps : ot_ctas));
   } else {  // FAM_RED_OUTER

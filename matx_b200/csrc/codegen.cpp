@@ -489,8 +489,8 @@ int kernel_wrapper_src(const ExprInfo &info, const KernelSpec &s, const std::str
       break;
     case FAM_RED_OUTER_TMA:
       if (info.nleaf != 1) return fail("red_outer_tma serves plain tensors only");
-      // 2 CTAs of up to 512 threads per SM (<= 64 registers): the ring, not the register file, holds the bytes in flight
-      k << "extern \"C\" __global__ void __launch_bounds__(512, 2) " << symbol
+      // up to 512 consumer threads + the producer warp; the ring, not the register file, holds the bytes in flight
+      k << "extern \"C\" __global__ void __launch_bounds__(544) " << symbol
         << "(const __grid_constant__ mxb::RedParams p) { mxb::reduce_outer_tma_body<" << dtype_ctype(info.leaf_dtype[0]) << ", " << op << ", " << O << ">(p); }\n";
       break;
     case FAM_VAR_SMEM:

@@ -121,6 +121,10 @@ struct RedParams {
   int scan_group;   // warp team, rows of <= 32 vectors: lanes per row (power of two), 0 = a whole warp per row
   u32 scan_flags;   // TILES mode: bit 0 issues the next tile's loads before the publish instead of after (sweep knob)
   int tma_rt;       // reduce_outer_tma: reduce rows per ring stage (splits = ring depth, tx = 16-byte chunks per strip)
+  int tma_mode;     // reduce_outer_tma: 1 = tile copies through `tmap`, 0 = cp.async.bulk copies (whole stage or per row)
+  // CUtensorMap over the leaf as {vector dim in 8-byte elements, reduce dim, outer batch dim} (opaque 128 bytes, must
+  // stay in the kernel's parameter space: the copy instruction takes its address)
+  __align__(64) unsigned long long tmap[16];
 };
 
 // elementwise: up to KMAXD collapsed dims, innermost last
@@ -1816,13 +1820,27 @@ __device__ __forceinline__ void var_inner_tma_body(const RedParams &p) {
 // K2t: reduce_outer_tma — reduce_outer (strided / permuted reduce dim, a batch dim is the unit-stride vector dim) for
 // a plain tensor with ONE collapsed reduce dim, tiles staged in shared memory by the TMA engine.  A CTA owns a strip
 // of TX 16-byte chunks of the vector dim (an "item" = one strip of one outer batch index) and walks the reduce index
-// in chunks of RT rows: one stage of the ring = RT rows x strip bytes, filled by `cp.async.bulk` (one copy when the
-// strip covers whole contiguous rows, else one copy per row issued by the lanes of warp 0) on an mbarrier; all
-// threads wait for the stage, fold their rows out of shared memory (one LDS.128 per row: a warp reads consecutive
-// chunks, conflict free), one barrier, and warp 0 re-arms the stage with the chunk `stages` ahead.  The ring runs
-// ACROSS the items of a CTA, so the copy engine keeps (stages - 1) x RT rows in flight per CTA through the item
-// epilogues — 3-4x the bytes the LDG walker can hold in registers, which is what bounds that one (48 KB per SM).
+// in chunks of RT rows: one stage of the ring = RT rows x TX chunks.  Warp-specialised: the LAST warp of the CTA is
+// the producer — it waits for a stage's `empty` mbarrier, arms its `full` mbarrier with the byte count and issues the
+// copy: ONE `cp.async.bulk.tensor.3d` (tile mode, tensor map over {vector dim, reduce dim, outer batch dim}: any
+// pitch, out-of-range rows / columns zero-filled and never read), or, without a tensor map, `cp.async.bulk` copies
+// (one when the strip covers whole contiguous rows, else one per row).  The other warps are consumers: wait on
+// `full`, fold their rows out of shared memory (one LDS.128 per row: a warp reads consecutive chunks, conflict
+// free), and one lane per warp arrives on `empty`.  No CTA-wide barrier in the loop (the first version, with a
+// __syncthreads per stage and warp 0 issuing, stalled 65 % of its issue slots on that barrier).  The ring runs ACROSS
+// the items of a CTA, so the copy engine keeps `stages` x RT rows in flight per CTA through the item epilogues —
+// 3-4x the bytes the LDG walker can hold in registers, which is what bounds that one (48 KB per SM).
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_arrive(u64 *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tensor_g2s_3d(void *dst_smem, const void *tmap, int c0, int c1, int c2, u64 *bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+               : "memory");
+}
+
 template <class Tin, class Op, class OutT>
 __device__ __forceinline__ void reduce_outer_tma_body(const RedParams &p) {
   asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -1830,14 +1848,17 @@ __device__ __forceinline__ void reduce_outer_tma_body(const RedParams &p) {
   typedef typename Op::acc_t acc_t;
   enum { V = 16 / (int)sizeof(Tin) };
   extern __shared__ __align__(128) unsigned char s_dyn[];
-  u64 *full = (u64 *)s_dyn;                  // one mbarrier per stage (first 128 bytes)
-  const int stages = p.splits;               // ring depth
+  u64 *full = (u64 *)s_dyn;                  // first 128 bytes: full[0..7], empty[0..7]
+  u64 *empty = full + 8;
+  const int stages = p.splits;               // ring depth (<= 8)
   const int RT = p.tma_rt;                   // rows per stage
-  const int TX = p.tx, TY = (int)blockDim.x / TX;
-  const u32 stage_bytes = (u32)RT * (u32)TX * 16u;
+  const int NC = (int)blockDim.x - 32;       // consumer threads; the last warp is the producer
+  const int TX = p.tx, TY = NC / TX;
+  const u32 rowb = (u32)TX * 16u;            // bytes of one full strip row
+  const u32 stage_bytes = (u32)RT * rowb;
   unsigned char *ring = s_dyn + 128;
   acc_t *s_part = (acc_t *)(ring + (size_t)stages * stage_bytes);   // [TY - 1][TX * V]
-  const int tid = threadIdx.x, tx = tid % TX, ty = tid / TX;
+  const int tid = threadIdx.x, lane = tid & 31;
   const int nb = p.nb;
   const i64 C = p.bsz[nb - 1];
   const i64 tile = (i64)TX * V;
@@ -1845,46 +1866,67 @@ __device__ __forceinline__ void reduce_outer_tma_body(const RedParams &p) {
   const i64 items = (p.B / C) * ctiles;
   const i64 R = p.R;
   const i64 nch = (R + RT - 1) / RT;
-  const i64 pitch = p.leaf[0].rs[0] * (i64)sizeof(Tin);   // bytes between consecutive reduce rows
   const i64 n_items = items > (i64)blockIdx.x ? (items - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-  const i64 total = n_items * nch;           // chunks this CTA consumes
-
-  // warp 0: arm stage (q % stages) with chunk q of this CTA's chunk sequence
-  auto issue = [&](i64 q, int s) {
-    const int lane = tid & 31;
-    const i64 n = q / nch, ch = q - n * nch;
-    const i64 w = (i64)blockIdx.x + n * gridDim.x;
-    const i64 bo = w / ctiles, ct = w - bo * ctiles;
-    i64 bidx[KMAXD];
-    decomp(bo, nb - 1, p.bsz, bidx);
-    i64 off = ct * tile;
-#pragma unroll
-    for (int d = 0; d < KMAXD - 1; ++d) if (d < nb - 1) off += bidx[d] * p.leaf[0].bs[d];
-    const i64 cols = (C - ct * tile) < tile ? (C - ct * tile) : tile;
-    const u32 wb = (u32)(cols * (i64)sizeof(Tin));
-    const i64 r0 = ch * RT;
-    const int rows = (int)((R - r0) < RT ? (R - r0) : RT);
-    const char *src = (const char *)p.leaf[0].ptr + off * (i64)sizeof(Tin) + r0 * pitch;
-    unsigned char *dst = ring + (size_t)s * stage_bytes;
-    if (lane == 0) mbar_expect_tx(&full[s], (u32)rows * wb);
-    __syncwarp();
-    if (pitch == (i64)wb) {
-      if (lane == 0) bulk_g2s(dst, src, (u32)rows * wb, &full[s]);
-    } else {
-      for (int r = lane; r < rows; r += 32) bulk_g2s(dst + (size_t)r * wb, src + (i64)r * pitch, wb, &full[s]);
-    }
-  };
+  const bool tensor = p.tma_mode == 1;
+  // row pitch inside a stage: the tensor copy always lands a full TX-chunk box, the bulk copies pack the strip's own width
 
   if (tid == 0) {
-    for (int s = 0; s < stages; ++s) mbar_init(&full[s], 1);
+    for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], (u32)(NC / 32)); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  if (tid < 32) {
-    for (int s = 0; s < stages; ++s) if ((i64)s < total) issue(s, s);
+
+  if (tid >= NC) {
+    // ---------------- producer warp ----------------
+    const i64 pitch = p.leaf[0].rs[0] * (i64)sizeof(Tin);   // bytes between consecutive reduce rows
+    int s = 0;
+    u32 round = 0;
+    for (i64 n = 0; n < n_items; ++n) {
+      const i64 w = (i64)blockIdx.x + n * gridDim.x;
+      const i64 bo = w / ctiles, ct = w - bo * ctiles;
+      const i64 cols = (C - ct * tile) < tile ? (C - ct * tile) : tile;
+      const u32 wb = (u32)(cols * (i64)sizeof(Tin));
+      const char *src = nullptr;
+      if (!tensor) {
+        i64 bidx[KMAXD];
+        decomp(bo, nb - 1, p.bsz, bidx);
+        i64 off = ct * tile;
+#pragma unroll
+        for (int d = 0; d < KMAXD - 1; ++d) if (d < nb - 1) off += bidx[d] * p.leaf[0].bs[d];
+        src = (const char *)p.leaf[0].ptr + off * (i64)sizeof(Tin);
+      }
+      for (i64 ch = 0; ch < nch; ++ch) {
+        if (round > 0) {
+          if (lane == 0) mbar_wait(&empty[s], (round - 1u) & 1u);
+          __syncwarp();
+        }
+        unsigned char *dst = ring + (size_t)s * stage_bytes;
+        const i64 r0 = ch * RT;
+        if (tensor) {
+          if (lane == 0) {
+            mbar_expect_tx(&full[s], stage_bytes);
+            // coordinates in 8-byte elements along the vector dim, rows, outer batch index
+            tensor_g2s_3d(dst, p.tmap, (int)(ct * TX * 2), (int)r0, (int)bo, &full[s]);
+          }
+        } else {
+          const int rows = (int)((R - r0) < RT ? (R - r0) : RT);
+          if (lane == 0) mbar_expect_tx(&full[s], (u32)rows * wb);
+          __syncwarp();
+          const char *sp = src + r0 * pitch;
+          if (pitch == (i64)wb) {
+            if (lane == 0) bulk_g2s(dst, sp, (u32)rows * wb, &full[s]);
+          } else {
+            for (int r = lane; r < rows; r += 32) bulk_g2s(dst + (size_t)r * wb, sp + (i64)r * pitch, wb, &full[s]);
+          }
+        }
+        if (++s == stages) { s = 0; ++round; }
+      }
+    }
+    return;
   }
 
-  i64 q = 0;
+  // ---------------- consumer warps ----------------
+  const int tx = tid % TX, ty = tid / TX;
   int s = 0;
   u32 phase = 0;
   for (i64 n = 0; n < n_items; ++n) {
@@ -1893,7 +1935,7 @@ __device__ __forceinline__ void reduce_outer_tma_body(const RedParams &p) {
     const i64 c0 = ct * tile + (i64)tx * V;      // first column of this thread (C is a multiple of V: host rule)
     const bool active = c0 < C && ty < TY;
     const i64 cols = (C - ct * tile) < tile ? (C - ct * tile) : tile;
-    const u32 wb = (u32)(cols * (i64)sizeof(Tin));
+    const u32 spitch = tensor ? rowb : (u32)(cols * (i64)sizeof(Tin));
     acc_t acc[V];
 #pragma unroll
     for (int v = 0; v < V; ++v) acc[v] = Op::init();
@@ -1906,7 +1948,7 @@ __device__ __forceinline__ void reduce_outer_tma_body(const RedParams &p) {
       for (int d = 0; d < KMAXD - 1; ++d) if (d < nb - 1) rowflat += bidx[d] * p.bflat[d] * R;
     }
     const i64 colflat = p.bflat[nb - 1] * R;
-    for (i64 ch = 0; ch < nch; ++ch, ++q) {
+    for (i64 ch = 0; ch < nch; ++ch) {
       mbar_wait(&full[s], phase);
       const i64 r0 = ch * RT;
       const int rows = (int)((R - r0) < RT ? (R - r0) : RT);
@@ -1917,7 +1959,7 @@ __device__ __forceinline__ void reduce_outer_tma_body(const RedParams &p) {
         for (; r + 3 * TY < rows; r += 4 * TY) {
           union { uint4 q; Vec<Tin, V> x; } u[4];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) u[i].q = *(const uint4 *)(sbase + (size_t)(r + i * TY) * wb);
+          for (int i = 0; i < 4; ++i) u[i].q = *(const uint4 *)(sbase + (size_t)(r + i * TY) * spitch);
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
 #pragma unroll
@@ -1926,23 +1968,24 @@ __device__ __forceinline__ void reduce_outer_tma_body(const RedParams &p) {
         }
         for (; r < rows; r += TY) {
           union { uint4 q; Vec<Tin, V> x; } u;
-          u.q = *(const uint4 *)(sbase + (size_t)r * wb);
+          u.q = *(const uint4 *)(sbase + (size_t)r * spitch);
 #pragma unroll
           for (int v = 0; v < V; ++v) Op::step(acc[v], cvt<T>(u.x.v[v]), rowflat + (i64)v * colflat + r0 + r);
         }
       }
-      __syncthreads();   // every thread is done with stage s
-      if (tid < 32 && q + stages < total) issue(q + stages, s);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[s]);   // this warp is done with stage s
       if (++s == stages) { s = 0; phase ^= 1u; }
     }
     if (n + 1 == n_items) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    // TY partials per column meet in shared memory (fixed order: ty = 0, 1, ...)
+    // TY partials per column meet in shared memory (fixed order: ty = 0, 1, ...); consumer-only named barrier
     if (TY > 1) {
+      asm volatile("bar.sync 1, %0;" ::"r"(NC) : "memory");   // the previous item's readers of s_part are done
       if (active && ty > 0) {
 #pragma unroll
         for (int v = 0; v < V; ++v) s_part[((size_t)(ty - 1) * TX + tx) * V + v] = acc[v];
       }
-      __syncthreads();
+      asm volatile("bar.sync 1, %0;" ::"r"(NC) : "memory");
       if (active && ty == 0) {
 #pragma unroll
         for (int v = 0; v < V; ++v) {
@@ -1951,7 +1994,6 @@ __device__ __forceinline__ void reduce_outer_tma_body(const RedParams &p) {
           acc[v] = a;
         }
       }
-      // the next write to s_part comes after the next item's chunk barriers (nch >= 1), so no barrier is needed here
     }
     if (active && ty == 0) {
 #pragma unroll

@@ -73,7 +73,26 @@ def test_sliced_view_and_int32(oracle):
     assert k.startswith("red_outer_tma"), k
     xi = data(rng, (100, 19200), A.I32)
     for op in ["sum", "max", "argmin"]:
-        k = check(oracle, op, lambda t, op=op: getattr(mx, op)(t, [0]), [xi], A.I32)
+        k = check(oracle, op, lambda t, op=op: getattr(mx, op)(t, [0]), [xi], A.I32, tol=1e-30)   # integer sums are exact
+    assert k.startswith("red_outer_tma"), k
+
+
+@pytest.mark.parametrize("mode", ["0", "1"])
+def test_both_copy_modes(oracle, monkeypatch, mode):
+    """MXB_OUTER_TMA_MODE=1: one tensor-map tile copy per stage (UTMALDG); =0: cp.async.bulk copies, one per stage when
+    the strip is whole contiguous rows, else one per row.  Ragged strips and ragged last chunks in both."""
+    monkeypatch.setenv("MXB_OUTER_TMA_MODE", mode)
+    rng = np.random.default_rng(60)
+    x = data(rng, (151, 75, 1056), A.F32, ties=True)          # 264 chunks per row: strips of 32, the last one 8 wide
+    for op in ["argmax", "min", "all"]:
+        k = check(oracle, op, lambda t, op=op: getattr(mx, op)(mx.permute(t, [2, 0, 1]), [2]), [x], A.F32)
+        assert k.startswith("red_outer_tma"), k
+    y = data(rng, (200, 67, 512), A.F32, ties=True)           # whole 2 KB rows per strip: contiguous
+    for op in ["argmin", "max"]:
+        k = check(oracle, op, lambda t, op=op: getattr(mx, op)(mx.permute(t, [2, 0, 1]), [2]), [y], A.F32)
+        assert k.startswith("red_outer_tma"), k
+    z = data(rng, (130, 20000), A.F32, ties=True)             # no other batch dim: column reductions
+    k = check(oracle, "argmax", lambda t: mx.argmax(t, [0]), [z], A.F32)
     assert k.startswith("red_outer_tma"), k
 
 

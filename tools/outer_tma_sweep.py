@@ -29,13 +29,17 @@ def sweep(name, build, nbytes, check, envs):
 
 
 ENVS = [{"MXB_OUTER_TMA": 0}, {}]
-for tx in (32, 64, 128):
-    for kb in (16, 32, 48):
-        ENVS.append({"MXB_TUNE_TX": tx, "MXB_TUNE_OT_STAGE_KB": kb})
-ENVS += [{"MXB_TUNE_OT_CTAS": 1, "MXB_TUNE_STAGES": 6}, {"MXB_TUNE_OT_CTAS": 1, "MXB_TUNE_STAGES": 6, "MXB_TUNE_BLOCK": 512},
-         {"MXB_TUNE_OT_CTAS": 1, "MXB_TUNE_STAGES": 4, "MXB_TUNE_OT_STAGE_KB": 48, "MXB_TUNE_BLOCK": 512},
-         {"MXB_TUNE_OT_CTAS": 3, "MXB_TUNE_OT_STAGE_KB": 16}, {"MXB_TUNE_OT_CTAS": 4, "MXB_TUNE_OT_STAGE_KB": 16, "MXB_TUNE_STAGES": 3},
-         {"MXB_TUNE_BLOCK": 512}, {"MXB_TUNE_STAGES": 2}, {"MXB_TUNE_OT_STAGE_KB": 24, "MXB_TUNE_STAGES": 4}]
+for mode in (1, 0):
+    for tx in (32, 64, 128):
+        for kb in (16, 32):
+            ENVS.append({"MXB_OUTER_TMA_MODE": mode, "MXB_TUNE_TX": tx, "MXB_TUNE_OT_STAGE_KB": kb})
+for tx in (64, 128):
+    ENVS += [{"MXB_TUNE_TX": tx, "MXB_TUNE_OT_CTAS": 1, "MXB_TUNE_STAGES": 6}, {"MXB_TUNE_TX": tx, "MXB_TUNE_OT_CTAS": 1, "MXB_TUNE_STAGES": 6, "MXB_TUNE_BLOCK": 512},
+             {"MXB_TUNE_TX": tx, "MXB_TUNE_OT_CTAS": 1, "MXB_TUNE_STAGES": 4, "MXB_TUNE_OT_STAGE_KB": 48, "MXB_TUNE_BLOCK": 512},
+             {"MXB_TUNE_TX": tx, "MXB_TUNE_OT_CTAS": 3, "MXB_TUNE_OT_STAGE_KB": 16}, {"MXB_TUNE_TX": tx, "MXB_TUNE_BLOCK": 512},
+             {"MXB_TUNE_TX": tx, "MXB_TUNE_STAGES": 2}, {"MXB_TUNE_TX": tx, "MXB_TUNE_OT_L2PROMO": 0}, {"MXB_TUNE_TX": tx, "MXB_TUNE_OT_L2PROMO": 3},
+             {"MXB_TUNE_TX": tx, "MXB_TUNE_OT_STAGE_KB": 64, "MXB_TUNE_OT_CTAS": 1, "MXB_TUNE_STAGES": 3, "MXB_TUNE_BLOCK": 512}]
+SHORT = ENVS[:2] + [{"MXB_OUTER_TMA_MODE": m, "MXB_TUNE_TX": tx} for m in (1, 0) for tx in (32, 64, 128)]
 
 d = 1024
 t = (torch.rand(d, d, d, device="cuda") * 0.25).to(torch.bfloat16)
@@ -58,7 +62,7 @@ o = torch.empty(1024, 512, device="cuda")
 tx_, to_ = mx.make_tensor(x), mx.make_tensor(o)
 wantx = x[:8].amax(1).t()
 sweep("fp32 512x1024x1024 permuted max", lambda: to_.set(mx.max(mx.permute(tx_, [2, 0, 1]), [2])).run(ex), x.numel() * 4 + o.numel() * 4,
-      lambda: bool(torch.equal(o[:, :8], wantx)), ENVS[:2] + [{"MXB_TUNE_TX": 64}, {"MXB_TUNE_TX": 128}, {"MXB_TUNE_TX": 32}])
+      lambda: bool(torch.equal(o[:, :8], wantx)), SHORT)
 del x, o
 torch.cuda.empty_cache()
 
@@ -68,4 +72,4 @@ oc = torch.empty(65536, device="cuda")
 ty_, toc = mx.make_tensor(y), mx.make_tensor(oc)
 wanty = y.double().sum(0)
 sweep("fp32 4096x65536 column sums", lambda: toc.set(mx.sum(ty_, [0])).run(ex), y.numel() * 4 + oc.numel() * 4,
-      lambda: bool((((oc.double() - wanty).abs() / wanty).max() <= 1e-5).item()), ENVS[:2] + [{"MXB_TUNE_TX": 64}, {"MXB_TUNE_TX": 128}, {"MXB_TUNE_TX": 32}])
+      lambda: bool((((oc.double() - wanty).abs() / wanty).max() <= 1e-5).item()), SHORT)
