@@ -6,20 +6,23 @@ from . import ops as mx
 
 
 def _time(ex, fn, iters=8, warm=2):
+    """(mean, best) device time of one launch in ms: three bursts of `iters` back-to-back launches, each between two
+    events on the launching stream (an event pair around a single launch would also time the host-side lowering of
+    the NEXT statement whenever the kernel is shorter than that, ~40 us)."""
     import torch
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
-    evs = []
-    for _ in range(iters):
+    bursts = []
+    for _ in range(3):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        fn()
+        for _ in range(iters):
+            fn()
         b.record()
-        evs.append((a, b))
-    torch.cuda.synchronize()
-    ts = [a.elapsed_time(b) for a, b in evs]
-    return sum(ts) / len(ts), min(ts)
+        torch.cuda.synchronize()
+        bursts.append(a.elapsed_time(b) / iters)
+    return sum(bursts) / len(bursts), min(bursts)
 
 
 def _entry(ex, ms, best, nbytes, nelem, peak):

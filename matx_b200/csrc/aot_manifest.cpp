@@ -198,6 +198,11 @@ void aot_manifest(std::vector<ManifestItem> *items) {
       if ((d == MXB_F32 || d == MXB_BF16) && op != MXB_RED_PROD) add(e, FAM_RED_OUTER_TMA, op, d, 0, false);
     }
   }
+  // one-pass variance (Welford + Chan) for rows that cannot stay on chip and for strided rows
+  for (int d : {MXB_F32, MXB_C64})
+    for (int team : {0, 1}) add(prog_identity(d), FAM_RED_INNER, MXB_RED_VAR, MXB_F32, team, d == MXB_F32);
+  add(prog_identity(MXB_F32), FAM_RED_OUTER, MXB_RED_VAR, MXB_F32, 0, false);
+  add(prog_identity(MXB_F32), FAM_RED_OUTER_TMA, MXB_RED_VAR, MXB_F32, 0, false);
   for (int d : {MXB_F32, MXB_C64}) add(prog_identity(d), FAM_VAR_SMEM, MXB_RED_VAR, MXB_F32, 0, false);
   add(prog_identity(MXB_F64), FAM_VAR_SMEM, MXB_RED_VAR, MXB_F64, 0, false);
   for (int ipt : {1, 2, 4, 8}) {

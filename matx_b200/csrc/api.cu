@@ -187,6 +187,7 @@ int acc_bytes(int op, int value_dtype) {
     case MXB_RED_ARGMAX: case MXB_RED_ARGMIN: return 16;
     case MXB_RED_ANY: case MXB_RED_ALL: return 4;
     case KOP_LSE: return 2 * dtype_bytes(value_dtype);
+    case MXB_RED_VAR: return 16;   // one-pass (mean, M2, n) state
     default: return dtype_bytes(value_dtype);
   }
 }
@@ -357,6 +358,11 @@ int reduce_launch(mxb_context *h, int kop, const mxb_expr_t &e, const ExprInfo &
   spec.out_dtype = out_dtype;
   int rot = -1;
   int var_ipt = 0, var_threads = 0, tma_ctas = 1, var_group_g = 0;
+  // variance of rows that are NOT vectorisable along their innermost dim (strided / permuted rows, column variance):
+  // the two-pass families would walk them one element per sector, so they go to the coalesced generic walkers with
+  // the one-pass (mean, M2, n) op instead (fp32 / complex<float>)
+  const bool chan_ok = kop == MXB_RED_VAR && (info.value_dtype == MXB_F32 || info.value_dtype == MXB_C64) && env_int("MXB_VAR_CHAN", 1);
+  if (var_smem && chan_ok && vmax > 1 && !inner_ok(vmax) && outer_dim(vmax) >= 0) var_smem = false;
   if (var_smem) {
     spec.family = FAM_VAR_SMEM;
     spec.V = (vmax > 1 && inner_ok(vmax)) ? vmax : 1;
@@ -561,6 +567,8 @@ int reduce_launch(mxb_context *h, int kop, const mxb_expr_t &e, const ExprInfo &
   p.idx.ptr = idx_out ? idx_out->data : nullptr;
   p.idx_base = opt.idx_base;
   p.post_div = opt.post_div ? 1 : 0;
+  // one-pass variance through the generic walkers: the stored value is M2 / (N - ddof)
+  if (kop == MXB_RED_VAR && (spec.family == FAM_RED_INNER || spec.family == FAM_RED_OUTER || spec.family == FAM_RED_OUTER_TMA)) p.post_div = 1;
   p.post_scale_f = (float)opt.post_scale;
   p.post_scale_d = opt.post_scale;
   p.post_sqrt = opt.post_sqrt ? 1 : 0;
@@ -830,8 +838,14 @@ int reduce_impl(mxb_context *h, int op, const mxb_expr_t *expr_in, int n_reduce,
     if (row_bytes <= (int64_t)h->max_smem_optin - 4096 && !getenv("MXB_VAR_TWO_LAUNCH")) {
       return reduce_launch(h, MXB_RED_VAR, e, info, n_reduce, out, nullptr, opt, /*var_smem=*/true);
     }
-    // Row does not fit in shared memory: the reference's own scheme — mean, then the sum of
-    // |x - mean|^2 — as two launches over the same skeletons (two reads of the input, like the reference).
+    // Row does not fit in shared memory.  fp32 / complex<float>: ONE read through the generic walkers with the
+    // one-pass (mean, M2, n) op (Welford per thread, Chan's combine across threads / CTAs).
+    if ((info.value_dtype == MXB_F32 || info.value_dtype == MXB_C64) && env_int("MXB_VAR_CHAN", 1) && !getenv("MXB_VAR_TWO_LAUNCH")) {
+      opt.post_div = true;
+      return reduce_launch(h, MXB_RED_VAR, e, info, n_reduce, out, nullptr, opt);
+    }
+    // fp64: the reference's own scheme — mean, then the sum of |x - mean|^2 — as two launches over the same
+    // skeletons (two reads of the input, like the reference).
     int64_t B = 1;
     for (int d = 0; d < nbd; ++d) B *= e.size[d];
     st = ensure_tmp(h, (size_t)std::max<int64_t>(B, 1) * (size_t)dtype_bytes(info.value_dtype));

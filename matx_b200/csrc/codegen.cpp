@@ -467,6 +467,9 @@ int kernel_wrapper_src(const ExprInfo &info, const KernelSpec &s, const std::str
         op = "mxb::OpArg<" + T + (s.op == MXB_RED_ARGMAX ? ", true>" : ", false>"); break;
       case MXB_RED_ANY: op = "mxb::OpLogic<" + T + ", true>"; break;
       case MXB_RED_ALL: op = "mxb::OpLogic<" + T + ", false>"; break;
+      case MXB_RED_VAR:   // one-pass (mean, M2, n) states through the generic walkers
+        if (!(info.value_dtype == MXB_F32 || cplx)) return fail("one-pass variance serves fp32 and complex<float>");
+        op = "mxb::OpVar<" + T + ">"; break;
       case KOP_LSE:
         if (!(info.value_dtype == MXB_F32 || info.value_dtype == MXB_F64)) return fail("softmax of a non-real-floating expression");
         op = "mxb::OpLse<" + T + ">"; break;

@@ -740,6 +740,44 @@ template <class T> struct OpLse {
   static __device__ __forceinline__ result_t finish(acc_t a) { return a.m; }
   static __device__ __forceinline__ i64 index(acc_t) { return 0; }
 };
+// one-pass variance: running (mean, M2 = sum |x - mean|^2, n) per thread (Welford's update), partial states combined
+// with Chan's parallel formula — numerically the stable way to get a variance from ONE read when the row cannot be
+// kept on chip for the reference's two passes (transforms/reduce.h:1406-1444): rows longer than shared memory, full
+// tensors, strided / permuted rows through the coalesced walkers.  Agrees with the two-pass result to a few fp32 ulp
+// of the variance (tests: 2e-5 bar, also on data with |mean| >> stddev and planted outliers).  `out` receives
+// M2 / (N - ddof) (and its sqrt for stdd) through the usual post-processing.  fp32 and complex<float>.
+template <class T> struct __align__(16) VarAcc { T mean; float m2; float n; };
+template <> struct __align__(16) VarAcc<float> { float mean; float m2; float n; float pad; };
+__device__ __forceinline__ float var_abs2dot(float d, float e) { return d * e; }
+__device__ __forceinline__ float var_abs2dot(cfloat d, cfloat e) { return d.re * e.re + d.im * e.im; }   // Re(d * conj(e))
+template <class T> struct OpVar {
+  typedef VarAcc<T> acc_t; typedef float result_t; enum { HAS_INDEX = 0 };
+  static __device__ __forceinline__ T zero() { return cvt<T>(0.0f); }
+  static __device__ __forceinline__ acc_t init() { acc_t a; a.mean = zero(); a.m2 = 0.f; a.n = 0.f; return a; }
+  static __device__ __forceinline__ void step(acc_t &a, T x, i64) {
+    a.n += 1.f;
+    const T d = x - a.mean;
+    a.mean = a.mean + d * __frcp_rn(a.n);
+    a.m2 += var_abs2dot(d, x - a.mean);
+  }
+  static __device__ __forceinline__ void merge(acc_t &a, acc_t b) {
+    if (b.n == 0.f) return;               // identity
+    if (a.n == 0.f) { a = b; return; }
+    const float n = a.n + b.n, f = b.n / n;
+    const T d = b.mean - a.mean;
+    a.mean = a.mean + d * f;
+    a.m2 = a.m2 + b.m2 + var_abs2dot(d, d) * (a.n * f);
+    a.n = n;
+  }
+  static __device__ __forceinline__ acc_t warp(acc_t a) {
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) { acc_t o = shfl_xor_t(a, m); merge(a, o); }
+    return a;
+  }
+  static __device__ __forceinline__ result_t finish(acc_t a) { return a.m2; }
+  static __device__ __forceinline__ i64 index(acc_t) { return 0; }
+};
+
 // second output of an op (none by default)
 template <class Op> struct AuxStore {
   static __device__ __forceinline__ void go(void *, i64, typename Op::acc_t) {}

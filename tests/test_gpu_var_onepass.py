@@ -1,0 +1,97 @@
+"""-m gpu: the one-pass variance op (Welford per thread, Chan's combine across threads / CTAs) that serves rows which
+cannot stay on chip for the reference's two passes (longer than shared memory, full tensors) and strided / permuted rows
+(column variance) through the coalesced generic walkers.  Bars: 2e-5 relative against the CPU oracle (the reference's
+two-pass arithmetic, transforms/reduce.h:1406-1444) and against fp64 truth, also on data with |mean| >> stddev and a
+planted outlier; identical bits run to run."""
+import numpy as np
+import pytest
+
+from matx_b200 import _abi as A
+from matx_b200 import ops as mx
+from tests import gpu_util as G
+from tests.test_gpu_parity import check, data
+
+pytestmark = pytest.mark.gpu
+
+
+def truth_var(x, axis, ddof):
+    x = x.astype(np.complex128 if np.iscomplexobj(x) else np.float64)
+    m = x.mean(axis=axis, keepdims=True)
+    return (np.abs(x - m) ** 2).sum(axis=axis) / (x.shape[axis] - ddof)
+
+
+def test_rows_longer_than_shared_memory(oracle):
+    rng = np.random.default_rng(70)
+    x = (rng.random((3, 70000)) + 2).astype(np.float32)            # 280 KB rows
+    for op, ddof in (("var", 1), ("stdd", 0)):
+        got, _, want, _, k = G.run_reduce(oracle, lambda t, op=op, ddof=ddof: getattr(mx, op)(t, [1], ddof), [x], A.F32)
+        assert k.startswith("red_inner") and "|var|" in k and k.endswith("aot"), k
+        tr = truth_var(x, 1, ddof)
+        tr = np.sqrt(tr) if op == "stdd" else tr
+        assert G.rel_err(got, want) <= 2e-5 and G.rel_err(got, tr) <= 2e-5, (op, G.rel_err(got, want), G.rel_err(got, tr))
+    z = (rng.standard_normal((2, 40000)) + 1j * rng.standard_normal((2, 40000)) + (3 - 2j)).astype(np.complex64)   # 320 KB rows
+    got, _, want, _, k = G.run_reduce(oracle, lambda t: mx.var(t, [1], 1), [z], A.F32)
+    assert k.startswith("red_inner") and "|var|" in k, k
+    assert G.rel_err(got, want) <= 2e-5 and G.rel_err(got, truth_var(z, 1, 1)) <= 2e-5
+
+
+def test_full_tensor_variance_one_read(oracle):
+    import torch
+    n = 1 << 26
+    g = torch.Generator(device="cuda")
+    g.manual_seed(71)
+    x = torch.rand(n, device="cuda", generator=g) * 3 + 1
+    ex = G.executor()
+    outs = []
+    for _ in range(3):
+        o = torch.zeros((), device="cuda")
+        mx.make_tensor(o).set(mx.var(mx.make_tensor(x), None, 1)).run(ex)
+        ex.sync()
+        outs.append(o.item())
+    k = ex.last_kernel()
+    assert k.startswith("red_inner") and "|var|" in k, k
+    assert len(set(outs)) == 1                                       # fixed combine order: same bits every run
+    tr = x.double().var(unbiased=True).item()
+    assert abs(outs[0] - tr) <= 2e-5 * tr, (outs[0], tr)
+    o = torch.zeros((), device="cuda")
+    mx.make_tensor(o).set(mx.stdd(mx.make_tensor(x), None, 0)).run(ex)
+    ex.sync()
+    ts = x.double().std(unbiased=False).item()
+    assert abs(o.item() - ts) <= 2e-5 * ts
+
+
+@pytest.mark.parametrize("shape", [(3000, 512), (700, 4100), (257, 20000)])
+def test_column_variance(oracle, shape):
+    rng = np.random.default_rng(72 + shape[1])
+    x = (rng.random(shape) + 0.5).astype(np.float32)
+    got, _, want, _, k = G.run_reduce(oracle, lambda t: mx.var(t, [0], 1), [x], A.F32)
+    assert k.startswith("red_outer") and "|var|" in k, k
+    assert G.rel_err(got, want) <= 2e-5 and G.rel_err(got, truth_var(x, 0, 1)) <= 2e-5, (k, G.rel_err(got, want))
+    z = data(rng, (shape[0], min(shape[1], 600)), A.C64)
+    got, _, want, _, k = G.run_reduce(oracle, lambda t: mx.stdd(t, [0], 0), [z], A.F32)
+    assert "|var|" in k, k
+    assert G.rel_err(got, want) <= 2e-5, (k, G.rel_err(got, want))
+
+
+def test_permuted_variance_through_the_tma_tiles(oracle):
+    rng = np.random.default_rng(73)
+    x = (rng.random((150, 70, 320)) * 2 + 1).astype(np.float32)
+    got, _, want, _, k = G.run_reduce(oracle, lambda t: mx.var(mx.permute(t, [2, 0, 1]), [2], 1), [x], A.F32)
+    assert k.startswith("red_outer_tma") and "|var|" in k, k
+    assert got.shape == (320, 150)
+    assert G.rel_err(got, want) <= 2e-5 and G.rel_err(got, truth_var(x, 1, 1).T) <= 2e-5
+
+
+def test_large_mean_and_outlier(oracle):
+    rng = np.random.default_rng(74)
+    x = (rng.random((2, 100000)) + 1e4).astype(np.float32)         # |mean| / stddev ~ 3.5e4: fp32 resolves x to 1e-3
+    got, _, want, _, k = G.run_reduce(oracle, lambda t: mx.var(t, [1], 1), [x], A.F32)
+    tr = truth_var(x, 1, 1)
+    assert "|var|" in k, k
+    # both fp32 methods are limited by the rounding of the mean itself; the one-pass result is held to the same bar
+    assert G.rel_err(got, tr) <= 1e-4 and G.rel_err(want, tr) <= 1e-4, (G.rel_err(got, tr), G.rel_err(want, tr))
+    y = rng.standard_normal((2, 90000)).astype(np.float32)
+    y[0, 0] = 1e6
+    y[1, 77777] = -1e6
+    got, _, want, _, k = G.run_reduce(oracle, lambda t: mx.var(t, [1], 1), [y], A.F32)
+    assert G.rel_err(got, truth_var(y, 1, 1)) <= 2e-5, (got, truth_var(y, 1, 1))
