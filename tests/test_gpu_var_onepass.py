@@ -88,8 +88,10 @@ def test_large_mean_and_outlier(oracle):
     got, _, want, _, k = G.run_reduce(oracle, lambda t: mx.var(t, [1], 1), [x], A.F32)
     tr = truth_var(x, 1, 1)
     assert "|var|" in k, k
-    # both fp32 methods are limited by the rounding of the mean itself; the one-pass result is held to the same bar
-    assert G.rel_err(got, tr) <= 1e-4 and G.rel_err(want, tr) <= 1e-4, (G.rel_err(got, tr), G.rel_err(want, tr))
+    # fp32 resolves these values to 1e-3, which bounds any fp32 method; the one-pass result stays within 1e-4 of fp64
+    # truth (measured 1.3e-5).  The reference's HostExecutor arithmetic (sequential fp32 sum for the mean, restated by the
+    # oracle) is NOT usable as the yardstick here: its mean drifts and the variance comes out 158x too large (13.2 vs 0.083).
+    assert G.rel_err(got, tr) <= 1e-4, (G.rel_err(got, tr), G.rel_err(want, tr))
     y = rng.standard_normal((2, 90000)).astype(np.float32)
     y[0, 0] = 1e6
     y[1, 77777] = -1e6
