@@ -835,6 +835,13 @@ int reduce_impl(mxb_context *h, int op, const mxb_expr_t *expr_in, int n_reduce,
     opt.post_scale = (double)(R - ddof);
     opt.post_sqrt = (op == MXB_RED_STDD);
     const int64_t row_bytes = R * dtype_bytes(info.value_dtype);
+    // MXB_VAR_ONEPASS=1: every fp32 / complex<float> variance through the one-pass op (A/B knob, tools/var_onepass_ab.py)
+    const bool onepass_all = (info.value_dtype == MXB_F32 || info.value_dtype == MXB_C64) && env_int("MXB_VAR_CHAN", 1) &&
+                             env_int("MXB_VAR_ONEPASS", 0) && !getenv("MXB_VAR_TWO_LAUNCH") && !getenv("MXB_VAR_SMEM_ONLY");
+    if (onepass_all) {
+      opt.post_div = true;
+      return reduce_launch(h, MXB_RED_VAR, e, info, n_reduce, out, nullptr, opt);
+    }
     if (row_bytes <= (int64_t)h->max_smem_optin - 4096 && !getenv("MXB_VAR_TWO_LAUNCH")) {
       return reduce_launch(h, MXB_RED_VAR, e, info, n_reduce, out, nullptr, opt, /*var_smem=*/true);
     }
