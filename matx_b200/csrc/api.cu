@@ -187,7 +187,7 @@ int acc_bytes(int op, int value_dtype) {
     case MXB_RED_ARGMAX: case MXB_RED_ARGMIN: return 16;
     case MXB_RED_ANY: case MXB_RED_ALL: return 4;
     case KOP_LSE: return 2 * dtype_bytes(value_dtype);
-    case MXB_RED_VAR: return 16;   // one-pass (mean, M2, n) state
+    case MXB_RED_VAR: return value_dtype == MXB_C64 ? 32 : 16;   // one-pass (pivot, s1, s2, count) state: 16 / 24 bytes
     default: return dtype_bytes(value_dtype);
   }
 }

@@ -740,41 +740,55 @@ template <class T> struct OpLse {
   static __device__ __forceinline__ result_t finish(acc_t a) { return a.m; }
   static __device__ __forceinline__ i64 index(acc_t) { return 0; }
 };
-// one-pass variance: running (mean, M2 = sum |x - mean|^2, n) per thread (Welford's update), partial states combined
-// with Chan's parallel formula — numerically the stable way to get a variance from ONE read when the row cannot be
+// one-pass variance: every accumulator lane keeps SHIFTED sums about a pivot K — s1 = sum (x - K), s2 = sum |x - K|^2,
+// cnt — i.e. the state (mean = K + s1/cnt, M2 = s2 - |s1|^2/cnt, cnt) in a form whose per-element update is three
+// arithmetic instructions and no division.  The pivot is the lane's first element and the state is re-centred
+// (K <- mean, s1 <- 0, s2 <- M2) every 64 elements, so the cancellation in s2 - |s1|^2/cnt is bounded by the 64
+// elements since the last re-centring whatever the data (|mean| >> stddev, outliers).  Partial states are combined
+// with Chan's parallel formula.  Numerically the stable way to get a variance from ONE read when the row cannot be
 // kept on chip for the reference's two passes (transforms/reduce.h:1406-1444): rows longer than shared memory, full
-// tensors, strided / permuted rows through the coalesced walkers.  Agrees with the two-pass result to a few fp32 ulp
-// of the variance (tests: 2e-5 bar, also on data with |mean| >> stddev and planted outliers).  `out` receives
-// M2 / (N - ddof) (and its sqrt for stdd) through the usual post-processing.  fp32 and complex<float>.
-template <class T> struct __align__(16) VarAcc { T mean; float m2; float n; };
-template <> struct __align__(16) VarAcc<float> { float mean; float m2; float n; float pad; };
+// tensors, strided / permuted rows through the coalesced walkers.  `out` receives M2 / (N - ddof) (and its sqrt for
+// stdd) through the usual post-processing.  fp32 and complex<float>.  (A Welford update with a correctly rounded
+// reciprocal per element was measured first: same accuracy, ~30 instructions per element, 0.64-0.72 of the HBM peak.)
+template <class T> struct VarAcc { T k; T s1; float s2; int cnt; };   // 16 bytes (fp32) / 24 bytes (complex<float>)
 __device__ __forceinline__ float var_abs2dot(float d, float e) { return d * e; }
 __device__ __forceinline__ float var_abs2dot(cfloat d, cfloat e) { return d.re * e.re + d.im * e.im; }   // Re(d * conj(e))
 template <class T> struct OpVar {
   typedef VarAcc<T> acc_t; typedef float result_t; enum { HAS_INDEX = 0 };
   static __device__ __forceinline__ T zero() { return cvt<T>(0.0f); }
-  static __device__ __forceinline__ acc_t init() { acc_t a; a.mean = zero(); a.m2 = 0.f; a.n = 0.f; return a; }
+  static __device__ __forceinline__ acc_t init() { acc_t a; a.k = zero(); a.s1 = zero(); a.s2 = 0.f; a.cnt = 0; return a; }
+  // (K, s1, s2, cnt) -> (mean, 0, M2, cnt)
+  static __device__ __forceinline__ void recentre(acc_t &a) {
+    if (a.cnt == 0) return;
+    const T m = a.s1 * (1.0f / (float)a.cnt);
+    a.k = a.k + m;
+    a.s2 = a.s2 - var_abs2dot(a.s1, m);
+    a.s1 = zero();
+  }
   static __device__ __forceinline__ void step(acc_t &a, T x, i64) {
-    a.n += 1.f;
-    const T d = x - a.mean;
-    a.mean = a.mean + d * __frcp_rn(a.n);
-    a.m2 += var_abs2dot(d, x - a.mean);
+    if (a.cnt == 0) a.k = x;
+    const T d = x - a.k;
+    a.s1 = a.s1 + d;
+    a.s2 += var_abs2dot(d, d);
+    if (((++a.cnt) & 63) == 0) recentre(a);
   }
   static __device__ __forceinline__ void merge(acc_t &a, acc_t b) {
-    if (b.n == 0.f) return;               // identity
-    if (a.n == 0.f) { a = b; return; }
-    const float n = a.n + b.n, f = b.n / n;
-    const T d = b.mean - a.mean;
-    a.mean = a.mean + d * f;
-    a.m2 = a.m2 + b.m2 + var_abs2dot(d, d) * (a.n * f);
-    a.n = n;
+    if (b.cnt == 0) return;               // identity
+    if (a.cnt == 0) { a = b; return; }
+    recentre(a);
+    recentre(b);
+    const float na = (float)a.cnt, nb = (float)b.cnt, f = nb / (na + nb);
+    const T d = b.k - a.k;
+    a.k = a.k + d * f;
+    a.s2 = a.s2 + b.s2 + var_abs2dot(d, d) * (na * f);
+    a.cnt += b.cnt;
   }
   static __device__ __forceinline__ acc_t warp(acc_t a) {
 #pragma unroll
     for (int m = 16; m > 0; m >>= 1) { acc_t o = shfl_xor_t(a, m); merge(a, o); }
     return a;
   }
-  static __device__ __forceinline__ result_t finish(acc_t a) { return a.m2; }
+  static __device__ __forceinline__ result_t finish(acc_t a) { recentre(a); return a.s2; }
   static __device__ __forceinline__ i64 index(acc_t) { return 0; }
 };
 
