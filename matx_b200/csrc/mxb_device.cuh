@@ -743,9 +743,10 @@ template <class T> struct OpLse {
 // one-pass variance: every accumulator lane keeps SHIFTED sums about a pivot K — s1 = sum (x - K), s2 = sum |x - K|^2,
 // cnt — i.e. the state (mean = K + s1/cnt, M2 = s2 - |s1|^2/cnt, cnt) in a form whose per-element update is three
 // arithmetic instructions and no division.  The pivot is the lane's first element and the state is re-centred
-// (K <- mean, s1 <- 0, s2 <- M2) every 64 elements, so the cancellation in s2 - |s1|^2/cnt is bounded by the 64
-// elements since the last re-centring whatever the data (|mean| >> stddev, outliers).  Partial states are combined
-// with Chan's parallel formula.  Numerically the stable way to get a variance from ONE read when the row cannot be
+// (K <- mean, s1 <- ~0, s2 <- M2) after 8 elements and then every 64, so the cancellation in s2 - |s1|^2/cnt is bounded by the 64
+// elements since the last re-centring whatever the data (|mean| >> stddev, outliers).  Partial states are combined by
+// re-expressing one about the other's (re-centred) pivot — Chan's parallel formula without its divisions; moving a
+// pivot is exact algebra for any offset, so an approximate reciprocal (MUFU.RCP) picks the new pivot.  Numerically the stable way to get a variance from ONE read when the row cannot be
 // kept on chip for the reference's two passes (transforms/reduce.h:1406-1444): rows longer than shared memory, full
 // tensors, strided / permuted rows through the coalesced walkers.  `out` receives M2 / (N - ddof) (and its sqrt for
 // stdd) through the usual post-processing.  fp32 and complex<float>.  (A Welford update with a correctly rounded
@@ -757,30 +758,35 @@ template <class T> struct OpVar {
   typedef VarAcc<T> acc_t; typedef float result_t; enum { HAS_INDEX = 0 };
   static __device__ __forceinline__ T zero() { return cvt<T>(0.0f); }
   static __device__ __forceinline__ acc_t init() { acc_t a; a.k = zero(); a.s1 = zero(); a.s2 = 0.f; a.cnt = 0; return a; }
-  // (K, s1, s2, cnt) -> (mean, 0, M2, cnt)
+  // move the pivot by m: exact algebra for ANY m (sum (x-K-m) = s1 - n m, sum |x-K-m|^2 = s2 - 2 Re(conj(m) s1) + n |m|^2)
+  static __device__ __forceinline__ void shift(acc_t &a, T m) {
+    const float n = (float)a.cnt;
+    a.k = a.k + m;
+    a.s2 = a.s2 + (n * var_abs2dot(m, m) - 2.f * var_abs2dot(m, a.s1));
+    a.s1 = a.s1 - m * n;
+  }
+  // pivot <- (an approximation of) the mean: MUFU.RCP is enough, the shift is exact for whatever m comes out
   static __device__ __forceinline__ void recentre(acc_t &a) {
     if (a.cnt == 0) return;
-    const T m = a.s1 * (1.0f / (float)a.cnt);
-    a.k = a.k + m;
-    a.s2 = a.s2 - var_abs2dot(a.s1, m);
-    a.s1 = zero();
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"((float)a.cnt));
+    shift(a, a.s1 * r);
   }
   static __device__ __forceinline__ void step(acc_t &a, T x, i64) {
     if (a.cnt == 0) a.k = x;
     const T d = x - a.k;
     a.s1 = a.s1 + d;
     a.s2 += var_abs2dot(d, d);
-    if (((++a.cnt) & 63) == 0) recentre(a);
+    if (((++a.cnt) & 63) == 8) recentre(a);   // after 8, 72, 136, ... elements: a bad first pivot (an outlier) is dropped early
   }
+  // a <- a (+) b: a's pivot goes to a's mean, b is re-expressed about it (no division), the sums add
   static __device__ __forceinline__ void merge(acc_t &a, acc_t b) {
     if (b.cnt == 0) return;               // identity
     if (a.cnt == 0) { a = b; return; }
     recentre(a);
-    recentre(b);
-    const float na = (float)a.cnt, nb = (float)b.cnt, f = nb / (na + nb);
-    const T d = b.k - a.k;
-    a.k = a.k + d * f;
-    a.s2 = a.s2 + b.s2 + var_abs2dot(d, d) * (na * f);
+    shift(b, a.k - b.k);
+    a.s1 = a.s1 + b.s1;
+    a.s2 += b.s2;
     a.cnt += b.cnt;
   }
   static __device__ __forceinline__ acc_t warp(acc_t a) {
@@ -788,7 +794,12 @@ template <class T> struct OpVar {
     for (int m = 16; m > 0; m >>= 1) { acc_t o = shfl_xor_t(a, m); merge(a, o); }
     return a;
   }
-  static __device__ __forceinline__ result_t finish(acc_t a) { recentre(a); return a.s2; }
+  // M2 = s2 - |s1|^2 / n about a pivot that is the mean to rounding: the correction term is tiny, the division exact
+  static __device__ __forceinline__ result_t finish(acc_t a) {
+    if (a.cnt == 0) return 0.f;
+    recentre(a);
+    return a.s2 - var_abs2dot(a.s1, a.s1) / (float)a.cnt;
+  }
   static __device__ __forceinline__ i64 index(acc_t) { return 0; }
 };
 
