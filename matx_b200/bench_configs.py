@@ -152,6 +152,27 @@ def run_next(ex, peak):
         res[name] = r
         del x, y
         torch.cuda.empty_cache()
+    # variance where the row cannot stay on chip (one-pass op): a full tensor, 256 KB rows, column variance
+    for name, shape, dims in (("var(x) fp32 2^30 (full tensor, one read)", (1 << 30,), None),
+                              ("var(x,{1}) fp32 4096x65536 (256 KB rows)", (4096, 65536), [1]),
+                              ("var(x,{0}) fp32 4096x65536 (column variance)", (4096, 65536), [0])):
+        x = torch.rand(*shape, device="cuda") + 0.5
+        oshape = () if dims is None else ((shape[0],) if dims == [1] else (shape[1],))
+        o = torch.empty(oshape, device="cuda")
+        tx, to = mx.make_tensor(x), mx.make_tensor(o)
+        ms, best = _time(ex, lambda: to.set(mx.var(tx, dims, 1)).run(ex))
+        r = _entry(ex, ms, best, x.numel() * 4 + o.numel() * 4, x.numel(), peak)
+        if dims is None:
+            want = x.double().var(unbiased=True)
+            r["rel_err_vs_fp64"] = ((o.double() - want).abs() / want).item()
+        else:
+            xs = x[:64].double() if dims == [1] else x[:, :64].double()
+            want = xs.var(dim=1 if dims == [1] else 0, unbiased=True)
+            got = o[:64].double()
+            r["max_rel_err_first_64_vs_fp64"] = ((got - want).abs() / want).max().item()
+        res[name] = r
+        del x, o
+        torch.cuda.empty_cache()
     return res
 
 

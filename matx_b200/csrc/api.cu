@@ -838,7 +838,12 @@ int reduce_impl(mxb_context *h, int op, const mxb_expr_t *expr_in, int n_reduce,
     // MXB_VAR_ONEPASS=1: every fp32 / complex<float> variance through the one-pass op (A/B knob, tools/var_onepass_ab.py)
     const bool onepass_all = (info.value_dtype == MXB_F32 || info.value_dtype == MXB_C64) && env_int("MXB_VAR_CHAN", 1) &&
                              env_int("MXB_VAR_ONEPASS", 0) && !getenv("MXB_VAR_TWO_LAUNCH") && !getenv("MXB_VAR_SMEM_ONLY");
-    if (onepass_all) {
+    // fp32 rows of 16..128 elements: the warp-team walker with the one-pass op beats the register-resident two-pass
+    // group kernel (8388608x32: 0.54 vs 0.38 of peak, 4194304x64: 0.48 vs 0.36; profiles/r1_var_onepass_ab.jsonl)
+    const bool onepass_short = info.value_dtype == MXB_F32 && env_int("MXB_VAR_CHAN", 1) && R >= env_int("MXB_VAR_ONEPASS_MIN_R", 16) &&
+                               R <= env_int("MXB_VAR_ONEPASS_MAX_R", 128) && !getenv("MXB_VAR_TWO_LAUNCH") && !getenv("MXB_VAR_SMEM_ONLY") &&
+                               !getenv("MXB_VAR_NO_GROUP");
+    if (onepass_all || onepass_short) {
       opt.post_div = true;
       return reduce_launch(h, MXB_RED_VAR, e, info, n_reduce, out, nullptr, opt);
     }
