@@ -314,7 +314,7 @@ int reduce_launch(mxb_context *h, int kop, const mxb_expr_t &e, const ExprInfo &
   if (B == 0) return MXB_OK;
   if (R == 0) return fail(MXB_ERR_INVALID, "reduction over zero elements");
 
-  const int out_dtype = opt.raw_partial ? info.value_dtype : out->dtype;
+  const int out_dtype = opt.raw_partial ? (kop == MXB_RED_VAR ? (int)MXB_F32 : info.value_dtype) : out->dtype;
   const int vmax = env_int("MXB_TUNE_V", 0) > 0 ? env_int("MXB_TUNE_V", 0) : policy_vmax(info);
   const int nl = e.n_leaves;
 
@@ -362,7 +362,7 @@ int reduce_launch(mxb_context *h, int kop, const mxb_expr_t &e, const ExprInfo &
   // the two-pass families would walk them one element per sector, so they go to the coalesced generic walkers with
   // the one-pass (mean, M2, n) op instead (fp32 / complex<float>)
   const bool chan_ok = kop == MXB_RED_VAR && (info.value_dtype == MXB_F32 || info.value_dtype == MXB_C64) && env_int("MXB_VAR_CHAN", 1);
-  if (var_smem && chan_ok && vmax > 1 && !inner_ok(vmax) && outer_dim(vmax) >= 0) var_smem = false;
+  if (var_smem && chan_ok && vmax > 1 && !inner_ok(vmax) && outer_dim(vmax) >= 0 && R < (1ll << 31)) var_smem = false;
   if (var_smem) {
     spec.family = FAM_VAR_SMEM;
     spec.V = (vmax > 1 && inner_ok(vmax)) ? vmax : 1;
@@ -733,6 +733,15 @@ int var_partial(mxb_context *h, const mxb_expr_t &e, const ExprInfo &info, const
   int64_t n = 1;
   for (int d = 0; d < e.rank; ++d) n *= e.size[d];
   if (n <= 0) return fail(MXB_ERR_INVALID, "variance of an empty slab");
+  if ((info.value_dtype == MXB_F32 || info.value_dtype == MXB_C64) && env_int("MXB_VAR_CHAN", 1) && n < (1ll << 31)) {
+    // ONE launch, one read: the one-pass state of the slab, written (or pushed to the peers) by the last CTA as the
+    // (mean, M2, n) record of doubles the fold expects
+    mxb_out_t rec_out;
+    memset(&rec_out, 0, sizeof rec_out);
+    rec_out.data = record;
+    rec_out.dtype = MXB_F32;
+    return reduce_launch(h, MXB_RED_VAR, e, info, e.rank, &rec_out, nullptr, popt, false);
+  }
   int st = ensure_tmp(h, 64);
   if (st != MXB_OK) return st;
   const int rdt = info.value_dtype == MXB_F64 ? MXB_F64 : MXB_F32;
@@ -837,7 +846,7 @@ int reduce_impl(mxb_context *h, int op, const mxb_expr_t *expr_in, int n_reduce,
     const int64_t row_bytes = R * dtype_bytes(info.value_dtype);
     // MXB_VAR_ONEPASS=1: every fp32 / complex<float> variance through the one-pass op (A/B knob, tools/var_onepass_ab.py)
     const bool onepass_all = (info.value_dtype == MXB_F32 || info.value_dtype == MXB_C64) && env_int("MXB_VAR_CHAN", 1) &&
-                             env_int("MXB_VAR_ONEPASS", 0) && !getenv("MXB_VAR_TWO_LAUNCH") && !getenv("MXB_VAR_SMEM_ONLY");
+                             env_int("MXB_VAR_ONEPASS", 0) && !getenv("MXB_VAR_TWO_LAUNCH") && !getenv("MXB_VAR_SMEM_ONLY") && R < (1ll << 31);
     // fp32 rows of 16..128 elements: the warp-team walker with the one-pass op beats the register-resident two-pass
     // group kernel (8388608x32: 0.54 vs 0.38 of peak, 4194304x64: 0.48 vs 0.36; profiles/r1_var_onepass_ab.jsonl)
     const bool onepass_short = info.value_dtype == MXB_F32 && env_int("MXB_VAR_CHAN", 1) && R >= env_int("MXB_VAR_ONEPASS_MIN_R", 16) &&
@@ -852,7 +861,8 @@ int reduce_impl(mxb_context *h, int op, const mxb_expr_t *expr_in, int n_reduce,
     }
     // Row does not fit in shared memory.  fp32 / complex<float>: ONE read through the generic walkers with the
     // one-pass (mean, M2, n) op (Welford per thread, Chan's combine across threads / CTAs).
-    if ((info.value_dtype == MXB_F32 || info.value_dtype == MXB_C64) && env_int("MXB_VAR_CHAN", 1) && !getenv("MXB_VAR_TWO_LAUNCH")) {
+    if ((info.value_dtype == MXB_F32 || info.value_dtype == MXB_C64) && env_int("MXB_VAR_CHAN", 1) && !getenv("MXB_VAR_TWO_LAUNCH") &&
+        R < (1ll << 31)) {   // the state counts elements in an int
       opt.post_div = true;
       return reduce_launch(h, MXB_RED_VAR, e, info, n_reduce, out, nullptr, opt);
     }

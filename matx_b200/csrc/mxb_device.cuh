@@ -870,13 +870,39 @@ __device__ __forceinline__ void decomp(i64 flat, int n, const i64 *sz, i64 *idx)
   }
 }
 
-template <class Op, class OutT>
-__device__ __forceinline__ void store_result(const RedParams &p, i64 b, typename Op::acc_t acc) {
-  if (p.raw_partial) {
+// what a slab's 32-byte record holds: the accumulator's own bits, except for the one-pass variance, whose record is
+// the (mean re, mean im, M2, n) quadruple of doubles that the multi-GPU fold combines with Chan's formula
+template <class Op> struct PartialPack {
+  static __device__ __forceinline__ void go(PartialRec &rec, typename Op::acc_t acc) {
     union { PartialRec rec; typename Op::acc_t a; } u;
 #pragma unroll
     for (int i = 0; i < 8; ++i) u.rec.w[i] = 0;
     u.a = acc;
+    rec = u.rec;
+  }
+};
+__device__ __forceinline__ double var_re(float x) { return (double)x; }
+__device__ __forceinline__ double var_im(float) { return 0.0; }
+__device__ __forceinline__ double var_re(cfloat x) { return (double)x.re; }
+__device__ __forceinline__ double var_im(cfloat x) { return (double)x.im; }
+template <class T> struct PartialPack<OpVar<T> > {
+  static __device__ __forceinline__ void go(PartialRec &rec, VarAcc<T> a) {
+    union { PartialRec rec; double d[4]; } u;
+    const double n = (double)a.cnt, inv = a.cnt ? 1.0 / n : 0.0;
+    const double s1r = var_re(a.s1), s1i = var_im(a.s1);
+    u.d[0] = var_re(a.k) + s1r * inv;                           // mean
+    u.d[1] = var_im(a.k) + s1i * inv;
+    u.d[2] = (double)a.s2 - (s1r * s1r + s1i * s1i) * inv;      // M2 about that mean
+    u.d[3] = n;
+    rec = u.rec;
+  }
+};
+
+template <class Op, class OutT>
+__device__ __forceinline__ void store_result(const RedParams &p, i64 b, typename Op::acc_t acc) {
+  if (p.raw_partial) {
+    union { PartialRec rec; int pad_; } u;
+    PartialPack<Op>::go(u.rec, acc);
     if (p.raw_partial == 2) {
       push_record(p.peer, u.rec);
       return;
