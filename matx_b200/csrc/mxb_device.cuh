@@ -777,7 +777,17 @@ template <class T> struct OpVar {
     const T d = x - a.k;
     a.s1 = a.s1 + d;
     a.s2 += var_abs2dot(d, d);
-    if (((++a.cnt) & 63) == 8) recentre(a);   // after 8, 72, 136, ... elements: a bad first pivot (an outlier) is dropped early
+    if (((++a.cnt) & 63) == 8) {
+      // after 8, 72, 136, ... elements (a bad first pivot — an outlier — is dropped early): K <- K + m, m = s1 / cnt by
+      // MUFU.RCP.  The compact form drops the residual s1 - cnt*m = s1 * O(2^-23) (the hot loop stays small: the full
+      // shift() inlined V x U times cost 10 % on long rows); merges and the final value use the exact shift
+      float r;
+      asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"((float)a.cnt));
+      const T m = a.s1 * r;
+      a.k = a.k + m;
+      a.s2 -= var_abs2dot(a.s1, m);
+      a.s1 = zero();
+    }
   }
   // a <- a (+) b: a's pivot goes to a's mean, b is re-expressed about it (no division), the sums add
   static __device__ __forceinline__ void merge(acc_t &a, acc_t b) {
