@@ -18,6 +18,8 @@
  *                                                             include/matx/transforms/cub.h:647-894,1281-1328
  *   mxb_softmax      <- softmax_impl (both overloads)         include/matx/transforms/reduce.h:362-445
  *   mxb_cumsum       <- cumsum_impl + ExecPrefixScanEx        include/matx/transforms/cub.h:2367-2395,375-408
+ *   mxb_find         <- find_impl / find_idx_impl + ExecSelect / ExecSelectIndex
+ *                                                             include/matx/transforms/cub.h:2609-2625,2705-2721,912-1010
  *   mxb_create / mxb_destroy / mxb_set_stream
  *                    <- cudaExecutor ctor / getStream         include/matx/executors/cuda.h:60-82
  *   mxb_sync         <- CudaExecutorBase::sync                include/matx/executors/cuda_executor_common.h:137
@@ -188,6 +190,20 @@ int mxb_softmax(mxb_handle_t h, const mxb_expr_t *expr, int n_reduce_dims, const
  * many rows -> a CTA per row with a running carry; few long rows -> a CTA per tile, tile and group totals exchanged
  * through L2 inside the launch. */
 int mxb_cumsum(mxb_handle_t h, const mxb_expr_t *expr, const mxb_out_t *out);
+
+/* Stream compaction: out[0 .. n) = the elements x of `expr` (row-major flat order, stable) with `x <select_op> threshold`
+ * (want_indices == 0) or their flat indices (want_indices != 0), and *count_out = n.  Reference: find_impl / find_idx_impl
+ * (cudaExecutor overloads, transforms/cub.h:2609-2625,2705-2721 -> matxCubPlan_t::ExecSelect / ExecSelectIndex :912-1010,
+ * cub::DeviceSelect::If) with the selection functors LT / GT / EQ / NEQ / LTE / GTE (:2521-2588); the host path
+ * (:2656-2675,2752-2770) defines the order and the int count.  `out` is rank 1 and contiguous; values are converted to
+ * its dtype, indices need MXB_I32 (the reference's static_cast<int>) or MXB_I64.  Elements beyond out->size[0] are counted
+ * but not written (the reference would write past the end).  `count_out` is rank 0, MXB_I32.  Real value types only.
+ * Two launches (count + in-launch scan of the tile counts, scatter), deterministic, nothing to clear between calls. */
+typedef enum {
+  MXB_SEL_LT = 0, MXB_SEL_GT = 1, MXB_SEL_EQ = 2, MXB_SEL_NEQ = 3, MXB_SEL_LTE = 4, MXB_SEL_GTE = 5, MXB_SEL_COUNT
+} mxb_select_op_t;
+int mxb_find(mxb_handle_t h, const mxb_expr_t *expr, int select_op, double threshold, const mxb_out_t *out,
+             const mxb_out_t *count_out, int want_indices);
 
 /* ---- multi-GPU (no counterpart in the reference) -------------------------------- */
 /* Slab-sharded full-tensor reductions: each rank reduces its slab with mxb_reduce_partial into a

@@ -377,6 +377,19 @@ class b200Executor : public cudaExecutor {
       return !b200_detail::check_or_fallback(mxb_cumsum(h_.get(), &b.e, &out));
     }
   }
+  // find / find_idx with one of the reference's selection functors (LT / GT / EQ / NEQ / LTE / GTE, cub.h:2521-2588)
+  template <class Out, class Cnt, class In, class T> bool find(Out &dest, Cnt &num_found, const In &in, int sel_op, T thr, bool want_idx) const {
+    if constexpr (!b200_detail::lowerable<In>() || Out::Rank() != 1 || Cnt::Rank() != 0 ||
+                  !std::is_same_v<typename Cnt::value_type, int> || !std::is_arithmetic_v<T>) return false;
+    else {
+      b200_detail::Builder b;
+      mxb_out_t out, cnt;
+      if (!b200_detail::out_desc(dest, out)) return false;
+      if (!b200_detail::out_desc(num_found, cnt)) return false;
+      if (!b200_detail::lower_root(b, in)) return false;
+      return !b200_detail::check_or_fallback(mxb_find(h_.get(), &b.e, sel_op, static_cast<double>(thr), &out, &cnt, want_idx ? 1 : 0));
+    }
+  }
   template <class Out, class Idx, class In> bool reduce_idx(int op, Out &dest, Idx *idest, const In &in, int ddof) const {
     if constexpr (!b200_detail::lowerable<In>()) return false;
     else {
@@ -503,6 +516,42 @@ void cumsum_impl(OutputTensor &a_out, const InputOperator &a, const b200Executor
 template <typename OutputTensor, typename InputOperator>
 void cumsum_impl(OutputTensor &a_out, const InputOperator &a, b200Executor &exec) {
   cumsum_impl(a_out, a, static_cast<const b200Executor &>(exec));
+}
+
+// find / find_idx (transforms/cub.h:2609-2625,2705-2721): FindOp::Exec / FindIdxOp::Exec call
+// `find_impl(out, num_found, a_, sel_, ex)` (operators/find.h:89, find_idx.h:89), so
+// `(mtie(out, num_found) = find(x, GT{0.5f})).run(exec)` lands here when the functor is one of the reference's six
+// comparison structs (their threshold is the public member c_); any other callable keeps the reference path.
+namespace b200_detail {
+template <class S> struct sel_code { static constexpr int value = -1; };
+template <class T> struct sel_code<LT<T>> { static constexpr int value = MXB_SEL_LT; };
+template <class T> struct sel_code<GT<T>> { static constexpr int value = MXB_SEL_GT; };
+template <class T> struct sel_code<EQ<T>> { static constexpr int value = MXB_SEL_EQ; };
+template <class T> struct sel_code<NEQ<T>> { static constexpr int value = MXB_SEL_NEQ; };
+template <class T> struct sel_code<LTE<T>> { static constexpr int value = MXB_SEL_LTE; };
+template <class T> struct sel_code<GTE<T>> { static constexpr int value = MXB_SEL_GTE; };
+}  // namespace b200_detail
+template <typename SelectType, typename CountTensor, typename OutputTensor, typename InputOperator>
+void find_impl(OutputTensor &a_out, CountTensor &num_found, const InputOperator &a, SelectType sel, const b200Executor &exec) {
+  bool done = false;
+  if constexpr (b200_detail::sel_code<SelectType>::value >= 0)
+    done = exec.find(a_out, num_found, a, b200_detail::sel_code<SelectType>::value, sel.c_, false);
+  if (!done) find_impl(a_out, num_found, a, sel, static_cast<const cudaExecutor &>(exec));
+}
+template <typename SelectType, typename CountTensor, typename OutputTensor, typename InputOperator>
+void find_impl(OutputTensor &a_out, CountTensor &num_found, const InputOperator &a, SelectType sel, b200Executor &exec) {
+  find_impl(a_out, num_found, a, sel, static_cast<const b200Executor &>(exec));
+}
+template <typename SelectType, typename CountTensor, typename OutputTensor, typename InputOperator>
+void find_idx_impl(OutputTensor &a_out, CountTensor &num_found, const InputOperator &a, SelectType sel, const b200Executor &exec) {
+  bool done = false;
+  if constexpr (b200_detail::sel_code<SelectType>::value >= 0)
+    done = exec.find(a_out, num_found, a, b200_detail::sel_code<SelectType>::value, sel.c_, true);
+  if (!done) find_idx_impl(a_out, num_found, a, sel, static_cast<const cudaExecutor &>(exec));
+}
+template <typename SelectType, typename CountTensor, typename OutputTensor, typename InputOperator>
+void find_idx_impl(OutputTensor &a_out, CountTensor &num_found, const InputOperator &a, SelectType sel, b200Executor &exec) {
+  find_idx_impl(a_out, num_found, a, sel, static_cast<const b200Executor &>(exec));
 }
 
 // allclose (transforms/reduce.h:1321-1331): all(isclose(in1, in2, rtol, atol)) into a rank-0 int tensor, one launch

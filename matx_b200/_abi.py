@@ -29,6 +29,7 @@ DTYPE_BYTES = [4, 8, 2, 2, 8, 4, 8, 1]
 
 # mxb_reduce_op_t
 RED_SUM, RED_MEAN, RED_VAR, RED_STDD, RED_MAX, RED_MIN, RED_ARGMAX, RED_ARGMIN, RED_ANY, RED_ALL, RED_PROD = range(11)
+SEL_LT, SEL_GT, SEL_EQ, SEL_NEQ, SEL_LTE, SEL_GTE = range(6)   # mxb_select_op_t
 
 # mxb_opcode_t
 OP_LEAF, OP_CONST = 0, 1
@@ -68,7 +69,7 @@ EXPORTED = [
     "mxb_create", "mxb_destroy", "mxb_set_stream", "mxb_sync", "mxb_elementwise", "mxb_reduce", "mxb_reduce_partial",
     "mxb_reduce_finalize", "mxb_version", "mxb_last_error", "mxb_device_count", "mxb_last_kernel", "mxb_launch_count",
     "mxb_is_aot", "mxb_reduce_partial_push", "mxb_exchange_finalize", "mxb_exchange_alloc", "mxb_exchange_open", "mxb_exchange_close",
-    "mxb_exchange_free", "mxb_softmax", "mxb_cumsum",
+    "mxb_exchange_free", "mxb_softmax", "mxb_cumsum", "mxb_find",
 ]
 
 
@@ -111,6 +112,7 @@ def _load() -> C.CDLL:
     lib.mxb_reduce.argtypes = [vp, i32, C.POINTER(Expr), i32, C.POINTER(Out), C.POINTER(Out), i32]
     lib.mxb_softmax.argtypes = [vp, C.POINTER(Expr), i32, C.POINTER(Out)]
     lib.mxb_cumsum.argtypes = [vp, C.POINTER(Expr), C.POINTER(Out)]
+    lib.mxb_find.argtypes = [vp, C.POINTER(Expr), i32, C.c_double, C.POINTER(Out), C.POINTER(Out), i32]
     lib.mxb_reduce_partial.argtypes = [vp, i32, C.POINTER(Expr), i64, vp]
     lib.mxb_reduce_finalize.argtypes = [vp, i32, i32, vp, i32, i64, i64, i32, C.POINTER(Out), C.POINTER(Out)]
     lib.mxb_reduce_partial_push.argtypes = [vp, i32, C.POINTER(Expr), i64, C.POINTER(Peers), i32, i32]

@@ -263,6 +263,13 @@ void aot_manifest(std::vector<ManifestItem> *items) {
       it.spec.U = (u == 1 || one_only) ? 1 : 2;
       if (!(u != 1 && one_only)) items->push_back(it);
     }
+  // find / find_idx of plain tensors: count pass, value scatter, index scatter (int and index_t outputs)
+  for (int d : {MXB_F32, MXB_F64, MXB_I32}) {
+    add(prog_identity(d), FAM_SELECT, -1, d, 0, d == MXB_F32);
+    add(prog_identity(d), FAM_SELECT, -1, d, 1, d == MXB_F32);
+    add(prog_identity(d), FAM_SELECT, -1, MXB_I32, 2, d == MXB_F32);
+    add(prog_identity(d), FAM_SELECT, -1, MXB_I64, 2, false);
+  }
   // permuted copies (bench/00_operators/operators.cu:40-59) and the row + column mix
   for (int d : {MXB_F32, MXB_F64, MXB_C64, MXB_BF16, MXB_I32}) add(prog_identity(d), FAM_EW_TR, -1, d, 0, false);
   add(prog_vector_add(MXB_F32), FAM_EW_TR, -1, MXB_F32, 0, false);

@@ -1882,6 +1882,125 @@ int mxb_cumsum(mxb_handle_t h, const mxb_expr_t *expr_in, const mxb_out_t *out) 
   return launch(h, k, grid, 256u, 0, p);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// find / find_idx: stream compaction in the flat (row-major) order of the expression
+// ---------------------------------------------------------------------------------------------------
+int mxb_find(mxb_handle_t h, const mxb_expr_t *expr_in, int select_op, double threshold, const mxb_out_t *out,
+             const mxb_out_t *count_out, int want_indices) {
+  if (!h) return fail(MXB_ERR_INVALID, "null handle");
+  if (!expr_in) return fail(MXB_ERR_INVALID, "null expression");
+  if (expr_in->rank >= 0 && expr_in->rank <= MXB_MAX_RANK && count_out && count_out->data && count_out->rank == 0 && count_out->dtype == MXB_I32) {
+    int64_t n0 = 1;
+    for (int d = 0; d < expr_in->rank; ++d) n0 *= expr_in->size[d];
+    if (n0 == 0) {   // reference: num_found() = 0 and nothing else (cub.h:2660-2663); an empty tensor may have a null pointer
+      MXB_CUDA(cudaSetDevice(h->device));
+      MXB_CUDA(cudaMemsetAsync(count_out->data, 0, sizeof(int), h->stream));
+      return MXB_OK;
+    }
+  }
+  int st = check_expr_shape(expr_in);
+  if (st != MXB_OK) return st;
+  if (select_op < 0 || select_op >= MXB_SEL_COUNT) return fail(MXB_ERR_INVALID, "unknown selection op");
+  if (!out || !out->data) return fail(MXB_ERR_INVALID, "null output");
+  if (out->rank != 1 || (out->size[0] > 1 && out->stride[0] != 1)) return fail(MXB_ERR_INVALID, "find output must be rank 1 and contiguous");
+  if (!count_out || !count_out->data) return fail(MXB_ERR_INVALID, "null count output");
+  if (count_out->rank != 0) return fail(MXB_ERR_INVALID, "num_found must be rank 0 (the reference static_asserts it)");
+  if (count_out->dtype != MXB_I32) return fail(MXB_ERR_INVALID, "num_found must be MXB_I32 (tensor_t<int, 0>)");
+  if (out->dtype < 0 || out->dtype >= MXB_DTYPE_COUNT) return fail(MXB_ERR_INVALID, "output dtype out of range");
+  if (want_indices && out->dtype != MXB_I32 && out->dtype != MXB_I64) return fail(MXB_ERR_INVALID, "find_idx output must be MXB_I32 or MXB_I64");
+  if (out->dtype == MXB_C64 || out->dtype == MXB_BF16 || out->dtype == MXB_F16) return fail(MXB_ERR_NOT_SUPPORTED, "find output dtype is not lowered");
+  MXB_CUDA(cudaSetDevice(h->device));
+
+  mxb_expr_t e;
+  std::string err;
+  st = canonicalize(expr_in, &e, &err);
+  if (st != MXB_OK) return fail(st, err);
+  ExprInfo info;
+  st = analyze_expr(&e, &info, &err);
+  if (st != MXB_OK) return fail(st, err);
+  if (!(info.value_dtype == MXB_F32 || info.value_dtype == MXB_F64 || info.value_dtype == MXB_I32 || info.value_dtype == MXB_I64 || info.value_dtype == MXB_U8))
+    return fail(MXB_ERR_NOT_SUPPORTED, "find / find_idx of this value type is not lowered (the reference orders real types only)");
+
+  // collapse neighbours only: the flat order of the selection is the row-major order of the expression's dims
+  Group g;
+  g.n = e.rank;
+  for (int d = 0; d < e.rank; ++d) {
+    g.size[d] = e.size[d];
+    for (int k = 0; k < e.n_leaves; ++k) g.ls[k][d] = e.leaves[k].stride[d];
+    g.os[d] = 0;
+    g.is[d] = 0;
+  }
+  int64_t N = 1;
+  for (int d = 0; d < e.rank; ++d) N *= e.size[d];
+  // size-1 dims carry no order information; broadcast (stride-0) dims do, so the generic collapse rule applies as is
+  collapse(g, e.n_leaves);
+  if (g.n > KMAXD) return fail(MXB_ERR_NOT_SUPPORTED, "view does not collapse to <= 4 dims");
+
+  const int nl = e.n_leaves;
+  int V = 1;
+  bool unit = nl > 0;
+  if (g.n == 1) {
+    const int vmax = policy_vmax(info);
+    bool ok = vmax > 1;
+    for (int k = 0; k < nl; ++k) {
+      const int64_t in = g.ls[k][0];
+      if (in != 1) unit = false;
+      if (in != 0 && in != 1) ok = false;
+      if (in == 1 && !aligned_to(e.leaves[k].data, (int64_t)vmax * dtype_bytes(e.leaves[k].dtype))) ok = false;
+    }
+    if (ok && unit) V = vmax;
+  } else {
+    unit = false;
+  }
+  if (env_int("MXB_TUNE_V", 0) == 1) V = 1;
+
+  const int64_t TILE = (int64_t)256 * V * 4;
+  const int64_t ntiles = (N + TILE - 1) / TILE;
+  st = ensure_ws(h, (size_t)ntiles * 12 + 64, 1);
+  if (st != MXB_OK) return st;
+
+  EwParams p;
+  memset(&p, 0, sizeof p);
+  p.nd = g.n;
+  p.N = N;
+  p.nleaf = nl;
+  p.all_unit = (unit && V > 1) ? 1 : 0;
+  for (int d = 0; d < g.n; ++d) {
+    p.sz[d] = g.size[d];
+    for (int k = 0; k < nl; ++k) p.leaf[k].bs[d] = g.ls[k][d];
+  }
+  for (int k = 0; k < nl; ++k) p.leaf[k].ptr = e.leaves[k].data;
+  p.out.ptr = out->data;
+  fill_consts(e, p.c);
+  p.sel_op = select_op;
+  p.sel_thr_d = threshold;
+  p.sel_thr_i = (int64_t)threshold;
+  p.sel_offsets = (unsigned long long *)h->ws;                       // 8-byte entries first (alignment)
+  p.sel_counts = (unsigned *)((char *)h->ws + (size_t)ntiles * 8);
+  p.sel_ticket = h->tickets;
+  p.sel_total = (int *)count_out->data;
+  p.sel_cap = out->size[0];
+
+  const unsigned grid = (unsigned)std::min<int64_t>(ntiles, (int64_t)h->sm_count * 8);
+  KernelSpec spec;
+  spec.family = FAM_SELECT;
+  spec.op = -1;
+  spec.V = V;
+  spec.U = 4;
+  Kernel k;
+  spec.team = 0;
+  spec.out_dtype = info.value_dtype;
+  st = get_kernel(info, spec, &k);
+  if (st != MXB_OK) return st;
+  st = launch(h, k, grid, 256, 0, p);
+  if (st != MXB_OK) return st;
+  spec.team = want_indices ? 2 : 1;
+  spec.out_dtype = out->dtype;
+  st = get_kernel(info, spec, &k);
+  if (st != MXB_OK) return st;
+  return launch(h, k, grid, 256, 0, p);
+}
+
 int mxb_is_aot(const mxb_expr_t *expr, int reduce_op_or_minus1) {
   if (!expr) return 0;
   mxb_expr_t e;
@@ -1934,7 +2053,7 @@ int mxb_debug_compile(const mxb_expr_t *expr, int family, int reduce_op, int out
   if (st != MXB_OK) return fail(st, err);
   KernelSpec spec;
   spec.family = family;
-  spec.op = (family == FAM_EW || family == FAM_EW_TR || family == FAM_SCAN || family == FAM_SM_GROUP || family == FAM_SM_REG) ? -1 : kernel_op(reduce_op);
+  spec.op = (family == FAM_EW || family == FAM_EW_TR || family == FAM_SCAN || family == FAM_SM_GROUP || family == FAM_SM_REG || family == FAM_SELECT) ? -1 : kernel_op(reduce_op);
   spec.out_dtype = out_dtype;
   spec.V = V > 0 ? V : policy_vmax(info);
   spec.U = policy_unroll(info, spec.V, family);

@@ -430,6 +430,7 @@ int policy_unroll(const ExprInfo &info, int V, int family) {
   if (family == FAM_RED_OUTER_TMA) return 1;
   if (family == FAM_VAR_REG || family == FAM_VAR_TMA || family == FAM_VAR_GROUP || family == FAM_SM_GROUP || family == FAM_SM_REG) return 1;
   if (family == FAM_EW_TR) return 1;
+  if (family == FAM_SELECT) return 4;
   if (family == FAM_VAR_SMEM) return bytes >= 32 ? 4 : 8;
   if (family == FAM_EW) return bytes >= 32 ? (info.nleaf <= 2 ? 2 : 1) : (info.nleaf <= 2 ? 4 : 2);
   return bytes >= 32 ? 2 : (info.nleaf <= 2 ? 4 : 2);
@@ -437,7 +438,7 @@ int policy_unroll(const ExprInfo &info, int V, int family) {
 
 std::string kernel_key(const ExprInfo &info, const KernelSpec &s) {
   std::ostringstream k;
-  static const char *fam[] = {"red_inner", "red_outer", "var_smem", "ew", "var_reg", "var_tma", "var_group", "softmax_group", "softmax_reg", "ew_tr", "scan", "red_outer_tma"};
+  static const char *fam[] = {"red_inner", "red_outer", "var_smem", "ew", "var_reg", "var_tma", "var_group", "softmax_group", "softmax_reg", "ew_tr", "scan", "red_outer_tma", "select"};
   k << fam[s.family] << "|" << info.name << "|" << (s.op >= 0 ? reduce_op_name(s.op) : "-") << "|" << dtype_name(s.out_dtype)
     << "|V" << s.V << "|U" << s.U << "|T" << s.team;
   return k.str();
@@ -540,6 +541,13 @@ int kernel_wrapper_src(const ExprInfo &info, const KernelSpec &s, const std::str
       if (s.V != 2 && s.V != 4 && s.V != 8) return fail("ew_tr moves 16-byte chunks of 2-, 4- or 8-byte elements");
       k << "extern \"C\" __global__ void __launch_bounds__(256) " << symbol
         << "(const __grid_constant__ mxb::EwParams p) { mxb::ew_tr_body<" << E << ", " << O << ", " << (16 / s.V) << ">(p); }\n";
+      break;
+    case FAM_SELECT:
+      // team = pass: 0 count (+ in-launch scan of the tile counts), 1 scatter values, 2 scatter flat indices
+      if (cplx || info.value_dtype == MXB_BF16 || info.value_dtype == MXB_F16) return fail("find / find_idx serve real value types");
+      if (s.team < 0 || s.team > 2) return fail("select pass out of range");
+      k << "extern \"C\" __global__ void __launch_bounds__(256) " << symbol
+        << "(const __grid_constant__ mxb::EwParams p) { mxb::select_body<" << E << ", " << O << ", " << s.V << ", " << s.team << ">(p); }\n";
       break;
     default: return fail("unknown kernel family");
   }

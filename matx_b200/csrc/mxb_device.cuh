@@ -143,6 +143,15 @@ struct EwParams {
   int tr_yvec;        // staged leaves may be read in aligned 16-byte chunks
   int tr_xvec;        // X-walking leaves may be read in aligned V-element vectors
   int tr_ovec;        // the output may be written in aligned V-element vectors
+  // select family (find / find_idx) only
+  int sel_op;                      // mxb_select_op_t: x < c, x > c, x == c, x != c, x <= c, x >= c
+  double sel_thr_d;                // the threshold c for floating value types ...
+  i64 sel_thr_i;                   // ... and for integer ones
+  u32 *sel_counts;                 // selected elements per tile (count pass)
+  unsigned long long *sel_offsets; // exclusive prefix of sel_counts (written by the count pass's last CTA)
+  u32 *sel_ticket;                 // self-resetting arrival counter of the count pass
+  int *sel_total;                  // num_found (clamped to INT_MAX like the reference's int count)
+  i64 sel_cap;                     // capacity of the output: elements beyond it are counted but not written
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -2901,6 +2910,193 @@ __device__ __forceinline__ void scan_inner_body(const RedParams &p) {
   } else {
     if (p.all_unit) scan_inner_body_impl<E, OutT, V, U, true>(p);
     else scan_inner_body_impl<E, OutT, V, U, false>(p);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// S1: select — stream compaction behind find / find_idx (reference: find_impl / find_idx_impl, transforms/cub.h:2609-2790,
+// cub::DeviceSelect::If over the row-major flattened operator with the functors LT / GT / EQ / NEQ / LTE / GTE,
+// :2521-2588).  Output order = flat index order (stable), count = number selected.  Two launches, no spinning:
+//   count pass    a tile = 256 threads x U chunks x V elements of the flat index space; the CTA counts its selected
+//                 elements (popc of the per-chunk flag masks, redux.sync add, shared memory) into sel_counts[tile];
+//                 the LAST CTA to finish (self-resetting ticket) turns the counts into exclusive offsets and writes
+//                 num_found;
+//   scatter pass  the same tiles are evaluated again; an element's position is offsets[tile] + (chunks before) +
+//                 (warps before in its chunk) + (lanes before in its warp: shuffle scan) + (flags before in its vector);
+//                 values (MODE 1) or flat indices (MODE 2) are stored there.
+// The input is read twice (the second read comes from L2 when it fits); CUB's single-pass decoupled look-back reads it
+// once — the tile-exchange machinery of `scan` is the route to that here.
+// ------------------------------------------------------------------------------------------------
+constexpr int SEL_NT = 256, SEL_U = 4;
+template <class T> __device__ __forceinline__ bool sel_test(T x, int op, T c) {
+  switch (op) {
+    case 0: return x < c;
+    case 1: return x > c;
+    case 2: return x == c;
+    case 3: return x != c;
+    case 4: return x <= c;
+    default: return x >= c;
+  }
+}
+template <class T> struct SelThr { static __device__ __forceinline__ T get(const EwParams &p) { return (T)p.sel_thr_d; } };
+template <> struct SelThr<int> { static __device__ __forceinline__ int get(const EwParams &p) { return (int)p.sel_thr_i; } };
+template <> struct SelThr<i64> { static __device__ __forceinline__ i64 get(const EwParams &p) { return p.sel_thr_i; } };
+template <> struct SelThr<unsigned char> { static __device__ __forceinline__ unsigned char get(const EwParams &p) { return (unsigned char)p.sel_thr_i; } };
+
+// flags (bit v = element v selected) and values of the V elements starting at flat index j0
+template <class E, int V>
+__device__ __forceinline__ u32 sel_eval(const EwParams &p, i64 j0, typename E::value_type thr, typename E::value_type *vals) {
+  typedef typename E::value_type T;
+  u32 flags = 0;
+  if (j0 >= p.N) return 0;
+  const int nd = p.nd;
+  if (nd == 1) {
+    const char *base[E::NL];
+    i64 inner[E::NL];
+#pragma unroll
+    for (int k = 0; k < E::NL; ++k) { base[k] = (const char *)p.leaf[k].ptr; inner[k] = p.leaf[k].bs[0]; }
+    if (V > 1 && j0 + V <= p.N && p.all_unit) {
+      typename E::template Regs<V> r;
+      E::template loadv<V, true>(r, base, inner, j0);
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        vals[v] = E::template eval<V>(r, v, p.c);
+        flags |= (u32)sel_test<T>(vals[v], p.sel_op, thr) << v;
+      }
+      return flags;
+    }
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      if (j0 + v < p.N) {
+        typename E::template Regs<1> r;
+        E::template loadv<1, false>(r, base, inner, j0 + v);
+        vals[v] = E::template eval<1>(r, 0, p.c);
+        flags |= (u32)sel_test<T>(vals[v], p.sel_op, thr) << v;
+      }
+    }
+    return flags;
+  }
+  // N-D view that does not collapse: one element at a time through the row-major decomposition (V == 1 by host rule)
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    if (j0 + v < p.N) {
+      i64 idx[KMAXD];
+      decomp(j0 + v, nd, p.sz, idx);
+      const char *base[E::NL];
+      i64 inner[E::NL];
+#pragma unroll
+      for (int k = 0; k < E::NL; ++k) {
+        i64 off = 0;
+#pragma unroll
+        for (int d = 0; d < KMAXD - 1; ++d) if (d < nd - 1) off += idx[d] * p.leaf[k].bs[d];
+        base[k] = (const char *)p.leaf[k].ptr + off * E::leaf_bytes(k);
+        inner[k] = p.leaf[k].bs[nd - 1];
+      }
+      typename E::template Regs<1> r;
+      E::template loadv<1, false>(r, base, inner, idx[nd - 1]);
+      vals[v] = E::template eval<1>(r, 0, p.c);
+      flags |= (u32)sel_test<T>(vals[v], p.sel_op, thr) << v;
+    }
+  }
+  return flags;
+}
+
+template <class E, class OutT, int V, int MODE>
+__device__ __forceinline__ void select_body(const EwParams &p) {
+  pdl_prologue();
+  typedef typename E::value_type T;
+  constexpr int NT = SEL_NT, U = SEL_U, NW = NT / 32;
+  __shared__ u32 s_w[U][NW];
+  __shared__ unsigned long long s_seg[NT];
+  __shared__ int s_last;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const i64 TILE = (i64)NT * V * U;
+  const i64 ntiles = (p.N + TILE - 1) / TILE;
+  const T thr = SelThr<T>::get(p);
+
+  for (i64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    u32 flags[U];
+    T vals[U][V];
+#pragma unroll
+    for (int u = 0; u < U; ++u) flags[u] = sel_eval<E, V>(p, tile * TILE + ((i64)u * NT + tid) * V, thr, vals[u]);
+    if (MODE == 0) {
+      u32 c = 0;
+#pragma unroll
+      for (int u = 0; u < U; ++u) c += (u32)__popc(flags[u]);
+      c = __reduce_add_sync(0xffffffffu, c);
+      if (lane == 0) s_w[0][warp] = c;
+      __syncthreads();
+      if (tid == 0) {
+        u32 t = 0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) t += s_w[0][w];
+        __stcg(p.sel_counts + tile, t);
+      }
+      __syncthreads();
+    } else {
+      u32 excl[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const u32 c = (u32)__popc(flags[u]);
+        u32 incl = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const u32 o = __shfl_up_sync(0xffffffffu, incl, d);
+          if (lane >= d) incl += o;
+        }
+        excl[u] = incl - c;
+        if (lane == 31) s_w[u][warp] = incl;
+      }
+      __syncthreads();
+      unsigned long long pos = __ldcg(p.sel_offsets + tile);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        u32 before = 0, chunk = 0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) { const u32 t = s_w[u][w]; chunk += t; if (w < warp) before += t; }
+        const i64 j0 = tile * TILE + ((i64)u * NT + tid) * V;
+        unsigned long long q = pos + before + excl[u];
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          if ((flags[u] >> v) & 1u) {
+            if ((i64)q < p.sel_cap) ((OutT *)p.out.ptr)[q] = MODE == 1 ? cvt<OutT>(vals[u][v]) : (OutT)(j0 + v);
+            ++q;
+          }
+        }
+        pos += chunk;
+      }
+      __syncthreads();   // s_w is reused by the next tile
+    }
+  }
+
+  if (MODE == 0) {
+    // grid stage: the last CTA to arrive scans the tile counts (fixed order) and publishes num_found
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+      const u32 t = atomicInc(p.sel_ticket, gridDim.x - 1);
+      s_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      const i64 seg = (ntiles + NT - 1) / NT, b0 = (i64)tid * seg, b1 = (b0 + seg < ntiles) ? (b0 + seg) : ntiles;
+      unsigned long long sum = 0;
+      for (i64 i = b0; i < b1; ++i) sum += __ldcg(p.sel_counts + i);
+      s_seg[tid] = sum;
+      __syncthreads();
+      unsigned long long run = 0;
+      for (int t = 0; t < tid; ++t) run += s_seg[t];
+      if (tid == NT - 1) {
+        const unsigned long long total = run + sum;
+        *p.sel_total = total > 0x7fffffffull ? 0x7fffffff : (int)total;
+      }
+      for (i64 i = b0; i < b1; ++i) {
+        const u32 c = __ldcg(p.sel_counts + i);
+        __stcg(p.sel_offsets + i, run);
+        run += c;
+      }
+    }
   }
 }
 

@@ -374,6 +374,39 @@ class CumsumExpr:
 def cumsum(a): return CumsumExpr(a)
 
 
+class _Select:
+    """Selection functors of find / find_idx (transforms/cub.h:2521-2588): LT{c}(x) = x < c, and so on."""
+    op = -1
+
+    def __init__(self, c):
+        self.c = c
+
+
+class LT(_Select): op = A.SEL_LT        # noqa: E701
+class GT(_Select): op = A.SEL_GT        # noqa: E701
+class EQ(_Select): op = A.SEL_EQ        # noqa: E701
+class NEQ(_Select): op = A.SEL_NEQ      # noqa: E701
+class LTE(_Select): op = A.SEL_LTE      # noqa: E701
+class GTE(_Select): op = A.SEL_GTE      # noqa: E701
+
+
+class FindExpr:
+    """find(a, sel) / find_idx(a, sel) (operators/find.h:40-110, find_idx.h:40-110 -> find_impl / find_idx_impl,
+    transforms/cub.h:2609-2625,2705-2721): `(mtie(out, num_found) = find(a, GT{0.5})).run(exec)`; `out` is rank 1,
+    `num_found` a rank-0 int tensor; elements are visited in flat row-major order."""
+
+    def __init__(self, a, sel: _Select, want_indices: bool):
+        if not isinstance(sel, _Select):
+            raise TypeError("find / find_idx take one of LT, GT, EQ, NEQ, LTE, GTE (a callable cannot cross the C ABI)")
+        self.a = _wrap(a, None)
+        self.sel = sel
+        self.want_indices = want_indices
+
+
+def find(a, sel): return FindExpr(a, sel, False)
+def find_idx(a, sel): return FindExpr(a, sel, True)
+
+
 class mtie:
     """mtie(values, indices) — multi-output LHS (core/tie.h:44-117)."""
 
@@ -489,6 +522,15 @@ class Set:
 
     def __init__(self, lhs, rhs):
         self.lhs = lhs
+        if isinstance(rhs, FindExpr):
+            if not isinstance(lhs, mtie) or len(lhs.outs) != 2:
+                raise TypeError("find / find_idx need mtie(out, num_found) on the left-hand side")
+            if len(lhs.outs[0].shape) != 1:
+                raise TypeError("find output must be rank 1")
+            if len(lhs.outs[1].shape) != 0:
+                raise TypeError("Num found output tensor rank must be 0")   # the reference's static_assert
+            self.rhs = rhs
+            return
         self.rhs = rhs if isinstance(rhs, (ReduceExpr, CumsumExpr)) else _wrap(rhs, lhs if isinstance(lhs, Op) else None)
         if isinstance(lhs, mtie):
             if not isinstance(self.rhs, ReduceExpr) or self.rhs.op not in (A.RED_ARGMAX, A.RED_ARGMIN):
@@ -504,7 +546,12 @@ class Set:
                 raise A.MatxB200Error(A.ERR_SIZE, "lhs shape %s does not match rhs shape %s" % (o.shape, shape))  # matxInvalidSize
 
     def run(self, ex: "CudaExecutor") -> None:
-        if isinstance(self.rhs, CumsumExpr):
+        if isinstance(self.rhs, FindExpr):
+            r = self.rhs
+            e = lower_elementwise(r.a)
+            out, cnt = _out_desc(self.lhs.outs[0]), _out_desc(self.lhs.outs[1])
+            A.check(A.lib.mxb_find(ex.handle, C.byref(e), r.sel.op, float(r.sel.c), C.byref(out), C.byref(cnt), 1 if r.want_indices else 0))
+        elif isinstance(self.rhs, CumsumExpr):
             e = lower_elementwise(self.rhs.a)
             out = _out_desc(self.lhs)
             A.check(A.lib.mxb_cumsum(ex.handle, C.byref(e), C.byref(out)))

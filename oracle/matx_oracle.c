@@ -523,3 +523,30 @@ int orc_cumsum(const mxb_expr_t *e, const mxb_out_t *out) {
   }
   return 0;
 }
+
+/* find / find_idx — find_impl / find_idx_impl(HostExecutor), transforms/cub.h:2656-2675,2752-2770: walk the operator in
+ * flat row-major order (cbegin .. cend), keep the elements the selection functor accepts (LT / GT / EQ / NEQ / LTE / GTE
+ * with the threshold in the VALUE type, :2521-2588) — or their flat index as static_cast<int> — and count them in an int.
+ * select_op follows mxb_select_op_t.  Elements beyond the output's capacity are counted but not stored. */
+int orc_find(const mxb_expr_t *e, int select_op, double threshold, const mxb_out_t *out, int32_t *count_out, int want_indices) {
+  static const int kOp[6] = {MXB_OP_LT, MXB_OP_GT, MXB_OP_EQ, MXB_OP_NE, MXB_OP_LE, MXB_OP_GE};
+  if (select_op < 0 || select_op > 5 || out->rank != 1) return 1;
+  int64_t N = 1;
+  for (int d = 0; d < e->rank; ++d) N *= e->size[d];
+  int64_t idx[MXB_MAX_RANK] = {0};
+  int32_t cnt = 0;
+  for (int64_t f = 0; f < N; ++f) {
+    unflatten(f, e->rank, e->size, idx);
+    val_t x = eval_expr(e, idx);
+    val_t c;
+    if (x.t == MXB_F32) c = mk_f((float)threshold);
+    else if (x.t == MXB_F64) c = mk_d(threshold);
+    else c = mk_i(x.t, (long long)threshold);
+    if (compare(kOp[select_op], x, c)) {
+      if (cnt < out->size[0]) store_val(out->data, out->dtype, cnt, want_indices ? mk_i(MXB_I64, f) : x);
+      ++cnt;
+    }
+  }
+  *count_out = cnt;
+  return 0;
+}

@@ -277,6 +277,39 @@ extern "C" int MREF_NAME(mref_binary_f32)(int mode, int opcode, const float *a, 
     }
   });
 }
+// test/00_operators/ReductionTests.cu:1615-1693 — (mtie(out, num_found) = find / find_idx(t, SEL{thresh})).run(exec)
+// on a (possibly strided) rank-1 or rank-2 fp32 view; sel: 0 LT, 1 GT, 2 EQ, 3 NEQ, 4 LTE, 5 GTE
+template <int RANK, class Ex> static void ref_find_rank(Ex &ex, int sel, float thr, float *in, const int64_t *shape, const int64_t *strides,
+                                                         void *out, int64_t cap, int *num_found, int want_idx) {
+  auto t = make_view<float, RANK>(in, shape, strides);
+  auto nf = make_tensor<int>(num_found, {});
+  auto run = [&](auto functor) {
+    if (want_idx) {
+      auto o = make_tensor<int>(reinterpret_cast<int *>(out), {cap});
+      (mtie(o, nf) = find_idx(t, functor)).run(ex);
+    } else {
+      auto o = make_tensor<float>(reinterpret_cast<float *>(out), {cap});
+      (mtie(o, nf) = find(t, functor)).run(ex);
+    }
+  };
+  switch (sel) {
+    case 0: run(LT<float>{thr}); break;
+    case 1: run(GT<float>{thr}); break;
+    case 2: run(EQ<float>{thr}); break;
+    case 3: run(NEQ<float>{thr}); break;
+    case 4: run(LTE<float>{thr}); break;
+    case 5: run(GTE<float>{thr}); break;
+    default: throw 1;
+  }
+}
+extern "C" int MREF_NAME(mref_find_f32)(int mode, int sel, float thr, int rank, const int64_t *shape, const int64_t *strides, float *in,
+                                        void *out, int64_t cap, int *num_found, int want_idx) {
+  return with_exec(mode, [&](auto &ex) {
+    if (rank == 1) ref_find_rank<1>(ex, sel, thr, in, shape, strides, out, cap, num_found, want_idx);
+    else if (rank == 2) ref_find_rank<2>(ex, sel, thr, in, shape, strides, out, cap, num_found, want_idx);
+    else throw 1;
+  });
+}
 extern "C" int MREF_NAME(mref_threads)(void) {
 #if defined(MATX_EN_OMP) && !defined(MREF_CUDA)
   return omp_get_num_procs();

@@ -234,6 +234,22 @@ static int run_checks() {
       (l1 = cumsum(lx)).run(ref); (l2 = cumsum(lx)).run(b200); ref.sync();
       report("cumsum(x) 2^20 in one row (tile exchange)", max_rel(l2, l1, 1 << 20) == 0 && !strncmp(b200.last_kernel(), "scan|", 5), b200.last_kernel());
     }
+    // find / find_idx: ReductionTests.cu:1615-1693 (values in [0, 2), GT 0.5) plus ties and a multi-tile input
+    {
+      const index_t nf_n = 100000;
+      auto fx = make_tensor<float>({nf_n});
+      for (index_t i = 0; i < nf_n; ++i) fx(i) = float((i * 7919) % 9) * 0.25f;
+      auto v1 = make_tensor<float>({nf_n}), v2 = make_tensor<float>({nf_n});
+      auto i1 = make_tensor<int>({nf_n}), i2 = make_tensor<int>({nf_n});
+      auto n1 = make_tensor<int>({}), n2 = make_tensor<int>({}), n3 = make_tensor<int>({}), n4 = make_tensor<int>({});
+      (mtie(v1, n1) = find(fx, GT<float>{0.5f})).run(ref); (mtie(v2, n2) = find(fx, GT<float>{0.5f})).run(b200); ref.sync();
+      const std::string kf = b200.last_kernel();
+      (mtie(i1, n3) = find_idx(fx, LTE<float>{1.0f})).run(ref); (mtie(i2, n4) = find_idx(fx, LTE<float>{1.0f})).run(b200); ref.sync();
+      bool ok = n1() == n2() && n3() == n4() && n1() > 0 && n3() > 0;
+      for (index_t i = 0; ok && i < n1(); ++i) ok = v1(i) == v2(i);
+      for (index_t i = 0; ok && i < n3(); ++i) ok = i1(i) == i2(i) && fx(i2(i)) <= 1.0f;
+      report("(mtie(out, num_found) = find / find_idx(x, SEL{c})) stream compaction", ok && !strncmp(kf.c_str(), "select|", 7) && !strncmp(b200.last_kernel(), "select|", 7), b200.last_kernel());
+    }
     // permuted copy: bench/00_operators/operators.cu:40-59, scaled down
     auto x = make_tensor<float>({50, 40, 6, 30});
     std::mt19937 g(23);
@@ -354,6 +370,16 @@ static void run_bench() {
     (lx = random<float>({n}, UNIFORM)).run(ref);
     line("cumsum fp32 2^28", "y = cumsum(x)", 2.0 * 4 * n, time_ms(stream, 5, [&] { (ly = cumsum(lx)).run(ref); }),
          time_ms(stream, 5, [&] { (ly = cumsum(lx)).run(b200); }));
+  }
+  {  // find: stream compaction of 2^28 fp32 at 1 % and 50 % selectivity
+    const index_t n = index_t(1) << 28;
+    auto fx = make_tensor<float>({n}, MATX_DEVICE_MEMORY), fo = make_tensor<float>({n}, MATX_DEVICE_MEMORY);
+    auto nf = make_tensor<int>({}, MATX_DEVICE_MEMORY);
+    (fx = random<float>({n}, UNIFORM)).run(ref);
+    line("find fp32 2^28 (1 % selected)", "mtie(out, n) = find(x, GT{0.99})", 4.0 * n * 1.01, time_ms(stream, 3, [&] { (mtie(fo, nf) = find(fx, GT<float>{0.99f})).run(ref); }),
+         time_ms(stream, 5, [&] { (mtie(fo, nf) = find(fx, GT<float>{0.99f})).run(b200); }));
+    line("find fp32 2^28 (50 % selected)", "mtie(out, n) = find(x, GT{0.5})", 4.0 * n * 1.5, time_ms(stream, 3, [&] { (mtie(fo, nf) = find(fx, GT<float>{0.5f})).run(ref); }),
+         time_ms(stream, 5, [&] { (mtie(fo, nf) = find(fx, GT<float>{0.5f})).run(b200); }));
   }
   {  // C5
     const index_t d = 1024;

@@ -48,6 +48,7 @@ class Oracle:
         lib.orc_reduce.argtypes = [C.c_int, C.POINTER(A.Expr), C.c_int, C.POINTER(A.Out), C.POINTER(A.Out), C.c_int, C.c_int]
         lib.orc_softmax.argtypes = [C.POINTER(A.Expr), C.c_int, C.POINTER(A.Out)]
         lib.orc_cumsum.argtypes = [C.POINTER(A.Expr), C.POINTER(A.Out)]
+        lib.orc_find.argtypes = [C.POINTER(A.Expr), C.c_int, C.c_double, C.POINTER(A.Out), C.POINTER(C.c_int32), C.c_int]
 
     def elementwise(self, rhs, out: np.ndarray, out_dtype: int | None = None) -> np.ndarray:
         rhs = mx._wrap(rhs, None)
@@ -58,6 +59,14 @@ class Oracle:
         o = mx._out_desc(lhs)
         assert self.lib.orc_elementwise(C.byref(e), C.byref(o)) == 0
         return out
+
+    def find(self, r: "mx.FindExpr", out: np.ndarray) -> int:
+        """Fills `out` (rank 1) and returns num_found."""
+        e = mx.lower_elementwise(r.a)
+        o = mx._out_desc(np_tensor(out))
+        n = C.c_int32(0)
+        assert self.lib.orc_find(C.byref(e), r.sel.op, float(r.sel.c), C.byref(o), C.byref(n), 1 if r.want_indices else 0) == 0
+        return int(n.value)
 
     def cumsum(self, r: "mx.CumsumExpr", out: np.ndarray, out_dtype: int | None = None) -> np.ndarray:
         e = mx.lower_elementwise(r.a)

@@ -132,6 +132,18 @@ def test_outer_tma_kernel_compiles_for_sm100a(npdt, dt, op):
     assert st == A.OK, (A.lib.mxb_last_error(), log.value.decode()[:2000])
 
 
+@pytest.mark.parametrize("team,out_dt", [(0, A.F32), (1, A.F32), (2, A.I32), (2, A.I64)])
+def test_select_kernels_compile_for_sm100a(team, out_dt):
+    """Family 12 (find / find_idx): count pass, value scatter, index scatter — of an expression operand, vector and scalar."""
+    a = np_tensor(np.zeros(64, np.float32))
+    e = mx.lower_elementwise(mx.sqrt(mx.abs(a)) * 2.0 - 1.0)
+    for V in (4, 1):
+        log = C.create_string_buffer(1 << 16)
+        st = A.lib.mxb_debug_compile(C.byref(e), 12, -1, out_dt, V, team, log, len(log))
+        assert st == A.OK, (A.lib.mxb_last_error(), log.value.decode()[:2000])
+    assert A.lib.mxb_find(None, C.byref(e), 0, 0.0, None, None, 0) == A.ERR_INVALID   # null handle: an error, not a crash
+
+
 def test_paired_fp32_body_compiles_for_sm100a():
     """Pure-fp32 programs get a second body on the packed fp32 instructions (FFMA2 / FMUL2 / FADD2): NVRTC must know
     the sm_100 intrinsics and the packed log / normcdf."""
