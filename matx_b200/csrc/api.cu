@@ -1956,7 +1956,8 @@ int mxb_find(mxb_handle_t h, const mxb_expr_t *expr_in, int select_op, double th
 
   const int64_t TILE = (int64_t)256 * V * 4;
   const int64_t ntiles = (N + TILE - 1) / TILE;
-  st = ensure_ws(h, (size_t)ntiles * 12 + 64, 1);
+  const unsigned grid = (unsigned)std::min<int64_t>(ntiles, (int64_t)h->sm_count * env_int("MXB_TUNE_SEL_CTAS", 8));
+  st = ensure_ws(h, (size_t)grid * 16 + 64, 1);
   if (st != MXB_OK) return st;
 
   EwParams p;
@@ -1975,13 +1976,12 @@ int mxb_find(mxb_handle_t h, const mxb_expr_t *expr_in, int select_op, double th
   p.sel_op = select_op;
   p.sel_thr_d = threshold;
   p.sel_thr_i = (int64_t)threshold;
-  p.sel_offsets = (unsigned long long *)h->ws;                       // 8-byte entries first (alignment)
-  p.sel_counts = (unsigned *)((char *)h->ws + (size_t)ntiles * 8);
+  p.sel_offsets = (unsigned long long *)h->ws;
+  p.sel_counts = (unsigned long long *)h->ws + grid;
   p.sel_ticket = h->tickets;
   p.sel_total = (int *)count_out->data;
   p.sel_cap = out->size[0];
 
-  const unsigned grid = (unsigned)std::min<int64_t>(ntiles, (int64_t)h->sm_count * 8);
   KernelSpec spec;
   spec.family = FAM_SELECT;
   spec.op = -1;

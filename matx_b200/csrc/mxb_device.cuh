@@ -147,7 +147,7 @@ struct EwParams {
   int sel_op;                      // mxb_select_op_t: x < c, x > c, x == c, x != c, x <= c, x >= c
   double sel_thr_d;                // the threshold c for floating value types ...
   i64 sel_thr_i;                   // ... and for integer ones
-  u32 *sel_counts;                 // selected elements per tile (count pass)
+  unsigned long long *sel_counts;  // selected elements per CTA (count pass; both passes give a CTA the same run of tiles)
   unsigned long long *sel_offsets; // exclusive prefix of sel_counts (written by the count pass's last CTA)
   u32 *sel_ticket;                 // self-resetting arrival counter of the count pass
   int *sel_total;                  // num_found (clamped to INT_MAX like the reference's int count)
@@ -2917,13 +2917,13 @@ __device__ __forceinline__ void scan_inner_body(const RedParams &p) {
 // S1: select — stream compaction behind find / find_idx (reference: find_impl / find_idx_impl, transforms/cub.h:2609-2790,
 // cub::DeviceSelect::If over the row-major flattened operator with the functors LT / GT / EQ / NEQ / LTE / GTE,
 // :2521-2588).  Output order = flat index order (stable), count = number selected.  Two launches, no spinning:
-//   count pass    a tile = 256 threads x U chunks x V elements of the flat index space; the CTA counts its selected
-//                 elements (popc of the per-chunk flag masks, redux.sync add, shared memory) into sel_counts[tile];
-//                 the LAST CTA to finish (self-resetting ticket) turns the counts into exclusive offsets and writes
-//                 num_found;
-//   scatter pass  the same tiles are evaluated again; an element's position is offsets[tile] + (chunks before) +
-//                 (warps before in its chunk) + (lanes before in its warp: shuffle scan) + (flags before in its vector);
-//                 values (MODE 1) or flat indices (MODE 2) are stored there.
+//   count pass    a tile = 256 threads x U chunks x V elements of the flat index space; CTA c owns a contiguous run of
+//                 tiles, its threads count their selected elements (popc of the flag masks) with no barrier in the loop,
+//                 one CTA total goes to sel_counts[c]; the LAST CTA to finish (self-resetting ticket) turns the totals
+//                 into exclusive offsets and writes num_found;
+//   scatter pass  CTA c walks the same tiles with a running output position that starts at offsets[c]; an element's
+//                 position is that + (chunks before in the tile) + (warps before in its chunk) + (lanes before in its
+//                 warp: shuffle scan) + (flags before in its vector); values (MODE 1) or flat indices (MODE 2) go there.
 // The input is read twice (the second read comes from L2 when it fits); CUB's single-pass decoupled look-back reads it
 // once — the tile-exchange machinery of `scan` is the route to that here.
 // ------------------------------------------------------------------------------------------------
@@ -3013,64 +3013,27 @@ __device__ __forceinline__ void select_body(const EwParams &p) {
   const i64 TILE = (i64)NT * V * U;
   const i64 ntiles = (p.N + TILE - 1) / TILE;
   const T thr = SelThr<T>::get(p);
-
-  for (i64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    u32 flags[U];
-    T vals[U][V];
-#pragma unroll
-    for (int u = 0; u < U; ++u) flags[u] = sel_eval<E, V>(p, tile * TILE + ((i64)u * NT + tid) * V, thr, vals[u]);
-    if (MODE == 0) {
-      u32 c = 0;
-#pragma unroll
-      for (int u = 0; u < U; ++u) c += (u32)__popc(flags[u]);
-      c = __reduce_add_sync(0xffffffffu, c);
-      if (lane == 0) s_w[0][warp] = c;
-      __syncthreads();
-      if (tid == 0) {
-        u32 t = 0;
-#pragma unroll
-        for (int w = 0; w < NW; ++w) t += s_w[0][w];
-        __stcg(p.sel_counts + tile, t);
-      }
-      __syncthreads();
-    } else {
-      u32 excl[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const u32 c = (u32)__popc(flags[u]);
-        u32 incl = c;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-          const u32 o = __shfl_up_sync(0xffffffffu, incl, d);
-          if (lane >= d) incl += o;
-        }
-        excl[u] = incl - c;
-        if (lane == 31) s_w[u][warp] = incl;
-      }
-      __syncthreads();
-      unsigned long long pos = __ldcg(p.sel_offsets + tile);
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        u32 before = 0, chunk = 0;
-#pragma unroll
-        for (int w = 0; w < NW; ++w) { const u32 t = s_w[u][w]; chunk += t; if (w < warp) before += t; }
-        const i64 j0 = tile * TILE + ((i64)u * NT + tid) * V;
-        unsigned long long q = pos + before + excl[u];
-#pragma unroll
-        for (int v = 0; v < V; ++v) {
-          if ((flags[u] >> v) & 1u) {
-            if ((i64)q < p.sel_cap) ((OutT *)p.out.ptr)[q] = MODE == 1 ? cvt<OutT>(vals[u][v]) : (OutT)(j0 + v);
-            ++q;
-          }
-        }
-        pos += chunk;
-      }
-      __syncthreads();   // s_w is reused by the next tile
-    }
-  }
+  // both passes give CTA c the SAME contiguous run of tiles, so only one total per CTA crosses the grid
+  const i64 tpc = (ntiles + gridDim.x - 1) / gridDim.x;
+  const i64 t0 = (i64)blockIdx.x * tpc, t1 = (t0 + tpc < ntiles) ? (t0 + tpc) : ntiles;
 
   if (MODE == 0) {
-    // grid stage: the last CTA to arrive scans the tile counts (fixed order) and publishes num_found
+    u32 c = 0;   // per thread: at most tpc * U * V elements
+    for (i64 tile = t0; tile < t1; ++tile) {
+      T vals[V];
+#pragma unroll
+      for (int u = 0; u < U; ++u) c += (u32)__popc(sel_eval<E, V>(p, tile * TILE + ((i64)u * NT + tid) * V, thr, vals));
+    }
+    c = __reduce_add_sync(0xffffffffu, c);
+    if (lane == 0) s_w[0][warp] = c;
+    __syncthreads();
+    if (tid == 0) {
+      unsigned long long t = 0;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) t += s_w[0][w];
+      __stcg(p.sel_counts + blockIdx.x, t);
+    }
+    // grid stage: the last CTA to arrive scans the per-CTA totals (fixed order) and publishes num_found
     __threadfence();
     __syncthreads();
     if (tid == 0) {
@@ -3080,7 +3043,8 @@ __device__ __forceinline__ void select_body(const EwParams &p) {
     __syncthreads();
     if (s_last) {
       __threadfence();
-      const i64 seg = (ntiles + NT - 1) / NT, b0 = (i64)tid * seg, b1 = (b0 + seg < ntiles) ? (b0 + seg) : ntiles;
+      const i64 G = gridDim.x;
+      const i64 seg = (G + NT - 1) / NT, b0 = (i64)tid * seg, b1 = (b0 + seg < G) ? (b0 + seg) : G;
       unsigned long long sum = 0;
       for (i64 i = b0; i < b1; ++i) sum += __ldcg(p.sel_counts + i);
       s_seg[tid] = sum;
@@ -3092,11 +3056,50 @@ __device__ __forceinline__ void select_body(const EwParams &p) {
         *p.sel_total = total > 0x7fffffffull ? 0x7fffffff : (int)total;
       }
       for (i64 i = b0; i < b1; ++i) {
-        const u32 c = __ldcg(p.sel_counts + i);
+        const unsigned long long c2 = __ldcg(p.sel_counts + i);
         __stcg(p.sel_offsets + i, run);
-        run += c;
+        run += c2;
       }
     }
+    return;
+  }
+
+  unsigned long long pos = __ldcg(p.sel_offsets + blockIdx.x);   // running output position of this CTA
+  for (i64 tile = t0; tile < t1; ++tile) {
+    u32 flags[U], excl[U];
+    T vals[U][V];
+#pragma unroll
+    for (int u = 0; u < U; ++u) flags[u] = sel_eval<E, V>(p, tile * TILE + ((i64)u * NT + tid) * V, thr, vals[u]);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const u32 c = (u32)__popc(flags[u]);
+      u32 incl = c;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const u32 o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += o;
+      }
+      excl[u] = incl - c;
+      if (lane == 31) s_w[u][warp] = incl;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      u32 before = 0, chunk = 0;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) { const u32 t = s_w[u][w]; chunk += t; if (w < warp) before += t; }
+      const i64 j0 = tile * TILE + ((i64)u * NT + tid) * V;
+      unsigned long long q = pos + before + excl[u];
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        if ((flags[u] >> v) & 1u) {
+          if ((i64)q < p.sel_cap) ((OutT *)p.out.ptr)[q] = MODE == 1 ? cvt<OutT>(vals[u][v]) : (OutT)(j0 + v);
+          ++q;
+        }
+      }
+      pos += chunk;
+    }
+    __syncthreads();   // s_w is reused by the next tile
   }
 }
 
