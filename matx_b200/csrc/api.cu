@@ -56,7 +56,12 @@ int cuda_fail(cudaError_t e, const char *what) {
   g_err = std::string(what) + ": " + cudaGetErrorString(e);
   return MXB_ERR_CUDA;
 }
-#define MXB_CUDA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_fail(e_, #call); } while (0)
+// MXB_PLAN_ONLY=1 (set before mxb_create): the host side runs as usual — view collapsing, kernel-family choice, launch
+// geometry — but no CUDA call is made and nothing is launched; mxb_last_kernel() reports the kernel key plus
+// grid / block / dynamic shared memory.  It exists so that the dispatch policy can be tested on a box without a GPU
+// (tests/test_dispatch_plan.py); it computes nothing and is not a fallback.
+bool g_plan = false;
+#define MXB_CUDA(call) do { if (!g_plan) { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_fail(e_, #call); } } while (0)
 
 int ensure_ws(mxb_context *h, size_t bytes, size_t tickets) {
   if (bytes > h->ws_bytes) {
@@ -204,6 +209,13 @@ int get_kernel(const ExprInfo &info, const KernelSpec &spec, Kernel *k) {
   k->fn = (flavor && *flavor) ? nullptr : lookup_aot(k->key);
   k->jit = false;
   if (k->fn) return MXB_OK;
+  if (g_plan) {   // plan only: prove that the instance can be generated, do not build or load it
+    std::string wrap, err;
+    const int st = kernel_wrapper_src(info, spec, kernel_symbol(k->key), &wrap, &err);
+    if (st != MXB_OK) return fail(st, err);
+    k->jit = true;
+    return MXB_OK;
+  }
   if (getenv("MXB_DISABLE_JIT")) return fail(MXB_ERR_JIT, "no ahead-of-time kernel for " + k->key + " and MXB_DISABLE_JIT is set");
   const std::string sym = kernel_symbol(k->key);
   std::string wrap, err;
@@ -219,6 +231,11 @@ int get_kernel(const ExprInfo &info, const KernelSpec &spec, Kernel *k) {
 template <class P>
 int launch(mxb_context *h, const Kernel &k, unsigned grid, unsigned block, unsigned smem, P &params) {
   if (grid == 0) return MXB_OK;
+  if (g_plan) {
+    h->launches++;
+    h->last_kernel = k.key + (k.jit ? "|jit" : "|aot") + "|grid=" + std::to_string(grid) + "|block=" + std::to_string(block) + "|smem=" + std::to_string(smem);
+    return MXB_OK;
+  }
   if (k.jit) {
     std::string err;
     int st = jit_launch(k.fn, grid, block, smem, (void *)h->stream, (void *)&params, &err);
@@ -486,7 +503,7 @@ int reduce_launch(mxb_context *h, int kop, const mxb_expr_t &e, const ExprInfo &
       if (st > 8) st = 8;
       // tile copies: tensor map over {vector dim in 8-byte elements, reduce rows, other batch dim}
       bool have_map = false;
-      EncodeTiledFn enc = want_mode == 0 ? nullptr : tensor_map_encoder();
+      EncodeTiledFn enc = (want_mode == 0 || g_plan) ? nullptr : tensor_map_encoder();
       if (enc && st >= 2) {
         const int64_t Bo = other >= 0 ? gb.size[other] : 1;
         const cuuint64_t gdim[3] = {(cuuint64_t)(C * esz / 8), (cuuint64_t)R, (cuuint64_t)Bo};
@@ -500,6 +517,7 @@ int reduce_launch(mxb_context *h, int kop, const mxb_expr_t &e, const ExprInfo &
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
           have_map = true;
       }
+      if (g_plan && want_mode != 0 && st >= 2) have_map = true;   // plan only: assume the driver encodes the map, as on the B200 box
       const bool contiguous_strips = pitch == C * esz && cv <= ot_tx;   // one bulk copy per stage
       if (st >= 2 && (have_map ? want_mode != 0 : (contiguous_strips || want_mode == 0))) {
         spec.family = FAM_RED_OUTER_TMA;
@@ -1115,6 +1133,13 @@ int mxb_device_count(void) {
 int mxb_create(mxb_handle_t *out_handle, void *stream) {
   if (!out_handle) return fail(MXB_ERR_INVALID, "null handle pointer");
   *out_handle = nullptr;
+  if (env_int("MXB_PLAN_ONLY", 0)) {
+    g_plan = true;
+    mxb_context *hp = new mxb_context();   // B200 figures: 148 SMs, 227 KB of opt-in shared memory per CTA
+    hp->device = -1;
+    *out_handle = hp;
+    return MXB_OK;
+  }
   if (mxb_device_count() <= 0) return fail(MXB_ERR_NO_DEVICE, "no CUDA device visible: this library has no CPU fallback");
   mxb_context *h = new mxb_context();
   cudaError_t e = cudaGetDevice(&h->device);
@@ -1136,7 +1161,7 @@ int mxb_create(mxb_handle_t *out_handle, void *stream) {
 
 int mxb_destroy(mxb_handle_t h) {
   if (!h) return MXB_OK;
-  cudaSetDevice(h->device);
+  if (h->device >= 0) cudaSetDevice(h->device);
   if (h->ws) cudaFreeAsync(h->ws, h->stream);
   if (h->tickets) cudaFreeAsync(h->tickets, h->stream);
   if (h->tmp) cudaFreeAsync(h->tmp, h->stream);
