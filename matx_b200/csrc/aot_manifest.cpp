@@ -270,6 +270,10 @@ void aot_manifest(std::vector<ManifestItem> *items) {
     add(prog_identity(d), FAM_SELECT, -1, MXB_I32, 2, d == MXB_F32);
     add(prog_identity(d), FAM_SELECT, -1, MXB_I64, 2, false);
   }
+  // opt-in fast instances (MXB_SEL_FAST=1): branch-free predicate, 1-D unit-stride operands only
+  add(prog_identity(MXB_F32), FAM_SELECT, -1, MXB_F32, 3, false);
+  add(prog_identity(MXB_F32), FAM_SELECT, -1, MXB_F32, 4, false);
+  add(prog_identity(MXB_F32), FAM_SELECT, -1, MXB_I32, 5, false);
   // permuted copies (bench/00_operators/operators.cu:40-59) and the row + column mix
   for (int d : {MXB_F32, MXB_F64, MXB_C64, MXB_BF16, MXB_I32}) add(prog_identity(d), FAM_EW_TR, -1, d, 0, false);
   add(prog_vector_add(MXB_F32), FAM_EW_TR, -1, MXB_F32, 0, false);

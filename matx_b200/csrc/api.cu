@@ -2013,13 +2013,16 @@ int mxb_find(mxb_handle_t h, const mxb_expr_t *expr_in, int select_op, double th
   spec.V = V;
   spec.U = 4;
   Kernel k;
-  spec.team = 0;
+  // MXB_SEL_FAST=1 (opt-in, not yet measured): branch-free predicate and no N-D code in the kernels of a 1-D
+  // unit-stride operand — the first of the two fixes DESIGN.md section 4 `select` names
+  const int fast = (env_int("MXB_SEL_FAST", 0) && g.n == 1 && V > 1 && p.all_unit) ? 3 : 0;
+  spec.team = fast + 0;
   spec.out_dtype = info.value_dtype;
   st = get_kernel(info, spec, &k);
   if (st != MXB_OK) return st;
   st = launch(h, k, grid, 256, 0, p);
   if (st != MXB_OK) return st;
-  spec.team = want_indices ? 2 : 1;
+  spec.team = fast + (want_indices ? 2 : 1);
   spec.out_dtype = out->dtype;
   st = get_kernel(info, spec, &k);
   if (st != MXB_OK) return st;

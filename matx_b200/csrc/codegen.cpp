@@ -543,9 +543,10 @@ int kernel_wrapper_src(const ExprInfo &info, const KernelSpec &s, const std::str
         << "(const __grid_constant__ mxb::EwParams p) { mxb::ew_tr_body<" << E << ", " << O << ", " << (16 / s.V) << ">(p); }\n";
       break;
     case FAM_SELECT:
-      // team = pass: 0 count (+ in-launch scan of the tile counts), 1 scatter values, 2 scatter flat indices
+      // team = pass: 0 count (+ in-launch scan of the CTA totals), 1 scatter values, 2 scatter flat indices; +3 = the
+      // opt-in fast instances for 1-D unit-stride operands (MXB_SEL_FAST=1)
       if (cplx || info.value_dtype == MXB_BF16 || info.value_dtype == MXB_F16) return fail("find / find_idx serve real value types");
-      if (s.team < 0 || s.team > 2) return fail("select pass out of range");
+      if (s.team < 0 || s.team > 5) return fail("select pass out of range");   // 3..5: the opt-in fast instances
       k << "extern \"C\" __global__ void __launch_bounds__(256) " << symbol
         << "(const __grid_constant__ mxb::EwParams p) { mxb::select_body<" << E << ", " << O << ", " << s.V << ", " << s.team << ">(p); }\n";
       break;

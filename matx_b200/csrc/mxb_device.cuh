@@ -2938,6 +2938,13 @@ template <class T> __device__ __forceinline__ bool sel_test(T x, int op, T c) {
     default: return x >= c;
   }
 }
+// branch-free form for the opt-in fast instances: category of x against c (less / greater / equal / unordered) indexes
+// a 4-bit acceptance mask (LT 0001, GT 0010, EQ 0100, NEQ 1011, LTE 0101, GTE 0110)
+__device__ __forceinline__ u32 sel_mask(int op) { return (0x65B421u >> (4 * op)) & 0xFu; }
+template <class T> __device__ __forceinline__ u32 sel_flag(T x, T c, u32 mask) {
+  const u32 cat = x < c ? 0u : (x > c ? 1u : (x == c ? 2u : 3u));
+  return (mask >> cat) & 1u;
+}
 template <class T> struct SelThr { static __device__ __forceinline__ T get(const EwParams &p) { return (T)p.sel_thr_d; } };
 template <> struct SelThr<int> { static __device__ __forceinline__ int get(const EwParams &p) { return (int)p.sel_thr_i; } };
 template <> struct SelThr<i64> { static __device__ __forceinline__ i64 get(const EwParams &p) { return p.sel_thr_i; } };
@@ -3001,8 +3008,38 @@ __device__ __forceinline__ u32 sel_eval(const EwParams &p, i64 j0, typename E::v
   return flags;
 }
 
-template <class E, class OutT, int V, int MODE>
+// 1-D unit-stride operands only (host rule for the fast instances): no N-D decomposition, no per-element switch
+template <class E, int V>
+__device__ __forceinline__ u32 sel_eval_fast(const EwParams &p, const char *const *base, const i64 *inner, i64 j0, typename E::value_type thr,
+                                             u32 mask, typename E::value_type *vals) {
+  typedef typename E::value_type T;
+  u32 flags = 0;
+  if (j0 + V <= p.N) {
+    typename E::template Regs<V> r;
+    E::template loadv<V, true>(r, base, inner, j0);
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      vals[v] = E::template eval<V>(r, v, p.c);
+      flags |= sel_flag<T>(vals[v], thr, mask) << v;
+    }
+  } else {
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      if (j0 + v < p.N) {
+        typename E::template Regs<1> r;
+        E::template loadv<1, false>(r, base, inner, j0 + v);
+        vals[v] = E::template eval<1>(r, 0, p.c);
+        flags |= sel_flag<T>(vals[v], thr, mask) << v;
+      }
+    }
+  }
+  return flags;
+}
+
+template <class E, class OutT, int V, int MODE_IN>
 __device__ __forceinline__ void select_body(const EwParams &p) {
+  constexpr bool FAST = MODE_IN >= 3;       // opt-in instances (MXB_SEL_FAST=1): modes 3 / 4 / 5 = fast count / values / indices
+  constexpr int MODE = MODE_IN % 3;
   pdl_prologue();
   typedef typename E::value_type T;
   constexpr int NT = SEL_NT, U = SEL_U, NW = NT / 32;
@@ -3016,13 +3053,21 @@ __device__ __forceinline__ void select_body(const EwParams &p) {
   // both passes give CTA c the SAME contiguous run of tiles, so only one total per CTA crosses the grid
   const i64 tpc = (ntiles + gridDim.x - 1) / gridDim.x;
   const i64 t0 = (i64)blockIdx.x * tpc, t1 = (t0 + tpc < ntiles) ? (t0 + tpc) : ntiles;
+  const char *fbase[E::NL];
+  i64 finner[E::NL];
+#pragma unroll
+  for (int k = 0; k < E::NL; ++k) { fbase[k] = (const char *)p.leaf[k].ptr; finner[k] = p.leaf[k].bs[0]; }
+  const u32 fmask = sel_mask(p.sel_op);
 
   if (MODE == 0) {
     u32 c = 0;   // per thread: at most tpc * U * V elements
     for (i64 tile = t0; tile < t1; ++tile) {
       T vals[V];
 #pragma unroll
-      for (int u = 0; u < U; ++u) c += (u32)__popc(sel_eval<E, V>(p, tile * TILE + ((i64)u * NT + tid) * V, thr, vals));
+      for (int u = 0; u < U; ++u) {
+        const i64 j0 = tile * TILE + ((i64)u * NT + tid) * V;
+        c += (u32)__popc(FAST ? sel_eval_fast<E, V>(p, fbase, finner, j0, thr, fmask, vals) : sel_eval<E, V>(p, j0, thr, vals));
+      }
     }
     c = __reduce_add_sync(0xffffffffu, c);
     if (lane == 0) s_w[0][warp] = c;
@@ -3069,7 +3114,10 @@ __device__ __forceinline__ void select_body(const EwParams &p) {
     u32 flags[U], excl[U];
     T vals[U][V];
 #pragma unroll
-    for (int u = 0; u < U; ++u) flags[u] = sel_eval<E, V>(p, tile * TILE + ((i64)u * NT + tid) * V, thr, vals[u]);
+    for (int u = 0; u < U; ++u) {
+      const i64 j0 = tile * TILE + ((i64)u * NT + tid) * V;
+      flags[u] = FAST ? sel_eval_fast<E, V>(p, fbase, finner, j0, thr, fmask, vals[u]) : sel_eval<E, V>(p, j0, thr, vals[u]);
+    }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const u32 c = (u32)__popc(flags[u]);

@@ -127,6 +127,21 @@ def test_error_convention():
     assert ei.value.status == A.ERR_NOT_SUPPORTED
 
 
+@pytest.mark.skipif(__import__("os").environ.get("MXB_TEST_OPT_IN") != "1", reason="opt-in instances (MXB_SEL_FAST=1), not yet validated on a GPU")
+@pytest.mark.parametrize("sel", range(6))
+def test_fast_instances_opt_in(oracle, monkeypatch, sel):
+    monkeypatch.setenv("MXB_SEL_FAST", "1")
+    rng = np.random.default_rng(300 + sel)
+    for n in (1, 4097, (1 << 20) + 3):
+        x = (rng.integers(0, 9, n) * 0.25).astype(np.float32)
+        x[:: 7] = np.nan if sel == 3 else x[:: 7]          # NEQ accepts NaN, the ordered comparisons reject it
+        for want_idx in (False, True):
+            res = run_find(oracle, lambda t: t, x, SEL[sel](1.0), want_idx)
+            got, n_got, want, wn, k = res
+            assert n_got == wn and np.array_equal(got[:wn], want[:wn], equal_nan=True), k
+            assert "|T%d|" % (5 if want_idx else 4) in k, k
+
+
 def test_full_size_against_masked_select():
     import torch
     ex = mx.CudaExecutor()
