@@ -65,4 +65,13 @@ plan("scan.rows", np_tensor(empty((16384, 4096), f32)), mx.cumsum(a))
 plan("find.values", (np_tensor(empty(1 << 28, f32)), np_tensor(empty((), np.int32))), mx.find(v, mx.GT(0.5)))
 plan("find.strided_idx", (np_tensor(empty(1 << 20, np.int32)), np_tensor(empty((), np.int32))),
      mx.find_idx(np_tensor(empty((2048, 1024), f32)[:, ::2]), mx.LT(0.5)))
+# eligibility edges of the TMA-tiled reduce_outer
+narrow = np_tensor(empty((300, 64, 36), f32))
+plan("tma.narrow_rows", np_tensor(empty((36, 300), f32)), mx.max(mx.permute(narrow, [2, 0, 1]), [2]))          # 9 chunks per row
+shortr = np_tensor(empty((400, 32, 512), f32))
+plan("tma.short_reduce_dim", np_tensor(empty((512, 400), f32)), mx.max(mx.permute(shortr, [2, 0, 1]), [2]))   # R = 32 < 64
+m2 = np_tensor(empty((4096, 65536), f32))
+plan("tma.fused_expression", np_tensor(empty(65536, f32)), mx.sum(m * m2, [0]))                              # two leaves
+odd = np_tensor(empty((4096, 65536 + 4), f32)[:, 1:65533])                                                   # rows start 4 bytes off
+plan("tma.unaligned", np_tensor(empty(65532, f32)), mx.sum(odd, [0]))
 print(json.dumps(res))

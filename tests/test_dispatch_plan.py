@@ -62,6 +62,15 @@ def test_strided_reduce_dims_take_the_tma_tiles(plans):
     assert plans["colsum.tall"].startswith("red_outer|")          # 1000 columns: too few strips for the ring -> LDG walker with split R
 
 
+def test_tma_eligibility_edges(plans):
+    assert plans["tma.narrow_rows"].startswith("red_outer|"), plans["tma.narrow_rows"]            # < 32 chunks per row: LDG walker
+    assert plans["tma.short_reduce_dim"].startswith("red_outer|"), plans["tma.short_reduce_dim"]  # fewer than 64 reduce rows
+    k = plans["tma.fused_expression"]
+    assert k.startswith("red_outer|") and "|V4|" in k, k                                          # expressions keep the LDG walker
+    k = plans["tma.unaligned"]
+    assert not k.startswith("red_outer_tma") and "|V1|" in k, k                                   # no 16-byte alignment: scalar walk
+
+
 def test_elementwise_scan_and_select_families(plans):
     assert plans["ew.vector_add"].startswith("ew|") and plans["ew.vector_add"].split("|grid")[0].endswith("aot")
     assert plans["ew_tr.permute"].startswith("ew_tr|")
