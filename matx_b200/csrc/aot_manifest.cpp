@@ -209,6 +209,9 @@ void aot_manifest(std::vector<ManifestItem> *items) {
     for (int d : {MXB_F32, MXB_C64, MXB_BF16}) add(prog_identity(d), FAM_VAR_TMA, MXB_RED_VAR, MXB_F32, ipt, false);
     add(prog_identity(MXB_F64), FAM_VAR_TMA, MXB_RED_VAR, MXB_F64, ipt, false);
   }
+  // opt-in twin of var_tma (MXB_VAR_TMA2=1): producer warp + two consumer teams
+  for (int ipt : {4, 8, 16})
+    for (int d : {MXB_F32, MXB_C64}) add(prog_identity(d), FAM_VAR_TMA2, MXB_RED_VAR, MXB_F32, ipt, false);
   for (int ipt : {1, 2, 4, 8}) {
     for (int d : {MXB_F32, MXB_C64}) add(prog_identity(d), FAM_VAR_GROUP, MXB_RED_VAR, MXB_F32, ipt, false);
     for (int d : {MXB_F32, MXB_C64}) add(prog_identity(d), FAM_VAR_REG, MXB_RED_VAR, MXB_F32, ipt, false);

@@ -430,6 +430,16 @@ int reduce_launch(mxb_context *h, int kop, const mxb_expr_t &e, const ExprInfo &
         spec.V = policy_vmax(info);
         var_ipt = (int)stages;
         tma_ctas = (int)ctas;
+        // opt-in (MXB_VAR_TMA2=1, not yet measured): producer warp + two consumer teams of 256 threads, one CTA per SM,
+        // rows of at most 256 x 16 vectors
+        if (env_int("MXB_VAR_TMA2", 0) && rowbytes / 16 <= 256 * 16) {
+          const int64_t st2 = std::min<int64_t>(4, ((int64_t)h->max_smem_optin - 1024 - 128) / rowstride);
+          if (st2 >= 2) {
+            spec.family = FAM_VAR_TMA2;
+            var_ipt = (int)st2;
+            tma_ctas = 1;
+          }
+        }
       }
     }
   } else if (vmax > 1 && inner_ok(vmax)) {
@@ -545,6 +555,13 @@ int reduce_launch(mxb_context *h, int kop, const mxb_expr_t &e, const ExprInfo &
     if (ipt > 8) { tma_block = 1024; ipt = 8; }
     spec.team = ipt;
   }
+  if (spec.family == FAM_VAR_TMA2) {
+    const int64_t Rv16 = gr.size[0] * dtype_bytes(e.leaves[0].dtype) / 16;
+    int ipt = 1;
+    while ((int64_t)ipt * 256 < Rv16) ipt <<= 1;
+    spec.team = ipt;
+    tma_block = 2 * 256 + 32;   // two consumer teams + the producer warp
+  }
   if (tune_u > 0 && spec.family != FAM_VAR_REG) spec.U = tune_u;
 
   RedParams p;
@@ -610,7 +627,7 @@ int reduce_launch(mxb_context *h, int kop, const mxb_expr_t &e, const ExprInfo &
   const int sm = h->sm_count;
   unsigned grid = 1, block = tune_block > 0 ? (unsigned)tune_block : 256u, smem = 0;
   // persistent grids: CTAs per SM x SM count (every CTA loops over its share of the rows / tiles)
-  if (spec.family == FAM_VAR_TMA) {
+  if (spec.family == FAM_VAR_TMA || spec.family == FAM_VAR_TMA2) {
     const int64_t rowstride = (R * dtype_bytes(e.leaves[0].dtype) + 127) & ~int64_t(127);
     p.splits = var_ipt;  // ring depth
     block = (unsigned)tma_block;

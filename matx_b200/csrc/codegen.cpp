@@ -428,6 +428,7 @@ int policy_unroll(const ExprInfo &info, int V, int family) {
   const int bytes = V * info.max_leaf_bytes;  // widest load of one step
   if (family == FAM_RED_OUTER) return 4;
   if (family == FAM_RED_OUTER_TMA) return 1;
+  if (family == FAM_VAR_TMA2) return 1;
   if (family == FAM_VAR_REG || family == FAM_VAR_TMA || family == FAM_VAR_GROUP || family == FAM_SM_GROUP || family == FAM_SM_REG) return 1;
   if (family == FAM_EW_TR) return 1;
   if (family == FAM_SELECT) return 4;
@@ -438,7 +439,7 @@ int policy_unroll(const ExprInfo &info, int V, int family) {
 
 std::string kernel_key(const ExprInfo &info, const KernelSpec &s) {
   std::ostringstream k;
-  static const char *fam[] = {"red_inner", "red_outer", "var_smem", "ew", "var_reg", "var_tma", "var_group", "softmax_group", "softmax_reg", "ew_tr", "scan", "red_outer_tma", "select"};
+  static const char *fam[] = {"red_inner", "red_outer", "var_smem", "ew", "var_reg", "var_tma", "var_group", "softmax_group", "softmax_reg", "ew_tr", "scan", "red_outer_tma", "select", "var_tma2"};
   k << fam[s.family] << "|" << info.name << "|" << (s.op >= 0 ? reduce_op_name(s.op) : "-") << "|" << dtype_name(s.out_dtype)
     << "|V" << s.V << "|U" << s.U << "|T" << s.team;
   return k.str();
@@ -524,6 +525,12 @@ int kernel_wrapper_src(const ExprInfo &info, const KernelSpec &s, const std::str
       if (!(info.value_dtype == MXB_F32 || info.value_dtype == MXB_F64 || cplx)) return fail("var of a non-floating expression");
       k << "extern \"C\" __global__ void __launch_bounds__(1024) " << symbol
         << "(const __grid_constant__ mxb::RedParams p) { mxb::var_inner_tma_body<" << dtype_ctype(info.leaf_dtype[0]) << ", " << O << ", " << s.team << ">(p); }\n";
+      break;
+    case FAM_VAR_TMA2:   // opt-in (MXB_VAR_TMA2=1): producer warp + two consumer teams, team = vectors per thread
+      if (info.nleaf != 1) return fail("var_tma2 serves plain tensors only");
+      if (!(info.value_dtype == MXB_F32 || info.value_dtype == MXB_F64 || cplx)) return fail("var of a non-floating expression");
+      k << "extern \"C\" __global__ void __launch_bounds__(544) " << symbol
+        << "(const __grid_constant__ mxb::RedParams p) { mxb::var_inner_tma2_body<" << dtype_ctype(info.leaf_dtype[0]) << ", " << O << ", " << s.team << ">(p); }\n";
       break;
     case FAM_EW:
       // team = minimum resident CTAs per SM asked of the compiler (0 = no cap): arithmetic-heavy programs trade a few

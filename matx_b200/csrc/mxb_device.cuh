@@ -1925,6 +1925,130 @@ __device__ __forceinline__ void var_inner_tma_body(const RedParams &p) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// K3t2: var_inner_tma2 (opt-in, MXB_VAR_TMA2=1) — var_inner_tma with the warp specialisation that made reduce_outer_tma
+// work: the LAST warp only feeds the ring (waits on a stage's `empty` mbarrier, arms `full`, one cp.async.bulk per row);
+// the other 16 warps are TWO teams of 256 threads that take alternate rows, each with its own named barrier and its own
+// double-buffered partials — while one team sits in a barrier of its row the other computes, and nobody waits for a
+// thread-0 re-arm.  A team copies its row share shared -> registers (IPT 16-byte vectors per thread), releases the
+// stage (one `empty` arrival per warp) and runs the reference's two passes from registers.  Same arithmetic, same
+// results as var_inner_tma.  Rows of at most 256 * IPT vectors (64 KB at IPT = 16).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_arrive_cta(u64 *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+template <class Tin, class OutT, int IPT>
+__device__ __forceinline__ void var_inner_tma2_body(const RedParams &p) {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  typedef typename Widen<Tin>::type T;
+  typedef typename AbsDev2<T>::real_t RT;
+  enum { V = 16 / (int)sizeof(Tin), TEAM = 256, NWT = TEAM / 32 };
+  extern __shared__ __align__(128) unsigned char s_dyn[];
+  __shared__ T s_sum[2][2][NWT];     // [team][row parity within the team][warp]
+  __shared__ RT s_sq[2][2][NWT];
+  u64 *full = (u64 *)s_dyn;          // first 128 bytes: full[0..7], empty[0..7]
+  u64 *empty = full + 8;
+  unsigned char *buf = s_dyn + 128;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int stages = p.splits;
+  const i64 R = p.R;
+  const u32 rowbytes = (u32)(R * (i64)sizeof(Tin));
+  const u32 rowstride = (rowbytes + 127u) & ~127u;
+  const i64 Rv = R / V;
+  const i64 nrows = p.B > (i64)blockIdx.x ? (p.B - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;   // rows of this CTA
+
+  auto row_off = [&](i64 b, const i64 *strides) -> i64 {
+    i64 bidx[KMAXD];
+    decomp(b, p.nb, p.bsz, bidx);
+    i64 off = 0;
+#pragma unroll
+    for (int d = 0; d < KMAXD; ++d) if (d < p.nb) off += bidx[d] * strides[d];
+    return off;
+  };
+
+  if (tid == 0) {
+    for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NWT); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (tid >= 2 * TEAM) {
+    // ---------------- producer warp ----------------
+    if (lane == 0) {
+      int s = 0;
+      u32 round = 0;
+      for (i64 k = 0; k < nrows; ++k) {
+        if (round > 0) mbar_wait(&empty[s], (round - 1u) & 1u);
+        const i64 b = (i64)blockIdx.x + k * gridDim.x;
+        mbar_expect_tx(&full[s], rowbytes);
+        bulk_g2s(buf + (size_t)s * rowstride, (const char *)p.leaf[0].ptr + row_off(b, p.leaf[0].bs) * (i64)sizeof(Tin), rowbytes, &full[s]);
+        if (++s == stages) { s = 0; ++round; }
+      }
+    }
+    return;
+  }
+
+  // ---------------- two consumer teams, alternate rows ----------------
+  const int team = tid / TEAM, tt = tid % TEAM, wt = tt >> 5;
+  const int bar_id = 1 + team;
+  int par = 0;
+  for (i64 k = team; k < nrows; k += 2) {
+    const int s = (int)(k % stages);
+    mbar_wait(&full[s], (u32)((k / stages) & 1));
+    const Vec<Tin, V> *x = (const Vec<Tin, V> *)(buf + (size_t)s * rowstride);
+    Vec<Tin, V> q[IPT];
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) {
+      const i64 j = tt + (i64)i * TEAM;
+      if (j < Rv) {
+        union { uint4 u; Vec<Tin, V> v; } ld;
+        ld.u = *(const uint4 *)(x + j);
+        q[i] = ld.v;
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive_cta(&empty[s]);   // this warp holds its share in registers: the stage may be refilled
+    // pass 1: mean
+    T acc = OpSum<T>::init();
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) {
+      if (tt + (i64)i * TEAM < Rv) {
+#pragma unroll
+        for (int v = 0; v < V; ++v) acc = acc + cvt<T>(q[i].v[v]);
+      }
+    }
+    acc = OpSum<T>::warp(acc);
+    if (lane == 0) s_sum[team][par][wt] = acc;
+    asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"((int)TEAM) : "memory");
+    T tot = OpSum<T>::init();
+#pragma unroll
+    for (int w = 0; w < NWT; ++w) tot = tot + s_sum[team][par][w];   // same order in every thread
+    const T mean = MeanDiv<T>::go(tot, R);
+    // pass 2: sum of |x - mean|^2 out of registers
+    RT sq = (RT)0;
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) {
+      if (tt + (i64)i * TEAM < Rv) {
+#pragma unroll
+        for (int v = 0; v < V; ++v) sq += AbsDev2<T>::go(cvt<T>(q[i].v[v]), mean);
+      }
+    }
+    sq = OpSum<RT>::warp(sq);
+    if (lane == 0) s_sq[team][par][wt] = sq;
+    asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"((int)TEAM) : "memory");
+    if (tt == 0) {
+      RT tsq = (RT)0;
+#pragma unroll
+      for (int w = 0; w < NWT; ++w) tsq += s_sq[team][par][w];
+      RT res = tsq / (RT)p.post_scale_d;
+      if (p.post_sqrt) res = f_sqrt(res);
+      const i64 b = (i64)blockIdx.x + k * gridDim.x;
+      ((OutT *)p.out.ptr)[row_off(b, p.out.bs)] = cvt<OutT>(res);
+    }
+    par ^= 1;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // K2t: reduce_outer_tma — reduce_outer (strided / permuted reduce dim, a batch dim is the unit-stride vector dim) for
 // a plain tensor with ONE collapsed reduce dim, tiles staged in shared memory by the TMA engine.  A CTA owns a strip
 // of TX 16-byte chunks of the vector dim (an "item" = one strip of one outer batch index) and walks the reduce index
