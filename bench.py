@@ -96,50 +96,76 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------------------------
 # reference arm: matx::HostExecutor<ThreadsMode::ALL> compiled from /root/reference (oracle/_ref), host cores only
 # --------------------------------------------------------------------------------------------------------------
-def cpu_reference_pass(ref, x, n: int):
-    """One pass = the three statements on the first n elements; returns seconds."""
-    import numpy as np
-    from matx_b200 import _abi as A
-    out = np.zeros((), np.float32)
-    idx = np.zeros((), np.int64)
-    t0 = time.perf_counter()
-    for op in (A.RED_SUM, A.RED_MAX, A.RED_ARGMAX):
-        rc = ref.reduce(op, x.ctypes.data, A.F32, [n], [1], [0], out.ctypes.data, idx.ctypes.data, 1, mode=1)
+RED_SUM, RED_MAX, RED_ARGMAX = 0, 4, 6   # mxb_reduce_op_t values the reference wrapper takes (include/matx_b200.h)
+REF_LIB = os.path.join(ROOT, "oracle", "_ref", "libmatx_ref_host.so")
+
+
+class _RefHost:
+    """oracle/_ref/libmatx_ref_host.so (oracle/ref_wrap.cu: unmodified MatX statements on matx::HostExecutor) through
+    ctypes.  Nothing of matx_b200 is imported here: the reference arm must not map libmatx_b200.so."""
+
+    def __init__(self):
+        import ctypes as C
+        if not os.path.exists(REF_LIB):
+            raise RuntimeError("oracle/_ref/libmatx_ref_host.so is missing (build it where /root/reference exists: `python oracle/build_ref.py`)")
+        self.C = C
+        self.lib = C.CDLL(REF_LIB)
+        self.f = self.lib.mref_reduce_dt0__host   # fp32 reductions
+        self.f.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_void_p, C.c_int,
+                           C.POINTER(C.c_int), C.c_void_p, C.c_void_p, C.c_int]
+        self.cores = int(self.lib.mref_threads_host())
+
+    def full_reduce(self, op: int, x, out, idx) -> None:
+        C = self.C
+        sh, st, dm = (C.c_int64 * 1)(x.size), (C.c_int64 * 1)(1), (C.c_int * 1)(0)
+        rc = self.f(1, op, 1, sh, st, C.c_void_p(x.ctypes.data), 1, dm, C.c_void_p(out.ctypes.data), C.c_void_p(idx.ctypes.data), 1)   # mode 1 = ThreadsMode::ALL
         if rc != 0:
             raise RuntimeError("reference statement failed (%d)" % rc)
-    return time.perf_counter() - t0
 
 
-def load_reference():
-    from tests import oracle_harness as H
-    ref = H.load_ref_host()
-    if ref is None:
-        raise RuntimeError("oracle/_ref/libmatx_ref_host.so is missing (build it here with `python oracle/build_ref.py`)")
-    f = ref.fn("mref_threads")
-    return ref, int(f())
+def cpu_reference_pass(ref: _RefHost, x):
+    """One step = the three statements over x; returns (seconds, results)."""
+    import numpy as np
+    outs = [np.zeros((), np.float32) for _ in range(3)]
+    idx = np.zeros((), np.int64)
+    t0 = time.perf_counter()
+    for op, o in zip((RED_SUM, RED_MAX, RED_ARGMAX), outs):
+        ref.full_reduce(op, x, o, idx)
+    return time.perf_counter() - t0, (float(outs[0]), float(outs[1]), float(outs[2]), int(idx))
+
+
+def host_input(n: int):
+    """The C2 tensor on the host: U[0,1) fp32, generated in parallel blocks (numpy's generator is single-threaded)."""
+    import numpy as np
+    from concurrent.futures import ThreadPoolExecutor
+    x = np.empty(n, np.float32)
+    blk = 1 << 24
+    def fill(i):
+        np.random.default_rng(4000 + i).random(out=x[i * blk:(i + 1) * blk], dtype=np.float32)
+    with ThreadPoolExecutor(max_workers=min(16, os.cpu_count() or 1)) as ex:
+        list(ex.map(fill, range((n + blk - 1) // blk)))
+    return x
 
 
 def run_reference(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import numpy as np
-    ref, cores = load_reference()
-    n = 1 << 28  # bounded sample of the workload: 1 GiB of the 4 GiB tensor
-    rng = np.random.default_rng(4)
-    x = rng.random(n, dtype=np.float32)
+    ref = _RefHost()
+    n = int(os.environ.get("MXB_BENCH_REF_ELEMS", N_ELEMS))   # the stated config: all 2^30 elements (test hook: fewer)
+    x = host_input(n)
     for _ in range(max(1, args.warmup)):
-        cpu_reference_pass(ref, x, n)
-    ts = [cpu_reference_pass(ref, x, n) for _ in range(args.steps)]
+        cpu_reference_pass(ref, x)
+    ts = [cpu_reference_pass(ref, x)[0] for _ in range(args.steps)]
     t = sum(ts) / len(ts)
     val = algorithmic_bytes(n) / t / 1e9
-    sample = "first 2^28 of the 2^30 fp32 elements, sum+max+argmax per step, HostExecutor<ThreadsMode::ALL>"
+    sample = "the whole workload: %d fp32 elements, sum+max+argmax per step, matx::HostExecutor<ThreadsMode::ALL>" % n
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "elements_per_sec": 3 * n / t,
-        "config": {"workload": "C2: full-tensor sum/max/argmax, fp32 2^30 elements (reference arm runs a 2^28 sample per step)"},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
+        "config": {"workload": "C2: full-tensor sum + max + argmax, fp32 2^30 elements" if n == N_ELEMS else "C2 on %d elements (test hook)" % n},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": ref.cores, "kind": "reference", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -167,9 +193,9 @@ def run_ours(args) -> None:
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # keep stdout to the ONE JSON line: NCCL's version banner goes to stderr
-        os.environ["NCCL_DEBUG"] = os.environ.get("MXB_NCCL_DEBUG", "WARN")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        # a pre-set NCCL_DEBUG (the driver's INFO, to count ranks) is respected; whatever NCCL prints to fd 1 lands on
+        # stderr through the dup2 above, so stdout still carries exactly the ONE JSON line
+        os.environ.setdefault("NCCL_DEBUG", "WARN")
         dist.init_process_group("nccl", device_id=dev)
 
     # N > 1: the step (3 partial kernels, one all-gather, 3 folds) is launch-latency sensitive (~75 us kernels at N = 8),
@@ -256,9 +282,13 @@ def run_ours(args) -> None:
     assert abs(o_sum.item() - tsum.item()) <= 1e-5 * tsum.item(), (o_sum.item(), tsum.item())
     assert o_max.item() == tmax.item() and o_amax.item() == tmax.item()
     gi = o_idx.item()
+    # lowest GLOBAL index: the owner of the winning index holds the max there and nothing equal before it in its slab;
+    # every rank whose slab lies wholly before the winner holds no equal value at all (checked on every rank)
     if start <= gi < start + count:
         assert x[gi - start].item() == tmax.item()
         assert not bool((x[:gi - start] == tmax).any().item()), "argmax is not the lowest index"
+    elif start + count <= gi:
+        assert not bool((x == tmax).any().item()), "rank %d holds the max before the reported global index %d" % (rank, gi)
 
     # ---- timed region: K steps, CUDA events on the launching stream, max over ranks ----
     l0 = ex.launch_count()
@@ -284,36 +314,52 @@ def run_ours(args) -> None:
     # ---- roofline of the dominant kernel (per-launch CUDA-event duration inside this process) ----
     peak, peak_src = measured_peak()
     per_kernel = {}
-    for name in OPS:
-        evs = []
-        for _ in range(10):
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    o_f = torch.zeros((), device=dev)
+    o_i = torch.zeros((), device=dev, dtype=torch.int64)
+    stmts = {
+        "sum": lambda: mx.make_tensor(o_sum).set(mx.sum(tx)).run(ex),
+        "max": lambda: mx.make_tensor(o_max).set(mx.max(tx)).run(ex),
+        "argmax": lambda: mx.mtie(mx.make_tensor(o_amax), mx.make_tensor(o_idx)).set(mx.argmax(tx)).run(ex),
+        # the other full-tensor reductions north_star names (this rank's slab; not part of the timed step)
+        "min": lambda: mx.make_tensor(o_f).set(mx.min(tx)).run(ex),
+        "argmin": lambda: mx.mtie(mx.make_tensor(o_f), mx.make_tensor(o_i)).set(mx.argmin(tx)).run(ex),
+        "any": lambda: mx.make_tensor(o_f).set(mx.any(tx)).run(ex),
+        "all": lambda: mx.make_tensor(o_f).set(mx.all(tx)).run(ex),
+        "mean": lambda: mx.make_tensor(o_f).set(mx.mean(tx)).run(ex),
+        "var": lambda: mx.make_tensor(o_f).set(mx.var(tx, None, 1)).run(ex),
+    }
+    for name, stmt in stmts.items():
+        for _ in range(2):
+            stmt()
+        bursts = []
+        for _ in range(3):   # three bursts of 10 back-to-back launches between two events (an event pair per launch would
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)   # also time the host lowering)
             a.record()
-            if name == "sum":
-                mx.make_tensor(o_sum).set(mx.sum(tx)).run(ex)
-            elif name == "max":
-                mx.make_tensor(o_max).set(mx.max(tx)).run(ex)
-            else:
-                mx.mtie(mx.make_tensor(o_amax), mx.make_tensor(o_idx)).set(mx.argmax(tx)).run(ex)
+            for _ in range(10):
+                stmt()
             b.record()
-            evs.append((a, b))
-        torch.cuda.synchronize()
-        ts = [a.elapsed_time(b) for a, b in evs]
-        per_kernel[name] = {"ms_avg": sum(ts) / len(ts), "ms_best": min(ts), "kernel": ex.last_kernel(),
-                            "GBps": (count * 4 + 16) / (sum(ts) / len(ts) * 1e-3) / 1e9}
+            torch.cuda.synchronize()
+            bursts.append(a.elapsed_time(b) / 10)
+        avg = sum(bursts) / len(bursts)
+        per_kernel[name] = {"ms_avg": avg, "ms_best": min(bursts), "kernel": ex.last_kernel(),
+                            "GBps": (count * 4 + 16) / (avg * 1e-3) / 1e9, "frac": (count * 4 + 16) / (avg * 1e-3) / 1e9 / peak,
+                            "in_timed_step": name in OPS}
     dom = per_kernel["sum"]
-    # DRAM traffic of the dominant kernel per launch, from the committed `ncu --set full` capture of the same kernel
-    # on the full 2^30-element input (only meaningful at N = 1, where the launch processes the same bytes)
-    traffic = None
+    # DRAM traffic of the dominant kernel per launch: dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the same
+    # kernel key on the full 2^30-element input, from this round's `ncu --set full` capture (profiles/ncu_traffic.json names
+    # the capture file; a bench number is never taken under the profiler).  Only meaningful at N = 1.
+    traffic, traffic_src = None, None
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-            tr = json.load(f).get(dom["kernel"].rsplit("|", 1)[0])
+            tj = json.load(f)
+        tr = tj.get(dom["kernel"].rsplit("|", 1)[0])
         if tr and world == 1:
             traffic = tr["dram_bytes_per_launch"]
+            traffic_src = tr.get("source", tj.get("_source"))
     except (OSError, ValueError):
         pass
     roofline = {"bound": "hbm", "achieved": dom["GBps"], "peak": peak, "unit": "GB/s", "frac": dom["GBps"] / peak,
-                "traffic": traffic, "algorithmic_bytes_per_launch": count * 4 + 16, "kernel": dom["kernel"], "peak_source": peak_src, "frac_of_nominal_8000": dom["GBps"] / 8000.0,
+                "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes_per_launch": count * 4 + 16, "kernel": dom["kernel"], "peak_source": peak_src, "frac_of_nominal_8000": dom["GBps"] / 8000.0,
                 "per_kernel": per_kernel}
 
     # ---- e2e: host buffers through the public API, H2D of the input + D2H of the results inside the timed region ----
@@ -341,7 +387,7 @@ def run_ours(args) -> None:
             torch.cuda.synchronize()
             return hres
 
-        e2e_steps = max(2, min(args.steps, 5))
+        e2e_steps = max(2, args.steps)
         e2e_step()
         barrier()
         t0 = time.perf_counter()
@@ -361,16 +407,16 @@ def run_ours(args) -> None:
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         try:
-            ref, cores = load_reference()
-            n = 1 << 28
-            hxs = np.random.default_rng(4).random(n, dtype=np.float32)
-            cpu_reference_pass(ref, hxs, n)
+            ref = _RefHost()
+            hxs = host_input(N_ELEMS)
+            cpu_reference_pass(ref, hxs)
             reps, t_acc = 0, 0.0
             while t_acc < 10.0 and reps < 50:
-                t_acc += cpu_reference_pass(ref, hxs, n)
+                t_acc += cpu_reference_pass(ref, hxs)[0]
                 reps += 1
-            cpu = {"value": algorithmic_bytes(n) / (t_acc / reps) / 1e9, "unit": UNIT, "cores": cores, "kind": "reference",
-                   "sample": "first 2^28 of the 2^30 elements, %d passes of sum+max+argmax, matx::HostExecutor<ThreadsMode::ALL>" % reps}
+            cpu = {"value": algorithmic_bytes(N_ELEMS) / (t_acc / reps) / 1e9, "unit": UNIT, "cores": ref.cores, "kind": "reference",
+                   "sample": "the whole workload (2^30 fp32 elements), %d passes of sum+max+argmax, matx::HostExecutor<ThreadsMode::ALL>" % reps}
+            del hxs
         except Exception as exc:  # the checker is optional for the GPU number; say why it is absent
             cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference", "sample": "unavailable: %s" % exc}
 
@@ -441,6 +487,8 @@ def run_ours(args) -> None:
         guard.cancel()
         if rank == 0:
             line["batched_sharded"] = batched
+            # the same numbers under a key of the contract's own objects (C1 / C3 / C4 / C5 at this N)
+            line["roofline"]["per_config"] = batched
 
     if rank == 0 and world == 1 and args.all_configs:
         del x, tx
@@ -472,7 +520,7 @@ def run_ours(args) -> None:
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-e2e", action="store_true")

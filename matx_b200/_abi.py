@@ -1,7 +1,9 @@
 """ctypes mirror of include/matx_b200.h and the loader of libmatx_b200.so.
 
-The library is the product: if it is missing or fails to load, importing this module raises — there is no
-Python / torch fallback for any compute entry point.
+The library is the product: if it is missing or fails to load, the first use of `lib` raises (and so does
+`matx_b200.ops`'s CudaExecutor) — there is no Python / torch fallback for any compute entry point.  The constants and
+struct mirrors above the loader are importable without the library (bench.py's reference arm uses them and must not
+map libmatx_b200.so into its process).
 """
 from __future__ import annotations
 
@@ -136,9 +138,23 @@ def _load() -> C.CDLL:
     return lib
 
 
-lib = _load()
+_lib = None
+
+
+def load() -> C.CDLL:
+    """dlopen libmatx_b200.so once; raises ImportError when it is missing."""
+    global _lib
+    if _lib is None:
+        _lib = _load()
+    return _lib
+
+
+def __getattr__(name: str):
+    if name == "lib":   # `A.lib` loads on first use
+        return load()
+    raise AttributeError("module %r has no attribute %r" % (__name__, name))
 
 
 def check(status: int) -> None:
     if status != OK:
-        raise MatxB200Error(status, (lib.mxb_last_error() or b"").decode())
+        raise MatxB200Error(status, (load().mxb_last_error() or b"").decode())

@@ -30,6 +30,11 @@ NVCC_FLAGS = [
 ]
 CXX_FLAGS = ["-std=c++17", "-O2", "-fPIC"]
 
+
+def _cuda_include() -> str:
+    """<cuda.h> for the host files that use driver TYPES (entry points are resolved at run time with dlsym)."""
+    return os.path.join(os.path.dirname(os.path.dirname(os.path.realpath(_nvcc()))), "include")
+
 HOST_SOURCES = ["codegen.cpp", "jit.cpp", "aot_manifest.cpp"]
 GEN_SOURCES = ["gen_main.cpp", "codegen.cpp", "aot_manifest.cpp"]
 ALL_INPUTS = ["mxb_device.cuh", "mxb_internal.h", "api.cu", "gen_main.cpp"] + HOST_SOURCES
@@ -83,7 +88,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     for s in HOST_SOURCES:
         o = os.path.join(OBJ, s.replace(".cpp", ".o"))
         objs.append(o)
-        jobs.append((["g++"] + CXX_FLAGS + ["-c", os.path.join(CSRC, s), "-o", o], o))
+        jobs.append((["g++"] + CXX_FLAGS + ["-I" + _cuda_include(), "-c", os.path.join(CSRC, s), "-o", o], o))
     o = os.path.join(OBJ, "device_src.o")
     objs.append(o)
     jobs.append((["g++"] + CXX_FLAGS + ["-c", os.path.join(GEN, "device_src.cpp"), "-o", o], o))

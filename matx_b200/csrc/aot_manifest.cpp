@@ -185,7 +185,32 @@ void aot_manifest(std::vector<ManifestItem> *items) {
       items->push_back(it);
     }
   };
+  // explicit vector width / loads in flight (the dispatcher's choices that differ from the shared policy)
+  auto add_vu = [&](const mxb_expr_t &e, int family, int op, int out_dtype, int team, int V, int U) {
+    ExprInfo info;
+    std::string err;
+    if (analyze_expr(&e, &info, &err) != MXB_OK) return;
+    ManifestItem it;
+    it.expr = e;
+    it.spec.family = family;
+    it.spec.op = op;
+    it.spec.out_dtype = out_dtype;
+    it.spec.V = V;
+    it.spec.U = U;
+    it.spec.team = team;
+    items->push_back(it);
+  };
   const int kAllOps[] = {MXB_RED_SUM, MXB_RED_PROD, MXB_RED_MAX, MXB_RED_MIN, MXB_RED_ARGMAX, MXB_RED_ARGMIN, MXB_RED_ANY, MXB_RED_ALL};
+  // CTA-per-item streaming of a single contiguous reduce run: 32-byte loads for the sums, four loads in flight for all
+  add_vu(prog_identity(MXB_F32), FAM_RED_INNER, MXB_RED_SUM, MXB_F32, 0, 8, 4);
+  add_vu(prog_identity(MXB_F32), FAM_RED_INNER, MXB_RED_PROD, MXB_F32, 0, 8, 4);
+  add_vu(prog_identity(MXB_I32), FAM_RED_INNER, MXB_RED_SUM, MXB_I32, 0, 8, 4);
+  for (int op : kAllOps) {
+    if (op != MXB_RED_PROD) add_vu(prog_identity(MXB_F64), FAM_RED_INNER, op, MXB_F64, 0, 4, 4);
+    if (op == MXB_RED_SUM || op == MXB_RED_ANY || op == MXB_RED_ALL) add_vu(prog_identity(MXB_C64), FAM_RED_INNER, op, MXB_C64, 0, 4, 4);
+  }
+  add_vu(prog_identity(MXB_C64), FAM_RED_INNER, MXB_RED_VAR, MXB_F32, 0, 4, 4);
+  for (int op : {MXB_RED_SUM, MXB_RED_MAX, MXB_RED_ARGMAX}) add_vu(prog_abs2(MXB_C64), FAM_RED_INNER, op, MXB_F32, 0, 4, 4);
   // identity programs: full / per-row reductions of plain tensors
   for (int d : {MXB_F32, MXB_F64, MXB_BF16, MXB_C64, MXB_I32}) {
     const mxb_expr_t e = prog_identity(d);
@@ -273,10 +298,12 @@ void aot_manifest(std::vector<ManifestItem> *items) {
     add(prog_identity(d), FAM_SELECT, -1, MXB_I32, 2, d == MXB_F32);
     add(prog_identity(d), FAM_SELECT, -1, MXB_I64, 2, false);
   }
-  // opt-in fast instances (MXB_SEL_FAST=1): branch-free predicate, 1-D unit-stride operands only
-  add(prog_identity(MXB_F32), FAM_SELECT, -1, MXB_F32, 3, false);
-  add(prog_identity(MXB_F32), FAM_SELECT, -1, MXB_F32, 4, false);
-  add(prog_identity(MXB_F32), FAM_SELECT, -1, MXB_I32, 5, false);
+  // single-pass look-back kernels: values, int / index_t flat indices
+  for (int d : {MXB_F32, MXB_F64, MXB_I32}) {
+    add(prog_identity(d), FAM_SELECT, -1, d, 3, d == MXB_F32);
+    add(prog_identity(d), FAM_SELECT, -1, MXB_I32, 4, d == MXB_F32);
+    add(prog_identity(d), FAM_SELECT, -1, MXB_I64, 4, false);
+  }
   // permuted copies (bench/00_operators/operators.cu:40-59) and the row + column mix
   for (int d : {MXB_F32, MXB_F64, MXB_C64, MXB_BF16, MXB_I32}) add(prog_identity(d), FAM_EW_TR, -1, d, 0, false);
   add(prog_vector_add(MXB_F32), FAM_EW_TR, -1, MXB_F32, 0, false);

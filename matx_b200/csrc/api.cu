@@ -42,9 +42,10 @@ struct mxb_context {
   size_t tmp_bytes = 0;
   std::string last_kernel;
   int64_t launches = 0;
-  void *scan_ws = nullptr;  // tile / group totals, epoch-coded flags, self-resetting counters of the scan family
-  size_t scan_ws_bytes = 0, scan_cap_tiles = 0, scan_cap_groups = 0;
-  unsigned scan_epoch = 0;
+  // single-pass select / look-back scan: tile status words + {epoch, exit ticket} (device-resident epoch: graph-replay safe)
+  void *lb_status = nullptr;
+  size_t lb_cap_tiles = 0;
+  unsigned *lb_ctl = nullptr;   // [0] epoch (starts at 1), [1] exit ticket
 };
 
 namespace {
@@ -88,6 +89,30 @@ int ensure_tmp(mxb_context *h, size_t bytes) {
     h->tmp_bytes = nb;
   }
   return MXB_OK;
+}
+
+// Published-total slots of the look-back kernels (single-pass select, TILES-mode scan) and their control words
+// {launch epoch, exit ticket}.  Two regions that never overlap: 8-byte slots {tag : 32-bit value} and 16-byte slots
+// {tag, 64-bit value}, so a stale VALUE can never sit where a later launch reads a tag.  Zeroed once: a zero slot belongs
+// to epoch 0, which no launch uses (the device-side epoch starts at 1 and skips 0 when it wraps).
+int ensure_lb(mxb_context *h, size_t slots) {
+  if (!h->lb_ctl) {
+    MXB_CUDA(cudaMallocAsync((void **)&h->lb_ctl, 64, h->stream));
+    MXB_CUDA(cudaMemsetAsync(h->lb_ctl, 0, 64, h->stream));
+    static const unsigned one = 1;
+    MXB_CUDA(cudaMemcpyAsync(h->lb_ctl, &one, sizeof one, cudaMemcpyHostToDevice, h->stream));
+  }
+  if (slots > h->lb_cap_tiles) {
+    if (h->lb_status) MXB_CUDA(cudaFreeAsync(h->lb_status, h->stream));
+    const size_t nt = std::max<size_t>(slots + slots / 4, 16384);
+    MXB_CUDA(cudaMallocAsync(&h->lb_status, nt * 24, h->stream));
+    MXB_CUDA(cudaMemsetAsync(h->lb_status, 0, nt * 24, h->stream));
+    h->lb_cap_tiles = nt;
+  }
+  return MXB_OK;
+}
+void *lb_region(mxb_context *h, int slot_bytes) {   // 8-byte slots first, 16-byte slots behind them
+  return slot_bytes == 8 ? h->lb_status : (void *)((char *)h->lb_status + h->lb_cap_tiles * 8);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -228,8 +253,10 @@ int get_kernel(const ExprInfo &info, const KernelSpec &spec, Kernel *k) {
   return MXB_OK;
 }
 
+// coop: cooperative launch — the runtime guarantees that every CTA of the grid is resident at once (or refuses the
+// launch), which the look-back kernels' tile waits rely on; such launches do not use programmatic dependent launch
 template <class P>
-int launch(mxb_context *h, const Kernel &k, unsigned grid, unsigned block, unsigned smem, P &params) {
+int launch(mxb_context *h, const Kernel &k, unsigned grid, unsigned block, unsigned smem, P &params, bool coop = false) {
   if (grid == 0) return MXB_OK;
   if (g_plan) {
     h->launches++;
@@ -238,13 +265,26 @@ int launch(mxb_context *h, const Kernel &k, unsigned grid, unsigned block, unsig
   }
   if (k.jit) {
     std::string err;
-    int st = jit_launch(k.fn, grid, block, smem, (void *)h->stream, (void *)&params, &err);
+    int st = jit_launch(k.fn, grid, block, smem, (void *)h->stream, (void *)&params, &err, !coop && env_int("MXB_PDL", 1) != 0, coop);
     if (st != MXB_OK) return fail(st, err);
   } else {
     // static + dynamic shared memory above 48 KB needs the opt-in; the kernels carry up to ~3 KB of static smem
     if (smem > 40 * 1024) MXB_CUDA(cudaFuncSetAttribute(k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     void *args[] = {(void *)&params};
-    if (env_int("MXB_PDL", 1)) {
+    if (coop) {
+      cudaLaunchConfig_t cfg;
+      memset(&cfg, 0, sizeof cfg);
+      cfg.gridDim = dim3(grid);
+      cfg.blockDim = dim3(block);
+      cfg.dynamicSmemBytes = smem;
+      cfg.stream = h->stream;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeCooperative;
+      attr[0].val.cooperative = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      MXB_CUDA(cudaLaunchKernelExC(&cfg, k.fn, args));
+    } else if (env_int("MXB_PDL", 1)) {
       // programmatic dependent launch: the kernel may be scheduled while its predecessor on the stream drains; every
       // kernel body starts with griddepcontrol.wait, so nothing is read or written before the predecessor has completed
       cudaLaunchConfig_t cfg;
@@ -266,6 +306,19 @@ int launch(mxb_context *h, const Kernel &k, unsigned grid, unsigned block, unsig
   h->launches++;
   h->last_kernel = k.key + (k.jit ? "|jit" : "|aot");
   return MXB_OK;
+}
+
+// CTAs of `k` that fit on one SM at once (launch-time occupancy; `dflt` in plan-only mode or when the query fails)
+int resident_ctas(const Kernel &k, unsigned block, unsigned smem, int dflt) {
+  if (g_plan || !k.fn) return dflt;
+  int occ = 0;
+  if (k.jit) {
+    occ = jit_occupancy(k.fn, block, smem);
+  } else {
+    if (smem > 40 * 1024) cudaFuncSetAttribute(k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k.fn, (int)block, smem) != cudaSuccess) { occ = 0; cudaGetLastError(); }
+  }
+  return occ > 0 ? occ : dflt;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -448,6 +501,9 @@ int reduce_launch(mxb_context *h, int kop, const mxb_expr_t &e, const ExprInfo &
   } else if (vmax > 1 && (rot = outer_dim(vmax)) >= 0) {
     spec.family = FAM_RED_OUTER;
     spec.V = vmax;
+  } else if (vmax > 2 && inner_ok(vmax / 2)) {   // half-width vectors before giving up on them (8-byte aligned views)
+    spec.family = FAM_RED_INNER;
+    spec.V = vmax / 2;
   } else if (inner_ok(1)) {
     spec.family = FAM_RED_INNER;
     spec.V = 1;
@@ -654,29 +710,66 @@ int reduce_launch(mxb_context *h, int kop, const mxb_expr_t &e, const ExprInfo &
     spec.team = (row_bytes >= t1_limit || B < 8 * (int64_t)sm) ? 0 : 1;
     if (row_bytes < 4096) spec.team = 1;   // short rows never want a whole CTA
     if (env_int("MXB_TUNE_TEAM", -1) >= 0) spec.team = env_int("MXB_TUNE_TEAM", -1);
+    if (spec.team == 0 && tune_u <= 0 && env_int("MXB_TUNE_V", 0) <= 0 && nl <= 2 && gr.n == 1) {
+      // CTA-per-item streaming of one or two operands (profiles/r2_sweeps.md): four loads per leaf in flight, and — for
+      // the sums, whose per-element work is one add — 32-byte loads (fp32 2^30: 0.5877 vs 0.5991 ms; the arg ops and
+      // max / min keep 16 bytes: their per-element compare chains want the registers)
+      spec.U = 4;
+      const bool sum_like = kop == MXB_RED_SUM || kop == MXB_RED_PROD;
+      const int wide = 32 / info.max_leaf_bytes;
+      if (sum_like && wide > spec.V && wide <= 8 && spec.V > 1 && inner_ok(wide)) spec.V = wide;
+    }
+    // many long rows, one CTA per row at a time: 128-thread CTAs (8 per SM) hide a row's CTA stage behind the other
+    // rows' loads better than 4 CTAs of 256 (complex<float> 65536 x 8192 mean: 0.5829 vs 0.6080 ms)
+    if (spec.team == 0 && tune_block <= 0 && B >= 2 * (int64_t)sm) block = 128;
     if (spec.team == 0) {
       const int64_t L = gr.size[gr.n - 1];
       const int64_t Q = (R / L) * (L / spec.V);  // vector steps per row
       int64_t S = 1;
-      int cps = tune_cps > 0 ? tune_cps : 8;
+      // CTAs that are co-resident per SM: the grid is exactly one resident wave and the work items are dealt
+      // dynamically (RedParams::work_ctr), so no CTA ever waits behind another for an SM
+      spec.minb = env_int("MXB_TUNE_MINB", 0);
+      Kernel kq;
+      int st = get_kernel(info, spec, &kq);
+      if (st != MXB_OK) return st;
+      const int resident = resident_ctas(kq, block, 0, 4);
+      int cps = tune_cps > 0 ? tune_cps : std::min(resident, 8);
+      const int64_t grid_max = (int64_t)sm * cps;
       if (B < 2 * (int64_t)sm) {
-        // few long rows: `S` CTAs per row.  8 CTAs of 256 threads per SM = two waves (the block scheduler evens out the
-        // tail) for big inputs; below ~8 MiB per SM one resident wave (4 CTAs/SM at 64 registers) has the smaller fixed
-        // cost (tools/small_sweep.py)
-        const int64_t bytes_per_sm = B * R * info.max_leaf_bytes * std::max(1, nl) / sm;
-        if (tune_cps <= 0 && bytes_per_sm < (8ll << 20)) cps = 4;
-        S = ((int64_t)sm * cps + B - 1) / B;
-        const int64_t maxS = std::max<int64_t>(1, Q / ((int64_t)block * spec.U * 2));
-        S = std::max<int64_t>(1, std::min(S, maxS));
+        // few long rows: a row is cut into S items.  One contiguous reduce run: an item is a contiguous chunk of tiles
+        // (64 KB of the widest leaf; more for inputs so large that the final fold of the S partials would show), drawn
+        // dynamically.  Several runs per row: S ranges of vector steps, one per resident CTA.
+        if (gr.n == 1) {
+          const int64_t nfull = Q / ((int64_t)block * spec.U);
+          const int64_t want = env_int("MXB_TUNE_CHUNK_TILES", 0) > 0 ? env_int("MXB_TUNE_CHUNK_TILES", 0)
+                                                                       : (B * nfull >= 8 * grid_max ? 4 : (B * nfull >= 2 * grid_max ? 2 : 1));
+          const int64_t cht = std::max<int64_t>(want, (nfull + 16383) / 16384);
+          S = std::max<int64_t>(1, (nfull + cht - 1) / cht);
+          p.chunk_tiles = (int)cht;
+        } else {
+          S = (grid_max + B - 1) / B;
+          const int64_t maxS = std::max<int64_t>(1, Q / ((int64_t)block * spec.U * 2));
+          S = std::max<int64_t>(1, std::min(S, maxS));
+        }
       }
       p.splits = (int)S;
-      if (S > 1) {
-        int st = ensure_ws(h, (size_t)(B * S) * (size_t)acc_bytes(kop, info.value_dtype), (size_t)B);
-        if (st != MXB_OK) return st;
-        p.ws = h->ws;
-        p.tickets = h->tickets;
+      grid = (unsigned)std::min<int64_t>(B * S, grid_max);
+      const bool dynamic = B * S > (int64_t)grid && env_int("MXB_TUNE_DYNAMIC", 1) && B * S < (1ll << 31);
+      // combine exact in any order (max / min / arg / any / all, integer sums): one accumulator per CTA across its items
+      const bool exact_op = kop == MXB_RED_MAX || kop == MXB_RED_MIN || kop == MXB_RED_ARGMAX || kop == MXB_RED_ARGMIN || kop == MXB_RED_ANY ||
+                            kop == MXB_RED_ALL || ((kop == MXB_RED_SUM || kop == MXB_RED_PROD) && (info.value_dtype == MXB_I32 || info.value_dtype == MXB_I64));
+      if (dynamic && B == 1 && S > 1 && exact_op && env_int("MXB_TUNE_CARRY", 1)) p.carry_items = 1;
+      {
+        int st2 = ensure_ws(h, S > 1 ? (size_t)std::max<int64_t>(B * S, grid) * (size_t)acc_bytes(kop, info.value_dtype) : 0, (size_t)(S > 1 ? B : 0) + 2);
+        if (st2 != MXB_OK) return st2;
+        if (S > 1) {
+          p.ws = h->ws;
+          p.tickets = h->tickets;
+        }
+        // the two words after the per-row tickets: work counter + exit ticket (both return to zero by themselves)
+        if (dynamic) p.work_ctr = h->tickets + (S > 1 ? B : 0);
       }
-      grid = (unsigned)std::min<int64_t>(B * S, (int64_t)sm * cps);
+      return launch(h, kq, grid, block, smem, p);
     } else {
       // G lanes per row: enough lanes for one vector step each, at most a warp; 32 / G rows share a warp
       const int64_t L = gr.size[gr.n - 1];
@@ -1182,7 +1275,8 @@ int mxb_destroy(mxb_handle_t h) {
   if (h->ws) cudaFreeAsync(h->ws, h->stream);
   if (h->tickets) cudaFreeAsync(h->tickets, h->stream);
   if (h->tmp) cudaFreeAsync(h->tmp, h->stream);
-  if (h->scan_ws) cudaFreeAsync(h->scan_ws, h->stream);
+  if (h->lb_status) cudaFreeAsync(h->lb_status, h->stream);
+  if (h->lb_ctl) cudaFreeAsync(h->lb_ctl, h->stream);
   delete h;
   return MXB_OK;
 }
@@ -1873,55 +1967,34 @@ int mxb_cumsum(mxb_handle_t h, const mxb_expr_t *expr_in, const mxb_out_t *out) 
       rows_per_warp = 32 / G;
     }
   }
+  Kernel k;
+  st = get_kernel(info, spec, &k);
+  if (st != MXB_OK) return st;
   unsigned grid;
   if (tiles_mode) {
-    const int64_t gpr = (tpr + 127) / 128;   // SCAN_GROUP
-    // Regions are laid out from CAPACITIES that only grow (values are 8 bytes at most), so a word that is a flag in
-    // one launch is a flag in every launch: a stale tile total can never be mistaken for the current epoch.
-    const size_t need_t = (size_t)(B * tpr), need_g = (size_t)(B * gpr);
-    if (need_t > h->scan_cap_tiles || need_g > h->scan_cap_groups || !h->scan_ws) {
-      if (h->scan_ws) MXB_CUDA(cudaFreeAsync(h->scan_ws, h->stream));
-      h->scan_cap_tiles = std::max<size_t>(std::max(need_t, h->scan_cap_tiles), 4096);
-      h->scan_cap_groups = std::max<size_t>(std::max(need_g, h->scan_cap_groups), 1024);
-      const size_t nb = h->scan_cap_tiles * 20 + h->scan_cap_groups * 20 + 1024;
-      MXB_CUDA(cudaMallocAsync(&h->scan_ws, nb, h->stream));
-      MXB_CUDA(cudaMemsetAsync(h->scan_ws, 0, nb, h->stream));   // flags 0 = no epoch
-      h->scan_ws_bytes = nb;
-      h->scan_epoch = 0;
-    }
-    // 4-byte totals travel packed with their epoch in 8-byte slots; 8-byte totals have their own slots plus flag words.
-    // The two never share memory, so a stale 8-byte total cannot pose as a packed {epoch, value} word.
-    const bool wide = dtype_bytes(vt) >= 8;
-    const size_t o_agg4 = 0, o_gagg4 = o_agg4 + h->scan_cap_tiles * 8, o_agg8 = o_gagg4 + h->scan_cap_groups * 8,
-                 o_gagg8 = o_agg8 + h->scan_cap_tiles * 8, o_af = o_gagg8 + h->scan_cap_groups * 8, o_gf = o_af + h->scan_cap_tiles * 4;
-    const size_t o_agg = wide ? o_agg8 : o_agg4, o_gagg = wide ? o_gagg8 : o_gagg4;
-    // flags are epoch-coded: nothing to clear between launches
-    if (++h->scan_epoch == 0) {   // 2^32 launches later: start over
-      MXB_CUDA(cudaMemsetAsync(h->scan_ws, 0, h->scan_ws_bytes, h->stream));
-      h->scan_epoch = 1;
-    }
-    char *w = (char *)h->scan_ws;
-    p.scan_agg = w + o_agg;
-    p.scan_gagg = w + o_gagg;
-    p.scan_agg_flag = (unsigned *)(w + o_af);
-    p.scan_gagg_flag = (unsigned *)(w + o_gf);
-    p.scan_epoch = h->scan_epoch;
+    // slots: tile totals, group totals (32 tiles), running totals at supergroup starts (1024 tiles), per row
+    const int64_t gpr = (tpr + 31) / 32, spr = (tpr + 1023) / 1024;
+    const size_t need_t = (size_t)(B * tpr), need_g = (size_t)(B * gpr), need_s = (size_t)(B * spr);
+    st = ensure_lb(h, need_t + need_g + need_s);
+    if (st != MXB_OK) return st;
+    const int sb = dtype_bytes(vt) >= 8 ? 16 : 8;
+    char *w = (char *)lb_region(h, sb);
+    p.scan_agg = w;
+    p.scan_gagg = w + need_t * sb;
+    p.scan_sagg = w + (need_t + need_g) * sb;
+    p.scan_ctl = h->lb_ctl;
     // tiles are dealt round-robin to the grid and a tile waits for its predecessors, so every CTA must be resident:
-    // the kernels are built with __launch_bounds__(256, 3), which guarantees 3 CTAs per SM
-    const int per_sm = env_int("MXB_SCAN_GRID_PER_SM", 0) > 0 ? std::min(env_int("MXB_SCAN_GRID_PER_SM", 0), 3) : 3;
+    // the grid is sized from the launch-time occupancy and launched cooperatively (the runtime refuses a grid that
+    // cannot be co-resident instead of letting it spin)
+    const int res = resident_ctas(k, 256, 0, 3);
+    const int per_sm = env_int("MXB_SCAN_GRID_PER_SM", 0) > 0 ? std::min(env_int("MXB_SCAN_GRID_PER_SM", 0), res) : res;
     grid = (unsigned)std::min<int64_t>(B * tpr, (int64_t)sm * per_sm);
-    // MXB_SCAN_ONE_TILE_PER_CTA=1: a CTA per tile, relying on CTAs being dispatched in blockIdx order (CUB's assumption)
-    if (env_int("MXB_SCAN_ONE_TILE_PER_CTA", 0)) grid = (unsigned)(B * tpr);
-    p.scan_flags = (unsigned)env_int("MXB_SCAN_FLAGS", 0);
   } else {
     const int tune_cps = env_int("MXB_TUNE_CTAS_PER_SM", 0);
     const int64_t rows_per_cta = warp_team ? 8 * rows_per_warp : 1;
     grid = (unsigned)std::min<int64_t>((B + rows_per_cta - 1) / rows_per_cta, (int64_t)sm * (tune_cps > 0 ? tune_cps : 8));
   }
-  Kernel k;
-  st = get_kernel(info, spec, &k);
-  if (st != MXB_OK) return st;
-  return launch(h, k, grid, 256u, 0, p);
+  return launch(h, k, grid, 256u, 0, p, /*coop=*/tiles_mode);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -1998,9 +2071,6 @@ int mxb_find(mxb_handle_t h, const mxb_expr_t *expr_in, int select_op, double th
 
   const int64_t TILE = (int64_t)256 * V * 4;
   const int64_t ntiles = (N + TILE - 1) / TILE;
-  const unsigned grid = (unsigned)std::min<int64_t>(ntiles, (int64_t)h->sm_count * env_int("MXB_TUNE_SEL_CTAS", 8));
-  st = ensure_ws(h, (size_t)grid * 16 + 64, 1);
-  if (st != MXB_OK) return st;
 
   EwParams p;
   memset(&p, 0, sizeof p);
@@ -2018,9 +2088,6 @@ int mxb_find(mxb_handle_t h, const mxb_expr_t *expr_in, int select_op, double th
   p.sel_op = select_op;
   p.sel_thr_d = threshold;
   p.sel_thr_i = (int64_t)threshold;
-  p.sel_offsets = (unsigned long long *)h->ws;
-  p.sel_counts = (unsigned long long *)h->ws + grid;
-  p.sel_ticket = h->tickets;
   p.sel_total = (int *)count_out->data;
   p.sel_cap = out->size[0];
 
@@ -2030,16 +2097,40 @@ int mxb_find(mxb_handle_t h, const mxb_expr_t *expr_in, int select_op, double th
   spec.V = V;
   spec.U = 4;
   Kernel k;
-  // MXB_SEL_FAST=1 (opt-in, not yet measured): branch-free predicate and no N-D code in the kernels of a 1-D
-  // unit-stride operand — the first of the two fixes DESIGN.md section 4 `select` names
-  const int fast = (env_int("MXB_SEL_FAST", 0) && g.n == 1 && V > 1 && p.all_unit) ? 3 : 0;
-  spec.team = fast + 0;
+
+  // ---- one pass (select1p): a view that collapses to one dim, counts that fit 32 bits --------------------------------
+  if (g.n == 1 && N < (1ll << 32) - TILE && env_int("MXB_SEL_TWO_PASS", 0) == 0) {
+    if (V == 1) p.all_unit = 0;
+    spec.team = want_indices ? 4 : 3;
+    spec.out_dtype = out->dtype;
+    st = get_kernel(info, spec, &k);
+    if (st != MXB_OK) return st;
+    const unsigned smem = (unsigned)(2 * TILE * dtype_bytes(out->dtype));
+    const int res = resident_ctas(k, 256, smem, 3);
+    const int cps = env_int("MXB_TUNE_SEL_CTAS", 0) > 0 ? std::min(env_int("MXB_TUNE_SEL_CTAS", 0), res) : res;
+    const unsigned grid = (unsigned)std::min<int64_t>(ntiles, (int64_t)h->sm_count * cps);
+    st = ensure_lb(h, (size_t)(ntiles + (ntiles + 31) / 32 + (ntiles + 1023) / 1024 + 2));
+    if (st != MXB_OK) return st;
+    p.sel_status = (unsigned long long *)lb_region(h, 8);
+    p.sel_epoch = h->lb_ctl;
+    p.sel_ticket = h->lb_ctl + 1;
+    return launch(h, k, grid, 256, smem, p, /*coop=*/true);
+  }
+
+  // ---- two passes: N-D views that do not collapse (row-major decomposition per element), counts beyond 32 bits -------
+  const unsigned grid = (unsigned)std::min<int64_t>(ntiles, (int64_t)h->sm_count * (env_int("MXB_TUNE_SEL_CTAS", 0) > 0 ? env_int("MXB_TUNE_SEL_CTAS", 0) : 8));
+  st = ensure_ws(h, (size_t)grid * 16 + 64, 1);
+  if (st != MXB_OK) return st;
+  p.sel_offsets = (unsigned long long *)h->ws;
+  p.sel_counts = (unsigned long long *)h->ws + grid;
+  p.sel_ticket = h->tickets;
+  spec.team = 0;
   spec.out_dtype = info.value_dtype;
   st = get_kernel(info, spec, &k);
   if (st != MXB_OK) return st;
   st = launch(h, k, grid, 256, 0, p);
   if (st != MXB_OK) return st;
-  spec.team = fast + (want_indices ? 2 : 1);
+  spec.team = want_indices ? 2 : 1;
   spec.out_dtype = out->dtype;
   st = get_kernel(info, spec, &k);
   if (st != MXB_OK) return st;

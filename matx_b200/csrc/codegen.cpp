@@ -475,6 +475,7 @@ std::string kernel_key(const ExprInfo &info, const KernelSpec &s) {
   static const char *fam[] = {"red_inner", "red_outer", "var_smem", "ew", "var_reg", "var_tma", "var_group", "softmax_group", "softmax_reg", "ew_tr", "scan", "red_outer_tma", "select", "var_tma2"};
   k << fam[s.family] << "|" << info.name << "|" << (s.op >= 0 ? reduce_op_name(s.op) : "-") << "|" << dtype_name(s.out_dtype)
     << "|V" << s.V << "|U" << s.U << "|T" << s.team;
+  if (s.minb > 0) k << "|M" << s.minb;
   return k.str();
 }
 std::string kernel_symbol(const std::string &key) {
@@ -515,7 +516,7 @@ int kernel_wrapper_src(const ExprInfo &info, const KernelSpec &s, const std::str
   const std::string VU = std::to_string(s.V) + ", " + std::to_string(s.U);
   switch (s.family) {
     case FAM_RED_INNER:
-      k << "extern \"C\" __global__ void __launch_bounds__(" << (s.team == 0 ? 512 : 256) << ") " << symbol
+      k << "extern \"C\" __global__ void __launch_bounds__(" << (s.minb > 0 ? "256, " + std::to_string(s.minb) : std::string(s.team == 0 ? "512" : "256")) << ") " << symbol
         << "(const __grid_constant__ mxb::RedParams p) { mxb::reduce_inner_body<" << E << ", " << op << ", " << O << ", " << VU
         << ", " << s.team << ">(p); }\n";
       break;
@@ -583,12 +584,16 @@ int kernel_wrapper_src(const ExprInfo &info, const KernelSpec &s, const std::str
         << "(const __grid_constant__ mxb::EwParams p) { mxb::ew_tr_body<" << E << ", " << O << ", " << (16 / s.V) << ">(p); }\n";
       break;
     case FAM_SELECT:
-      // team = pass: 0 count (+ in-launch scan of the CTA totals), 1 scatter values, 2 scatter flat indices; +3 = the
-      // opt-in fast instances for 1-D unit-stride operands (MXB_SEL_FAST=1)
+      // team = kernel: 0 count (+ in-launch scan of the CTA totals), 1 scatter values, 2 scatter flat indices (the two-pass
+      // pair for N-D views); 3 / 4 = the single-pass look-back kernel writing values / flat indices
       if (cplx || info.value_dtype == MXB_BF16 || info.value_dtype == MXB_F16) return fail("find / find_idx serve real value types");
-      if (s.team < 0 || s.team > 5) return fail("select pass out of range");   // 3..5: the opt-in fast instances
-      k << "extern \"C\" __global__ void __launch_bounds__(256) " << symbol
-        << "(const __grid_constant__ mxb::EwParams p) { mxb::select_body<" << E << ", " << O << ", " << s.V << ", " << s.team << ">(p); }\n";
+      if (s.team < 0 || s.team > 4) return fail("select kernel out of range");
+      if (s.team >= 3)
+        k << "extern \"C\" __global__ void __launch_bounds__(256, 3) " << symbol
+          << "(const __grid_constant__ mxb::EwParams p) { mxb::select1p_body<" << E << ", " << O << ", " << s.V << ", " << (s.team - 2) << ">(p); }\n";
+      else
+        k << "extern \"C\" __global__ void __launch_bounds__(256) " << symbol
+          << "(const __grid_constant__ mxb::EwParams p) { mxb::select_body<" << E << ", " << O << ", " << s.V << ", " << s.team << ">(p); }\n";
       break;
     default: return fail("unknown kernel family");
   }

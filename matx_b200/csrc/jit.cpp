@@ -5,6 +5,7 @@
 // functor (codegen.cpp), dropped into the same skeleton header the AOT kernels use, and compiled for
 // sm_100a once per (program, kernel family, reduce op, dtypes).  NVRTC and the driver are dlopen'ed on
 // first use so that the library itself loads on a machine with neither.
+#include <cuda.h>   // types only (CUlaunchConfig, CUfunction ...): every driver entry point is resolved with dlsym
 #include <dlfcn.h>
 #include <sys/stat.h>
 #include <unistd.h>
@@ -42,9 +43,6 @@ const void *lookup_aot(const std::string &key) {
 namespace {
 typedef struct _nvrtcProgram *nvrtcProgram;
 typedef int nvrtcResult;
-typedef int CUresult;
-typedef struct CUmod_st *CUmodule;
-typedef struct CUfunc_st *CUfunction;
 
 struct Dyn {
   bool tried = false, ok = false;
@@ -60,8 +58,12 @@ struct Dyn {
   CUresult (*ModuleLoadData)(CUmodule *, const void *) = nullptr;
   CUresult (*ModuleGetFunction)(CUfunction *, CUmodule, const char *) = nullptr;
   CUresult (*GetErrorStringDrv)(CUresult, const char **) = nullptr;
-  CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, void *, void **, void **) = nullptr;
-  CUresult (*FuncSetAttribute)(CUfunction, int, int) = nullptr;
+  CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream, void **, void **) = nullptr;
+  CUresult (*FuncSetAttribute)(CUfunction, CUfunction_attribute, int) = nullptr;
+  CUresult (*LaunchKernelEx)(const CUlaunchConfig *, CUfunction, void **, void **) = nullptr;   // optional (PDL launches)
+  CUresult (*CtxGetCurrent)(CUcontext *) = nullptr;
+  CUresult (*ModuleUnload)(CUmodule) = nullptr;
+  CUresult (*OccupancyMaxActiveBlocks)(int *, CUfunction, int, size_t) = nullptr;
   std::string include_dir;
 };
 Dyn g_dyn;
@@ -106,7 +108,11 @@ bool dyn_init(std::string *err) {
   MXB_SYM(hc, GetErrorStringDrv, "cuGetErrorString")
   MXB_SYM(hc, LaunchKernel, "cuLaunchKernel")
   MXB_SYM(hc, FuncSetAttribute, "cuFuncSetAttribute")
+  MXB_SYM(hc, CtxGetCurrent, "cuCtxGetCurrent")
+  MXB_SYM(hc, ModuleUnload, "cuModuleUnload")
+  MXB_SYM(hc, OccupancyMaxActiveBlocks, "cuOccupancyMaxActiveBlocksPerMultiprocessor")
 #undef MXB_SYM
+  *(void **)(&g_dyn.LaunchKernelEx) = dlsym(hc, "cuLaunchKernelEx");
   // cuda_fp16.h / cuda_bf16.h live next to the toolkit
   for (const std::string &r : roots)
     if (file_exists(r + "/include/cuda_bf16.h")) { g_dyn.include_dir = r + "/include"; break; }
@@ -143,9 +149,16 @@ int64_t g_jit_compiles = 0;
 
 const void *jit_get_kernel(const std::string &key, const std::string &symbol, const std::string &source, std::string *err) {
   std::lock_guard<std::mutex> lock(g_mu);
-  auto it = g_jit.find(key);
-  if (it != g_jit.end()) return it->second;
   if (!dyn_init(err)) return nullptr;
+  // a CUfunction belongs to the context its module was loaded in: one entry per (context, kernel), so a second handle on
+  // another GPU of the same process gets a function of ITS device
+  CUcontext ctx = nullptr;
+  g_dyn.CtxGetCurrent(&ctx);
+  char ctxs[32];
+  snprintf(ctxs, sizeof ctxs, "@%p|", (void *)ctx);
+  const std::string ckey = ctxs + key;
+  auto it = g_jit.find(ckey);
+  if (it != g_jit.end()) return it->second;
 
   // disk cache keyed by the full source text (skeleton + functor + wrapper)
   char hname[64];
@@ -153,9 +166,17 @@ const void *jit_get_kernel(const std::string &key, const std::string &symbol, co
            (unsigned long long)fnv64(std::string(kDeviceHeaderText)));
   const std::string cpath = cache_dir() + "/" + hname;
   std::string cubin;
+  bool from_disk = false;
   if (!getenv("MXB_NO_DISK_CACHE")) {
     std::ifstream f(cpath, std::ios::binary);
-    if (f) { std::stringstream ss; ss << f.rdbuf(); cubin = ss.str(); }
+    if (f) { std::stringstream ss; ss << f.rdbuf(); cubin = ss.str(); from_disk = !cubin.empty(); }
+  }
+  CUmodule mod = nullptr;
+  if (from_disk && g_dyn.ModuleLoadData(&mod, cubin.data()) != 0) {
+    // truncated / corrupt cache entry: drop it and build again, once
+    mod = nullptr;
+    cubin.clear();
+    unlink(cpath.c_str());
   }
   if (cubin.empty()) {
     nvrtcProgram prog = nullptr;
@@ -190,8 +211,7 @@ const void *jit_get_kernel(const std::string &key, const std::string &symbol, co
       if (f) { f.write(cubin.data(), (std::streamsize)cubin.size()); f.close(); rename(tmp.c_str(), cpath.c_str()); }
     }
   }
-  CUmodule mod = nullptr;
-  CUresult cr = g_dyn.ModuleLoadData(&mod, cubin.data());
+  CUresult cr = mod ? CUDA_SUCCESS : g_dyn.ModuleLoadData(&mod, cubin.data());
   if (cr != 0) {
     const char *s = nullptr;
     g_dyn.GetErrorStringDrv(cr, &s);
@@ -201,20 +221,51 @@ const void *jit_get_kernel(const std::string &key, const std::string &symbol, co
   CUfunction fn = nullptr;
   cr = g_dyn.ModuleGetFunction(&fn, mod, symbol.c_str());
   if (cr != 0) { if (err) *err = "cuModuleGetFunction failed for " + symbol; return nullptr; }
-  g_jit[key] = (const void *)fn;
+  g_jit[ckey] = (const void *)fn;
   return (const void *)fn;
 }
 
+int jit_occupancy(const void *fn, unsigned block, unsigned smem) {
+  if (!g_dyn.ok || !g_dyn.OccupancyMaxActiveBlocks) return 0;
+  int n = 0;
+  if (g_dyn.OccupancyMaxActiveBlocks(&n, (CUfunction)fn, (int)block, (size_t)smem) != 0) return 0;
+  return n;
+}
 
-int jit_launch(const void *fn, unsigned grid, unsigned block, unsigned smem, void *stream, void *params, std::string *err) {
+
+int jit_launch(const void *fn, unsigned grid, unsigned block, unsigned smem, void *stream, void *params, std::string *err, bool pdl, bool coop) {
   if (!g_dyn.ok) { if (err) *err = "JIT runtime not initialised"; return MXB_ERR_JIT; }
   CUfunction f = (CUfunction)fn;
   if (smem > 40 * 1024) {
-    const CUresult a = g_dyn.FuncSetAttribute(f, 8 /* CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES */, (int)smem);
+    const CUresult a = g_dyn.FuncSetAttribute(f, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem);
     if (a != 0) { if (err) *err = "cuFuncSetAttribute(max dynamic smem) failed"; return MXB_ERR_CUDA; }
   }
   void *args[] = {params};
-  const CUresult r = g_dyn.LaunchKernel(f, grid, 1, 1, block, 1, 1, smem, stream, args, nullptr);
+  CUresult r;
+  if (coop && !g_dyn.LaunchKernelEx) { if (err) *err = "cuLaunchKernelEx missing: cooperative launch unavailable"; return MXB_ERR_CUDA; }
+  if (g_dyn.LaunchKernelEx && (pdl || coop)) {
+    // programmatic dependent launch, like the ahead-of-time kernels (every body starts with griddepcontrol.wait)
+    CUlaunchConfig cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDimX = grid; cfg.gridDimY = 1; cfg.gridDimZ = 1;
+    cfg.blockDimX = block; cfg.blockDimY = 1; cfg.blockDimZ = 1;
+    cfg.sharedMemBytes = smem;
+    cfg.hStream = (CUstream)stream;
+    CUlaunchAttribute attr[1];
+    memset(attr, 0, sizeof attr);
+    if (coop) {
+      attr[0].id = CU_LAUNCH_ATTRIBUTE_COOPERATIVE;
+      attr[0].value.cooperative = 1;
+    } else {
+      attr[0].id = CU_LAUNCH_ATTRIBUTE_PROGRAMMATIC_STREAM_SERIALIZATION;
+      attr[0].value.programmaticStreamSerializationAllowed = 1;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    r = g_dyn.LaunchKernelEx(&cfg, f, args, nullptr);
+  } else {
+    r = g_dyn.LaunchKernel(f, grid, 1, 1, block, 1, 1, smem, (CUstream)stream, args, nullptr);
+  }
   if (r != 0) {
     const char *s = nullptr;
     g_dyn.GetErrorStringDrv(r, &s);

@@ -115,9 +115,10 @@ struct RedParams {
   PeerPush peer;
   i64 out_rs[KMAXD];  // softmax / scan: strides of the output over the reduce dims
   // scan family only: the handle's scan workspace (tile / group totals, epoch-coded flags)
-  void *scan_agg, *scan_gagg;
-  u32 *scan_agg_flag, *scan_gagg_flag;
-  u32 scan_epoch;
+  // TILES mode: published totals {tag : value} of tiles / groups of 32 tiles / supergroup starts (8-byte slots for 4-byte
+  // values, 16-byte slots for 8-byte values), the device-resident launch epoch and the exit ticket
+  void *scan_agg, *scan_gagg, *scan_sagg;
+  u32 *scan_ctl;
   int scan_group;   // warp team, rows of <= 32 vectors: lanes per row (power of two), 0 = a whole warp per row
   u32 scan_flags;   // TILES mode: bit 0 issues the next tile's loads before the publish instead of after (sweep knob)
   int tma_rt;       // reduce_outer_tma: reduce rows per ring stage (splits = ring depth, tx = 16-byte chunks per strip)
@@ -125,6 +126,16 @@ struct RedParams {
   // CUtensorMap over the leaf as {vector dim in 8-byte elements, reduce dim, outer batch dim} (opaque 128 bytes, must
   // stay in the kernel's parameter space: the copy instruction takes its address)
   __align__(64) unsigned long long tmap[16];
+  // reduce_inner, CTA-per-item flavour: dynamic work distribution.  work_ctr != nullptr: a CTA takes item blockIdx.x first
+  // and then draws gridDim.x + atomicAdd(work_ctr, 1) until the items run out (the SMs never run at the same speed — HBM
+  // channel conflicts, the other die — and a static deal ends at the speed of the slowest); work_ctr[1] is the
+  // self-resetting exit ticket whose last holder zeroes work_ctr[0] for the next launch.  Which CTA runs an item does
+  // not change what the item computes, so results stay run-to-run deterministic.
+  u32 *work_ctr;
+  int chunk_tiles;  // > 0 (one contiguous reduce run): split s of a row owns tiles [s * chunk_tiles, (s + 1) * chunk_tiles)
+  // 1 (dynamic deal, one row, an op whose combine is exact in any order — max / min / arg / any / all, integer sums): a
+  // CTA keeps ONE accumulator across all the items it draws and writes one partial at exit (no per-item CTA stage)
+  int carry_items;
 };
 
 // elementwise: up to KMAXD collapsed dims, innermost last
@@ -152,6 +163,10 @@ struct EwParams {
   u32 *sel_ticket;                 // self-resetting arrival counter of the count pass
   int *sel_total;                  // num_found (clamped to INT_MAX like the reference's int count)
   i64 sel_cap;                     // capacity of the output: elements beyond it are counted but not written
+  // single-pass select (select1p): one 64-bit status word per tile {(epoch << 2 | state) : running count}, the launch
+  // epoch (device-resident: bumped by the last CTA out, so a CUDA-graph replay sees a fresh epoch too) and the exit ticket
+  unsigned long long *sel_status;
+  u32 *sel_epoch;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -1029,6 +1044,7 @@ template <class E, class Op, class OutT, int V, int U, int TEAM, bool UNIT>
 __device__ __forceinline__ void reduce_inner_body_impl(const RedParams &p) {
   typedef typename Op::acc_t acc_t;
   __shared__ acc_t s_acc[32];
+  __shared__ acc_t s_acc2[TEAM == 0 ? 2 : 1][TEAM == 0 ? 32 : 1];
   __shared__ int s_last;
 
   // TEAM == 1: G lanes per row (G = p.tx, a power of two <= 32), 32 / G rows per warp; the row loop is warp-uniform
@@ -1048,7 +1064,19 @@ __device__ __forceinline__ void reduce_inner_body_impl(const RedParams &p) {
   const i64 S = TEAM == 0 ? (i64)p.splits : 1;
   const i64 work = p.B * S;
 
-  for (i64 wb = wb0; wb < work; wb += wstep) {
+  __shared__ i64 s_next[2];
+  const bool dyn = TEAM == 0 && p.work_ctr != nullptr;
+  const bool carry = dyn && p.carry_items != 0;
+  bool first_item = true;
+  acc_t acc[V];
+  int par = 0;
+  for (i64 wb = wb0; wb < work;) {
+    i64 wnext = wb + wstep;
+    // dynamic deal: the draw for the NEXT item goes out first and stays in a register until the CTA stage, so its L2
+    // round trip hides behind this item's loads (parking it in shared memory right away would stall thread 0 on the
+    // atomic's return before it has issued a single load: measured 6 % on 64 KB items)
+    u32 drawn = 0;
+    if (dyn && threadIdx.x == 0) drawn = atomicAdd(p.work_ctr, 1u);
     i64 w = wb + gid;
     const bool valid = w < work;
     if (!valid) w = work - 1;
@@ -1080,9 +1108,11 @@ __device__ __forceinline__ void reduce_inner_body_impl(const RedParams &p) {
         for (int d = 0; d < KMAXD; ++d) if (d < p.nb) row0 += bidx[d] * p.bflat[d] * p.R;
       }
     }
-    acc_t acc[V];
+    if (!carry || first_item) {
 #pragma unroll
-    for (int v = 0; v < V; ++v) acc[v] = Op::init();
+      for (int v = 0; v < V; ++v) acc[v] = Op::init();
+      first_item = false;
+    }
 
     // vector steps of the row are numbered q = o * Lv + jv, Q of them
     const i64 Q = O * Lv;
@@ -1092,7 +1122,11 @@ __device__ __forceinline__ void reduce_inner_body_impl(const RedParams &p) {
       // tiles, which keeps the DRAM pages they open shared); inside a tile every thread has U loads in flight.
       const i64 tile = (i64)nthr * U;
       const i64 nfull = Q / tile;
-      for (i64 t = s; t < nfull; t += S) {
+      const i64 cht = p.chunk_tiles;   // > 0: this split owns a contiguous run of tiles, else tiles are dealt round-robin
+      const i64 tfirst = cht > 0 ? s * cht : s;
+      const i64 tend = cht > 0 ? ((tfirst + cht < nfull) ? tfirst + cht : nfull) : nfull;
+      const i64 tstep = cht > 0 ? 1 : S;
+      for (i64 t = tfirst; t < tend; t += tstep) {
         const i64 q = t * tile + tid;
         typename E::template Regs<V> r[U];
 #pragma unroll
@@ -1104,7 +1138,7 @@ __device__ __forceinline__ void reduce_inner_body_impl(const RedParams &p) {
           for (int v = 0; v < V; ++v) Op::step(acc[v], E::template eval<V>(r[u], v, p.c), row0 + j0 + v);
         }
       }
-      if (s == nfull % S) {  // the ragged last tile goes to the next split in turn
+      if (s == (cht > 0 ? S - 1 : nfull % S)) {  // the ragged last tile goes to the next split in turn (contiguous runs: to the last split)
         for (i64 q = nfull * tile + tid; q < Q; q += nthr) {
           typename E::template Regs<V> r;
           E::template loadv<V, UNIT>(r, base, inner, q * V);
@@ -1142,34 +1176,112 @@ __device__ __forceinline__ void reduce_inner_body_impl(const RedParams &p) {
         Op::merge(acc[0], one);
       }
     }
+    if (carry) {
+      // one accumulator across the items of this CTA: only the next draw has to be published
+      if (threadIdx.x == 0) s_next[par] = (i64)gridDim.x + (i64)drawn;
+      __syncthreads();
+      wnext = s_next[par];
+      par ^= 1;
+      wb = wnext;
+      continue;
+    }
 #pragma unroll
     for (int v = 1; v < V; ++v) Op::merge(acc[0], acc[v]);
     // streaming part of this CTA's last work item is over: let the next kernel on the stream start launching while
     // the warp / CTA / grid stages finish (it still waits for this grid to complete before touching memory)
-    if (wb + wstep >= work) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (!dyn && wnext >= work) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (dyn && threadIdx.x == 0) s_next[par] = (i64)gridDim.x + (i64)drawn;   // published by the CTA stage's barriers
 
     if (TEAM == 1) {
       acc_t tot = group_merge<Op>(acc[0], G);
       if (tid == 0 && valid) store_result<Op, OutT>(p, b, tot);
     } else {
-      acc_t tot = cta_merge<Op>(acc[0], s_acc);
-      if (S == 1) {
-        if (tid == 0) store_result<Op, OutT>(p, b, tot);
-      } else {
-        acc_t *ws = (acc_t *)p.ws;
-        if (tid == 0) {
-          st_cg_t(&ws[b * S + s], tot);
-          __threadfence();
-          const u32 t = atomicInc(&p.tickets[b], (u32)(S - 1));
-          s_last = (t == (u32)(S - 1));
+      // CTA stage, ONE barrier per item: the per-warp partials are double-buffered by item parity (the barrier also
+      // publishes thread 0's draw of the next item)
+      const int lane = (int)threadIdx.x & 31, warp = (int)threadIdx.x >> 5, nwarp = ((int)blockDim.x + 31) >> 5;
+      const acc_t wtot = Op::warp(acc[0]);
+      if (lane == 0) s_acc2[par][warp] = wtot;
+      __syncthreads();
+      if (warp == 0) {
+        const acc_t v = (lane < nwarp) ? s_acc2[par][lane] : Op::init();
+        const acc_t tot = nwarp > 1 ? Op::warp(v) : wtot;
+        if (lane == 0) {
+          if (S == 1) {
+            store_result<Op, OutT>(p, b, tot);
+          } else {
+            st_cg_t(&((acc_t *)p.ws)[b * S + s], tot);
+            if (!dyn) {   // static deal (every CTA has one item): per-row ticket, the last arrival folds the row
+              __threadfence();
+              const u32 t = atomicInc(&p.tickets[b], (u32)(S - 1));
+              s_last = (t == (u32)(S - 1));
+            }
+          }
         }
+      }
+      if (S > 1 && !dyn) {
         __syncthreads();
         if (s_last) {
           __threadfence();
           acc_t a = Op::init();
-          for (i64 i = tid; i < S; i += nthr) Op::merge(a, ld_cg_t(&ws[b * S + i]));
+          for (i64 i = tid; i < S; i += nthr) Op::merge(a, ld_cg_t(&((const acc_t *)p.ws)[b * S + i]));
           a = cta_merge<Op>(a, s_acc);
           if (tid == 0) store_result<Op, OutT>(p, b, a);
+        }
+      }
+    }
+    if (dyn) {
+      wnext = s_next[par];
+      if (wnext >= work) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    }
+    par ^= 1;
+    wb = wnext;
+  }
+  if (carry) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (first_item) {
+#pragma unroll
+      for (int v = 0; v < V; ++v) acc[v] = Op::init();
+    }
+#pragma unroll
+    for (int v = 1; v < V; ++v) Op::merge(acc[0], acc[v]);
+    const acc_t tot = cta_merge<Op>(acc[0], s_acc);
+    if (threadIdx.x == 0) st_cg_t(&((acc_t *)p.ws)[blockIdx.x], tot);
+  }
+  if (dyn) {
+    // exit ticket: every draw of this CTA has returned and its partials are written; the last CTA out rewinds the work
+    // counter for the next launch and folds the partials of every row (S per row; one per CTA in carry mode) in a fixed
+    // order (deterministic)
+    const i64 nfold = carry ? (i64)gridDim.x : S;
+    if (threadIdx.x == 0) {
+      __threadfence();
+      const bool last = atomicInc(p.work_ctr + 1, gridDim.x - 1) == gridDim.x - 1;
+      if (last) atomicExch(p.work_ctr, 0u);
+      s_last = last ? 1 : 0;
+    }
+    __syncthreads();
+    if (s_last && (S > 1 || carry)) {
+      __threadfence();
+      const acc_t *ws = (const acc_t *)p.ws;
+      if (p.B == 1) {
+        // four independent loads per trip: the fold is one CTA against L2 latency
+        acc_t a = Op::init();
+        const i64 nt = blockDim.x;
+        i64 i = threadIdx.x;
+        for (; i + 3 * nt < nfold; i += 4 * nt) {
+          const acc_t x0 = ld_cg_t(&ws[i]), x1 = ld_cg_t(&ws[i + nt]), x2 = ld_cg_t(&ws[i + 2 * nt]), x3 = ld_cg_t(&ws[i + 3 * nt]);
+          Op::merge(a, x0); Op::merge(a, x1); Op::merge(a, x2); Op::merge(a, x3);
+        }
+        for (; i < nfold; i += nt) Op::merge(a, ld_cg_t(&ws[i]));
+        a = cta_merge<Op>(a, s_acc);
+        if (threadIdx.x == 0) store_result<Op, OutT>(p, 0, a);
+      } else {
+        // a warp per row: lane-strided partials, then the op's warp stage
+        const int lane = (int)threadIdx.x & 31, nwarp = (int)blockDim.x >> 5;
+        for (i64 b = threadIdx.x >> 5; b < p.B; b += nwarp) {
+          acc_t a = Op::init();
+          for (i64 i = lane; i < S; i += 32) Op::merge(a, ld_cg_t(&ws[b * S + i]));
+          a = Op::warp(a);
+          if (lane == 0) store_result<Op, OutT>(p, b, a);
         }
       }
     }
@@ -2274,15 +2386,19 @@ __device__ __forceinline__ void ew_body_impl(const EwParams &p) {
     const char *base[E::NL];
 #pragma unroll
     for (int k = 0; k < E::NL; ++k) base[k] = (const char *)p.leaf[k].ptr;
-    i64 q = t0;
-    for (; q + (i64)(U - 1) * nthr < Q; q += (i64)U * nthr) {
+    // a CTA takes batches of blockDim.x * U consecutive vectors (its U loads per leaf are neighbours in memory: the
+    // streams a CTA has open stay within one DRAM page per operand), batches are dealt round-robin to the grid
+    const i64 bsz = (i64)blockDim.x * U;
+    const i64 nbatch = Q / bsz;
+    for (i64 bi = blockIdx.x; bi < nbatch; bi += gridDim.x) {
+      const i64 q = bi * bsz + threadIdx.x;
       typename E::template Regs<V> r[U];
 #pragma unroll
-      for (int u = 0; u < U; ++u) E::template loadv<V, UNIT>(r[u], base, inner, (q + (i64)u * nthr) * V);
+      for (int u = 0; u < U; ++u) E::template loadv<V, UNIT>(r[u], base, inner, (q + (i64)u * blockDim.x) * V);
 #pragma unroll
-      for (int u = 0; u < U; ++u) ew_store<E, OutT, V>(p, (char *)p.out.ptr, oinner, (q + (i64)u * nthr) * V, r[u]);
+      for (int u = 0; u < U; ++u) ew_store<E, OutT, V>(p, (char *)p.out.ptr, oinner, (q + (i64)u * blockDim.x) * V, r[u]);
     }
-    for (; q < Q; q += nthr) {
+    for (i64 q = nbatch * bsz + t0; q < Q; q += nthr) {
       typename E::template Regs<V> r;
       E::template loadv<V, UNIT>(r, base, inner, q * V);
       ew_store<E, OutT, V>(p, (char *)p.out.ptr, oinner, q * V, r);
@@ -2571,62 +2687,67 @@ __device__ __forceinline__ void ew_tr_body(const EwParams &p) {
 // coalesced), scans them in registers, the warp scans the thread totals with shuffles, the eight warp totals of the U
 // chunks meet in shared memory.  All additions happen in a FIXED order, so results are run-to-run deterministic.
 //   mode ROWS  (p.splits == 1): a CTA owns whole rows and walks their tiles with a carry in a register.
-//   mode TILES (p.splits  > 1): few long rows -> the tiles of all rows are dealt round-robin to a grid of co-resident
-//     CTAs (3 per SM, which the launch bounds guarantee), so a tile only ever waits for tiles that are running or
-//     done.  A tile publishes its total; the LAST tile of each group of SCAN_GROUP tiles also publishes the group's
-//     total; a tile's carry is (totals of the groups before its own) + (totals of the tiles before it in its group):
-//     two flat, fixed-order sums of at most a few hundred L2-resident values gathered by all 256 threads at once — no
-//     serial chain between tiles, no atomics (a tile counter on one address serialises at ~13 ns per tile, which was
-//     the whole run time of the first version), and no dependence on which neighbour happened to finish first (CUB's
-//     look-back adds whatever it finds, so its float sums vary from run to run).  Flags carry the launch epoch:
-//     nothing is cleared between launches.
+//   mode TILES (p.splits  > 1): few long rows -> the tiles of all rows are dealt round-robin to a grid whose CTAs are all
+//     resident (cooperative launch), so a tile only ever waits for tiles that are running or done.  Every tile publishes
+//     its total; the last tile of a GROUP of 32 tiles publishes the group's total; the last tile of a SUPERGROUP of 32
+//     groups publishes the running total at the start of the next supergroup (the only chained quantity: one link per
+//     1024 tiles, far slower than the stream).  A tile's carry = that running total + the totals of the groups before
+//     its own in the supergroup + the totals of the tiles before it in its group: at most 1 + 31 + 31 values, fetched by
+//     warp 0 with all loads in flight at once and summed by fixed-shape shuffle trees — one L2 round trip when the
+//     neighbours are done, no atomics, and no dependence on which neighbour happened to finish first (CUB's look-back adds
+//     whatever it finds, so its float sums vary from run to run; these do not).
 //   Both modes keep the NEXT tile's loads in flight while the current tile goes through its barriers and its carry
 //   exchange (the loads are issued into the registers the evaluation has just freed).
 // ------------------------------------------------------------------------------------------------
 constexpr int SCAN_NT = 256;
-constexpr int SCAN_GROUP = 128;
 
-// workspace (RedParams::scan_*): agg = T[B * tiles_per_row] tile totals, gagg = T[B * groups_per_row] group totals,
-// *_flag == launch epoch once the value is valid
-
-__device__ __forceinline__ u32 ld_acquire_u32(const u32 *p) {
-  u32 v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void st_release_u32(u32 *p, u32 v) {
-  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-// A published total.  4-byte values travel WITH their flag in one 8-byte word (epoch in the high half): one relaxed
-// load both tests and fetches, no acquire / release and no second round trip (what CUB's tile status words do).
-// 8-byte values use the separate epoch flag with release / acquire.
-template <class T> struct ScanSlot {
-  static __device__ __forceinline__ void publish(T *val, u32 *flag, i64 i, T v, u32 epoch) {
-    if (sizeof(T) == 4) {
-      union { T t; u32 w; } u;
-      u.t = v;
-      const unsigned long long word = ((unsigned long long)epoch << 32) | u.w;
-      asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"((unsigned long long *)val + i), "l"(word) : "memory");
-    } else {
-      st_cg_t(val + i, v);
-      st_release_u32(flag + i, epoch);
-    }
+
+// A published total: tag = (launch epoch << 2) | 1 in the high half of a 64-bit word.  4-byte values travel IN that word
+// (one relaxed load both tests and fetches, what CUB's tile status words do); 8-byte values sit beside it in a 16-byte
+// slot moved with one 128-bit access (never torn inside an aligned 16-byte sector; CUB's ScanTileState makes the same
+// assumption for 8-byte types).  The epoch lives in device memory and is bumped by the last CTA out, so nothing is
+// cleared between launches and a CUDA-graph replay gets a fresh epoch as well.
+template <class T, int BYTES = (int)sizeof(T)> struct ScanSlot;
+template <class T> struct ScanSlot<T, 4> {
+  enum { STRIDE = 8 };
+  static __device__ __forceinline__ void publish(void *slots, i64 i, T v, u32 tag) {
+    union { T t; u32 w; } u;
+    u.t = v;
+    st_relaxed_u64((unsigned long long *)slots + i, ((unsigned long long)tag << 32) | u.w);
   }
-  static __device__ __forceinline__ T wait(const T *val, const u32 *flag, i64 i, u32 epoch) {
-    if (sizeof(T) == 4) {
-      unsigned long long word;
-      while (true) {
-        asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(word) : "l"((const unsigned long long *)val + i) : "memory");
-        if ((u32)(word >> 32) == epoch) break;
-        __nanosleep(20);
-      }
-      union { T t; u32 w; } u;
-      u.w = (u32)word;
-      return u.t;
-    } else {
-      while (ld_acquire_u32(flag + i) != epoch) __nanosleep(20);
-      return ld_cg_t(val + i);
+  static __device__ __forceinline__ T wait(const void *slots, i64 i, u32 tag) {
+    unsigned long long w = ld_relaxed_u64((const unsigned long long *)slots + i);
+    while ((u32)(w >> 32) != tag) { __nanosleep(20); w = ld_relaxed_u64((const unsigned long long *)slots + i); }
+    union { T t; u32 w; } u;
+    u.w = (u32)w;
+    return u.t;
+  }
+};
+template <class T> struct ScanSlot<T, 8> {
+  enum { STRIDE = 16 };
+  static __device__ __forceinline__ void publish(void *slots, i64 i, T v, u32 tag) {
+    union { T t; unsigned long long w; } u;
+    u.t = v;
+    asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"((unsigned long long *)slots + 2 * i), "l"((unsigned long long)tag << 32), "l"(u.w) : "memory");
+  }
+  static __device__ __forceinline__ T wait(const void *slots, i64 i, u32 tag) {
+    unsigned long long f, w;
+    while (true) {
+      asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(f), "=l"(w) : "l"((const unsigned long long *)slots + 2 * i) : "memory");
+      if ((u32)(f >> 32) == tag) break;
+      __nanosleep(20);
     }
+    union { T t; unsigned long long w; } u;
+    u.w = w;
+    return u.t;
   }
 };
 
@@ -2638,32 +2759,48 @@ template <class T> __device__ __forceinline__ T shfl_up_t(T v, int d) {
   for (int i = 0; i < W; ++i) b.w[i] = __shfl_up_sync(0xffffffffu, a.w[i], d);
   return b.t;
 }
-template <class T> __device__ __forceinline__ T scan_zero() { return cvt<T>(0.0f); }
-
-// fixed-order sum of n published values by one warp: lane-strided partial sums, then a shuffle tree
-template <class T>
-__device__ __forceinline__ T warp_sum_published(const T *val, const u32 *flag, i64 n, u32 epoch, int lane) {
-  T acc = scan_zero<T>();
-  for (i64 i = lane; i < n; i += 32) {
-    while (ld_acquire_u32(flag + i) != epoch) __nanosleep(20);
-    acc = acc + ld_cg_t(val + i);
-  }
+template <class T> __device__ __forceinline__ T shfl_idx_t(T v, int src) {
+  enum { W = sizeof(T) / 4 };
+  union { T t; u32 w[W]; } a, b;
+  a.t = v;
 #pragma unroll
-  for (int m = 16; m > 0; m >>= 1) acc = acc + shfl_xor_t(acc, m);
-  return acc;
+  for (int i = 0; i < W; ++i) b.w[i] = __shfl_sync(0xffffffffu, a.w[i], src);
+  return b.t;
 }
-
-// fixed-order sum over the CTA (shuffle tree per warp, warp totals added in warp order); result in every thread
-template <class T, int NW> __device__ __forceinline__ T scan_block_sum(T v, T *s_red) {
+template <class T> __device__ __forceinline__ T scan_zero() { return cvt<T>(0.0f); }
+template <> __device__ __forceinline__ u32 scan_zero<u32>() { return 0u; }
+// fixed-shape butterfly sum over a warp: every lane ends with the same bits (a + b == b + a exactly)
+template <class T> __device__ __forceinline__ T warp_tree_sum(T v) {
 #pragma unroll
   for (int m = 16; m > 0; m >>= 1) v = v + shfl_xor_t(v, m);
-  __syncthreads();                       // previous use of s_red is over
-  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
-  __syncthreads();
-  T tot = s_red[0];
-#pragma unroll
-  for (int w = 1; w < NW; ++w) tot = tot + s_red[w];
-  return tot;
+  return v;
+}
+
+// Carry of tile `ct` (of a row of `tpr` tiles) from the published totals, by ONE warp (all 32 lanes call it; every lane
+// returns the carry).  The caller has already published this tile's own total in agg[ct].  Three levels, all loads in
+// flight at once: running total at the start of the tile's supergroup (1024 tiles; chained, published by the last tile
+// of the previous supergroup) + totals of the groups (32 tiles) before the tile's own in that supergroup + totals of the
+// tiles before it in its group.  The last tile of a group publishes the group total, the last tile of a supergroup the
+// next running total.  Sums are fixed-shape shuffle trees: the carry does not depend on timing.
+// (A flat CUB-style look-back would walk back through every tile of the same WAVE here — the persistent grid starts a
+// wave of tiles together, none of them has a running total yet — one L2 round trip per 32 tiles: measured 5 us per tile.)
+template <class T>
+__device__ __forceinline__ T hier_carry(void *agg, void *gagg, void *sagg, i64 ct, i64 tpr, T total, u32 tag, int lane) {
+  const i64 g = ct >> 5, first = g << 5, sg = ct >> 10, gfirst = sg << 5;
+  const int n2 = (int)(ct - first), n1 = (int)(g - gfirst);
+  T a = scan_zero<T>(), b = scan_zero<T>(), c = scan_zero<T>();
+  if (lane < n2) a = ScanSlot<T>::wait(agg, first + lane, tag);
+  if (lane < n1) b = ScanSlot<T>::wait(gagg, gfirst + lane, tag);
+  if (lane == 0 && sg > 0) c = ScanSlot<T>::wait(sagg, sg, tag);
+  const T sa = warp_tree_sum(a), sb = warp_tree_sum(b);
+  c = shfl_idx_t(c, 0);
+  const bool last_tile = ct == tpr - 1;
+  if ((ct & 31) == 31 || last_tile) {
+    const T gt = sa + total;                       // this group's total
+    if (lane == 0) ScanSlot<T>::publish(gagg, g, gt, tag);
+    if (((g & 31) == 31) && !last_tile && lane == 0) ScanSlot<T>::publish(sagg, sg + 1, c + (sb + gt), tag);
+  }
+  return (c + sb) + sa;
 }
 
 // warp-per-row flavour for short rows: no shared memory, no barrier; a warp walks its rows in steps of 32 x U x V
@@ -2829,18 +2966,18 @@ template <class E, class OutT, int V, int U, bool UNIT>
 __device__ __forceinline__ void scan_inner_body_impl(const RedParams &p) {
   typedef typename E::value_type T;
   constexpr int NT = SCAN_NT, NW = NT / 32;
-  __shared__ T s_warp[U][NW];   // warp totals of every chunk, then their exclusive prefixes
-  __shared__ T s_chunk[U];      // chunk totals
-  __shared__ T s_red[NW + 1];   // mode TILES: scratch of the fixed-order block sums
+  __shared__ T s_warp[2][U][NW];   // warp totals of every chunk, double-buffered by tile parity: one barrier per tile (ROWS)
+  __shared__ T s_carry[2];         // TILES: the tile's carry, from warp 0
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const u32 epoch = p.scan_epoch;
   const i64 L = p.rsz[0];
   const i64 TILE = (i64)NT * V * U;
   const i64 tpr = (L + TILE - 1) / TILE;          // tiles per row
   const bool tiles_mode = p.splits > 1;
-  const i64 gpr = (tpr + SCAN_GROUP - 1) / SCAN_GROUP;
+  const i64 gpr = (tpr + 31) >> 5, spr = (tpr + 1023) >> 10;
   const i64 total_tiles = p.B * tpr;
   const i64 oinner = p.out_rs[0];
+  u32 tag = 0;
+  if (tiles_mode) tag = ((__ldcg(p.scan_ctl) & 0x3fffffffu) << 2) | 1u;
 
   const char *base[E::NL];
   i64 inner[E::NL];
@@ -2866,162 +3003,161 @@ __device__ __forceinline__ void scan_inner_body_impl(const RedParams &p) {
   // ---- first work item ----
   i64 cb, ct;   // current row, current tile of it
   i64 gid = blockIdx.x;   // TILES: global tile id, advanced by gridDim.x per trip
+  bool have = true;
   if (tiles_mode) {
-    if (gid >= total_tiles) return;
-    cb = gid / tpr;
+    have = gid < total_tiles;
+    cb = have ? gid / tpr : 0;
     ct = gid - cb * tpr;
   } else {
     cb = blockIdx.x;
     ct = 0;
-    if (cb >= p.B) return;
+    have = cb < p.B;
   }
-  OutT *orow = setup_row(cb);
-  typename E::template Regs<V> r[U];
-  bool full[U];
-#pragma unroll
-  for (int u = 0; u < U; ++u) {
-    const i64 j = ct * TILE + ((i64)u * NT + tid) * V;
-    full[u] = V == 1 ? (j < L) : (j + V <= L);
-    if (full[u]) E::template loadv<V, UNIT>(r[u], base, inner, j);
-  }
-  T carry = scan_zero<T>();
-
-  while (true) {
-    const i64 j0 = ct * TILE;
-    // ---- evaluate + thread-local scan of the tile whose loads were issued one trip ago ----
-    T x[U][V];
+  if (have) {
+    OutT *orow = setup_row(cb);
+    typename E::template Regs<V> r[U];
+    bool full[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const i64 j = j0 + ((i64)u * NT + tid) * V;
-      if (full[u]) {
+      const i64 j = ct * TILE + ((i64)u * NT + tid) * V;
+      full[u] = V == 1 ? (j < L) : (j + V <= L);
+      if (full[u]) E::template loadv<V, UNIT>(r[u], base, inner, j);
+    }
+    T carry = scan_zero<T>();
+    int par = 0;
+
+    while (true) {
+      const i64 j0 = ct * TILE;
+      // ---- evaluate + thread-local scan of the tile whose loads were issued one trip ago ----
+      T x[U][V];
 #pragma unroll
-        for (int v = 0; v < V; ++v) x[u][v] = E::template eval<V>(r[u], v, p.c);
-      } else {
+      for (int u = 0; u < U; ++u) {
+        const i64 j = j0 + ((i64)u * NT + tid) * V;
+        if (full[u]) {
 #pragma unroll
-        for (int v = 0; v < V; ++v) {
-          x[u][v] = scan_zero<T>();
-          if (V > 1 && j + v < L) {
-            typename E::template Regs<1> r1;
-            E::template loadv<1, false>(r1, base, inner, j + v);
-            x[u][v] = E::template eval<1>(r1, 0, p.c);
+          for (int v = 0; v < V; ++v) x[u][v] = E::template eval<V>(r[u], v, p.c);
+        } else {
+#pragma unroll
+          for (int v = 0; v < V; ++v) {
+            x[u][v] = scan_zero<T>();
+            if (V > 1 && j + v < L) {
+              typename E::template Regs<1> r1;
+              E::template loadv<1, false>(r1, base, inner, j + v);
+              x[u][v] = E::template eval<1>(r1, 0, p.c);
+            }
           }
         }
+#pragma unroll
+        for (int v = 1; v < V; ++v) x[u][v] = x[u][v - 1] + x[u][v];
       }
+      // ---- warp stage: inclusive scan of the thread totals, U chunks at once ----
+      T wexcl[U];
 #pragma unroll
-      for (int v = 1; v < V; ++v) x[u][v] = x[u][v - 1] + x[u][v];
-    }
-    // ---- warp stage: inclusive scan of the thread totals, U chunks at once ----
-    T wexcl[U];
+      for (int u = 0; u < U; ++u) {
+        T incl = x[u][V - 1];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      T incl = x[u][V - 1];
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const T o = shfl_up_t(incl, d);
-        if (lane >= d) incl = o + incl;
-      }
-      const T ex = shfl_up_t(incl, 1);
-      wexcl[u] = lane == 0 ? scan_zero<T>() : ex;
-      if (lane == 31) s_warp[u][warp] = incl;
-    }
-    __syncthreads();   // (A)
-    // ---- the NEXT tile's loads go out now: they fly while this tile goes through the CTA / grid stages ----
-    i64 nb, nt;
-    if (tiles_mode) {
-      const i64 g = gid + gridDim.x;
-      nb = g < total_tiles ? g / tpr : p.B;
-      nt = g - nb * tpr;
-    } else {
-      nb = ct + 1 < tpr ? cb : cb + gridDim.x;
-      nt = ct + 1 < tpr ? ct + 1 : 0;
-    }
-    const bool more = nb < p.B;
-    OutT *orow_next = orow;
-    bool full_next[U];
-    auto prefetch = [&]() {
-      if (more) {
-        if (nb != cb) orow_next = setup_row(nb);
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const i64 j = nt * TILE + ((i64)u * NT + tid) * V;
-          full_next[u] = V == 1 ? (j < L) : (j + V <= L);
-          if (full_next[u]) E::template loadv<V, UNIT>(r[u], base, inner, j);
+        for (int d = 1; d < 32; d <<= 1) {
+          const T o = shfl_up_t(incl, d);
+          if (lane >= d) incl = o + incl;
         }
+        const T ex = shfl_up_t(incl, 1);
+        wexcl[u] = lane == 0 ? scan_zero<T>() : ex;
+        if (lane == 31) s_warp[par][u][warp] = incl;
       }
-    };
-    // ROWS: right away.  TILES: only after this tile's total is published — every other tile's carry waits for that
-    // store, and anything queued in front of it delays them all (measured on 2^28 fp32: 0.62 ms late, 0.69 ms early;
-    // with release stores, which also wait for the thread's earlier loads, 1.28 vs 1.53).  scan_flags bit 0 forces early.
-    const bool early = !tiles_mode || (p.scan_flags & 1);
-    if (early) prefetch();
-    // ---- CTA stage: thread u turns chunk u's warp totals into exclusive prefixes and the chunk total ----
-    if (tid < U) {
-      T run = scan_zero<T>();
+      __syncthreads();   // (A)
+      // ---- CTA stage: every thread folds the warp totals it needs (broadcast reads, fixed order) ----
+      T wpre[U], ctot[U];
 #pragma unroll
-      for (int w = 0; w < NW; ++w) { const T v = s_warp[tid][w]; s_warp[tid][w] = run; run = run + v; }
-      s_chunk[tid] = run;
-    }
-    __syncthreads();   // (B)
-    T ctot[U];
+      for (int u = 0; u < U; ++u) {
+        T run = scan_zero<T>();
+        wpre[u] = run;
 #pragma unroll
-    for (int u = 0; u < U; ++u) ctot[u] = s_chunk[u];
-    if (tiles_mode) {
-      // ---- grid stage: publish, close the group if last, gather the carry (all threads fetch in parallel) ----
-      T total = ctot[0];
-#pragma unroll
-      for (int u = 1; u < U; ++u) total = total + ctot[u];
-      const i64 g = ct / SCAN_GROUP, first = g * SCAN_GROUP;
-      const i64 gcount = (tpr - first) < SCAN_GROUP ? (tpr - first) : SCAN_GROUP;
-      // (4-byte values live in 8-byte slots, see ScanSlot)
-      T *agg = (T *)((char *)p.scan_agg + (size_t)(cb * tpr) * 8);
-      T *gagg = (T *)((char *)p.scan_gagg + (size_t)(cb * gpr) * 8);
-      u32 *aflag = p.scan_agg_flag + cb * tpr, *gflag = p.scan_gagg_flag + cb * gpr;
-      if (tid == 0) ScanSlot<T>::publish(agg, aflag, ct, total, epoch);
-      if (!early) prefetch();
-      const i64 n1 = g, n2 = ct - first;
-      if (ct == first + gcount - 1) {
-        // last tile of its group: the group's total goes out first (it needs the group's own tiles only), then the
-        // totals of the earlier groups are gathered for this tile's carry
-        T a = scan_zero<T>();
-        for (i64 i = tid; i < n2; i += NT) a = a + ScanSlot<T>::wait(agg, aflag, first + i, epoch);
-        const T stiles = scan_block_sum<T, NW>(a, s_red);
-        if (tid == 0) ScanSlot<T>::publish(gagg, gflag, g, stiles + total, epoch);
-        a = scan_zero<T>();
-        for (i64 i = tid; i < n1; i += NT) a = a + ScanSlot<T>::wait(gagg, gflag, i, epoch);
-        carry = scan_block_sum<T, NW>(a, s_red) + stiles;
+        for (int w = 0; w < NW; ++w) {
+          if (w == warp) wpre[u] = run;
+          run = run + s_warp[par][u][w];
+        }
+        ctot[u] = run;
+      }
+      // ---- where the next tile is ----
+      i64 nb, nt;
+      if (tiles_mode) {
+        const i64 g = gid + gridDim.x;
+        nb = g < total_tiles ? g / tpr : p.B;
+        nt = g - nb * tpr;
       } else {
-        // carry = (totals of the groups before this one) + (totals of the tiles before this one in its group)
-        T acc = scan_zero<T>();
-        for (i64 i = tid; i < n1 + n2; i += NT)
-          acc = acc + (i < n1 ? ScanSlot<T>::wait(gagg, gflag, i, epoch) : ScanSlot<T>::wait(agg, aflag, first + (i - n1), epoch));
-        carry = scan_block_sum<T, NW>(acc, s_red);
+        nb = ct + 1 < tpr ? cb : cb + gridDim.x;
+        nt = ct + 1 < tpr ? ct + 1 : 0;
+      }
+      const bool more = nb < p.B;
+      OutT *orow_next = orow;
+      bool full_next[U];
+      auto prefetch = [&]() {   // the NEXT tile's loads fly while this tile goes through its grid stage and its stores
+        if (more) {
+          if (nb != cb) orow_next = setup_row(nb);
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const i64 j = nt * TILE + ((i64)u * NT + tid) * V;
+            full_next[u] = V == 1 ? (j < L) : (j + V <= L);
+            if (full_next[u]) E::template loadv<V, UNIT>(r[u], base, inner, j);
+          }
+        }
+      };
+      if (tiles_mode) {
+        // ---- grid stage: publish first (every later tile waits for that store), then gather the carry ----
+        T total = ctot[0];
+#pragma unroll
+        for (int u = 1; u < U; ++u) total = total + ctot[u];
+        char *agg = (char *)p.scan_agg + (size_t)(cb * tpr) * ScanSlot<T>::STRIDE;
+        char *gagg = (char *)p.scan_gagg + (size_t)(cb * gpr) * ScanSlot<T>::STRIDE;
+        char *sagg = (char *)p.scan_sagg + (size_t)(cb * spr) * ScanSlot<T>::STRIDE;
+        if (tid == 0) ScanSlot<T>::publish(agg, ct, total, tag);
+        prefetch();
+        if (warp == 0) {
+          const T cr = hier_carry<T>(agg, gagg, sagg, ct, tpr, total, tag, lane);
+          if (lane == 0) s_carry[par] = cr;
+        }
+        __syncthreads();   // (B)
+        carry = s_carry[par];
+      } else {
+        prefetch();
+      }
+      // ---- finish: carry + chunk prefix + warp prefix + lane prefix + local scan, one vector store ----
+      T cpre = carry;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const i64 j = j0 + ((i64)u * NT + tid) * V;
+        const T pre = (cpre + wpre[u]) + wexcl[u];
+        Vec<OutT, V> o;
+#pragma unroll
+        for (int v = 0; v < V; ++v) o.v[v] = cvt<OutT>(pre + x[u][v]);
+        if (V > 1 && j + V <= L && oinner == 1 && p.tx) StBytes<(int)sizeof(OutT) * V>::st(orow + j, &o);
+        else {
+#pragma unroll
+          for (int v = 0; v < V; ++v) if (j + v < L) orow[(j + v) * oinner] = o.v[v];
+        }
+        cpre = cpre + ctot[u];
+      }
+      if (!more) break;
+      carry = (!tiles_mode && nb == cb) ? cpre : scan_zero<T>();
+      cb = nb;
+      ct = nt;
+      gid += gridDim.x;
+      orow = orow_next;
+#pragma unroll
+      for (int u = 0; u < U; ++u) full[u] = full_next[u];
+      par ^= 1;
+    }
+  }
+  if (tiles_mode) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    // exit ticket: the last CTA out opens the next epoch (every slot of this launch is stale from then on)
+    if (tid == 0) {
+      __threadfence();
+      if (atomicInc(p.scan_ctl + 1, gridDim.x - 1) == gridDim.x - 1) {
+        u32 e = (__ldcg(p.scan_ctl) + 1u) & 0x3fffffffu;
+        *(volatile u32 *)p.scan_ctl = e ? e : 1u;
       }
     }
-    // ---- finish: carry + chunk prefix + warp prefix + lane prefix + local scan, one vector store ----
-    T cpre = carry;
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const i64 j = j0 + ((i64)u * NT + tid) * V;
-      const T pre = (cpre + s_warp[u][warp]) + wexcl[u];
-      Vec<OutT, V> o;
-#pragma unroll
-      for (int v = 0; v < V; ++v) o.v[v] = cvt<OutT>(pre + x[u][v]);
-      if (V > 1 && j + V <= L && oinner == 1 && p.tx) StBytes<(int)sizeof(OutT) * V>::st(orow + j, &o);
-      else {
-#pragma unroll
-        for (int v = 0; v < V; ++v) if (j + v < L) orow[(j + v) * oinner] = o.v[v];
-      }
-      cpre = cpre + ctot[u];
-    }
-    if (!more) break;
-    carry = (!tiles_mode && nb == cb) ? cpre : scan_zero<T>();
-    cb = nb;
-    ct = nt;
-    gid += gridDim.x;
-    orow = orow_next;
-#pragma unroll
-    for (int u = 0; u < U; ++u) full[u] = full_next[u];
-    __syncthreads();   // (C) s_warp / s_chunk are reused by the next trip
   }
 }
 
@@ -3062,7 +3198,7 @@ template <class T> __device__ __forceinline__ bool sel_test(T x, int op, T c) {
     default: return x >= c;
   }
 }
-// branch-free form for the opt-in fast instances: category of x against c (less / greater / equal / unordered) indexes
+// branch-free form (single-pass kernel): category of x against c (less / greater / equal / unordered) indexes
 // a 4-bit acceptance mask (LT 0001, GT 0010, EQ 0100, NEQ 1011, LTE 0101, GTE 0110)
 __device__ __forceinline__ u32 sel_mask(int op) { return (0x65B421u >> (4 * op)) & 0xFu; }
 template <class T> __device__ __forceinline__ u32 sel_flag(T x, T c, u32 mask) {
@@ -3132,38 +3268,9 @@ __device__ __forceinline__ u32 sel_eval(const EwParams &p, i64 j0, typename E::v
   return flags;
 }
 
-// 1-D unit-stride operands only (host rule for the fast instances): no N-D decomposition, no per-element switch
-template <class E, int V>
-__device__ __forceinline__ u32 sel_eval_fast(const EwParams &p, const char *const *base, const i64 *inner, i64 j0, typename E::value_type thr,
-                                             u32 mask, typename E::value_type *vals) {
-  typedef typename E::value_type T;
-  u32 flags = 0;
-  if (j0 + V <= p.N) {
-    typename E::template Regs<V> r;
-    E::template loadv<V, true>(r, base, inner, j0);
-#pragma unroll
-    for (int v = 0; v < V; ++v) {
-      vals[v] = E::template eval<V>(r, v, p.c);
-      flags |= sel_flag<T>(vals[v], thr, mask) << v;
-    }
-  } else {
-#pragma unroll
-    for (int v = 0; v < V; ++v) {
-      if (j0 + v < p.N) {
-        typename E::template Regs<1> r;
-        E::template loadv<1, false>(r, base, inner, j0 + v);
-        vals[v] = E::template eval<1>(r, 0, p.c);
-        flags |= sel_flag<T>(vals[v], thr, mask) << v;
-      }
-    }
-  }
-  return flags;
-}
-
 template <class E, class OutT, int V, int MODE_IN>
 __device__ __forceinline__ void select_body(const EwParams &p) {
-  constexpr bool FAST = MODE_IN >= 3;       // opt-in instances (MXB_SEL_FAST=1): modes 3 / 4 / 5 = fast count / values / indices
-  constexpr int MODE = MODE_IN % 3;
+  constexpr int MODE = MODE_IN;             // 0 count (+ in-launch scan of the CTA totals), 1 scatter values, 2 scatter flat indices
   pdl_prologue();
   typedef typename E::value_type T;
   constexpr int NT = SEL_NT, U = SEL_U, NW = NT / 32;
@@ -3177,11 +3284,6 @@ __device__ __forceinline__ void select_body(const EwParams &p) {
   // both passes give CTA c the SAME contiguous run of tiles, so only one total per CTA crosses the grid
   const i64 tpc = (ntiles + gridDim.x - 1) / gridDim.x;
   const i64 t0 = (i64)blockIdx.x * tpc, t1 = (t0 + tpc < ntiles) ? (t0 + tpc) : ntiles;
-  const char *fbase[E::NL];
-  i64 finner[E::NL];
-#pragma unroll
-  for (int k = 0; k < E::NL; ++k) { fbase[k] = (const char *)p.leaf[k].ptr; finner[k] = p.leaf[k].bs[0]; }
-  const u32 fmask = sel_mask(p.sel_op);
 
   if (MODE == 0) {
     u32 c = 0;   // per thread: at most tpc * U * V elements
@@ -3190,7 +3292,7 @@ __device__ __forceinline__ void select_body(const EwParams &p) {
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const i64 j0 = tile * TILE + ((i64)u * NT + tid) * V;
-        c += (u32)__popc(FAST ? sel_eval_fast<E, V>(p, fbase, finner, j0, thr, fmask, vals) : sel_eval<E, V>(p, j0, thr, vals));
+        c += (u32)__popc(sel_eval<E, V>(p, j0, thr, vals));
       }
     }
     c = __reduce_add_sync(0xffffffffu, c);
@@ -3240,7 +3342,7 @@ __device__ __forceinline__ void select_body(const EwParams &p) {
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const i64 j0 = tile * TILE + ((i64)u * NT + tid) * V;
-      flags[u] = FAST ? sel_eval_fast<E, V>(p, fbase, finner, j0, thr, fmask, vals[u]) : sel_eval<E, V>(p, j0, thr, vals[u]);
+      flags[u] = sel_eval<E, V>(p, j0, thr, vals[u]);
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -3272,6 +3374,156 @@ __device__ __forceinline__ void select_body(const EwParams &p) {
       pos += chunk;
     }
     __syncthreads();   // s_w is reused by the next tile
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// S1p: select1p — find / find_idx in ONE pass: every element is read once, the selected ones are written once.
+// (reference: cub::DeviceSelect::If behind find_impl / find_idx_impl, transforms/cub.h:912-1010,2609-2790.)
+// A tile is 256 threads x 4 chunks x V elements of the flat index space; tiles are dealt round-robin to a grid whose
+// CTAs are all resident (cooperative launch), so a tile only ever waits for tiles that are running or done.
+//   1. the tile's values sit in registers (loads issued one tile ahead); branch-free predicate -> flag bits;
+//   2. ranks inside the tile: the four chunk counts of a thread travel packed in one word (a byte each, a warp's
+//      inclusive sum is <= 128) through ONE shuffle scan; warp totals meet in shared memory (one barrier);
+//   3. the tile publishes its count and warp 0 gathers the tile's output offset from the published counts of the tiles /
+//      groups / supergroup before it (hier_carry, the same three-level exchange as the TILES-mode scan): one L2 round
+//      trip when the neighbours are done.  The output is deterministic and stable;
+//   4. meanwhile the other warps compact the selected values (or flat indices) into shared memory by rank; after the
+//      second barrier the CTA copies the compacted run to out[excl ...] with full-sector stores.
+// Shared-memory staging and the per-warp totals are double-buffered by tile parity: two barriers per tile.
+// Status words carry the launch epoch, so nothing is cleared between launches.
+// ------------------------------------------------------------------------------------------------
+template <class E, class OutT, int V, int MODE>   // MODE 1: values, 2: flat indices
+__device__ __forceinline__ void select1p_body(const EwParams &p) {
+  pdl_prologue();
+  typedef typename E::value_type T;
+  typedef typename E::template Regs<V> R;
+  constexpr int NT = 256, U = 4, NW = NT / 32;
+  extern __shared__ __align__(16) unsigned char sel_smem[];
+  OutT *stage = (OutT *)sel_smem;                      // [2][NT * U * V]
+  __shared__ u32 s_w[2][NW];
+  __shared__ u32 s_excl[2];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const i64 TILE = (i64)NT * V * U;
+  const i64 ntiles = (p.N + TILE - 1) / TILE;
+  const T thr = SelThr<T>::get(p);
+  const u32 fmask = sel_mask(p.sel_op);
+  const u32 epoch = __ldcg(p.sel_epoch) & 0x3fffffffu;
+  const u32 tag = (epoch << 2) | 1u;
+  // slots: tile counts, group counts (32 tiles), running counts at supergroup starts (1024 tiles)
+  unsigned long long *agg = p.sel_status, *gagg = agg + ntiles, *sagg = gagg + ((ntiles + 31) >> 5);
+  const char *base[E::NL];
+  i64 inner[E::NL];
+#pragma unroll
+  for (int k = 0; k < E::NL; ++k) { base[k] = (const char *)p.leaf[k].ptr; inner[k] = p.leaf[k].bs[0]; }
+  const bool unit = p.all_unit != 0;
+
+  R r[U];
+  auto issue = [&](i64 tile) {     // vector loads of the full vectors of `tile`; ragged ends are fetched at evaluation time
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const i64 j0 = tile * TILE + ((i64)u * NT + tid) * V;
+      if (j0 + V <= p.N) {
+        if (unit) E::template loadv<V, true>(r[u], base, inner, j0);
+        else E::template loadv<V, false>(r[u], base, inner, j0);
+      }
+    }
+  };
+  i64 tile = blockIdx.x;
+  if (tile < ntiles) issue(tile);
+  int par = 0;
+  for (; tile < ntiles; tile += gridDim.x, par ^= 1) {
+    const i64 t0 = tile * TILE;
+    T vals[U][V];
+    u32 flags[U];
+    u32 packed = 0;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const i64 j0 = t0 + ((i64)u * NT + tid) * V;
+      u32 f = 0;
+      if (j0 + V <= p.N) {
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          vals[u][v] = E::template eval<V>(r[u], v, p.c);
+          f |= sel_flag<T>(vals[u][v], thr, fmask) << v;
+        }
+      } else {
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          if (j0 + v < p.N) {
+            typename E::template Regs<1> r1;
+            E::template loadv<1, false>(r1, base, inner, j0 + v);
+            vals[u][v] = E::template eval<1>(r1, 0, p.c);
+            f |= sel_flag<T>(vals[u][v], thr, fmask) << v;
+          }
+        }
+      }
+      flags[u] = f;
+      packed |= (u32)__popc(f) << (8 * u);
+    }
+    // the next tile's loads fly while this one goes through its barriers and its look-back
+    if (tile + gridDim.x < ntiles) issue(tile + gridDim.x);
+    // ranks inside the warp: one shuffle scan over the four packed byte counters
+    u32 incl = packed;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const u32 o = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += o;
+    }
+    const u32 wexcl = incl - packed;
+    if (lane == 31) s_w[par][warp] = incl;
+    __syncthreads();   // (A)
+    // warps before mine and the chunk totals, two 16-bit lanes per word (8 warps x 128 fit easily)
+    u32 blo = 0, bhi = 0, tlo = 0, thi = 0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+      const u32 x = s_w[par][w];
+      const u32 lo = x & 0x00ff00ffu, hi = (x >> 8) & 0x00ff00ffu;
+      tlo += lo; thi += hi;
+      if (w < warp) { blo += lo; bhi += hi; }
+    }
+    const u32 tot[4] = {tlo & 0xffffu, thi & 0xffffu, tlo >> 16, thi >> 16};
+    const u32 bef[4] = {blo & 0xffffu, bhi & 0xffffu, blo >> 16, bhi >> 16};
+    const u32 total = tot[0] + tot[1] + tot[2] + tot[3];
+    if (tid == 0) ScanSlot<u32>::publish(agg, tile, total, tag);   // first thing: every later tile waits for this store
+    // compact the selected elements into shared memory by rank
+    OutT *stg = stage + (size_t)par * TILE;
+    u32 coff = 0;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      u32 pos = coff + bef[u] + ((wexcl >> (8 * u)) & 0xffu);
+      const i64 j0 = t0 + ((i64)u * NT + tid) * V;
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        if ((flags[u] >> v) & 1u) { stg[pos] = MODE == 1 ? cvt<OutT>(vals[u][v]) : (OutT)(j0 + v); ++pos; }
+      }
+      coff += tot[u];
+    }
+    if (warp == 0) {
+      const u32 excl = hier_carry<u32>(agg, gagg, sagg, tile, ntiles, total, tag, lane);
+      if (lane == 0) {
+        s_excl[par] = excl;
+        if (tile == ntiles - 1) {
+          const unsigned long long all = (unsigned long long)excl + total;
+          *p.sel_total = all > 0x7fffffffull ? 0x7fffffff : (int)all;
+        }
+      }
+    }
+    __syncthreads();   // (B) staging complete, running total known
+    const i64 excl = (i64)s_excl[par];
+    OutT *dst = (OutT *)p.out.ptr + excl;
+    const i64 room = p.sel_cap - excl;     // elements beyond the capacity are counted, not written
+    for (u32 i = tid; i < total; i += NT)
+      if ((i64)i < room) dst[i] = stg[i];
+  }
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  // exit ticket: the last CTA out opens the next epoch (every status word of this launch is stale from then on)
+  if (tid == 0) {
+    __threadfence();
+    if (atomicInc(p.sel_ticket, gridDim.x - 1) == gridDim.x - 1) {
+      const u32 e = (epoch + 1u) & 0x3fffffffu;
+      *(volatile u32 *)p.sel_epoch = e ? e : 1u;   // epoch 0 is what freshly zeroed status words carry: never used
+    }
   }
 }
 

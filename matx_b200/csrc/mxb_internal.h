@@ -42,6 +42,7 @@ struct KernelSpec {
   int out_dtype = 0;
   int V = 1, U = 1;
   int team = 0;       // FAM_RED_INNER: 0 = CTA per row, 1 = warp per row; FAM_VAR_REG: vectors per thread (IPT)
+  int minb = 0;       // > 0: minimum resident CTAs per SM asked of the compiler (__launch_bounds__ second argument)
 };
 
 // unique key of (expression, spec); also yields the extern "C" symbol name
@@ -96,6 +97,7 @@ mxb_expr_t prog_vector_add(int dtype);     // a + b            (bench/00_operato
 }  // namespace mxbh
 
 namespace mxbh {
-int jit_launch(const void *fn, unsigned grid, unsigned block, unsigned smem, void *stream, void *params, std::string *err);
+int jit_launch(const void *fn, unsigned grid, unsigned block, unsigned smem, void *stream, void *params, std::string *err, bool pdl = true, bool coop = false);
+int jit_occupancy(const void *fn, unsigned block, unsigned smem);   // resident CTAs per SM of a JIT-built kernel (0 = unknown)
 int jit_compile_only(const std::string &source, std::string *log);
 }  // namespace mxbh

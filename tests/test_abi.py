@@ -132,10 +132,10 @@ def test_outer_tma_kernel_compiles_for_sm100a(npdt, dt, op):
     assert st == A.OK, (A.lib.mxb_last_error(), log.value.decode()[:2000])
 
 
-@pytest.mark.parametrize("team,out_dt", [(0, A.F32), (1, A.F32), (2, A.I32), (2, A.I64), (3, A.F32), (4, A.F32), (5, A.I64)])
+@pytest.mark.parametrize("team,out_dt", [(0, A.F32), (1, A.F32), (2, A.I32), (2, A.I64), (3, A.F32), (3, A.F64), (4, A.I32), (4, A.I64)])
 def test_select_kernels_compile_for_sm100a(team, out_dt):
     """Family 12 (find / find_idx): count pass, value scatter, index scatter — of an expression operand, vector and scalar;
-    teams 3..5 are the opt-in fast instances (MXB_SEL_FAST=1)."""
+    teams 3 / 4 are the single-pass look-back kernel (values / flat indices)."""
     a = np_tensor(np.zeros(64, np.float32))
     e = mx.lower_elementwise(mx.sqrt(mx.abs(a)) * 2.0 - 1.0)
     for V in (4, 1):

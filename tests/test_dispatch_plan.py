@@ -29,8 +29,8 @@ def geom(s):
 
 def test_headline_config_is_a_split_row_reduction_on_a_persistent_grid(plans):
     k = plans["c2.sum"]
-    assert k.startswith("red_inner|") and "|sum|f32|V4|U4|T0|aot" in k, k
-    assert geom(k) == {"grid": 148 * 8, "block": 256, "smem": 0}, k        # 8 CTAs per SM on 148 SMs, one launch
+    assert k.startswith("red_inner|") and "|sum|f32|V8|U4|T0|aot" in k, k          # 32-byte loads, four in flight
+    assert geom(k) == {"grid": 148 * 4, "block": 256, "smem": 0}, k        # one resident wave (4 CTAs per SM at 64 registers), chunks dealt dynamically
     assert "|argmax|" in plans["c2.argmax"] and plans["c2.argmax"].startswith("red_inner|")
 
 
@@ -76,6 +76,7 @@ def test_elementwise_scan_and_select_families(plans):
     assert plans["ew_tr.permute"].startswith("ew_tr|")
     assert plans["scan.rows"].startswith("scan|")
     k = plans["find.values"]
-    assert k.startswith("select|") and "|f32|V4|U4|T1|aot" in k and geom(k)["grid"] == 148 * 8, k
+    # 1-D view: the single-pass look-back kernel, one resident wave (3 CTAs per SM), two staging buffers of one tile each
+    assert k.startswith("select|") and "|f32|V4|U4|T3|aot" in k and geom(k) == {"grid": 148 * 3, "block": 256, "smem": 2 * 4096 * 4}, k
     k = plans["find.strided_idx"]
-    assert k.startswith("select|") and "|i32|V1|U4|T2|" in k, k    # a strided view does not collapse: scalar walk, index scatter
+    assert k.startswith("select|") and "|i32|V1|U4|T4|" in k, k    # every other column of a matrix collapses to ONE strided dim: scalar walk, single pass

@@ -127,19 +127,59 @@ def test_error_convention():
     assert ei.value.status == A.ERR_NOT_SUPPORTED
 
 
-@pytest.mark.skipif(__import__("os").environ.get("MXB_TEST_OPT_IN") != "1", reason="opt-in instances (MXB_SEL_FAST=1), not yet validated on a GPU")
 @pytest.mark.parametrize("sel", range(6))
-def test_fast_instances_opt_in(oracle, monkeypatch, sel):
-    monkeypatch.setenv("MXB_SEL_FAST", "1")
+def test_single_pass_and_two_pass_kernels_agree_with_the_oracle(oracle, monkeypatch, sel):
+    """1-D views take the single-pass look-back kernel (T3 values / T4 indices); MXB_SEL_TWO_PASS=1 forces the count +
+    scatter pair that serves N-D views.  Both against the oracle, NaN included (NEQ accepts it, ordered comparisons do not)."""
     rng = np.random.default_rng(300 + sel)
-    for n in (1, 4097, (1 << 20) + 3):
+    for n in (1, 4097, 3 * 4096, (1 << 20) + 3):
         x = (rng.integers(0, 9, n) * 0.25).astype(np.float32)
-        x[:: 7] = np.nan if sel == 3 else x[:: 7]          # NEQ accepts NaN, the ordered comparisons reject it
-        for want_idx in (False, True):
-            res = run_find(oracle, lambda t: t, x, SEL[sel](1.0), want_idx)
-            got, n_got, want, wn, k = res
-            assert n_got == wn and np.array_equal(got[:wn], want[:wn], equal_nan=True), k
-            assert "|T%d|" % (5 if want_idx else 4) in k, k
+        x[:: 7] = np.nan if sel == 3 else x[:: 7]
+        for two_pass in ("0", "1"):
+            monkeypatch.setenv("MXB_SEL_TWO_PASS", two_pass)
+            for want_idx in (False, True):
+                got, n_got, want, wn, k = run_find(oracle, lambda t: t, x, SEL[sel](1.0), want_idx)
+                assert n_got == wn and np.array_equal(got[:wn], want[:wn], equal_nan=True), k
+                want_t = (2 if want_idx else 1) if two_pass == "1" else (4 if want_idx else 3)
+                assert "|T%d|" % want_t in k, k
+
+
+def test_single_pass_many_tiles_and_repeated_launches(oracle):
+    """More tiles than resident CTAs (look-back across several probes of 32 tiles), all-selected and none-selected tiles,
+    and back-to-back launches on one handle (the status words are epoch-coded: nothing is cleared in between)."""
+    import torch
+    ex = mx.CudaExecutor()
+    n = (1 << 24) + 12345
+    rng = np.random.default_rng(77)
+    x = rng.random(n, dtype=np.float32)
+    x[: 1 << 20] = 2.0                       # 256 tiles in a row with everything selected
+    x[1 << 22: (1 << 22) + (1 << 21)] = -1.0  # 512 tiles with nothing selected
+    dx = torch.from_numpy(x).cuda()
+    for rep, thr in enumerate((0.5, 0.999, 0.5, 0.0, 1.5, 0.25)):
+        out = torch.full((n,), -7.0, device="cuda")
+        nf = torch.zeros((), dtype=torch.int32, device="cuda")
+        mx.mtie(mx.make_tensor(out), mx.make_tensor(nf)).set(mx.find(mx.make_tensor(dx), mx.GT(thr))).run(ex)
+        ex.sync()
+        want = x[x > np.float32(thr)]
+        assert "|T3|" in ex.last_kernel() and nf.item() == want.size, (rep, ex.last_kernel(), nf.item(), want.size)
+        assert np.array_equal(out[: want.size].cpu().numpy(), want) and bool((out[want.size:] == -7.0).all().item())
+        idx = torch.full((n,), -7, dtype=torch.int64, device="cuda")
+        mx.mtie(mx.make_tensor(idx), mx.make_tensor(nf)).set(mx.find_idx(mx.make_tensor(dx), mx.LTE(thr))).run(ex)
+        ex.sync()
+        wi = np.nonzero(x <= np.float32(thr))[0]
+        assert nf.item() == wi.size and np.array_equal(idx[: wi.size].cpu().numpy(), wi)
+
+
+def test_output_capacity_is_respected_by_the_single_pass_kernel():
+    import torch
+    ex = mx.CudaExecutor()
+    x = torch.arange(100000, device="cuda", dtype=torch.float32)
+    out = torch.full((1000 + 64,), -7.0, device="cuda")
+    nf = torch.zeros((), dtype=torch.int32, device="cuda")
+    mx.mtie(mx.make_tensor(out[:1000]), mx.make_tensor(nf)).set(mx.find(mx.make_tensor(x), mx.GTE(10.0))).run(ex)
+    ex.sync()
+    assert nf.item() == 100000 - 10                                   # counted in full ...
+    assert torch.equal(out[:1000], x[10:1010]) and bool((out[1000:] == -7.0).all().item())   # ... written up to the capacity
 
 
 def test_full_size_against_masked_select():

@@ -1,5 +1,5 @@
-"""find / find_idx over sizes, selectivities and dtypes, default kernels against the opt-in fast instances
-(MXB_SEL_FAST=1), with torch.masked_select beside it.  Development tool, run under gpurun."""
+"""find / find_idx over sizes, selectivities and dtypes: the single-pass look-back kernel (fast = 1) against the two-pass
+count + scatter pair (MXB_SEL_TWO_PASS=1, fast = 0), with torch.masked_select beside it.  Development tool, run under gpurun."""
 import json
 import os
 import sys
@@ -22,7 +22,7 @@ for logn in (20, 24, 28):
         want = torch.masked_select(x, x > thr)
         ms_t, _ = bc._time(ex, lambda: torch.masked_select(x, x > thr), iters=5, warm=2)
         for fast in ("0", "1"):
-            os.environ["MXB_SEL_FAST"] = fast
+            os.environ["MXB_SEL_TWO_PASS"] = "0" if fast == "1" else "1"
             for name, fn in (("find", lambda: mx.mtie(to, tn).set(mx.find(tx, mx.GT(thr))).run(ex)),
                              ("find_idx", lambda: mx.mtie(ti, tn).set(mx.find_idx(tx, mx.GT(thr))).run(ex))):
                 try:
@@ -35,6 +35,6 @@ for logn in (20, 24, 28):
                                       "torch_masked_select_ms": round(ms_t, 4), "kernel": ex.last_kernel()}), flush=True)
                 except Exception as exc:  # noqa: BLE001
                     print(json.dumps({"n": n, "op": name, "fast": int(fast), "error": str(exc)[:200]}), flush=True)
-        os.environ.pop("MXB_SEL_FAST", None)
+        os.environ.pop("MXB_SEL_TWO_PASS", None)
     del x, out, idx
     torch.cuda.empty_cache()
