@@ -20,6 +20,9 @@
  *   mxb_cumsum       <- cumsum_impl + ExecPrefixScanEx        include/matx/transforms/cub.h:2367-2395,375-408
  *   mxb_find         <- find_impl / find_idx_impl + ExecSelect / ExecSelectIndex
  *                                                             include/matx/transforms/cub.h:2609-2625,2705-2721,912-1010
+ *   mxb_hist         <- hist_impl + ExecHistEven              include/matx/transforms/cub.h:2464-2503,320-359
+ *   mxb_sort         <- sort_impl + ExecSort                  include/matx/transforms/cub.h:2145-2190,428-560
+ *   mxb_unique       <- unique_impl + ExecUnique              include/matx/transforms/cub.h:2796-2842,1052-1110
  *   mxb_create / mxb_destroy / mxb_set_stream
  *                    <- cudaExecutor ctor / getStream         include/matx/executors/cuda.h:60-82
  *   mxb_sync         <- CudaExecutorBase::sync                include/matx/executors/cuda_executor_common.h:137
@@ -205,6 +208,24 @@ typedef enum {
 int mxb_find(mxb_handle_t h, const mxb_expr_t *expr, int select_op, double threshold, const mxb_out_t *out,
              const mxb_out_t *count_out, int want_indices);
 
+/* out(b..., k) = number of elements x of row b of `expr` (its last dim) with lower <= x < upper that fall in bin k of
+ * `bins = out->size[last]` even-width bins (reference: hist_impl, transforms/cub.h:2464-2503 -> ExecHistEven :320-359,
+ * cub::DeviceHistogram::HistogramEven with num_levels = bins + 1; the bin arithmetic is CUB's: int((x - lower) * (T(bins) /
+ * T(upper - lower))) for floating types, ((x - lower) * bins) / (upper - lower) in 64-bit for integers).  `out` is MXB_I32,
+ * same leading sizes as `expr`, bins of a row contiguous.  One memset + one launch. */
+int mxb_hist(mxb_handle_t h, const mxb_expr_t *expr, double lower, double upper, const mxb_out_t *out);
+
+/* Sort every row (last dim) of `expr` into `out`, ascending (descending != 0: descending) — keys only (reference:
+ * sort_impl, transforms/cub.h:2145-2190 -> cub::DeviceRadixSort::SortKeys, per row for rank > 1; the HostExecutor
+ * overload is std::sort per row).  fp32 / fp64 / int32 / int64; `out` contiguous, the operand's value type.  A
+ * non-contiguous view or an expression is evaluated into `out` first (the reference copies as well). */
+int mxb_sort(mxb_handle_t h, const mxb_expr_t *expr, const mxb_out_t *out, int descending);
+
+/* out[0 .. n) = the distinct values of the rank-1 `expr` in ascending order, *count_out = n (reference: unique_impl,
+ * transforms/cub.h:2796-2842: sort + cub::DeviceSelect::Unique; the HostExecutor overload is std::sort + std::unique).
+ * Elements beyond out->size[0] are counted but not written. */
+int mxb_unique(mxb_handle_t h, const mxb_expr_t *expr, const mxb_out_t *out, const mxb_out_t *count_out);
+
 /* ---- multi-GPU (no counterpart in the reference) -------------------------------- */
 /* Slab-sharded full-tensor reductions: each rank reduces its slab with mxb_reduce_partial into a
  * 32-byte device record, the host exchanges the records with ONE collective (NCCL all-gather of
@@ -227,7 +248,12 @@ int mxb_reduce_finalize(mxb_handle_t h, int reduce_op, int32_t value_dtype, cons
  * counters of all ranks and folds all statements' records in rank order.  No NCCL call, no host round trip, graph
  * capturable.  The host maps the buffers once (CUDA IPC): rec[r] / flag[r] point at rank r's buffers as seen from
  * THIS device; buffers are zero-initialised and sized MXB_EXCHANGE_REC_BYTES(world) / MXB_EXCHANGE_FLAG_BYTES(world);
- * epoch is a zeroed local u32.  Records are double-buffered by step parity, so a fast rank can run one step ahead. */
+ * epoch is a zeroed LOCAL control block of MXB_EXCHANGE_CTL_BYTES (completed exchanges, a sticky error word, and how many
+ * records of every source rank have been consumed: steps with different n_items may share one exchange).  Records are
+ * double-buffered by step parity, so a fast rank can run one step ahead.  A peer that does not deliver within 5 s makes
+ * the fold write NaN / -1 into that step's outputs and set the error word: mxb_exchange_check (which synchronises the
+ * handle's stream) then returns MXB_ERR_CUDA. */
+#define MXB_EXCHANGE_CTL_BYTES 128
 #define MXB_MAX_PEERS 8
 #define MXB_MAX_ITEMS 8
 #define MXB_EXCHANGE_REC_BYTES(world) (2 * (world) * MXB_MAX_ITEMS * MXB_PARTIAL_BYTES)
@@ -250,6 +276,7 @@ int mxb_reduce_partial_push(mxb_handle_t h, int reduce_op, const mxb_expr_t *exp
                             const mxb_peers_t *peers, int item, int n_items);
 int mxb_exchange_finalize(mxb_handle_t h, const mxb_peers_t *peers, const mxb_fold_item_t *items, int n_items,
                           int64_t global_count);
+int mxb_exchange_check(mxb_handle_t h, const mxb_peers_t *peers);
 /* Exchange-buffer plumbing (CUDA IPC, one box).  mxb_exchange_alloc: cudaMalloc + zero `bytes` on the handle's
  * device and export a 64-byte IPC handle; the host passes the handles around (any transport) and every other rank
  * maps them with mxb_exchange_open from ITS device (peer access is enabled as part of the mapping).  The owner

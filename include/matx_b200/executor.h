@@ -26,13 +26,16 @@
 //
 // Lowered node types: tensor views (any strides: permuted / sliced / cloned views are just strides), arithmetic
 // scalars, matxBinaryOp, matxUnaryOp with the functors of operators/scalar_ops.h:434-503, PermuteOp, CloneOp, DiagOp
-// (so trace(x) = sum(diag(x)) is one strided reduction) and IsCloseOp (so allclose is one fused all-reduction).
-// The expression-template nodes keep their operands private, so the walker reads them through layout mirrors
-// (same member types in the same order; sizes are checked with static_assert).
+// (so trace(x) = sum(diag(x)) is one strided reduction), IsCloseOp (so allclose is one fused all-reduction), CastOp
+// (as_type<T> / as_float ...), ConstVal (ones / zeros), SliceOp (slice of an expression) and LCollapseOp / RCollapseOp
+// (when the operands walk the collapsed dims contiguously).  The expression-template nodes keep their operands private,
+// so the walker reads them through layout mirrors (same member types in the same order); see mirror_ok below for what
+// guards them.
 #pragma once
 
 #include <matx.h>
 
+#include <atomic>
 #include <cstdio>
 #include <cstring>
 #include <memory>
@@ -116,6 +119,47 @@ template <class O1, class O2> struct node_kind<matx::detail::IsCloseOp<O1, O2>> 
   struct Mirror { matx::detail::base_type_t<O1> op1_; matx::detail::base_type_t<O2> op2_; inner rtol_; inner atol_; };
 };
 
+template <class T, class NewType> struct node_kind<matx::detail::CastOp<T, NewType>> {   // operators/cast.h:62-66 (as_type<T>, as_float ...)
+  static constexpr int value = 7;
+  using A = T; using To = NewType;
+  struct Mirror { matx::detail::base_type_t<T> op_; };
+};
+template <class T, class ShapeType> struct node_kind<matx::detail::ConstVal<T, ShapeType>> {   // operators/constval.h:40-45 (ones / zeros)
+  static constexpr int value = 8;
+  using V = T;
+  struct Mirror { ShapeType s_; T v_; };
+};
+template <int DIM, class T, class StrideType> struct node_kind<matx::detail::SliceOp<DIM, T, StrideType>> {   // operators/slice.h:49-61
+  static constexpr int value = 9;
+  using A = T;
+  static constexpr bool strided = !std::is_same_v<StrideType, matx::detail::NoStride>;
+  struct Mirror {
+    matx::detail::base_type_t<T> op_; cuda::std::array<index_t, DIM> sizes_; cuda::std::array<int32_t, DIM> dims_;
+    cuda::std::array<index_t, T::Rank()> starts_; StrideType strides_;
+  };
+};
+template <int DIM, class T1> struct node_kind<matx::detail::LCollapseOp<DIM, T1>> {   // operators/collapse.h:43-47
+  static constexpr int value = 10;
+  using A = T1;
+  static constexpr int dim = DIM;
+  struct Mirror { matx::detail::base_type_t<T1> op_; index_t size_; };
+};
+template <int DIM, class T1> struct node_kind<matx::detail::RCollapseOp<DIM, T1>> {   // operators/collapse.h:330-335
+  static constexpr int value = 11;
+  using A = T1;
+  static constexpr int dim = DIM;
+  struct Mirror { matx::detail::base_type_t<T1> op_; index_t size_; int32_t dyn_rank_; };
+};
+
+// A layout mirror is only as good as its agreement with the class it shadows.  Compile time: same size and alignment
+// (the node classes are not standard-layout types once their operands are not — `is_standard_layout` cannot be asked of
+// them — so declaration order is what the Itanium C++ ABI lays out, as for any class with one access level).  Run time,
+// per statement: whatever the mirror read is cross-checked against what the node reports through its PUBLIC interface
+// (operand sizes against Size(), collapsed extents, slice sizes) before anything is launched; a mismatch falls back to
+// the reference path instead of reading through a wrong offset.  The by-the-letter fix is the accessor patch in
+// INTEGRATION.md.
+template <class Mirror, class Op> constexpr bool mirror_ok() { return sizeof(Mirror) == sizeof(Op) && alignof(Mirror) == alignof(Op); }
+
 template <class T> constexpr int rank_of_operand() {
   if constexpr (std::is_arithmetic_v<T> || is_complex_v<T>) return 0;
   else return T::Rank();
@@ -134,12 +178,18 @@ template <class T0> constexpr bool lowerable() {
   else if constexpr (node_kind<T>::value == 6)
     return (std::is_same_v<typename node_kind<T>::inner, float> || std::is_same_v<typename node_kind<T>::inner, double>) &&
            lowerable<typename node_kind<T>::A>() && lowerable<typename node_kind<T>::B>();
+  else if constexpr (node_kind<T>::value == 7) return dtype_of<typename node_kind<T>::To>::value >= 0 && lowerable<typename node_kind<T>::A>();
+  else if constexpr (node_kind<T>::value == 8)
+    return (std::is_arithmetic_v<typename node_kind<T>::V> && dtype_of<typename node_kind<T>::V>::value >= 0) ||
+           std::is_same_v<typename node_kind<T>::V, cuda::std::complex<float>>;
+  else if constexpr (node_kind<T>::value == 9 || node_kind<T>::value == 10 || node_kind<T>::value == 11) return lowerable<typename node_kind<T>::A>();
   else return false;
 }
 
 struct Builder {
   mxb_expr_t e;
   bool ok = true;
+  int next_gid = 0;   // collapse nodes met so far (DimMap::gid)
   Builder() { std::memset(&e, 0, sizeof e); }
   // Expression templates hold their operands by value, so `auto d1 = ...;` used twice arrives as two identical
   // sub-trees: nodes, leaves and constants are hash-consed here and the program becomes a DAG again (every distinct
@@ -176,8 +226,22 @@ struct Builder {
   }
 };
 
-// axes[i] = dim of the root index space that dim i of `op` walks
-template <class Op0> int lower(Builder &b, const Op0 &op, const int *axes) {
+// How dim d of an operand walks the root index space:  index_d = off + scale * digit,  digit = (root[axis] / div) % Size(d)
+// (div == 1 and gid == 0 for every dim that was not folded by a collapse node: digit = root[axis]).  axis < 0: the dim
+// sits at the fixed index `off` (a dim a slice dropped).  gid != 0: the dim is one digit of a collapsed root dim; the
+// digits of one collapse share a gid, the innermost has div == 1.  Permute / clone / diag / slice only move and compose
+// these entries; a tensor leaf turns them into a data offset and per-axis strides, which works for collapsed digits
+// exactly when the tensor walks them contiguously (stride_d * scale_d == div_d * stride_base * scale_base).
+struct DimMap { int axis; index_t scale, off, div; int gid; };
+inline DimMap compose(const DimMap &p, index_t c, index_t k) {   // child index = c + k * parent index
+  DimMap r = p;
+  r.scale = p.scale * k;
+  r.off = c + k * p.off;
+  return r;
+}
+constexpr int kMapDims = MXB_MAX_RANK > 0 ? MXB_MAX_RANK : 1;
+
+template <class Op0> int lower(Builder &b, const Op0 &op, const DimMap *m) {
   using Op = remove_cvref_t<Op0>;
   if constexpr (std::is_arithmetic_v<Op> || std::is_same_v<Op, cuda::std::complex<float>>) {
     if constexpr (std::is_arithmetic_v<Op>) return b.constant(static_cast<double>(op), 0.0, dtype_of<Op>::value);
@@ -185,91 +249,156 @@ template <class Op0> int lower(Builder &b, const Op0 &op, const int *axes) {
   } else if constexpr (is_tensor_view_v<Op> || matx::is_tensor_impl_v<Op>) {
     mxb_leaf_t lf;
     std::memset(&lf, 0, sizeof lf);
-    lf.data = op.Data();
     lf.dtype = dtype_of<typename Op::value_type>::value;
-    for (int d = 0; d < Op::Rank(); ++d) lf.stride[axes[d]] += op.Stride(d);
+    index_t off = 0;
+    for (int d = 0; d < Op::Rank(); ++d) {
+      const index_t st = op.Stride(d);
+      off += m[d].off * st;
+      if (m[d].axis < 0) continue;
+      if (m[d].gid == 0 || m[d].div == 1) { lf.stride[m[d].axis] += m[d].scale * st; continue; }
+      if (op.Size(d) <= 1) continue;
+      int e = -1;
+      for (int k = 0; k < Op::Rank(); ++k) if (m[k].gid == m[d].gid && m[k].div == 1) e = k;
+      if (e < 0 || m[d].scale * st != m[d].div * m[e].scale * op.Stride(e)) { b.ok = false; return 0; }   // not contiguous across the collapsed dims
+    }
+    lf.data = op.Data() + off;
     return b.leaf(lf);
   } else if constexpr (node_kind<Op>::value == 1) {
     using K = node_kind<Op>;
-    static_assert(sizeof(typename K::Mirror) == sizeof(Op), "matxBinaryOp layout changed: update the mirror");
-    const auto &m = reinterpret_cast<const typename K::Mirror &>(op);
-    constexpr int R = Op::Rank(), RA = rank_of_operand<remove_cvref_t<decltype(m.in1_)>>(), RB = rank_of_operand<remove_cvref_t<decltype(m.in2_)>>();
-    const int a = lower(b, m.in1_, axes + (R - RA));  // lower-rank operands line up with the trailing dims
-    const int c = lower(b, m.in2_, axes + (R - RB));
+    static_assert(mirror_ok<typename K::Mirror, Op>(), "matxBinaryOp layout changed: update the mirror");
+    const auto &mi = reinterpret_cast<const typename K::Mirror &>(op);
+    constexpr int R = Op::Rank(), RA = rank_of_operand<remove_cvref_t<decltype(mi.in1_)>>(), RB = rank_of_operand<remove_cvref_t<decltype(mi.in2_)>>();
+    const int a = lower(b, mi.in1_, m + (R - RA));  // lower-rank operands line up with the trailing dims
+    const int c = lower(b, mi.in2_, m + (R - RB));
     return b.node(fn_code<typename K::Fn>::value, a, c);
   } else if constexpr (node_kind<Op>::value == 2) {
     using K = node_kind<Op>;
-    static_assert(sizeof(typename K::Mirror) == sizeof(Op), "matxUnaryOp layout changed: update the mirror");
-    const auto &m = reinterpret_cast<const typename K::Mirror &>(op);
-    return b.node(fn_code<typename K::Fn>::value, lower(b, m.in1_, axes));
+    static_assert(mirror_ok<typename K::Mirror, Op>(), "matxUnaryOp layout changed: update the mirror");
+    const auto &mi = reinterpret_cast<const typename K::Mirror &>(op);
+    if constexpr (Op::Rank() > 0) {
+      for (int d = 0; d < Op::Rank(); ++d) if (mi.size_[d] != op.Size(d)) { b.ok = false; return 0; }   // the mirror read what Size() reports
+    }
+    return b.node(fn_code<typename K::Fn>::value, lower(b, mi.in1_, m));
   } else if constexpr (node_kind<Op>::value == 3) {
     using K = node_kind<Op>;
-    static_assert(sizeof(typename K::Mirror) == sizeof(Op), "PermuteOp layout changed: update the mirror");
-    const auto &m = reinterpret_cast<const typename K::Mirror &>(op);
-    int child[MXB_MAX_RANK];
-    bool seen[MXB_MAX_RANK] = {false};
+    static_assert(mirror_ok<typename K::Mirror, Op>(), "PermuteOp layout changed: update the mirror");
+    const auto &mi = reinterpret_cast<const typename K::Mirror &>(op);
+    DimMap child[kMapDims];
+    bool seen[kMapDims] = {false};
     for (int i = 0; i < Op::Rank(); ++i) {
-      const int d = m.dims_[i];  // output dim i is input dim dims_[i]  (operators/permute.h:276)
-      if (d < 0 || d >= Op::Rank() || seen[d] || op.Size(i) != m.op_.Size(d)) { b.ok = false; return 0; }
+      const int d = mi.dims_[i];  // output dim i is input dim dims_[i]  (operators/permute.h:276)
+      if (d < 0 || d >= Op::Rank() || seen[d] || op.Size(i) != mi.op_.Size(d)) { b.ok = false; return 0; }
       seen[d] = true;
-      child[d] = axes[i];
+      child[d] = m[i];
     }
-    return lower(b, m.op_, child);
+    return lower(b, mi.op_, child);
   } else if constexpr (node_kind<Op>::value == 4) {
     using K = node_kind<Op>;
-    static_assert(sizeof(typename K::Mirror) == sizeof(Op), "CloneOp layout changed: update the mirror");
-    const auto &m = reinterpret_cast<const typename K::Mirror &>(op);
-    constexpr int RA = remove_cvref_t<decltype(m.op_)>::Rank();
-    int child[MXB_MAX_RANK > 0 ? MXB_MAX_RANK : 1];
+    static_assert(mirror_ok<typename K::Mirror, Op>(), "CloneOp layout changed: update the mirror");
+    const auto &mi = reinterpret_cast<const typename K::Mirror &>(op);
+    constexpr int RA = remove_cvref_t<decltype(mi.op_)>::Rank();
+    DimMap child[kMapDims];
     for (int d = 0; d < RA; ++d) {
-      const index_t od = m.dims_[d];  // input dim d is output dim dims_[d]  (operators/clone.h:137)
-      if (od < 0 || od >= K::crank) { b.ok = false; return 0; }
-      child[d] = axes[od];
+      const index_t od = mi.dims_[d];  // input dim d is output dim dims_[d]  (operators/clone.h:137)
+      if (od < 0 || od >= K::crank || mi.op_.Size(d) != op.Size(static_cast<int>(od))) { b.ok = false; return 0; }
+      child[d] = m[od];
     }
-    return lower(b, m.op_, child);
+    return lower(b, mi.op_, child);
   } else if constexpr (node_kind<Op>::value == 5) {
     // diag(op, k): the result's last dim walks rows AND columns of the operand (operators/diag.h:145-190), i.e. both
-    // of the operand's last two dims map to the same root dim and their strides add up.  k != 0 offsets the data
-    // pointer, which only a tensor operand has.
+    // of the operand's last two dims map to the same root dim and their strides add up.  k != 0 offsets the column
+    // (k > 0) or the row (k < 0) index.
     using K = node_kind<Op>;
-    static_assert(sizeof(typename K::Mirror) == sizeof(Op), "DiagOp layout changed: update the mirror");
-    const auto &m = reinterpret_cast<const typename K::Mirror &>(op);
-    using Child = remove_cvref_t<decltype(m.op_)>;
+    static_assert(mirror_ok<typename K::Mirror, Op>(), "DiagOp layout changed: update the mirror");
+    const auto &mi = reinterpret_cast<const typename K::Mirror &>(op);
+    using Child = remove_cvref_t<decltype(mi.op_)>;
     constexpr int RA = Child::Rank();
-    int child[MXB_MAX_RANK];
-    for (int d = 0; d < RA - 2; ++d) child[d] = axes[d];
-    child[RA - 2] = child[RA - 1] = axes[RA - 2];
-    if (m.k_ == 0) return lower(b, m.op_, child);
-    {  // the reference's size rule for k != 0 (diag.h:262-267) runs off a non-square matrix: leave that to the reference
-      const index_t rows = m.op_.Size(RA - 2), cols = m.op_.Size(RA - 1);
-      const index_t valid = m.k_ > 0 ? cuda::std::min(rows, cols - m.k_) : cuda::std::min(rows + m.k_, cols);
+    DimMap child[kMapDims];
+    for (int d = 0; d < RA - 2; ++d) child[d] = m[d];
+    child[RA - 2] = child[RA - 1] = m[RA - 2];
+    if (mi.k_ != 0) {
+      // the reference's size rule for k != 0 (diag.h:262-267) runs off a non-square matrix: leave that to the reference
+      const index_t rows = mi.op_.Size(RA - 2), cols = mi.op_.Size(RA - 1);
+      const index_t valid = mi.k_ > 0 ? cuda::std::min(rows, cols - mi.k_) : cuda::std::min(rows + mi.k_, cols);
       if (op.Size(RA - 2) > valid) { b.ok = false; return 0; }
+      if (mi.k_ > 0) child[RA - 1] = compose(m[RA - 2], mi.k_, 1);
+      else child[RA - 2] = compose(m[RA - 2], -mi.k_, 1);
     }
-    if constexpr (is_tensor_view_v<Child> || matx::is_tensor_impl_v<Child>) {
-      mxb_leaf_t lf;
-      std::memset(&lf, 0, sizeof lf);
-      const index_t off = m.k_ > 0 ? m.k_ * m.op_.Stride(RA - 1) : -m.k_ * m.op_.Stride(RA - 2);
-      lf.data = m.op_.Data() + off;
-      lf.dtype = dtype_of<typename Child::value_type>::value;
-      for (int d = 0; d < RA; ++d) lf.stride[child[d]] += m.op_.Stride(d);
-      return b.leaf(lf);
-    } else {
-      b.ok = false;
-      return 0;
-    }
+    return lower(b, mi.op_, child);
   } else if constexpr (node_kind<Op>::value == 6) {
     // isclose: int(|a - b| <= atol + rtol * |b|), tolerances in the operands' inner type (operators/isclose.h)
     using K = node_kind<Op>;
-    static_assert(sizeof(typename K::Mirror) == sizeof(Op), "IsCloseOp layout changed: update the mirror");
-    const auto &m = reinterpret_cast<const typename K::Mirror &>(op);
-    constexpr int R = Op::Rank(), RA = rank_of_operand<remove_cvref_t<decltype(m.op1_)>>(), RB = rank_of_operand<remove_cvref_t<decltype(m.op2_)>>();
-    const int a = lower(b, m.op1_, axes + (R - RA));
-    const int c = lower(b, m.op2_, axes + (R - RB));
+    static_assert(mirror_ok<typename K::Mirror, Op>(), "IsCloseOp layout changed: update the mirror");
+    const auto &mi = reinterpret_cast<const typename K::Mirror &>(op);
+    constexpr int R = Op::Rank(), RA = rank_of_operand<remove_cvref_t<decltype(mi.op1_)>>(), RB = rank_of_operand<remove_cvref_t<decltype(mi.op2_)>>();
+    const int a = lower(b, mi.op1_, m + (R - RA));
+    const int c = lower(b, mi.op2_, m + (R - RB));
     constexpr int tol_dt = dtype_of<typename K::inner>::value;
     const int diff = b.node(MXB_OP_ABS, b.node(MXB_OP_SUB, a, c));
-    const int bound = b.node(MXB_OP_ADD, b.constant(static_cast<double>(m.atol_), 0.0, tol_dt),
-                             b.node(MXB_OP_MUL, b.constant(static_cast<double>(m.rtol_), 0.0, tol_dt), b.node(MXB_OP_ABS, c)));
+    const int bound = b.node(MXB_OP_ADD, b.constant(static_cast<double>(mi.atol_), 0.0, tol_dt),
+                             b.node(MXB_OP_MUL, b.constant(static_cast<double>(mi.rtol_), 0.0, tol_dt), b.node(MXB_OP_ABS, c)));
     return b.node(MXB_OP_CAST, b.node(MXB_OP_LE, diff, bound), -1, MXB_I32);
+  } else if constexpr (node_kind<Op>::value == 7) {
+    // as_type<NewType>(op): static_cast per element (operators/cast.h:62-66)
+    using K = node_kind<Op>;
+    static_assert(mirror_ok<typename K::Mirror, Op>(), "CastOp layout changed: update the mirror");
+    const auto &mi = reinterpret_cast<const typename K::Mirror &>(op);
+    if constexpr (Op::Rank() > 0) {
+      for (int d = 0; d < Op::Rank(); ++d) if (mi.op_.Size(d) != op.Size(d)) { b.ok = false; return 0; }
+    }
+    return b.node(MXB_OP_CAST, lower(b, mi.op_, m), -1, dtype_of<typename K::To>::value);
+  } else if constexpr (node_kind<Op>::value == 8) {
+    // ones() / zeros() / a shaped constant (operators/constval.h:40-45): the value, whatever the index
+    using K = node_kind<Op>;
+    static_assert(mirror_ok<typename K::Mirror, Op>(), "ConstVal layout changed: update the mirror");
+    const auto &mi = reinterpret_cast<const typename K::Mirror &>(op);
+    if constexpr (std::is_arithmetic_v<typename K::V>) return b.constant(static_cast<double>(mi.v_), 0.0, dtype_of<typename K::V>::value);
+    else return b.constant(mi.v_.real(), mi.v_.imag(), MXB_C64);
+  } else if constexpr (node_kind<Op>::value == 9) {
+    // slice(op, starts, ends[, strides]) as an operator node (operators/slice.h:192-224): output dim j walks input dim
+    // dims_[j] from starts[j] (sic: the reference indexes starts_ by the OUTPUT dim there) in steps of strides_[dims_[j]];
+    // a dropped input dim sits at starts_[i]
+    using K = node_kind<Op>;
+    static_assert(mirror_ok<typename K::Mirror, Op>(), "SliceOp layout changed: update the mirror");
+    const auto &mi = reinterpret_cast<const typename K::Mirror &>(op);
+    using Child = remove_cvref_t<decltype(mi.op_)>;
+    constexpr int RA = Child::Rank();
+    DimMap child[kMapDims];
+    for (int i = 0; i < RA; ++i) child[i] = DimMap{-1, 0, mi.starts_[i], 1, 0};
+    for (int j = 0; j < Op::Rank(); ++j) {
+      const int i = mi.dims_[j];
+      if (i < 0 || i >= RA || mi.sizes_[j] != op.Size(j)) { b.ok = false; return 0; }
+      index_t step = 1;
+      if constexpr (K::strided) step = mi.strides_[i];
+      child[i] = compose(m[j], mi.starts_[j], step);
+    }
+    return lower(b, mi.op_, child);
+  } else if constexpr (node_kind<Op>::value == 10 || node_kind<Op>::value == 11) {
+    // lcollapse<DIM>(op) / rcollapse<DIM>(op) (operators/collapse.h:150-176,441-470): the first / last DIM dims of the
+    // operand become the digits of ONE dim of the result (row-major)
+    using K = node_kind<Op>;
+    static_assert(mirror_ok<typename K::Mirror, Op>(), "collapse op layout changed: update the mirror");
+    const auto &mi = reinterpret_cast<const typename K::Mirror &>(op);
+    using Child = remove_cvref_t<decltype(mi.op_)>;
+    constexpr int RA = Child::Rank(), DIM = K::dim, R = Op::Rank();
+    constexpr bool left = node_kind<Op>::value == 10;
+    const int cdim = left ? 0 : R - 1;            // the collapsed dim of the result
+    const int c0 = left ? 0 : RA - DIM;           // the operand dims it folds: [c0, c0 + DIM)
+    const DimMap &pm = m[cdim];
+    if (pm.scale != 1 || pm.off != 0 || pm.div != 1 || pm.gid != 0 || mi.size_ != op.Size(cdim)) { b.ok = false; return 0; }
+    DimMap child[kMapDims];
+    for (int i = 0; i < R; ++i) {
+      if (i == cdim) continue;
+      child[left ? DIM - 1 + i : i] = m[i];
+    }
+    const int gid = ++b.next_gid;
+    index_t div = 1;
+    for (int j = DIM - 1; j >= 0; --j) {
+      child[c0 + j] = DimMap{pm.axis, 1, 0, div, gid};
+      div *= mi.op_.Size(c0 + j);
+    }
+    if (div != mi.size_) { b.ok = false; return 0; }
+    return lower(b, mi.op_, child);
   } else {
     b.ok = false;
     return 0;
@@ -280,9 +409,9 @@ template <class Op> bool lower_root(Builder &b, const Op &op) {
   constexpr int R = rank_of_operand<remove_cvref_t<Op>>();
   if constexpr (R > MXB_MAX_RANK) return false;
   b.e.rank = R;
-  int axes[MXB_MAX_RANK > 0 ? MXB_MAX_RANK : 1];
-  for (int d = 0; d < R; ++d) { axes[d] = d; if constexpr (R > 0) b.e.size[d] = op.Size(d); }
-  b.e.root = lower(b, op, axes);
+  DimMap m[kMapDims];
+  for (int d = 0; d < R; ++d) { m[d] = DimMap{d, 1, 0, 1, 0}; if constexpr (R > 0) b.e.size[d] = op.Size(d); }
+  b.e.root = lower(b, op, m);
   return b.ok;
 }
 
@@ -334,6 +463,11 @@ class b200Executor : public cudaExecutor {
   mxb_handle_t handle() const { return h_.get(); }
   const char *last_kernel() const { return mxb_last_kernel(h_.get()); }   // "" when the last statement fell back
   long long native_launches() const { return mxb_launch_count(h_.get()); }
+  // statements (or transform calls) of this executor and its copies that ran on the REFERENCE path because the lowering
+  // does not cover them (unknown node type, unsupported dtype / view) — a performance cliff, not an error; a program
+  // that expects the native path asserts that this stays 0
+  long long fallbacks() const { return fb_->load(); }
+  void reset_fallbacks() const { fb_->store(0); }
 
   // `(tensor = expression).run(exec)` lands here (operators/base_operator.h:255-262)
   template <typename Op> void Exec(const Op &op) const {
@@ -347,8 +481,9 @@ class b200Executor : public cudaExecutor {
           if (!b200_detail::check_or_fallback(mxb_elementwise(h_.get(), &b.e, &out))) return;
         }
       }
+      fb_->fetch_add(1);
     }
-    cudaExecutor::Exec(op);  // reference generic kernels, same stream
+    cudaExecutor::Exec(op);  // reference generic kernels, same stream (also every non-assignment statement)
   }
 
   // one reduction statement; returns false when the reference path has to take it
@@ -358,70 +493,111 @@ class b200Executor : public cudaExecutor {
   // softmax over the trailing n_axes dims of `in` (already permuted so that the softmax axes are innermost); `dest` is
   // walked in the same permuted order
   template <class Out, class In> bool softmax_trailing(Out &dest, const In &in, int n_axes) const {
-    if constexpr (!b200_detail::lowerable<In>()) return false;
+    if constexpr (!b200_detail::lowerable<In>()) return fell_back();
     else {
       b200_detail::Builder b;
       mxb_out_t out;
-      if (!b200_detail::out_desc(dest, out)) return false;
-      if (!b200_detail::lower_root(b, in)) return false;
-      return !b200_detail::check_or_fallback(mxb_softmax(h_.get(), &b.e, n_axes, &out));
+      if (!b200_detail::out_desc(dest, out)) return fell_back();
+      if (!b200_detail::lower_root(b, in)) return fell_back();
+      return native(mxb_softmax(h_.get(), &b.e, n_axes, &out));
     }
   }
   template <class Out, class In> bool cumsum(Out &dest, const In &in) const {
-    if constexpr (!b200_detail::lowerable<In>()) return false;
+    if constexpr (!b200_detail::lowerable<In>()) return fell_back();
     else {
       b200_detail::Builder b;
       mxb_out_t out;
-      if (!b200_detail::out_desc(dest, out)) return false;
-      if (!b200_detail::lower_root(b, in)) return false;
-      return !b200_detail::check_or_fallback(mxb_cumsum(h_.get(), &b.e, &out));
+      if (!b200_detail::out_desc(dest, out)) return fell_back();
+      if (!b200_detail::lower_root(b, in)) return fell_back();
+      return native(mxb_cumsum(h_.get(), &b.e, &out));
     }
   }
   // find / find_idx with one of the reference's selection functors (LT / GT / EQ / NEQ / LTE / GTE, cub.h:2521-2588)
   template <class Out, class Cnt, class In, class T> bool find(Out &dest, Cnt &num_found, const In &in, int sel_op, T thr, bool want_idx) const {
+    // The reference's functors convert each element to THEIR type T and compare in T (transforms/cub.h:2514-2588), so
+    // find(int_tensor, LT<float>{0.5f}) or EQ<int>{1} on floats compare differently from the element type's own
+    // comparison: only the case T == element type is taken natively (the threshold then crosses the ABI exactly, except
+    // for 64-bit integers beyond 2^53, which are left to the reference as well).
     if constexpr (!b200_detail::lowerable<In>() || Out::Rank() != 1 || Cnt::Rank() != 0 ||
-                  !std::is_same_v<typename Cnt::value_type, int> || !std::is_arithmetic_v<T>) return false;
+                  !std::is_same_v<typename Cnt::value_type, int> || !std::is_arithmetic_v<T> ||
+                  !std::is_same_v<T, typename In::value_type>) return fell_back();
+    else if (sizeof(T) == 8 && std::is_integral_v<T> && static_cast<T>(static_cast<double>(thr)) != thr) return fell_back();
     else {
       b200_detail::Builder b;
       mxb_out_t out, cnt;
-      if (!b200_detail::out_desc(dest, out)) return false;
-      if (!b200_detail::out_desc(num_found, cnt)) return false;
-      if (!b200_detail::lower_root(b, in)) return false;
-      return !b200_detail::check_or_fallback(mxb_find(h_.get(), &b.e, sel_op, static_cast<double>(thr), &out, &cnt, want_idx ? 1 : 0));
+      if (!b200_detail::out_desc(dest, out)) return fell_back();
+      if (!b200_detail::out_desc(num_found, cnt)) return fell_back();
+      if (!b200_detail::lower_root(b, in)) return fell_back();
+      return native(mxb_find(h_.get(), &b.e, sel_op, static_cast<double>(thr), &out, &cnt, want_idx ? 1 : 0));
+    }
+  }
+  template <class Out, class In> bool sort(Out &dest, const In &in, bool descending) const {
+    if constexpr (!b200_detail::lowerable<In>()) return fell_back();
+    else {
+      b200_detail::Builder b;
+      mxb_out_t out;
+      if (!b200_detail::out_desc(dest, out)) return fell_back();
+      if (!b200_detail::lower_root(b, in)) return fell_back();
+      return native(mxb_sort(h_.get(), &b.e, &out, descending ? 1 : 0));
+    }
+  }
+  template <class Out, class In> bool hist(Out &dest, const In &in, double lower, double upper) const {
+    if constexpr (!b200_detail::lowerable<In>()) return fell_back();
+    else {
+      b200_detail::Builder b;
+      mxb_out_t out;
+      if (!b200_detail::out_desc(dest, out)) return fell_back();
+      if (!b200_detail::lower_root(b, in)) return fell_back();
+      return native(mxb_hist(h_.get(), &b.e, lower, upper, &out));
+    }
+  }
+  template <class Out, class Cnt, class In> bool unique(Out &dest, Cnt &num_found, const In &in) const {
+    if constexpr (!b200_detail::lowerable<In>() || Out::Rank() != 1 || Cnt::Rank() != 0 || !std::is_same_v<typename Cnt::value_type, int>) return fell_back();
+    else {
+      b200_detail::Builder b;
+      mxb_out_t out, cnt;
+      if (!b200_detail::out_desc(dest, out)) return fell_back();
+      if (!b200_detail::out_desc(num_found, cnt)) return fell_back();
+      if (!b200_detail::lower_root(b, in)) return fell_back();
+      return native(mxb_unique(h_.get(), &b.e, &out, &cnt));
     }
   }
   template <class Out, class Idx, class In> bool reduce_idx(int op, Out &dest, Idx *idest, const In &in, int ddof) const {
-    if constexpr (!b200_detail::lowerable<In>()) return false;
+    if constexpr (!b200_detail::lowerable<In>()) return fell_back();
     else {
       b200_detail::Builder b;
       mxb_out_t out, iout;
-      if (!b200_detail::out_desc(dest, out)) return false;
-      if (idest && !b200_detail::out_desc(*idest, iout)) return false;
-      if (!b200_detail::lower_root(b, in)) return false;
+      if (!b200_detail::out_desc(dest, out)) return fell_back();
+      if (idest && !b200_detail::out_desc(*idest, iout)) return fell_back();
+      if (!b200_detail::lower_root(b, in)) return fell_back();
       constexpr int n_reduce = In::Rank() - Out::Rank();
-      return !b200_detail::check_or_fallback(mxb_reduce(h_.get(), op, &b.e, n_reduce, &out, idest ? &iout : nullptr, ddof));
+      return native(mxb_reduce(h_.get(), op, &b.e, n_reduce, &out, idest ? &iout : nullptr, ddof));
     }
   }
 
  private:
+  bool fell_back() const { fb_->fetch_add(1); return false; }
+  bool native(int status) const { return b200_detail::check_or_fallback(status) ? fell_back() : true; }
   void init() {
     mxb_handle_t h = nullptr;
     const int st = mxb_create(&h, reinterpret_cast<void *>(getStream()));
     if (st != MXB_OK) { MATX_THROW(matxCudaError, std::string("libmatx_b200: ") + mxb_last_error()); }
     h_ = std::shared_ptr<mxb_context>(h, [](mxb_context *p) { mxb_destroy(p); });
+    fb_ = std::make_shared<std::atomic<long long>>(0);
   }
   // rhs of lower rank than the lhs broadcasts over the leading dims of the lhs
   template <class Rhs> static bool lower_for_lhs(b200_detail::Builder &b, const Rhs &rhs, const mxb_out_t &out) {
     constexpr int R = b200_detail::rank_of_operand<remove_cvref_t<Rhs>>();
     if (R > out.rank) return false;
     b.e.rank = out.rank;
-    int axes[MXB_MAX_RANK > 0 ? MXB_MAX_RANK : 1];
+    b200_detail::DimMap m[b200_detail::kMapDims];
     for (int d = 0; d < out.rank; ++d) b.e.size[d] = out.size[d];
-    for (int d = 0; d < R; ++d) axes[d] = out.rank - R + d;
-    b.e.root = b200_detail::lower(b, rhs, axes);
+    for (int d = 0; d < R; ++d) m[d] = b200_detail::DimMap{out.rank - R + d, 1, 0, 1, 0};
+    b.e.root = b200_detail::lower(b, rhs, m);
     return b.ok;
   }
   std::shared_ptr<mxb_context> h_;
+  std::shared_ptr<std::atomic<long long>> fb_;
 };
 
 // ---- the transform seam: overloads found by ADL from SumOp::Exec etc. -----------------------------------------------
@@ -552,6 +728,60 @@ void find_idx_impl(OutputTensor &a_out, CountTensor &num_found, const InputOpera
 template <typename SelectType, typename CountTensor, typename OutputTensor, typename InputOperator>
 void find_idx_impl(OutputTensor &a_out, CountTensor &num_found, const InputOperator &a, SelectType sel, b200Executor &exec) {
   find_idx_impl(a_out, num_found, a, sel, static_cast<const b200Executor &>(exec));
+}
+
+// sort / unique (transforms/cub.h:2145-2190,2796-2842): SortOp::Exec and UniqueOp::Exec pass the executor
+// (operators/sort.h:301, unique.h:88), so `(out = sort(x, SORT_DIR_ASC)).run(exec)` and
+// `(mtie(out, num_found) = unique(x)).run(exec)` land here.
+template <typename OutputTensor, typename InputOperator>
+void sort_impl(OutputTensor &a_out, const InputOperator &a, const SortDirection_t dir, const b200Executor &exec) {
+  if (!exec.sort(a_out, a, dir == SORT_DIR_DESC)) sort_impl(a_out, a, dir, static_cast<const cudaExecutor &>(exec));
+}
+template <typename OutputTensor, typename InputOperator>
+void sort_impl(OutputTensor &a_out, const InputOperator &a, const SortDirection_t dir, b200Executor &exec) {
+  sort_impl(a_out, a, dir, static_cast<const b200Executor &>(exec));
+}
+template <typename CountTensor, typename OutputTensor, typename InputOperator>
+void unique_impl(OutputTensor &a_out, CountTensor &num_found, const InputOperator &a, const b200Executor &exec) {
+  if (!exec.unique(a_out, num_found, a)) unique_impl(a_out, num_found, a, static_cast<const cudaExecutor &>(exec));
+}
+template <typename CountTensor, typename OutputTensor, typename InputOperator>
+void unique_impl(OutputTensor &a_out, CountTensor &num_found, const InputOperator &a, b200Executor &exec) {
+  unique_impl(a_out, num_found, a, static_cast<const b200Executor &>(exec));
+}
+
+// hist (transforms/cub.h:2464-2503) and the operator form of softmax: HistOp::Exec and SoftmaxOp::Exec hand their impl the
+// bare STREAM (operators/hist.h:107, softmax.h:105-108), so the executor type is gone by the time an overload is chosen.
+// With the two one-line changes of INTEGRATION.md (`ex` instead of `ex.getStream()`; tools/make_overlay.py writes such
+// headers into an include directory that precedes the reference's) the calls below are found instead: the first pair keeps
+// every OTHER executor on the reference's stream overloads, the b200Executor ones go native.
+template <typename OutputTensor, typename InputOperator>
+void hist_impl(OutputTensor &a_out, const InputOperator &a, const typename InputOperator::value_type lower,
+               const typename InputOperator::value_type upper, int num_levels, const cudaExecutor &exec) {
+  hist_impl(a_out, a, lower, upper, num_levels, exec.getStream());
+}
+template <typename OutputTensor, typename InputOperator>
+void hist_impl(OutputTensor &a_out, const InputOperator &a, const typename InputOperator::value_type lower,
+               const typename InputOperator::value_type upper, int num_levels, const b200Executor &exec) {
+  bool done = false;
+  if constexpr (std::is_arithmetic_v<typename InputOperator::value_type>) {
+    if (num_levels == static_cast<int>(a_out.Size(OutputTensor::Rank() - 1)) + 1)
+      done = exec.hist(a_out, a, static_cast<double>(lower), static_cast<double>(upper));
+  }
+  if (!done) hist_impl(a_out, a, lower, upper, num_levels, exec.getStream());
+}
+template <typename OutputTensor, typename InputOperator>
+void hist_impl(OutputTensor &a_out, const InputOperator &a, const typename InputOperator::value_type lower,
+               const typename InputOperator::value_type upper, int num_levels, b200Executor &exec) {
+  hist_impl(a_out, a, lower, upper, num_levels, static_cast<const b200Executor &>(exec));
+}
+template <typename OutType, typename InType>
+void softmax_impl(OutType dest, const InType &in, const cudaExecutor &exec) {
+  softmax_impl(dest, in, exec.getStream());
+}
+template <typename OutType, typename InType, typename PermDims>
+void softmax_impl(OutType dest, const InType &in, PermDims dims, const cudaExecutor &exec) {
+  softmax_impl(dest, in, dims, exec.getStream());
 }
 
 // allclose (transforms/reduce.h:1321-1331): all(isclose(in1, in2, rtol, atol)) into a rank-0 int tensor, one launch

@@ -71,7 +71,7 @@ EXPORTED = [
     "mxb_create", "mxb_destroy", "mxb_set_stream", "mxb_sync", "mxb_elementwise", "mxb_reduce", "mxb_reduce_partial",
     "mxb_reduce_finalize", "mxb_version", "mxb_last_error", "mxb_device_count", "mxb_last_kernel", "mxb_launch_count",
     "mxb_is_aot", "mxb_reduce_partial_push", "mxb_exchange_finalize", "mxb_exchange_alloc", "mxb_exchange_open", "mxb_exchange_close",
-    "mxb_exchange_free", "mxb_softmax", "mxb_cumsum", "mxb_find",
+    "mxb_exchange_free", "mxb_exchange_check", "mxb_softmax", "mxb_cumsum", "mxb_find", "mxb_hist", "mxb_sort", "mxb_unique",
 ]
 
 
@@ -115,10 +115,14 @@ def _load() -> C.CDLL:
     lib.mxb_softmax.argtypes = [vp, C.POINTER(Expr), i32, C.POINTER(Out)]
     lib.mxb_cumsum.argtypes = [vp, C.POINTER(Expr), C.POINTER(Out)]
     lib.mxb_find.argtypes = [vp, C.POINTER(Expr), i32, C.c_double, C.POINTER(Out), C.POINTER(Out), i32]
+    lib.mxb_hist.argtypes = [vp, C.POINTER(Expr), C.c_double, C.c_double, C.POINTER(Out)]
+    lib.mxb_sort.argtypes = [vp, C.POINTER(Expr), C.POINTER(Out), i32]
+    lib.mxb_unique.argtypes = [vp, C.POINTER(Expr), C.POINTER(Out), C.POINTER(Out)]
     lib.mxb_reduce_partial.argtypes = [vp, i32, C.POINTER(Expr), i64, vp]
     lib.mxb_reduce_finalize.argtypes = [vp, i32, i32, vp, i32, i64, i64, i32, C.POINTER(Out), C.POINTER(Out)]
     lib.mxb_reduce_partial_push.argtypes = [vp, i32, C.POINTER(Expr), i64, C.POINTER(Peers), i32, i32]
     lib.mxb_exchange_finalize.argtypes = [vp, C.POINTER(Peers), C.POINTER(FoldItem), i32, i64]
+    lib.mxb_exchange_check.argtypes = [vp, C.POINTER(Peers)]
     lib.mxb_exchange_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp), C.c_char_p]
     lib.mxb_exchange_open.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
     lib.mxb_exchange_close.argtypes = [vp, vp]

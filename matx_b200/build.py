@@ -37,7 +37,7 @@ def _cuda_include() -> str:
 
 HOST_SOURCES = ["codegen.cpp", "jit.cpp", "aot_manifest.cpp"]
 GEN_SOURCES = ["gen_main.cpp", "codegen.cpp", "aot_manifest.cpp"]
-ALL_INPUTS = ["mxb_device.cuh", "mxb_internal.h", "api.cu", "gen_main.cpp"] + HOST_SOURCES
+ALL_INPUTS = ["mxb_device.cuh", "mxb_internal.h", "mxb_sort.cuh", "api.cu", "gen_main.cpp"] + HOST_SOURCES
 
 
 def _nvcc() -> str:

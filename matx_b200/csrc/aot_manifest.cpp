@@ -50,6 +50,7 @@ int canonicalize(const mxb_expr_t *in, mxb_expr_t *out, std::string *err) {
   auto fail = [&](const std::string &m) { if (err) *err = m; return (int)MXB_ERR_INVALID; };
   if (in->n_nodes <= 0 || in->n_nodes > MXB_MAX_NODES || in->root < 0 || in->root >= in->n_nodes) return fail("malformed program");
   if (in->n_leaves < 0 || in->n_leaves > MXB_MAX_LEAVES || in->n_consts < 0 || in->n_consts > MXB_MAX_CONSTS) return fail("malformed program");
+  if (in->rank < 0 || in->rank > MXB_MAX_RANK) return fail("expression rank out of range");
   memset(out, 0, sizeof *out);
   out->rank = in->rank;
   memcpy(out->size, in->size, sizeof in->size);
@@ -98,9 +99,10 @@ int canonicalize(const mxb_expr_t *in, mxb_expr_t *out, std::string *err) {
     if (!leafish) {
       if (n.src[0] < 0 || n.src[0] >= in->n_nodes || n.src[0] == f.node) return fail("operand id out of range");
       if (binary && (n.src[1] < 0 || n.src[1] >= in->n_nodes || n.src[1] == f.node)) return fail("operand id out of range");
-      if (f.stage == 0) { f.stage = 1; if (memo[n.src[0]] < 0) { st.push_back({n.src[0], 0}); continue; } }
-      if (f.stage == 1) { f.stage = 2; if (binary && memo[n.src[1]] < 0) { st.push_back({n.src[1], 0}); continue; } }
-      if (st.size() > 4 * MXB_MAX_NODES) return fail("cyclic program");
+      // the walk of a DAG never holds more frames than there are nodes: a deeper stack means a cycle (a -> b -> a)
+      if (st.size() > (size_t)in->n_nodes) return fail("cyclic program");
+      if (f.stage == 0) { f.stage = 1; if (memo[n.src[0]] < 0) { const int c = n.src[0]; st.push_back({c, 0}); continue; } }
+      if (f.stage == 1) { f.stage = 2; if (binary && memo[n.src[1]] < 0) { const int c = n.src[1]; st.push_back({c, 0}); continue; } }
     }
     int s0, s1 = -1;
     if (n.opcode == MXB_OP_LEAF) {
@@ -304,6 +306,8 @@ void aot_manifest(std::vector<ManifestItem> *items) {
     add(prog_identity(d), FAM_SELECT, -1, MXB_I32, 4, d == MXB_F32);
     add(prog_identity(d), FAM_SELECT, -1, MXB_I64, 4, false);
   }
+  // histograms of plain tensors
+  for (int d : {MXB_F32, MXB_F64, MXB_I32}) add(prog_identity(d), FAM_HIST, -1, MXB_I32, 0, d == MXB_F32);
   // permuted copies (bench/00_operators/operators.cu:40-59) and the row + column mix
   for (int d : {MXB_F32, MXB_F64, MXB_C64, MXB_BF16, MXB_I32}) add(prog_identity(d), FAM_EW_TR, -1, d, 0, false);
   add(prog_vector_add(MXB_F32), FAM_EW_TR, -1, MXB_F32, 0, false);

@@ -20,6 +20,7 @@
 
 #include "mxb_device.cuh"
 #include "mxb_internal.h"
+#include "mxb_sort.cuh"
 
 using namespace mxbh;
 using mxb::EwParams;
@@ -38,8 +39,12 @@ struct mxb_context {
   size_t ws_bytes = 0;
   unsigned *tickets = nullptr;
   size_t n_tickets = 0;
-  void *tmp = nullptr;  // mean scratch of the two-launch variance
+  void *tmp = nullptr;  // mean scratch of the two-launch variance; the radix sort's second key buffer
   size_t tmp_bytes = 0;
+  void *tmp2 = nullptr; // unique: the sorted copy of the operand
+  size_t tmp2_bytes = 0;
+  unsigned *sort_ctr = nullptr;   // radix sort: per-(row, chunk, digit) counts and offsets
+  size_t sort_ctr_words = 0;
   std::string last_kernel;
   int64_t launches = 0;
   // single-pass select / look-back scan: tile status words + {epoch, exit ticket} (device-resident epoch: graph-replay safe)
@@ -1173,26 +1178,47 @@ template <class T> __device__ void fold_logic(int op, const uint4 *recs, int wor
   *(T *)out = mxb::cvt<T>(a);
 }
 
+// this rank's exchange control block (the zeroed words behind `epoch`): [0] completed exchanges, [1] sticky error word,
+// [16 + r] records of source rank r consumed so far.  The arrival counters count records cumulatively, so a step waits for
+// arrived[r] - consumed[r] >= n_items: steps of different sizes can share one exchange.
+constexpr int EXC_ERR = 1, EXC_CONSUMED = 16;
+
 __global__ void exchange_finalize_kernel(const __grid_constant__ ExchangeParams p) {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const int lane = threadIdx.x;
   const unsigned e = *p.epoch + 1u;
-  const unsigned target = e * (unsigned)p.n_items;
   // lanes 0..world-1 each wait for one source rank (bounded: a dead peer must not hang this GPU)
+  bool ok = true;
   if (lane < p.world) {
+    const unsigned seen = p.epoch[EXC_CONSUMED + lane];
     unsigned long long t0, t1;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
     while (true) {
       unsigned v;
       asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p.flag + lane) : "memory");
-      if ((int)(v - target) >= 0) break;
+      if ((int)(v - seen - (unsigned)p.n_items) >= 0) break;
       asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
-      if (t1 - t0 > 5000000000ull) break;  // 5 s
+      if (t1 - t0 > 5000000000ull) { ok = false; break; }  // 5 s
       __nanosleep(100);
     }
+    p.epoch[EXC_CONSUMED + lane] = seen + (unsigned)p.n_items;
   }
-  __syncwarp();
+  ok = __all_sync(0xffffffffu, ok);
   const int slot = (int)(e & 1u);
-  if (lane < p.n_items) {
+  if (!ok) {
+    // a peer never delivered: nothing is folded (the slot may hold a stale record); the outputs get a sentinel and the
+    // sticky error word makes mxb_exchange_check return MXB_ERR_CUDA
+    if (lane == 0) p.epoch[EXC_ERR] = e;
+    if (lane < p.n_items) {
+      const FoldItemDev it = p.item[lane];
+      const bool real64 = it.dtype == MXB_F64;
+      if (it.dtype == MXB_F32 || it.dtype == MXB_C64 || real64) {
+        if (real64) *(double *)it.out = __longlong_as_double(0x7ff8000000000000LL);
+        else *(float *)it.out = __int_as_float(0x7fc00000);
+      }
+      if (it.idx) *it.idx = -1;
+    }
+  } else if (lane < p.n_items) {
     const FoldItemDev it = p.item[lane];
     const uint4 *recs = p.rec + ((size_t)slot * p.world * mxb::KMAXITEMS + lane) * 2;  // 2 x uint4 per 32-byte record
     const int stride16 = mxb::KMAXITEMS * 2;
@@ -1275,6 +1301,8 @@ int mxb_destroy(mxb_handle_t h) {
   if (h->ws) cudaFreeAsync(h->ws, h->stream);
   if (h->tickets) cudaFreeAsync(h->tickets, h->stream);
   if (h->tmp) cudaFreeAsync(h->tmp, h->stream);
+  if (h->tmp2) cudaFreeAsync(h->tmp2, h->stream);
+  if (h->sort_ctr) cudaFreeAsync(h->sort_ctr, h->stream);
   if (h->lb_status) cudaFreeAsync(h->lb_status, h->stream);
   if (h->lb_ctl) cudaFreeAsync(h->lb_ctl, h->stream);
   delete h;
@@ -1458,10 +1486,38 @@ int mxb_exchange_finalize(mxb_handle_t h, const mxb_peers_t *peers, const mxb_fo
     p.item[k].idx = (long long *)it.idx_out;
     p.item[k].ddof = it.ddof;
   }
-  exchange_finalize_kernel<<<1, 32, 0, h->stream>>>(p);
-  MXB_CUDA(cudaGetLastError());
+  {
+    // programmatic dependent launch: the fold kernel's launch latency hides behind the tail of the last slab kernel (it
+    // starts with griddepcontrol.wait, so it reads nothing before that kernel has completed)
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3(1);
+    cfg.blockDim = dim3(32);
+    cfg.stream = h->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = env_int("MXB_PDL", 1) ? 1 : 0;
+    if (!g_plan) {
+      void *args[] = {(void *)&p};
+      MXB_CUDA(cudaLaunchKernelExC(&cfg, (const void *)exchange_finalize_kernel, args));
+    }
+  }
   h->launches++;
   h->last_kernel = "exchange_finalize";
+  return MXB_OK;
+}
+
+int mxb_exchange_check(mxb_handle_t h, const mxb_peers_t *peers) {
+  if (!h || !peers || !peers->epoch) return fail(MXB_ERR_INVALID, "bad exchange arguments");
+  MXB_CUDA(cudaSetDevice(h->device));
+  MXB_CUDA(cudaStreamSynchronize(h->stream));
+  unsigned ctl[2] = {0, 0};
+  MXB_CUDA(cudaMemcpy(ctl, peers->epoch, sizeof ctl, cudaMemcpyDeviceToHost));
+  if (ctl[EXC_ERR] != 0)
+    return fail(MXB_ERR_CUDA, "fused exchange: a peer's records did not arrive within 5 s at exchange " + std::to_string(ctl[EXC_ERR]) +
+                                  " of " + std::to_string(ctl[0]) + "; the outputs of that step hold NaN / -1");
   return MXB_OK;
 }
 
@@ -1937,7 +1993,9 @@ int mxb_cumsum(mxb_handle_t h, const mxb_expr_t *expr_in, const mxb_out_t *out) 
   p.B = B;
   p.R = L;
   p.nleaf = nl;
-  p.splits = tiles_mode ? 2 : 1;
+  // TILES mode exchange: 2 = flat two-level gather by the whole CTA (the measured default), 3 = pipelined three-level jobs by one warp
+  const bool scan_pipe = env_int("MXB_SCAN_PIPELINE", 0) != 0;
+  p.splits = tiles_mode ? (scan_pipe ? 3 : 2) : 1;
   for (int d = 0; d < gb.n; ++d) {
     p.bsz[d] = gb.size[d];
     p.out.bs[d] = gb.os[d];
@@ -1970,7 +2028,7 @@ int mxb_cumsum(mxb_handle_t h, const mxb_expr_t *expr_in, const mxb_out_t *out) 
   Kernel k;
   st = get_kernel(info, spec, &k);
   if (st != MXB_OK) return st;
-  unsigned grid;
+  unsigned grid, scan_smem = 0;
   if (tiles_mode) {
     // slots: tile totals, group totals (32 tiles), running totals at supergroup starts (1024 tiles), per row
     const int64_t gpr = (tpr + 31) / 32, spr = (tpr + 1023) / 1024;
@@ -1986,7 +2044,11 @@ int mxb_cumsum(mxb_handle_t h, const mxb_expr_t *expr_in, const mxb_out_t *out) 
     // tiles are dealt round-robin to the grid and a tile waits for its predecessors, so every CTA must be resident:
     // the grid is sized from the launch-time occupancy and launched cooperatively (the runtime refuses a grid that
     // cannot be co-resident instead of letting it spin)
-    const int res = resident_ctas(k, 256, 0, 3);
+    int depth = env_int("MXB_TUNE_SCAN_DEPTH", 0) > 0 ? env_int("MXB_TUNE_SCAN_DEPTH", 0) : 4;
+    while (depth > 2 && (int64_t)depth * tile * dtype_bytes(vt) > 72 * 1024) --depth;
+    p.scan_depth = std::min(depth, 8);
+    scan_smem = scan_pipe ? (unsigned)((int64_t)p.scan_depth * tile * dtype_bytes(vt)) : 0u;
+    const int res = resident_ctas(k, 256, scan_smem, 3);
     const int per_sm = env_int("MXB_SCAN_GRID_PER_SM", 0) > 0 ? std::min(env_int("MXB_SCAN_GRID_PER_SM", 0), res) : res;
     grid = (unsigned)std::min<int64_t>(B * tpr, (int64_t)sm * per_sm);
   } else {
@@ -1994,14 +2056,14 @@ int mxb_cumsum(mxb_handle_t h, const mxb_expr_t *expr_in, const mxb_out_t *out) 
     const int64_t rows_per_cta = warp_team ? 8 * rows_per_warp : 1;
     grid = (unsigned)std::min<int64_t>((B + rows_per_cta - 1) / rows_per_cta, (int64_t)sm * (tune_cps > 0 ? tune_cps : 8));
   }
-  return launch(h, k, grid, 256u, 0, p, /*coop=*/tiles_mode);
+  return launch(h, k, grid, 256u, scan_smem, p, /*coop=*/tiles_mode);
 }
 
 // ---------------------------------------------------------------------------------------------------
 // find / find_idx: stream compaction in the flat (row-major) order of the expression
 // ---------------------------------------------------------------------------------------------------
-int mxb_find(mxb_handle_t h, const mxb_expr_t *expr_in, int select_op, double threshold, const mxb_out_t *out,
-             const mxb_out_t *count_out, int want_indices) {
+static int find_impl(mxb_handle_t h, const mxb_expr_t *expr_in, int select_op, double threshold, const mxb_out_t *out,
+                     const mxb_out_t *count_out, int want_indices, bool unique) {
   if (!h) return fail(MXB_ERR_INVALID, "null handle");
   if (!expr_in) return fail(MXB_ERR_INVALID, "null expression");
   if (expr_in->rank >= 0 && expr_in->rank <= MXB_MAX_RANK && count_out && count_out->data && count_out->rank == 0 && count_out->dtype == MXB_I32) {
@@ -2015,7 +2077,8 @@ int mxb_find(mxb_handle_t h, const mxb_expr_t *expr_in, int select_op, double th
   }
   int st = check_expr_shape(expr_in);
   if (st != MXB_OK) return st;
-  if (select_op < 0 || select_op >= MXB_SEL_COUNT) return fail(MXB_ERR_INVALID, "unknown selection op");
+  if (unique) select_op = MXB_SEL_COUNT;   // internal: adjacent-difference flags over a sorted operand (mxb_unique)
+  else if (select_op < 0 || select_op >= MXB_SEL_COUNT) return fail(MXB_ERR_INVALID, "unknown selection op");
   if (!out || !out->data) return fail(MXB_ERR_INVALID, "null output");
   if (out->rank != 1 || (out->size[0] > 1 && out->stride[0] != 1)) return fail(MXB_ERR_INVALID, "find output must be rank 1 and contiguous");
   if (!count_out || !count_out->data) return fail(MXB_ERR_INVALID, "null count output");
@@ -2099,13 +2162,20 @@ int mxb_find(mxb_handle_t h, const mxb_expr_t *expr_in, int select_op, double th
   Kernel k;
 
   // ---- one pass (select1p): a view that collapses to one dim, counts that fit 32 bits --------------------------------
-  if (g.n == 1 && N < (1ll << 32) - TILE && env_int("MXB_SEL_TWO_PASS", 0) == 0) {
+  if (unique && !(g.n == 1 && N < (1ll << 32) - TILE)) return fail(MXB_ERR_NOT_SUPPORTED, "unique of more than 2^32 elements");
+  if (g.n == 1 && N < (1ll << 32) - TILE && (unique || env_int("MXB_SEL_TWO_PASS", 0) == 0)) {
     if (V == 1) p.all_unit = 0;
     spec.team = want_indices ? 4 : 3;
     spec.out_dtype = out->dtype;
     st = get_kernel(info, spec, &k);
     if (st != MXB_OK) return st;
-    const unsigned smem = (unsigned)(2 * TILE * dtype_bytes(out->dtype));
+    // pipeline depth: tiles of a CTA between rank + stage (phase 1) and offset + copy-out (phase 2); every staged tile
+    // holds up to TILE output elements.  4 is the depth at which every exchange job finds its inputs published
+    int depth = env_int("MXB_TUNE_SEL_DEPTH", 0) > 0 ? env_int("MXB_TUNE_SEL_DEPTH", 0) : 4;
+    while (depth > 2 && (int64_t)depth * TILE * dtype_bytes(out->dtype) > 96 * 1024) --depth;
+    depth = std::min(depth, 8);
+    p.sel_depth = depth;
+    const unsigned smem = (unsigned)(depth * TILE * dtype_bytes(out->dtype));
     const int res = resident_ctas(k, 256, smem, 3);
     const int cps = env_int("MXB_TUNE_SEL_CTAS", 0) > 0 ? std::min(env_int("MXB_TUNE_SEL_CTAS", 0), res) : res;
     const unsigned grid = (unsigned)std::min<int64_t>(ntiles, (int64_t)h->sm_count * cps);
@@ -2135,6 +2205,318 @@ int mxb_find(mxb_handle_t h, const mxb_expr_t *expr_in, int select_op, double th
   st = get_kernel(info, spec, &k);
   if (st != MXB_OK) return st;
   return launch(h, k, grid, 256, 0, p);
+}
+
+int mxb_find(mxb_handle_t h, const mxb_expr_t *expr_in, int select_op, double threshold, const mxb_out_t *out,
+             const mxb_out_t *count_out, int want_indices) {
+  return find_impl(h, expr_in, select_op, threshold, out, count_out, want_indices, false);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// hist: even-width histogram of every row (reference: hist_impl, transforms/cub.h:2464-2503)
+// ---------------------------------------------------------------------------------------------------
+int mxb_hist(mxb_handle_t h, const mxb_expr_t *expr_in, double lower, double upper, const mxb_out_t *out) {
+  if (!h) return fail(MXB_ERR_INVALID, "null handle");
+  int st = check_expr_shape(expr_in);
+  if (st != MXB_OK) return st;
+  if (expr_in->rank < 1) return fail(MXB_ERR_INVALID, "hist needs rank >= 1");
+  if (!out || !out->data) return fail(MXB_ERR_INVALID, "null output");
+  if (out->dtype != MXB_I32) return fail(MXB_ERR_INVALID, "histogram output must be MXB_I32 (the reference static_asserts int)");
+  if (out->rank != expr_in->rank) return fail(MXB_ERR_SIZE, "histogram output rank must equal the input rank");
+  for (int d = 0; d + 1 < out->rank; ++d)
+    if (out->size[d] != expr_in->size[d]) return fail(MXB_ERR_SIZE, "output size mismatch in dim " + std::to_string(d));
+  const int64_t bins = out->size[out->rank - 1];
+  if (bins < 1 || bins > (1 << 24)) return fail(MXB_ERR_INVALID, "bin count out of range");
+  if (!(upper > lower)) return fail(MXB_ERR_INVALID, "hist needs lower < upper");
+  if (bins > 1 && out->stride[out->rank - 1] != 1) return fail(MXB_ERR_NOT_SUPPORTED, "the bins of a row must be contiguous");
+  MXB_CUDA(cudaSetDevice(h->device));
+  mxb_expr_t e;
+  std::string err;
+  st = canonicalize(expr_in, &e, &err);
+  if (st != MXB_OK) return fail(st, err);
+  ExprInfo info;
+  st = analyze_expr(&e, &info, &err);
+  if (st != MXB_OK) return fail(st, err);
+  const int vt = info.value_dtype;
+  if (!(vt == MXB_F32 || vt == MXB_F64 || vt == MXB_I32 || vt == MXB_I64 || vt == MXB_U8))
+    return fail(MXB_ERR_NOT_SUPPORTED, "hist of this value type is not lowered");
+
+  const int nbd = e.rank - 1, nl = e.n_leaves;
+  Group gb;
+  gb.n = nbd;
+  for (int d = 0; d < nbd; ++d) {
+    gb.size[d] = e.size[d];
+    for (int k = 0; k < nl; ++k) gb.ls[k][d] = e.leaves[k].stride[d];
+    gb.os[d] = out->stride[d];
+    gb.is[d] = 0;
+  }
+  collapse(gb, nl);
+  if (gb.n > KMAXD) return fail(MXB_ERR_NOT_SUPPORTED, "batch dims do not collapse to <= 4");
+  const int64_t L = e.size[e.rank - 1];
+  int64_t B = 1;
+  for (int d = 0; d < gb.n; ++d) B *= gb.size[d];
+  if (B == 0) return MXB_OK;
+  // the output is an accumulator: zero every row's bins on the stream first (rows may be strided)
+  {
+    bool dense = true;
+    int64_t w = bins;
+    for (int d = nbd - 1; d >= 0; --d) { if (out->size[d] > 1 && out->stride[d] != w) dense = false; w *= out->size[d]; }
+    if (dense) MXB_CUDA(cudaMemsetAsync(out->data, 0, (size_t)(B * bins) * 4, h->stream));
+    else if (gb.n <= 1) MXB_CUDA(cudaMemset2DAsync(out->data, (size_t)(gb.n ? gb.os[0] : bins) * 4, 0, (size_t)bins * 4, (size_t)B, h->stream));
+    else return fail(MXB_ERR_NOT_SUPPORTED, "histogram rows must be dense or singly strided");
+  }
+  if (L == 0) return MXB_OK;
+
+  int V = policy_vmax(info);
+  auto in_ok = [&](int v) {
+    for (int k = 0; k < nl; ++k) {
+      const int64_t in = e.leaves[k].stride[e.rank - 1];
+      if (in != 0 && in != 1) return false;
+      if (in == 0) continue;
+      if (!aligned_to(e.leaves[k].data, (int64_t)v * dtype_bytes(e.leaves[k].dtype))) return false;
+      for (int d = 0; d < gb.n; ++d) if (gb.ls[k][d] % v) return false;
+    }
+    return true;
+  };
+  if (V > 1 && !in_ok(V)) V = 1;
+  KernelSpec spec;
+  spec.family = FAM_HIST;
+  spec.op = -1;
+  spec.out_dtype = MXB_I32;
+  spec.V = V;
+  spec.U = 4;
+  Kernel k;
+  st = get_kernel(info, spec, &k);
+  if (st != MXB_OK) return st;
+
+  RedParams p;
+  memset(&p, 0, sizeof p);
+  p.nb = gb.n;
+  p.nr = 1;
+  p.B = B;
+  p.R = L;
+  p.nleaf = nl;
+  for (int d = 0; d < gb.n; ++d) {
+    p.bsz[d] = gb.size[d];
+    p.out.bs[d] = gb.os[d];
+    for (int kk = 0; kk < nl; ++kk) p.leaf[kk].bs[d] = gb.ls[kk][d];
+  }
+  p.rsz[0] = L;
+  bool unit = nl > 0;
+  for (int kk = 0; kk < nl; ++kk) {
+    p.leaf[kk].rs[0] = e.leaves[kk].stride[e.rank - 1];
+    p.leaf[kk].ptr = e.leaves[kk].data;
+    unit = unit && p.leaf[kk].rs[0] == 1;
+  }
+  p.all_unit = unit ? 1 : 0;
+  p.out.ptr = out->data;
+  fill_consts(e, p.c);
+  p.hist_lo_d = lower;
+  p.hist_hi_d = upper;
+  p.hist_lo_i = (int64_t)lower;
+  p.hist_hi_i = (int64_t)upper;
+  p.hist_bins = (int)bins;
+  const int64_t smem_need = bins * 4;
+  p.hist_smem = smem_need <= 128 * 1024 ? 1 : 0;
+  const unsigned smem = p.hist_smem ? (unsigned)smem_need : 0u;
+  // chunks per row: enough items to fill the machine, at least 64 K elements each (the flush costs `bins` atomics)
+  const int64_t grid_max = (int64_t)h->sm_count * 8;
+  int64_t S = 1;
+  if (B < grid_max) S = std::max<int64_t>(1, std::min<int64_t>((grid_max + B - 1) / B, (L + 65535) / 65536));
+  p.splits = (int)S;
+  const unsigned grid = (unsigned)std::min<int64_t>(B * S, grid_max);
+  return launch(h, k, grid, 256u, smem, p);
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------
+// sort: every row of the innermost dim, keys only (reference: sort_impl, transforms/cub.h:2145-2190)
+// ---------------------------------------------------------------------------------------------------
+namespace {
+int ensure_buf(mxb_context *h, void **buf, size_t *have, size_t bytes) {
+  if (bytes > *have) {
+    if (*buf) MXB_CUDA(cudaFreeAsync(*buf, h->stream));
+    const size_t nb = std::max<size_t>(bytes, 64 * 1024);
+    MXB_CUDA(cudaMallocAsync(buf, nb, h->stream));
+    *have = nb;
+  }
+  return MXB_OK;
+}
+
+template <class K>
+int sort_rows_typed(mxb_context *h, const void *in, void *out, int kind, int64_t B, int64_t L, bool desc) {
+  mxbsort::SortParams p;
+  memset(&p, 0, sizeof p);
+  p.B = B;
+  p.L = L;
+  p.kind = kind;
+  p.desc = desc ? 1 : 0;
+  const int sm = h->sm_count;
+  if (L <= 4096) {
+    int n2 = 1;
+    while (n2 < L) n2 <<= 1;
+    if (n2 < 2) n2 = 2;
+    p.in = in;
+    p.out = out;
+    const unsigned grid = (unsigned)std::min<int64_t>(B, (int64_t)sm * 8);
+    if (!g_plan) mxbsort::bitonic_rows_kernel<K><<<grid, 256, (size_t)n2 * sizeof(K), h->stream>>>(p, n2);
+    MXB_CUDA(cudaGetLastError());
+    h->launches++;
+    h->last_kernel = std::string("sort_bitonic|") + (sizeof(K) == 4 ? "k32" : "k64");
+    return MXB_OK;
+  }
+  if (L >= (1ll << 32)) return fail(MXB_ERR_NOT_SUPPORTED, "rows of 2^32 or more keys");
+  const int passes = (int)sizeof(K);
+  int64_t cpr = std::max<int64_t>(1, std::min<int64_t>((L + 8191) / 8192, 2048));
+  if (B * cpr > (1ll << 22)) cpr = std::max<int64_t>(1, (1ll << 22) / B);
+  const int64_t chunk = ((L + cpr - 1) / cpr + 255) / 256 * 256;
+  cpr = (L + chunk - 1) / chunk;
+  p.cpr = (int)cpr;
+  p.chunk = chunk;
+  int st = ensure_buf(h, &h->tmp, &h->tmp_bytes, (size_t)(B * L) * sizeof(K));
+  if (st != MXB_OK) return st;
+  const size_t words = (size_t)(B * cpr) * 256;
+  if (2 * words > h->sort_ctr_words) {
+    if (h->sort_ctr) MXB_CUDA(cudaFreeAsync(h->sort_ctr, h->stream));
+    MXB_CUDA(cudaMallocAsync((void **)&h->sort_ctr, 2 * words * 4, h->stream));
+    h->sort_ctr_words = 2 * words;
+  }
+  p.counts = h->sort_ctr;
+  p.offsets = h->sort_ctr + words;
+  const unsigned grid = (unsigned)std::min<int64_t>(B * cpr, (int64_t)sm * 8);
+  const void *src = in;
+  for (int pass = 0; pass < passes; ++pass) {
+    // ping-pong: the even number of passes ends in `out`
+    void *dst = (pass & 1) ? out : h->tmp;
+    p.in = src;
+    p.out = dst;
+    p.shift = 8 * pass;
+    p.first = pass == 0;
+    p.last = pass == passes - 1;
+    if (!g_plan) {
+      mxbsort::radix_count_kernel<K><<<grid, 256, 0, h->stream>>>(p);
+      mxbsort::radix_scan_kernel<<<(unsigned)std::min<int64_t>(B, (int64_t)sm * 8), 256, 0, h->stream>>>(p);
+      mxbsort::radix_scatter_kernel<K><<<grid, 256, 0, h->stream>>>(p);
+    }
+    MXB_CUDA(cudaGetLastError());
+    h->launches += 3;
+    src = dst;
+  }
+  h->last_kernel = std::string("sort_radix|") + (sizeof(K) == 4 ? "k32" : "k64") + "|passes=" + std::to_string(passes);
+  return MXB_OK;
+}
+
+int sort_rows(mxb_context *h, const void *in, void *out, int dtype, int64_t B, int64_t L, bool desc) {
+  if (B == 0 || L == 0) return MXB_OK;
+  switch (dtype) {
+    case MXB_F32: return sort_rows_typed<uint32_t>(h, in, out, 2, B, L, desc);
+    case MXB_I32: return sort_rows_typed<uint32_t>(h, in, out, 1, B, L, desc);
+    case MXB_F64: return sort_rows_typed<unsigned long long>(h, in, out, 2, B, L, desc);
+    case MXB_I64: return sort_rows_typed<unsigned long long>(h, in, out, 1, B, L, desc);
+    default: return fail(MXB_ERR_NOT_SUPPORTED, "sort of this key type is not lowered (fp32, fp64, int32, int64)");
+  }
+}
+
+// a program that is ONE leaf walking `dims` row-major-contiguously with the output's dtype: sortable in place of a copy
+const void *plain_contiguous_leaf(const mxb_expr_t &e, int out_dtype) {
+  if (e.n_nodes != 1 || e.nodes[0].opcode != MXB_OP_LEAF || e.n_leaves != 1) return nullptr;
+  const mxb_leaf_t &lf = e.leaves[0];
+  if (lf.dtype != out_dtype) return nullptr;
+  int64_t w = 1;
+  for (int d = e.rank - 1; d >= 0; --d) {
+    if (e.size[d] > 1 && lf.stride[d] != w) return nullptr;
+    w *= e.size[d];
+  }
+  return lf.data;
+}
+}  // namespace
+
+extern "C" {
+
+int mxb_sort(mxb_handle_t h, const mxb_expr_t *expr_in, const mxb_out_t *out, int descending) {
+  if (!h) return fail(MXB_ERR_INVALID, "null handle");
+  int st = check_expr_shape(expr_in);
+  if (st != MXB_OK) return st;
+  if (expr_in->rank < 1) return fail(MXB_ERR_INVALID, "sort needs rank >= 1");
+  if (!out || !out->data) return fail(MXB_ERR_INVALID, "null output");
+  if (out->rank != expr_in->rank) return fail(MXB_ERR_SIZE, "sort output rank must equal the input rank");
+  int64_t w = 1, N = 1;
+  for (int d = out->rank - 1; d >= 0; --d) {
+    if (out->size[d] != expr_in->size[d]) return fail(MXB_ERR_SIZE, "output size mismatch in dim " + std::to_string(d));
+    if (out->size[d] > 1 && out->stride[d] != w) return fail(MXB_ERR_NOT_SUPPORTED, "sort output must be contiguous (the reference requires it too)");
+    w *= out->size[d];
+    N *= out->size[d];
+  }
+  MXB_CUDA(cudaSetDevice(h->device));
+  mxb_expr_t e;
+  std::string err;
+  st = canonicalize(expr_in, &e, &err);
+  if (st != MXB_OK) return fail(st, err);
+  ExprInfo info;
+  st = analyze_expr(&e, &info, &err);
+  if (st != MXB_OK) return fail(st, err);
+  if (info.value_dtype != out->dtype) return fail(MXB_ERR_INVALID, "sort output dtype must equal the operand's value type");
+  if (N == 0) return MXB_OK;
+  const int64_t L = e.size[e.rank - 1], B = N / L;
+  const void *src = plain_contiguous_leaf(e, out->dtype);
+  if (!src) {
+    // an expression / a strided view: evaluate it into the output (contiguous) and sort there, like the reference's copy
+    st = mxb_elementwise(h, expr_in, out);
+    if (st != MXB_OK) return st;
+    src = out->data;
+  }
+  return sort_rows(h, src, out->data, out->dtype, B, L, descending != 0);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// unique: sorted distinct values of a rank-1 operand + their count (reference: unique_impl, transforms/cub.h:2796-2842)
+// ---------------------------------------------------------------------------------------------------
+int mxb_unique(mxb_handle_t h, const mxb_expr_t *expr_in, const mxb_out_t *out, const mxb_out_t *count_out) {
+  if (!h) return fail(MXB_ERR_INVALID, "null handle");
+  int st = check_expr_shape(expr_in);
+  if (st != MXB_OK) return st;
+  if (expr_in->rank != 1) return fail(MXB_ERR_NOT_SUPPORTED, "unique serves rank-1 operands");
+  if (!out || !out->data || out->rank != 1 || (out->size[0] > 1 && out->stride[0] != 1)) return fail(MXB_ERR_INVALID, "unique output must be rank 1 and contiguous");
+  if (!count_out || !count_out->data || count_out->rank != 0 || count_out->dtype != MXB_I32) return fail(MXB_ERR_INVALID, "num_found must be a rank-0 MXB_I32");
+  MXB_CUDA(cudaSetDevice(h->device));
+  const int64_t N = expr_in->size[0];
+  if (N == 0) {
+    MXB_CUDA(cudaMemsetAsync(count_out->data, 0, sizeof(int), h->stream));
+    return MXB_OK;
+  }
+  mxb_expr_t e;
+  std::string err;
+  st = canonicalize(expr_in, &e, &err);
+  if (st != MXB_OK) return fail(st, err);
+  ExprInfo info;
+  st = analyze_expr(&e, &info, &err);
+  if (st != MXB_OK) return fail(st, err);
+  const int vt = info.value_dtype;
+  if (vt != out->dtype) return fail(MXB_ERR_INVALID, "unique output dtype must equal the operand's value type");
+  if (!(vt == MXB_F32 || vt == MXB_F64 || vt == MXB_I32 || vt == MXB_I64)) return fail(MXB_ERR_NOT_SUPPORTED, "unique of this value type is not lowered");
+  st = ensure_buf(h, &h->tmp2, &h->tmp2_bytes, (size_t)N * dtype_bytes(vt));
+  if (st != MXB_OK) return st;
+  mxb_out_t sorted;
+  memset(&sorted, 0, sizeof sorted);
+  sorted.data = h->tmp2;
+  sorted.dtype = vt;
+  sorted.rank = 1;
+  sorted.size[0] = N;
+  sorted.stride[0] = 1;
+  st = mxb_sort(h, expr_in, &sorted, 0);
+  if (st != MXB_OK) return st;
+  mxb_expr_t se;
+  memset(&se, 0, sizeof se);
+  se.rank = 1;
+  se.size[0] = N;
+  se.n_nodes = 1;
+  se.n_leaves = 1;
+  se.nodes[0] = mxb_node_t{MXB_OP_LEAF, {0, -1}, 0};
+  se.leaves[0].data = h->tmp2;
+  se.leaves[0].dtype = vt;
+  se.leaves[0].stride[0] = 1;
+  return find_impl(h, &se, 0, 0.0, out, count_out, 0, /*unique=*/true);
 }
 
 int mxb_is_aot(const mxb_expr_t *expr, int reduce_op_or_minus1) {

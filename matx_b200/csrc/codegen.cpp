@@ -144,8 +144,8 @@ bool is_binary(int op) { return op >= MXB_OP_ADD && op <= MXB_OP_ATAN2; }
 static int analyze_expr_uncached(const mxb_expr_t *e, ExprInfo *info, std::string *err);
 int analyze_expr(const mxb_expr_t *e, ExprInfo *info, std::string *err) {
   if (!e || e->n_nodes <= 0 || e->n_nodes > MXB_MAX_NODES || e->n_leaves < 0 || e->n_leaves > MXB_MAX_LEAVES || e->n_consts < 0 ||
-      e->n_consts > MXB_MAX_CONSTS)
-    return analyze_expr_uncached(e, info, err);
+      e->n_consts > MXB_MAX_CONSTS || e->rank < 0 || e->rank > MXB_MAX_RANK)
+    return analyze_expr_uncached(e, info, err);   // malformed: the uncached path names the problem
   std::string key;
   key.reserve(16 + (size_t)e->n_nodes * sizeof(mxb_node_t) + (size_t)(e->n_leaves + e->n_consts) * 4);
   const int32_t head[4] = {e->n_nodes, e->n_leaves, e->n_consts, e->root};
@@ -465,6 +465,7 @@ int policy_unroll(const ExprInfo &info, int V, int family) {
   if (family == FAM_VAR_REG || family == FAM_VAR_TMA || family == FAM_VAR_GROUP || family == FAM_SM_GROUP || family == FAM_SM_REG) return 1;
   if (family == FAM_EW_TR) return 1;
   if (family == FAM_SELECT) return 4;
+  if (family == FAM_HIST) return 4;
   if (family == FAM_VAR_SMEM) return bytes >= 32 ? 4 : 8;
   if (family == FAM_EW) return bytes >= 32 ? (info.nleaf <= 2 ? 2 : 1) : (info.nleaf <= 2 ? 4 : 2);
   return bytes >= 32 ? 2 : (info.nleaf <= 2 ? 4 : 2);
@@ -472,7 +473,7 @@ int policy_unroll(const ExprInfo &info, int V, int family) {
 
 std::string kernel_key(const ExprInfo &info, const KernelSpec &s) {
   std::ostringstream k;
-  static const char *fam[] = {"red_inner", "red_outer", "var_smem", "ew", "var_reg", "var_tma", "var_group", "softmax_group", "softmax_reg", "ew_tr", "scan", "red_outer_tma", "select", "var_tma2"};
+  static const char *fam[] = {"red_inner", "red_outer", "var_smem", "ew", "var_reg", "var_tma", "var_group", "softmax_group", "softmax_reg", "ew_tr", "scan", "red_outer_tma", "select", "var_tma2", "hist"};
   k << fam[s.family] << "|" << info.name << "|" << (s.op >= 0 ? reduce_op_name(s.op) : "-") << "|" << dtype_name(s.out_dtype)
     << "|V" << s.V << "|U" << s.U << "|T" << s.team;
   if (s.minb > 0) k << "|M" << s.minb;
@@ -594,6 +595,12 @@ int kernel_wrapper_src(const ExprInfo &info, const KernelSpec &s, const std::str
       else
         k << "extern \"C\" __global__ void __launch_bounds__(256) " << symbol
           << "(const __grid_constant__ mxb::EwParams p) { mxb::select_body<" << E << ", " << O << ", " << s.V << ", " << s.team << ">(p); }\n";
+      break;
+    case FAM_HIST:
+      if (!(info.value_dtype == MXB_F32 || info.value_dtype == MXB_F64 || info.value_dtype == MXB_I32 || info.value_dtype == MXB_I64 || info.value_dtype == MXB_U8))
+        return fail("hist serves real value types");
+      k << "extern \"C\" __global__ void __launch_bounds__(256) " << symbol
+        << "(const __grid_constant__ mxb::RedParams p) { mxb::hist_body<" << E << ", " << VU << ">(p); }\n";
       break;
     default: return fail("unknown kernel family");
   }

@@ -119,6 +119,12 @@ struct RedParams {
   // values, 16-byte slots for 8-byte values), the device-resident launch epoch and the exit ticket
   void *scan_agg, *scan_gagg, *scan_sagg;
   u32 *scan_ctl;
+  // hist family: HistogramEven bounds and bin count (reference: cub::DeviceHistogram::HistogramEven behind hist_impl)
+  double hist_lo_d, hist_hi_d;
+  i64 hist_lo_i, hist_hi_i;
+  int hist_bins;
+  int hist_smem;    // 1 = privatised bins in shared memory, 0 = straight to global memory (more bins than fit)
+  int scan_depth;   // tiles of one CTA between their phase 1 (local scan, parked in shared memory) and phase 2 (carry + store)
   int scan_group;   // warp team, rows of <= 32 vectors: lanes per row (power of two), 0 = a whole warp per row
   u32 scan_flags;   // TILES mode: bit 0 issues the next tile's loads before the publish instead of after (sweep knob)
   int tma_rt;       // reduce_outer_tma: reduce rows per ring stage (splits = ring depth, tx = 16-byte chunks per strip)
@@ -167,6 +173,7 @@ struct EwParams {
   // epoch (device-resident: bumped by the last CTA out, so a CUDA-graph replay sees a fresh epoch too) and the exit ticket
   unsigned long long *sel_status;
   u32 *sel_epoch;
+  int sel_depth;                   // tiles of one CTA between their phase 1 (rank + stage) and phase 2 (offset + copy-out): 4..8
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -2718,36 +2725,40 @@ __device__ __forceinline__ void st_relaxed_u64(unsigned long long *p, unsigned l
 template <class T, int BYTES = (int)sizeof(T)> struct ScanSlot;
 template <class T> struct ScanSlot<T, 4> {
   enum { STRIDE = 8 };
+  struct Word { unsigned long long w; };
   static __device__ __forceinline__ void publish(void *slots, i64 i, T v, u32 tag) {
     union { T t; u32 w; } u;
     u.t = v;
     st_relaxed_u64((unsigned long long *)slots + i, ((unsigned long long)tag << 32) | u.w);
   }
+  static __device__ __forceinline__ Word peek(const void *slots, i64 i) { Word r; r.w = ld_relaxed_u64((const unsigned long long *)slots + i); return r; }
+  static __device__ __forceinline__ bool ready(const Word &r, u32 tag) { return (u32)(r.w >> 32) == tag; }
+  static __device__ __forceinline__ T value(const Word &r) { union { T t; u32 w; } u; u.w = (u32)r.w; return u.t; }
   static __device__ __forceinline__ T wait(const void *slots, i64 i, u32 tag) {
-    unsigned long long w = ld_relaxed_u64((const unsigned long long *)slots + i);
-    while ((u32)(w >> 32) != tag) { __nanosleep(20); w = ld_relaxed_u64((const unsigned long long *)slots + i); }
-    union { T t; u32 w; } u;
-    u.w = (u32)w;
-    return u.t;
+    Word r = peek(slots, i);
+    while (!ready(r, tag)) { __nanosleep(20); r = peek(slots, i); }
+    return value(r);
   }
 };
 template <class T> struct ScanSlot<T, 8> {
   enum { STRIDE = 16 };
+  struct Word { unsigned long long f, w; };
   static __device__ __forceinline__ void publish(void *slots, i64 i, T v, u32 tag) {
     union { T t; unsigned long long w; } u;
     u.t = v;
     asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"((unsigned long long *)slots + 2 * i), "l"((unsigned long long)tag << 32), "l"(u.w) : "memory");
   }
+  static __device__ __forceinline__ Word peek(const void *slots, i64 i) {
+    Word r;
+    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(r.f), "=l"(r.w) : "l"((const unsigned long long *)slots + 2 * i) : "memory");
+    return r;
+  }
+  static __device__ __forceinline__ bool ready(const Word &r, u32 tag) { return (u32)(r.f >> 32) == tag; }
+  static __device__ __forceinline__ T value(const Word &r) { union { T t; unsigned long long w; } u; u.w = r.w; return u.t; }
   static __device__ __forceinline__ T wait(const void *slots, i64 i, u32 tag) {
-    unsigned long long f, w;
-    while (true) {
-      asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(f), "=l"(w) : "l"((const unsigned long long *)slots + 2 * i) : "memory");
-      if ((u32)(f >> 32) == tag) break;
-      __nanosleep(20);
-    }
-    union { T t; unsigned long long w; } u;
-    u.w = w;
-    return u.t;
+    Word r = peek(slots, i);
+    while (!ready(r, tag)) { __nanosleep(20); r = peek(slots, i); }
+    return value(r);
   }
 };
 
@@ -2776,6 +2787,92 @@ template <class T> __device__ __forceinline__ T warp_tree_sum(T v) {
   return v;
 }
 
+// One in-flight read of a published slot: issue() sends the load, get() spins only if the value was not there yet.  The
+// pipelined kernels issue the reads of an iteration's exchange jobs before the iteration's own work and collect them after
+// it, so the L2 round trip hides behind the work.
+template <class T> struct SlotRead {
+  typename ScanSlot<T>::Word w;
+  const void *slots;
+  i64 i;
+  bool on;
+  __device__ __forceinline__ void issue(const void *s, i64 idx, bool enable) {
+    slots = s; i = idx; on = enable;
+    if (on) w = ScanSlot<T>::peek(slots, i);
+  }
+  __device__ __forceinline__ T get(u32 tag) {
+    if (!on) return scan_zero<T>();
+    while (!ScanSlot<T>::ready(w, tag)) { __nanosleep(20); w = ScanSlot<T>::peek(slots, i); }
+    return ScanSlot<T>::value(w);
+  }
+};
+
+// The three-level exchange of hier_carry, split into jobs that run in DIFFERENT iterations of a pipelined tile loop
+// (depth D >= 4: phase 1 of a tile — load, local work, publish its total — runs D - 1 iterations before its phase 2 — carry,
+// store), by warp 0 of the CTA that owns the tile:
+//   close   iteration + 1  a tile that ends its group of 32 sums the group's tile totals and publishes the group total
+//   chain   iteration + 2  a tile that ends its supergroup of 32 groups publishes the running total at the next one
+//   carry   iteration + D - 1  running total at the supergroup start + group totals before + tile totals before
+// Everything a job reads was published at least one iteration earlier by CTAs running the same loop, so the reads find
+// their data instead of spinning on it (they still spin if a CTA lags), and the sums keep their fixed shape.
+template <class T> struct TileExchange {
+  char *agg, *gagg, *sagg;   // slots of row 0; row r sits tpr / gpr / spr slots further
+  i64 tpr, gpr, spr;
+  u32 tag;
+  int lane;
+  SlotRead<T> ca, cb, cc, ga, sb, sc;   // carry: tiles / groups / supergroup start; close: tiles; chain: groups / supergroup start
+  i64 close_ct, chain_ct, close_row, chain_row;
+  __device__ __forceinline__ void init(void *a, void *g, void *sp, i64 tiles_per_row, u32 tg, int ln) {
+    agg = (char *)a; gagg = (char *)g; sagg = (char *)sp;
+    tpr = tiles_per_row; gpr = (tpr + 31) >> 5; spr = (tpr + 1023) >> 10;
+    tag = tg; lane = ln;
+    close_ct = chain_ct = -1; close_row = chain_row = 0;
+  }
+  __device__ __forceinline__ char *A(i64 row) const { return agg + (size_t)(row * tpr) * ScanSlot<T>::STRIDE; }
+  __device__ __forceinline__ char *G(i64 row) const { return gagg + (size_t)(row * gpr) * ScanSlot<T>::STRIDE; }
+  __device__ __forceinline__ char *S(i64 row) const { return sagg + (size_t)(row * spr) * ScanSlot<T>::STRIDE; }
+  __device__ __forceinline__ bool closes_group(i64 ct) const { return (ct & 31) == 31 || ct == tpr - 1; }
+  __device__ __forceinline__ bool closes_super(i64 ct) const { return (ct & 1023) == 1023 && ct != tpr - 1; }
+  // a tile publishes its own total (phase 1)
+  __device__ __forceinline__ void publish_tile(i64 row, i64 ct, T total) const { ScanSlot<T>::publish(A(row), ct, total, tag); }
+  // top of an iteration: (row, tile within the row) of the close / chain / carry job, tile < 0 = none
+  __device__ __forceinline__ void issue(i64 row_close, i64 ct_close, i64 row_chain, i64 ct_chain, i64 row_carry, i64 ct_carry) {
+    close_ct = (ct_close >= 0 && closes_group(ct_close)) ? ct_close : -1;
+    chain_ct = (ct_chain >= 0 && closes_super(ct_chain)) ? ct_chain : -1;
+    close_row = row_close;
+    chain_row = row_chain;
+    {
+      const i64 first = (close_ct >> 5) << 5;
+      ga.issue(A(row_close), first + lane, close_ct >= 0 && first + lane < close_ct);
+    }
+    {
+      const i64 sg = chain_ct >> 10;
+      sb.issue(G(row_chain), (sg << 5) + lane, chain_ct >= 0);
+      sc.issue(S(row_chain), sg, chain_ct >= 0 && sg > 0 && lane == 0);
+    }
+    {
+      const i64 g = ct_carry >> 5, first = g << 5, sg = ct_carry >> 10, gfirst = sg << 5;
+      ca.issue(A(row_carry), first + lane, ct_carry >= 0 && first + lane < ct_carry);
+      cb.issue(G(row_carry), gfirst + lane, ct_carry >= 0 && gfirst + lane < g);
+      cc.issue(S(row_carry), sg, ct_carry >= 0 && sg > 0 && lane == 0);
+    }
+  }
+  // bottom of the iteration: finish the jobs; `close_total` = the closing tile's own total; returns the carry (all lanes)
+  __device__ __forceinline__ T finish(T close_total) {
+    if (close_ct >= 0) {
+      const T gt = warp_tree_sum(ga.get(tag)) + close_total;
+      if (lane == 0) ScanSlot<T>::publish(G(close_row), close_ct >> 5, gt, tag);
+    }
+    if (chain_ct >= 0) {
+      const T st = warp_tree_sum(sb.get(tag));
+      const T c = shfl_idx_t(sc.get(tag), 0);
+      if (lane == 0) ScanSlot<T>::publish(S(chain_row), (chain_ct >> 10) + 1, c + st, tag);
+    }
+    const T sa = warp_tree_sum(ca.get(tag)), sbb = warp_tree_sum(cb.get(tag));
+    const T c = shfl_idx_t(cc.get(tag), 0);
+    return (c + sbb) + sa;
+  }
+};
+
 // Carry of tile `ct` (of a row of `tpr` tiles) from the published totals, by ONE warp (all 32 lanes call it; every lane
 // returns the carry).  The caller has already published this tile's own total in agg[ct].  Three levels, all loads in
 // flight at once: running total at the start of the tile's supergroup (1024 tiles; chained, published by the last tile
@@ -2788,18 +2885,21 @@ template <class T>
 __device__ __forceinline__ T hier_carry(void *agg, void *gagg, void *sagg, i64 ct, i64 tpr, T total, u32 tag, int lane) {
   const i64 g = ct >> 5, first = g << 5, sg = ct >> 10, gfirst = sg << 5;
   const int n2 = (int)(ct - first), n1 = (int)(g - gfirst);
-  T a = scan_zero<T>(), b = scan_zero<T>(), c = scan_zero<T>();
+  // the group's total goes out as soon as the group's own tiles are in — BEFORE waiting for anything of an earlier
+  // group: the first tiles of the next group wait for it, and waiting for earlier groups first would chain the groups
+  T a = scan_zero<T>();
   if (lane < n2) a = ScanSlot<T>::wait(agg, first + lane, tag);
+  const T sa = warp_tree_sum(a);
+  const bool last_tile = ct == tpr - 1;
+  const bool closes_group = (ct & 31) == 31 || last_tile;
+  const T gt = sa + total;                         // this group's total (meaningful when the tile closes its group)
+  if (closes_group && lane == 0) ScanSlot<T>::publish(gagg, g, gt, tag);
+  T b = scan_zero<T>(), c = scan_zero<T>();
   if (lane < n1) b = ScanSlot<T>::wait(gagg, gfirst + lane, tag);
   if (lane == 0 && sg > 0) c = ScanSlot<T>::wait(sagg, sg, tag);
-  const T sa = warp_tree_sum(a), sb = warp_tree_sum(b);
+  const T sb = warp_tree_sum(b);
   c = shfl_idx_t(c, 0);
-  const bool last_tile = ct == tpr - 1;
-  if ((ct & 31) == 31 || last_tile) {
-    const T gt = sa + total;                       // this group's total
-    if (lane == 0) ScanSlot<T>::publish(gagg, g, gt, tag);
-    if (((g & 31) == 31) && !last_tile && lane == 0) ScanSlot<T>::publish(sagg, sg + 1, c + (sb + gt), tag);
-  }
+  if (closes_group && ((g & 31) == 31) && !last_tile && lane == 0) ScanSlot<T>::publish(sagg, sg + 1, c + (sb + gt), tag);
   return (c + sb) + sa;
 }
 
@@ -2963,27 +3063,20 @@ __device__ __forceinline__ void scan_warp_body_impl(const RedParams &p) {
 }
 
 template <class E, class OutT, int V, int U, bool UNIT>
-__device__ __forceinline__ void scan_inner_body_impl(const RedParams &p) {
+__device__ __forceinline__ void scan_inner_body_impl(const RedParams &p) {   // mode ROWS: a CTA walks whole rows
   typedef typename E::value_type T;
   constexpr int NT = SCAN_NT, NW = NT / 32;
-  __shared__ T s_warp[2][U][NW];   // warp totals of every chunk, double-buffered by tile parity: one barrier per tile (ROWS)
-  __shared__ T s_carry[2];         // TILES: the tile's carry, from warp 0
+  __shared__ T s_warp[2][U][NW];   // warp totals of every chunk, double-buffered by tile parity: one barrier per tile
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const i64 L = p.rsz[0];
   const i64 TILE = (i64)NT * V * U;
   const i64 tpr = (L + TILE - 1) / TILE;          // tiles per row
-  const bool tiles_mode = p.splits > 1;
-  const i64 gpr = (tpr + 31) >> 5, spr = (tpr + 1023) >> 10;
-  const i64 total_tiles = p.B * tpr;
   const i64 oinner = p.out_rs[0];
-  u32 tag = 0;
-  if (tiles_mode) tag = ((__ldcg(p.scan_ctl) & 0x3fffffffu) << 2) | 1u;
 
   const char *base[E::NL];
   i64 inner[E::NL];
 #pragma unroll
   for (int k = 0; k < E::NL; ++k) inner[k] = p.leaf[k].rs[0];
-  // row b: leaf row bases (for the loads) and the output row
   auto setup_row = [&](i64 b) -> OutT * {
     i64 bidx[KMAXD];
     decomp(b, p.nb, p.bsz, bidx);
@@ -3000,20 +3093,165 @@ __device__ __forceinline__ void scan_inner_body_impl(const RedParams &p) {
     return (OutT *)p.out.ptr + oo;
   };
 
-  // ---- first work item ----
-  i64 cb, ct;   // current row, current tile of it
-  i64 gid = blockIdx.x;   // TILES: global tile id, advanced by gridDim.x per trip
-  bool have = true;
-  if (tiles_mode) {
-    have = gid < total_tiles;
-    cb = have ? gid / tpr : 0;
-    ct = gid - cb * tpr;
-  } else {
-    cb = blockIdx.x;
-    ct = 0;
-    have = cb < p.B;
+  i64 cb = blockIdx.x, ct = 0;
+  if (cb >= p.B) return;
+  OutT *orow = setup_row(cb);
+  typename E::template Regs<V> r[U];
+  bool full[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const i64 j = ct * TILE + ((i64)u * NT + tid) * V;
+    full[u] = V == 1 ? (j < L) : (j + V <= L);
+    if (full[u]) E::template loadv<V, UNIT>(r[u], base, inner, j);
   }
-  if (have) {
+  T carry = scan_zero<T>();
+  int par = 0;
+  while (true) {
+    const i64 j0 = ct * TILE;
+    T x[U][V];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const i64 j = j0 + ((i64)u * NT + tid) * V;
+      if (full[u]) {
+#pragma unroll
+        for (int v = 0; v < V; ++v) x[u][v] = E::template eval<V>(r[u], v, p.c);
+      } else {
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          x[u][v] = scan_zero<T>();
+          if (V > 1 && j + v < L) {
+            typename E::template Regs<1> r1;
+            E::template loadv<1, false>(r1, base, inner, j + v);
+            x[u][v] = E::template eval<1>(r1, 0, p.c);
+          }
+        }
+      }
+#pragma unroll
+      for (int v = 1; v < V; ++v) x[u][v] = x[u][v - 1] + x[u][v];
+    }
+    T wexcl[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      T incl = x[u][V - 1];
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const T o = shfl_up_t(incl, d);
+        if (lane >= d) incl = o + incl;
+      }
+      const T ex = shfl_up_t(incl, 1);
+      wexcl[u] = lane == 0 ? scan_zero<T>() : ex;
+      if (lane == 31) s_warp[par][u][warp] = incl;
+    }
+    __syncthreads();
+    T wpre[U], ctot[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      T run = scan_zero<T>();
+      wpre[u] = run;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) {
+        if (w == warp) wpre[u] = run;
+        run = run + s_warp[par][u][w];
+      }
+      ctot[u] = run;
+    }
+    // the NEXT tile's loads fly while this tile's stores go out
+    const i64 nb = ct + 1 < tpr ? cb : cb + gridDim.x;
+    const i64 nt = ct + 1 < tpr ? ct + 1 : 0;
+    const bool more = nb < p.B;
+    OutT *orow_next = orow;
+    bool full_next[U];
+    if (more) {
+      if (nb != cb) orow_next = setup_row(nb);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const i64 j = nt * TILE + ((i64)u * NT + tid) * V;
+        full_next[u] = V == 1 ? (j < L) : (j + V <= L);
+        if (full_next[u]) E::template loadv<V, UNIT>(r[u], base, inner, j);
+      }
+    }
+    T cpre = carry;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const i64 j = j0 + ((i64)u * NT + tid) * V;
+      const T pre = (cpre + wpre[u]) + wexcl[u];
+      Vec<OutT, V> o;
+#pragma unroll
+      for (int v = 0; v < V; ++v) o.v[v] = cvt<OutT>(pre + x[u][v]);
+      if (V > 1 && j + V <= L && oinner == 1 && p.tx) StBytes<(int)sizeof(OutT) * V>::st(orow + j, &o);
+      else {
+#pragma unroll
+        for (int v = 0; v < V; ++v) if (j + v < L) orow[(j + v) * oinner] = o.v[v];
+      }
+      cpre = cpre + ctot[u];
+    }
+    if (!more) break;
+    carry = nb == cb ? cpre : scan_zero<T>();
+    cb = nb;
+    ct = nt;
+    orow = orow_next;
+#pragma unroll
+    for (int u = 0; u < U; ++u) full[u] = full_next[u];
+    par ^= 1;
+  }
+}
+
+// fixed-order sum over the CTA (shuffle tree per warp, warp totals added in warp order); result in every thread
+template <class T, int NW> __device__ __forceinline__ T scan_block_sum(T v, T *s_red) {
+#pragma unroll
+  for (int m = 16; m > 0; m >>= 1) v = v + shfl_xor_t(v, m);
+  __syncthreads();                       // previous use of s_red is over
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  T tot = s_red[0];
+#pragma unroll
+  for (int w = 1; w < NW; ++w) tot = tot + s_red[w];
+  return tot;
+}
+
+// mode TILES, flat exchange (p.splits == 2; the measured default): a tile publishes its total; the LAST tile of each group
+// of SCAN_GROUP tiles also publishes the group's total; a tile's carry = (totals of the groups before its own) + (totals of
+// the tiles before it in its group): two flat, fixed-order sums of at most a few hundred L2-resident values gathered by all
+// 256 threads at once — no serial chain between tiles, no atomics, and no dependence on which neighbour happened to
+// finish first.  The next tile's loads are issued right after the publish and fly through the gather.
+constexpr int SCAN_GROUP = 128;
+template <class E, class OutT, int V, int U, bool UNIT>
+__device__ __forceinline__ void scan_tiles_flat_body_impl(const RedParams &p) {
+  typedef typename E::value_type T;
+  constexpr int NT = SCAN_NT, NW = NT / 32;
+  __shared__ T s_warp[2][U][NW];
+  __shared__ T s_red[NW + 1];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const i64 L = p.rsz[0];
+  const i64 TILE = (i64)NT * V * U;
+  const i64 tpr = (L + TILE - 1) / TILE;
+  const i64 gpr = (tpr + SCAN_GROUP - 1) / SCAN_GROUP;
+  const i64 total_tiles = p.B * tpr;
+  const i64 oinner = p.out_rs[0];
+  const u32 tag = ((__ldcg(p.scan_ctl) & 0x3fffffffu) << 2) | 1u;
+
+  const char *base[E::NL];
+  i64 inner[E::NL];
+#pragma unroll
+  for (int k = 0; k < E::NL; ++k) inner[k] = p.leaf[k].rs[0];
+  auto setup_row = [&](i64 b) -> OutT * {
+    i64 bidx[KMAXD];
+    decomp(b, p.nb, p.bsz, bidx);
+    i64 oo = 0;
+#pragma unroll
+    for (int k = 0; k < E::NL; ++k) {
+      i64 off = 0;
+#pragma unroll
+      for (int d = 0; d < KMAXD; ++d) if (d < p.nb) off += bidx[d] * p.leaf[k].bs[d];
+      base[k] = (const char *)p.leaf[k].ptr + off * E::leaf_bytes(k);
+    }
+#pragma unroll
+    for (int d = 0; d < KMAXD; ++d) if (d < p.nb) oo += bidx[d] * p.out.bs[d];
+    return (OutT *)p.out.ptr + oo;
+  };
+  i64 gid = blockIdx.x;
+  if (gid < total_tiles) {
+    i64 cb = gid / tpr, ct = gid - cb * tpr;
     OutT *orow = setup_row(cb);
     typename E::template Regs<V> r[U];
     bool full[U];
@@ -3023,12 +3261,9 @@ __device__ __forceinline__ void scan_inner_body_impl(const RedParams &p) {
       full[u] = V == 1 ? (j < L) : (j + V <= L);
       if (full[u]) E::template loadv<V, UNIT>(r[u], base, inner, j);
     }
-    T carry = scan_zero<T>();
     int par = 0;
-
     while (true) {
       const i64 j0 = ct * TILE;
-      // ---- evaluate + thread-local scan of the tile whose loads were issued one trip ago ----
       T x[U][V];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
@@ -3050,7 +3285,6 @@ __device__ __forceinline__ void scan_inner_body_impl(const RedParams &p) {
 #pragma unroll
         for (int v = 1; v < V; ++v) x[u][v] = x[u][v - 1] + x[u][v];
       }
-      // ---- warp stage: inclusive scan of the thread totals, U chunks at once ----
       T wexcl[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
@@ -3065,7 +3299,6 @@ __device__ __forceinline__ void scan_inner_body_impl(const RedParams &p) {
         if (lane == 31) s_warp[par][u][warp] = incl;
       }
       __syncthreads();   // (A)
-      // ---- CTA stage: every thread folds the warp totals it needs (broadcast reads, fixed order) ----
       T wpre[U], ctot[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
@@ -3078,50 +3311,46 @@ __device__ __forceinline__ void scan_inner_body_impl(const RedParams &p) {
         }
         ctot[u] = run;
       }
-      // ---- where the next tile is ----
-      i64 nb, nt;
-      if (tiles_mode) {
-        const i64 g = gid + gridDim.x;
-        nb = g < total_tiles ? g / tpr : p.B;
-        nt = g - nb * tpr;
-      } else {
-        nb = ct + 1 < tpr ? cb : cb + gridDim.x;
-        nt = ct + 1 < tpr ? ct + 1 : 0;
-      }
+      T total = ctot[0];
+#pragma unroll
+      for (int u = 1; u < U; ++u) total = total + ctot[u];
+      char *agg = (char *)p.scan_agg + (size_t)(cb * tpr) * ScanSlot<T>::STRIDE;
+      char *gagg = (char *)p.scan_gagg + (size_t)(cb * gpr) * ScanSlot<T>::STRIDE;
+      if (tid == 0) ScanSlot<T>::publish(agg, ct, total, tag);
+      // the NEXT tile's loads go out right behind the publish
+      const i64 ng = gid + gridDim.x;
+      const i64 nb = ng < total_tiles ? ng / tpr : p.B;
+      const i64 nt = ng - nb * tpr;
       const bool more = nb < p.B;
       OutT *orow_next = orow;
       bool full_next[U];
-      auto prefetch = [&]() {   // the NEXT tile's loads fly while this tile goes through its grid stage and its stores
-        if (more) {
-          if (nb != cb) orow_next = setup_row(nb);
+      if (more) {
+        if (nb != cb) orow_next = setup_row(nb);
 #pragma unroll
-          for (int u = 0; u < U; ++u) {
-            const i64 j = nt * TILE + ((i64)u * NT + tid) * V;
-            full_next[u] = V == 1 ? (j < L) : (j + V <= L);
-            if (full_next[u]) E::template loadv<V, UNIT>(r[u], base, inner, j);
-          }
+        for (int u = 0; u < U; ++u) {
+          const i64 j = nt * TILE + ((i64)u * NT + tid) * V;
+          full_next[u] = V == 1 ? (j < L) : (j + V <= L);
+          if (full_next[u]) E::template loadv<V, UNIT>(r[u], base, inner, j);
         }
-      };
-      if (tiles_mode) {
-        // ---- grid stage: publish first (every later tile waits for that store), then gather the carry ----
-        T total = ctot[0];
-#pragma unroll
-        for (int u = 1; u < U; ++u) total = total + ctot[u];
-        char *agg = (char *)p.scan_agg + (size_t)(cb * tpr) * ScanSlot<T>::STRIDE;
-        char *gagg = (char *)p.scan_gagg + (size_t)(cb * gpr) * ScanSlot<T>::STRIDE;
-        char *sagg = (char *)p.scan_sagg + (size_t)(cb * spr) * ScanSlot<T>::STRIDE;
-        if (tid == 0) ScanSlot<T>::publish(agg, ct, total, tag);
-        prefetch();
-        if (warp == 0) {
-          const T cr = hier_carry<T>(agg, gagg, sagg, ct, tpr, total, tag, lane);
-          if (lane == 0) s_carry[par] = cr;
-        }
-        __syncthreads();   // (B)
-        carry = s_carry[par];
-      } else {
-        prefetch();
       }
-      // ---- finish: carry + chunk prefix + warp prefix + lane prefix + local scan, one vector store ----
+      const i64 g = ct / SCAN_GROUP, first = g * SCAN_GROUP;
+      const i64 gcount = (tpr - first) < SCAN_GROUP ? (tpr - first) : SCAN_GROUP;
+      const i64 n1 = g, n2 = ct - first;
+      T carry;
+      if (ct == first + gcount - 1) {
+        T a = scan_zero<T>();
+        for (i64 i = tid; i < n2; i += NT) a = a + ScanSlot<T>::wait(agg, first + i, tag);
+        const T stiles = scan_block_sum<T, NW>(a, s_red);
+        if (tid == 0) ScanSlot<T>::publish(gagg, g, stiles + total, tag);
+        a = scan_zero<T>();
+        for (i64 i = tid; i < n1; i += NT) a = a + ScanSlot<T>::wait(gagg, i, tag);
+        carry = scan_block_sum<T, NW>(a, s_red) + stiles;
+      } else {
+        T acc = scan_zero<T>();
+        for (i64 i = tid; i < n1 + n2; i += NT)
+          acc = acc + (i < n1 ? ScanSlot<T>::wait(gagg, i, tag) : ScanSlot<T>::wait(agg, first + (i - n1), tag));
+        carry = scan_block_sum<T, NW>(acc, s_red);
+      }
       T cpre = carry;
 #pragma unroll
       for (int u = 0; u < U; ++u) {
@@ -3138,25 +3367,198 @@ __device__ __forceinline__ void scan_inner_body_impl(const RedParams &p) {
         cpre = cpre + ctot[u];
       }
       if (!more) break;
-      carry = (!tiles_mode && nb == cb) ? cpre : scan_zero<T>();
       cb = nb;
       ct = nt;
-      gid += gridDim.x;
+      gid = ng;
       orow = orow_next;
 #pragma unroll
       for (int u = 0; u < U; ++u) full[u] = full_next[u];
       par ^= 1;
     }
   }
-  if (tiles_mode) {
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    // exit ticket: the last CTA out opens the next epoch (every slot of this launch is stale from then on)
-    if (tid == 0) {
-      __threadfence();
-      if (atomicInc(p.scan_ctl + 1, gridDim.x - 1) == gridDim.x - 1) {
-        u32 e = (__ldcg(p.scan_ctl) + 1u) & 0x3fffffffu;
-        *(volatile u32 *)p.scan_ctl = e ? e : 1u;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (tid == 0) {
+    __threadfence();
+    if (atomicInc(p.scan_ctl + 1, gridDim.x - 1) == gridDim.x - 1) {
+      u32 e = (__ldcg(p.scan_ctl) + 1u) & 0x3fffffffu;
+      *(volatile u32 *)p.scan_ctl = e ? e : 1u;
+    }
+  }
+}
+
+// mode TILES: few long rows.  The tiles of all rows are dealt round-robin to a grid whose CTAs are all resident
+// (cooperative launch).  Pipelined like select1p: phase 1 of a tile (load, tile-local inclusive scan, publish the tile
+// total, park the scanned tile in a shared-memory slot) runs D - 1 iterations before its phase 2 (carry from the
+// TileExchange jobs, add, store), so the exchange's L2 round trips happen while the CTA works on later tiles.
+template <class E, class OutT, int V, int U, bool UNIT>
+__device__ __forceinline__ void scan_tiles_body_impl(const RedParams &p) {
+  typedef typename E::value_type T;
+  constexpr int NT = SCAN_NT, NW = NT / 32, DMAX = 8;
+  extern __shared__ __align__(16) unsigned char scan_smem[];
+  T *stage = (T *)scan_smem;        // [D][NT * U * V] tile-local inclusive scans
+  __shared__ T s_warp[2][U][NW];
+  __shared__ T s_tot[DMAX];
+  __shared__ T s_carry[2];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int D = p.scan_depth;
+  const i64 L = p.rsz[0];
+  const i64 TILE = (i64)NT * V * U;
+  const i64 tpr = (L + TILE - 1) / TILE;
+  const i64 total_tiles = p.B * tpr;
+  const i64 G = gridDim.x;
+  const i64 mine = total_tiles > (i64)blockIdx.x ? (total_tiles - blockIdx.x + G - 1) / G : 0;
+  const i64 oinner = p.out_rs[0];
+  const u32 tag = ((__ldcg(p.scan_ctl) & 0x3fffffffu) << 2) | 1u;
+  TileExchange<T> xc;
+  xc.init(p.scan_agg, p.scan_gagg, p.scan_sagg, tpr, tag, lane);
+
+  const char *base[E::NL];
+  i64 inner[E::NL];
+#pragma unroll
+  for (int k = 0; k < E::NL; ++k) inner[k] = p.leaf[k].rs[0];
+  auto setup_in = [&](i64 b) {
+    i64 bidx[KMAXD];
+    decomp(b, p.nb, p.bsz, bidx);
+#pragma unroll
+    for (int k = 0; k < E::NL; ++k) {
+      i64 off = 0;
+#pragma unroll
+      for (int d = 0; d < KMAXD; ++d) if (d < p.nb) off += bidx[d] * p.leaf[k].bs[d];
+      base[k] = (const char *)p.leaf[k].ptr + off * E::leaf_bytes(k);
+    }
+  };
+  auto out_row = [&](i64 b) -> OutT * {
+    i64 bidx[KMAXD];
+    decomp(b, p.nb, p.bsz, bidx);
+    i64 oo = 0;
+#pragma unroll
+    for (int d = 0; d < KMAXD; ++d) if (d < p.nb) oo += bidx[d] * p.out.bs[d];
+    return (OutT *)p.out.ptr + oo;
+  };
+  typename E::template Regs<V> r[U];
+  bool full[U];
+  i64 loaded_row = -1;
+  auto issue_loads = [&](i64 gid) {
+    const i64 b = gid / tpr, t = gid - b * tpr;
+    if (b != loaded_row) { setup_in(b); loaded_row = b; }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const i64 j = t * TILE + ((i64)u * NT + tid) * V;
+      full[u] = V == 1 ? (j < L) : (j + V <= L);
+      if (full[u]) E::template loadv<V, UNIT>(r[u], base, inner, j);
+    }
+  };
+  if (mine > 0) issue_loads(blockIdx.x);
+  for (i64 it = 0; it < mine + D - 1; ++it) {
+    const int par = (int)(it & 1);
+    const bool p1 = it < mine;
+    const i64 it2 = it - (D - 1);
+    const bool p2 = it2 >= 0;
+    const i64 gid = (i64)blockIdx.x + it * G, gid2 = (i64)blockIdx.x + it2 * G;
+    const int slot = (int)(it % D), slot2 = (int)(((it2 % D) + D) % D);
+    const i64 cb = p1 ? gid / tpr : 0, ct = p1 ? gid - cb * tpr : 0;
+    const i64 cb2 = p2 ? gid2 / tpr : 0, ct2 = p2 ? gid2 - cb2 * tpr : -1;
+    if (warp == 0) {
+      i64 rc = 0, tc = -1, rh = 0, th = -1;
+      if (it >= 1 && it - 1 < mine) { const i64 g1 = gid - G; rc = g1 / tpr; tc = g1 - rc * tpr; }
+      if (it >= 2 && it - 2 < mine) { const i64 g2 = gid - 2 * G; rh = g2 / tpr; th = g2 - rh * tpr; }
+      xc.issue(rc, tc, rh, th, cb2, ct2);
+    }
+    if (p1) {
+      const i64 j0 = ct * TILE;
+      T x[U][V];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const i64 j = j0 + ((i64)u * NT + tid) * V;
+        if (full[u]) {
+#pragma unroll
+          for (int v = 0; v < V; ++v) x[u][v] = E::template eval<V>(r[u], v, p.c);
+        } else {
+#pragma unroll
+          for (int v = 0; v < V; ++v) {
+            x[u][v] = scan_zero<T>();
+            if (V > 1 && j + v < L) {
+              typename E::template Regs<1> r1;
+              E::template loadv<1, false>(r1, base, inner, j + v);
+              x[u][v] = E::template eval<1>(r1, 0, p.c);
+            }
+          }
+        }
+#pragma unroll
+        for (int v = 1; v < V; ++v) x[u][v] = x[u][v - 1] + x[u][v];
       }
+      if (it + 1 < mine) issue_loads(gid + G);   // the next tile's loads fly while this one is scanned and parked
+      T wexcl[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        T incl = x[u][V - 1];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const T o = shfl_up_t(incl, d);
+          if (lane >= d) incl = o + incl;
+        }
+        const T ex = shfl_up_t(incl, 1);
+        wexcl[u] = lane == 0 ? scan_zero<T>() : ex;
+        if (lane == 31) s_warp[par][u][warp] = incl;
+      }
+      __syncthreads();   // (A)
+      T cpre = scan_zero<T>();
+      T *stg = stage + (size_t)slot * TILE;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        T run = scan_zero<T>(), wpre = run;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+          if (w == warp) wpre = run;
+          run = run + s_warp[par][u][w];
+        }
+        const T pre = (cpre + wpre) + wexcl[u];
+        Vec<T, V> o;
+#pragma unroll
+        for (int v = 0; v < V; ++v) o.v[v] = pre + x[u][v];
+        *(Vec<T, V> *)(stg + ((size_t)u * NT + tid) * V) = o;
+        cpre = cpre + run;
+      }
+      if (tid == 0) {   // the tile's total: every later tile of the row waits for this store
+        xc.publish_tile(cb, ct, cpre);
+        s_tot[slot] = cpre;
+      }
+    } else {
+      __syncthreads();   // (A) keeps the barrier count uniform while the pipeline drains
+    }
+    if (warp == 0) {
+      const T ctot = xc.close_ct >= 0 ? s_tot[(int)((it - 1) % D)] : scan_zero<T>();
+      const T cr = xc.finish(ctot);
+      if (lane == 0) s_carry[par] = cr;
+    }
+    __syncthreads();   // (B)
+    if (p2) {
+      const T carry = s_carry[par];
+      OutT *orow = out_row(cb2);
+      const T *stg = stage + (size_t)slot2 * TILE;
+      const i64 j0 = ct2 * TILE;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const i64 j = j0 + ((i64)u * NT + tid) * V;
+        const Vec<T, V> x = *(const Vec<T, V> *)(stg + ((size_t)u * NT + tid) * V);
+        Vec<OutT, V> o;
+#pragma unroll
+        for (int v = 0; v < V; ++v) o.v[v] = cvt<OutT>(carry + x.v[v]);
+        if (V > 1 && j + V <= L && oinner == 1 && p.tx) StBytes<(int)sizeof(OutT) * V>::st(orow + j, &o);
+        else {
+#pragma unroll
+          for (int v = 0; v < V; ++v) if (j + v < L) orow[(j + v) * oinner] = o.v[v];
+        }
+      }
+    }
+  }
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  // exit ticket: the last CTA out opens the next epoch (every slot of this launch is stale from then on)
+  if (tid == 0) {
+    __threadfence();
+    if (atomicInc(p.scan_ctl + 1, gridDim.x - 1) == gridDim.x - 1) {
+      u32 e = (__ldcg(p.scan_ctl) + 1u) & 0x3fffffffu;
+      *(volatile u32 *)p.scan_ctl = e ? e : 1u;
     }
   }
 }
@@ -3167,6 +3569,12 @@ __device__ __forceinline__ void scan_inner_body(const RedParams &p) {
   if (TEAM == 1) {
     if (p.all_unit) scan_warp_body_impl<E, OutT, V, U, true>(p);
     else scan_warp_body_impl<E, OutT, V, U, false>(p);
+  } else if (p.splits == 2) {
+    if (p.all_unit) scan_tiles_flat_body_impl<E, OutT, V, U, true>(p);
+    else scan_tiles_flat_body_impl<E, OutT, V, U, false>(p);
+  } else if (p.splits > 2) {
+    if (p.all_unit) scan_tiles_body_impl<E, OutT, V, U, true>(p);
+    else scan_tiles_body_impl<E, OutT, V, U, false>(p);
   } else {
     if (p.all_unit) scan_inner_body_impl<E, OutT, V, U, true>(p);
     else scan_inner_body_impl<E, OutT, V, U, false>(p);
@@ -3393,25 +3801,54 @@ __device__ __forceinline__ void select_body(const EwParams &p) {
 // Shared-memory staging and the per-warp totals are double-buffered by tile parity: two barriers per tile.
 // Status words carry the launch epoch, so nothing is cleared between launches.
 // ------------------------------------------------------------------------------------------------
+// predicate of one selection op as a type: the tile loop is instantiated per op (one compare + one predicated OR per
+// element) instead of classifying every element against a runtime mask
+template <int OP> struct SelPred {
+  template <class T> static __device__ __forceinline__ bool test(T x, T c) {
+    return OP == 0 ? (x < c) : OP == 1 ? (x > c) : OP == 2 ? (x == c) : OP == 3 ? (x != c) : OP == 4 ? (x <= c) : (x >= c);
+  }
+};
+template <int OP, class T, int V> __device__ __forceinline__ u32 sel_flags_vec(const T *vals, T thr) {
+  u32 f = 0;
+#pragma unroll
+  for (int v = 0; v < V; ++v) f |= (SelPred<OP>::test(vals[v], thr) ? 1u : 0u) << v;
+  return f;
+}
+template <class T, int V> __device__ __forceinline__ u32 sel_flags_op(int op, const T *vals, T thr) {
+  switch (op) {
+    case 0: return sel_flags_vec<0, T, V>(vals, thr);
+    case 1: return sel_flags_vec<1, T, V>(vals, thr);
+    case 2: return sel_flags_vec<2, T, V>(vals, thr);
+    case 3: return sel_flags_vec<3, T, V>(vals, thr);
+    case 4: return sel_flags_vec<4, T, V>(vals, thr);
+    default: return sel_flags_vec<5, T, V>(vals, thr);
+  }
+}
+
 template <class E, class OutT, int V, int MODE>   // MODE 1: values, 2: flat indices
 __device__ __forceinline__ void select1p_body(const EwParams &p) {
   pdl_prologue();
   typedef typename E::value_type T;
   typedef typename E::template Regs<V> R;
-  constexpr int NT = 256, U = 4, NW = NT / 32;
+  constexpr int NT = 256, U = 4, NW = NT / 32, DMAX = 8;
   extern __shared__ __align__(16) unsigned char sel_smem[];
-  OutT *stage = (OutT *)sel_smem;                      // [2][NT * U * V]
+  OutT *stage = (OutT *)sel_smem;                      // [D][NT * U * V]: compacted tiles waiting for their offset
   __shared__ u32 s_w[2][NW];
+  __shared__ u32 s_tot[DMAX];
   __shared__ u32 s_excl[2];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int D = p.sel_depth;                           // pipeline depth: phase 2 of a tile runs D - 1 iterations after its phase 1
   const i64 TILE = (i64)NT * V * U;
   const i64 ntiles = (p.N + TILE - 1) / TILE;
+  const i64 G = gridDim.x;
+  const i64 mine = ntiles > (i64)blockIdx.x ? (ntiles - blockIdx.x + G - 1) / G : 0;   // tiles of this CTA
   const T thr = SelThr<T>::get(p);
-  const u32 fmask = sel_mask(p.sel_op);
+  const bool unique_mode = p.sel_op == 6;             // MXB_SEL_UNIQUE (mxb_unique): adjacent-difference flags over a sorted operand
+  const u32 fmask = sel_mask(unique_mode ? 0 : p.sel_op);
   const u32 epoch = __ldcg(p.sel_epoch) & 0x3fffffffu;
-  const u32 tag = (epoch << 2) | 1u;
   // slots: tile counts, group counts (32 tiles), running counts at supergroup starts (1024 tiles)
-  unsigned long long *agg = p.sel_status, *gagg = agg + ntiles, *sagg = gagg + ((ntiles + 31) >> 5);
+  TileExchange<u32> xc;
+  xc.init(p.sel_status, p.sel_status + ntiles, p.sel_status + ntiles + ((ntiles + 31) >> 5), ntiles, (epoch << 2) | 1u, lane);
   const char *base[E::NL];
   i64 inner[E::NL];
 #pragma unroll
@@ -3419,102 +3856,167 @@ __device__ __forceinline__ void select1p_body(const EwParams &p) {
   const bool unit = p.all_unit != 0;
 
   R r[U];
-  auto issue = [&](i64 tile) {     // vector loads of the full vectors of `tile`; ragged ends are fetched at evaluation time
+  auto issue_loads = [&](i64 tile) {     // vector loads of the full vectors of `tile`; ragged ends are fetched at evaluation time
+    const i64 jt = tile * TILE + (i64)tid * V;
+    if ((tile + 1) * TILE <= p.N && unit) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) E::template loadv<V, true>(r[u], base, inner, jt + (i64)u * NT * V);
+      return;
+    }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const i64 j0 = tile * TILE + ((i64)u * NT + tid) * V;
+      const i64 j0 = jt + (i64)u * NT * V;
       if (j0 + V <= p.N) {
         if (unit) E::template loadv<V, true>(r[u], base, inner, j0);
         else E::template loadv<V, false>(r[u], base, inner, j0);
       }
     }
   };
-  i64 tile = blockIdx.x;
-  if (tile < ntiles) issue(tile);
-  int par = 0;
-  for (; tile < ntiles; tile += gridDim.x, par ^= 1) {
-    const i64 t0 = tile * TILE;
-    T vals[U][V];
-    u32 flags[U];
-    u32 packed = 0;
+  if (mine > 0) issue_loads(blockIdx.x);
+  for (i64 it = 0; it < mine + D - 1; ++it) {
+    const int par = (int)(it & 1);
+    const bool p1 = it < mine;                 // phase 1 of local tile `it`
+    const i64 it2 = it - (D - 1);              // phase 2 of local tile `it2`
+    const bool p2 = it2 >= 0;
+    const i64 tile = (i64)blockIdx.x + it * G, tile2 = (i64)blockIdx.x + it2 * G;
+    const int slot = (int)(it % D), slot2 = (int)(((it2 % D) + D) % D);
+    // ---- warp 0: the reads of this iteration's exchange jobs go out before the iteration's own work ----
+    if (warp == 0) {
+      const i64 tc = (it >= 1 && it - 1 < mine) ? tile - G : -1;        // close: the tile of the previous iteration
+      const i64 th = (it >= 2 && it - 2 < mine) ? tile - 2 * G : -1;    // chain: the one before
+      xc.issue(0, tc, 0, th, 0, p2 ? tile2 : -1);
+    }
+    u32 total = 0;
+    if (p1) {
+      const i64 t0 = tile * TILE;
+      T vals[U][V];
+      u32 flags[U];
+      u32 packed = 0;
+      if (t0 + TILE <= p.N && !unique_mode) {
+        // a full tile (all but the last): no bounds in the loop, the op is a compile-time functor inside sel_flags_op
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const i64 j0 = t0 + ((i64)u * NT + tid) * V;
-      u32 f = 0;
-      if (j0 + V <= p.N) {
+        for (int u = 0; u < U; ++u) {
 #pragma unroll
-        for (int v = 0; v < V; ++v) {
-          vals[u][v] = E::template eval<V>(r[u], v, p.c);
-          f |= sel_flag<T>(vals[u][v], thr, fmask) << v;
+          for (int v = 0; v < V; ++v) vals[u][v] = E::template eval<V>(r[u], v, p.c);
+        }
+        const int op = p.sel_op;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          flags[u] = sel_flags_op<T, V>(op, vals[u], thr);
+          packed |= (u32)__popc(flags[u]) << (8 * u);
         }
       } else {
 #pragma unroll
-        for (int v = 0; v < V; ++v) {
-          if (j0 + v < p.N) {
-            typename E::template Regs<1> r1;
-            E::template loadv<1, false>(r1, base, inner, j0 + v);
-            vals[u][v] = E::template eval<1>(r1, 0, p.c);
+      for (int u = 0; u < U; ++u) {
+        const i64 j0 = t0 + ((i64)u * NT + tid) * V;
+        u32 f = 0;
+        if (j0 + V <= p.N) {
+#pragma unroll
+          for (int v = 0; v < V; ++v) {
+            vals[u][v] = E::template eval<V>(r[u], v, p.c);
             f |= sel_flag<T>(vals[u][v], thr, fmask) << v;
           }
+        } else {
+#pragma unroll
+          for (int v = 0; v < V; ++v) {
+            if (j0 + v < p.N) {
+              typename E::template Regs<1> r1;
+              E::template loadv<1, false>(r1, base, inner, j0 + v);
+              vals[u][v] = E::template eval<1>(r1, 0, p.c);
+              f |= sel_flag<T>(vals[u][v], thr, fmask) << v;
+            }
+          }
         }
+        if (unique_mode) {
+          // unique over a SORTED operand (std::unique / cub::DeviceSelect::Unique): keep x[j] iff j == 0 or x[j] != x[j - 1]
+          f = 0;
+          if (j0 < p.N) {
+            T prev = vals[u][0];
+            if (j0 > 0) {
+              typename E::template Regs<1> r1;
+              E::template loadv<1, false>(r1, base, inner, j0 - 1);
+              prev = E::template eval<1>(r1, 0, p.c);
+            }
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+              if (j0 + v < p.N) {
+                const bool keep = (j0 + v == 0) || !(vals[u][v] == prev);
+                f |= (keep ? 1u : 0u) << v;
+                prev = vals[u][v];
+              }
+            }
+          }
+        }
+        flags[u] = f;
+        packed |= (u32)__popc(f) << (8 * u);
       }
-      flags[u] = f;
-      packed |= (u32)__popc(f) << (8 * u);
-    }
-    // the next tile's loads fly while this one goes through its barriers and its look-back
-    if (tile + gridDim.x < ntiles) issue(tile + gridDim.x);
-    // ranks inside the warp: one shuffle scan over the four packed byte counters
-    u32 incl = packed;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const u32 o = __shfl_up_sync(0xffffffffu, incl, d);
-      if (lane >= d) incl += o;
-    }
-    const u32 wexcl = incl - packed;
-    if (lane == 31) s_w[par][warp] = incl;
-    __syncthreads();   // (A)
-    // warps before mine and the chunk totals, two 16-bit lanes per word (8 warps x 128 fit easily)
-    u32 blo = 0, bhi = 0, tlo = 0, thi = 0;
-#pragma unroll
-    for (int w = 0; w < NW; ++w) {
-      const u32 x = s_w[par][w];
-      const u32 lo = x & 0x00ff00ffu, hi = (x >> 8) & 0x00ff00ffu;
-      tlo += lo; thi += hi;
-      if (w < warp) { blo += lo; bhi += hi; }
-    }
-    const u32 tot[4] = {tlo & 0xffffu, thi & 0xffffu, tlo >> 16, thi >> 16};
-    const u32 bef[4] = {blo & 0xffffu, bhi & 0xffffu, blo >> 16, bhi >> 16};
-    const u32 total = tot[0] + tot[1] + tot[2] + tot[3];
-    if (tid == 0) ScanSlot<u32>::publish(agg, tile, total, tag);   // first thing: every later tile waits for this store
-    // compact the selected elements into shared memory by rank
-    OutT *stg = stage + (size_t)par * TILE;
-    u32 coff = 0;
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      u32 pos = coff + bef[u] + ((wexcl >> (8 * u)) & 0xffu);
-      const i64 j0 = t0 + ((i64)u * NT + tid) * V;
-#pragma unroll
-      for (int v = 0; v < V; ++v) {
-        if ((flags[u] >> v) & 1u) { stg[pos] = MODE == 1 ? cvt<OutT>(vals[u][v]) : (OutT)(j0 + v); ++pos; }
       }
-      coff += tot[u];
+      // the next tile's loads fly while this one is ranked and staged
+      if (it + 1 < mine) issue_loads(tile + G);
+      // ranks inside the warp: one shuffle scan over the four packed byte counters
+      u32 incl = packed;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const u32 o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += o;
+      }
+      const u32 wexcl = incl - packed;
+      if (lane == 31) s_w[par][warp] = incl;
+      __syncthreads();   // (A)
+      // warps before mine and the chunk totals, two 16-bit lanes per word (8 warps x 128 fit easily)
+      u32 blo = 0, bhi = 0, tlo = 0, thi = 0;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) {
+        const u32 x = s_w[par][w];
+        const u32 lo = x & 0x00ff00ffu, hi = (x >> 8) & 0x00ff00ffu;
+        tlo += lo; thi += hi;
+        if (w < warp) { blo += lo; bhi += hi; }
+      }
+      const u32 tot[4] = {tlo & 0xffffu, thi & 0xffffu, tlo >> 16, thi >> 16};
+      const u32 bef[4] = {blo & 0xffffu, bhi & 0xffffu, blo >> 16, bhi >> 16};
+      total = tot[0] + tot[1] + tot[2] + tot[3];
+      if (tid == 0) {   // first thing: every later tile waits for this store
+        xc.publish_tile(0, tile, total);
+        s_tot[slot] = total;
+      }
+      // compact the selected elements into this tile's staging slot by rank
+      OutT *stg = stage + (size_t)slot * TILE;
+      u32 coff = 0;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        u32 pos = coff + bef[u] + ((wexcl >> (8 * u)) & 0xffu);
+        const i64 j0 = t0 + ((i64)u * NT + tid) * V;
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          if ((flags[u] >> v) & 1u) { stg[pos] = MODE == 1 ? cvt<OutT>(vals[u][v]) : (OutT)(j0 + v); ++pos; }
+        }
+        coff += tot[u];
+      }
+    } else {
+      __syncthreads();   // (A) keeps the barrier count uniform while the pipeline drains
     }
     if (warp == 0) {
-      const u32 excl = hier_carry<u32>(agg, gagg, sagg, tile, ntiles, total, tag, lane);
-      if (lane == 0) {
+      // the closing tile's own total: written to s_tot one iteration ago (behind barrier B of that iteration)
+      const u32 ctot = xc.close_ct >= 0 ? s_tot[(int)((it - 1) % D)] : 0u;
+      const u32 excl = xc.finish(ctot);
+      if (lane == 0 && p2) {
         s_excl[par] = excl;
-        if (tile == ntiles - 1) {
-          const unsigned long long all = (unsigned long long)excl + total;
+        if (tile2 == ntiles - 1) {
+          const unsigned long long all = (unsigned long long)excl + s_tot[slot2];
           *p.sel_total = all > 0x7fffffffull ? 0x7fffffff : (int)all;
         }
       }
     }
-    __syncthreads();   // (B) staging complete, running total known
-    const i64 excl = (i64)s_excl[par];
-    OutT *dst = (OutT *)p.out.ptr + excl;
-    const i64 room = p.sel_cap - excl;     // elements beyond the capacity are counted, not written
-    for (u32 i = tid; i < total; i += NT)
-      if ((i64)i < room) dst[i] = stg[i];
+    __syncthreads();   // (B) this iteration's staging is complete, the drained tile's offset is known
+    if (p2) {
+      const i64 excl = (i64)s_excl[par];
+      const u32 n = s_tot[slot2];
+      const OutT *stg = stage + (size_t)slot2 * TILE;
+      OutT *dst = (OutT *)p.out.ptr + excl;
+      const i64 room = p.sel_cap - excl;     // elements beyond the capacity are counted, not written
+      for (u32 i = tid; i < n; i += NT)
+        if ((i64)i < room) dst[i] = stg[i];
+    }
   }
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   // exit ticket: the last CTA out opens the next epoch (every status word of this launch is stale from then on)
@@ -3525,6 +4027,123 @@ __device__ __forceinline__ void select1p_body(const EwParams &p) {
       *(volatile u32 *)p.sel_epoch = e ? e : 1u;   // epoch 0 is what freshly zeroed status words carry: never used
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// H1: hist — even-width histogram of every row (reference: hist_impl -> cub::DeviceHistogram::HistogramEven,
+// transforms/cub.h:320-359,2464-2503; bin arithmetic restated from CCCL's ScaleTransform, cub/device/dispatch/kernels/
+// kernel_histogram.cuh:75-245: a sample counts iff lower <= x < upper, bin = int((x - lower) * scale) with scale =
+// T(bins) / T(upper - lower) for floating types and ((x - lower) * bins) / (upper - lower) in 64-bit unsigned arithmetic
+// for integers).  A work item is a chunk of one row; a CTA keeps the item's bins in shared memory (atomicAdd.shared),
+// then adds the non-empty ones to the row's output bins (integer atomics: the result does not depend on the order).  The
+// host zeroes the output on the stream first.
+// ------------------------------------------------------------------------------------------------
+template <class T> struct HistBin {   // floating types
+  T lo, hi, scale;
+  int bins;
+  __device__ __forceinline__ void init(const RedParams &p) { lo = (T)p.hist_lo_d; hi = (T)p.hist_hi_d; bins = p.hist_bins; scale = (T)((T)p.hist_bins / (T)(hi - lo)); }
+  // a sample a hair below `upper` can round to bin == bins in (x - lower) * scale (999.99994f * 0.256f = 256.0f): CUB's
+  // formula would index past its last bin there; such a sample is dropped (the oracle does the same)
+  __device__ __forceinline__ int bin(T x) const {
+    if (!(x >= lo && x < hi)) return -1;
+    const int b = (int)((x - lo) * scale);
+    return b < bins ? b : -1;
+  }
+};
+template <class T> struct HistBinInt {
+  i64 lo, hi;
+  u64 bins, range;
+  __device__ __forceinline__ void init(const RedParams &p) { lo = p.hist_lo_i; hi = p.hist_hi_i; bins = (u64)p.hist_bins; range = (u64)(hi - lo); }
+  __device__ __forceinline__ int bin(T x) const { const i64 v = (i64)x; return (v >= lo && v < hi) ? (int)(((u64)(v - lo) * bins) / range) : -1; }
+};
+template <> struct HistBin<int> : HistBinInt<int> {};
+template <> struct HistBin<i64> : HistBinInt<i64> {};
+template <> struct HistBin<unsigned char> : HistBinInt<unsigned char> {};
+
+template <class E, int V, int U, bool UNIT>
+__device__ __forceinline__ void hist_body_impl(const RedParams &p) {
+  typedef typename E::value_type T;
+  extern __shared__ __align__(16) unsigned char hist_smem[];
+  int *s_bins = (int *)hist_smem;
+  const int nthr = blockDim.x, tid = threadIdx.x;
+  const int bins = p.hist_bins;
+  const bool priv = p.hist_smem != 0;
+  HistBin<T> hb;
+  hb.init(p);
+  const i64 L = p.rsz[0], Lv = L / V, tail = L - Lv * V;
+  const i64 S = p.splits;                      // chunks per row
+  const i64 per = (Lv + S - 1) / S;            // vector steps per chunk
+  const i64 work = p.B * S;
+  for (i64 w = blockIdx.x; w < work; w += gridDim.x) {
+    const i64 b = w / S, s = w - b * S;
+    const char *base[E::NL];
+    i64 inner[E::NL];
+    i64 bidx[KMAXD];
+    decomp(b, p.nb, p.bsz, bidx);
+    i64 oo = 0;
+#pragma unroll
+    for (int k = 0; k < E::NL; ++k) {
+      i64 off = 0;
+#pragma unroll
+      for (int d = 0; d < KMAXD; ++d) if (d < p.nb) off += bidx[d] * p.leaf[k].bs[d];
+      base[k] = (const char *)p.leaf[k].ptr + off * E::leaf_bytes(k);
+      inner[k] = p.leaf[k].rs[0];
+    }
+#pragma unroll
+    for (int d = 0; d < KMAXD; ++d) if (d < p.nb) oo += bidx[d] * p.out.bs[d];
+    int *obins = (int *)p.out.ptr + oo;          // the row's bins are contiguous (host rule)
+    int *dst = priv ? s_bins : obins;
+    if (priv) {
+      for (int i = tid; i < bins; i += nthr) s_bins[i] = 0;
+      __syncthreads();
+    }
+    const i64 q0 = s * per, q1 = (q0 + per < Lv) ? q0 + per : Lv;
+    i64 q = q0 + tid;
+    for (; q + (i64)(U - 1) * nthr < q1; q += (i64)U * nthr) {
+      typename E::template Regs<V> r[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) E::template loadv<V, UNIT>(r[u], base, inner, (q + (i64)u * nthr) * V);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          const int bi = hb.bin(E::template eval<V>(r[u], v, p.c));
+          if (bi >= 0) atomicAdd(dst + bi, 1);
+        }
+      }
+    }
+    for (; q < q1; q += nthr) {
+      typename E::template Regs<V> r;
+      E::template loadv<V, UNIT>(r, base, inner, q * V);
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        const int bi = hb.bin(E::template eval<V>(r, v, p.c));
+        if (bi >= 0) atomicAdd(dst + bi, 1);
+      }
+    }
+    if (V > 1 && tail > 0 && s == S - 1) {
+      for (i64 j = Lv * V + tid; j < L; j += nthr) {
+        typename E::template Regs<1> r;
+        E::template loadv<1, false>(r, base, inner, j);
+        const int bi = hb.bin(E::template eval<1>(r, 0, p.c));
+        if (bi >= 0) atomicAdd(dst + bi, 1);
+      }
+    }
+    if (priv) {
+      __syncthreads();
+      for (int i = tid; i < bins; i += nthr) {
+        const int c = s_bins[i];
+        if (c) atomicAdd(obins + i, c);
+      }
+      __syncthreads();
+    }
+  }
+}
+template <class E, int V, int U>
+__device__ __forceinline__ void hist_body(const RedParams &p) {
+  pdl_prologue();
+  if (p.all_unit) hist_body_impl<E, V, U, true>(p);
+  else hist_body_impl<E, V, U, false>(p);
 }
 
 }  // namespace mxb

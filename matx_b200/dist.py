@@ -189,3 +189,7 @@ class PeerExchange:
         for op, e, off, k in plan["push"]:
             A.check(lib.mxb_reduce_partial_push(h, op, C.byref(e), off, peers, k, plan["n"]))
         A.check(lib.mxb_exchange_finalize(h, peers, plan["fold"], plan["n"], plan["count"]))
+
+    def check(self) -> None:
+        """Synchronise and raise if any exchange since the last check timed out on a peer (its outputs hold NaN / -1)."""
+        A.check(A.lib.mxb_exchange_check(self.ex.handle, C.byref(self.peers)))

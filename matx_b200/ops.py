@@ -407,6 +407,48 @@ def find(a, sel): return FindExpr(a, sel, False)
 def find_idx(a, sel): return FindExpr(a, sel, True)
 
 
+SORT_DIR_ASC, SORT_DIR_DESC = 0, 1    # SortDirection_t (transforms/cub.h:75-78)
+
+
+class SortExpr:
+    """sort(a, dir) (operators/sort.h -> sort_impl, transforms/cub.h:2145-2190): every row of the last dim sorted, same
+    shape as the operand."""
+
+    def __init__(self, a, direction: int = SORT_DIR_ASC):
+        self.a = _wrap(a, None)
+        if len(self.a.shape) < 1:
+            raise ValueError("sort needs an operand of rank >= 1")
+        self.direction = direction
+        self.out_shape = tuple(self.a.shape)
+
+
+class HistExpr:
+    """hist(a, lower, upper, num_levels) (operators/hist.h:40-125 -> hist_impl, transforms/cub.h:2464-2503): counts of
+    every row of the last dim in num_levels - 1 even-width bins over [lower, upper); int output."""
+
+    def __init__(self, a, lower, upper, num_levels: int):
+        self.a = _wrap(a, None)
+        if len(self.a.shape) < 1:
+            raise ValueError("hist needs an operand of rank >= 1")
+        self.lower, self.upper, self.num_levels = lower, upper, int(num_levels)
+        self.out_shape = tuple(self.a.shape[:-1]) + (self.num_levels - 1,)
+
+
+class UniqueExpr:
+    """unique(a) (operators/unique.h -> unique_impl, transforms/cub.h:2796-2842): `(mtie(out, num_found) = unique(a)).run(exec)`,
+    rank-1 operand, the distinct values in ascending order."""
+
+    def __init__(self, a):
+        self.a = _wrap(a, None)
+        if len(self.a.shape) != 1:
+            raise ValueError("unique takes a rank-1 operand")
+
+
+def sort(a, direction: int = SORT_DIR_ASC): return SortExpr(a, direction)
+def hist(a, lower, upper, num_levels: int): return HistExpr(a, lower, upper, num_levels)
+def unique(a): return UniqueExpr(a)
+
+
 class mtie:
     """mtie(values, indices) — multi-output LHS (core/tie.h:44-117)."""
 
@@ -522,6 +564,18 @@ class Set:
 
     def __init__(self, lhs, rhs):
         self.lhs = lhs
+        if isinstance(rhs, UniqueExpr):
+            if not isinstance(lhs, mtie) or len(lhs.outs) != 2 or len(lhs.outs[0].shape) != 1 or len(lhs.outs[1].shape) != 0:
+                raise TypeError("unique needs mtie(out, num_found) with a rank-1 output and a rank-0 count")
+            self.rhs = rhs
+            return
+        if isinstance(rhs, (SortExpr, HistExpr)):
+            if isinstance(lhs, mtie):
+                raise TypeError("sort / hist have one output")
+            if tuple(lhs.shape) != tuple(rhs.out_shape):
+                raise A.MatxB200Error(A.ERR_SIZE, "lhs shape %s does not match rhs shape %s" % (lhs.shape, rhs.out_shape))
+            self.rhs = rhs
+            return
         if isinstance(rhs, FindExpr):
             if not isinstance(lhs, mtie) or len(lhs.outs) != 2:
                 raise TypeError("find / find_idx need mtie(out, num_found) on the left-hand side")
@@ -546,7 +600,19 @@ class Set:
                 raise A.MatxB200Error(A.ERR_SIZE, "lhs shape %s does not match rhs shape %s" % (o.shape, shape))  # matxInvalidSize
 
     def run(self, ex: "CudaExecutor") -> None:
-        if isinstance(self.rhs, FindExpr):
+        if isinstance(self.rhs, UniqueExpr):
+            e = lower_elementwise(self.rhs.a)
+            out, cnt = _out_desc(self.lhs.outs[0]), _out_desc(self.lhs.outs[1])
+            A.check(A.lib.mxb_unique(ex.handle, C.byref(e), C.byref(out), C.byref(cnt)))
+        elif isinstance(self.rhs, SortExpr):
+            e = lower_elementwise(self.rhs.a)
+            out = _out_desc(self.lhs)
+            A.check(A.lib.mxb_sort(ex.handle, C.byref(e), C.byref(out), 1 if self.rhs.direction == SORT_DIR_DESC else 0))
+        elif isinstance(self.rhs, HistExpr):
+            e = lower_elementwise(self.rhs.a)
+            out = _out_desc(self.lhs)
+            A.check(A.lib.mxb_hist(ex.handle, C.byref(e), float(self.rhs.lower), float(self.rhs.upper), C.byref(out)))
+        elif isinstance(self.rhs, FindExpr):
             r = self.rhs
             e = lower_elementwise(r.a)
             out, cnt = _out_desc(self.lhs.outs[0]), _out_desc(self.lhs.outs[1])

@@ -75,7 +75,8 @@ def build_ref(cuda: bool = False, force: bool = False) -> str | None:
     os.makedirs(OUT_REF, exist_ok=True)
     tag = "cuda" if cuda else "host"
     # one translation unit per element type (the reduce instantiation sets are large) plus the fused statements
-    units = [("dt0", ["-DMREF_DTYPE=0"]), ("dt4", ["-DMREF_DTYPE=4"]), ("dt2", ["-DMREF_DTYPE=2"]), ("fused", ["-DMREF_FUSED"])]
+    units = [("dt0", ["-DMREF_DTYPE=0"]), ("dt4", ["-DMREF_DTYPE=4"]), ("dt2", ["-DMREF_DTYPE=2"]), ("fused", ["-DMREF_FUSED"]),
+             ("sort", ["-DMREF_SORT"])]
     if not cuda:
         units += [("dt1", ["-DMREF_DTYPE=1"]), ("dt5", ["-DMREF_DTYPE=5"])]
     objs = []
@@ -113,7 +114,15 @@ def build_dropin(force: bool = False) -> str | None:
     if not force and os.path.exists(DROPIN_BIN) and os.path.getmtime(DROPIN_BIN) >= newest:
         return DROPIN_BIN
     os.makedirs(OUT_REF, exist_ok=True)
-    cmd = _nvcc_base(False) + ["-I" + os.path.join(root, "include"), src, "-o", DROPIN_BIN, "-L" + os.path.join(root, "matx_b200"),
+    # overlay headers (operators/softmax.h, operators/hist.h handing their impl the executor): generated from the reference's
+    # own text into oracle/_ref/overlay and put in FRONT of the reference's include directory
+    sys.path.insert(0, os.path.join(root, "tools"))
+    import make_overlay
+    overlay = make_overlay.main()
+    base = _nvcc_base(False)
+    ref_inc = "-I" + os.path.join(REF, "include")
+    base.insert(base.index(ref_inc), "-I" + overlay)
+    cmd = base + ["-DMXB_OVERLAY", "-I" + os.path.join(root, "include"), src, "-o", DROPIN_BIN, "-L" + os.path.join(root, "matx_b200"),
                                "-lmatx_b200", "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN/../../matx_b200",
                                "-lcublas", "-lcublasLt", "-lcufft", "-lcurand", "-lcusolver", "-lcusparse", "-lcuda"]
     _run(cmd)

@@ -550,3 +550,113 @@ int orc_find(const mxb_expr_t *e, int select_op, double threshold, const mxb_out
   *count_out = cnt;
   return 0;
 }
+
+/* ---- sort / unique / hist -----------------------------------------------------------
+ * sort: the HostExecutor overload of sort_impl (transforms/cub.h:2192-2240) — std::sort of every row of the last dim,
+ *       ascending or descending (std::greater).  Restated with qsort on the value type (sorting is a function of the
+ *       multiset of values; only the relative order of -0.0 / +0.0 and of NaNs is unspecified, and the tests avoid both).
+ * unique: the HostExecutor overload of unique_impl (:2844-2880) — std::sort, then std::unique, count in an int.
+ * hist: the reference has NO host implementation; the arithmetic is third-party: cub::DeviceHistogram::HistogramEven of
+ *       NVIDIA/cccl 3.3.0 (pinned in cmake/versions.json:3-8, not vendored under /root/reference; the nearest copy in this
+ *       image is the 3.3.2 tree inside the flashinfer wheel).  Restated from its published algorithm
+ *       (cub/device/dispatch/kernels/kernel_histogram.cuh, ScaleTransform): a sample counts iff lower <= x < upper; bin =
+ *       (int)((x - lower) * scale), scale = T(bins) / T(upper - lower), for floating T; ((x - lower) * bins) / (upper - lower)
+ *       in unsigned 64-bit arithmetic for integers.  Pinned by the reference's own known answers (test/00_tensor/CUBTests.cu:
+ *       153-197), not by a run of the reference: parity for hist is "pinned to third party" (DESIGN.md section 5). */
+static int cmp_f32(const void *a, const void *b) { float x = *(const float *)a, y = *(const float *)b; return (x > y) - (x < y); }
+static int cmp_f64(const void *a, const void *b) { double x = *(const double *)a, y = *(const double *)b; return (x > y) - (x < y); }
+static int cmp_i32(const void *a, const void *b) { int32_t x = *(const int32_t *)a, y = *(const int32_t *)b; return (x > y) - (x < y); }
+static int cmp_i64(const void *a, const void *b) { int64_t x = *(const int64_t *)a, y = *(const int64_t *)b; return (x > y) - (x < y); }
+
+static int sort_buffer(void *buf, int dtype, int64_t n, int descending) {
+  size_t esz;
+  int (*cmp)(const void *, const void *);
+  switch (dtype) {
+    case MXB_F32: esz = 4; cmp = cmp_f32; break;
+    case MXB_F64: esz = 8; cmp = cmp_f64; break;
+    case MXB_I32: esz = 4; cmp = cmp_i32; break;
+    case MXB_I64: esz = 8; cmp = cmp_i64; break;
+    default: return 1;
+  }
+  qsort(buf, (size_t)n, esz, cmp);
+  if (descending) {
+    char *p = (char *)buf, tmp[8];
+    for (int64_t i = 0, j = n - 1; i < j; ++i, --j) {
+      memcpy(tmp, p + i * esz, esz); memcpy(p + i * esz, p + j * esz, esz); memcpy(p + j * esz, tmp, esz);
+    }
+  }
+  return 0;
+}
+
+/* out (contiguous, the expression's shape and value type) = every row of the last dim of `e`, sorted */
+int orc_sort(const mxb_expr_t *e, const mxb_out_t *out, int descending) {
+  if (e->rank < 1 || out->rank != e->rank) return 1;
+  int64_t N = 1;
+  for (int d = 0; d < e->rank; ++d) N *= e->size[d];
+  if (N == 0) return 0;
+  const int64_t L = e->size[e->rank - 1];
+  int64_t idx[MXB_MAX_RANK] = {0};
+  for (int64_t f = 0; f < N; ++f) {
+    unflatten(f, e->rank, e->size, idx);
+    store_val(out->data, out->dtype, f, conv(eval_expr(e, idx), out->dtype));
+  }
+  const size_t esz = (out->dtype == MXB_F64 || out->dtype == MXB_I64) ? 8 : 4;
+  for (int64_t b = 0; b < N / L; ++b)
+    if (sort_buffer((char *)out->data + (size_t)(b * L) * esz, out->dtype, L, descending)) return 1;
+  return 0;
+}
+
+int orc_unique(const mxb_expr_t *e, const mxb_out_t *out, int32_t *count_out) {
+  if (e->rank != 1 || out->rank != 1) return 1;
+  const int64_t N = e->size[0];
+  const size_t esz = (out->dtype == MXB_F64 || out->dtype == MXB_I64) ? 8 : 4;
+  char *tmp = (char *)malloc((size_t)(N > 0 ? N : 1) * esz);
+  if (!tmp) return 1;
+  int64_t idx[MXB_MAX_RANK] = {0};
+  for (int64_t f = 0; f < N; ++f) { idx[0] = f; store_val(tmp, out->dtype, f, conv(eval_expr(e, idx), out->dtype)); }
+  if (sort_buffer(tmp, out->dtype, N, 0)) { free(tmp); return 1; }
+  int32_t cnt = 0;
+  for (int64_t f = 0; f < N; ++f) {
+    if (f == 0 || memcmp(tmp + f * esz, tmp + (f - 1) * esz, esz) != 0) {
+      /* std::unique compares with ==: -0.0 == +0.0 and NaN != NaN; the tests use neither */
+      if (cnt < out->size[0]) memcpy((char *)out->data + (size_t)cnt * esz, tmp + f * esz, esz);
+      ++cnt;
+    }
+  }
+  free(tmp);
+  *count_out = cnt;
+  return 0;
+}
+
+/* out(b..., k) int32 counts; bins = out->size[last]; out walks its own strides */
+int orc_hist(const mxb_expr_t *e, double lower, double upper, const mxb_out_t *out) {
+  if (e->rank < 1 || out->rank != e->rank || out->dtype != MXB_I32) return 1;
+  const int64_t bins = out->size[out->rank - 1], L = e->size[e->rank - 1];
+  int64_t B = 1;
+  for (int d = 0; d + 1 < e->rank; ++d) B *= e->size[d];
+  int64_t idx[MXB_MAX_RANK] = {0}, bidx[MXB_MAX_RANK] = {0};
+  for (int64_t b = 0; b < B; ++b) {
+    unflatten(b, e->rank - 1, e->size, bidx);
+    int64_t obase = 0;
+    for (int d = 0; d + 1 < e->rank; ++d) { idx[d] = bidx[d]; obase += bidx[d] * out->stride[d]; }
+    int32_t *ob = (int32_t *)out->data + obase;
+    for (int64_t k = 0; k < bins; ++k) ob[k * out->stride[out->rank - 1]] = 0;
+    for (int64_t j = 0; j < L; ++j) {
+      idx[e->rank - 1] = j;
+      val_t x = eval_expr(e, idx);
+      int bin = -1;
+      if (x.t == MXB_F32) {
+        const float lo = (float)lower, hi = (float)upper, scale = (float)bins / (hi - lo);
+        if (x.f >= lo && x.f < hi) bin = (int)((x.f - lo) * scale);
+      } else if (x.t == MXB_F64) {
+        const double scale = (double)bins / (upper - lower);
+        if (x.d >= lower && x.d < upper) bin = (int)((x.d - lower) * scale);
+      } else if (is_int(x.t)) {
+        const long long lo = (long long)lower, hi = (long long)upper;
+        if (x.i >= lo && x.i < hi) bin = (int)(((unsigned long long)(x.i - lo) * (unsigned long long)bins) / (unsigned long long)(hi - lo));
+      } else return 1;
+      if (bin >= 0 && bin < bins) ob[bin * out->stride[out->rank - 1]] += 1;
+    }
+  }
+  return 0;
+}

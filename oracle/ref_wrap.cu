@@ -318,3 +318,35 @@ extern "C" int MREF_NAME(mref_threads)(void) {
 #endif
 }
 #endif  // MREF_FUSED
+
+#ifdef MREF_SORT
+// ---- sort / unique statements of the reference (HostExecutor overloads: transforms/cub.h:2192-2240,2844-2880) -----------
+template <class T>
+static int ref_sort_rows(int mode, int desc, T *in, T *out, int64_t rows, int64_t cols) {
+  return with_exec(mode, [&](auto &ex) {
+    if (rows == 1) {
+      auto t = make_tensor<T>(in, {cols});
+      auto o = make_tensor<T>(out, {cols});
+      (o = matx::sort(t, desc ? SORT_DIR_DESC : SORT_DIR_ASC)).run(ex);
+    } else {
+      auto t = make_tensor<T>(in, {rows, cols});
+      auto o = make_tensor<T>(out, {rows, cols});
+      (o = matx::sort(t, desc ? SORT_DIR_DESC : SORT_DIR_ASC)).run(ex);
+    }
+  });
+}
+extern "C" int MREF_NAME(mref_sort_f32)(int mode, int desc, float *in, float *out, int64_t rows, int64_t cols) { return ref_sort_rows<float>(mode, desc, in, out, rows, cols); }
+extern "C" int MREF_NAME(mref_sort_f64)(int mode, int desc, double *in, double *out, int64_t rows, int64_t cols) { return ref_sort_rows<double>(mode, desc, in, out, rows, cols); }
+extern "C" int MREF_NAME(mref_sort_i32)(int mode, int desc, int *in, int *out, int64_t rows, int64_t cols) { return ref_sort_rows<int>(mode, desc, in, out, rows, cols); }
+template <class T>
+static int ref_unique(int mode, T *in, int64_t n, T *out, int *num_found) {
+  return with_exec(mode, [&](auto &ex) {
+    auto t = make_tensor<T>(in, {n});
+    auto o = make_tensor<T>(out, {n});
+    auto nf = make_tensor<int>(num_found, {});
+    (mtie(o, nf) = unique(t)).run(ex);
+  });
+}
+extern "C" int MREF_NAME(mref_unique_f32)(int mode, float *in, int64_t n, float *out, int *num_found) { return ref_unique<float>(mode, in, n, out, num_found); }
+extern "C" int MREF_NAME(mref_unique_i32)(int mode, int *in, int64_t n, int *out, int *num_found) { return ref_unique<int>(mode, in, n, out, num_found); }
+#endif  // MREF_SORT

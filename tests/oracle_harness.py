@@ -49,6 +49,9 @@ class Oracle:
         lib.orc_softmax.argtypes = [C.POINTER(A.Expr), C.c_int, C.POINTER(A.Out)]
         lib.orc_cumsum.argtypes = [C.POINTER(A.Expr), C.POINTER(A.Out)]
         lib.orc_find.argtypes = [C.POINTER(A.Expr), C.c_int, C.c_double, C.POINTER(A.Out), C.POINTER(C.c_int32), C.c_int]
+        lib.orc_sort.argtypes = [C.POINTER(A.Expr), C.POINTER(A.Out), C.c_int]
+        lib.orc_unique.argtypes = [C.POINTER(A.Expr), C.POINTER(A.Out), C.POINTER(C.c_int32)]
+        lib.orc_hist.argtypes = [C.POINTER(A.Expr), C.c_double, C.c_double, C.POINTER(A.Out)]
 
     def elementwise(self, rhs, out: np.ndarray, out_dtype: int | None = None) -> np.ndarray:
         rhs = mx._wrap(rhs, None)
@@ -67,6 +70,25 @@ class Oracle:
         n = C.c_int32(0)
         assert self.lib.orc_find(C.byref(e), r.sel.op, float(r.sel.c), C.byref(o), C.byref(n), 1 if r.want_indices else 0) == 0
         return int(n.value)
+
+    def sort(self, r: "mx.SortExpr", out: np.ndarray) -> np.ndarray:
+        e = mx.lower_elementwise(r.a)
+        o = mx._out_desc(np_tensor(out))
+        assert self.lib.orc_sort(C.byref(e), C.byref(o), 1 if r.direction == mx.SORT_DIR_DESC else 0) == 0
+        return out
+
+    def unique(self, r: "mx.UniqueExpr", out: np.ndarray) -> int:
+        e = mx.lower_elementwise(r.a)
+        o = mx._out_desc(np_tensor(out))
+        n = C.c_int32(0)
+        assert self.lib.orc_unique(C.byref(e), C.byref(o), C.byref(n)) == 0
+        return int(n.value)
+
+    def hist(self, r: "mx.HistExpr", out: np.ndarray) -> np.ndarray:
+        e = mx.lower_elementwise(r.a)
+        o = mx._out_desc(np_tensor(out))
+        assert self.lib.orc_hist(C.byref(e), float(r.lower), float(r.upper), C.byref(o)) == 0
+        return out
 
     def cumsum(self, r: "mx.CumsumExpr", out: np.ndarray, out_dtype: int | None = None) -> np.ndarray:
         e = mx.lower_elementwise(r.a)

@@ -183,3 +183,26 @@ def test_set_checks_shapes_like_the_reference():
         a + np_tensor(np.zeros(7, np.float32))
     with pytest.raises(TypeError):
         mx.mtie(a, a).set(mx.sum(a))
+
+
+def test_malformed_programs_are_rejected_not_crashed():
+    """A cyclic program (a -> b -> a) or a rank outside [0, MXB_MAX_RANK] must come back as MXB_ERR_INVALID from every
+    entry point that canonicalises (the cycle used to exhaust memory, the rank to read out of bounds)."""
+    x = np_tensor(np.zeros(8, np.float32))
+    e = mx.lower_elementwise(-x)
+    buf = C.create_string_buffer(4096)
+    cyc = A.Expr.from_buffer_copy(e)
+    cyc.n_nodes = 2
+    cyc.nodes[0].opcode, cyc.nodes[0].src[0] = A.OP_NEG, 1
+    cyc.nodes[1].opcode, cyc.nodes[1].src[0] = A.OP_NEG, 0
+    cyc.root = 0
+    assert A.lib.mxb_debug_codegen(C.byref(cyc), buf, len(buf)) == A.ERR_INVALID
+    assert b"cyclic" in A.lib.mxb_last_error()
+    assert A.lib.mxb_is_aot(C.byref(cyc), -1) == 0
+    for bad_rank in (-1, A.MXB_MAX_RANK + 1, 1 << 20):
+        r = A.Expr.from_buffer_copy(e)
+        r.rank = bad_rank
+        assert A.lib.mxb_debug_codegen(C.byref(r), buf, len(buf)) == A.ERR_INVALID, bad_rank
+        assert A.lib.mxb_is_aot(C.byref(r), -1) == 0
+        log = C.create_string_buffer(256)
+        assert A.lib.mxb_debug_compile(C.byref(r), 3, -1, A.F32, 1, 0, log, len(log)) == A.ERR_INVALID

@@ -86,3 +86,62 @@ def test_partial_records_and_rank_order_fold(world):
             assert abs(got - want) <= 2e-5 * abs(want), (op, vdt, got, want)
             if op == A.RED_ARGMIN:
                 assert idx.item() == int(np.argmin(x))
+
+
+def test_steps_of_different_sizes_share_one_exchange_and_timeouts_are_reported():
+    """the arrival counters are cumulative, so the fold must count what it has CONSUMED per source rank — a
+    3-statement step followed by a 2-statement step (and back) on one peer table; and a step whose peer never delivers
+    must not fold the stale slot: NaN / -1 in the outputs and MXB_ERR_CUDA from mxb_exchange_check."""
+    import ctypes as C
+    import torch
+    world, n = 2, 100_000
+    rng = np.random.default_rng(5)
+    ex = mx.CudaExecutor()
+    bufs = [torch.zeros(mxd.PeerExchange.buffer_bytes(world), dtype=torch.uint8, device="cuda") for _ in range(world)]
+    pes = [mxd.PeerExchange(ex, world, r, _sim_buffers=bufs) for r in range(world)]
+    for step, ops in enumerate(([A.RED_SUM, A.RED_MAX, A.RED_ARGMAX], [A.RED_MIN, A.RED_SUM], [A.RED_ARGMIN, A.RED_MAX, A.RED_SUM], [A.RED_MAX])):
+        x = rng.integers(0, 50, n).astype(np.float32)
+        dx = torch.from_numpy(x).cuda()
+        outs, plans = [], []
+        for r in range(world):
+            start, count = mxd.slab(n, r, world, align=64)
+            t = mx.make_tensor(dx[start:start + count])
+            o = [(torch.zeros((), device="cuda"), torch.zeros((), dtype=torch.int64, device="cuda")) for _ in ops]
+            items = [(op, v, i if op in (A.RED_ARGMAX, A.RED_ARGMIN) else None) for op, (v, i) in zip(ops, o)]
+            outs.append(o)
+            plans.append((pes[r], pes[r].prepare(items, t, start, n)))
+        for pe, plan in plans:
+            for op, e, off, k in plan["push"]:
+                A.check(A.lib.mxb_reduce_partial_push(ex.handle, op, C.byref(e), off, C.byref(pe.peers), k, plan["n"]))
+        for pe, plan in plans:
+            A.check(A.lib.mxb_exchange_finalize(ex.handle, C.byref(pe.peers), plan["fold"], plan["n"], plan["count"]))
+        for pe in pes:
+            pe.check()
+        want = {A.RED_SUM: x.astype(np.float64).sum(), A.RED_MAX: x.max(), A.RED_MIN: x.min(), A.RED_ARGMAX: x.max(), A.RED_ARGMIN: x.min()}
+        for o in outs:
+            for op, (v, i) in zip(ops, o):
+                assert abs(v.item() - want[op]) <= 1e-5 * max(1.0, abs(want[op])), (step, op)
+                if op == A.RED_ARGMAX:
+                    assert i.item() == int(np.argmax(x)), step
+                if op == A.RED_ARGMIN:
+                    assert i.item() == int(np.argmin(x)), step
+
+
+@pytest.mark.skipif(__import__("os").environ.get("MXB_TEST_SLOW") != "1", reason="waits out the 5 s peer timeout (MXB_TEST_SLOW=1)")
+def test_missing_peer_is_an_error_not_a_stale_fold():
+    import ctypes as C
+    import torch
+    world, n = 2, 10_000
+    ex = mx.CudaExecutor()
+    bufs = [torch.zeros(mxd.PeerExchange.buffer_bytes(world), dtype=torch.uint8, device="cuda") for _ in range(world)]
+    pes = [mxd.PeerExchange(ex, world, r, _sim_buffers=bufs) for r in range(world)]
+    dx = torch.ones(n, device="cuda")
+    v, i = torch.zeros((), device="cuda"), torch.zeros((), dtype=torch.int64, device="cuda")
+    plan = pes[0].prepare([(A.RED_ARGMAX, v, i)], mx.make_tensor(dx[: n // 2]), 0, n)
+    for op, e, off, k in plan["push"]:     # rank 0 pushes, rank 1 never does
+        A.check(A.lib.mxb_reduce_partial_push(ex.handle, op, C.byref(e), off, C.byref(pes[0].peers), k, plan["n"]))
+    A.check(A.lib.mxb_exchange_finalize(ex.handle, C.byref(pes[0].peers), plan["fold"], plan["n"], plan["count"]))
+    with pytest.raises(A.MatxB200Error) as ei:
+        pes[0].check()
+    assert ei.value.status == A.ERR_CUDA and "did not arrive" in str(ei.value)
+    assert np.isnan(v.item()) and i.item() == -1
