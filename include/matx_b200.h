@@ -158,8 +158,9 @@ typedef struct mxb_context *mxb_handle_t;
 
 /* ---- lifetime ------------------------------------------------------------------------------- */
 /* Creates a handle bound to the calling thread's current device and to `stream` (a cudaStream_t,
- * NULL = legacy default stream).  The handle owns the grid-combine scratch used by its launches,
- * so one handle must not be used from two host threads at once (use one handle per executor). */
+ * NULL = legacy default stream).  The handle owns the scratch its launches use (grid-combine partials, tile exchange
+ * slots); every entry point locks the handle, so it may be shared by several host threads — their statements are
+ * serialised onto the handle's stream.  Threads that want to overlap use one handle each. */
 int mxb_create(mxb_handle_t *out_handle, void *stream);
 int mxb_destroy(mxb_handle_t h);
 int mxb_set_stream(mxb_handle_t h, void *stream);
@@ -177,6 +178,12 @@ int mxb_elementwise(mxb_handle_t h, const mxb_expr_t *expr, const mxb_out_t *out
  * One launch per call (VAR/STDD: one launch when a reduced row fits in shared memory). */
 int mxb_reduce(mxb_handle_t h, int reduce_op, const mxb_expr_t *expr, int n_reduce_dims,
                const mxb_out_t *out, const mxb_out_t *idx_out, int ddof);
+
+/* min and max of the trailing `n_reduce_dims` dims with their absolute flat indices, ONE read of the operand (reference:
+ * argminmax_impl, transforms/reduce.h:1090-1109 -> cub_dualargreduce, cub.h:1439-1491).  Four outputs of rank expr->rank -
+ * n_reduce_dims; the two value outputs share a dtype, the index outputs are MXB_I64; lowest index wins ties on both sides. */
+int mxb_argminmax(mxb_handle_t h, const mxb_expr_t *expr, int n_reduce_dims, const mxb_out_t *out_min, const mxb_out_t *idx_min,
+                  const mxb_out_t *out_max, const mxb_out_t *idx_max);
 
 /* out(b..., r...) = exp(x(b..., r...) - max_r x(b..., :)) / sum_r exp(x(b..., :) - max_r x(b..., :)) over the trailing
  * `n_reduce_dims` dims of `expr` (1 <= n_reduce_dims <= rank; the caller permutes the softmax axes innermost in BOTH
@@ -289,6 +296,7 @@ int mxb_exchange_free(mxb_handle_t h, void *ptr);
 
 /* ---- introspection ---------------------------------------------------------------------------- */
 int mxb_version(void);                /* major*1000 + minor */
+void mxb_reload_env(void);            /* the MXB_* tuning knobs are read once per thread: re-read them after changing one */
 const char *mxb_last_error(void);     /* thread-local text of the last non-OK status */
 int mxb_device_count(void);           /* 0 when no CUDA device / driver */
 /* Name of the kernel family the last mxb_elementwise / mxb_reduce on this handle launched

@@ -574,6 +574,18 @@ class b200Executor : public cudaExecutor {
       return native(mxb_reduce(h_.get(), op, &b.e, n_reduce, &out, idest ? &iout : nullptr, ddof));
     }
   }
+  template <class Out, class Idx, class In> bool argminmax(Out &dmin, Idx &imin, Out &dmax, Idx &imax, const In &in) const {
+    if constexpr (!b200_detail::lowerable<In>()) return fell_back();
+    else {
+      b200_detail::Builder b;
+      mxb_out_t o[4];
+      if (!b200_detail::out_desc(dmin, o[0]) || !b200_detail::out_desc(imin, o[1]) || !b200_detail::out_desc(dmax, o[2]) ||
+          !b200_detail::out_desc(imax, o[3])) return fell_back();
+      if (!b200_detail::lower_root(b, in)) return fell_back();
+      constexpr int n_reduce = In::Rank() - Out::Rank();
+      return native(mxb_argminmax(h_.get(), &b.e, n_reduce, &o[0], &o[1], &o[2], &o[3]));
+    }
+  }
 
  private:
   bool fell_back() const { fb_->fetch_add(1); return false; }
@@ -632,13 +644,13 @@ MXB_SHIM_ARGREDUCE(argmax, MXB_RED_ARGMAX)
 MXB_SHIM_ARGREDUCE(argmin, MXB_RED_ARGMIN)
 #undef MXB_SHIM_ARGREDUCE
 
-// argminmax (transforms/reduce.h:1090-1109): min and max with their indices.  Served as argmin + argmax — two
-// single-pass launches at the HBM roofline each (the reference's dual-arg CUB path first materialises operator inputs
-// and carries 32-byte tuples); a fused dual-arg operator is listed under "next" in DESIGN.md.
+// argminmax (transforms/reduce.h:1090-1109): min and max with their indices from ONE read of the operand (mxb_argminmax:
+// the dual (value, index) state rides the row walkers; strided reduce dims and differently laid out output pairs run
+// argmin + argmax inside the library).
 template <typename OutType, typename TensorIndexType, typename InType>
 void argminmax_impl(OutType destmin, TensorIndexType &idestmin, OutType destmax, TensorIndexType &idestmax, const InType &in,
                     const b200Executor &exec) {
-  if (exec.reduce_idx(MXB_RED_ARGMIN, destmin, &idestmin, in, 1) && exec.reduce_idx(MXB_RED_ARGMAX, destmax, &idestmax, in, 1)) return;
+  if (exec.argminmax(destmin, idestmin, destmax, idestmax, in)) return;
   argminmax_impl(destmin, idestmin, destmax, idestmax, in, static_cast<const cudaExecutor &>(exec));
 }
 template <typename OutType, typename TensorIndexType, typename InType>

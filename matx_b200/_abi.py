@@ -70,8 +70,8 @@ class Out(C.Structure):
 EXPORTED = [
     "mxb_create", "mxb_destroy", "mxb_set_stream", "mxb_sync", "mxb_elementwise", "mxb_reduce", "mxb_reduce_partial",
     "mxb_reduce_finalize", "mxb_version", "mxb_last_error", "mxb_device_count", "mxb_last_kernel", "mxb_launch_count",
-    "mxb_is_aot", "mxb_reduce_partial_push", "mxb_exchange_finalize", "mxb_exchange_alloc", "mxb_exchange_open", "mxb_exchange_close",
-    "mxb_exchange_free", "mxb_exchange_check", "mxb_softmax", "mxb_cumsum", "mxb_find", "mxb_hist", "mxb_sort", "mxb_unique",
+    "mxb_is_aot", "mxb_reload_env", "mxb_reduce_partial_push", "mxb_exchange_finalize", "mxb_exchange_alloc", "mxb_exchange_open", "mxb_exchange_close",
+    "mxb_exchange_free", "mxb_exchange_check", "mxb_softmax", "mxb_cumsum", "mxb_find", "mxb_hist", "mxb_sort", "mxb_unique", "mxb_argminmax",
 ]
 
 
@@ -115,6 +115,7 @@ def _load() -> C.CDLL:
     lib.mxb_softmax.argtypes = [vp, C.POINTER(Expr), i32, C.POINTER(Out)]
     lib.mxb_cumsum.argtypes = [vp, C.POINTER(Expr), C.POINTER(Out)]
     lib.mxb_find.argtypes = [vp, C.POINTER(Expr), i32, C.c_double, C.POINTER(Out), C.POINTER(Out), i32]
+    lib.mxb_argminmax.argtypes = [vp, C.POINTER(Expr), i32, C.POINTER(Out), C.POINTER(Out), C.POINTER(Out), C.POINTER(Out)]
     lib.mxb_hist.argtypes = [vp, C.POINTER(Expr), C.c_double, C.c_double, C.POINTER(Out)]
     lib.mxb_sort.argtypes = [vp, C.POINTER(Expr), C.POINTER(Out), i32]
     lib.mxb_unique.argtypes = [vp, C.POINTER(Expr), C.POINTER(Out), C.POINTER(Out)]
@@ -127,6 +128,7 @@ def _load() -> C.CDLL:
     lib.mxb_exchange_open.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
     lib.mxb_exchange_close.argtypes = [vp, vp]
     lib.mxb_exchange_free.argtypes = [vp, vp]
+    lib.mxb_reload_env.restype = None
     lib.mxb_last_error.restype = C.c_char_p
     lib.mxb_last_kernel.argtypes = [vp]
     lib.mxb_last_kernel.restype = C.c_char_p
@@ -140,6 +142,20 @@ def _load() -> C.CDLL:
         if fn.restype is C.c_int:
             fn.restype = C.c_int
     return lib
+
+
+_env_seen = None
+
+
+def sync_env() -> None:
+    """The library reads its MXB_* knobs once per thread; tests flip them with monkeypatch between statements, so the Python
+    mirror tells the library to re-read whenever the MXB_* part of os.environ has changed since the last statement."""
+    global _env_seen
+    cur = tuple(sorted((k, v) for k, v in os.environ.items() if k.startswith("MXB_")))
+    if cur != _env_seen:
+        if _env_seen is not None or cur:
+            load().mxb_reload_env()
+        _env_seen = cur
 
 
 _lib = None

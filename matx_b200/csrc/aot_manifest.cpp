@@ -206,6 +206,10 @@ void aot_manifest(std::vector<ManifestItem> *items) {
   // CTA-per-item streaming of a single contiguous reduce run: 32-byte loads for the sums, four loads in flight for all
   add_vu(prog_identity(MXB_F32), FAM_RED_INNER, MXB_RED_SUM, MXB_F32, 0, 8, 4);
   add_vu(prog_identity(MXB_F32), FAM_RED_INNER, MXB_RED_PROD, MXB_F32, 0, 8, 4);
+  add_vu(prog_identity(MXB_F32), FAM_RED_INNER, MXB_RED_MAX, MXB_F32, 0, 8, 4);
+  add_vu(prog_identity(MXB_F32), FAM_RED_INNER, MXB_RED_MIN, MXB_F32, 0, 8, 4);
+  add_vu(prog_identity(MXB_I32), FAM_RED_INNER, MXB_RED_MAX, MXB_I32, 0, 8, 4);
+  add_vu(prog_identity(MXB_I32), FAM_RED_INNER, MXB_RED_MIN, MXB_I32, 0, 8, 4);
   add_vu(prog_identity(MXB_I32), FAM_RED_INNER, MXB_RED_SUM, MXB_I32, 0, 8, 4);
   for (int op : kAllOps) {
     if (op != MXB_RED_PROD) add_vu(prog_identity(MXB_F64), FAM_RED_INNER, op, MXB_F64, 0, 4, 4);
@@ -225,6 +229,8 @@ void aot_manifest(std::vector<ManifestItem> *items) {
       if ((d == MXB_F32 || d == MXB_BF16) && op != MXB_RED_PROD) add(e, FAM_RED_OUTER_TMA, op, d, 0, false);
     }
   }
+  // fused argminmax of plain fp32 tensors
+  for (int team : {0, 1}) add(prog_identity(MXB_F32), FAM_RED_INNER, KOP_ARGMINMAX, MXB_F32, team, false);
   // one-pass variance (Welford + Chan) for rows that cannot stay on chip and for strided rows
   for (int d : {MXB_F32, MXB_C64})
     for (int team : {0, 1}) add(prog_identity(d), FAM_RED_INNER, MXB_RED_VAR, MXB_F32, team, d == MXB_F32);
@@ -236,9 +242,6 @@ void aot_manifest(std::vector<ManifestItem> *items) {
     for (int d : {MXB_F32, MXB_C64, MXB_BF16}) add(prog_identity(d), FAM_VAR_TMA, MXB_RED_VAR, MXB_F32, ipt, false);
     add(prog_identity(MXB_F64), FAM_VAR_TMA, MXB_RED_VAR, MXB_F64, ipt, false);
   }
-  // opt-in twin of var_tma (MXB_VAR_TMA2=1): producer warp + two consumer teams
-  for (int ipt : {4, 8, 16})
-    for (int d : {MXB_F32, MXB_C64}) add(prog_identity(d), FAM_VAR_TMA2, MXB_RED_VAR, MXB_F32, ipt, false);
   for (int ipt : {1, 2, 4, 8}) {
     for (int d : {MXB_F32, MXB_C64}) add(prog_identity(d), FAM_VAR_GROUP, MXB_RED_VAR, MXB_F32, ipt, false);
     for (int d : {MXB_F32, MXB_C64}) add(prog_identity(d), FAM_VAR_REG, MXB_RED_VAR, MXB_F32, ipt, false);

@@ -13,6 +13,9 @@
 #include <cuda.h>  // CUtensorMap types only; the encoder's entry point is queried at run time
 
 #include <algorithm>
+#include <atomic>
+#include <mutex>
+#include <unordered_map>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -31,6 +34,11 @@ using mxb::RedParams;
 // context
 // ---------------------------------------------------------------------------------------------------
 struct mxb_context {
+  // One handle = one stream + one set of scratch buffers.  Entry points take this lock, so a handle (a b200Executor and
+  // its copies) may be used from several host threads: their statements are serialised onto the handle's stream, which
+  // is what keeps the shared scratch safe (the reference keys its plan caches per thread, core/cache.h:224-245; threads
+  // that want to overlap use one executor each, as there).
+  std::recursive_mutex mu;
   int device = 0;
   cudaStream_t stream = nullptr;
   int sm_count = 148;
@@ -212,14 +220,33 @@ EncodeTiledFn tensor_map_encoder() {
 }
 
 bool aligned_to(const void *p, int64_t bytes) { return ((uintptr_t)p % (uintptr_t)bytes) == 0; }
-int env_int(const char *name, int dflt) {
+// Development / tuning knobs (MXB_TUNE_*, MXB_VAR_*, ...) are environment variables.  They are read ONCE per thread and
+// knob — a dispatch used to cost ~15 getenv() scans of the environment — and again only after mxb_reload_env() (the
+// Python test harness calls it when it has changed a knob).  Names are string literals: the cache is keyed by pointer.
+std::atomic<unsigned> g_env_gen{1};
+struct EnvCache {
+  unsigned gen = 0;
+  std::unordered_map<const void *, std::pair<bool, int>> v;   // literal -> (set, value)
+};
+const std::pair<bool, int> &env_lookup(const char *name) {
+  thread_local EnvCache c;
+  const unsigned g = g_env_gen.load(std::memory_order_relaxed);
+  if (c.gen != g) { c.v.clear(); c.gen = g; }
+  auto it = c.v.find((const void *)name);
+  if (it != c.v.end()) return it->second;
   const char *v = getenv(name);
-  return (v && *v) ? atoi(v) : dflt;
+  return c.v.emplace((const void *)name, std::make_pair(v && *v, (v && *v) ? atoi(v) : 0)).first->second;
 }
+int env_int(const char *name, int dflt) {
+  const std::pair<bool, int> &e = env_lookup(name);
+  return e.first ? e.second : dflt;
+}
+bool env_set(const char *name) { return env_lookup(name).first; }
 
 int acc_bytes(int op, int value_dtype) {
   switch (op) {
     case MXB_RED_ARGMAX: case MXB_RED_ARGMIN: return 16;
+    case KOP_ARGMINMAX: return 32;
     case MXB_RED_ANY: case MXB_RED_ALL: return 4;
     case KOP_LSE: return 2 * dtype_bytes(value_dtype);
     case MXB_RED_VAR: return value_dtype == MXB_C64 ? 32 : 16;   // one-pass (pivot, s1, s2, count) state: 16 / 24 bytes
@@ -234,7 +261,7 @@ struct Kernel { const void *fn = nullptr; bool jit = false; std::string key; };
 
 int get_kernel(const ExprInfo &info, const KernelSpec &spec, Kernel *k) {
   k->key = kernel_key(info, spec);
-  const char *flavor = getenv("MXB_LD_FLAVOR");  // development knob: forces a JIT build with another load cache policy
+  const char *flavor = env_set("MXB_LD_FLAVOR") ? getenv("MXB_LD_FLAVOR") : nullptr;  // development knob: forces a JIT build with another load cache policy
   if (flavor && *flavor) k->key += std::string("|F") + flavor;
   k->fn = (flavor && *flavor) ? nullptr : lookup_aot(k->key);
   k->jit = false;
@@ -246,7 +273,7 @@ int get_kernel(const ExprInfo &info, const KernelSpec &spec, Kernel *k) {
     k->jit = true;
     return MXB_OK;
   }
-  if (getenv("MXB_DISABLE_JIT")) return fail(MXB_ERR_JIT, "no ahead-of-time kernel for " + k->key + " and MXB_DISABLE_JIT is set");
+  if (env_set("MXB_DISABLE_JIT")) return fail(MXB_ERR_JIT, "no ahead-of-time kernel for " + k->key + " and MXB_DISABLE_JIT is set");
   const std::string sym = kernel_symbol(k->key);
   std::string wrap, err;
   int st = kernel_wrapper_src(info, spec, sym, &wrap, &err);
@@ -337,6 +364,7 @@ struct RedOptions {
   int64_t idx_base = 0;
   const mxb_peers_t *peers = nullptr;  // raw_partial + peers: push the record into every rank's exchange buffer
   int peer_item = 0;
+  void *out2 = nullptr, *idx2 = nullptr;   // KOP_ARGMINMAX: the max value / max index outputs (strides of out / idx_out)
 };
 
 int check_expr_shape(const mxb_expr_t *e) {
@@ -442,9 +470,9 @@ int reduce_launch(mxb_context *h, int kop, const mxb_expr_t &e, const ExprInfo &
     spec.family = FAM_VAR_SMEM;
     spec.V = (vmax > 1 && inner_ok(vmax)) ? vmax : 1;
     // rows that fit in the registers of one CTA: blockDim.x * IPT vectors, single contiguous run, no ragged tail
-    if (gr.n == 1 && inner_ok(spec.V) && gr.size[0] % spec.V == 0 && !getenv("MXB_VAR_SMEM_ONLY")) {
+    if (gr.n == 1 && inner_ok(spec.V) && gr.size[0] % spec.V == 0 && !env_set("MXB_VAR_SMEM_ONLY")) {
       const int64_t Lv = gr.size[0] / spec.V;
-      if (Lv <= 256 && !getenv("MXB_VAR_NO_GROUP")) {
+      if (Lv <= 256 && !env_set("MXB_VAR_NO_GROUP")) {
         // short rows: G lanes of a warp per row, the row in registers, shuffles only
         int G = 1;
         while (G < 32 && G < Lv) G <<= 1;
@@ -464,7 +492,7 @@ int reduce_launch(mxb_context *h, int kop, const mxb_expr_t &e, const ExprInfo &
     }
     // plain tensor, long contiguous rows: TMA-staged ring of rows in shared memory (one HBM read, copy engine keeps
     // rows in flight while the SM runs the two passes)
-    if (e.n_nodes == 1 && nl == 1 && gr.n == 1 && gr.ls[0][0] == 1 && !getenv("MXB_VAR_SMEM_ONLY") && !getenv("MXB_VAR_NO_TMA")) {
+    if (e.n_nodes == 1 && nl == 1 && gr.n == 1 && gr.ls[0][0] == 1 && !env_set("MXB_VAR_SMEM_ONLY") && !env_set("MXB_VAR_NO_TMA")) {
       const int64_t esz = dtype_bytes(e.leaves[0].dtype);
       const int64_t rowbytes = gr.size[0] * esz;
       const int64_t rowstride = (rowbytes + 127) & ~int64_t(127);
@@ -488,16 +516,6 @@ int reduce_launch(mxb_context *h, int kop, const mxb_expr_t &e, const ExprInfo &
         spec.V = policy_vmax(info);
         var_ipt = (int)stages;
         tma_ctas = (int)ctas;
-        // opt-in (MXB_VAR_TMA2=1, not yet measured): producer warp + two consumer teams of 256 threads, one CTA per SM,
-        // rows of at most 256 x 16 vectors
-        if (env_int("MXB_VAR_TMA2", 0) && rowbytes / 16 <= 256 * 16) {
-          const int64_t st2 = std::min<int64_t>(4, ((int64_t)h->max_smem_optin - 1024 - 128) / rowstride);
-          if (st2 >= 2) {
-            spec.family = FAM_VAR_TMA2;
-            var_ipt = (int)st2;
-            tma_ctas = 1;
-          }
-        }
       }
     }
   } else if (vmax > 1 && inner_ok(vmax)) {
@@ -519,6 +537,7 @@ int reduce_launch(mxb_context *h, int kop, const mxb_expr_t &e, const ExprInfo &
     spec.family = FAM_RED_INNER;  // V == 1 walks any strides
     spec.V = 1;
   }
+  if (kop == KOP_ARGMINMAX && spec.family != FAM_RED_INNER) return MXB_ERR_NOT_SUPPORTED;   // mxb_argminmax runs argmin + argmax
   // ---- strided / permuted reduce dim of a plain tensor: TMA-staged tiles instead of the LDG column walker ----
   // (one collapsed reduce dim, at most one other batch dim, 16-byte granularity everywhere, enough strips to fill
   // the machine without splitting R).  Tile copies go through a tensor map (any pitch); without one, plain bulk
@@ -616,13 +635,6 @@ int reduce_launch(mxb_context *h, int kop, const mxb_expr_t &e, const ExprInfo &
     if (ipt > 8) { tma_block = 1024; ipt = 8; }
     spec.team = ipt;
   }
-  if (spec.family == FAM_VAR_TMA2) {
-    const int64_t Rv16 = gr.size[0] * dtype_bytes(e.leaves[0].dtype) / 16;
-    int ipt = 1;
-    while ((int64_t)ipt * 256 < Rv16) ipt <<= 1;
-    spec.team = ipt;
-    tma_block = 2 * 256 + 32;   // two consumer teams + the producer warp
-  }
   if (tune_u > 0 && spec.family != FAM_VAR_REG) spec.U = tune_u;
 
   RedParams p;
@@ -662,6 +674,8 @@ int reduce_launch(mxb_context *h, int kop, const mxb_expr_t &e, const ExprInfo &
   p.out.ptr = out ? out->data : nullptr;
   p.idx.ptr = idx_out ? idx_out->data : nullptr;
   p.idx_base = opt.idx_base;
+  p.out2 = opt.out2;
+  p.idx2 = opt.idx2;
   p.post_div = opt.post_div ? 1 : 0;
   // one-pass variance through the generic walkers: the stored value is M2 / (N - ddof)
   if (kop == MXB_RED_VAR && (spec.family == FAM_RED_INNER || spec.family == FAM_RED_OUTER || spec.family == FAM_RED_OUTER_TMA)) p.post_div = 1;
@@ -688,7 +702,7 @@ int reduce_launch(mxb_context *h, int kop, const mxb_expr_t &e, const ExprInfo &
   const int sm = h->sm_count;
   unsigned grid = 1, block = tune_block > 0 ? (unsigned)tune_block : 256u, smem = 0;
   // persistent grids: CTAs per SM x SM count (every CTA loops over its share of the rows / tiles)
-  if (spec.family == FAM_VAR_TMA || spec.family == FAM_VAR_TMA2) {
+  if (spec.family == FAM_VAR_TMA) {
     const int64_t rowstride = (R * dtype_bytes(e.leaves[0].dtype) + 127) & ~int64_t(127);
     p.splits = var_ipt;  // ring depth
     block = (unsigned)tma_block;
@@ -710,23 +724,29 @@ int reduce_launch(mxb_context *h, int kop, const mxb_expr_t &e, const ExprInfo &
     const int64_t row_bytes = R * info.max_leaf_bytes;
     // rows under 32 KB (arg ops, whose CTA stage is the expensive one: under 128 KB): a warp — or a slice of one —
     // per row, no shared memory, no barrier; longer rows: a CTA, or several, per row (tools/shape_sweep*.py)
-    const bool arg_op = (kop == MXB_RED_ARGMAX || kop == MXB_RED_ARGMIN);
+    const bool arg_op = (kop == MXB_RED_ARGMAX || kop == MXB_RED_ARGMIN || kop == KOP_ARGMINMAX);
     const int64_t t1_limit = env_int("MXB_TUNE_T1_BYTES", arg_op ? 131072 : 32768);
     spec.team = (row_bytes >= t1_limit || B < 8 * (int64_t)sm) ? 0 : 1;
     if (row_bytes < 4096) spec.team = 1;   // short rows never want a whole CTA
     if (env_int("MXB_TUNE_TEAM", -1) >= 0) spec.team = env_int("MXB_TUNE_TEAM", -1);
-    if (spec.team == 0 && tune_u <= 0 && env_int("MXB_TUNE_V", 0) <= 0 && nl <= 2 && gr.n == 1) {
+    // ops whose state is a multi-word record with a costly merge (one-pass variance, running log-sum-exp) keep the
+    // round-1 shape: the per-item CTA stage is what they pay for (full-tensor var: 0.65 ms static vs 1.35 ms with 64 KB items)
+    const bool heavy_merge = kop == MXB_RED_VAR || kop == KOP_LSE;
+    // accumulators wider than two words (arg ops, variance) are compiled without the dynamic deal (mxb_device.cuh, DYN_OK):
+    // they and log-sum-exp take the static round-robin deal of round 1
+    const bool static_deal = heavy_merge || acc_bytes(kop, info.value_dtype) > 8;
+    if (spec.team == 0 && tune_u <= 0 && env_int("MXB_TUNE_V", 0) <= 0 && nl <= 2 && gr.n == 1 && !heavy_merge) {
       // CTA-per-item streaming of one or two operands (profiles/r2_sweeps.md): four loads per leaf in flight, and — for
-      // the sums, whose per-element work is one add — 32-byte loads (fp32 2^30: 0.5877 vs 0.5991 ms; the arg ops and
-      // max / min keep 16 bytes: their per-element compare chains want the registers)
+      // the ops whose per-element work is one add or compare (sum, prod, max, min) — 32-byte loads (fp32 2^30 sum: 0.5877
+      // vs 0.5991 ms); the arg ops keep 16 bytes: their (value, index) compare chains want the registers
       spec.U = 4;
-      const bool sum_like = kop == MXB_RED_SUM || kop == MXB_RED_PROD;
+      const bool sum_like = kop == MXB_RED_SUM || kop == MXB_RED_PROD || kop == MXB_RED_MAX || kop == MXB_RED_MIN;   // one add / compare per element
       const int wide = 32 / info.max_leaf_bytes;
       if (sum_like && wide > spec.V && wide <= 8 && spec.V > 1 && inner_ok(wide)) spec.V = wide;
     }
     // many long rows, one CTA per row at a time: 128-thread CTAs (8 per SM) hide a row's CTA stage behind the other
     // rows' loads better than 4 CTAs of 256 (complex<float> 65536 x 8192 mean: 0.5829 vs 0.6080 ms)
-    if (spec.team == 0 && tune_block <= 0 && B >= 2 * (int64_t)sm) block = 128;
+    if (spec.team == 0 && tune_block <= 0 && B >= 2 * (int64_t)sm && !heavy_merge) block = 128;
     if (spec.team == 0) {
       const int64_t L = gr.size[gr.n - 1];
       const int64_t Q = (R / L) * (L / spec.V);  // vector steps per row
@@ -740,6 +760,7 @@ int reduce_launch(mxb_context *h, int kop, const mxb_expr_t &e, const ExprInfo &
       const int resident = resident_ctas(kq, block, 0, 4);
       int cps = tune_cps > 0 ? tune_cps : std::min(resident, 8);
       const int64_t grid_max = (int64_t)sm * cps;
+      bool rr_static = false;
       if (B < 2 * (int64_t)sm) {
         // few long rows: a row is cut into S items.  One contiguous reduce run: an item is a contiguous chunk of tiles
         // (64 KB of the widest leaf; more for inputs so large that the final fold of the S partials would show), drawn
@@ -748,8 +769,15 @@ int reduce_launch(mxb_context *h, int kop, const mxb_expr_t &e, const ExprInfo &
           const int64_t nfull = Q / ((int64_t)block * spec.U);
           const int64_t want = env_int("MXB_TUNE_CHUNK_TILES", 0) > 0 ? env_int("MXB_TUNE_CHUNK_TILES", 0)
                                                                        : (B * nfull >= 8 * grid_max ? 4 : (B * nfull >= 2 * grid_max ? 2 : 1));
-          const int64_t cht = std::max<int64_t>(want, (nfull + 16383) / 16384);
-          S = std::max<int64_t>(1, (nfull + cht - 1) / cht);
+          int64_t cht = std::max<int64_t>(want, (nfull + 16383) / 16384);
+          // the round-1 deal — tiles round-robin over sm x 8 static splits, no chunks (MXB_TUNE_RR=1 forces it for the A/B)
+          if (static_deal || env_int("MXB_TUNE_RR", 0)) cht = 0;
+          if (cht > 0) {
+            S = std::max<int64_t>(1, (nfull + cht - 1) / cht);
+          } else {
+            rr_static = true;   // 8 CTAs per SM in two waves, one split each, tiles dealt round-robin to the splits
+            S = std::max<int64_t>(1, std::min<int64_t>(((int64_t)sm * 8 + B - 1) / B, std::max<int64_t>(1, nfull / 2)));
+          }
           p.chunk_tiles = (int)cht;
         } else {
           S = (grid_max + B - 1) / B;
@@ -758,10 +786,12 @@ int reduce_launch(mxb_context *h, int kop, const mxb_expr_t &e, const ExprInfo &
         }
       }
       p.splits = (int)S;
-      grid = (unsigned)std::min<int64_t>(B * S, grid_max);
-      const bool dynamic = B * S > (int64_t)grid && env_int("MXB_TUNE_DYNAMIC", 1) && B * S < (1ll << 31);
+      grid = (unsigned)std::min<int64_t>(B * S, rr_static ? (int64_t)sm * 8 : grid_max);
+      // dynamic deal for the chunks of split rows; whole rows (S == 1) stay on the static round-robin: their CTA stage is
+      // per row either way and the draw only adds latency there (complex<float> 65536 x 8192 mean: 0.592 static, 0.614 dynamic)
+      const bool dynamic = !rr_static && !static_deal && B * S > (int64_t)grid && (S > 1 || env_int("MXB_TUNE_DYNAMIC", 0) == 2) && env_int("MXB_TUNE_DYNAMIC", 1) && B * S < (1ll << 31);
       // combine exact in any order (max / min / arg / any / all, integer sums): one accumulator per CTA across its items
-      const bool exact_op = kop == MXB_RED_MAX || kop == MXB_RED_MIN || kop == MXB_RED_ARGMAX || kop == MXB_RED_ARGMIN || kop == MXB_RED_ANY ||
+      const bool exact_op = kop == MXB_RED_MAX || kop == MXB_RED_MIN || kop == MXB_RED_ARGMAX || kop == MXB_RED_ARGMIN || kop == KOP_ARGMINMAX || kop == MXB_RED_ANY ||
                             kop == MXB_RED_ALL || ((kop == MXB_RED_SUM || kop == MXB_RED_PROD) && (info.value_dtype == MXB_I32 || info.value_dtype == MXB_I64));
       if (dynamic && B == 1 && S > 1 && exact_op && env_int("MXB_TUNE_CARRY", 1)) p.carry_items = 1;
       {
@@ -931,6 +961,7 @@ int var_partial(mxb_context *h, const mxb_expr_t &e, const ExprInfo &info, const
 int reduce_impl(mxb_context *h, int op, const mxb_expr_t *expr_in, int n_reduce, const mxb_out_t *out, const mxb_out_t *idx_out,
                 int ddof, const RedOptions *partial_opt) {
   if (!h) return fail(MXB_ERR_INVALID, "null handle");
+  std::lock_guard<std::recursive_mutex> lock_(h->mu);
   if (op < 0 || op >= MXB_RED_COUNT) return fail(MXB_ERR_INVALID, "unknown reduce op");
   int st = check_expr_shape(expr_in);
   if (st != MXB_OK) return st;
@@ -979,22 +1010,22 @@ int reduce_impl(mxb_context *h, int op, const mxb_expr_t *expr_in, int n_reduce,
     const int64_t row_bytes = R * dtype_bytes(info.value_dtype);
     // MXB_VAR_ONEPASS=1: every fp32 / complex<float> variance through the one-pass op (A/B knob, tools/var_onepass_ab.py)
     const bool onepass_all = (info.value_dtype == MXB_F32 || info.value_dtype == MXB_C64) && env_int("MXB_VAR_CHAN", 1) &&
-                             env_int("MXB_VAR_ONEPASS", 0) && !getenv("MXB_VAR_TWO_LAUNCH") && !getenv("MXB_VAR_SMEM_ONLY") && R < (1ll << 31);
+                             env_int("MXB_VAR_ONEPASS", 0) && !env_set("MXB_VAR_TWO_LAUNCH") && !env_set("MXB_VAR_SMEM_ONLY") && R < (1ll << 31);
     // fp32 rows of 16..128 elements: the warp-team walker with the one-pass op beats the register-resident two-pass
     // group kernel (8388608x32: 0.54 vs 0.38 of peak, 4194304x64: 0.48 vs 0.36; profiles/r1_var_onepass_ab.jsonl)
     const bool onepass_short = info.value_dtype == MXB_F32 && env_int("MXB_VAR_CHAN", 1) && R >= env_int("MXB_VAR_ONEPASS_MIN_R", 16) &&
-                               R <= env_int("MXB_VAR_ONEPASS_MAX_R", 128) && !getenv("MXB_VAR_TWO_LAUNCH") && !getenv("MXB_VAR_SMEM_ONLY") &&
-                               !getenv("MXB_VAR_NO_GROUP");
+                               R <= env_int("MXB_VAR_ONEPASS_MAX_R", 128) && !env_set("MXB_VAR_TWO_LAUNCH") && !env_set("MXB_VAR_SMEM_ONLY") &&
+                               !env_set("MXB_VAR_NO_GROUP");
     if (onepass_all || onepass_short) {
       opt.post_div = true;
       return reduce_launch(h, MXB_RED_VAR, e, info, n_reduce, out, nullptr, opt);
     }
-    if (row_bytes <= (int64_t)h->max_smem_optin - 4096 && !getenv("MXB_VAR_TWO_LAUNCH")) {
+    if (row_bytes <= (int64_t)h->max_smem_optin - 4096 && !env_set("MXB_VAR_TWO_LAUNCH")) {
       return reduce_launch(h, MXB_RED_VAR, e, info, n_reduce, out, nullptr, opt, /*var_smem=*/true);
     }
     // Row does not fit in shared memory.  fp32 / complex<float>: ONE read through the generic walkers with the
     // one-pass (mean, M2, n) op (Welford per thread, Chan's combine across threads / CTAs).
-    if ((info.value_dtype == MXB_F32 || info.value_dtype == MXB_C64) && env_int("MXB_VAR_CHAN", 1) && !getenv("MXB_VAR_TWO_LAUNCH") &&
+    if ((info.value_dtype == MXB_F32 || info.value_dtype == MXB_C64) && env_int("MXB_VAR_CHAN", 1) && !env_set("MXB_VAR_TWO_LAUNCH") &&
         R < (1ll << 31)) {   // the state counts elements in an int
       opt.post_div = true;
       return reduce_launch(h, MXB_RED_VAR, e, info, n_reduce, out, nullptr, opt);
@@ -1258,6 +1289,7 @@ __global__ void exchange_finalize_kernel(const __grid_constant__ ExchangeParams 
 extern "C" {
 
 int mxb_version(void) { return MXB_VERSION_MAJOR * 1000 + MXB_VERSION_MINOR; }
+void mxb_reload_env(void) { g_env_gen.fetch_add(1); }
 const char *mxb_last_error(void) { return g_err.c_str(); }
 
 int mxb_device_count(void) {
@@ -1311,6 +1343,7 @@ int mxb_destroy(mxb_handle_t h) {
 
 int mxb_set_stream(mxb_handle_t h, void *stream) {
   if (!h) return fail(MXB_ERR_INVALID, "null handle");
+  std::lock_guard<std::recursive_mutex> lock_(h->mu);
   if ((cudaStream_t)stream != h->stream) {
     // scratch is stream-ordered: hand it over only once the old stream is done with it
     MXB_CUDA(cudaStreamSynchronize(h->stream));
@@ -1321,6 +1354,7 @@ int mxb_set_stream(mxb_handle_t h, void *stream) {
 
 int mxb_sync(mxb_handle_t h) {
   if (!h) return fail(MXB_ERR_INVALID, "null handle");
+  std::lock_guard<std::recursive_mutex> lock_(h->mu);
   MXB_CUDA(cudaStreamSynchronize(h->stream));
   return MXB_OK;
 }
@@ -1331,6 +1365,50 @@ int64_t mxb_launch_count(mxb_handle_t h) { return h ? h->launches : 0; }
 int mxb_reduce(mxb_handle_t h, int reduce_op, const mxb_expr_t *expr, int n_reduce_dims, const mxb_out_t *out,
                const mxb_out_t *idx_out, int ddof) {
   return reduce_impl(h, reduce_op, expr, n_reduce_dims, out, idx_out, ddof, nullptr);
+}
+
+int mxb_argminmax(mxb_handle_t h, const mxb_expr_t *expr_in, int n_reduce, const mxb_out_t *out_min, const mxb_out_t *idx_min,
+                  const mxb_out_t *out_max, const mxb_out_t *idx_max) {
+  if (!h) return fail(MXB_ERR_INVALID, "null handle");
+  std::lock_guard<std::recursive_mutex> lock_(h->mu);
+  int st = check_expr_shape(expr_in);
+  if (st != MXB_OK) return st;
+  if (n_reduce < 0 || n_reduce > expr_in->rank) return fail(MXB_ERR_INVALID, "n_reduce_dims out of range");
+  const int nbd = expr_in->rank - n_reduce;
+  const mxb_out_t *outs[4] = {out_min, idx_min, out_max, idx_max};
+  for (int k = 0; k < 4; ++k) {
+    if (!outs[k] || !outs[k]->data) return fail(MXB_ERR_INVALID, "argminmax needs four outputs");
+    if (outs[k]->rank != nbd) return fail(MXB_ERR_SIZE, "output rank must be expr rank - n_reduce_dims");
+    for (int d = 0; d < nbd; ++d)
+      if (outs[k]->size[d] != expr_in->size[d]) return fail(MXB_ERR_SIZE, "output size mismatch in dim " + std::to_string(d));
+  }
+  if (idx_min->dtype != MXB_I64 || idx_max->dtype != MXB_I64) return fail(MXB_ERR_INVALID, "index outputs must be MXB_I64 (matx::index_t)");
+  if (out_min->dtype != out_max->dtype) return fail(MXB_ERR_INVALID, "the two value outputs must have one dtype");
+  if (out_min->dtype < 0 || out_min->dtype >= MXB_DTYPE_COUNT) return fail(MXB_ERR_INVALID, "output dtype out of range");
+  // one launch writes both pairs through the strides of the first: the min and max outputs must be laid out alike
+  bool same_layout = true;
+  for (int d = 0; d < nbd; ++d)
+    if (out_min->size[d] > 1 && (out_min->stride[d] != out_max->stride[d] || idx_min->stride[d] != idx_max->stride[d])) same_layout = false;
+  MXB_CUDA(cudaSetDevice(h->device));
+  mxb_expr_t e;
+  std::string err;
+  st = canonicalize(expr_in, &e, &err);
+  if (st != MXB_OK) return fail(st, err);
+  ExprInfo info;
+  st = analyze_expr(&e, &info, &err);
+  if (st != MXB_OK) return fail(st, err);
+  // the dual state rides the row walkers only (reduce_inner): a strided reduce dim (reduce_launch answers
+  // MXB_ERR_NOT_SUPPORTED before launching anything), differently laid out output pairs and complex values take two launches
+  if (same_layout && info.value_dtype != MXB_C64) {
+    RedOptions opt;
+    opt.out2 = out_max->data;
+    opt.idx2 = idx_max->data;
+    st = reduce_launch(h, KOP_ARGMINMAX, e, info, n_reduce, out_min, idx_min, opt);
+    if (st != MXB_ERR_NOT_SUPPORTED) return st;
+  }
+  st = reduce_impl(h, MXB_RED_ARGMIN, expr_in, n_reduce, out_min, idx_min, 1, nullptr);
+  if (st != MXB_OK) return st;
+  return reduce_impl(h, MXB_RED_ARGMAX, expr_in, n_reduce, out_max, idx_max, 1, nullptr);
 }
 
 int mxb_reduce_partial(mxb_handle_t h, int reduce_op, const mxb_expr_t *expr, int64_t slab_offset, void *partial_record) {
@@ -1351,6 +1429,7 @@ int mxb_reduce_partial(mxb_handle_t h, int reduce_op, const mxb_expr_t *expr, in
 int mxb_reduce_finalize(mxb_handle_t h, int reduce_op, int32_t value_dtype, const void *gathered_records, int world,
                         int64_t record_stride_bytes, int64_t global_count, int ddof, const mxb_out_t *out, const mxb_out_t *idx_out) {
   if (!h) return fail(MXB_ERR_INVALID, "null handle");
+  std::lock_guard<std::recursive_mutex> lock_(h->mu);
   if (!gathered_records || world <= 0) return fail(MXB_ERR_INVALID, "no records to fold");
   if (record_stride_bytes == 0) record_stride_bytes = MXB_PARTIAL_BYTES;
   if (record_stride_bytes < MXB_PARTIAL_BYTES || record_stride_bytes % 16) return fail(MXB_ERR_INVALID, "record stride must be a multiple of 16 and >= 32");
@@ -1455,6 +1534,7 @@ int mxb_exchange_free(mxb_handle_t h, void *ptr) {
 
 int mxb_exchange_finalize(mxb_handle_t h, const mxb_peers_t *peers, const mxb_fold_item_t *items, int n_items, int64_t global_count) {
   if (!h) return fail(MXB_ERR_INVALID, "null handle");
+  std::lock_guard<std::recursive_mutex> lock_(h->mu);
   if (!peers || !items || n_items < 1 || n_items > MXB_MAX_ITEMS) return fail(MXB_ERR_INVALID, "bad exchange arguments");
   if (peers->world < 1 || peers->world > MXB_MAX_PEERS) return fail(MXB_ERR_INVALID, "bad peer table");
   MXB_CUDA(cudaSetDevice(h->device));
@@ -1523,6 +1603,7 @@ int mxb_exchange_check(mxb_handle_t h, const mxb_peers_t *peers) {
 
 int mxb_elementwise(mxb_handle_t h, const mxb_expr_t *expr_in, const mxb_out_t *out) {
   if (!h) return fail(MXB_ERR_INVALID, "null handle");
+  std::lock_guard<std::recursive_mutex> lock_(h->mu);
   int st = check_expr_shape(expr_in);
   if (st != MXB_OK) return st;
   if (!out || !out->data) return fail(MXB_ERR_INVALID, "null output");
@@ -1722,6 +1803,7 @@ int mxb_elementwise(mxb_handle_t h, const mxb_expr_t *expr_in, const mxb_out_t *
 // ---------------------------------------------------------------------------------------------------
 int mxb_softmax(mxb_handle_t h, const mxb_expr_t *expr_in, int n_reduce, const mxb_out_t *out) {
   if (!h) return fail(MXB_ERR_INVALID, "null handle");
+  std::lock_guard<std::recursive_mutex> lock_(h->mu);
   int st = check_expr_shape(expr_in);
   if (st != MXB_OK) return st;
   if (n_reduce < 1 || n_reduce > expr_in->rank) return fail(MXB_ERR_INVALID, "softmax needs 1 <= n_reduce_dims <= rank");
@@ -1768,7 +1850,7 @@ int mxb_softmax(mxb_handle_t h, const mxb_expr_t *expr_in, int n_reduce, const m
 
   // ---- one launch, row in registers: a single reduce run that every leaf and the output walk with stride 0 / 1 ----
   const int obytes = dtype_bytes(out->dtype);
-  bool rows_ok = gr.n == 1 && gb.n <= KMAXD && gr.os[0] == 1 && !getenv("MXB_SOFTMAX_TWO_LAUNCH");
+  bool rows_ok = gr.n == 1 && gb.n <= KMAXD && gr.os[0] == 1 && !env_set("MXB_SOFTMAX_TWO_LAUNCH");
   for (int k = 0; rows_ok && k < nl; ++k) rows_ok = (gr.ls[k][0] == 0 || gr.ls[k][0] == 1);
   if (rows_ok) {
     int vmax = env_int("MXB_TUNE_V", 0) > 0 ? env_int("MXB_TUNE_V", 0) : policy_vmax(info);
@@ -1903,6 +1985,7 @@ int mxb_softmax(mxb_handle_t h, const mxb_expr_t *expr_in, int n_reduce, const m
 // ---------------------------------------------------------------------------------------------------
 int mxb_cumsum(mxb_handle_t h, const mxb_expr_t *expr_in, const mxb_out_t *out) {
   if (!h) return fail(MXB_ERR_INVALID, "null handle");
+  std::lock_guard<std::recursive_mutex> lock_(h->mu);
   int st = check_expr_shape(expr_in);
   if (st != MXB_OK) return st;
   if (expr_in->rank < 1) return fail(MXB_ERR_INVALID, "cumsum needs rank >= 1");
@@ -2065,6 +2148,7 @@ int mxb_cumsum(mxb_handle_t h, const mxb_expr_t *expr_in, const mxb_out_t *out) 
 static int find_impl(mxb_handle_t h, const mxb_expr_t *expr_in, int select_op, double threshold, const mxb_out_t *out,
                      const mxb_out_t *count_out, int want_indices, bool unique) {
   if (!h) return fail(MXB_ERR_INVALID, "null handle");
+  std::lock_guard<std::recursive_mutex> lock_(h->mu);
   if (!expr_in) return fail(MXB_ERR_INVALID, "null expression");
   if (expr_in->rank >= 0 && expr_in->rank <= MXB_MAX_RANK && count_out && count_out->data && count_out->rank == 0 && count_out->dtype == MXB_I32) {
     int64_t n0 = 1;
@@ -2169,17 +2253,16 @@ static int find_impl(mxb_handle_t h, const mxb_expr_t *expr_in, int select_op, d
     spec.out_dtype = out->dtype;
     st = get_kernel(info, spec, &k);
     if (st != MXB_OK) return st;
-    // pipeline depth: tiles of a CTA between rank + stage (phase 1) and offset + copy-out (phase 2); every staged tile
-    // holds up to TILE output elements.  4 is the depth at which every exchange job finds its inputs published
-    int depth = env_int("MXB_TUNE_SEL_DEPTH", 0) > 0 ? env_int("MXB_TUNE_SEL_DEPTH", 0) : 4;
-    while (depth > 2 && (int64_t)depth * TILE * dtype_bytes(out->dtype) > 96 * 1024) --depth;
-    depth = std::min(depth, 8);
-    p.sel_depth = depth;
-    const unsigned smem = (unsigned)(depth * TILE * dtype_bytes(out->dtype));
-    const int res = resident_ctas(k, 256, smem, 3);
+    // warp tiles of 32 lanes x 32 elements (16 for 8-byte values), dealt round-robin to the warps of a grid that is
+    // resident as a whole (cooperative launch: a tile only waits for tiles whose warps are running)
+    const int64_t wtile = 32 * (dtype_bytes(info.value_dtype) > 4 ? 16 : 32);
+    const int64_t nwt = (N + wtile - 1) / wtile;
+    const unsigned smem = 0;
+    const int res = resident_ctas(k, 256, smem, 4);
     const int cps = env_int("MXB_TUNE_SEL_CTAS", 0) > 0 ? std::min(env_int("MXB_TUNE_SEL_CTAS", 0), res) : res;
-    const unsigned grid = (unsigned)std::min<int64_t>(ntiles, (int64_t)h->sm_count * cps);
-    st = ensure_lb(h, (size_t)(ntiles + (ntiles + 31) / 32 + (ntiles + 1023) / 1024 + 2));
+    const unsigned grid = (unsigned)std::min<int64_t>((nwt + 7) / 8, (int64_t)h->sm_count * cps);
+    // status words: tile counts | group counts | running counts at supergroup starts | supergroup counts
+    st = ensure_lb(h, (size_t)(nwt + (nwt + 31) / 32 + 2 * ((nwt + 1023) / 1024) + 4));
     if (st != MXB_OK) return st;
     p.sel_status = (unsigned long long *)lb_region(h, 8);
     p.sel_epoch = h->lb_ctl;
@@ -2217,6 +2300,7 @@ int mxb_find(mxb_handle_t h, const mxb_expr_t *expr_in, int select_op, double th
 // ---------------------------------------------------------------------------------------------------
 int mxb_hist(mxb_handle_t h, const mxb_expr_t *expr_in, double lower, double upper, const mxb_out_t *out) {
   if (!h) return fail(MXB_ERR_INVALID, "null handle");
+  std::lock_guard<std::recursive_mutex> lock_(h->mu);
   int st = check_expr_shape(expr_in);
   if (st != MXB_OK) return st;
   if (expr_in->rank < 1) return fail(MXB_ERR_INVALID, "hist needs rank >= 1");
@@ -2436,6 +2520,7 @@ extern "C" {
 
 int mxb_sort(mxb_handle_t h, const mxb_expr_t *expr_in, const mxb_out_t *out, int descending) {
   if (!h) return fail(MXB_ERR_INVALID, "null handle");
+  std::lock_guard<std::recursive_mutex> lock_(h->mu);
   int st = check_expr_shape(expr_in);
   if (st != MXB_OK) return st;
   if (expr_in->rank < 1) return fail(MXB_ERR_INVALID, "sort needs rank >= 1");
@@ -2474,6 +2559,7 @@ int mxb_sort(mxb_handle_t h, const mxb_expr_t *expr_in, const mxb_out_t *out, in
 // ---------------------------------------------------------------------------------------------------
 int mxb_unique(mxb_handle_t h, const mxb_expr_t *expr_in, const mxb_out_t *out, const mxb_out_t *count_out) {
   if (!h) return fail(MXB_ERR_INVALID, "null handle");
+  std::lock_guard<std::recursive_mutex> lock_(h->mu);
   int st = check_expr_shape(expr_in);
   if (st != MXB_OK) return st;
   if (expr_in->rank != 1) return fail(MXB_ERR_NOT_SUPPORTED, "unique serves rank-1 operands");

@@ -43,6 +43,7 @@ const char *dtype_ctype(int d) {
 const char *reduce_op_name(int op) {
   static const char *n[] = {"sum", "mean", "var", "stdd", "max", "min", "argmax", "argmin", "any", "all", "prod"};
   if (op == KOP_LSE) return "lse";
+  if (op == KOP_ARGMINMAX) return "argminmax";
   return (op >= 0 && op < MXB_RED_COUNT) ? n[op] : "?";
 }
 uint64_t fnv64(const std::string &s) {
@@ -461,7 +462,6 @@ int policy_unroll(const ExprInfo &info, int V, int family) {
   const int bytes = V * info.max_leaf_bytes;  // widest load of one step
   if (family == FAM_RED_OUTER) return 4;
   if (family == FAM_RED_OUTER_TMA) return 1;
-  if (family == FAM_VAR_TMA2) return 1;
   if (family == FAM_VAR_REG || family == FAM_VAR_TMA || family == FAM_VAR_GROUP || family == FAM_SM_GROUP || family == FAM_SM_REG) return 1;
   if (family == FAM_EW_TR) return 1;
   if (family == FAM_SELECT) return 4;
@@ -502,6 +502,9 @@ int kernel_wrapper_src(const ExprInfo &info, const KernelSpec &s, const std::str
       case MXB_RED_ARGMAX: case MXB_RED_ARGMIN:
         if (cplx) return fail("argmax/argmin of a complex expression (the reference rejects it too)");
         op = "mxb::OpArg<" + T + (s.op == MXB_RED_ARGMAX ? ", true>" : ", false>"); break;
+      case KOP_ARGMINMAX:
+        if (cplx) return fail("argminmax of a complex expression (the reference rejects it too)");
+        op = "mxb::OpArgMinMax<" + T + ">"; break;
       case MXB_RED_ANY: op = "mxb::OpLogic<" + T + ", true>"; break;
       case MXB_RED_ALL: op = "mxb::OpLogic<" + T + ", false>"; break;
       case MXB_RED_VAR:   // one-pass (mean, M2, n) states through the generic walkers
@@ -560,12 +563,6 @@ int kernel_wrapper_src(const ExprInfo &info, const KernelSpec &s, const std::str
       if (!(info.value_dtype == MXB_F32 || info.value_dtype == MXB_F64 || cplx)) return fail("var of a non-floating expression");
       k << "extern \"C\" __global__ void __launch_bounds__(1024) " << symbol
         << "(const __grid_constant__ mxb::RedParams p) { mxb::var_inner_tma_body<" << dtype_ctype(info.leaf_dtype[0]) << ", " << O << ", " << s.team << ">(p); }\n";
-      break;
-    case FAM_VAR_TMA2:   // opt-in (MXB_VAR_TMA2=1): producer warp + two consumer teams, team = vectors per thread
-      if (info.nleaf != 1) return fail("var_tma2 serves plain tensors only");
-      if (!(info.value_dtype == MXB_F32 || info.value_dtype == MXB_F64 || cplx)) return fail("var of a non-floating expression");
-      k << "extern \"C\" __global__ void __launch_bounds__(544) " << symbol
-        << "(const __grid_constant__ mxb::RedParams p) { mxb::var_inner_tma2_body<" << dtype_ctype(info.leaf_dtype[0]) << ", " << O << ", " << s.team << ">(p); }\n";
       break;
     case FAM_EW:
       // team = minimum resident CTAs per SM asked of the compiler (0 = no cap): arithmetic-heavy programs trade a few

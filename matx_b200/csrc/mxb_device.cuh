@@ -99,6 +99,7 @@ struct RedParams {
   int splits;      // CTAs cooperating on one row (inner_cta) or on one output tile (outer)
   LeafDev leaf[KMAXLEAF];
   OutDev out, idx;
+  void *out2, *idx2;  // argminmax: the max value / max index outputs (same batch strides as out / idx)
   void *ws;        // splits > 1: B*splits partial records
   u32 *tickets;    // splits > 1: one self-resetting counter per row / tile
   i64 idx_base;    // added to every reported flat index (slab offset in multi-GPU partials)
@@ -726,6 +727,83 @@ template <bool IS_MAX> __device__ __forceinline__ ArgAcc<float> warp_arg_f32(Arg
 template <> __device__ __forceinline__ ArgAcc<float> OpArg<float, true>::warp(ArgAcc<float> a) { return warp_arg_f32<true>(a); }
 template <> __device__ __forceinline__ ArgAcc<float> OpArg<float, false>::warp(ArgAcc<float> a) { return warp_arg_f32<false>(a); }
 
+// argminmax: min and max with their indices in ONE read (reference: argminmax_impl -> cub_dualargreduce,
+// transforms/reduce.h:1090-1109, cub.h:1439-1491; it carries 32-byte tuples through CUB and first materialises operator
+// inputs).  State = the two arg states side by side; lowest index wins ties on both sides.
+template <class T> struct __align__(16) ArgMMAcc { T vmin, vmax; i64 imin, imax; };
+template <class T> struct OpArgMinMax {
+  typedef ArgMMAcc<T> acc_t; typedef T result_t; enum { HAS_INDEX = 1, DUAL = 1 };
+  typedef OpArg<T, false> Mn; typedef OpArg<T, true> Mx;
+  static __device__ __forceinline__ acc_t init() {
+    acc_t a; a.vmin = Limits<T>::highest(); a.vmax = Limits<T>::lowest(); a.imin = a.imax = 0x7fffffffffffffffLL; return a;
+  }
+  static __device__ __forceinline__ void step(acc_t &a, T x, i64 i) {
+    if (x < a.vmin || (a.imin == 0x7fffffffffffffffLL && x == a.vmin)) { a.vmin = x; a.imin = i; }
+    if (x > a.vmax || (a.imax == 0x7fffffffffffffffLL && x == a.vmax)) { a.vmax = x; a.imax = i; }
+  }
+  static __device__ __forceinline__ void merge(acc_t &a, acc_t b) {
+    if (b.vmin < a.vmin || (b.vmin == a.vmin && b.imin < a.imin)) { a.vmin = b.vmin; a.imin = b.imin; }
+    if (b.vmax > a.vmax || (b.vmax == a.vmax && b.imax < a.imax)) { a.vmax = b.vmax; a.imax = b.imax; }
+  }
+  static __device__ __forceinline__ acc_t warp(acc_t a) {
+    ArgAcc<T> lo, hi;
+    lo.val = a.vmin; lo.idx = a.imin; hi.val = a.vmax; hi.idx = a.imax;
+    lo = Mn::warp(lo);
+    hi = Mx::warp(hi);
+    acc_t r; r.vmin = lo.val; r.imin = lo.idx; r.vmax = hi.val; r.imax = hi.idx;
+    return r;
+  }
+  static __device__ __forceinline__ result_t finish(acc_t a) { return a.vmin; }
+  static __device__ __forceinline__ i64 index(acc_t a) { return a.imin; }
+};
+
+// Block steps of the arg ops.  A thread's V x U elements of a tile arrive in increasing index order, and a running
+// extremum is replaced less and less often as the walk goes on (the k-th element of random data improves it with
+// probability 1 / k), so the common case is decided by ONE min / max per element: the block's extremum (NaNs ignored, as the
+// per-element compare ignores them) is tested against the state, and only a block that can change the state takes the exact
+// per-element steps.  Same result as stepping every element; ~1 instruction per element instead of ~10.
+template <class T> __device__ __forceinline__ T nn_max(T a, T b) { return a > b ? a : b; }
+template <class T> __device__ __forceinline__ T nn_min(T a, T b) { return a < b ? a : b; }
+template <> __device__ __forceinline__ float nn_max<float>(float a, float b) { return fmaxf(a, b); }
+template <> __device__ __forceinline__ float nn_min<float>(float a, float b) { return fminf(a, b); }
+template <> __device__ __forceinline__ double nn_max<double>(double a, double b) { return fmax(a, b); }
+template <> __device__ __forceinline__ double nn_min<double>(double a, double b) { return fmin(a, b); }
+template <class Op> struct OpBlock { enum { ON = 0 }; };
+template <class T, bool IS_MAX> struct OpBlock<OpArg<T, IS_MAX> > {
+  enum { ON = 1 };
+  typedef OpArg<T, IS_MAX> Op;
+  template <int N> static __device__ __forceinline__ void step(typename Op::acc_t &a, const T *x, i64 i0) {
+    T m = x[0];
+#pragma unroll
+    for (int k = 1; k < N; ++k) m = IS_MAX ? nn_max<T>(m, x[k]) : nn_min<T>(m, x[k]);
+    if (Op::better(m, a.val) || a.idx == 0x7fffffffffffffffLL) {
+#pragma unroll
+      for (int k = 0; k < N; ++k) Op::step(a, x[k], i0 + k);
+    }
+  }
+};
+template <class T> struct OpBlock<OpArgMinMax<T> > {
+  enum { ON = 1 };
+  typedef OpArgMinMax<T> Op;
+  template <int N> static __device__ __forceinline__ void step(typename Op::acc_t &a, const T *x, i64 i0) {
+    T lo = x[0], hi = x[0];
+#pragma unroll
+    for (int k = 1; k < N; ++k) { lo = nn_min<T>(lo, x[k]); hi = nn_max<T>(hi, x[k]); }
+    if (lo < a.vmin || hi > a.vmax || a.imin == 0x7fffffffffffffffLL || a.imax == 0x7fffffffffffffffLL) {
+#pragma unroll
+      for (int k = 0; k < N; ++k) Op::step(a, x[k], i0 + k);
+    }
+  }
+};
+
+template <class Op, int N, class T, bool ON = (OpBlock<Op>::ON != 0)> struct BlockStepCall {
+  static __device__ __forceinline__ void go(typename Op::acc_t &, const T *, i64) {}
+};
+template <class Op, int N, class T> struct BlockStepCall<Op, N, T, true> {
+  static __device__ __forceinline__ void go(typename Op::acc_t &a, const T *x, i64 i0) { OpBlock<Op>::template step<N>(a, x, i0); }
+};
+template <class Op, int N, class T> __device__ __forceinline__ void block_step(typename Op::acc_t &a, const T *x, i64 i0) { BlockStepCall<Op, N, T>::go(a, x, i0); }
+
 // any / all (reference: reduceOpAny / reduceOpAll, transforms/reduce.h:153-177; result is 0 / 1 in the
 // output tensor's type).  The warp stage is a vote.
 template <class T, bool IS_ANY> struct OpLogic {
@@ -844,6 +922,23 @@ template <class T> struct OpVar {
   static __device__ __forceinline__ i64 index(acc_t) { return 0; }
 };
 
+// the second (value, index) pair of a dual op (none by default)
+template <class Op, class OutT> struct DualStore {
+  static __device__ __forceinline__ void go(const RedParams &, i64, i64, const i64 *, typename Op::acc_t) {}
+};
+template <class T, class OutT> struct DualStore<OpArgMinMax<T>, OutT> {
+  static __device__ __forceinline__ void go(const RedParams &p, i64 oo, i64 io, const i64 *bidx, ArgMMAcc<T> a) {
+    ((OutT *)p.out2)[oo] = cvt<OutT>(a.vmax);
+    i64 ix = a.imax;
+    if (ix == 0x7fffffffffffffffLL) {   // nothing compared greater than the identity: first element, as std::max_element
+      i64 fb = 0;
+#pragma unroll
+      for (int d = 0; d < KMAXD; ++d) if (d < p.nb) fb += bidx[d] * p.bflat[d];
+      ix = p.idx_base + fb * p.R;
+    }
+    ((i64 *)p.idx2)[io] = ix;
+  }
+};
 // second output of an op (none by default)
 template <class Op> struct AuxStore {
   static __device__ __forceinline__ void go(void *, i64, typename Op::acc_t) {}
@@ -978,6 +1073,7 @@ __device__ __forceinline__ void store_result(const RedParams &p, i64 b, typename
     }
     ((i64 *)p.idx.ptr)[io] = ix;
   }
+  DualStore<Op, OutT>::go(p, oo, io, bidx, acc);
   AuxStore<Op>::go(p.idx.ptr, io, acc);
 }
 
@@ -1036,6 +1132,37 @@ __device__ __forceinline__ void outer_bases(const RedParams &p, i64 o, const cha
   }
 }
 
+// The last CTA out of a dynamically dealt reduce_inner launch folds the partials in item order (deterministic).
+template <class Op, class OutT>
+__device__ __forceinline__ void dyn_fold(const RedParams &p, i64 nfold, typename Op::acc_t *s_acc) {
+  typedef typename Op::acc_t acc_t;
+  __threadfence();
+  const acc_t *ws = (const acc_t *)p.ws;
+  if (p.B == 1) {
+    // four independent loads per trip: the fold is one CTA against L2 latency
+    acc_t a = Op::init();
+    const i64 nt = blockDim.x;
+    i64 i = threadIdx.x;
+    for (; i + 3 * nt < nfold; i += 4 * nt) {
+      const acc_t x0 = ld_cg_t(&ws[i]), x1 = ld_cg_t(&ws[i + nt]), x2 = ld_cg_t(&ws[i + 2 * nt]), x3 = ld_cg_t(&ws[i + 3 * nt]);
+      Op::merge(a, x0); Op::merge(a, x1); Op::merge(a, x2); Op::merge(a, x3);
+    }
+    for (; i < nfold; i += nt) Op::merge(a, ld_cg_t(&ws[i]));
+    a = cta_merge<Op>(a, s_acc);
+    if (threadIdx.x == 0) store_result<Op, OutT>(p, 0, a);
+  } else {
+    // a warp per row: lane-strided partials, then the op's warp stage
+    const i64 S = p.splits;
+    const int lane = (int)threadIdx.x & 31, nwarp = (int)blockDim.x >> 5;
+    for (i64 b = threadIdx.x >> 5; b < p.B; b += nwarp) {
+      acc_t a = Op::init();
+      for (i64 i = lane; i < S; i += 32) Op::merge(a, ld_cg_t(&ws[b * S + i]));
+      a = Op::warp(a);
+      if (lane == 0) store_result<Op, OutT>(p, b, a);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // K1: reduce_inner — rows whose innermost reduce dim is the vector dim (unit stride or broadcast in
 // every leaf when V > 1; any stride when V == 1, which makes V == 1 the universal fallback).
@@ -1072,7 +1199,11 @@ __device__ __forceinline__ void reduce_inner_body_impl(const RedParams &p) {
   const i64 work = p.B * S;
 
   __shared__ i64 s_next[2];
-  const bool dyn = TEAM == 0 && p.work_ctr != nullptr;
+  // the dynamic deal is compiled in for one- and two-word accumulators only (sum / prod / max / min / any / all): with the
+  // wide states (arg ops, variance, log-sum-exp) its bookkeeping cost a CTA per SM in registers (64 -> 80), which the deal
+  // does not win back; the host never passes a work counter for those
+  constexpr bool DYN_OK = TEAM == 0 && sizeof(acc_t) <= 8;
+  const bool dyn = DYN_OK && p.work_ctr != nullptr;
   const bool carry = dyn && p.carry_items != 0;
   bool first_item = true;
   acc_t acc[V];
@@ -1141,8 +1272,15 @@ __device__ __forceinline__ void reduce_inner_body_impl(const RedParams &p) {
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           const i64 j0 = (q + (i64)u * nthr) * V;
+          if (OpBlock<Op>::ON) {   // arg ops: one accumulator, the vector's V elements as a block
+            typename E::value_type xs[V];
 #pragma unroll
-          for (int v = 0; v < V; ++v) Op::step(acc[v], E::template eval<V>(r[u], v, p.c), row0 + j0 + v);
+            for (int v = 0; v < V; ++v) xs[v] = E::template eval<V>(r[u], v, p.c);
+            block_step<Op, V>(acc[0], xs, row0 + j0);
+          } else {
+#pragma unroll
+            for (int v = 0; v < V; ++v) Op::step(acc[v], E::template eval<V>(r[u], v, p.c), row0 + j0 + v);
+          }
         }
       }
       if (s == (cht > 0 ? S - 1 : nfull % S)) {  // the ragged last tile goes to the next split in turn (contiguous runs: to the last split)
@@ -1266,32 +1404,7 @@ __device__ __forceinline__ void reduce_inner_body_impl(const RedParams &p) {
       s_last = last ? 1 : 0;
     }
     __syncthreads();
-    if (s_last && (S > 1 || carry)) {
-      __threadfence();
-      const acc_t *ws = (const acc_t *)p.ws;
-      if (p.B == 1) {
-        // four independent loads per trip: the fold is one CTA against L2 latency
-        acc_t a = Op::init();
-        const i64 nt = blockDim.x;
-        i64 i = threadIdx.x;
-        for (; i + 3 * nt < nfold; i += 4 * nt) {
-          const acc_t x0 = ld_cg_t(&ws[i]), x1 = ld_cg_t(&ws[i + nt]), x2 = ld_cg_t(&ws[i + 2 * nt]), x3 = ld_cg_t(&ws[i + 3 * nt]);
-          Op::merge(a, x0); Op::merge(a, x1); Op::merge(a, x2); Op::merge(a, x3);
-        }
-        for (; i < nfold; i += nt) Op::merge(a, ld_cg_t(&ws[i]));
-        a = cta_merge<Op>(a, s_acc);
-        if (threadIdx.x == 0) store_result<Op, OutT>(p, 0, a);
-      } else {
-        // a warp per row: lane-strided partials, then the op's warp stage
-        const int lane = (int)threadIdx.x & 31, nwarp = (int)blockDim.x >> 5;
-        for (i64 b = threadIdx.x >> 5; b < p.B; b += nwarp) {
-          acc_t a = Op::init();
-          for (i64 i = lane; i < S; i += 32) Op::merge(a, ld_cg_t(&ws[b * S + i]));
-          a = Op::warp(a);
-          if (lane == 0) store_result<Op, OutT>(p, b, a);
-        }
-      }
-    }
+    if (s_last && (S > 1 || carry)) dyn_fold<Op, OutT>(p, nfold, s_acc);
   }
 }
 
@@ -2040,130 +2153,6 @@ __device__ __forceinline__ void var_inner_tma_body(const RedParams &p) {
       for (int d = 0; d < KMAXD; ++d) if (d < p.nb) oo += bidx[d] * p.out.bs[d];
       ((OutT *)p.out.ptr)[oo] = cvt<OutT>(res);
     }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// K3t2: var_inner_tma2 (opt-in, MXB_VAR_TMA2=1) — var_inner_tma with the warp specialisation that made reduce_outer_tma
-// work: the LAST warp only feeds the ring (waits on a stage's `empty` mbarrier, arms `full`, one cp.async.bulk per row);
-// the other 16 warps are TWO teams of 256 threads that take alternate rows, each with its own named barrier and its own
-// double-buffered partials — while one team sits in a barrier of its row the other computes, and nobody waits for a
-// thread-0 re-arm.  A team copies its row share shared -> registers (IPT 16-byte vectors per thread), releases the
-// stage (one `empty` arrival per warp) and runs the reference's two passes from registers.  Same arithmetic, same
-// results as var_inner_tma.  Rows of at most 256 * IPT vectors (64 KB at IPT = 16).
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void mbar_arrive_cta(u64 *bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-template <class Tin, class OutT, int IPT>
-__device__ __forceinline__ void var_inner_tma2_body(const RedParams &p) {
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-  typedef typename Widen<Tin>::type T;
-  typedef typename AbsDev2<T>::real_t RT;
-  enum { V = 16 / (int)sizeof(Tin), TEAM = 256, NWT = TEAM / 32 };
-  extern __shared__ __align__(128) unsigned char s_dyn[];
-  __shared__ T s_sum[2][2][NWT];     // [team][row parity within the team][warp]
-  __shared__ RT s_sq[2][2][NWT];
-  u64 *full = (u64 *)s_dyn;          // first 128 bytes: full[0..7], empty[0..7]
-  u64 *empty = full + 8;
-  unsigned char *buf = s_dyn + 128;
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int stages = p.splits;
-  const i64 R = p.R;
-  const u32 rowbytes = (u32)(R * (i64)sizeof(Tin));
-  const u32 rowstride = (rowbytes + 127u) & ~127u;
-  const i64 Rv = R / V;
-  const i64 nrows = p.B > (i64)blockIdx.x ? (p.B - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;   // rows of this CTA
-
-  auto row_off = [&](i64 b, const i64 *strides) -> i64 {
-    i64 bidx[KMAXD];
-    decomp(b, p.nb, p.bsz, bidx);
-    i64 off = 0;
-#pragma unroll
-    for (int d = 0; d < KMAXD; ++d) if (d < p.nb) off += bidx[d] * strides[d];
-    return off;
-  };
-
-  if (tid == 0) {
-    for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NWT); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-
-  if (tid >= 2 * TEAM) {
-    // ---------------- producer warp ----------------
-    if (lane == 0) {
-      int s = 0;
-      u32 round = 0;
-      for (i64 k = 0; k < nrows; ++k) {
-        if (round > 0) mbar_wait(&empty[s], (round - 1u) & 1u);
-        const i64 b = (i64)blockIdx.x + k * gridDim.x;
-        mbar_expect_tx(&full[s], rowbytes);
-        bulk_g2s(buf + (size_t)s * rowstride, (const char *)p.leaf[0].ptr + row_off(b, p.leaf[0].bs) * (i64)sizeof(Tin), rowbytes, &full[s]);
-        if (++s == stages) { s = 0; ++round; }
-      }
-    }
-    return;
-  }
-
-  // ---------------- two consumer teams, alternate rows ----------------
-  const int team = tid / TEAM, tt = tid % TEAM, wt = tt >> 5;
-  const int bar_id = 1 + team;
-  int par = 0;
-  for (i64 k = team; k < nrows; k += 2) {
-    const int s = (int)(k % stages);
-    mbar_wait(&full[s], (u32)((k / stages) & 1));
-    const Vec<Tin, V> *x = (const Vec<Tin, V> *)(buf + (size_t)s * rowstride);
-    Vec<Tin, V> q[IPT];
-#pragma unroll
-    for (int i = 0; i < IPT; ++i) {
-      const i64 j = tt + (i64)i * TEAM;
-      if (j < Rv) {
-        union { uint4 u; Vec<Tin, V> v; } ld;
-        ld.u = *(const uint4 *)(x + j);
-        q[i] = ld.v;
-      }
-    }
-    __syncwarp();
-    if (lane == 0) mbar_arrive_cta(&empty[s]);   // this warp holds its share in registers: the stage may be refilled
-    // pass 1: mean
-    T acc = OpSum<T>::init();
-#pragma unroll
-    for (int i = 0; i < IPT; ++i) {
-      if (tt + (i64)i * TEAM < Rv) {
-#pragma unroll
-        for (int v = 0; v < V; ++v) acc = acc + cvt<T>(q[i].v[v]);
-      }
-    }
-    acc = OpSum<T>::warp(acc);
-    if (lane == 0) s_sum[team][par][wt] = acc;
-    asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"((int)TEAM) : "memory");
-    T tot = OpSum<T>::init();
-#pragma unroll
-    for (int w = 0; w < NWT; ++w) tot = tot + s_sum[team][par][w];   // same order in every thread
-    const T mean = MeanDiv<T>::go(tot, R);
-    // pass 2: sum of |x - mean|^2 out of registers
-    RT sq = (RT)0;
-#pragma unroll
-    for (int i = 0; i < IPT; ++i) {
-      if (tt + (i64)i * TEAM < Rv) {
-#pragma unroll
-        for (int v = 0; v < V; ++v) sq += AbsDev2<T>::go(cvt<T>(q[i].v[v]), mean);
-      }
-    }
-    sq = OpSum<RT>::warp(sq);
-    if (lane == 0) s_sq[team][par][wt] = sq;
-    asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"((int)TEAM) : "memory");
-    if (tt == 0) {
-      RT tsq = (RT)0;
-#pragma unroll
-      for (int w = 0; w < NWT; ++w) tsq += s_sq[team][par][w];
-      RT res = tsq / (RT)p.post_scale_d;
-      if (p.post_sqrt) res = f_sqrt(res);
-      const i64 b = (i64)blockIdx.x + k * gridDim.x;
-      ((OutT *)p.out.ptr)[row_off(b, p.out.bs)] = cvt<OutT>(res);
-    }
-    par ^= 1;
   }
 }
 
@@ -3788,18 +3777,20 @@ __device__ __forceinline__ void select_body(const EwParams &p) {
 // ------------------------------------------------------------------------------------------------
 // S1p: select1p — find / find_idx in ONE pass: every element is read once, the selected ones are written once.
 // (reference: cub::DeviceSelect::If behind find_impl / find_idx_impl, transforms/cub.h:912-1010,2609-2790.)
-// A tile is 256 threads x 4 chunks x V elements of the flat index space; tiles are dealt round-robin to a grid whose
-// CTAs are all resident (cooperative launch), so a tile only ever waits for tiles that are running or done.
-//   1. the tile's values sit in registers (loads issued one tile ahead); branch-free predicate -> flag bits;
-//   2. ranks inside the tile: the four chunk counts of a thread travel packed in one word (a byte each, a warp's
-//      inclusive sum is <= 128) through ONE shuffle scan; warp totals meet in shared memory (one barrier);
-//   3. the tile publishes its count and warp 0 gathers the tile's output offset from the published counts of the tiles /
-//      groups / supergroup before it (hier_carry, the same three-level exchange as the TILES-mode scan): one L2 round
-//      trip when the neighbours are done.  The output is deterministic and stable;
-//   4. meanwhile the other warps compact the selected values (or flat indices) into shared memory by rank; after the
-//      second barrier the CTA copies the compacted run to out[excl ...] with full-sector stores.
-// Shared-memory staging and the per-warp totals are double-buffered by tile parity: two barriers per tile.
-// Status words carry the launch epoch, so nothing is cleared between launches.
+// The unit of work is a WARP tile: 32 lanes x EPL elements (EPL = 32, 16 for 8-byte values) of the flat index space,
+// as 16- or 32-byte vector loads (lane-adjacent vectors: coalesced).  Warp tiles are dealt round-robin to the warps of a
+// grid whose CTAs are all resident (cooperative launch), so a tile only ever waits for tiles that are running or done.
+// There is no shared memory and no barrier: a warp never waits for another warp of its CTA, only for the published
+// counts of earlier tiles, and the other warps of the SM (32 resident) cover that wait.
+//   1. branch-free predicate -> one flag bit per element in ONE register per lane;
+//   2. ranks inside the tile: the per-vector counts of a lane travel packed (a byte each; 16 bits for vectors of more
+//      than 7 elements) through shuffle scans, the per-vector warp totals come from lane 31;
+//   3. the tile publishes its count and gathers its output offset from the published counts before it (sel_carry: tile
+//      counts of its group of 32, group counts of its supergroup of 32 groups, running count at the supergroup start —
+//      no chain: a supergroup's closer sums the supergroups' OWN totals, so the depth of the dependency is constant);
+//   4. the selected values (or flat indices) go straight to out[offset + rank]: ranks grow with the lane, so a store
+//      instruction covers a run of at most 32 x V consecutive outputs.
+// The output is deterministic and stable.  Status words carry the launch epoch: nothing is cleared between launches.
 // ------------------------------------------------------------------------------------------------
 // predicate of one selection op as a type: the tile loop is instantiated per op (one compare + one predicated OR per
 // element) instead of classifying every element against a runtime mask
@@ -3808,113 +3799,104 @@ template <int OP> struct SelPred {
     return OP == 0 ? (x < c) : OP == 1 ? (x > c) : OP == 2 ? (x == c) : OP == 3 ? (x != c) : OP == 4 ? (x <= c) : (x >= c);
   }
 };
-template <int OP, class T, int V> __device__ __forceinline__ u32 sel_flags_vec(const T *vals, T thr) {
-  u32 f = 0;
-#pragma unroll
-  for (int v = 0; v < V; ++v) f |= (SelPred<OP>::test(vals[v], thr) ? 1u : 0u) << v;
-  return f;
-}
-template <class T, int V> __device__ __forceinline__ u32 sel_flags_op(int op, const T *vals, T thr) {
-  switch (op) {
-    case 0: return sel_flags_vec<0, T, V>(vals, thr);
-    case 1: return sel_flags_vec<1, T, V>(vals, thr);
-    case 2: return sel_flags_vec<2, T, V>(vals, thr);
-    case 3: return sel_flags_vec<3, T, V>(vals, thr);
-    case 4: return sel_flags_vec<4, T, V>(vals, thr);
-    default: return sel_flags_vec<5, T, V>(vals, thr);
+
+// offset of warp tile `ct` from the published counts (all 32 lanes call it, every lane returns the offset); the caller has
+// published the tile's own count in agg[ct].  own[sg] = count of supergroup sg alone, run[sg] = count of everything before
+// supergroup sg (published by the closer of supergroup sg - 1 from own[0 .. sg - 1]).
+__device__ __forceinline__ u32 sel_carry(void *agg, void *gagg, void *run, void *own, i64 ct, i64 ntiles, u32 total, u32 tag, int lane) {
+  typedef ScanSlot<u32> SL;
+  const i64 g = ct >> 5, first = g << 5, sg = ct >> 10, gfirst = sg << 5;
+  const int n2 = (int)(ct - first), n1 = (int)(g - gfirst);
+  // every read goes out before the first wait
+  SL::Word wa, wb, wc;
+  if (lane < n2) wa = SL::peek(agg, first + lane);
+  if (lane < n1) wb = SL::peek(gagg, gfirst + lane);
+  if (lane == 0 && sg > 0) wc = SL::peek(run, sg);
+  u32 a = 0, b = 0, c = 0;
+  if (lane < n2) { while (!SL::ready(wa, tag)) { __nanosleep(20); wa = SL::peek(agg, first + lane); } a = SL::value(wa); }
+  const u32 sa = warp_tree_sum(a);
+  const bool last_tile = ct == ntiles - 1;
+  const bool closes_group = (ct & 31) == 31 || last_tile;
+  const u32 gt = sa + total;
+  if (closes_group && lane == 0) SL::publish(gagg, g, gt, tag);   // before waiting for anything of an earlier group
+  if (lane < n1) { while (!SL::ready(wb, tag)) { __nanosleep(20); wb = SL::peek(gagg, gfirst + lane); } b = SL::value(wb); }
+  const u32 sb = warp_tree_sum(b);
+  if (closes_group && (g & 31) == 31 && !last_tile) {
+    // this tile ends supergroup sg: its own count goes out, then the running count at the start of the next one
+    const u32 mine = sb + gt;
+    if (lane == 0) SL::publish(own, sg, mine, tag);
+    u32 acc = 0;
+    for (i64 i = lane; i < sg; i += 32) acc += SL::wait(own, i, tag);
+    acc = warp_tree_sum(acc);
+    if (lane == 0) SL::publish(run, sg + 1, acc + mine, tag);
   }
+  if (lane == 0 && sg > 0) { while (!SL::ready(wc, tag)) { __nanosleep(20); wc = SL::peek(run, sg); } c = SL::value(wc); }
+  c = __shfl_sync(0xffffffffu, c, 0);
+  return (c + sb) + sa;
 }
 
-template <class E, class OutT, int V, int MODE>   // MODE 1: values, 2: flat indices
-__device__ __forceinline__ void select1p_body(const EwParams &p) {
-  pdl_prologue();
+template <class E, class OutT, int V, int MODE, bool UNIT, int OP>   // MODE 1: values, 2: flat indices; OP < 0: runtime op / unique
+__device__ __forceinline__ void select1p_tiles(const EwParams &p) {
   typedef typename E::value_type T;
   typedef typename E::template Regs<V> R;
-  constexpr int NT = 256, U = 4, NW = NT / 32, DMAX = 8;
-  extern __shared__ __align__(16) unsigned char sel_smem[];
-  OutT *stage = (OutT *)sel_smem;                      // [D][NT * U * V]: compacted tiles waiting for their offset
-  __shared__ u32 s_w[2][NW];
-  __shared__ u32 s_tot[DMAX];
-  __shared__ u32 s_excl[2];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int D = p.sel_depth;                           // pipeline depth: phase 2 of a tile runs D - 1 iterations after its phase 1
-  const i64 TILE = (i64)NT * V * U;
+  constexpr int EPL = sizeof(T) > 4 ? 16 : 32;      // elements per lane and tile
+  constexpr int U = EPL / V;                        // vectors per lane and tile
+  constexpr i64 TILE = (i64)32 * EPL;
+  constexpr int CB = (32 * V <= 255) ? 8 : 16;      // bits of a packed counter (inclusive warp sums reach 32 * V)
+  constexpr int CPW = 32 / CB;                      // counters per word
+  constexpr int NWORD = (U + CPW - 1) / CPW;
+  constexpr u32 CMASK = CB == 8 ? 0xffu : 0xffffu;
+  constexpr u32 VMASK = V >= 32 ? 0xffffffffu : ((1u << V) - 1u);
+  static_assert(EPL % V == 0 && U >= 1, "vector width must divide the elements per lane");
+  const int lane = threadIdx.x & 31;
+  const i64 wpc = blockDim.x >> 5;
+  const i64 nwarp = (i64)gridDim.x * wpc, gw = (i64)blockIdx.x * wpc + (threadIdx.x >> 5);
   const i64 ntiles = (p.N + TILE - 1) / TILE;
-  const i64 G = gridDim.x;
-  const i64 mine = ntiles > (i64)blockIdx.x ? (ntiles - blockIdx.x + G - 1) / G : 0;   // tiles of this CTA
   const T thr = SelThr<T>::get(p);
   const bool unique_mode = p.sel_op == 6;             // MXB_SEL_UNIQUE (mxb_unique): adjacent-difference flags over a sorted operand
   const u32 fmask = sel_mask(unique_mode ? 0 : p.sel_op);
   const u32 epoch = __ldcg(p.sel_epoch) & 0x3fffffffu;
-  // slots: tile counts, group counts (32 tiles), running counts at supergroup starts (1024 tiles)
-  TileExchange<u32> xc;
-  xc.init(p.sel_status, p.sel_status + ntiles, p.sel_status + ntiles + ((ntiles + 31) >> 5), ntiles, (epoch << 2) | 1u, lane);
+  const u32 tag = (epoch << 2) | 1u;
+  // slots: tile counts | group counts (32 tiles) | running counts at supergroup starts (1024 tiles) | supergroup counts
+  const i64 ngroup = (ntiles + 31) >> 5, nsuper = (ntiles + 1023) >> 10;
+  unsigned long long *agg = p.sel_status, *gagg = agg + ntiles, *run = gagg + ngroup, *own = run + nsuper + 1;
   const char *base[E::NL];
   i64 inner[E::NL];
 #pragma unroll
   for (int k = 0; k < E::NL; ++k) { base[k] = (const char *)p.leaf[k].ptr; inner[k] = p.leaf[k].bs[0]; }
-  const bool unit = p.all_unit != 0;
+  OutT *out = (OutT *)p.out.ptr;
+  const u32 cap = p.sel_cap > 0xffffffffll ? 0xffffffffu : (u32)p.sel_cap;
 
-  R r[U];
-  auto issue_loads = [&](i64 tile) {     // vector loads of the full vectors of `tile`; ragged ends are fetched at evaluation time
-    const i64 jt = tile * TILE + (i64)tid * V;
-    if ((tile + 1) * TILE <= p.N && unit) {
+  for (i64 tile = gw; tile < ntiles; tile += nwarp) {
+    const i64 t0 = tile * TILE;
+    const i64 jl = t0 + (i64)lane * V;              // first element of this lane's vector 0; vector u sits 32 * V further
+    T vals[U][V];
+    u32 f = 0;                                      // bit u * V + v: element (u, v) of this lane is selected
+    if (OP >= 0 && t0 + TILE <= p.N) {
+      // a full tile (all but the last): no bounds, the predicate is a compile-time functor
+      R r[U];
 #pragma unroll
-      for (int u = 0; u < U; ++u) E::template loadv<V, true>(r[u], base, inner, jt + (i64)u * NT * V);
-      return;
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const i64 j0 = jt + (i64)u * NT * V;
-      if (j0 + V <= p.N) {
-        if (unit) E::template loadv<V, true>(r[u], base, inner, j0);
-        else E::template loadv<V, false>(r[u], base, inner, j0);
-      }
-    }
-  };
-  if (mine > 0) issue_loads(blockIdx.x);
-  for (i64 it = 0; it < mine + D - 1; ++it) {
-    const int par = (int)(it & 1);
-    const bool p1 = it < mine;                 // phase 1 of local tile `it`
-    const i64 it2 = it - (D - 1);              // phase 2 of local tile `it2`
-    const bool p2 = it2 >= 0;
-    const i64 tile = (i64)blockIdx.x + it * G, tile2 = (i64)blockIdx.x + it2 * G;
-    const int slot = (int)(it % D), slot2 = (int)(((it2 % D) + D) % D);
-    // ---- warp 0: the reads of this iteration's exchange jobs go out before the iteration's own work ----
-    if (warp == 0) {
-      const i64 tc = (it >= 1 && it - 1 < mine) ? tile - G : -1;        // close: the tile of the previous iteration
-      const i64 th = (it >= 2 && it - 2 < mine) ? tile - 2 * G : -1;    // chain: the one before
-      xc.issue(0, tc, 0, th, 0, p2 ? tile2 : -1);
-    }
-    u32 total = 0;
-    if (p1) {
-      const i64 t0 = tile * TILE;
-      T vals[U][V];
-      u32 flags[U];
-      u32 packed = 0;
-      if (t0 + TILE <= p.N && !unique_mode) {
-        // a full tile (all but the last): no bounds in the loop, the op is a compile-time functor inside sel_flags_op
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-#pragma unroll
-          for (int v = 0; v < V; ++v) vals[u][v] = E::template eval<V>(r[u], v, p.c);
-        }
-        const int op = p.sel_op;
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          flags[u] = sel_flags_op<T, V>(op, vals[u], thr);
-          packed |= (u32)__popc(flags[u]) << (8 * u);
-        }
-      } else {
+      for (int u = 0; u < U; ++u) E::template loadv<V, UNIT>(r[u], base, inner, jl + (i64)u * 32 * V);
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const i64 j0 = t0 + ((i64)u * NT + tid) * V;
-        u32 f = 0;
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          vals[u][v] = E::template eval<V>(r[u], v, p.c);
+          if (SelPred<OP < 0 ? 0 : OP>::test(vals[u][v], thr)) f |= 1u << (u * V + v);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const i64 j0 = jl + (i64)u * 32 * V;
+        u32 fu = 0;
         if (j0 + V <= p.N) {
+          R r;
+          E::template loadv<V, UNIT>(r, base, inner, j0);
 #pragma unroll
           for (int v = 0; v < V; ++v) {
-            vals[u][v] = E::template eval<V>(r[u], v, p.c);
-            f |= sel_flag<T>(vals[u][v], thr, fmask) << v;
+            vals[u][v] = E::template eval<V>(r, v, p.c);
+            fu |= sel_flag<T>(vals[u][v], thr, fmask) << v;
           }
         } else {
 #pragma unroll
@@ -3923,13 +3905,13 @@ __device__ __forceinline__ void select1p_body(const EwParams &p) {
               typename E::template Regs<1> r1;
               E::template loadv<1, false>(r1, base, inner, j0 + v);
               vals[u][v] = E::template eval<1>(r1, 0, p.c);
-              f |= sel_flag<T>(vals[u][v], thr, fmask) << v;
+              fu |= sel_flag<T>(vals[u][v], thr, fmask) << v;
             }
           }
         }
         if (unique_mode) {
           // unique over a SORTED operand (std::unique / cub::DeviceSelect::Unique): keep x[j] iff j == 0 or x[j] != x[j - 1]
-          f = 0;
+          fu = 0;
           if (j0 < p.N) {
             T prev = vals[u][0];
             if (j0 > 0) {
@@ -3941,88 +3923,95 @@ __device__ __forceinline__ void select1p_body(const EwParams &p) {
             for (int v = 0; v < V; ++v) {
               if (j0 + v < p.N) {
                 const bool keep = (j0 + v == 0) || !(vals[u][v] == prev);
-                f |= (keep ? 1u : 0u) << v;
+                fu |= (keep ? 1u : 0u) << v;
                 prev = vals[u][v];
               }
             }
           }
         }
-        flags[u] = f;
-        packed |= (u32)__popc(f) << (8 * u);
+        f |= fu << (u * V);
       }
-      }
-      // the next tile's loads fly while this one is ranked and staged
-      if (it + 1 < mine) issue_loads(tile + G);
-      // ranks inside the warp: one shuffle scan over the four packed byte counters
-      u32 incl = packed;
+    }
+    // ---- ranks: packed per-vector counts through shuffle scans ----
+    u32 own_w[NWORD], incl[NWORD];
 #pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const u32 o = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl += o;
-      }
-      const u32 wexcl = incl - packed;
-      if (lane == 31) s_w[par][warp] = incl;
-      __syncthreads();   // (A)
-      // warps before mine and the chunk totals, two 16-bit lanes per word (8 warps x 128 fit easily)
-      u32 blo = 0, bhi = 0, tlo = 0, thi = 0;
+    for (int w = 0; w < NWORD; ++w) own_w[w] = 0;
 #pragma unroll
-      for (int w = 0; w < NW; ++w) {
-        const u32 x = s_w[par][w];
-        const u32 lo = x & 0x00ff00ffu, hi = (x >> 8) & 0x00ff00ffu;
-        tlo += lo; thi += hi;
-        if (w < warp) { blo += lo; bhi += hi; }
+    for (int u = 0; u < U; ++u) own_w[u / CPW] |= (u32)__popc((f >> (u * V)) & VMASK) << (CB * (u % CPW));
+#pragma unroll
+    for (int w = 0; w < NWORD; ++w) incl[w] = own_w[w];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+#pragma unroll
+      for (int w = 0; w < NWORD; ++w) {
+        const u32 o = __shfl_up_sync(0xffffffffu, incl[w], d);
+        if (lane >= d) incl[w] += o;
       }
-      const u32 tot[4] = {tlo & 0xffffu, thi & 0xffffu, tlo >> 16, thi >> 16};
-      const u32 bef[4] = {blo & 0xffffu, bhi & 0xffffu, blo >> 16, bhi >> 16};
-      total = tot[0] + tot[1] + tot[2] + tot[3];
-      if (tid == 0) {   // first thing: every later tile waits for this store
-        xc.publish_tile(0, tile, total);
-        s_tot[slot] = total;
+    }
+    // per-vector totals of the warp (lane 31) -> where each vector row starts inside the tile, and the tile's count
+    u32 bef[U];
+    u32 total = 0;
+#pragma unroll
+    for (int w = 0; w < NWORD; ++w) {
+      const u32 t = __shfl_sync(0xffffffffu, incl[w], 31);
+#pragma unroll
+      for (int c = 0; c < CPW; ++c) {
+        if (w * CPW + c < U) { bef[w * CPW + c] = total; total += (t >> (CB * c)) & CMASK; }
       }
-      // compact the selected elements into this tile's staging slot by rank
-      OutT *stg = stage + (size_t)slot * TILE;
-      u32 coff = 0;
+    }
+    if (lane == 0) ScanSlot<u32>::publish(agg, tile, total, tag);   // first thing: every later tile waits for this store
+    const u32 off = sel_carry(agg, gagg, run, own, tile, ntiles, total, tag, lane);
+    if (tile == ntiles - 1 && lane == 0) {
+      const unsigned long long all = (unsigned long long)off + total;
+      *p.sel_total = all > 0x7fffffffull ? 0x7fffffff : (int)all;
+    }
+    // ---- the selected elements go straight to their final places ----
+    if (f) {
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        u32 pos = coff + bef[u] + ((wexcl >> (8 * u)) & 0xffu);
-        const i64 j0 = t0 + ((i64)u * NT + tid) * V;
+        const u32 fu = (f >> (u * V)) & VMASK;
+        if (fu) {
+          const u32 ex = ((incl[u / CPW] - own_w[u / CPW]) >> (CB * (u % CPW))) & CMASK;
+          u32 pos = off + bef[u] + ex;                 // counts stay below 2^32 (host check)
+          const i64 j0 = jl + (i64)u * 32 * V;
 #pragma unroll
-        for (int v = 0; v < V; ++v) {
-          if ((flags[u] >> v) & 1u) { stg[pos] = MODE == 1 ? cvt<OutT>(vals[u][v]) : (OutT)(j0 + v); ++pos; }
-        }
-        coff += tot[u];
-      }
-    } else {
-      __syncthreads();   // (A) keeps the barrier count uniform while the pipeline drains
-    }
-    if (warp == 0) {
-      // the closing tile's own total: written to s_tot one iteration ago (behind barrier B of that iteration)
-      const u32 ctot = xc.close_ct >= 0 ? s_tot[(int)((it - 1) % D)] : 0u;
-      const u32 excl = xc.finish(ctot);
-      if (lane == 0 && p2) {
-        s_excl[par] = excl;
-        if (tile2 == ntiles - 1) {
-          const unsigned long long all = (unsigned long long)excl + s_tot[slot2];
-          *p.sel_total = all > 0x7fffffffull ? 0x7fffffff : (int)all;
+          for (int v = 0; v < V; ++v) {
+            if ((fu >> v) & 1u) {
+              if (pos < cap) out[pos] = MODE == 1 ? cvt<OutT>(vals[u][v]) : (OutT)(j0 + v);   // beyond the capacity: counted, not written
+              ++pos;
+            }
+          }
         }
       }
     }
-    __syncthreads();   // (B) this iteration's staging is complete, the drained tile's offset is known
-    if (p2) {
-      const i64 excl = (i64)s_excl[par];
-      const u32 n = s_tot[slot2];
-      const OutT *stg = stage + (size_t)slot2 * TILE;
-      OutT *dst = (OutT *)p.out.ptr + excl;
-      const i64 room = p.sel_cap - excl;     // elements beyond the capacity are counted, not written
-      for (u32 i = tid; i < n; i += NT)
-        if ((i64)i < room) dst[i] = stg[i];
+  }
+}
+
+template <class E, class OutT, int V, int MODE>
+__device__ __forceinline__ void select1p_body(const EwParams &p) {
+  pdl_prologue();
+  const bool unit = p.all_unit != 0;
+  if (V > 1 || unit) {
+    // V > 1 is only ever launched over unit-stride leaves
+    switch (p.sel_op) {
+      case 0: select1p_tiles<E, OutT, V, MODE, true, 0>(p); break;
+      case 1: select1p_tiles<E, OutT, V, MODE, true, 1>(p); break;
+      case 2: select1p_tiles<E, OutT, V, MODE, true, 2>(p); break;
+      case 3: select1p_tiles<E, OutT, V, MODE, true, 3>(p); break;
+      case 4: select1p_tiles<E, OutT, V, MODE, true, 4>(p); break;
+      case 5: select1p_tiles<E, OutT, V, MODE, true, 5>(p); break;
+      default: select1p_tiles<E, OutT, V, MODE, true, -1>(p); break;
     }
+  } else {
+    select1p_tiles<E, OutT, V, MODE, false, -1>(p);
   }
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   // exit ticket: the last CTA out opens the next epoch (every status word of this launch is stale from then on)
-  if (tid == 0) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
     __threadfence();
     if (atomicInc(p.sel_ticket, gridDim.x - 1) == gridDim.x - 1) {
+      const u32 epoch = __ldcg(p.sel_epoch) & 0x3fffffffu;
       const u32 e = (epoch + 1u) & 0x3fffffffu;
       *(volatile u32 *)p.sel_epoch = e ? e : 1u;   // epoch 0 is what freshly zeroed status words carry: never used
     }

@@ -32,9 +32,11 @@ int analyze_expr(const mxb_expr_t *e, ExprInfo *info, std::string *err);
 
 // ---- kernel instances ----------------------------------------------------------------------------
 enum Family { FAM_RED_INNER = 0, FAM_RED_OUTER = 1, FAM_VAR_SMEM = 2, FAM_EW = 3, FAM_VAR_REG = 4, FAM_VAR_TMA = 5, FAM_VAR_GROUP = 6,
-              FAM_SM_GROUP = 7, FAM_SM_REG = 8, FAM_EW_TR = 9, FAM_SCAN = 10, FAM_RED_OUTER_TMA = 11, FAM_SELECT = 12, FAM_VAR_TMA2 = 13, FAM_HIST = 14 };
+              FAM_SM_GROUP = 7, FAM_SM_REG = 8, FAM_EW_TR = 9, FAM_SCAN = 10, FAM_RED_OUTER_TMA = 11, FAM_SELECT = 12, FAM_UNUSED_13 = 13, FAM_HIST = 14 };
 // internal kernel op: running (max, sum exp) of a row — the statistics pass of a long-row softmax
 constexpr int KOP_LSE = MXB_RED_COUNT;
+// internal kernel op: min and max with their indices in one read (mxb_argminmax)
+constexpr int KOP_ARGMINMAX = MXB_RED_COUNT + 1;
 
 struct KernelSpec {
   int family = 0;

@@ -310,6 +310,9 @@ def as_type(a, dtype: int): return UnOp(A.OP_CAST, a, dtype)
 # --------------------------------------------------------------------------------------------------------
 # reductions (lazy "transform ops", reference: operators/sum.h etc.)
 # --------------------------------------------------------------------------------------------------------
+RED_ARGMINMAX = -2   # host-side tag only: lowered to mxb_argminmax, not an mxb_reduce op id
+
+
 class ReduceExpr:
     def __init__(self, op: int, a, dims: Optional[Sequence[int]], ddof: int = 1):
         a = _wrap(a, None)
@@ -334,6 +337,11 @@ def max(a, dims=None): return ReduceExpr(A.RED_MAX, a, dims)        # noqa: A001
 def min(a, dims=None): return ReduceExpr(A.RED_MIN, a, dims)        # noqa: A001
 def argmax(a, dims=None): return ReduceExpr(A.RED_ARGMAX, a, dims)
 def argmin(a, dims=None): return ReduceExpr(A.RED_ARGMIN, a, dims)
+def argminmax(a, dims=None):
+    """`(mtie(minv, mini, maxv, maxi) = argminmax(x, dims))` (operators/argminmax.h): both extrema, one read of x."""
+    return ReduceExpr(RED_ARGMINMAX, a, dims)
+
+
 def any(a, dims=None): return ReduceExpr(A.RED_ANY, a, dims)        # noqa: A001
 def all(a, dims=None): return ReduceExpr(A.RED_ALL, a, dims)        # noqa: A001
 def prod(a, dims=None): return ReduceExpr(A.RED_PROD, a, dims)
@@ -587,10 +595,10 @@ class Set:
             return
         self.rhs = rhs if isinstance(rhs, (ReduceExpr, CumsumExpr)) else _wrap(rhs, lhs if isinstance(lhs, Op) else None)
         if isinstance(lhs, mtie):
-            if not isinstance(self.rhs, ReduceExpr) or self.rhs.op not in (A.RED_ARGMAX, A.RED_ARGMIN):
-                raise TypeError("mtie(...) takes argmax / argmin on the right-hand side")
-            if len(lhs.outs) != 2:
-                raise TypeError("mtie(values, indices) needs two outputs")
+            if not isinstance(self.rhs, ReduceExpr) or self.rhs.op not in (A.RED_ARGMAX, A.RED_ARGMIN, RED_ARGMINMAX):
+                raise TypeError("mtie(...) takes argmax / argmin / argminmax on the right-hand side")
+            if len(lhs.outs) != (4 if self.rhs.op == RED_ARGMINMAX else 2):
+                raise TypeError("mtie(values, indices) needs two outputs (argminmax: min value, min index, max value, max index)")
         shape = self.rhs.out_shape if isinstance(self.rhs, (ReduceExpr, CumsumExpr)) else self.rhs.shape
         outs = lhs.outs if isinstance(lhs, mtie) else (lhs,)
         for o in outs:
@@ -600,6 +608,7 @@ class Set:
                 raise A.MatxB200Error(A.ERR_SIZE, "lhs shape %s does not match rhs shape %s" % (o.shape, shape))  # matxInvalidSize
 
     def run(self, ex: "CudaExecutor") -> None:
+        A.sync_env()
         if isinstance(self.rhs, UniqueExpr):
             e = lower_elementwise(self.rhs.a)
             out, cnt = _out_desc(self.lhs.outs[0]), _out_desc(self.lhs.outs[1])
@@ -633,7 +642,12 @@ class Set:
         elif isinstance(self.rhs, ReduceExpr):
             r = self.rhs
             e = lower_reduce(r)
-            if isinstance(self.lhs, mtie):
+            if r.op == RED_ARGMINMAX:
+                if not isinstance(self.lhs, mtie):
+                    raise TypeError("argminmax needs mtie(minv, mini, maxv, maxi) on the left-hand side")
+                o = [_out_desc(t) for t in self.lhs.outs]
+                A.check(A.lib.mxb_argminmax(ex.handle, C.byref(e), len(r.dims), C.byref(o[0]), C.byref(o[1]), C.byref(o[2]), C.byref(o[3])))
+            elif isinstance(self.lhs, mtie):
                 out, idx = _out_desc(self.lhs.outs[0]), _out_desc(self.lhs.outs[1])
                 A.check(A.lib.mxb_reduce(ex.handle, r.op, C.byref(e), len(r.dims), C.byref(out), C.byref(idx), r.ddof))
             else:

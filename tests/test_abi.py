@@ -145,16 +145,6 @@ def test_select_kernels_compile_for_sm100a(team, out_dt):
     assert A.lib.mxb_find(None, C.byref(e), 0, 0.0, None, None, 0) == A.ERR_INVALID   # null handle: an error, not a crash
 
 
-@pytest.mark.parametrize("npdt,ipt", [(np.complex64, 16), (np.float32, 2), (np.float64, 8)])
-def test_var_tma2_compiles_for_sm100a(npdt, ipt):
-    """Family 13 (var_tma2, opt-in): producer warp + two consumer teams; the instances without an AOT twin go through NVRTC."""
-    x = np_tensor(np.zeros((4, 64), npdt))
-    e = mx.lower_reduce(mx.ReduceExpr(A.RED_VAR, x, [1]))
-    log = C.create_string_buffer(1 << 16)
-    st = A.lib.mxb_debug_compile(C.byref(e), 13, A.RED_VAR, A.F64 if npdt == np.float64 else A.F32, 0, ipt, log, len(log))
-    assert st == A.OK, (A.lib.mxb_last_error(), log.value.decode()[:2000])
-
-
 def test_paired_fp32_body_compiles_for_sm100a():
     """Pure-fp32 programs get a second body on the packed fp32 instructions (FFMA2 / FMUL2 / FADD2): NVRTC must know
     the sm_100 intrinsics and the packed log / normcdf."""

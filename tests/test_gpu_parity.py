@@ -175,8 +175,8 @@ def test_kernel_families_are_selected(oracle):
     x = data(rng, (64, 4096), A.F32)
     k = check(oracle, "sum", lambda t: mx.sum(t, [1]), [x], A.F32)
     assert k.startswith("red_inner") and "|T0" in k and "|V8|U4" in k and k.endswith("aot"), k   # few 16 KB rows: a CTA per row, 32-byte loads for sums
-    k = check(oracle, "max", lambda t: mx.max(t, [1]), [x], A.F32)
-    assert k.startswith("red_inner") and "|T0" in k and "|V4|U4" in k and k.endswith("aot"), k   # compare-select ops keep 16-byte loads
+    k = check(oracle, "argmax", lambda t: mx.argmax(t, [1]), [x], A.F32)
+    assert k.startswith("red_inner") and "|V4|U4" in k and k.endswith("aot"), k   # (value, index) ops keep 16-byte loads
     x = data(rng, (1500, 4096), A.F32)
     k = check(oracle, "sum", lambda t: mx.sum(t, [1]), [x], A.F32)
     assert k.startswith("red_inner") and "|T1" in k, k                                          # many 16 KB rows: a warp per row

@@ -53,7 +53,7 @@ def test_fp16_sum_family_fp32_accumulation(oracle, shape, dims):
     """sum / mean / var / stdd of fp16 inputs accumulate in fp32 (north star); fp32 output within 1e-5 of the oracle's fp32
     accumulation, fp16 output within 1e-2."""
     rng = np.random.default_rng(zlib.crc32(repr(("f16sum", shape, dims)).encode()))
-    bits = f16_bits(rng.random(shape) + 0.5)
+    bits = f16_bits(rng.random(shape) * 0.5 + 0.25)      # mean 0.5: the 70001-element sum stays below the fp16 maximum (65504)
     for op in ("sum", "mean", "var", "stdd"):
         build = (lambda t, op=op: getattr(mx, op)(t, dims)) if op in ("sum", "mean") else (lambda t, op=op: getattr(mx, op)(t, dims, 1))
         n_red = np.prod([shape[d] for d in (dims if dims is not None else range(len(shape)))])
@@ -161,3 +161,59 @@ def test_extreme_magnitudes_and_signed_zero(oracle):
     for op in ("max", "min"):
         got, _, want, _, _ = G.run_reduce(oracle, lambda t, op=op: getattr(mx, op)(t), [z], A.F32)
         assert got == want == 0.0
+
+
+# ---- argminmax: both extrema from one read --------------------------------------------------------------------------
+ARGMM_CASES = [((4099,), None, np.float32), ((1 << 22,), None, np.float32), ((37, 129), [1], np.float32), ((5, 70001), [1], np.float32),
+               ((300, 64), [0], np.float32), ((6, 33, 33), [1, 2], np.float32), ((64, 4096), [1], np.float64),
+               ((9, 5000), [1], np.int32), ((2048, 40), [1], np.float32)]
+
+
+@pytest.mark.parametrize("shape,dims,npdt", ARGMM_CASES)
+def test_argminmax_equals_argmin_and_argmax_of_the_oracle(oracle, shape, dims, npdt):
+    """(mtie(mn, imn, mx, imx) = argminmax(x, dims)): values and absolute flat indices bit-exact against the oracle's argmin
+    and argmax of the same bits (operators/argminmax.h; ReductionTests.cu ArgMinMax), ties -> lowest index on both sides."""
+    import torch
+    rng = np.random.default_rng(zlib.crc32(repr(("amm", shape, dims)).encode()))
+    x = rng.integers(-50, 50, shape).astype(npdt)             # few distinct values: the extrema repeat
+    dt = {np.float32: A.F32, np.float64: A.F64, np.int32: A.I32}[npdt]
+    _, _, wmin, wimin, _ = G.run_reduce(oracle, lambda t: mx.argmin(t, dims), [x], dt)
+    _, _, wmax, wimax, _ = G.run_reduce(oracle, lambda t: mx.argmax(t, dims), [x], dt)
+    dx = torch.from_numpy(x).cuda()
+    oshape = wmin.shape
+    tdt = {np.float32: torch.float32, np.float64: torch.float64, np.int32: torch.int32}[npdt]
+    mn, mxv = torch.zeros(oshape, dtype=tdt, device="cuda"), torch.zeros(oshape, dtype=tdt, device="cuda")
+    imn, imx = torch.full(oshape, -1, dtype=torch.int64, device="cuda"), torch.full(oshape, -1, dtype=torch.int64, device="cuda")
+    ex = mx.CudaExecutor()
+    mx.mtie(*(mx.make_tensor(t) for t in (mn, imn, mxv, imx))).set(mx.argminmax(mx.make_tensor(dx), dims)).run(ex)
+    ex.sync()
+    k = ex.last_kernel()
+    assert np.array_equal(mn.cpu().numpy(), wmin) and np.array_equal(mxv.cpu().numpy(), wmax), k
+    assert np.array_equal(imn.cpu().numpy(), wimin) and np.array_equal(imx.cpu().numpy(), wimax), k
+    if dims != [0]:
+        assert "argminmax" in k, k        # the fused instance served it (a strided reduce dim runs argmin + argmax)
+
+
+def test_argminmax_of_a_fused_expression_and_mismatched_outputs(oracle):
+    import torch
+    rng = np.random.default_rng(77)
+    a, b = rng.standard_normal((128, 3000)).astype(np.float32), rng.standard_normal((128, 3000)).astype(np.float32)
+    _, _, wmin, wimin, _ = G.run_reduce(oracle, lambda s, t: mx.argmin(mx.abs(s) - t, [1]), [a, b], A.F32)
+    _, _, wmax, wimax, _ = G.run_reduce(oracle, lambda s, t: mx.argmax(mx.abs(s) - t, [1]), [a, b], A.F32)
+    da, db = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    ta, tb = mx.make_tensor(da), mx.make_tensor(db)
+    ex = mx.CudaExecutor()
+    mn, mxv = torch.zeros(128, device="cuda"), torch.zeros(128, device="cuda")
+    imn, imx = torch.zeros(128, dtype=torch.int64, device="cuda"), torch.zeros(128, dtype=torch.int64, device="cuda")
+    mx.mtie(*(mx.make_tensor(t) for t in (mn, imn, mxv, imx))).set(mx.argminmax(mx.abs(ta) - tb, [1])).run(ex)
+    ex.sync()
+    assert "argminmax" in ex.last_kernel()
+    assert np.array_equal(mn.cpu().numpy(), wmin) and np.array_equal(imn.cpu().numpy(), wimin)
+    assert np.array_equal(mxv.cpu().numpy(), wmax) and np.array_equal(imx.cpu().numpy(), wimax)
+    # max outputs strided differently from the min outputs: the library runs argmin + argmax (same answers)
+    wide = torch.zeros(128, 2, device="cuda")
+    mx2 = wide[:, 0]
+    mx.mtie(mx.make_tensor(mn), mx.make_tensor(imn), mx.make_tensor(mx2), mx.make_tensor(imx)).set(mx.argminmax(mx.abs(ta) - tb, [1])).run(ex)
+    ex.sync()
+    assert "argminmax" not in ex.last_kernel()
+    assert np.array_equal(mx2.cpu().numpy(), wmax) and np.array_equal(mn.cpu().numpy(), wmin)

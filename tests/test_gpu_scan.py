@@ -147,3 +147,65 @@ def test_full_size_properties():
     assert ex.last_kernel().startswith("scan|")
     assert float(y[-1]) == float(x.double().sum())
     assert torch.equal(y[1:] - y[:-1], x[1:]) and float(y[0]) == float(x[0])
+
+
+def test_two_streams_run_long_row_cumsum_concurrently():
+    """the TILES-mode scan spins on tiles of other CTAs, so every CTA of its grid must be resident.  It is launched
+    cooperatively (the runtime guarantees co-residency or refuses), so two handles scanning long rows on two streams at
+    once must both finish — and be right."""
+    import threading
+
+    import torch
+    n = 1 << 24
+    xs = [torch.rand(n, device="cuda") for _ in range(2)]
+    outs = [torch.empty(n, device="cuda") for _ in range(2)]
+    streams = [torch.cuda.Stream() for _ in range(2)]
+    exs = [mx.CudaExecutor(s) for s in streams]
+    torch.cuda.synchronize()
+
+    def work(i):
+        with torch.cuda.stream(streams[i]):
+            for _ in range(20):
+                mx.make_tensor(outs[i]).set(mx.cumsum(mx.make_tensor(xs[i]))).run(exs[i])
+        exs[i].sync()
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(timeout=120)
+    assert not any(t.is_alive() for t in ts), "a concurrent long-row cumsum did not finish"
+    for x, o in zip(xs, outs):
+        want = torch.cumsum(x.double(), 0)
+        assert float(((o.double() - want).abs() / want).max().item()) <= 1e-5
+
+
+def test_one_executor_shared_by_two_host_threads():
+    """SURVEY 8b threading: one handle used from two host threads (a b200Executor copied into two threads shares it): the
+    entry points lock the handle, the statements serialise on its stream, every result is right."""
+    import threading
+
+    import torch
+    ex = mx.CudaExecutor()
+    n = 1 << 22
+    xs = [torch.rand(n, device="cuda") + i for i in range(2)]
+    res = [[], []]
+
+    def work(i):
+        o = torch.zeros((), device="cuda")
+        m = torch.zeros((), device="cuda")
+        idx = torch.zeros((), dtype=torch.int64, device="cuda")
+        for _ in range(50):
+            mx.make_tensor(o).set(mx.sum(mx.make_tensor(xs[i]))).run(ex)
+            mx.mtie(mx.make_tensor(m), mx.make_tensor(idx)).set(mx.argmax(mx.make_tensor(xs[i]))).run(ex)
+        ex.sync()
+        res[i] = [o.item(), m.item(), idx.item()]
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(timeout=120)
+    assert not any(t.is_alive() for t in ts)
+    for i in range(2):
+        truth = xs[i].double().sum().item()
+        assert abs(res[i][0] - truth) <= 1e-5 * truth
+        assert res[i][1] == xs[i].max().item() and res[i][2] == int(torch.argmax(xs[i]).item())

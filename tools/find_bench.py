@@ -1,40 +1,40 @@
-"""find / find_idx over sizes, selectivities and dtypes: the single-pass look-back kernel (fast = 1) against the two-pass
-count + scatter pair (MXB_SEL_TWO_PASS=1, fast = 0), with torch.masked_select beside it.  Development tool, run under gpurun."""
+"""find / find_idx timing on 2^28 fp32 at several selectivities and launch shapes (development tool, run under gpurun).
+Prints one JSON line per setting; `torch` column = torch.masked_select-free baseline is not used — the A/B against
+cub::DeviceSelect is tests/cpp/dropin_test --bench."""
 import json
 import os
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import torch
+import torch  # noqa: E402
 
-from matx_b200 import bench_configs as bc, ops as mx
+from matx_b200 import bench_configs as bc  # noqa: E402
+from matx_b200 import ops as mx  # noqa: E402
 
-ex = mx.CudaExecutor()
 PEAK = 6456.8
-for logn in (20, 24, 28):
-    n = 1 << logn
-    x = torch.rand(n, device="cuda")
-    out = torch.empty(n, device="cuda")
-    idx = torch.empty(n, dtype=torch.int32, device="cuda")
-    nf = torch.zeros((), dtype=torch.int32, device="cuda")
-    tx, to, ti, tn = (mx.make_tensor(t) for t in (x, out, idx, nf))
-    for thr in (0.99, 0.5, 0.01):
-        want = torch.masked_select(x, x > thr)
-        ms_t, _ = bc._time(ex, lambda: torch.masked_select(x, x > thr), iters=5, warm=2)
-        for fast in ("0", "1"):
-            os.environ["MXB_SEL_TWO_PASS"] = "0" if fast == "1" else "1"
-            for name, fn in (("find", lambda: mx.mtie(to, tn).set(mx.find(tx, mx.GT(thr))).run(ex)),
-                             ("find_idx", lambda: mx.mtie(ti, tn).set(mx.find_idx(tx, mx.GT(thr))).run(ex))):
-                try:
-                    ms, best = bc._time(ex, fn, iters=6, warm=2)
-                    ok = nf.item() == want.numel() and (torch.equal(out[: want.numel()], want) if name == "find"
-                                                        else torch.equal(x[idx[: want.numel()].long()], want))
-                    nbytes = n * 4 + want.numel() * 4
-                    print(json.dumps({"n": n, "selected": round(want.numel() / n, 4), "op": name, "fast": int(fast), "ms": round(ms, 4),
-                                      "GBps": round(nbytes / ms / 1e6, 1), "frac": round(nbytes / ms / 1e6 / PEAK, 3), "ok": bool(ok),
-                                      "torch_masked_select_ms": round(ms_t, 4), "kernel": ex.last_kernel()}), flush=True)
-                except Exception as exc:  # noqa: BLE001
-                    print(json.dumps({"n": n, "op": name, "fast": int(fast), "error": str(exc)[:200]}), flush=True)
-        os.environ.pop("MXB_SEL_TWO_PASS", None)
-    del x, out, idx
-    torch.cuda.empty_cache()
+n = 1 << 28
+x = torch.rand(n, device="cuda")
+tx = mx.make_tensor(x)
+out = torch.empty(n, device="cuda")
+iout = torch.empty(n, dtype=torch.int32, device="cuda")
+nf = torch.zeros((), dtype=torch.int32, device="cuda")
+envs = [{}] + [{"MXB_TUNE_SEL_CTAS": str(c)} for c in (1, 2)]
+if len(sys.argv) > 1:
+    envs = [json.loads(a) for a in sys.argv[1:]]
+for env in envs:
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    ex = mx.CudaExecutor()
+    for thr in (0.99, 0.9, 0.5, 0.0):
+        for idx in (False, True):
+            o = iout if idx else out
+            f = (mx.find_idx if idx else mx.find)(tx, mx.GT(thr))
+            fn = lambda: mx.mtie(mx.make_tensor(o), mx.make_tensor(nf)).set(f).run(ex)  # noqa: E731
+            ms, best = bc._time(ex, fn, iters=10, warm=3)
+            sel = int(nf.item())
+            want = int((x > thr).sum().item())
+            nbytes = n * 4 + sel * 4 + 4
+            print(json.dumps({"thr": thr, "idx": idx, "env": env, "ms": round(ms, 4), "best": round(best, 4), "selected": sel, "count_ok": sel == want,
+                              "GBps": round(nbytes / ms / 1e6, 1), "frac": round(nbytes / ms / 1e6 / PEAK, 3), "kernel": ex.last_kernel()}), flush=True)
+    for k, v in old.items():
+        os.environ.pop(k, None) if v is None else os.environ.__setitem__(k, v)
