@@ -230,7 +230,10 @@ void aot_manifest(std::vector<ManifestItem> *items) {
     }
   }
   // fused argminmax of plain fp32 tensors
-  for (int team : {0, 1}) add(prog_identity(MXB_F32), FAM_RED_INNER, KOP_ARGMINMAX, MXB_F32, team, false);
+  for (int team : {0, 1}) {
+    add(prog_identity(MXB_F32), FAM_RED_INNER, KOP_ARGMINMAX, MXB_F32, team, false);
+    if (team == 0) items->back().spec.minb = 4;   // the dispatcher's register cap for the CTA-per-item shape
+  }
   // one-pass variance (Welford + Chan) for rows that cannot stay on chip and for strided rows
   for (int d : {MXB_F32, MXB_C64})
     for (int team : {0, 1}) add(prog_identity(d), FAM_RED_INNER, MXB_RED_VAR, MXB_F32, team, d == MXB_F32);

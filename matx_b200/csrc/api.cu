@@ -753,7 +753,9 @@ int reduce_launch(mxb_context *h, int kop, const mxb_expr_t &e, const ExprInfo &
       int64_t S = 1;
       // CTAs that are co-resident per SM: the grid is exactly one resident wave and the work items are dealt
       // dynamically (RedParams::work_ctr), so no CTA ever waits behind another for an SM
-      spec.minb = env_int("MXB_TUNE_MINB", 0);
+      // the dual arg state: without a register cap the compiler takes 118 registers (two CTAs per SM); at 64 the few spills
+      // sit on the rare path that replaces an extremum (2^30 fp32: 0.82 -> 0.65 ms)
+      spec.minb = env_int("MXB_TUNE_MINB", kop == KOP_ARGMINMAX ? 4 : 0);
       Kernel kq;
       int st = get_kernel(info, spec, &kq);
       if (st != MXB_OK) return st;
@@ -2255,7 +2257,7 @@ static int find_impl(mxb_handle_t h, const mxb_expr_t *expr_in, int select_op, d
     if (st != MXB_OK) return st;
     // warp tiles of 32 lanes x 32 elements (16 for 8-byte values), dealt round-robin to the warps of a grid that is
     // resident as a whole (cooperative launch: a tile only waits for tiles whose warps are running)
-    const int64_t wtile = 32 * (dtype_bytes(info.value_dtype) > 4 ? 16 : 32);
+    const int64_t wtile = 32 * (V == 1 ? 8 : (dtype_bytes(info.value_dtype) > 4 ? 16 : 32));   // SelGeom::TILE (mxb_device.cuh)
     const int64_t nwt = (N + wtile - 1) / wtile;
     const unsigned smem = 0;
     const int res = resident_ctas(k, 256, smem, 4);
@@ -2267,6 +2269,8 @@ static int find_impl(mxb_handle_t h, const mxb_expr_t *expr_in, int select_op, d
     p.sel_status = (unsigned long long *)lb_region(h, 8);
     p.sel_epoch = h->lb_ctl;
     p.sel_ticket = h->lb_ctl + 1;
+    // bits 0-1: iterations between a tile's exchange jobs (1 or 2), bit 2: L2 prefetch of the warp's next tile
+    p.sel_depth = (env_int("MXB_TUNE_SEL_DEPTH", 1) == 2 ? 2 : 1) | (env_int("MXB_TUNE_SEL_L2AHEAD", 0) ? 4 : 0);
     return launch(h, k, grid, 256, smem, p, /*coop=*/true);
   }
 

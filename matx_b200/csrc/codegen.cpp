@@ -583,11 +583,12 @@ int kernel_wrapper_src(const ExprInfo &info, const KernelSpec &s, const std::str
       break;
     case FAM_SELECT:
       // team = kernel: 0 count (+ in-launch scan of the CTA totals), 1 scatter values, 2 scatter flat indices (the two-pass
-      // pair for N-D views); 3 / 4 = the single-pass look-back kernel writing values / flat indices
+      // pair for N-D views); 3 / 4 = the single-pass warp-tile kernel writing values / flat indices
       if (cplx || info.value_dtype == MXB_BF16 || info.value_dtype == MXB_F16) return fail("find / find_idx serve real value types");
       if (s.team < 0 || s.team > 4) return fail("select kernel out of range");
       if (s.team >= 3)
-        k << "extern \"C\" __global__ void __launch_bounds__(256, 3) " << symbol
+        // values: three CTAs per SM (the vector re-read of the tile being written needs the registers), indices: four
+        k << "extern \"C\" __global__ void __launch_bounds__(256, " << (s.team == 3 ? 3 : 4) << ") " << symbol
           << "(const __grid_constant__ mxb::EwParams p) { mxb::select1p_body<" << E << ", " << O << ", " << s.V << ", " << (s.team - 2) << ">(p); }\n";
       else
         k << "extern \"C\" __global__ void __launch_bounds__(256) " << symbol

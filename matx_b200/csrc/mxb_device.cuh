@@ -3800,66 +3800,96 @@ template <int OP> struct SelPred {
   }
 };
 
-// offset of warp tile `ct` from the published counts (all 32 lanes call it, every lane returns the offset); the caller has
-// published the tile's own count in agg[ct].  own[sg] = count of supergroup sg alone, run[sg] = count of everything before
-// supergroup sg (published by the closer of supergroup sg - 1 from own[0 .. sg - 1]).
-__device__ __forceinline__ u32 sel_carry(void *agg, void *gagg, void *run, void *own, i64 ct, i64 ntiles, u32 total, u32 tag, int lane) {
+// The exchange of the published counts, as jobs that a warp runs for tiles it ranked 1, 2, 3 and 4 iterations earlier (so
+// every job finds its inputs published by the other warps' previous iteration instead of waiting a round trip for them):
+//   close  (+1)  a tile that ends its group of 32 sums the group's tile counts          -> group count
+//   super  (+2)  a tile that ends its supergroup of 32 groups sums the group counts     -> the supergroup's OWN count
+//   run    (+3)  the same tile sums the own counts of every supergroup up to its own    -> running count at the next start
+//   carry  (+4)  running count at the supergroup start + group counts before + tile counts before = the tile's offset
+// No job depends on a job of the same kind, so the dependency depth is constant however many tiles there are.
+struct SelExchange {
   typedef ScanSlot<u32> SL;
-  const i64 g = ct >> 5, first = g << 5, sg = ct >> 10, gfirst = sg << 5;
-  const int n2 = (int)(ct - first), n1 = (int)(g - gfirst);
-  // every read goes out before the first wait
-  SL::Word wa, wb, wc;
-  if (lane < n2) wa = SL::peek(agg, first + lane);
-  if (lane < n1) wb = SL::peek(gagg, gfirst + lane);
-  if (lane == 0 && sg > 0) wc = SL::peek(run, sg);
-  u32 a = 0, b = 0, c = 0;
-  if (lane < n2) { while (!SL::ready(wa, tag)) { __nanosleep(20); wa = SL::peek(agg, first + lane); } a = SL::value(wa); }
-  const u32 sa = warp_tree_sum(a);
-  const bool last_tile = ct == ntiles - 1;
-  const bool closes_group = (ct & 31) == 31 || last_tile;
-  const u32 gt = sa + total;
-  if (closes_group && lane == 0) SL::publish(gagg, g, gt, tag);   // before waiting for anything of an earlier group
-  if (lane < n1) { while (!SL::ready(wb, tag)) { __nanosleep(20); wb = SL::peek(gagg, gfirst + lane); } b = SL::value(wb); }
-  const u32 sb = warp_tree_sum(b);
-  if (closes_group && (g & 31) == 31 && !last_tile) {
-    // this tile ends supergroup sg: its own count goes out, then the running count at the start of the next one
-    const u32 mine = sb + gt;
-    if (lane == 0) SL::publish(own, sg, mine, tag);
-    u32 acc = 0;
-    for (i64 i = lane; i < sg; i += 32) acc += SL::wait(own, i, tag);
-    acc = warp_tree_sum(acc);
-    if (lane == 0) SL::publish(run, sg + 1, acc + mine, tag);
+  unsigned long long *agg, *gagg, *run, *own;
+  i64 ntiles;
+  u32 tag;
+  int lane;
+  __device__ __forceinline__ u32 get(const unsigned long long *slots, i64 i, bool on) const {
+    u32 v = 0;
+    if (on) {
+      SL::Word w = SL::peek(slots, i);
+      while (!SL::ready(w, tag)) { __nanosleep(20); w = SL::peek(slots, i); }
+      v = SL::value(w);
+    }
+    return v;
   }
-  if (lane == 0 && sg > 0) { while (!SL::ready(wc, tag)) { __nanosleep(20); wc = SL::peek(run, sg); } c = SL::value(wc); }
-  c = __shfl_sync(0xffffffffu, c, 0);
-  return (c + sb) + sa;
-}
+  __device__ __forceinline__ bool closes_group(i64 ct) const { return ct >= 0 && ct < ntiles && ((ct & 31) == 31 || ct == ntiles - 1); }
+  __device__ __forceinline__ bool closes_super(i64 ct) const { return ct >= 0 && ct < ntiles - 1 && (ct & 1023) == 1023; }
+  __device__ __forceinline__ void close(i64 ct, u32 total) const {
+    const i64 first = (ct >> 5) << 5;
+    const u32 s = __reduce_add_sync(0xffffffffu, get(agg, first + lane, first + lane < ct));
+    if (lane == 0) SL::publish(gagg, ct >> 5, s + total, tag);
+  }
+  __device__ __forceinline__ void super(i64 ct) const {
+    if (!closes_super(ct)) return;
+    const i64 sg = ct >> 10;
+    const u32 s = __reduce_add_sync(0xffffffffu, get(gagg, (sg << 5) + lane, true));
+    if (lane == 0) SL::publish(own, sg, s, tag);
+  }
+  __device__ __forceinline__ void running(i64 ct) const {
+    if (!closes_super(ct)) return;
+    const i64 sg = ct >> 10;
+    u32 acc = 0;
+    for (i64 i = lane; i <= sg; i += 32) acc += get(own, i, true);
+    acc = __reduce_add_sync(0xffffffffu, acc);
+    if (lane == 0) SL::publish(run, sg + 1, acc, tag);
+  }
+  __device__ __forceinline__ u32 carry(i64 ct) const {
+    const i64 g = ct >> 5, first = g << 5, sg = ct >> 10, gfirst = sg << 5;
+    // the three reads go out together
+    const bool on_a = first + lane < ct, on_b = gfirst + lane < g, on_c = lane == 0 && sg > 0;
+    SL::Word wa, wb, wc;
+    if (on_a) wa = SL::peek(agg, first + lane);
+    if (on_b) wb = SL::peek(gagg, gfirst + lane);
+    if (on_c) wc = SL::peek(run, sg);
+    u32 v = 0;
+    if (on_a) { while (!SL::ready(wa, tag)) { __nanosleep(20); wa = SL::peek(agg, first + lane); } v += SL::value(wa); }
+    if (on_b) { while (!SL::ready(wb, tag)) { __nanosleep(20); wb = SL::peek(gagg, gfirst + lane); } v += SL::value(wb); }
+    if (on_c) { while (!SL::ready(wc, tag)) { __nanosleep(20); wc = SL::peek(run, sg); } v += SL::value(wc); }
+    return __reduce_add_sync(0xffffffffu, v);
+  }
+};
+
+constexpr int SEL_RING = 9;     // tile states a warp keeps: ranked in iteration i, written in iteration i + 4 * K (K = 1, 2)
+constexpr int SEL_WARPS = 8;    // warps per CTA (256 threads)
+template <class T, int V> struct SelGeom {
+  // elements per lane and tile: 32 (1024-element warp tiles), 16 for 8-byte values, 8 on the scalar (strided / broadcast) walk
+  enum { EPL = V == 1 ? 8 : (sizeof(T) > 4 ? 16 : 32), U = EPL / V, TILE = 32 * EPL,
+         CB = (32 * V <= 255) ? 8 : 16, CPW = 32 / CB, NWORD = (U + CPW - 1) / CPW, NSTATE = 1 + 2 * NWORD };
+};
 
 template <class E, class OutT, int V, int MODE, bool UNIT, int OP>   // MODE 1: values, 2: flat indices; OP < 0: runtime op / unique
-__device__ __forceinline__ void select1p_tiles(const EwParams &p) {
+__device__ __forceinline__ void select1p_tiles(const EwParams &p, u32 (*ring)[SEL_RING][SelGeom<typename E::value_type, V>::NSTATE][32]) {
   typedef typename E::value_type T;
   typedef typename E::template Regs<V> R;
-  constexpr int EPL = sizeof(T) > 4 ? 16 : 32;      // elements per lane and tile
-  constexpr int U = EPL / V;                        // vectors per lane and tile
-  constexpr i64 TILE = (i64)32 * EPL;
-  constexpr int CB = (32 * V <= 255) ? 8 : 16;      // bits of a packed counter (inclusive warp sums reach 32 * V)
-  constexpr int CPW = 32 / CB;                      // counters per word
-  constexpr int NWORD = (U + CPW - 1) / CPW;
+  typedef SelGeom<T, V> GEO;
+  constexpr int U = GEO::U, CB = GEO::CB, CPW = GEO::CPW, NWORD = GEO::NWORD;
+  constexpr i64 TILE = GEO::TILE;
   constexpr u32 CMASK = CB == 8 ? 0xffu : 0xffffu;
   constexpr u32 VMASK = V >= 32 ? 0xffffffffu : ((1u << V) - 1u);
-  static_assert(EPL % V == 0 && U >= 1, "vector width must divide the elements per lane");
-  const int lane = threadIdx.x & 31;
+  static_assert(GEO::EPL % V == 0 && U >= 1 && U * V <= 32, "a lane's flags must fit one word");
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const i64 wpc = blockDim.x >> 5;
-  const i64 nwarp = (i64)gridDim.x * wpc, gw = (i64)blockIdx.x * wpc + (threadIdx.x >> 5);
+  const i64 nwarp = (i64)gridDim.x * wpc, gw = (i64)blockIdx.x * wpc + warp;
   const i64 ntiles = (p.N + TILE - 1) / TILE;
   const T thr = SelThr<T>::get(p);
   const bool unique_mode = p.sel_op == 6;             // MXB_SEL_UNIQUE (mxb_unique): adjacent-difference flags over a sorted operand
   const u32 fmask = sel_mask(unique_mode ? 0 : p.sel_op);
   const u32 epoch = __ldcg(p.sel_epoch) & 0x3fffffffu;
-  const u32 tag = (epoch << 2) | 1u;
   // slots: tile counts | group counts (32 tiles) | running counts at supergroup starts (1024 tiles) | supergroup counts
   const i64 ngroup = (ntiles + 31) >> 5, nsuper = (ntiles + 1023) >> 10;
-  unsigned long long *agg = p.sel_status, *gagg = agg + ntiles, *run = gagg + ngroup, *own = run + nsuper + 1;
+  SelExchange xc;
+  xc.agg = p.sel_status; xc.gagg = xc.agg + ntiles; xc.run = xc.gagg + ngroup; xc.own = xc.run + nsuper + 1;
+  xc.ntiles = ntiles; xc.tag = (epoch << 2) | 1u; xc.lane = lane;
   const char *base[E::NL];
   i64 inner[E::NL];
 #pragma unroll
@@ -3867,143 +3897,223 @@ __device__ __forceinline__ void select1p_tiles(const EwParams &p) {
   OutT *out = (OutT *)p.out.ptr;
   const u32 cap = p.sel_cap > 0xffffffffll ? 0xffffffffu : (u32)p.sel_cap;
 
-  for (i64 tile = gw; tile < ntiles; tile += nwarp) {
+  auto slot_total = [&](int sl) {      // count of the tile whose state sits in ring slot `sl`
+    u32 t = 0;
+#pragma unroll
+    for (int w = 0; w < NWORD; ++w) {
+      const u32 x = ring[warp][sl][1 + NWORD + w][lane];
+#pragma unroll
+      for (int c = 0; c < CPW; ++c) if (w * CPW + c < U) t += (x >> (CB * c)) & CMASK;
+    }
+    return t;
+  };
+
+  // distance between a tile's jobs in iterations (1 or 2): at 2 the warps may drift an iteration apart without waiting
+  const int K = (p.sel_depth & 3) == 2 ? 2 : 1;
+  const int RN = 4 * K + 1;                           // ring slots in use
+  const bool l2_ahead = (p.sel_depth & 4) != 0;       // prefetch the next tile of this warp into L2
+  const i64 kw = (i64)K * nwarp;
+  int s0 = 0;   // ring slot of this iteration's tile; the tile of k iterations ago sits in slot (s0 - k) mod RN
+  for (i64 tile = gw; tile - 4 * kw < ntiles; tile += nwarp) {
+    const bool p1 = tile < ntiles;
     const i64 t0 = tile * TILE;
     const i64 jl = t0 + (i64)lane * V;              // first element of this lane's vector 0; vector u sits 32 * V further
-    T vals[U][V];
-    u32 f = 0;                                      // bit u * V + v: element (u, v) of this lane is selected
-    if (OP >= 0 && t0 + TILE <= p.N) {
-      // a full tile (all but the last): no bounds, the predicate is a compile-time functor
-      R r[U];
+    const bool fast = OP >= 0 && p1 && t0 + TILE <= p.N;
+    // ---- this iteration's loads go out first: the exchange jobs below run under their latency ----
+    R r[U];
+    if (fast) {
 #pragma unroll
       for (int u = 0; u < U; ++u) E::template loadv<V, UNIT>(r[u], base, inner, jl + (i64)u * 32 * V);
+    }
+    if (l2_ahead && UNIT && (tile + nwarp + 1) * TILE <= p.N) {
+      // one 128-byte line per lane and leaf: the next tile of this warp waits in L2 when its loads go out
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-#pragma unroll
-        for (int v = 0; v < V; ++v) {
-          vals[u][v] = E::template eval<V>(r[u], v, p.c);
-          if (SelPred<OP < 0 ? 0 : OP>::test(vals[u][v], thr)) f |= 1u << (u * V + v);
-        }
+      for (int k = 0; k < E::NL; ++k) {
+        const char *a = base[k] + ((tile + nwarp) * TILE * E::leaf_bytes(k)) + lane * 128;
+        if (lane * 128 < TILE * E::leaf_bytes(k)) asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
       }
-    } else {
+    }
+    // ---- exchange jobs of the tiles ranked K, 2K and 3K iterations ago ----
+    {
+      const int s1 = s0 >= K ? s0 - K : s0 - K + RN;
+      const i64 tb = tile - kw;
+      if (xc.closes_group(tb)) xc.close(tb, slot_total(s1));
+      xc.super(tile - 2 * kw);
+      xc.running(tile - 3 * kw);
+    }
+    // ---- the tile ranked 4K iterations ago: its offset ----
+    const i64 td = tile - 4 * kw;
+    const bool p4 = td >= 0 && td < ntiles;
+    const int s4 = s0 >= 4 * K ? s0 - 4 * K : s0 - 4 * K + RN;
+    u32 off = 0;
+    if (p4) {
+      off = xc.carry(td);
+      if (td == ntiles - 1 && lane == 0) {
+        const unsigned long long all = (unsigned long long)off + slot_total(s4);
+        *p.sel_total = all > 0x7fffffffull ? 0x7fffffff : (int)all;
+      }
+    }
+    // ---- rank this iteration's tile ----
+    if (p1) {
+      u32 f = 0;                                      // bit u * V + v: element (u, v) of this lane is selected
+      if (fast) {
+        // a full tile (all but the last): no bounds, the predicate is a compile-time functor
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const i64 j0 = jl + (i64)u * 32 * V;
-        u32 fu = 0;
-        if (j0 + V <= p.N) {
-          R r;
-          E::template loadv<V, UNIT>(r, base, inner, j0);
+        for (int u = 0; u < U; ++u) {
 #pragma unroll
           for (int v = 0; v < V; ++v) {
-            vals[u][v] = E::template eval<V>(r, v, p.c);
-            fu |= sel_flag<T>(vals[u][v], thr, fmask) << v;
-          }
-        } else {
-#pragma unroll
-          for (int v = 0; v < V; ++v) {
-            if (j0 + v < p.N) {
-              typename E::template Regs<1> r1;
-              E::template loadv<1, false>(r1, base, inner, j0 + v);
-              vals[u][v] = E::template eval<1>(r1, 0, p.c);
-              fu |= sel_flag<T>(vals[u][v], thr, fmask) << v;
-            }
+            if (SelPred<OP < 0 ? 0 : OP>::test(E::template eval<V>(r[u], v, p.c), thr)) f |= 1u << (u * V + v);
           }
         }
-        if (unique_mode) {
-          // unique over a SORTED operand (std::unique / cub::DeviceSelect::Unique): keep x[j] iff j == 0 or x[j] != x[j - 1]
-          fu = 0;
-          if (j0 < p.N) {
-            T prev = vals[u][0];
-            if (j0 > 0) {
-              typename E::template Regs<1> r1;
-              E::template loadv<1, false>(r1, base, inner, j0 - 1);
-              prev = E::template eval<1>(r1, 0, p.c);
+      } else {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const i64 j0 = jl + (i64)u * 32 * V;
+          T vals[V];
+          u32 fu = 0;
+          if (j0 + V <= p.N) {
+            R rr;
+            E::template loadv<V, UNIT>(rr, base, inner, j0);
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+              vals[v] = E::template eval<V>(rr, v, p.c);
+              fu |= sel_flag<T>(vals[v], thr, fmask) << v;
             }
+          } else {
 #pragma unroll
             for (int v = 0; v < V; ++v) {
               if (j0 + v < p.N) {
-                const bool keep = (j0 + v == 0) || !(vals[u][v] == prev);
-                fu |= (keep ? 1u : 0u) << v;
-                prev = vals[u][v];
+                typename E::template Regs<1> r1;
+                E::template loadv<1, false>(r1, base, inner, j0 + v);
+                vals[v] = E::template eval<1>(r1, 0, p.c);
+                fu |= sel_flag<T>(vals[v], thr, fmask) << v;
               }
             }
           }
-        }
-        f |= fu << (u * V);
-      }
-    }
-    // ---- ranks: packed per-vector counts through shuffle scans ----
-    u32 own_w[NWORD], incl[NWORD];
+          if (unique_mode) {
+            // unique over a SORTED operand (std::unique / cub::DeviceSelect::Unique): keep x[j] iff j == 0 or x[j] != x[j - 1]
+            fu = 0;
+            if (j0 < p.N) {
+              T prev = vals[0];
+              if (j0 > 0) {
+                typename E::template Regs<1> r1;
+                E::template loadv<1, false>(r1, base, inner, j0 - 1);
+                prev = E::template eval<1>(r1, 0, p.c);
+              }
 #pragma unroll
-    for (int w = 0; w < NWORD; ++w) own_w[w] = 0;
-#pragma unroll
-    for (int u = 0; u < U; ++u) own_w[u / CPW] |= (u32)__popc((f >> (u * V)) & VMASK) << (CB * (u % CPW));
-#pragma unroll
-    for (int w = 0; w < NWORD; ++w) incl[w] = own_w[w];
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-#pragma unroll
-      for (int w = 0; w < NWORD; ++w) {
-        const u32 o = __shfl_up_sync(0xffffffffu, incl[w], d);
-        if (lane >= d) incl[w] += o;
-      }
-    }
-    // per-vector totals of the warp (lane 31) -> where each vector row starts inside the tile, and the tile's count
-    u32 bef[U];
-    u32 total = 0;
-#pragma unroll
-    for (int w = 0; w < NWORD; ++w) {
-      const u32 t = __shfl_sync(0xffffffffu, incl[w], 31);
-#pragma unroll
-      for (int c = 0; c < CPW; ++c) {
-        if (w * CPW + c < U) { bef[w * CPW + c] = total; total += (t >> (CB * c)) & CMASK; }
-      }
-    }
-    if (lane == 0) ScanSlot<u32>::publish(agg, tile, total, tag);   // first thing: every later tile waits for this store
-    const u32 off = sel_carry(agg, gagg, run, own, tile, ntiles, total, tag, lane);
-    if (tile == ntiles - 1 && lane == 0) {
-      const unsigned long long all = (unsigned long long)off + total;
-      *p.sel_total = all > 0x7fffffffull ? 0x7fffffff : (int)all;
-    }
-    // ---- the selected elements go straight to their final places ----
-    if (f) {
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const u32 fu = (f >> (u * V)) & VMASK;
-        if (fu) {
-          const u32 ex = ((incl[u / CPW] - own_w[u / CPW]) >> (CB * (u % CPW))) & CMASK;
-          u32 pos = off + bef[u] + ex;                 // counts stay below 2^32 (host check)
-          const i64 j0 = jl + (i64)u * 32 * V;
-#pragma unroll
-          for (int v = 0; v < V; ++v) {
-            if ((fu >> v) & 1u) {
-              if (pos < cap) out[pos] = MODE == 1 ? cvt<OutT>(vals[u][v]) : (OutT)(j0 + v);   // beyond the capacity: counted, not written
-              ++pos;
+              for (int v = 0; v < V; ++v) {
+                if (j0 + v < p.N) {
+                  const bool keep = (j0 + v == 0) || !(vals[v] == prev);
+                  fu |= (keep ? 1u : 0u) << v;
+                  prev = vals[v];
+                }
+              }
             }
           }
+          f |= fu << (u * V);
+        }
+      }
+      // ranks: packed per-vector counts through shuffle scans; the per-vector totals of the warp come from lane 31
+      u32 own_w[NWORD], incl[NWORD];
+#pragma unroll
+      for (int w = 0; w < NWORD; ++w) own_w[w] = 0;
+#pragma unroll
+      for (int u = 0; u < U; ++u) own_w[u / CPW] |= (u32)__popc((f >> (u * V)) & VMASK) << (CB * (u % CPW));
+#pragma unroll
+      for (int w = 0; w < NWORD; ++w) incl[w] = own_w[w];
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+#pragma unroll
+        for (int w = 0; w < NWORD; ++w) {
+          const u32 o = __shfl_up_sync(0xffffffffu, incl[w], d);
+          if (lane >= d) incl[w] += o;
+        }
+      }
+      u32 total = 0;
+#pragma unroll
+      for (int w = 0; w < NWORD; ++w) {
+        const u32 t = __shfl_sync(0xffffffffu, incl[w], 31);
+        ring[warp][s0][1 + w][lane] = incl[w] - own_w[w];
+        ring[warp][s0][1 + NWORD + w][lane] = t;
+#pragma unroll
+        for (int c = 0; c < CPW; ++c) if (w * CPW + c < U) total += (t >> (CB * c)) & CMASK;
+      }
+      ring[warp][s0][0][lane] = f;
+      if (lane == 0) ScanSlot<u32>::publish(xc.agg, tile, total, xc.tag);
+    }
+    // ---- the selected elements of the tile ranked 4 iterations ago go to their final places ----
+    if (p4) {
+      const u32 f = ring[warp][s4][0][lane];
+      const i64 jd = td * TILE + (i64)lane * V;
+      // values: the tile is read again, as vectors, into the registers the ranking has just freed (it went through L2 four
+      // iterations ago) — carrying 32 values per lane across four iterations would cost the occupancy that hides the loads
+      const bool vec_again = MODE == 1 && V > 1 && (td + 1) * TILE <= p.N && __any_sync(0xffffffffu, f != 0);
+      u32 ex[NWORD], tw[NWORD];
+#pragma unroll
+      for (int w = 0; w < NWORD; ++w) { ex[w] = ring[warp][s4][1 + w][lane]; tw[w] = ring[warp][s4][1 + NWORD + w][lane]; }
+      u32 row = off;                                  // where vector row u starts in the output
+      constexpr int UH = U >= 2 ? U / 2 : 1;          // the re-read goes in two halves: half the registers
+#pragma unroll
+      for (int h = 0; h < U / UH; ++h) {
+        R r2[UH];
+        if (vec_again) {
+#pragma unroll
+          for (int u = 0; u < UH; ++u) E::template loadv<V, UNIT>(r2[u], base, inner, jd + (i64)(h * UH + u) * 32 * V);
+        }
+#pragma unroll
+        for (int uu = 0; uu < UH; ++uu) {
+          const int u = h * UH + uu;
+          const u32 fu = (f >> (u * V)) & VMASK;
+          if (fu) {
+            u32 pos = row + ((ex[u / CPW] >> (CB * (u % CPW))) & CMASK);   // counts stay below 2^32 (host check)
+            const i64 j0 = jd + (i64)u * 32 * V;
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+              if ((fu >> v) & 1u) {
+                if (pos < cap) {                      // beyond the capacity: counted, not written
+                  if (MODE == 1) {
+                    if (vec_again) {
+                      out[pos] = cvt<OutT>(E::template eval<V>(r2[uu], v, p.c));
+                    } else {
+                      typename E::template Regs<1> r1;
+                      E::template loadv<1, false>(r1, base, inner, j0 + v);
+                      out[pos] = cvt<OutT>(E::template eval<1>(r1, 0, p.c));
+                    }
+                  } else {
+                    out[pos] = (OutT)(j0 + v);
+                  }
+                }
+                ++pos;
+              }
+            }
+          }
+          row += (tw[u / CPW] >> (CB * (u % CPW))) & CMASK;
         }
       }
     }
+    s0 = s0 + 1 == RN ? 0 : s0 + 1;
   }
 }
 
 template <class E, class OutT, int V, int MODE>
 __device__ __forceinline__ void select1p_body(const EwParams &p) {
   pdl_prologue();
+  // per-warp ring of tile states, one column per lane: flags, exclusive packed counts, packed totals of the warp
+  __shared__ u32 ring[SEL_WARPS][SEL_RING][SelGeom<typename E::value_type, V>::NSTATE][32];
   const bool unit = p.all_unit != 0;
   if (V > 1 || unit) {
     // V > 1 is only ever launched over unit-stride leaves
     switch (p.sel_op) {
-      case 0: select1p_tiles<E, OutT, V, MODE, true, 0>(p); break;
-      case 1: select1p_tiles<E, OutT, V, MODE, true, 1>(p); break;
-      case 2: select1p_tiles<E, OutT, V, MODE, true, 2>(p); break;
-      case 3: select1p_tiles<E, OutT, V, MODE, true, 3>(p); break;
-      case 4: select1p_tiles<E, OutT, V, MODE, true, 4>(p); break;
-      case 5: select1p_tiles<E, OutT, V, MODE, true, 5>(p); break;
-      default: select1p_tiles<E, OutT, V, MODE, true, -1>(p); break;
+      case 0: select1p_tiles<E, OutT, V, MODE, true, 0>(p, ring); break;
+      case 1: select1p_tiles<E, OutT, V, MODE, true, 1>(p, ring); break;
+      case 2: select1p_tiles<E, OutT, V, MODE, true, 2>(p, ring); break;
+      case 3: select1p_tiles<E, OutT, V, MODE, true, 3>(p, ring); break;
+      case 4: select1p_tiles<E, OutT, V, MODE, true, 4>(p, ring); break;
+      case 5: select1p_tiles<E, OutT, V, MODE, true, 5>(p, ring); break;
+      default: select1p_tiles<E, OutT, V, MODE, true, -1>(p, ring); break;
     }
   } else {
-    select1p_tiles<E, OutT, V, MODE, false, -1>(p);
+    select1p_tiles<E, OutT, V, MODE, false, -1>(p, ring);
   }
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   // exit ticket: the last CTA out opens the next epoch (every status word of this launch is stale from then on)
