@@ -2269,8 +2269,6 @@ static int find_impl(mxb_handle_t h, const mxb_expr_t *expr_in, int select_op, d
     p.sel_status = (unsigned long long *)lb_region(h, 8);
     p.sel_epoch = h->lb_ctl;
     p.sel_ticket = h->lb_ctl + 1;
-    // bits 0-1: iterations between a tile's exchange jobs (1 or 2), bit 2: L2 prefetch of the warp's next tile
-    p.sel_depth = (env_int("MXB_TUNE_SEL_DEPTH", 1) == 2 ? 2 : 1) | (env_int("MXB_TUNE_SEL_L2AHEAD", 0) ? 4 : 0);
     return launch(h, k, grid, 256, smem, p, /*coop=*/true);
   }
 

@@ -3817,7 +3817,7 @@ struct SelExchange {
     u32 v = 0;
     if (on) {
       SL::Word w = SL::peek(slots, i);
-      while (!SL::ready(w, tag)) { __nanosleep(20); w = SL::peek(slots, i); }
+      while (!SL::ready(w, tag)) { __nanosleep(64); w = SL::peek(slots, i); }
       v = SL::value(w);
     }
     return v;
@@ -3852,31 +3852,50 @@ struct SelExchange {
     if (on_b) wb = SL::peek(gagg, gfirst + lane);
     if (on_c) wc = SL::peek(run, sg);
     u32 v = 0;
-    if (on_a) { while (!SL::ready(wa, tag)) { __nanosleep(20); wa = SL::peek(agg, first + lane); } v += SL::value(wa); }
-    if (on_b) { while (!SL::ready(wb, tag)) { __nanosleep(20); wb = SL::peek(gagg, gfirst + lane); } v += SL::value(wb); }
-    if (on_c) { while (!SL::ready(wc, tag)) { __nanosleep(20); wc = SL::peek(run, sg); } v += SL::value(wc); }
+    if (on_a) { while (!SL::ready(wa, tag)) { __nanosleep(64); wa = SL::peek(agg, first + lane); } v += SL::value(wa); }
+    if (on_b) { while (!SL::ready(wb, tag)) { __nanosleep(64); wb = SL::peek(gagg, gfirst + lane); } v += SL::value(wb); }
+    if (on_c) { while (!SL::ready(wc, tag)) { __nanosleep(64); wc = SL::peek(run, sg); } v += SL::value(wc); }
     return __reduce_add_sync(0xffffffffu, v);
   }
 };
 
-constexpr int SEL_RING = 9;     // tile states a warp keeps: ranked in iteration i, written in iteration i + 4 * K (K = 1, 2)
+constexpr int SEL_RING = 5;     // tile states a warp keeps: ranked in iteration i, written in iteration i + 4
 constexpr int SEL_WARPS = 8;    // warps per CTA (256 threads)
+constexpr u32 SEL_SPARSE = 96;  // tiles with at most this many selected elements are written by walking the set bits
 template <class T, int V> struct SelGeom {
   // elements per lane and tile: 32 (1024-element warp tiles), 16 for 8-byte values, 8 on the scalar (strided / broadcast) walk
   enum { EPL = V == 1 ? 8 : (sizeof(T) > 4 ? 16 : 32), U = EPL / V, TILE = 32 * EPL,
-         CB = (32 * V <= 255) ? 8 : 16, CPW = 32 / CB, NWORD = (U + CPW - 1) / CPW, NSTATE = 1 + 2 * NWORD };
+         CB = (32 * V <= 255) ? 8 : 16, CPW = 32 / CB, NWORD = (U + CPW - 1) / CPW,   // packed lane counts of the vector rows
+         RSW = (U + 1) / 2,                                                            // packed row starts, 16 bits each
+         NSTATE = 1 + NWORD + RSW };
 };
+
+// predicated store without a branch (the compiler turns `if (p) out[i] = v` into a divergence region per element)
+template <class OutT> __device__ __forceinline__ void st_if(bool p, OutT *addr, OutT v) { if (p) *addr = v; }
+template <> __device__ __forceinline__ void st_if<int>(bool p, int *addr, int v) {
+  asm volatile("{ .reg .pred q; setp.ne.u32 q, %0, 0; @q st.global.u32 [%1], %2; }" ::"r"((u32)p), "l"(addr), "r"(v) : "memory");
+}
+template <> __device__ __forceinline__ void st_if<float>(bool p, float *addr, float v) {
+  asm volatile("{ .reg .pred q; setp.ne.u32 q, %0, 0; @q st.global.f32 [%1], %2; }" ::"r"((u32)p), "l"(addr), "f"(v) : "memory");
+}
+template <> __device__ __forceinline__ void st_if<i64>(bool p, i64 *addr, i64 v) {
+  asm volatile("{ .reg .pred q; setp.ne.u32 q, %0, 0; @q st.global.u64 [%1], %2; }" ::"r"((u32)p), "l"(addr), "l"(v) : "memory");
+}
+template <> __device__ __forceinline__ void st_if<double>(bool p, double *addr, double v) {
+  asm volatile("{ .reg .pred q; setp.ne.u32 q, %0, 0; @q st.global.f64 [%1], %2; }" ::"r"((u32)p), "l"(addr), "d"(v) : "memory");
+}
 
 template <class E, class OutT, int V, int MODE, bool UNIT, int OP>   // MODE 1: values, 2: flat indices; OP < 0: runtime op / unique
 __device__ __forceinline__ void select1p_tiles(const EwParams &p, u32 (*ring)[SEL_RING][SelGeom<typename E::value_type, V>::NSTATE][32]) {
   typedef typename E::value_type T;
   typedef typename E::template Regs<V> R;
   typedef SelGeom<T, V> GEO;
-  constexpr int U = GEO::U, CB = GEO::CB, CPW = GEO::CPW, NWORD = GEO::NWORD;
+  constexpr int U = GEO::U, CB = GEO::CB, CPW = GEO::CPW, NWORD = GEO::NWORD, RSW = GEO::RSW;
   constexpr i64 TILE = GEO::TILE;
   constexpr u32 CMASK = CB == 8 ? 0xffu : 0xffffu;
   constexpr u32 VMASK = V >= 32 ? 0xffffffffu : ((1u << V) - 1u);
-  static_assert(GEO::EPL % V == 0 && U >= 1 && U * V <= 32, "a lane's flags must fit one word");
+  constexpr int VSH = V == 1 ? 0 : V == 2 ? 1 : V == 4 ? 2 : V == 8 ? 3 : V == 16 ? 4 : 5;
+  static_assert(GEO::EPL % V == 0 && U >= 1 && U * V <= 32 && (1 << VSH) == V, "a lane's flags must fit one word");
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const i64 wpc = blockDim.x >> 5;
   const i64 nwarp = (i64)gridDim.x * wpc, gw = (i64)blockIdx.x * wpc + warp;
@@ -3896,25 +3915,11 @@ __device__ __forceinline__ void select1p_tiles(const EwParams &p, u32 (*ring)[SE
   for (int k = 0; k < E::NL; ++k) { base[k] = (const char *)p.leaf[k].ptr; inner[k] = p.leaf[k].bs[0]; }
   OutT *out = (OutT *)p.out.ptr;
   const u32 cap = p.sel_cap > 0xffffffffll ? 0xffffffffu : (u32)p.sel_cap;
+  // ring words of a tile: [0] flags, [1 .. NWORD] exclusive lane counts of the vector rows (packed), then the row starts
+  // inside the tile (16 bits each; row 0 starts at 0, its half-word carries the tile's count instead)
 
-  auto slot_total = [&](int sl) {      // count of the tile whose state sits in ring slot `sl`
-    u32 t = 0;
-#pragma unroll
-    for (int w = 0; w < NWORD; ++w) {
-      const u32 x = ring[warp][sl][1 + NWORD + w][lane];
-#pragma unroll
-      for (int c = 0; c < CPW; ++c) if (w * CPW + c < U) t += (x >> (CB * c)) & CMASK;
-    }
-    return t;
-  };
-
-  // distance between a tile's jobs in iterations (1 or 2): at 2 the warps may drift an iteration apart without waiting
-  const int K = (p.sel_depth & 3) == 2 ? 2 : 1;
-  const int RN = 4 * K + 1;                           // ring slots in use
-  const bool l2_ahead = (p.sel_depth & 4) != 0;       // prefetch the next tile of this warp into L2
-  const i64 kw = (i64)K * nwarp;
-  int s0 = 0;   // ring slot of this iteration's tile; the tile of k iterations ago sits in slot (s0 - k) mod RN
-  for (i64 tile = gw; tile - 4 * kw < ntiles; tile += nwarp) {
+  int s0 = 0;   // ring slot of this iteration's tile; the tile of k iterations ago sits in slot (s0 - k) mod SEL_RING
+  for (i64 tile = gw; tile - 4 * nwarp < ntiles; tile += nwarp) {
     const bool p1 = tile < ntiles;
     const i64 t0 = tile * TILE;
     const i64 jl = t0 + (i64)lane * V;              // first element of this lane's vector 0; vector u sits 32 * V further
@@ -3925,34 +3930,20 @@ __device__ __forceinline__ void select1p_tiles(const EwParams &p, u32 (*ring)[SE
 #pragma unroll
       for (int u = 0; u < U; ++u) E::template loadv<V, UNIT>(r[u], base, inner, jl + (i64)u * 32 * V);
     }
-    if (l2_ahead && UNIT && (tile + nwarp + 1) * TILE <= p.N) {
-      // one 128-byte line per lane and leaf: the next tile of this warp waits in L2 when its loads go out
-#pragma unroll
-      for (int k = 0; k < E::NL; ++k) {
-        const char *a = base[k] + ((tile + nwarp) * TILE * E::leaf_bytes(k)) + lane * 128;
-        if (lane * 128 < TILE * E::leaf_bytes(k)) asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
-      }
-    }
-    // ---- exchange jobs of the tiles ranked K, 2K and 3K iterations ago ----
+    // ---- exchange jobs of the tiles ranked 1, 2 and 3 iterations ago ----
     {
-      const int s1 = s0 >= K ? s0 - K : s0 - K + RN;
-      const i64 tb = tile - kw;
-      if (xc.closes_group(tb)) xc.close(tb, slot_total(s1));
-      xc.super(tile - 2 * kw);
-      xc.running(tile - 3 * kw);
+      const int s1 = s0 >= 1 ? s0 - 1 : s0 - 1 + SEL_RING;
+      const i64 tb = tile - nwarp;
+      if (xc.closes_group(tb)) xc.close(tb, ring[warp][s1][1 + NWORD][lane] & 0xffffu);
+      xc.super(tile - 2 * nwarp);
+      xc.running(tile - 3 * nwarp);
     }
-    // ---- the tile ranked 4K iterations ago: its offset ----
-    const i64 td = tile - 4 * kw;
+    // ---- the tile ranked 4 iterations ago: its offset ----
+    const i64 td = tile - 4 * nwarp;
     const bool p4 = td >= 0 && td < ntiles;
-    const int s4 = s0 >= 4 * K ? s0 - 4 * K : s0 - 4 * K + RN;
+    const int s4 = s0 >= 4 ? s0 - 4 : s0 - 4 + SEL_RING;
     u32 off = 0;
-    if (p4) {
-      off = xc.carry(td);
-      if (td == ntiles - 1 && lane == 0) {
-        const unsigned long long all = (unsigned long long)off + slot_total(s4);
-        *p.sel_total = all > 0x7fffffffull ? 0x7fffffff : (int)all;
-      }
-    }
+    if (p4) off = xc.carry(td);
     // ---- rank this iteration's tile ----
     if (p1) {
       u32 f = 0;                                      // bit u * V + v: element (u, v) of this lane is selected
@@ -4029,69 +4020,100 @@ __device__ __forceinline__ void select1p_tiles(const EwParams &p, u32 (*ring)[SE
           if (lane >= d) incl[w] += o;
         }
       }
+      u32 rs[RSW];
+#pragma unroll
+      for (int w = 0; w < RSW; ++w) rs[w] = 0;
       u32 total = 0;
 #pragma unroll
       for (int w = 0; w < NWORD; ++w) {
         const u32 t = __shfl_sync(0xffffffffu, incl[w], 31);
         ring[warp][s0][1 + w][lane] = incl[w] - own_w[w];
-        ring[warp][s0][1 + NWORD + w][lane] = t;
 #pragma unroll
-        for (int c = 0; c < CPW; ++c) if (w * CPW + c < U) total += (t >> (CB * c)) & CMASK;
+        for (int c = 0; c < CPW; ++c) {
+          const int u = w * CPW + c;
+          if (u < U) {
+            if (u > 0) rs[u / 2] |= total << (16 * (u % 2));
+            total += (t >> (CB * c)) & CMASK;
+          }
+        }
       }
+      rs[0] |= total;                                 // row 0 starts at 0: its half-word carries the tile's count
+#pragma unroll
+      for (int w = 0; w < RSW; ++w) ring[warp][s0][1 + NWORD + w][lane] = rs[w];
       ring[warp][s0][0][lane] = f;
       if (lane == 0) ScanSlot<u32>::publish(xc.agg, tile, total, xc.tag);
     }
     // ---- the selected elements of the tile ranked 4 iterations ago go to their final places ----
     if (p4) {
       const u32 f = ring[warp][s4][0][lane];
+      u32 ex[NWORD], rs[RSW];
+#pragma unroll
+      for (int w = 0; w < NWORD; ++w) ex[w] = ring[warp][s4][1 + w][lane];
+#pragma unroll
+      for (int w = 0; w < RSW; ++w) rs[w] = ring[warp][s4][1 + NWORD + w][lane];
+      const u32 cnt = rs[0] & 0xffffu;
+      rs[0] &= 0xffff0000u;
+      if (td == ntiles - 1 && lane == 0) {
+        const unsigned long long all = (unsigned long long)off + cnt;
+        *p.sel_total = all > 0x7fffffffull ? 0x7fffffff : (int)all;
+      }
       const i64 jd = td * TILE + (i64)lane * V;
-      // values: the tile is read again, as vectors, into the registers the ranking has just freed (it went through L2 four
-      // iterations ago) — carrying 32 values per lane across four iterations would cost the occupancy that hides the loads
-      const bool vec_again = MODE == 1 && V > 1 && (td + 1) * TILE <= p.N && __any_sync(0xffffffffu, f != 0);
-      u32 ex[NWORD], tw[NWORD];
+      const bool walk = cnt <= SEL_SPARSE || (MODE == 1 && ((td + 1) * TILE > p.N || V == 1));
+      if (walk) {
+        // few selected elements (or a tile that cannot be read again as vectors): walk the set bits of the lane
+        u32 ff = f;
+        while (ff) {
+          const int bit = __ffs((int)ff) - 1;
+          ff &= ff - 1;
+          const int u = bit >> VSH, v = bit & (V - 1);
+          u32 exw = ex[0], rsw = rs[0];
 #pragma unroll
-      for (int w = 0; w < NWORD; ++w) { ex[w] = ring[warp][s4][1 + w][lane]; tw[w] = ring[warp][s4][1 + NWORD + w][lane]; }
-      u32 row = off;                                  // where vector row u starts in the output
-      constexpr int UH = U >= 2 ? U / 2 : 1;          // the re-read goes in two halves: half the registers
+          for (int w = 1; w < NWORD; ++w) if ((u / CPW) == w) exw = ex[w];
 #pragma unroll
-      for (int h = 0; h < U / UH; ++h) {
-        R r2[UH];
-        if (vec_again) {
-#pragma unroll
-          for (int u = 0; u < UH; ++u) E::template loadv<V, UNIT>(r2[u], base, inner, jd + (i64)(h * UH + u) * 32 * V);
+          for (int w = 1; w < RSW; ++w) if ((u >> 1) == w) rsw = rs[w];
+          const u32 below = (f >> (u << VSH)) & ((1u << v) - 1u);
+          const u32 pos = off + ((rsw >> (16 * (u & 1))) & 0xffffu) + ((exw >> (CB * (u % CPW))) & CMASK) + (u32)__popc(below);
+          const i64 j = jd + (i64)u * 32 * V + v;
+          if (pos < cap) {                            // beyond the capacity: counted, not written
+            if (MODE == 1) {
+              typename E::template Regs<1> r1;
+              E::template loadv<1, false>(r1, base, inner, j);
+              out[pos] = cvt<OutT>(E::template eval<1>(r1, 0, p.c));
+            } else {
+              out[pos] = (OutT)j;
+            }
+          }
         }
+      } else {
+        // many selected elements: every element slot of the tile, predicated stores, no divergence.  Values: the tile is
+        // read again, as vectors, into the registers the ranking has just freed (it went through L2 four iterations ago) —
+        // carrying 32 values per lane across four iterations would cost the occupancy that hides the loads
+        constexpr int UH = U >= 2 ? U / 2 : 1;        // the re-read goes in two halves: half the registers
 #pragma unroll
-        for (int uu = 0; uu < UH; ++uu) {
-          const int u = h * UH + uu;
-          const u32 fu = (f >> (u * V)) & VMASK;
-          if (fu) {
-            u32 pos = row + ((ex[u / CPW] >> (CB * (u % CPW))) & CMASK);   // counts stay below 2^32 (host check)
+        for (int h = 0; h < U / UH; ++h) {
+          R r2[UH];
+          if (MODE == 1) {
+#pragma unroll
+            for (int u = 0; u < UH; ++u) E::template loadv<V, UNIT>(r2[u], base, inner, jd + (i64)(h * UH + u) * 32 * V);
+          }
+#pragma unroll
+          for (int uu = 0; uu < UH; ++uu) {
+            const int u = h * UH + uu;
+            const u32 fu = (f >> (u * V)) & VMASK;
+            u32 pos = off + ((rs[u / 2] >> (16 * (u % 2))) & 0xffffu) + ((ex[u / CPW] >> (CB * (u % CPW))) & CMASK);
             const i64 j0 = jd + (i64)u * 32 * V;
 #pragma unroll
             for (int v = 0; v < V; ++v) {
-              if ((fu >> v) & 1u) {
-                if (pos < cap) {                      // beyond the capacity: counted, not written
-                  if (MODE == 1) {
-                    if (vec_again) {
-                      out[pos] = cvt<OutT>(E::template eval<V>(r2[uu], v, p.c));
-                    } else {
-                      typename E::template Regs<1> r1;
-                      E::template loadv<1, false>(r1, base, inner, j0 + v);
-                      out[pos] = cvt<OutT>(E::template eval<1>(r1, 0, p.c));
-                    }
-                  } else {
-                    out[pos] = (OutT)(j0 + v);
-                  }
-                }
-                ++pos;
-              }
+              const bool on = (fu >> v) & 1u;
+              const OutT val = MODE == 1 ? cvt<OutT>(E::template eval<V>(r2[uu], v, p.c)) : (OutT)(j0 + v);
+              st_if<OutT>(on && pos < cap, out + pos, val);
+              pos += on ? 1u : 0u;
             }
           }
-          row += (tw[u / CPW] >> (CB * (u % CPW))) & CMASK;
         }
       }
     }
-    s0 = s0 + 1 == RN ? 0 : s0 + 1;
+    s0 = s0 + 1 == SEL_RING ? 0 : s0 + 1;
   }
 }
 
