@@ -2269,6 +2269,9 @@ static int find_impl(mxb_handle_t h, const mxb_expr_t *expr_in, int select_op, d
     p.sel_status = (unsigned long long *)lb_region(h, 8);
     p.sel_epoch = h->lb_ctl;
     p.sel_ticket = h->lb_ctl + 1;
+    // low half: back-off between two polls of a slot that is not published yet (ns); high half: tiles with at most this
+    // many selected elements walk their set bits, fuller ones store every element slot under a predicate
+    p.sel_depth = (env_int("MXB_TUNE_SEL_NAP", 200) & 0xffff) | (env_int("MXB_TUNE_SEL_SPARSE", 32) << 16);
     return launch(h, k, grid, 256, smem, p, /*coop=*/true);
   }
 

@@ -3812,12 +3812,13 @@ struct SelExchange {
   unsigned long long *agg, *gagg, *run, *own;
   i64 ntiles;
   u32 tag;
+  u32 nap;     // back-off of a waiting lane between two polls (ns)
   int lane;
   __device__ __forceinline__ u32 get(const unsigned long long *slots, i64 i, bool on) const {
     u32 v = 0;
     if (on) {
       SL::Word w = SL::peek(slots, i);
-      while (!SL::ready(w, tag)) { __nanosleep(64); w = SL::peek(slots, i); }
+      while (!SL::ready(w, tag)) { __nanosleep(nap); w = SL::peek(slots, i); }
       v = SL::value(w);
     }
     return v;
@@ -3852,16 +3853,15 @@ struct SelExchange {
     if (on_b) wb = SL::peek(gagg, gfirst + lane);
     if (on_c) wc = SL::peek(run, sg);
     u32 v = 0;
-    if (on_a) { while (!SL::ready(wa, tag)) { __nanosleep(64); wa = SL::peek(agg, first + lane); } v += SL::value(wa); }
-    if (on_b) { while (!SL::ready(wb, tag)) { __nanosleep(64); wb = SL::peek(gagg, gfirst + lane); } v += SL::value(wb); }
-    if (on_c) { while (!SL::ready(wc, tag)) { __nanosleep(64); wc = SL::peek(run, sg); } v += SL::value(wc); }
+    if (on_a) { while (!SL::ready(wa, tag)) { __nanosleep(nap); wa = SL::peek(agg, first + lane); } v += SL::value(wa); }
+    if (on_b) { while (!SL::ready(wb, tag)) { __nanosleep(nap); wb = SL::peek(gagg, gfirst + lane); } v += SL::value(wb); }
+    if (on_c) { while (!SL::ready(wc, tag)) { __nanosleep(nap); wc = SL::peek(run, sg); } v += SL::value(wc); }
     return __reduce_add_sync(0xffffffffu, v);
   }
 };
 
 constexpr int SEL_RING = 5;     // tile states a warp keeps: ranked in iteration i, written in iteration i + 4
 constexpr int SEL_WARPS = 8;    // warps per CTA (256 threads)
-constexpr u32 SEL_SPARSE = 96;  // tiles with at most this many selected elements are written by walking the set bits
 template <class T, int V> struct SelGeom {
   // elements per lane and tile: 32 (1024-element warp tiles), 16 for 8-byte values, 8 on the scalar (strided / broadcast) walk
   enum { EPL = V == 1 ? 8 : (sizeof(T) > 4 ? 16 : 32), U = EPL / V, TILE = 32 * EPL,
@@ -3909,6 +3909,8 @@ __device__ __forceinline__ void select1p_tiles(const EwParams &p, u32 (*ring)[SE
   SelExchange xc;
   xc.agg = p.sel_status; xc.gagg = xc.agg + ntiles; xc.run = xc.gagg + ngroup; xc.own = xc.run + nsuper + 1;
   xc.ntiles = ntiles; xc.tag = (epoch << 2) | 1u; xc.lane = lane;
+  xc.nap = (u32)(p.sel_depth & 0xffff);
+  const u32 sparse_max = (u32)p.sel_depth >> 16;   // tiles with at most this many selected elements walk their set bits
   const char *base[E::NL];
   i64 inner[E::NL];
 #pragma unroll
@@ -4058,7 +4060,7 @@ __device__ __forceinline__ void select1p_tiles(const EwParams &p, u32 (*ring)[SE
         *p.sel_total = all > 0x7fffffffull ? 0x7fffffff : (int)all;
       }
       const i64 jd = td * TILE + (i64)lane * V;
-      const bool walk = cnt <= SEL_SPARSE || (MODE == 1 && ((td + 1) * TILE > p.N || V == 1));
+      const bool walk = cnt <= sparse_max || (MODE == 1 && ((td + 1) * TILE > p.N || V == 1));
       if (walk) {
         // few selected elements (or a tile that cannot be read again as vectors): walk the set bits of the lane
         u32 ff = f;
