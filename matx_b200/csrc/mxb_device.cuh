@@ -3239,6 +3239,7 @@ __device__ __forceinline__ void scan_tiles_flat_body_impl(const RedParams &p) {
     return (OutT *)p.out.ptr + oo;
   };
   i64 gid = blockIdx.x;
+  const i64 gq = (i64)gridDim.x / tpr, gr = (i64)gridDim.x - gq * tpr;
   if (gid < total_tiles) {
     i64 cb = gid / tpr, ct = gid - cb * tpr;
     OutT *orow = setup_row(cb);
@@ -3308,9 +3309,9 @@ __device__ __forceinline__ void scan_tiles_flat_body_impl(const RedParams &p) {
       if (tid == 0) ScanSlot<T>::publish(agg, ct, total, tag);
       // the NEXT tile's loads go out right behind the publish
       const i64 ng = gid + gridDim.x;
-      const i64 nb = ng < total_tiles ? ng / tpr : p.B;
-      const i64 nt = ng - nb * tpr;
-      const bool more = nb < p.B;
+      i64 nb = cb + gq, nt = ct + gr;          // (row, tile) of gid + gridDim.x without a division in the loop
+      if (nt >= tpr) { nt -= tpr; ++nb; }
+      const bool more = ng < total_tiles;
       OutT *orow_next = orow;
       bool full_next[U];
       if (more) {
@@ -3427,8 +3428,7 @@ __device__ __forceinline__ void scan_tiles_body_impl(const RedParams &p) {
   typename E::template Regs<V> r[U];
   bool full[U];
   i64 loaded_row = -1;
-  auto issue_loads = [&](i64 gid) {
-    const i64 b = gid / tpr, t = gid - b * tpr;
+  auto issue_loads = [&](i64 b, i64 t) {
     if (b != loaded_row) { setup_in(b); loaded_row = b; }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -3437,22 +3437,24 @@ __device__ __forceinline__ void scan_tiles_body_impl(const RedParams &p) {
       if (full[u]) E::template loadv<V, UNIT>(r[u], base, inner, j);
     }
   };
-  if (mine > 0) issue_loads(blockIdx.x);
+  // (row, tile in the row) of this CTA's tiles, stepped by G tiles per iteration without a division in the loop (six 64-bit
+  // divisions and three modulos per iteration were most of the instructions of this kernel)
+  const i64 gq = G / tpr, gr = G - gq * tpr;
+  auto step = [&](i64 &b, i64 &t) { t += gr; b += gq; if (t >= tpr) { t -= tpr; ++b; } };
+  i64 cb = (i64)blockIdx.x / tpr, ct = (i64)blockIdx.x - cb * tpr;   // tile of phase 1 (iteration `it`)
+  i64 b1 = 0, t1 = -1, b2 = 0, t2 = -1;                               // tiles of iterations it - 1 and it - 2 (none yet)
+  i64 cb2 = cb, ct2 = ct;                                             // tile of phase 2 (iteration it - (D - 1))
+  int slot = 0;
+  if (mine > 0) issue_loads(cb, ct);
   for (i64 it = 0; it < mine + D - 1; ++it) {
     const int par = (int)(it & 1);
     const bool p1 = it < mine;
-    const i64 it2 = it - (D - 1);
-    const bool p2 = it2 >= 0;
-    const i64 gid = (i64)blockIdx.x + it * G, gid2 = (i64)blockIdx.x + it2 * G;
-    const int slot = (int)(it % D), slot2 = (int)(((it2 % D) + D) % D);
-    const i64 cb = p1 ? gid / tpr : 0, ct = p1 ? gid - cb * tpr : 0;
-    const i64 cb2 = p2 ? gid2 / tpr : 0, ct2 = p2 ? gid2 - cb2 * tpr : -1;
-    if (warp == 0) {
-      i64 rc = 0, tc = -1, rh = 0, th = -1;
-      if (it >= 1 && it - 1 < mine) { const i64 g1 = gid - G; rc = g1 / tpr; tc = g1 - rc * tpr; }
-      if (it >= 2 && it - 2 < mine) { const i64 g2 = gid - 2 * G; rh = g2 / tpr; th = g2 - rh * tpr; }
-      xc.issue(rc, tc, rh, th, cb2, ct2);
-    }
+    const bool p2 = it >= D - 1;
+    const int slot2 = slot + 1 == D ? 0 : slot + 1;      // (it - (D - 1)) mod D
+    const int slot1 = slot == 0 ? D - 1 : slot - 1;      // (it - 1) mod D
+    if (warp == 0) xc.issue(b1, (it >= 1 && it - 1 < mine) ? t1 : -1, b2, (it >= 2 && it - 2 < mine) ? t2 : -1, cb2, p2 ? ct2 : -1);
+    i64 nb = cb, nt = ct;
+    step(nb, nt);
     if (p1) {
       const i64 j0 = ct * TILE;
       T x[U][V];
@@ -3476,7 +3478,7 @@ __device__ __forceinline__ void scan_tiles_body_impl(const RedParams &p) {
 #pragma unroll
         for (int v = 1; v < V; ++v) x[u][v] = x[u][v - 1] + x[u][v];
       }
-      if (it + 1 < mine) issue_loads(gid + G);   // the next tile's loads fly while this one is scanned and parked
+      if (it + 1 < mine) issue_loads(nb, nt);   // the next tile's loads fly while this one is scanned and parked
       T wexcl[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
@@ -3516,7 +3518,7 @@ __device__ __forceinline__ void scan_tiles_body_impl(const RedParams &p) {
       __syncthreads();   // (A) keeps the barrier count uniform while the pipeline drains
     }
     if (warp == 0) {
-      const T ctot = xc.close_ct >= 0 ? s_tot[(int)((it - 1) % D)] : scan_zero<T>();
+      const T ctot = xc.close_ct >= 0 ? s_tot[slot1] : scan_zero<T>();
       const T cr = xc.finish(ctot);
       if (lane == 0) s_carry[par] = cr;
     }
@@ -3539,7 +3541,12 @@ __device__ __forceinline__ void scan_tiles_body_impl(const RedParams &p) {
           for (int v = 0; v < V; ++v) if (j + v < L) orow[(j + v) * oinner] = o.v[v];
         }
       }
+      step(cb2, ct2);
     }
+    b2 = b1; t2 = t1;
+    b1 = cb; t1 = ct;
+    cb = nb; ct = nt;
+    slot = slot + 1 == D ? 0 : slot + 1;
   }
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   // exit ticket: the last CTA out opens the next epoch (every slot of this launch is stale from then on)
