@@ -1139,10 +1139,18 @@ __device__ __forceinline__ void dyn_fold(const RedParams &p, i64 nfold, typename
   __threadfence();
   const acc_t *ws = (const acc_t *)p.ws;
   if (p.B == 1) {
-    // four independent loads per trip: the fold is one CTA against L2 latency
+    // independent loads per trip: the fold is one CTA against L2 latency
     acc_t a = Op::init();
     const i64 nt = blockDim.x;
     i64 i = threadIdx.x;
+    // eight loads in flight per trip (the states here are one or two words): a 512 MB slab leaves 4096 partials, two trips
+    for (; i + 7 * nt < nfold; i += 8 * nt) {
+      acc_t x[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) x[k] = ld_cg_t(&ws[i + k * nt]);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) Op::merge(a, x[k]);
+    }
     for (; i + 3 * nt < nfold; i += 4 * nt) {
       const acc_t x0 = ld_cg_t(&ws[i]), x1 = ld_cg_t(&ws[i + nt]), x2 = ld_cg_t(&ws[i + 2 * nt]), x3 = ld_cg_t(&ws[i + 3 * nt]);
       Op::merge(a, x0); Op::merge(a, x1); Op::merge(a, x2); Op::merge(a, x3);

@@ -394,6 +394,10 @@ static void run_bench() {
     line("C2 fp32 2^30", "sum", n * 4.0, time_ms(stream, 10, [&] { (s = sum(x)).run(ref); }), time_ms(stream, 10, [&] { (s = sum(x)).run(b200); }));
     line("C2 fp32 2^30", "max", n * 4.0, time_ms(stream, 10, [&] { (s = max(x)).run(ref); }), time_ms(stream, 10, [&] { (s = max(x)).run(b200); }));
     line("C2 fp32 2^30", "argmax", n * 4.0, time_ms(stream, 10, [&] { (mtie(s, i) = argmax(x)).run(ref); }), time_ms(stream, 10, [&] { (mtie(s, i) = argmax(x)).run(b200); }));
+    auto s2 = make_tensor<float>({}, MATX_DEVICE_MEMORY);
+    auto i2 = make_tensor<index_t>({}, MATX_DEVICE_MEMORY);
+    line("C2 fp32 2^30", "argminmax", n * 4.0, time_ms(stream, 5, [&] { (mtie(s, i, s2, i2) = argminmax(x)).run(ref); }),
+         time_ms(stream, 10, [&] { (mtie(s, i, s2, i2) = argminmax(x)).run(b200); }));
   }
   {  // C1
     const index_t rows = 16384, cols = 4096;
@@ -466,6 +470,35 @@ static void run_bench() {
          time_ms(stream, 5, [&] { (mtie(fo, nf) = find(fx, GT<float>{0.99f})).run(b200); }));
     line("find fp32 2^28 (50 % selected)", "mtie(out, n) = find(x, GT{0.5})", 4.0 * n * 1.5, time_ms(stream, 3, [&] { (mtie(fo, nf) = find(fx, GT<float>{0.5f})).run(ref); }),
          time_ms(stream, 5, [&] { (mtie(fo, nf) = find(fx, GT<float>{0.5f})).run(b200); }));
+    auto fi = make_tensor<index_t>({n}, MATX_DEVICE_MEMORY);
+    line("find_idx fp32 2^28 (1 % selected)", "mtie(idx, n) = find_idx(x, GT{0.99})", 4.0 * n + 8.0 * n * 0.01, time_ms(stream, 3, [&] { (mtie(fi, nf) = find_idx(fx, GT<float>{0.99f})).run(ref); }),
+         time_ms(stream, 5, [&] { (mtie(fi, nf) = find_idx(fx, GT<float>{0.99f})).run(b200); }));
+    line("find_idx fp32 2^28 (50 % selected)", "mtie(idx, n) = find_idx(x, GT{0.5})", 4.0 * n + 8.0 * n * 0.5, time_ms(stream, 3, [&] { (mtie(fi, nf) = find_idx(fx, GT<float>{0.5f})).run(ref); }),
+         time_ms(stream, 5, [&] { (mtie(fi, nf) = find_idx(fx, GT<float>{0.5f})).run(b200); }));
+  }
+  {  // sort / unique / hist: the rank-3 neighbours beside cub::DeviceRadixSort / DeviceSelect::Unique / DeviceHistogram
+    const index_t n = index_t(1) << 24;
+    auto x = make_tensor<float>({n}, MATX_DEVICE_MEMORY), y = make_tensor<float>({n}, MATX_DEVICE_MEMORY);
+    (x = random<float>({n}, UNIFORM)).run(ref);
+    line("sort fp32 2^24", "y = sort(x, SORT_DIR_ASC)", 2.0 * 4 * n, time_ms(stream, 3, [&] { (y = matx::sort(x, SORT_DIR_ASC)).run(ref); }),
+         time_ms(stream, 3, [&] { (y = matx::sort(x, SORT_DIR_ASC)).run(b200); }));
+    auto m = make_tensor<float>({16384, 1024}, MATX_DEVICE_MEMORY), ms = make_tensor<float>({16384, 1024}, MATX_DEVICE_MEMORY);
+    (m = random<float>({16384, 1024}, UNIFORM)).run(ref);
+    line("sort fp32 16384x1024", "ms = sort(m, SORT_DIR_ASC) (rows)", 2.0 * 4 * 16384 * 1024, time_ms(stream, 2, [&] { (ms = matx::sort(m, SORT_DIR_ASC)).run(ref); }),
+         time_ms(stream, 3, [&] { (ms = matx::sort(m, SORT_DIR_ASC)).run(b200); }));
+    auto q = make_tensor<float>({n}, MATX_DEVICE_MEMORY);
+    (q = floor(x * 1000.f)).run(ref);
+    auto nu = make_tensor<int>({}, MATX_DEVICE_MEMORY);
+    line("unique fp32 2^24 (1000 distinct)", "mtie(u, n) = unique(q)", 3.0 * 4 * n, time_ms(stream, 3, [&] { (mtie(y, nu) = unique(q)).run(ref); }),
+         time_ms(stream, 3, [&] { (mtie(y, nu) = unique(q)).run(b200); }));
+#ifdef MXB_OVERLAY
+    const index_t nh = index_t(1) << 28;
+    auto hx = make_tensor<float>({nh}, MATX_DEVICE_MEMORY);
+    (hx = random<float>({nh}, UNIFORM)).run(ref);
+    auto hb = make_tensor<int>({256}, MATX_DEVICE_MEMORY);
+    line("hist fp32 2^28, 256 bins", "h = hist(x, 0, 1, 257)", 4.0 * nh, time_ms(stream, 3, [&] { (hb = hist(hx, 0.0f, 1.0f, 257)).run(ref); }),
+         time_ms(stream, 5, [&] { (hb = hist(hx, 0.0f, 1.0f, 257)).run(b200); }));
+#endif
   }
   {  // C5
     const index_t d = 1024;
