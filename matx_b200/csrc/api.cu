@@ -59,6 +59,15 @@ struct mxb_context {
   void *lb_status = nullptr;
   size_t lb_cap_tiles = 0;
   unsigned *lb_ctl = nullptr;   // [0] epoch (starts at 1), [1] exit ticket
+  // tensor maps of the TMA-tiled column reductions, keyed by everything the encoder sees: a repeated statement costs a
+  // 96-byte compare instead of a driver call (round-robin over a few entries; maps are plain values, nothing to release)
+  struct TmapEntry {
+    unsigned long long key[12];
+    CUtensorMap map;
+    bool used = false;
+  };
+  TmapEntry tmaps[8];
+  int tmap_next = 0;
 };
 
 namespace {
@@ -602,10 +611,22 @@ int reduce_launch(mxb_context *h, int kop, const mxb_expr_t &e, const ExprInfo &
         const cuuint32_t estr[3] = {1u, 1u, 1u};
         const int l2p = env_int("MXB_TUNE_OT_L2PROMO", 2);
         const bool fits = gdim[0] < (1ull << 31) && gdim[1] < (1ull << 31) && gdim[2] < (1ull << 31) && gstr[0] < (1ull << 40) && gstr[1] < (1ull << 40);
-        if (fits && enc(&ot_map, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, const_cast<void *>(e.leaves[0].data), gdim, gstr, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, (CUtensorMapL2promotion)l2p,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
-          have_map = true;
+        if (fits) {
+          const unsigned long long key[12] = {(unsigned long long)(uintptr_t)e.leaves[0].data, gdim[0], gdim[1], gdim[2], gstr[0], gstr[1],
+                                              box[0], box[1], box[2], (unsigned long long)l2p, 3ull, (unsigned long long)CU_TENSOR_MAP_DATA_TYPE_UINT64};
+          for (auto &t : h->tmaps)
+            if (t.used && !memcmp(t.key, key, sizeof key)) { ot_map = t.map; have_map = true; break; }
+          if (!have_map && enc(&ot_map, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, const_cast<void *>(e.leaves[0].data), gdim, gstr, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, (CUtensorMapL2promotion)l2p,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS) {
+            have_map = true;
+            auto &t = h->tmaps[h->tmap_next];
+            h->tmap_next = (h->tmap_next + 1) % 8;
+            memcpy(t.key, key, sizeof key);
+            t.map = ot_map;
+            t.used = true;
+          }
+        }
       }
       if (g_plan && want_mode != 0 && st >= 2) have_map = true;   // plan only: assume the driver encodes the map, as on the B200 box
       const bool contiguous_strips = pitch == C * esz && cv <= ot_tx;   // one bulk copy per stage
@@ -2255,9 +2276,9 @@ static int find_impl(mxb_handle_t h, const mxb_expr_t *expr_in, int select_op, d
     spec.out_dtype = out->dtype;
     st = get_kernel(info, spec, &k);
     if (st != MXB_OK) return st;
-    // warp tiles of 32 lanes x 32 elements (16 for 8-byte values), dealt round-robin to the warps of a grid that is
+    // warp tiles of 32 lanes x 64 elements (32 for 8-byte values, 8 on the scalar walk), dealt round-robin to the warps of a grid that is
     // resident as a whole (cooperative launch: a tile only waits for tiles whose warps are running)
-    const int64_t wtile = 32 * (V == 1 ? 8 : (dtype_bytes(info.value_dtype) > 4 ? 16 : 32));   // SelGeom::TILE (mxb_device.cuh)
+    const int64_t wtile = 32 * (V == 1 ? 8 : (dtype_bytes(info.value_dtype) > 4 ? 32 : 64));   // SelGeom::TILE (mxb_device.cuh)
     const int64_t nwt = (N + wtile - 1) / wtile;
     const unsigned smem = 0;
     const int res = resident_ctas(k, 256, smem, 4);
@@ -2271,7 +2292,9 @@ static int find_impl(mxb_handle_t h, const mxb_expr_t *expr_in, int select_op, d
     p.sel_ticket = h->lb_ctl + 1;
     // low half: back-off between two polls of a slot that is not published yet (ns); high half: tiles with at most this
     // many selected elements walk their set bits, fuller ones store every element slot under a predicate
-    p.sel_depth = (env_int("MXB_TUNE_SEL_NAP", 200) & 0xffff) | (env_int("MXB_TUNE_SEL_SPARSE", 32) << 16);
+    // (2048-element tiles, profiles/r2_find_warp_tiles_sweep.jsonl: indices walk up to a quarter of the tile, values — whose
+    // walk re-reads one element per set bit — up to 5 %)
+    p.sel_depth = (env_int("MXB_TUNE_SEL_NAP", 200) & 0xffff) | (env_int("MXB_TUNE_SEL_SPARSE", want_indices ? 512 : 96) << 16);
     return launch(h, k, grid, 256, smem, p, /*coop=*/true);
   }
 

@@ -3878,11 +3878,13 @@ struct SelExchange {
 constexpr int SEL_RING = 5;     // tile states a warp keeps: ranked in iteration i, written in iteration i + 4
 constexpr int SEL_WARPS = 8;    // warps per CTA (256 threads)
 template <class T, int V> struct SelGeom {
-  // elements per lane and tile: 32 (1024-element warp tiles), 16 for 8-byte values, 8 on the scalar (strided / broadcast) walk
-  enum { EPL = V == 1 ? 8 : (sizeof(T) > 4 ? 16 : 32), U = EPL / V, TILE = 32 * EPL,
+  // elements per lane and tile: 64 (2048-element warp tiles, read as two halves of eight 16-byte loads), 32 for 8-byte
+  // values, 8 on the scalar (strided / broadcast) walk
+  enum { EPL = V == 1 ? 8 : (sizeof(T) > 4 ? 32 : 64), U = EPL / V, UH = U / 2, TILE = 32 * EPL,
          CB = (32 * V <= 255) ? 8 : 16, CPW = 32 / CB, NWORD = (U + CPW - 1) / CPW,   // packed lane counts of the vector rows
-         RSW = (U + 1) / 2,                                                            // packed row starts, 16 bits each
-         NSTATE = 1 + NWORD + RSW };
+         FW = (U * V + 31) / 32,                                                       // flag words per lane
+         RSW = (U + 1) / 2,                                                            // packed row starts, 16 bits each (per warp)
+         LANE_WORDS = FW + NWORD, SLOT_WORDS = LANE_WORDS * 32 + RSW + 1 };
 };
 
 // predicated store without a branch (the compiler turns `if (p) out[i] = v` into a divergence region per element)
@@ -3901,16 +3903,17 @@ template <> __device__ __forceinline__ void st_if<double>(bool p, double *addr, 
 }
 
 template <class E, class OutT, int V, int MODE, bool UNIT, int OP>   // MODE 1: values, 2: flat indices; OP < 0: runtime op / unique
-__device__ __forceinline__ void select1p_tiles(const EwParams &p, u32 (*ring)[SEL_RING][SelGeom<typename E::value_type, V>::NSTATE][32]) {
+__device__ __forceinline__ void select1p_tiles(const EwParams &p, u32 *ring_all) {
   typedef typename E::value_type T;
   typedef typename E::template Regs<V> R;
   typedef SelGeom<T, V> GEO;
-  constexpr int U = GEO::U, CB = GEO::CB, CPW = GEO::CPW, NWORD = GEO::NWORD, RSW = GEO::RSW;
+  constexpr int U = GEO::U, UH = GEO::UH, CB = GEO::CB, CPW = GEO::CPW, NWORD = GEO::NWORD, RSW = GEO::RSW, FW = GEO::FW;
   constexpr i64 TILE = GEO::TILE;
   constexpr u32 CMASK = CB == 8 ? 0xffu : 0xffffu;
   constexpr u32 VMASK = V >= 32 ? 0xffffffffu : ((1u << V) - 1u);
   constexpr int VSH = V == 1 ? 0 : V == 2 ? 1 : V == 4 ? 2 : V == 8 ? 3 : V == 16 ? 4 : 5;
-  static_assert(GEO::EPL % V == 0 && U >= 1 && U * V <= 32 && (1 << VSH) == V, "a lane's flags must fit one word");
+  constexpr int RPW = 32 / V;                         // vector rows per flag word
+  static_assert(U % 2 == 0 && UH >= 1 && (1 << VSH) == V && (U * V) % 32 == 0 || U * V < 32, "tile geometry");
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const i64 wpc = blockDim.x >> 5;
   const i64 nwarp = (i64)gridDim.x * wpc, gw = (i64)blockIdx.x * wpc + warp;
@@ -3932,8 +3935,10 @@ __device__ __forceinline__ void select1p_tiles(const EwParams &p, u32 (*ring)[SE
   for (int k = 0; k < E::NL; ++k) { base[k] = (const char *)p.leaf[k].ptr; inner[k] = p.leaf[k].bs[0]; }
   OutT *out = (OutT *)p.out.ptr;
   const u32 cap = p.sel_cap > 0xffffffffll ? 0xffffffffu : (u32)p.sel_cap;
-  // ring words of a tile: [0] flags, [1 .. NWORD] exclusive lane counts of the vector rows (packed), then the row starts
-  // inside the tile (16 bits each; row 0 starts at 0, its half-word carries the tile's count instead)
+  // ring slot of a tile, per warp: per-lane words [w][lane] — flag words, then the exclusive lane counts of the vector
+  // rows (packed) — followed by words every lane shares: the rows' starts inside the tile (16 bits each) and the tile's count
+  u32 *wring = ring_all + (size_t)warp * SEL_RING * GEO::SLOT_WORDS;
+  auto slot_ptr = [&](int sl) { return wring + (size_t)sl * GEO::SLOT_WORDS; };
 
   int s0 = 0;   // ring slot of this iteration's tile; the tile of k iterations ago sits in slot (s0 - k) mod SEL_RING
   for (i64 tile = gw; tile - 4 * nwarp < ntiles; tile += nwarp) {
@@ -3941,17 +3946,17 @@ __device__ __forceinline__ void select1p_tiles(const EwParams &p, u32 (*ring)[SE
     const i64 t0 = tile * TILE;
     const i64 jl = t0 + (i64)lane * V;              // first element of this lane's vector 0; vector u sits 32 * V further
     const bool fast = OP >= 0 && p1 && t0 + TILE <= p.N;
-    // ---- this iteration's loads go out first: the exchange jobs below run under their latency ----
-    R r[U];
+    // ---- the loads of the tile's first half go out first: the exchange jobs below run under their latency ----
+    R r[UH];
     if (fast) {
 #pragma unroll
-      for (int u = 0; u < U; ++u) E::template loadv<V, UNIT>(r[u], base, inner, jl + (i64)u * 32 * V);
+      for (int u = 0; u < UH; ++u) E::template loadv<V, UNIT>(r[u], base, inner, jl + (i64)u * 32 * V);
     }
     // ---- exchange jobs of the tiles ranked 1, 2 and 3 iterations ago ----
     {
       const int s1 = s0 >= 1 ? s0 - 1 : s0 - 1 + SEL_RING;
       const i64 tb = tile - nwarp;
-      if (xc.closes_group(tb)) xc.close(tb, ring[warp][s1][1 + NWORD][lane] & 0xffffu);
+      if (xc.closes_group(tb)) xc.close(tb, slot_ptr(s1)[GEO::LANE_WORDS * 32 + RSW]);
       xc.super(tile - 2 * nwarp);
       xc.running(tile - 3 * nwarp);
     }
@@ -3961,18 +3966,97 @@ __device__ __forceinline__ void select1p_tiles(const EwParams &p, u32 (*ring)[SE
     const int s4 = s0 >= 4 ? s0 - 4 : s0 - 4 + SEL_RING;
     u32 off = 0;
     if (p4) off = xc.carry(td);
-    // ---- rank this iteration's tile ----
-    if (p1) {
-      u32 f = 0;                                      // bit u * V + v: element (u, v) of this lane is selected
-      if (fast) {
-        // a full tile (all but the last): no bounds, the predicate is a compile-time functor
+    // ---- flags of this iteration's tile: first half, then the second half's loads, which fly through the write below ----
+    u32 f[FW];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
+    for (int w = 0; w < FW; ++w) f[w] = 0;
+    auto flags_fast = [&](int h) {
 #pragma unroll
-          for (int v = 0; v < V; ++v) {
-            if (SelPred<OP < 0 ? 0 : OP>::test(E::template eval<V>(r[u], v, p.c), thr)) f |= 1u << (u * V + v);
+      for (int uu = 0; uu < UH; ++uu) {
+        const int u = h * UH + uu;
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          if (SelPred<OP < 0 ? 0 : OP>::test(E::template eval<V>(r[uu], v, p.c), thr)) f[(u * V + v) / 32] |= 1u << ((u * V + v) % 32);
+        }
+      }
+    };
+    if (fast) {
+      flags_fast(0);
+#pragma unroll
+      for (int u = 0; u < UH; ++u) E::template loadv<V, UNIT>(r[u], base, inner, jl + (i64)(UH + u) * 32 * V);
+    }
+    // ---- the selected elements of the tile ranked 4 iterations ago go to their final places ----
+    if (p4) {
+      const u32 *sp = slot_ptr(s4);
+      const u32 *shared_words = sp + GEO::LANE_WORDS * 32;
+      const u32 cnt = shared_words[RSW];
+      if (td == ntiles - 1 && lane == 0) {
+        const unsigned long long all = (unsigned long long)off + cnt;
+        *p.sel_total = all > 0x7fffffffull ? 0x7fffffff : (int)all;
+      }
+      const i64 jd = td * TILE + (i64)lane * V;
+      const bool walk = cnt <= sparse_max || (MODE == 1 && ((td + 1) * TILE > p.N || V == 1));
+      if (walk) {
+        // few selected elements (or a tile that cannot be read again as vectors): walk the set bits of the lane; the
+        // row's start and the lane's exclusive count come straight from the ring
+#pragma unroll
+        for (int w = 0; w < FW; ++w) {
+          const u32 fw = sp[w * 32 + lane];
+          u32 ff = fw;
+          while (ff) {
+            const int bit = __ffs((int)ff) - 1;
+            ff &= ff - 1;
+            const int u = w * RPW + (bit >> VSH), v = bit & (V - 1);
+            const u32 exw = sp[(FW + u / CPW) * 32 + lane];
+            const u32 rsw = shared_words[u >> 1];
+            const u32 below = (fw >> ((bit >> VSH) << VSH)) & ((1u << v) - 1u);
+            const u32 pos = off + ((rsw >> (16 * (u & 1))) & 0xffffu) + ((exw >> (CB * (u % CPW))) & CMASK) + (u32)__popc(below);
+            const i64 j = jd + (i64)u * 32 * V + v;
+            if (pos < cap) {                            // beyond the capacity: counted, not written
+              if (MODE == 1) {
+                typename E::template Regs<1> r1;
+                E::template loadv<1, false>(r1, base, inner, j);
+                out[pos] = cvt<OutT>(E::template eval<1>(r1, 0, p.c));
+              } else {
+                out[pos] = (OutT)j;
+              }
+            }
           }
         }
+      } else {
+        // many selected elements: every element slot of the tile, predicated stores, no divergence.  Values: the tile is
+        // read again, as vectors (it went through L2 four iterations ago) — carrying its values across four iterations
+        // would cost the occupancy that hides the loads
+        constexpr int UQ = UH >= 2 ? UH / 2 : 1;      // the re-read goes in quarters of the tile: a quarter of the registers
+#pragma unroll
+        for (int q = 0; q < U / UQ; ++q) {
+          R r2[UQ];
+          if (MODE == 1) {
+#pragma unroll
+            for (int u = 0; u < UQ; ++u) E::template loadv<V, UNIT>(r2[u], base, inner, jd + (i64)(q * UQ + u) * 32 * V);
+          }
+#pragma unroll
+          for (int uu = 0; uu < UQ; ++uu) {
+            const int u = q * UQ + uu;
+            const u32 fu = (sp[((u * V) / 32) * 32 + lane] >> ((u * V) % 32)) & VMASK;
+            const u32 exw = sp[(FW + u / CPW) * 32 + lane];
+            u32 pos = off + ((shared_words[u / 2] >> (16 * (u % 2))) & 0xffffu) + ((exw >> (CB * (u % CPW))) & CMASK);
+            const i64 j0 = jd + (i64)u * 32 * V;
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+              const bool on = (fu >> v) & 1u;
+              const OutT val = MODE == 1 ? cvt<OutT>(E::template eval<V>(r2[uu], v, p.c)) : (OutT)(j0 + v);
+              st_if<OutT>(on && pos < cap, out + pos, val);
+              pos += on ? 1u : 0u;
+            }
+          }
+        }
+      }
+    }
+    // ---- rank this iteration's tile ----
+    if (p1) {
+      if (fast) {
+        flags_fast(1);
       } else {
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -4018,7 +4102,7 @@ __device__ __forceinline__ void select1p_tiles(const EwParams &p, u32 (*ring)[SE
               }
             }
           }
-          f |= fu << (u * V);
+          f[(u * V) / 32] |= fu << ((u * V) % 32);
         }
       }
       // ranks: packed per-vector counts through shuffle scans; the per-vector totals of the warp come from lane 31
@@ -4026,7 +4110,7 @@ __device__ __forceinline__ void select1p_tiles(const EwParams &p, u32 (*ring)[SE
 #pragma unroll
       for (int w = 0; w < NWORD; ++w) own_w[w] = 0;
 #pragma unroll
-      for (int u = 0; u < U; ++u) own_w[u / CPW] |= (u32)__popc((f >> (u * V)) & VMASK) << (CB * (u % CPW));
+      for (int u = 0; u < U; ++u) own_w[u / CPW] |= (u32)__popc((f[(u * V) / 32] >> ((u * V) % 32)) & VMASK) << (CB * (u % CPW));
 #pragma unroll
       for (int w = 0; w < NWORD; ++w) incl[w] = own_w[w];
 #pragma unroll
@@ -4037,6 +4121,7 @@ __device__ __forceinline__ void select1p_tiles(const EwParams &p, u32 (*ring)[SE
           if (lane >= d) incl[w] += o;
         }
       }
+      u32 *sp = slot_ptr(s0);
       u32 rs[RSW];
 #pragma unroll
       for (int w = 0; w < RSW; ++w) rs[w] = 0;
@@ -4044,91 +4129,25 @@ __device__ __forceinline__ void select1p_tiles(const EwParams &p, u32 (*ring)[SE
 #pragma unroll
       for (int w = 0; w < NWORD; ++w) {
         const u32 t = __shfl_sync(0xffffffffu, incl[w], 31);
-        ring[warp][s0][1 + w][lane] = incl[w] - own_w[w];
+        sp[(FW + w) * 32 + lane] = incl[w] - own_w[w];
 #pragma unroll
         for (int c = 0; c < CPW; ++c) {
           const int u = w * CPW + c;
           if (u < U) {
-            if (u > 0) rs[u / 2] |= total << (16 * (u % 2));
+            rs[u / 2] |= total << (16 * (u % 2));
             total += (t >> (CB * c)) & CMASK;
           }
         }
       }
-      rs[0] |= total;                                 // row 0 starts at 0: its half-word carries the tile's count
 #pragma unroll
-      for (int w = 0; w < RSW; ++w) ring[warp][s0][1 + NWORD + w][lane] = rs[w];
-      ring[warp][s0][0][lane] = f;
-      if (lane == 0) ScanSlot<u32>::publish(xc.agg, tile, total, xc.tag);
-    }
-    // ---- the selected elements of the tile ranked 4 iterations ago go to their final places ----
-    if (p4) {
-      const u32 f = ring[warp][s4][0][lane];
-      u32 ex[NWORD], rs[RSW];
+      for (int w = 0; w < FW; ++w) sp[w * 32 + lane] = f[w];
+      if (lane == 0) {
 #pragma unroll
-      for (int w = 0; w < NWORD; ++w) ex[w] = ring[warp][s4][1 + w][lane];
-#pragma unroll
-      for (int w = 0; w < RSW; ++w) rs[w] = ring[warp][s4][1 + NWORD + w][lane];
-      const u32 cnt = rs[0] & 0xffffu;
-      rs[0] &= 0xffff0000u;
-      if (td == ntiles - 1 && lane == 0) {
-        const unsigned long long all = (unsigned long long)off + cnt;
-        *p.sel_total = all > 0x7fffffffull ? 0x7fffffff : (int)all;
+        for (int w = 0; w < RSW; ++w) sp[GEO::LANE_WORDS * 32 + w] = rs[w];
+        sp[GEO::LANE_WORDS * 32 + RSW] = total;
+        ScanSlot<u32>::publish(xc.agg, tile, total, xc.tag);
       }
-      const i64 jd = td * TILE + (i64)lane * V;
-      const bool walk = cnt <= sparse_max || (MODE == 1 && ((td + 1) * TILE > p.N || V == 1));
-      if (walk) {
-        // few selected elements (or a tile that cannot be read again as vectors): walk the set bits of the lane
-        u32 ff = f;
-        while (ff) {
-          const int bit = __ffs((int)ff) - 1;
-          ff &= ff - 1;
-          const int u = bit >> VSH, v = bit & (V - 1);
-          u32 exw = ex[0], rsw = rs[0];
-#pragma unroll
-          for (int w = 1; w < NWORD; ++w) if ((u / CPW) == w) exw = ex[w];
-#pragma unroll
-          for (int w = 1; w < RSW; ++w) if ((u >> 1) == w) rsw = rs[w];
-          const u32 below = (f >> (u << VSH)) & ((1u << v) - 1u);
-          const u32 pos = off + ((rsw >> (16 * (u & 1))) & 0xffffu) + ((exw >> (CB * (u % CPW))) & CMASK) + (u32)__popc(below);
-          const i64 j = jd + (i64)u * 32 * V + v;
-          if (pos < cap) {                            // beyond the capacity: counted, not written
-            if (MODE == 1) {
-              typename E::template Regs<1> r1;
-              E::template loadv<1, false>(r1, base, inner, j);
-              out[pos] = cvt<OutT>(E::template eval<1>(r1, 0, p.c));
-            } else {
-              out[pos] = (OutT)j;
-            }
-          }
-        }
-      } else {
-        // many selected elements: every element slot of the tile, predicated stores, no divergence.  Values: the tile is
-        // read again, as vectors, into the registers the ranking has just freed (it went through L2 four iterations ago) —
-        // carrying 32 values per lane across four iterations would cost the occupancy that hides the loads
-        constexpr int UH = U >= 2 ? U / 2 : 1;        // the re-read goes in two halves: half the registers
-#pragma unroll
-        for (int h = 0; h < U / UH; ++h) {
-          R r2[UH];
-          if (MODE == 1) {
-#pragma unroll
-            for (int u = 0; u < UH; ++u) E::template loadv<V, UNIT>(r2[u], base, inner, jd + (i64)(h * UH + u) * 32 * V);
-          }
-#pragma unroll
-          for (int uu = 0; uu < UH; ++uu) {
-            const int u = h * UH + uu;
-            const u32 fu = (f >> (u * V)) & VMASK;
-            u32 pos = off + ((rs[u / 2] >> (16 * (u % 2))) & 0xffffu) + ((ex[u / CPW] >> (CB * (u % CPW))) & CMASK);
-            const i64 j0 = jd + (i64)u * 32 * V;
-#pragma unroll
-            for (int v = 0; v < V; ++v) {
-              const bool on = (fu >> v) & 1u;
-              const OutT val = MODE == 1 ? cvt<OutT>(E::template eval<V>(r2[uu], v, p.c)) : (OutT)(j0 + v);
-              st_if<OutT>(on && pos < cap, out + pos, val);
-              pos += on ? 1u : 0u;
-            }
-          }
-        }
-      }
+      __syncwarp();
     }
     s0 = s0 + 1 == SEL_RING ? 0 : s0 + 1;
   }
@@ -4137,8 +4156,8 @@ __device__ __forceinline__ void select1p_tiles(const EwParams &p, u32 (*ring)[SE
 template <class E, class OutT, int V, int MODE>
 __device__ __forceinline__ void select1p_body(const EwParams &p) {
   pdl_prologue();
-  // per-warp ring of tile states, one column per lane: flags, exclusive packed counts, packed totals of the warp
-  __shared__ u32 ring[SEL_WARPS][SEL_RING][SelGeom<typename E::value_type, V>::NSTATE][32];
+  // per-warp ring of tile states (SelGeom::SLOT_WORDS per tile)
+  __shared__ u32 ring[SEL_WARPS * SEL_RING * SelGeom<typename E::value_type, V>::SLOT_WORDS];
   const bool unit = p.all_unit != 0;
   if (V > 1 || unit) {
     // V > 1 is only ever launched over unit-stride leaves
