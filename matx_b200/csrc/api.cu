@@ -2281,7 +2281,7 @@ static int find_impl(mxb_handle_t h, const mxb_expr_t *expr_in, int select_op, d
     const int64_t wtile = 32 * (V == 1 ? 8 : (dtype_bytes(info.value_dtype) > 4 ? 32 : 64));   // SelGeom::TILE (mxb_device.cuh)
     const int64_t nwt = (N + wtile - 1) / wtile;
     const unsigned smem = 0;
-    const int res = resident_ctas(k, 256, smem, 4);
+    const int res = resident_ctas(k, 256, smem, 3);
     const int cps = env_int("MXB_TUNE_SEL_CTAS", 0) > 0 ? std::min(env_int("MXB_TUNE_SEL_CTAS", 0), res) : res;
     const unsigned grid = (unsigned)std::min<int64_t>((nwt + 7) / 8, (int64_t)h->sm_count * cps);
     // status words: tile counts | group counts | running counts at supergroup starts | supergroup counts
@@ -2488,14 +2488,15 @@ int sort_rows_typed(mxb_context *h, const void *in, void *out, int kind, int64_t
   p.chunk = chunk;
   int st = ensure_buf(h, &h->tmp, &h->tmp_bytes, (size_t)(B * L) * sizeof(K));
   if (st != MXB_OK) return st;
-  const size_t words = (size_t)(B * cpr) * 256;
-  if (2 * words > h->sort_ctr_words) {
+  const size_t words = (size_t)(B * cpr) * 256, tot_words = (size_t)B * 256;
+  if (2 * words + tot_words > h->sort_ctr_words) {
     if (h->sort_ctr) MXB_CUDA(cudaFreeAsync(h->sort_ctr, h->stream));
-    MXB_CUDA(cudaMallocAsync((void **)&h->sort_ctr, 2 * words * 4, h->stream));
-    h->sort_ctr_words = 2 * words;
+    MXB_CUDA(cudaMallocAsync((void **)&h->sort_ctr, (2 * words + tot_words) * 4, h->stream));
+    h->sort_ctr_words = 2 * words + tot_words;
   }
   p.counts = h->sort_ctr;
   p.offsets = h->sort_ctr + words;
+  p.totals = h->sort_ctr + 2 * words;
   const unsigned grid = (unsigned)std::min<int64_t>(B * cpr, (int64_t)sm * 8);
   const void *src = in;
   for (int pass = 0; pass < passes; ++pass) {
@@ -2508,7 +2509,7 @@ int sort_rows_typed(mxb_context *h, const void *in, void *out, int kind, int64_t
     p.last = pass == passes - 1;
     if (!g_plan) {
       mxbsort::radix_count_kernel<K><<<grid, 256, 0, h->stream>>>(p);
-      mxbsort::radix_scan_kernel<<<(unsigned)std::min<int64_t>(B, (int64_t)sm * 8), 256, 0, h->stream>>>(p);
+      mxbsort::radix_scan_kernel<<<(unsigned)std::min<int64_t>(B * 32, (int64_t)sm * 8), 256, 0, h->stream>>>(p);   // a warp per (row, digit)
       mxbsort::radix_scatter_kernel<K><<<grid, 256, 0, h->stream>>>(p);
     }
     MXB_CUDA(cudaGetLastError());

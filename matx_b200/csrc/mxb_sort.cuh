@@ -10,10 +10,10 @@
 // negatives; signed integers: flip the sign bit; descending: complement), sorted, and mapped back on the last store.
 //   rows of <= 4096 keys   one CTA per row: bitonic network in shared memory (one read, one write);
 //   longer rows            least-significant-digit radix sort, 8 bits per pass.  Per pass: `count` (digit histogram of every
-//                          chunk of a row), `scan` (one CTA per row: exclusive offsets of (digit, chunk) in digit-major
-//                          order), `scatter` (a CTA walks its chunk in order, ranks 256 keys at a time — warp match + per-warp
-//                          digit counters — and writes every key to its digit's running offset: stable).  2 reads + 1 write
-//                          per pass and key; CUB's one-sweep does 1 + 1 — see DESIGN.md for the measured gap.
+//                          chunk of a row), `scan` (a warp per (row, digit): exclusive offsets over the chunks), `scatter`
+//                          (a CTA walks its chunk in rounds of 2048 keys, ranks them with warp matches + per-warp digit
+//                          counters and writes every key to its digit's running offset: stable).  2 reads + 1 write per
+//                          pass and key; CUB's one-sweep does 1 + 1 — see DESIGN.md for the measured gap.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -49,8 +49,9 @@ struct SortParams {
   int first, last;     // first pass maps raw bits to keys, the last pass maps them back
   int cpr;             // chunks per row
   i64 chunk;           // keys per chunk (multiple of 256)
-  u32 *counts;         // [B][cpr][256] keys per (chunk, digit)
-  u32 *offsets;        // [B][cpr][256] where the chunk's keys of a digit start in the row
+  u32 *counts;         // [B][256][cpr] keys per (digit, chunk)
+  u32 *offsets;        // [B][256][cpr] keys of the digit in earlier chunks of the row
+  u32 *totals;         // [B][256] keys of the digit in the row
 };
 
 // ---- short rows: bitonic network in shared memory -------------------------------------------------------------------------
@@ -82,6 +83,8 @@ __global__ void __launch_bounds__(256) bitonic_rows_kernel(const SortParams p, i
 }
 
 // ---- long rows: one radix pass = count, scan, scatter ---------------------------------------------------------------------
+// Counters are digit-major: counts[b][d][c] = keys of digit d in chunk c of row b, so the scan of one digit over the chunks
+// of a row is a walk over contiguous words.
 template <class K> __device__ __forceinline__ K load_key(const SortParams &p, const K *row, i64 i) {
   const K v = row[i];
   return p.first ? to_key<K>(v, p.kind, p.desc != 0) : v;
@@ -97,72 +100,121 @@ __global__ void __launch_bounds__(256) radix_count_kernel(const SortParams p) {
     s_cnt[threadIdx.x] = 0;
     __syncthreads();
     const i64 i0 = c * p.chunk, i1 = (i0 + p.chunk < p.L) ? i0 + p.chunk : p.L;
-    for (i64 i = i0 + threadIdx.x; i < i1; i += 256) {
-      const u32 d = (u32)(load_key<K>(p, row, i) >> p.shift) & 255u;
-      atomicAdd(&s_cnt[d], 1u);
+    for (i64 ii = i0; ii < i1; ii += 256) {   // warp-uniform trip count: the match below is a full-warp operation
+      const i64 i = ii + threadIdx.x;
+      const bool live = i < i1;
+      const u32 d = live ? ((u32)(load_key<K>(p, row, i) >> p.shift) & 255u) : 256u + (threadIdx.x & 31);
+      // lanes of a warp holding the same digit add once (sorted or skewed keys would serialise the shared-memory atomic)
+      const u32 peers = __match_any_sync(0xffffffffu, d);
+      if (live && (peers & ((1u << (threadIdx.x & 31)) - 1u)) == 0) atomicAdd(&s_cnt[d], (u32)__popc(peers));
     }
     __syncthreads();
-    p.counts[(b * p.cpr + c) * 256 + threadIdx.x] = s_cnt[threadIdx.x];
+    p.counts[(b * 256 + threadIdx.x) * p.cpr + c] = s_cnt[threadIdx.x];
     __syncthreads();
   }
 }
 
-// one CTA per row, thread d = digit d: offsets[c][d] = (keys of smaller digits in the row) + (keys of digit d in earlier chunks)
+// one WARP per (row, digit): exclusive scan of the digit's counts over the row's chunks (contiguous words), in place into
+// `offsets`, and the digit's total into totals[b][d] (the scatter kernel turns the totals into the digits' bases)
 __global__ void __launch_bounds__(256) radix_scan_kernel(const SortParams p) {
-  __shared__ u32 s_tot[256];
-  const int d = threadIdx.x;
-  for (i64 b = blockIdx.x; b < p.B; b += gridDim.x) {
-    const u32 *__restrict__ cnt = p.counts + b * p.cpr * 256;
-    u32 *__restrict__ off = p.offsets + b * p.cpr * 256;
-    u32 tot = 0;
-#pragma unroll 8
-    for (int c = 0; c < p.cpr; ++c) tot += cnt[c * 256 + d];
-    s_tot[d] = tot;
-    __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const i64 nw = (i64)gridDim.x * 8, w0 = (i64)blockIdx.x * 8 + (threadIdx.x >> 5);
+  for (i64 w = w0; w < p.B * 256; w += nw) {
+    const u32 *__restrict__ cnt = p.counts + w * p.cpr;
+    u32 *__restrict__ off = p.offsets + w * p.cpr;
     u32 run = 0;
-    for (int k = 0; k < d; ++k) run += s_tot[k];
-#pragma unroll 8
-    for (int c = 0; c < p.cpr; ++c) { off[c * 256 + d] = run; run += cnt[c * 256 + d]; }
-    __syncthreads();
+    for (int c0 = 0; c0 < p.cpr; c0 += 32) {
+      const int c = c0 + lane;
+      const u32 x = c < p.cpr ? cnt[c] : 0u;
+      u32 incl = x;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const u32 o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += o;
+      }
+      if (c < p.cpr) off[c] = run + incl - x;
+      run += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) p.totals[w] = run;
   }
 }
 
+// A CTA walks its chunk in rounds of 2048 keys: warp w owns the round's keys [w * 256, w * 256 + 256), lane l its keys
+// j * 32 + l (coalesced), so the order inside the round is (warp, j, lane) = the index order.  Ranks: per j the lanes of a
+// warp with the same digit are ranked by a warp match and added to the warp's running counter of that digit (no CTA
+// barrier inside the round); after one barrier the counters are scanned over the warps per digit, and every key goes to
+// base(digit) + keys of the digit in earlier rounds / warps + its rank: stable.
 template <class K>
 __global__ void __launch_bounds__(256) radix_scatter_kernel(const SortParams p) {
-  __shared__ u32 s_off[256];        // running output offset of every digit for this chunk
+  constexpr int KPT = 8;
+  __shared__ u32 s_off[256];        // where the next key of every digit goes (row-relative), for this chunk
   __shared__ u32 s_cnt[8][256];     // keys per (warp, digit) of the current round
+  __shared__ u32 s_base[8][256];    // output position of the first key of (warp, digit) in the current round
+  __shared__ u32 s_scan[8];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const u32 lt = (1u << lane) - 1u;
   const i64 work = p.B * p.cpr;
   for (i64 w = blockIdx.x; w < work; w += gridDim.x) {
     const i64 b = w / p.cpr, c = w - b * p.cpr;
     const K *row = (const K *)p.in + b * p.L;
     K *orow = (K *)p.out + b * p.L;
-    s_off[tid] = p.offsets[(b * p.cpr + c) * 256 + tid];
-    const i64 i0 = c * p.chunk, i1 = (i0 + p.chunk < p.L) ? i0 + p.chunk : p.L;
-    for (i64 r0 = i0; r0 < i1; r0 += 256) {
+    // base of digit `tid` in the row = total of the smaller digits (exclusive scan of the 256 totals over the CTA)
+    {
+      const u32 t = p.totals[b * 256 + tid];
+      u32 incl = t;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const u32 o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += o;
+      }
+      if (lane == 31) s_scan[warp] = incl;
+      __syncthreads();
+      u32 before = 0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) if (k < warp) before += s_scan[k];
+      s_off[tid] = before + incl - t + p.offsets[(b * 256 + tid) * p.cpr + c];
 #pragma unroll
       for (int k = 0; k < 8; ++k) s_cnt[k][tid] = 0;
-      __syncthreads();
-      const i64 i = r0 + tid;
-      const bool live = i < i1;
-      K key = 0;
-      u32 d = 256;   // dead lanes match nobody
-      if (live) { key = load_key<K>(p, row, i); d = (u32)(key >> p.shift) & 255u; }
-      // lanes of the warp holding the same digit: rank among them = lower lanes, the lowest of them records the count
-      const u32 peers = __match_any_sync(0xffffffffu, d);
-      const u32 rank = (u32)__popc(peers & ((1u << lane) - 1u));
-      if (live && rank == 0) s_cnt[warp][d] = (u32)__popc(peers);
-      __syncthreads();
-      if (live) {
-        u32 pos = s_off[d] + rank;
-        for (int k = 0; k < warp; ++k) pos += s_cnt[k][d];
-        orow[pos] = p.last ? from_key<K>(key, p.kind, p.desc != 0) : key;
+    }
+    __syncthreads();
+    const i64 i0 = c * p.chunk, i1 = (i0 + p.chunk < p.L) ? i0 + p.chunk : p.L;
+    for (i64 r0 = i0; r0 < i1; r0 += 256 * KPT) {
+      K key[KPT];
+      u32 dig[KPT], rank[KPT];
+      const i64 wbase = r0 + (i64)warp * 32 * KPT + lane;
+#pragma unroll
+      for (int j = 0; j < KPT; ++j) {
+        const i64 i = wbase + (i64)j * 32;
+        dig[j] = 256u + lane;   // dead lanes match nobody
+        if (i < i1) { key[j] = load_key<K>(p, row, i); dig[j] = (u32)(key[j] >> p.shift) & 255u; }
+      }
+#pragma unroll
+      for (int j = 0; j < KPT; ++j) {
+        const u32 peers = __match_any_sync(0xffffffffu, dig[j]);
+        const bool live = dig[j] < 256u;
+        u32 before = 0;
+        if (live) before = s_cnt[warp][dig[j]];
+        __syncwarp();
+        rank[j] = before + (u32)__popc(peers & lt);
+        if (live && (peers & lt) == 0) s_cnt[warp][dig[j]] = before + (u32)__popc(peers);
+        __syncwarp();
       }
       __syncthreads();
-      u32 add = 0;
+      {   // thread d: positions of the first key of (warp, d) in this round; the digit's offset moves past the round
+        u32 run = s_off[tid];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) add += s_cnt[k][tid];
-      s_off[tid] += add;
+        for (int k = 0; k < 8; ++k) { const u32 n = s_cnt[k][tid]; s_base[k][tid] = run; run += n; s_cnt[k][tid] = 0; }
+        s_off[tid] = run;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int j = 0; j < KPT; ++j) {
+        if (dig[j] < 256u) {
+          const u32 pos = s_base[warp][dig[j]] + rank[j];
+          orow[pos] = p.last ? from_key<K>(key[j], p.kind, p.desc != 0) : key[j];
+        }
+      }
+      // the next round's counters were cleared above; its first barrier orders the reads of s_base before they are rewritten
     }
     __syncthreads();
   }

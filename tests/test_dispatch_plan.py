@@ -76,7 +76,7 @@ def test_elementwise_scan_and_select_families(plans):
     assert plans["ew_tr.permute"].startswith("ew_tr|")
     assert plans["scan.rows"].startswith("scan|")
     k = plans["find.values"]
-    # 1-D view: the single-pass kernel over warp tiles, one resident wave (plan mode assumes 4 CTAs per SM), no shared memory
-    assert k.startswith("select|") and "|f32|V4|U4|T3|aot" in k and geom(k) == {"grid": 148 * 4, "block": 256, "smem": 0}, k
+    # 1-D view: the single-pass kernel over warp tiles, one resident wave (3 CTAs per SM), static shared memory only
+    assert k.startswith("select|") and "|f32|V4|U4|T3|aot" in k and geom(k) == {"grid": 148 * 3, "block": 256, "smem": 0}, k
     k = plans["find.strided_idx"]
     assert k.startswith("select|") and "|i32|V1|U4|T4|" in k, k    # every other column of a matrix collapses to ONE strided dim: scalar walk, single pass
