@@ -2480,10 +2480,11 @@ int sort_rows_typed(mxb_context *h, const void *in, void *out, int kind, int64_t
   }
   if (L >= (1ll << 32)) return fail(MXB_ERR_NOT_SUPPORTED, "rows of 2^32 or more keys");
   const int passes = (int)sizeof(K);
-  int64_t cpr = std::max<int64_t>(1, std::min<int64_t>((L + 8191) / 8192, 2048));
-  if (B * cpr > (1ll << 22)) cpr = std::max<int64_t>(1, (1ll << 22) / B);
-  const int64_t chunk = ((L + cpr - 1) / cpr + 255) / 256 * 256;
-  cpr = (L + chunk - 1) / chunk;
+  // chunks of whole 2048-key scatter rounds: about one chunk per resident CTA for long rows, never more than 4096 per row
+  int64_t want = std::max<int64_t>(2048, (B * L + (int64_t)sm * 8 - 1) / ((int64_t)sm * 8));
+  want = std::max<int64_t>(want, (L + 4095) / 4096);
+  const int64_t chunk = (want + 2047) / 2048 * 2048;
+  int64_t cpr = (L + chunk - 1) / chunk;
   p.cpr = (int)cpr;
   p.chunk = chunk;
   int st = ensure_buf(h, &h->tmp, &h->tmp_bytes, (size_t)(B * L) * sizeof(K));

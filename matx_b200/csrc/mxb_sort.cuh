@@ -100,13 +100,14 @@ __global__ void __launch_bounds__(256) radix_count_kernel(const SortParams p) {
     s_cnt[threadIdx.x] = 0;
     __syncthreads();
     const i64 i0 = c * p.chunk, i1 = (i0 + p.chunk < p.L) ? i0 + p.chunk : p.L;
-    for (i64 ii = i0; ii < i1; ii += 256) {   // warp-uniform trip count: the match below is a full-warp operation
-      const i64 i = ii + threadIdx.x;
-      const bool live = i < i1;
-      const u32 d = live ? ((u32)(load_key<K>(p, row, i) >> p.shift) & 255u) : 256u + (threadIdx.x & 31);
-      // lanes of a warp holding the same digit add once (sorted or skewed keys would serialise the shared-memory atomic)
-      const u32 peers = __match_any_sync(0xffffffffu, d);
-      if (live && (peers & ((1u << (threadIdx.x & 31)) - 1u)) == 0) atomicAdd(&s_cnt[d], (u32)__popc(peers));
+    // four loads in flight per thread; plain shared-memory atomics (a warp match costs one step per DISTINCT digit in the
+    // warp — 140 us instead of 48 per pass over 2^24 uniformly random keys)
+    for (i64 ii = i0 + threadIdx.x; ii < i1; ii += 1024) {
+      K k4[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) if (ii + j * 256 < i1) k4[j] = load_key<K>(p, row, ii + j * 256);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) if (ii + j * 256 < i1) atomicAdd(&s_cnt[(u32)(k4[j] >> p.shift) & 255u], 1u);
     }
     __syncthreads();
     p.counts[(b * 256 + threadIdx.x) * p.cpr + c] = s_cnt[threadIdx.x];
@@ -123,17 +124,22 @@ __global__ void __launch_bounds__(256) radix_scan_kernel(const SortParams p) {
     const u32 *__restrict__ cnt = p.counts + w * p.cpr;
     u32 *__restrict__ off = p.offsets + w * p.cpr;
     u32 run = 0;
-    for (int c0 = 0; c0 < p.cpr; c0 += 32) {
-      const int c = c0 + lane;
-      const u32 x = c < p.cpr ? cnt[c] : 0u;
-      u32 incl = x;
+    for (int c0 = 0; c0 < p.cpr; c0 += 128) {   // four loads in flight: the walk is one warp against L2 latency
+      u32 x[4];
 #pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const u32 o = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl += o;
+      for (int k = 0; k < 4; ++k) { const int c = c0 + k * 32 + lane; x[k] = c < p.cpr ? cnt[c] : 0u; }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int c = c0 + k * 32 + lane;
+        u32 incl = x[k];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const u32 o = __shfl_up_sync(0xffffffffu, incl, d);
+          if (lane >= d) incl += o;
+        }
+        if (c < p.cpr) off[c] = run + incl - x[k];
+        run += __shfl_sync(0xffffffffu, incl, 31);
       }
-      if (c < p.cpr) off[c] = run + incl - x;
-      run += __shfl_sync(0xffffffffu, incl, 31);
     }
     if (lane == 0) p.totals[w] = run;
   }
@@ -141,16 +147,19 @@ __global__ void __launch_bounds__(256) radix_scan_kernel(const SortParams p) {
 
 // A CTA walks its chunk in rounds of 2048 keys: warp w owns the round's keys [w * 256, w * 256 + 256), lane l its keys
 // j * 32 + l (coalesced), so the order inside the round is (warp, j, lane) = the index order.  Ranks: per j the lanes of a
-// warp with the same digit are ranked by a warp match and added to the warp's running counter of that digit (no CTA
-// barrier inside the round); after one barrier the counters are scanned over the warps per digit, and every key goes to
-// base(digit) + keys of the digit in earlier rounds / warps + its rank: stable.
+// warp with the same digit are ranked by votes and added to the warp's running counter of that digit (no CTA barrier
+// inside the round).  The round is then sorted by digit IN SHARED MEMORY (position = digits before + warps before + rank)
+// and written out from there, consecutive threads to consecutive addresses of a digit's run: scattering the keys straight
+// from the registers cost one 32-byte sector transaction per 4-byte key (146 us of a 175 us pass on random keys).  Stable.
 template <class K>
 __global__ void __launch_bounds__(256) radix_scatter_kernel(const SortParams p) {
-  constexpr int KPT = 8;
+  constexpr int KPT = 8, ROUND = 256 * KPT;
   __shared__ u32 s_off[256];        // where the next key of every digit goes (row-relative), for this chunk
   __shared__ u32 s_cnt[8][256];     // keys per (warp, digit) of the current round
-  __shared__ u32 s_base[8][256];    // output position of the first key of (warp, digit) in the current round
-  __shared__ u32 s_scan[8];
+  __shared__ u32 s_base[8][256];    // position inside the round's sorted order of the first key of (warp, digit)
+  __shared__ u32 s_delta[256];      // output position of a key of digit d = s_delta[d] + its position inside the round
+  __shared__ u32 s_scan[2][8];
+  __shared__ K s_keys[ROUND];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const u32 lt = (1u << lane) - 1u;
   const i64 work = p.B * p.cpr;
@@ -167,31 +176,40 @@ __global__ void __launch_bounds__(256) radix_scatter_kernel(const SortParams p) 
         const u32 o = __shfl_up_sync(0xffffffffu, incl, d);
         if (lane >= d) incl += o;
       }
-      if (lane == 31) s_scan[warp] = incl;
+      if (lane == 31) s_scan[0][warp] = incl;
       __syncthreads();
       u32 before = 0;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) if (k < warp) before += s_scan[k];
+      for (int k = 0; k < 8; ++k) if (k < warp) before += s_scan[0][k];
       s_off[tid] = before + incl - t + p.offsets[(b * 256 + tid) * p.cpr + c];
 #pragma unroll
       for (int k = 0; k < 8; ++k) s_cnt[k][tid] = 0;
     }
     __syncthreads();
     const i64 i0 = c * p.chunk, i1 = (i0 + p.chunk < p.L) ? i0 + p.chunk : p.L;
-    for (i64 r0 = i0; r0 < i1; r0 += 256 * KPT) {
+    int par = 1;
+    for (i64 r0 = i0; r0 < i1; r0 += ROUND, par ^= 1) {
+      const int nround = (int)((i1 - r0 < ROUND) ? (i1 - r0) : ROUND);
       K key[KPT];
       u32 dig[KPT], rank[KPT];
       const i64 wbase = r0 + (i64)warp * 32 * KPT + lane;
 #pragma unroll
       for (int j = 0; j < KPT; ++j) {
         const i64 i = wbase + (i64)j * 32;
-        dig[j] = 256u + lane;   // dead lanes match nobody
+        dig[j] = 256u;   // dead lanes: excluded from every vote below
         if (i < i1) { key[j] = load_key<K>(p, row, i); dig[j] = (u32)(key[j] >> p.shift) & 255u; }
       }
 #pragma unroll
       for (int j = 0; j < KPT; ++j) {
-        const u32 peers = __match_any_sync(0xffffffffu, dig[j]);
         const bool live = dig[j] < 256u;
+        // lanes holding the same digit, from one vote per digit bit (a fixed nine instructions; match.any takes one step
+        // per distinct value in the warp, 32 of them on random keys)
+        u32 peers = __ballot_sync(0xffffffffu, live);
+#pragma unroll
+        for (int bit = 0; bit < 8; ++bit) {
+          const u32 vote = __ballot_sync(0xffffffffu, (dig[j] >> bit) & 1u);
+          peers &= ((dig[j] >> bit) & 1u) ? vote : ~vote;
+        }
         u32 before = 0;
         if (live) before = s_cnt[warp][dig[j]];
         __syncwarp();
@@ -200,21 +218,42 @@ __global__ void __launch_bounds__(256) radix_scatter_kernel(const SortParams p) 
         __syncwarp();
       }
       __syncthreads();
-      {   // thread d: positions of the first key of (warp, d) in this round; the digit's offset moves past the round
-        u32 run = s_off[tid];
+      {   // thread d: the round's keys of digit d per warp -> where (warp, d) starts inside the round's sorted order
+        u32 n[8], tot = 0;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) { const u32 n = s_cnt[k][tid]; s_base[k][tid] = run; run += n; s_cnt[k][tid] = 0; }
-        s_off[tid] = run;
+        for (int k = 0; k < 8; ++k) { n[k] = s_cnt[k][tid]; tot += n[k]; s_cnt[k][tid] = 0; }
+        u32 incl = tot;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const u32 o = __shfl_up_sync(0xffffffffu, incl, d);
+          if (lane >= d) incl += o;
+        }
+        if (lane == 31) s_scan[par][warp] = incl;
+        __syncthreads();
+        u32 lstart = incl - tot;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) if (k < warp) lstart += s_scan[par][k];
+        u32 run = lstart;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { s_base[k][tid] = run; run += n[k]; }
+        s_delta[tid] = s_off[tid] - lstart;
+        s_off[tid] += tot;
       }
       __syncthreads();
 #pragma unroll
-      for (int j = 0; j < KPT; ++j) {
-        if (dig[j] < 256u) {
-          const u32 pos = s_base[warp][dig[j]] + rank[j];
-          orow[pos] = p.last ? from_key<K>(key[j], p.kind, p.desc != 0) : key[j];
+      for (int j = 0; j < KPT; ++j)
+        if (dig[j] < 256u) s_keys[s_base[warp][dig[j]] + rank[j]] = key[j];
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < KPT; ++k) {
+        const int i = k * 256 + tid;
+        if (i < nround) {
+          const K kk = s_keys[i];
+          const u32 pos = s_delta[(u32)(kk >> p.shift) & 255u] + (u32)i;
+          orow[pos] = p.last ? from_key<K>(kk, p.kind, p.desc != 0) : kk;
         }
       }
-      // the next round's counters were cleared above; its first barrier orders the reads of s_base before they are rewritten
+      // the next round touches s_keys / s_base / s_delta only behind its own barriers; s_scan alternates by round parity
     }
     __syncthreads();
   }
