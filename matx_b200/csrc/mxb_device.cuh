@@ -3887,6 +3887,9 @@ template <class T, int V> struct SelGeom {
          LANE_WORDS = FW + NWORD, SLOT_WORDS = LANE_WORDS * 32 + RSW + 1 };
 };
 
+// staging buffer of one vector row of a dense tile (32 lanes x V outputs per warp), when it fits 1 KB per warp
+template <class OutT, int V> struct SelStage { enum { ON = (32 * V * (int)sizeof(OutT) <= 1024) ? 1 : 0, BYTES = ON ? 32 * V * (int)sizeof(OutT) : 4 }; };
+
 // predicated store without a branch (the compiler turns `if (p) out[i] = v` into a divergence region per element)
 template <class OutT> __device__ __forceinline__ void st_if(bool p, OutT *addr, OutT v) { if (p) *addr = v; }
 template <> __device__ __forceinline__ void st_if<int>(bool p, int *addr, int v) {
@@ -3903,7 +3906,7 @@ template <> __device__ __forceinline__ void st_if<double>(bool p, double *addr, 
 }
 
 template <class E, class OutT, int V, int MODE, bool UNIT, int OP>   // MODE 1: values, 2: flat indices; OP < 0: runtime op / unique
-__device__ __forceinline__ void select1p_tiles(const EwParams &p, u32 *ring_all) {
+__device__ __forceinline__ void select1p_tiles(const EwParams &p, u32 *ring_all, void *stage_all) {
   typedef typename E::value_type T;
   typedef typename E::template Regs<V> R;
   typedef SelGeom<T, V> GEO;
@@ -3913,6 +3916,7 @@ __device__ __forceinline__ void select1p_tiles(const EwParams &p, u32 *ring_all)
   constexpr u32 VMASK = V >= 32 ? 0xffffffffu : ((1u << V) - 1u);
   constexpr int VSH = V == 1 ? 0 : V == 2 ? 1 : V == 4 ? 2 : V == 8 ? 3 : V == 16 ? 4 : 5;
   constexpr int RPW = 32 / V;                         // vector rows per flag word
+  constexpr bool STAGED = SelStage<OutT, V>::ON != 0; // dense tiles: rows compacted in shared memory before they are stored
   static_assert(U % 2 == 0 && UH >= 1 && (1 << VSH) == V && (U * V) % 32 == 0 || U * V < 32, "tile geometry");
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const i64 wpc = blockDim.x >> 5;
@@ -4040,14 +4044,40 @@ __device__ __forceinline__ void select1p_tiles(const EwParams &p, u32 *ring_all)
             const int u = q * UQ + uu;
             const u32 fu = (sp[((u * V) / 32) * 32 + lane] >> ((u * V) % 32)) & VMASK;
             const u32 exw = sp[(FW + u / CPW) * 32 + lane];
-            u32 pos = off + ((shared_words[u / 2] >> (16 * (u % 2))) & 0xffffu) + ((exw >> (CB * (u % CPW))) & CMASK);
+            const u32 rstart = (shared_words[u / 2] >> (16 * (u % 2))) & 0xffffu;
+            const u32 lrank = (exw >> (CB * (u % CPW))) & CMASK;     // selected elements of the row in lower lanes
             const i64 j0 = jd + (i64)u * 32 * V;
+            if (STAGED) {
+              // the row's selected elements meet in the warp's staging buffer, by rank, and leave as full coalesced stores:
+              // straight from the registers a store instruction touches every sector of the row's run for a quarter of it
+              OutT *stg = (OutT *)stage_all + (size_t)warp * 32 * V;
+              u32 lp = lrank;
 #pragma unroll
-            for (int v = 0; v < V; ++v) {
-              const bool on = (fu >> v) & 1u;
-              const OutT val = MODE == 1 ? cvt<OutT>(E::template eval<V>(r2[uu], v, p.c)) : (OutT)(j0 + v);
-              st_if<OutT>(on && pos < cap, out + pos, val);
-              pos += on ? 1u : 0u;
+              for (int v = 0; v < V; ++v) {
+                const bool on = (fu >> v) & 1u;
+                const OutT val = MODE == 1 ? cvt<OutT>(E::template eval<V>(r2[uu], v, p.c)) : (OutT)(j0 + v);
+                if (on) stg[lp] = val;
+                lp += on ? 1u : 0u;
+              }
+              __syncwarp();
+              const u32 rnext = u + 1 < U ? ((shared_words[(u + 1) / 2] >> (16 * ((u + 1) % 2))) & 0xffffu) : cnt;
+              const u32 rtot = rnext - rstart;
+#pragma unroll
+              for (int k = 0; k < V; ++k) {
+                const u32 i = (u32)(k * 32 + lane);
+                const u32 pos = off + rstart + i;
+                if (i < rtot && pos < cap) out[pos] = stg[i];
+              }
+              __syncwarp();
+            } else {
+              u32 pos = off + rstart + lrank;
+#pragma unroll
+              for (int v = 0; v < V; ++v) {
+                const bool on = (fu >> v) & 1u;
+                const OutT val = MODE == 1 ? cvt<OutT>(E::template eval<V>(r2[uu], v, p.c)) : (OutT)(j0 + v);
+                st_if<OutT>(on && pos < cap, out + pos, val);
+                pos += on ? 1u : 0u;
+              }
             }
           }
         }
@@ -4158,20 +4188,21 @@ __device__ __forceinline__ void select1p_body(const EwParams &p) {
   pdl_prologue();
   // per-warp ring of tile states (SelGeom::SLOT_WORDS per tile)
   __shared__ u32 ring[SEL_WARPS * SEL_RING * SelGeom<typename E::value_type, V>::SLOT_WORDS];
+  __shared__ __align__(16) unsigned char stage[SEL_WARPS * SelStage<OutT, V>::BYTES];
   const bool unit = p.all_unit != 0;
   if (V > 1 || unit) {
     // V > 1 is only ever launched over unit-stride leaves
     switch (p.sel_op) {
-      case 0: select1p_tiles<E, OutT, V, MODE, true, 0>(p, ring); break;
-      case 1: select1p_tiles<E, OutT, V, MODE, true, 1>(p, ring); break;
-      case 2: select1p_tiles<E, OutT, V, MODE, true, 2>(p, ring); break;
-      case 3: select1p_tiles<E, OutT, V, MODE, true, 3>(p, ring); break;
-      case 4: select1p_tiles<E, OutT, V, MODE, true, 4>(p, ring); break;
-      case 5: select1p_tiles<E, OutT, V, MODE, true, 5>(p, ring); break;
-      default: select1p_tiles<E, OutT, V, MODE, true, -1>(p, ring); break;
+      case 0: select1p_tiles<E, OutT, V, MODE, true, 0>(p, ring, stage); break;
+      case 1: select1p_tiles<E, OutT, V, MODE, true, 1>(p, ring, stage); break;
+      case 2: select1p_tiles<E, OutT, V, MODE, true, 2>(p, ring, stage); break;
+      case 3: select1p_tiles<E, OutT, V, MODE, true, 3>(p, ring, stage); break;
+      case 4: select1p_tiles<E, OutT, V, MODE, true, 4>(p, ring, stage); break;
+      case 5: select1p_tiles<E, OutT, V, MODE, true, 5>(p, ring, stage); break;
+      default: select1p_tiles<E, OutT, V, MODE, true, -1>(p, ring, stage); break;
     }
   } else {
-    select1p_tiles<E, OutT, V, MODE, false, -1>(p, ring);
+    select1p_tiles<E, OutT, V, MODE, false, -1>(p, ring, stage);
   }
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   // exit ticket: the last CTA out opens the next epoch (every status word of this launch is stale from then on)
