@@ -2075,6 +2075,7 @@ int mxb_cumsum(mxb_handle_t h, const mxb_expr_t *expr_in, const mxb_out_t *out) 
   // (8-byte values: two chunks, or the 16 running values per thread spill)
   spec.U = (L > (int64_t)256 * V) ? (dtype_bytes(vt) >= 8 ? 2 : 4) : 1;
   if (env_int("MXB_TUNE_U", 0) > 0) spec.U = env_int("MXB_TUNE_U", 0);
+  spec.minb = env_int("MXB_TUNE_MINB", 0);
   // short rows, many of them: a warp per row (no shared memory, no barrier)
   const bool warp_team = env_int("MXB_TUNE_TEAM", -1) >= 0 ? env_int("MXB_TUNE_TEAM", -1) == 1
                                                           : (L <= (int64_t)2048 && B >= 4 * (int64_t)h->sm_count);
@@ -2154,7 +2155,7 @@ int mxb_cumsum(mxb_handle_t h, const mxb_expr_t *expr_in, const mxb_out_t *out) 
     while (depth > 2 && (int64_t)depth * tile * dtype_bytes(vt) > 72 * 1024) --depth;
     p.scan_depth = std::min(depth, 8);
     scan_smem = scan_pipe ? (unsigned)((int64_t)p.scan_depth * tile * dtype_bytes(vt)) : 0u;
-    const int res = resident_ctas(k, 256, scan_smem, 3);
+    const int res = resident_ctas(k, 256, scan_smem, spec.minb > 0 ? spec.minb : 3);
     const int per_sm = env_int("MXB_SCAN_GRID_PER_SM", 0) > 0 ? std::min(env_int("MXB_SCAN_GRID_PER_SM", 0), res) : res;
     grid = (unsigned)std::min<int64_t>(B * tpr, (int64_t)sm * per_sm);
   } else {

@@ -573,7 +573,7 @@ int kernel_wrapper_src(const ExprInfo &info, const KernelSpec &s, const std::str
     case FAM_SCAN:
       if (!(info.value_dtype == MXB_F32 || info.value_dtype == MXB_F64 || cplx || info.value_dtype == MXB_I32 || info.value_dtype == MXB_I64))
         return fail("cumsum of this value type is not lowered");
-      k << "extern \"C\" __global__ void __launch_bounds__(256, 3) " << symbol
+      k << "extern \"C\" __global__ void __launch_bounds__(256, " << (s.minb > 0 ? s.minb : 3) << ") " << symbol
         << "(const __grid_constant__ mxb::RedParams p) { mxb::scan_inner_body<" << E << ", " << O << ", " << VU << ", " << s.team << ">(p); }\n";
       break;
     case FAM_EW_TR:
