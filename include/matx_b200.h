@@ -23,6 +23,7 @@
  *   mxb_hist         <- hist_impl + ExecHistEven              include/matx/transforms/cub.h:2464-2503,320-359
  *   mxb_sort         <- sort_impl + ExecSort                  include/matx/transforms/cub.h:2145-2190,428-560
  *   mxb_unique       <- unique_impl + ExecUnique              include/matx/transforms/cub.h:2796-2842,1052-1110
+ *   mxb_argminmax    <- argminmax_impl + ExecDualArgReduce    include/matx/transforms/reduce.h:1090-1109, cub.h:1439-1491
  *   mxb_create / mxb_destroy / mxb_set_stream
  *                    <- cudaExecutor ctor / getStream         include/matx/executors/cuda.h:60-82
  *   mxb_sync         <- CudaExecutorBase::sync                include/matx/executors/cuda_executor_common.h:137
@@ -208,7 +209,9 @@ int mxb_cumsum(mxb_handle_t h, const mxb_expr_t *expr, const mxb_out_t *out);
  * (:2656-2675,2752-2770) defines the order and the int count.  `out` is rank 1 and contiguous; values are converted to
  * its dtype, indices need MXB_I32 (the reference's static_cast<int>) or MXB_I64.  Elements beyond out->size[0] are counted
  * but not written (the reference would write past the end).  `count_out` is rank 0, MXB_I32.  Real value types only.
- * Two launches (count + in-launch scan of the tile counts, scatter), deterministic, nothing to clear between calls. */
+ * Views that collapse to one dim: ONE cooperative launch (every element read once; counts of 2048-element warp tiles
+ * exchanged through epoch-tagged device slots, nothing to clear between calls); N-D views that do not collapse: two launches
+ * (count + in-launch scan, scatter).  Deterministic and stable either way. */
 typedef enum {
   MXB_SEL_LT = 0, MXB_SEL_GT = 1, MXB_SEL_EQ = 2, MXB_SEL_NEQ = 3, MXB_SEL_LTE = 4, MXB_SEL_GTE = 5, MXB_SEL_COUNT
 } mxb_select_op_t;

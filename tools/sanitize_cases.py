@@ -75,4 +75,47 @@ for pe, plan in plans:
 for pe, plan in plans:
     A.check(A.lib.mxb_exchange_finalize(ex.handle, C.byref(pe.peers), plan["fold"], plan["n"], plan["count"]))
 ex.sync()
+# ---- round 2: argminmax, single-pass find / find_idx / unique (warp tiles, ring in shared memory), sort (bitonic rows and
+# the radix pass with its shared-memory staging), hist, cumsum in all three modes ----
+mn, mxv = torch.zeros(37, device="cuda"), torch.zeros(37, device="cuda")
+imn, imx = torch.zeros(37, dtype=torch.int64, device="cuda"), torch.zeros(37, dtype=torch.int64, device="cuda")
+mx.mtie(*(mx.make_tensor(t) for t in (mn, imn, mxv, imx))).set(mx.argminmax(x, [1])).run(ex)
+ex.sync()
+seen.add(ex.last_kernel().split("|")[0] + ":" + ex.last_kernel().split("|")[2])
+nf = torch.zeros((), dtype=torch.int32, device="cuda")
+for n_el, thr in ((300_001, 0.99), (300_001, 0.5), (300_001, 0.0), (5000, 0.9)):
+    fx = dev(rng.random(n_el, dtype=np.float32))
+    fo = torch.zeros(n_el, device="cuda")
+    fi = torch.zeros(n_el, dtype=torch.int64, device="cuda")
+    mx.mtie(mx.make_tensor(fo), mx.make_tensor(nf)).set(mx.find(mx.make_tensor(fx), mx.GT(thr))).run(ex)
+    mx.mtie(mx.make_tensor(fi), mx.make_tensor(nf)).set(mx.find_idx(mx.make_tensor(fx), mx.GT(thr))).run(ex)
+    ex.sync()
+    seen.add(ex.last_kernel().split("|")[0] + ":" + ex.last_kernel().split("|")[6])
+strided = mx.make_tensor(dev(rng.random((1000, 64), dtype=np.float32))[:, ::2])      # scalar walk of the single-pass kernel
+so = torch.zeros(32000, device="cuda")
+mx.mtie(mx.make_tensor(so), mx.make_tensor(nf)).set(mx.find(strided, mx.LT(0.3))).run(ex)
+keys = dev(rng.integers(-500, 500, 200_000).astype(np.float32))
+srt, uq = torch.zeros(200_000, device="cuda"), torch.zeros(200_000, device="cuda")
+mx.make_tensor(srt).set(mx.sort(mx.make_tensor(keys))).run(ex)
+ex.sync()
+seen.add(ex.last_kernel().split("|")[0])
+mx.mtie(mx.make_tensor(uq), mx.make_tensor(nf)).set(mx.unique(mx.make_tensor(keys))).run(ex)
+rows = dev(rng.random((64, 1000), dtype=np.float32))
+srows = torch.zeros((64, 1000), device="cuda")
+mx.make_tensor(srows).set(mx.sort(mx.make_tensor(rows), mx.SORT_DIR_DESC)).run(ex)
+ex.sync()
+seen.add(ex.last_kernel().split("|")[0])
+k64 = dev(rng.standard_normal(70_000))
+s64 = torch.zeros(70_000, dtype=torch.float64, device="cuda")
+mx.make_tensor(s64).set(mx.sort(mx.make_tensor(k64))).run(ex)
+hb = torch.zeros(16, dtype=torch.int32, device="cuda")
+mx.make_tensor(hb).set(mx.hist(mx.make_tensor(keys), -125.0, 125.0, 17)).run(ex)
+ex.sync()
+seen.add(ex.last_kernel().split("|")[0])
+for shape in ((3_000_001,), (300, 130), (24, 8192)):
+    cx = dev(rng.random(shape, dtype=np.float32))
+    co = torch.zeros(shape, device="cuda")
+    mx.make_tensor(co).set(mx.cumsum(mx.make_tensor(cx))).run(ex)
+    ex.sync()
+    seen.add(ex.last_kernel().split("|")[0] + ":" + ex.last_kernel().split("|")[6])
 print("kernel families exercised:", sorted(seen), "launches:", ex.launch_count())
