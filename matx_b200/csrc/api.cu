@@ -126,7 +126,7 @@ int ensure_lb(mxb_context *h, size_t slots) {
   }
   if (slots > h->lb_cap_tiles) {
     if (h->lb_status) MXB_CUDA(cudaFreeAsync(h->lb_status, h->stream));
-    const size_t nt = std::max<size_t>(slots + slots / 4, 16384);
+    const size_t nt = (std::max<size_t>(slots + slots / 4, 16384) + 15) & ~(size_t)15;   // even: the 16-byte slots behind the 8-byte ones stay aligned
     MXB_CUDA(cudaMallocAsync(&h->lb_status, nt * 24, h->stream));
     MXB_CUDA(cudaMemsetAsync(h->lb_status, 0, nt * 24, h->stream));
     h->lb_cap_tiles = nt;
@@ -2102,7 +2102,9 @@ int mxb_cumsum(mxb_handle_t h, const mxb_expr_t *expr_in, const mxb_out_t *out) 
   p.nleaf = nl;
   // TILES mode exchange: 2 = flat two-level gather by the whole CTA (the measured default), 3 = pipelined three-level jobs by one warp
   const bool scan_pipe = env_int("MXB_SCAN_PIPELINE", 0) != 0;
-  p.splits = tiles_mode ? (scan_pipe ? 3 : 2) : 1;
+  // 4 = warp tiles (4 KB per warp), phase 2 re-reads its tile through L2: no ring, no barrier
+  const bool scan_wt = tiles_mode && !scan_pipe && env_int("MXB_SCAN_WTILES", 1) != 0;   // 0: the flat CTA-tile exchange of round 1
+  p.splits = tiles_mode ? (scan_wt ? 4 : (scan_pipe ? 3 : 2)) : 1;
   for (int d = 0; d < gb.n; ++d) {
     p.bsz[d] = gb.size[d];
     p.out.bs[d] = gb.os[d];
@@ -2136,7 +2138,31 @@ int mxb_cumsum(mxb_handle_t h, const mxb_expr_t *expr_in, const mxb_out_t *out) 
   st = get_kernel(info, spec, &k);
   if (st != MXB_OK) return st;
   unsigned grid, scan_smem = 0;
-  if (tiles_mode) {
+  if (scan_wt) {
+    // warp tiles of 32 lanes x 32 elements (16 for 8-byte values); slots per row: tile totals | group totals | running
+    // totals at supergroup starts | supergroup totals
+    const int epl4 = env_int("MXB_SCAN_WT_EPL", 32) == 16 ? 16 : 32;
+    p.scan_plain = (e.n_nodes == 1 && nl == 1 && e.nodes[0].opcode == MXB_OP_LEAF && e.leaves[0].dtype == vt && unit && env_int("MXB_SCAN_WT_L2", 1)) ? 1 : 0;
+    p.scan_depth = epl4;
+    const int64_t wtile = 32 * std::max<int64_t>(V, dtype_bytes(vt) > 4 ? epl4 / 2 : epl4);
+    const int64_t wtpr = (L + wtile - 1) / wtile, gpr = (wtpr + 31) / 32, spr = (wtpr + 1023) / 1024;
+    const size_t need_t = (size_t)(B * wtpr), need_g = (size_t)(B * gpr), need_r = (size_t)(B * (spr + 1)), need_o = (size_t)(B * spr);
+    st = ensure_lb(h, need_t + need_g + need_r + need_o);
+    if (st != MXB_OK) return st;
+    const int sb = dtype_bytes(vt) >= 8 ? 16 : 8;
+    char *w = (char *)lb_region(h, sb);
+    p.scan_agg = w;
+    p.scan_gagg = w + need_t * sb;
+    p.scan_sagg = w + (need_t + need_g) * sb;
+    p.scan_own = w + (need_t + need_g + need_r) * sb;
+    p.scan_ctl = h->lb_ctl;
+    // the grid is one resident wave (cooperative launch): 3 CTAs per SM x 8 warps x 4 KB x 3 iterations = 43 MB of input lie
+    // between a tile's two reads, which L2 holds for the most part when the first read asks for it (evict_last) and the
+    // second read and the stores give way (evict_first): 1.45 GB instead of 2.1 GB read from DRAM for a 1 GiB row
+    const int res = resident_ctas(k, 256, 0, 3);
+    const int per_sm = std::min(env_int("MXB_SCAN_WT_CTAS", 3), res);
+    grid = (unsigned)std::min<int64_t>((B * wtpr + 7) / 8, (int64_t)sm * per_sm);
+  } else if (tiles_mode) {
     // slots: tile totals, group totals (32 tiles), running totals at supergroup starts (1024 tiles), per row
     const int64_t gpr = (tpr + 31) / 32, spr = (tpr + 1023) / 1024;
     const size_t need_t = (size_t)(B * tpr), need_g = (size_t)(B * gpr), need_s = (size_t)(B * spr);

@@ -118,7 +118,8 @@ struct RedParams {
   // scan family only: the handle's scan workspace (tile / group totals, epoch-coded flags)
   // TILES mode: published totals {tag : value} of tiles / groups of 32 tiles / supergroup starts (8-byte slots for 4-byte
   // values, 16-byte slots for 8-byte values), the device-resident launch epoch and the exit ticket
-  void *scan_agg, *scan_gagg, *scan_sagg;
+  void *scan_agg, *scan_gagg, *scan_sagg, *scan_own;
+  int scan_plain;  // the operand is ONE contiguous tensor of the value type: the warp-tile scan may read it with L2 policies
   u32 *scan_ctl;
   // hist family: HistogramEven bounds and bin count (reference: cub::DeviceHistogram::HistogramEven behind hist_impl)
   double hist_lo_d, hist_hi_d;
@@ -3567,12 +3568,248 @@ __device__ __forceinline__ void scan_tiles_body_impl(const RedParams &p) {
   }
 }
 
+// mode TILES on WARP tiles (p.splits == 4, the default): the single-pass design of select1p applied to the prefix sum of
+// few long rows.  A warp owns tiles of 32 lanes x EPL elements (4 KB).  Phase 1 of a tile reads it and publishes its total;
+// the exchange runs as jobs 1 and 2 iterations later (group totals; supergroup totals + running totals — fixed-shape sums,
+// so the result does not depend on timing); phase 2, three iterations later, reads the tile AGAIN — L2 is asked to keep
+// it in between — scans it in registers, adds the carry and stores.  Nothing is kept on chip between the phases, so there
+// is no ring, no shared memory and no barrier.
+template <class T> struct ScanXchg {
+  typedef ScanSlot<T> SL;
+  char *agg, *gagg, *run, *own;      // slots of row 0; row r sits tpr / gpr / spr + 1 / spr slots further
+  i64 tpr, gpr, spr;
+  u32 tag;
+  int lane;
+  __device__ __forceinline__ char *A(i64 row) const { return agg + (size_t)(row * tpr) * SL::STRIDE; }
+  __device__ __forceinline__ char *G(i64 row) const { return gagg + (size_t)(row * gpr) * SL::STRIDE; }
+  __device__ __forceinline__ char *R(i64 row) const { return run + (size_t)(row * (spr + 1)) * SL::STRIDE; }
+  __device__ __forceinline__ char *O(i64 row) const { return own + (size_t)(row * spr) * SL::STRIDE; }
+  __device__ __forceinline__ T get(const char *slots, i64 i, bool on) const { return on ? SL::wait(slots, i, tag) : scan_zero<T>(); }
+  __device__ __forceinline__ bool closes_group(i64 ct) const { return ct >= 0 && ((ct & 31) == 31 || ct == tpr - 1); }
+  __device__ __forceinline__ bool closes_super(i64 ct) const { return ct >= 0 && ct < tpr - 1 && (ct & 1023) == 1023; }
+  __device__ __forceinline__ void close(i64 row, i64 ct, T total) const {
+    const i64 first = (ct >> 5) << 5;
+    const T s = warp_tree_sum(get(A(row), first + lane, first + lane < ct));
+    if (lane == 0) SL::publish(G(row), ct >> 5, s + total, tag);
+  }
+  __device__ __forceinline__ void super(i64 row, i64 ct) const {
+    const i64 sg = ct >> 10;
+    const T s = warp_tree_sum(get(G(row), (sg << 5) + lane, true));
+    if (lane == 0) SL::publish(O(row), sg, s, tag);
+  }
+  __device__ __forceinline__ void running(i64 row, i64 ct) const {
+    const i64 sg = ct >> 10;
+    T acc = scan_zero<T>();
+    for (i64 i0 = 0; i0 <= sg; i0 += 32) acc = acc + warp_tree_sum(get(O(row), i0 + lane, i0 + lane <= sg));   // fixed order
+    if (lane == 0) SL::publish(R(row), sg + 1, acc, tag);
+  }
+  __device__ __forceinline__ T carry(i64 row, i64 ct) const {
+    const i64 g = ct >> 5, first = g << 5, sg = ct >> 10, gfirst = sg << 5;
+    const T a = get(A(row), first + lane, first + lane < ct);
+    const T b = get(G(row), gfirst + lane, gfirst + lane < g);
+    T c = get(R(row), sg, lane == 0 && sg > 0);
+    const T sa = warp_tree_sum(a), sb = warp_tree_sum(b);
+    c = shfl_idx_t(c, 0);
+    return (c + sb) + sa;
+  }
+};
+
+// 16-byte store that leaves L2 first: the scan's output must not push the tiles waiting for their second read out of L2
+__device__ __forceinline__ void st16_evict_first(void *d, const void *s) {
+  const u32 *x = (const u32 *)s;
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.b32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(d), "r"(x[0]), "r"(x[1]), "r"(x[2]), "r"(x[3]), "l"(pol) : "memory");
+}
+
+__device__ __forceinline__ unsigned long long l2_policy_evict_last() {
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ unsigned long long l2_policy_evict_first() {
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void ld16_hint(void *dst, const void *src, unsigned long long pol) {
+  u32 *x = (u32 *)dst;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.b32 {%0,%1,%2,%3}, [%4], %5;" : "=r"(x[0]), "=r"(x[1]), "=r"(x[2]), "=r"(x[3]) : "l"(src), "l"(pol));
+}
+
+template <class E, class OutT, int V, bool UNIT, int EPL4>
+__device__ __forceinline__ void scan_wtiles_body_impl(const RedParams &p) {
+  typedef typename E::value_type T;
+  typedef typename E::template Regs<V> R;
+  constexpr int EPL = (sizeof(T) > 4 ? EPL4 / 2 : EPL4) < V ? V : (sizeof(T) > 4 ? EPL4 / 2 : EPL4);      // elements per lane and tile
+  constexpr int U = EPL / V;                        // vectors per lane and tile
+  constexpr i64 TILE = (i64)32 * EPL;
+  static_assert(EPL % V == 0 && U >= 1, "vector width must divide the elements per lane");
+  const int lane = threadIdx.x & 31;
+  const i64 wpc = blockDim.x >> 5;
+  const i64 nwarp = (i64)gridDim.x * wpc, gw = (i64)blockIdx.x * wpc + (threadIdx.x >> 5);
+  const i64 L = p.rsz[0];
+  const i64 tpr = (L + TILE - 1) / TILE;
+  const i64 total_tiles = p.B * tpr;
+  const i64 oinner = p.out_rs[0];
+  ScanXchg<T> xc;
+  xc.agg = (char *)p.scan_agg; xc.gagg = (char *)p.scan_gagg; xc.run = (char *)p.scan_sagg; xc.own = (char *)p.scan_own;
+  xc.tpr = tpr; xc.gpr = (tpr + 31) >> 5; xc.spr = (tpr + 1023) >> 10;
+  xc.tag = ((__ldcg(p.scan_ctl) & 0x3fffffffu) << 2) | 1u;
+  xc.lane = lane;
+  i64 inner[E::NL];
+#pragma unroll
+  for (int k = 0; k < E::NL; ++k) inner[k] = p.leaf[k].rs[0];
+  auto row_bases = [&](i64 b, const char **base) -> OutT * {
+    i64 bidx[KMAXD];
+    decomp(b, p.nb, p.bsz, bidx);
+    i64 oo = 0;
+#pragma unroll
+    for (int k = 0; k < E::NL; ++k) {
+      i64 off = 0;
+#pragma unroll
+      for (int d = 0; d < KMAXD; ++d) if (d < p.nb) off += bidx[d] * p.leaf[k].bs[d];
+      base[k] = (const char *)p.leaf[k].ptr + off * E::leaf_bytes(k);
+    }
+#pragma unroll
+    for (int d = 0; d < KMAXD; ++d) if (d < p.nb) oo += bidx[d] * p.out.bs[d];
+    return (OutT *)p.out.ptr + oo;
+  };
+  // element values of this lane's part of tile (row base, ct): zero beyond the row's end
+  // a plain contiguous operand is read with an L2 policy: the first read asks L2 to keep the tile (evict_last), the second
+  // one — its last use — releases it (evict_first); so do the output stores
+  const bool plain = p.scan_plain != 0 && (int)sizeof(T) * V == 16 && UNIT;
+  const unsigned long long pol_keep = l2_policy_evict_last(), pol_drop = l2_policy_evict_first();
+  auto load_tile = [&](const char *const *base, i64 ct, T (&x)[U][V], unsigned long long pol) {
+    const i64 j0 = ct * TILE + (i64)lane * V;
+    if (plain && (ct + 1) * TILE <= L) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) ld16_hint(&x[u][0], base[0] + (j0 + (i64)u * 32 * V) * (i64)sizeof(T), pol);
+    } else if ((ct + 1) * TILE <= L) {
+      R r[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) E::template loadv<V, UNIT>(r[u], base, inner, j0 + (i64)u * 32 * V);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+#pragma unroll
+        for (int v = 0; v < V; ++v) x[u][v] = E::template eval<V>(r[u], v, p.c);
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          const i64 j = j0 + (i64)u * 32 * V + v;
+          x[u][v] = scan_zero<T>();
+          if (j < L) {
+            typename E::template Regs<1> r1;
+            E::template loadv<1, false>(r1, base, inner, j);
+            x[u][v] = E::template eval<1>(r1, 0, p.c);
+          }
+        }
+      }
+    }
+  };
+  // (row, tile in the row) of the tiles of the last five iterations, stepped by nwarp tiles without a division in the loop
+  const i64 gq = nwarp / tpr, gr = nwarp - gq * tpr;
+  // DIST iterations lie between a tile's two reads.  4 (one iteration per level of the exchange) never waits but leaves
+  // 58 MB between the reads: 0.53 ms for 2^28 fp32; 3 (supergroup total and running total in one iteration) 0.48 ms with
+  // 65 % of the second reads served by L2; 2 (all jobs in one iteration) makes the warps wait on each other: 0.63 ms
+  constexpr int DIST = 3;
+  i64 rb[DIST + 1], rt[DIST + 1];   // [0] this iteration ... [DIST] DIST iterations ago
+#pragma unroll
+  for (int k = 0; k <= DIST; ++k) { rb[k] = 0; rt[k] = -1; }
+  i64 nb = gw / tpr, nt = gw - nb * tpr;   // coordinates of `tile` before the loop's first step
+  T prev_total = scan_zero<T>();
+  for (i64 tile = gw; tile - DIST * nwarp < total_tiles; tile += nwarp) {
+#pragma unroll
+    for (int k = DIST; k > 0; --k) { rb[k] = rb[k - 1]; rt[k] = rt[k - 1]; }
+    const bool p1 = tile < total_tiles;
+    rb[0] = nb; rt[0] = p1 ? nt : -1;
+    nt += gr; nb += gq;
+    if (nt >= tpr) { nt -= tpr; ++nb; }
+    // ---- phase 1: read the tile, its total ----
+    T total = scan_zero<T>();
+    if (p1) {
+      const char *base[E::NL];
+      row_bases(rb[0], base);
+      T x[U][V];
+      load_tile(base, rt[0], x, pol_keep);
+      T s = scan_zero<T>();
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+#pragma unroll
+        for (int v = 0; v < V; ++v) s = s + x[u][v];
+      }
+      total = warp_tree_sum(s);
+      if (lane == 0) ScanSlot<T>::publish(xc.A(rb[0]), rt[0], total, xc.tag);
+    }
+    // ---- exchange jobs of the tiles read 1, 2 and 3 iterations ago ----
+    if (xc.closes_group(rt[1])) xc.close(rb[1], rt[1], prev_total);
+    if (xc.closes_super(rt[2])) { xc.super(rb[2], rt[2]); xc.running(rb[2], rt[2]); }
+    prev_total = total;
+    // ---- phase 2 of the tile read DIST iterations ago: carry, second read (L2), scan in registers, store ----
+    if (rt[DIST] >= 0) {
+      const char *base[E::NL];
+      OutT *orow = row_bases(rb[DIST], base);
+      const i64 ct = rt[DIST];
+      T x[U][V];
+      load_tile(base, ct, x, pol_drop);
+      const T carry = xc.carry(rb[DIST], ct);
+      T rowbase = carry;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+#pragma unroll
+        for (int v = 1; v < V; ++v) x[u][v] = x[u][v - 1] + x[u][v];
+        T incl = x[u][V - 1];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const T o = shfl_up_t(incl, d);
+          if (lane >= d) incl = o + incl;
+        }
+        const T exl = shfl_up_t(incl, 1);
+        const T pre = lane == 0 ? rowbase : rowbase + exl;
+        const i64 j = ct * TILE + ((i64)u * 32 + lane) * V;
+        Vec<OutT, V> o;
+#pragma unroll
+        for (int v = 0; v < V; ++v) o.v[v] = cvt<OutT>(pre + x[u][v]);
+        if (V > 1 && j + V <= L && oinner == 1 && p.tx) {
+          if (sizeof(OutT) * V == 16) st16_evict_first(orow + j, &o);
+          else StBytes<(int)sizeof(OutT) * V>::st(orow + j, &o);
+        } else {
+#pragma unroll
+          for (int v = 0; v < V; ++v) if (j + v < L) orow[(j + v) * oinner] = o.v[v];
+        }
+        rowbase = rowbase + shfl_idx_t(incl, 31);
+      }
+    }
+  }
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  // exit ticket: the last CTA out opens the next epoch (every slot of this launch is stale from then on)
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicInc(p.scan_ctl + 1, gridDim.x - 1) == gridDim.x - 1) {
+      u32 e = (__ldcg(p.scan_ctl) + 1u) & 0x3fffffffu;
+      *(volatile u32 *)p.scan_ctl = e ? e : 1u;
+    }
+  }
+}
+
 template <class E, class OutT, int V, int U, int TEAM>
 __device__ __forceinline__ void scan_inner_body(const RedParams &p) {
   pdl_prologue();
   if (TEAM == 1) {
     if (p.all_unit) scan_warp_body_impl<E, OutT, V, U, true>(p);
     else scan_warp_body_impl<E, OutT, V, U, false>(p);
+  } else if (p.splits == 4) {
+    if (p.scan_depth == 16) {
+      if (p.all_unit) scan_wtiles_body_impl<E, OutT, V, true, 16>(p);
+      else scan_wtiles_body_impl<E, OutT, V, false, 16>(p);
+    } else {
+      if (p.all_unit) scan_wtiles_body_impl<E, OutT, V, true, 32>(p);
+      else scan_wtiles_body_impl<E, OutT, V, false, 32>(p);
+    }
   } else if (p.splits == 2) {
     if (p.all_unit) scan_tiles_flat_body_impl<E, OutT, V, U, true>(p);
     else scan_tiles_flat_body_impl<E, OutT, V, U, false>(p);

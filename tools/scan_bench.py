@@ -11,7 +11,7 @@ from matx_b200 import ops as mx  # noqa: E402
 
 PEAK = 6456.8
 envs = [{}] + [json.loads(a) for a in sys.argv[1:]]
-for shape in ((1 << 28,), (4, 1 << 26)):
+for shape in ((1 << 28,), (4, 1 << 26), (3, 5000001)):
     x = torch.rand(shape, device="cuda")
     out = torch.empty_like(x)
     want = torch.cumsum(x.double(), -1)
