@@ -209,3 +209,59 @@ def test_one_executor_shared_by_two_host_threads():
         truth = xs[i].double().sum().item()
         assert abs(res[i][0] - truth) <= 1e-5 * truth
         assert res[i][1] == xs[i].max().item() and res[i][2] == int(torch.argmax(xs[i]).item())
+
+
+# ---- warp tiles (round 2, the default for few long rows): tile = 1024 elements (512 for 8-byte values), a group is 32
+# tiles, a supergroup 1024 tiles; sizes on and around every edge, several rows with ragged ends, all exchange paths ----
+@pytest.mark.parametrize("shape", [(32767,), (32768,), (32769,), ((1 << 20) - 1,), (1 << 20,), ((1 << 20) + 1,), (3 * (1 << 20) + 1025,),
+                                   (3, (1 << 20) + 77), (5, 40001), (2, 2 * (1 << 20))])
+def test_warp_tile_scan_edges_int32_exact(oracle, shape):
+    rng = np.random.default_rng(sum(shape))
+    x = rng.integers(-1000, 1000, shape).astype(np.int32)
+    for env in ({}, {"MXB_SCAN_WTILES": 0}):         # warp tiles, and the flat CTA-tile exchange kept beside them
+        got, want, k = run_cumsum(oracle, lambda t: t, [x], shape, A.I32, env=env)
+        assert k.startswith("scan|"), k
+        assert np.array_equal(got, np.cumsum(x.astype(np.int64), axis=-1).astype(np.int32)), (shape, env)
+
+
+@pytest.mark.parametrize("dt,npdt,tol", [(A.F32, np.float32, 1e-5), (A.F64, np.float64, 1e-12), (A.I64, np.int64, 0)])
+def test_warp_tile_scan_value_widths_and_operand_kinds(oracle, dt, npdt, tol):
+    """8-byte values take 512-element tiles; an unaligned row start takes the scalar loads; an expression operand the
+    generic loads (no L2 hints); a plain contiguous tensor the hinted 16-byte loads."""
+    rng = np.random.default_rng(dt)
+    n = (1 << 20) + 513
+    x = (rng.random(n + 1) * 4).astype(npdt) if tol else rng.integers(-9, 9, n + 1).astype(npdt)
+    for view_of, arr, ref in ((lambda t: t, x[:n].copy(), x[:n]), (lambda t: t.Slice([1], [n + 1]), x, x[1:]), (lambda t: t + t, x[:n].copy(), x[:n] + x[:n])):
+        got, want, k = run_cumsum(oracle, view_of, [arr], (n,), dt)
+        truth = np.cumsum(ref.astype(np.float64 if tol else np.int64))
+        if tol:
+            assert np.max(np.abs(got.astype(np.float64) - truth) / np.maximum(np.abs(truth), 1.0)) <= tol, (dt, k)
+        else:
+            assert np.array_equal(got, truth.astype(npdt)), (dt, k)
+
+
+def test_warp_tile_scan_is_deterministic_and_graph_replayable():
+    import torch
+    x = torch.rand((1 << 22) + 5, device="cuda")
+    outs = []
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        ex = mx.CudaExecutor(s)
+        o = torch.zeros_like(x)
+        fn = lambda: mx.make_tensor(o).set(mx.cumsum(mx.make_tensor(x))).run(ex)  # noqa: E731
+        for _ in range(3):
+            fn()
+            ex.sync()
+            outs.append(o.clone())
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=s):
+            fn()
+        for _ in range(3):
+            o.zero_()
+            g.replay()
+            s.synchronize()
+            outs.append(o.clone())
+    for t in outs[1:]:
+        assert torch.equal(t, outs[0])
+    truth = torch.cumsum(x.double(), 0)
+    assert float(((outs[0].double() - truth).abs() / truth).max()) <= 1e-5
