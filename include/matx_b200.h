@@ -197,9 +197,9 @@ int mxb_softmax(mxb_handle_t h, const mxb_expr_t *expr, int n_reduce_dims, const
 /* out(b..., j) = sum_{i <= j} expr(b..., i): inclusive prefix sum along the LAST dim of `expr` (reference: cumsum_impl,
  * transforms/cub.h:2367-2395 -> matxCubPlan_t::ExecPrefixScanEx :375-408, cub::DeviceScan::InclusiveSum launched once
  * per row).  `out` has the rank and sizes of `expr`; accumulation in the expression's arithmetic type (fp32 for 16-bit
- * floats).  One launch, one read and one write of every element, fixed summation order (run-to-run deterministic):
- * many rows -> a CTA per row with a running carry; few long rows -> a CTA per tile, tile and group totals exchanged
- * through L2 inside the launch. */
+ * floats).  One launch, fixed summation order (run-to-run deterministic): many rows -> a CTA per row with a running
+ * carry (one read, one write); few long rows -> 4 KB warp tiles whose totals are exchanged through L2 inside the launch;
+ * a tile is read twice, the second time out of L2 for the most part (one write). */
 int mxb_cumsum(mxb_handle_t h, const mxb_expr_t *expr, const mxb_out_t *out);
 
 /* Stream compaction: out[0 .. n) = the elements x of `expr` (row-major flat order, stable) with `x <select_op> threshold`
